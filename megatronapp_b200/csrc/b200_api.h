@@ -1,0 +1,166 @@
+// Host-callable launchers for every sm_100a kernel in the framework.
+// Plain C++ (no torch headers) so kernel TUs compile fast; bindings.cpp adapts tensors.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace b200 {
+
+constexpr int kMaxPeers = 8;
+
+enum GemmEpilogue : int {
+  kEpiStore16 = 0,    // D (bf16/fp16) = act(acc + bias)           (TMA store)
+  kEpiAccumF32 = 1,   // D32 += acc                                (wgrad into fp32 main_grad)
+  kEpiStoreF32 = 2,   // D32  = acc
+  kEpiReduceScatter = 3,  // GEMM -> reduce-scatter over peer memory (row-parallel linear)
+};
+
+enum GemmComm : int {
+  kCommNone = 0,
+  kCommAllGather = 1,      // all-gather(A rows) fused in front of the GEMM (column-parallel linear)
+  kCommReduceScatter = 2,  // reduce-scatter(D rows) fused behind the GEMM
+};
+
+struct GemmArgs {
+  // D[M,N] = A[M,K] * B[N,K]^T  (logical).  *_mn_major: operand stored transposed
+  // (A stored [K,M] / B stored [K,N], leading dimension = lda/ldb elements).
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* D = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0, ldd = 0;
+  bool a_mn_major = false;
+  bool b_mn_major = false;
+  bool is_bf16 = true;
+  int epilogue = kEpiStore16;
+  const void* bias = nullptr;  // optional [N], same 16-bit dtype as D
+  int act = 0;                 // 0 none, 1 tanh-GELU
+  void* D_pre = nullptr;       // optional pre-activation output (same shape/ld as D)
+  int block_n = 0;             // 0 = auto (128 or 256)
+  int num_sms = 0;             // 0 = all
+  // ---- fused collective (kCommAllGather / kCommReduceScatter) ----------------
+  int comm = kCommNone;
+  int tp_rank = 0, tp_size = 1;
+  int n_comm_ctas = 0;
+  uint32_t epoch = 0;                 // monotonically increasing per arena slot
+  // all-gather: A is this rank's gather buffer [M,K] in the symmetric arena,
+  // A_local is the local shard [M/tp,K]; peers' gather buffers / flag arrays below.
+  const void* A_local = nullptr;
+  int lda_local = 0;
+  void* peer_buf[kMaxPeers] = {nullptr};       // AG: peers' gather buffers; RS: peers' staging buffers
+  uint32_t* peer_flags[kMaxPeers] = {nullptr};  // per-peer flag arrays (index tp_rank = local)
+  // reduce-scatter: D is the local output shard [M/tp, N]; staging in peer_buf[tp_rank]
+  cudaStream_t stream = nullptr;
+};
+
+// returns 0 on success, otherwise a negative error code (bad shape / alignment)
+int gemm_bf16(const GemmArgs& args);
+const char* gemm_last_error();
+int gemm_flags_needed(int M, int N, int tp_size);
+
+// ---------------------------------------------------------------- elementwise / norm
+void layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
+                   float* rstd, int rows, int cols, float eps, bool rms, bool zero_centered,
+                   bool is_bf16, cudaStream_t s);
+void layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+                   const float* rstd, void* dx, float* dgamma_partial, float* dbeta_partial,
+                   int rows, int cols, bool rms, bool zero_centered, bool is_bf16, int n_partial,
+                   cudaStream_t s);
+void layernorm_bwd_finalize(const float* dgamma_partial, const float* dbeta_partial,
+                            float* dgamma, float* dbeta, int n_partial, int cols, bool accumulate,
+                            cudaStream_t s);
+int layernorm_bwd_partials(int rows);
+
+void bias_gelu_fwd(const void* x, const void* bias, void* y, int64_t rows, int cols, bool is_bf16,
+                   cudaStream_t s);
+void bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, int64_t rows,
+                   int cols, bool is_bf16, cudaStream_t s);
+void swiglu_fwd(const void* x, const void* bias, void* y, int64_t rows, int cols_out, bool is_bf16,
+                cudaStream_t s);
+void swiglu_bwd(const void* dy, const void* x, const void* bias, void* dx, int64_t rows,
+                int cols_out, bool is_bf16, cudaStream_t s);
+void bias_dropout_add(const void* x, const void* bias, const void* residual, void* out,
+                      uint8_t* mask_out, int64_t rows, int cols, float p, uint64_t seed,
+                      uint64_t offset, bool is_bf16, cudaStream_t s);
+void dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, bool is_bf16,
+                 cudaStream_t s);
+void rope_apply(const void* x, const float* cos_sin, void* y, int s, int b, int h, int d,
+                int rot_dim, bool interleaved, bool inverse, bool is_bf16, cudaStream_t st);
+void bias_grad_reduce(const void* dy, float* dbias, int64_t rows, int cols, bool is_bf16,
+                      bool accumulate, cudaStream_t s);
+
+// vocab-parallel cross entropy pieces (fp32 statistics; logits 16-bit or fp32)
+void ce_local_stats(const void* logits, const int64_t* labels, float* row_max, float* row_sumexp,
+                    float* tgt_logit, int64_t rows, int vocab_local, int vocab_start, int ldl,
+                    int logits_dtype, cudaStream_t s);
+void ce_rescale_sumexp(float* row_sumexp, const float* local_max, const float* global_max,
+                       int64_t rows, cudaStream_t s);
+void ce_grad(const void* logits, const int64_t* labels, const float* global_max,
+             const float* global_sumexp, const float* grad_loss, void* dlogits, int64_t rows,
+             int vocab_local, int vocab_start, int ldl, int logits_dtype, float label_smoothing,
+             int64_t vocab_total, cudaStream_t s);
+
+// optimizer / multi-tensor
+struct AdamArgs {
+  float* master;       // fp32 master params (flat)
+  float* exp_avg;
+  float* exp_avg_sq;
+  const float* grad;   // fp32 grads (flat), already scaled by grad_scale inside the kernel
+  void* param16;       // optional 16-bit model params (flat), may be nullptr
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+  float bias_correction1, bias_correction2;
+  bool is_bf16;
+  const float* found_inf;  // optional device flag: skip update when != 0
+};
+void adam_step(const AdamArgs& a, cudaStream_t s);
+void l2norm_sq(const void* x, int64_t n, int dtype, float* out_accum, cudaStream_t s);
+void scale_inplace(void* x, int64_t n, int dtype, float scale, const float* scale_dev,
+                   cudaStream_t s);
+void cast_copy(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, float scale,
+               cudaStream_t s);
+void add_into_f32(float* dst, const void* src, int src_dtype, int64_t n, cudaStream_t s);
+void check_finite(const void* x, int64_t n, int dtype, float* found_inf, cudaStream_t s);
+void chunk_mean(const void* x, float* out, int64_t rows, int cols, int pixels, bool is_bf16,
+                cudaStream_t s);
+
+// flash attention (tcgen05), layout [b, h, s, d] contiguous, d in {64, 128}
+struct AttnArgs {
+  const void* q; const void* k; const void* v; void* o; float* lse;
+  const void* d_o; void* dq; void* dk; void* dv; float* delta; float* dq_accum;
+  int b, hq, hkv, sq, sk, d;
+  float scale;
+  bool causal;
+  bool is_bf16;
+  void* probs_out;  // optional MegaScope export [b,hq,sq,sk] (fwd only)
+};
+int attn_fwd(const AttnArgs& a, cudaStream_t s);
+int attn_bwd(const AttnArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------- comm
+void push_flags_barrier(uint32_t* const* peer_flags, int rank, int size, int slot, uint32_t epoch,
+                        cudaStream_t s);
+struct RsArgs {  // fused scale + cast + reduce-scatter of a gradient bucket
+  const float* src;            // local fp32 bucket [n]
+  void* peer_stage[kMaxPeers]; // staging [size][n/size] in each peer's arena (16-bit or fp32)
+  uint32_t* peer_flags[kMaxPeers];
+  float* dst;                  // local fp32 shard [n/size]
+  int64_t n; int rank; int size; float scale; uint32_t epoch; int wire_dtype; int n_ctas;
+};
+void bucket_reduce_scatter(const RsArgs& a, cudaStream_t s);
+struct AgArgs {  // param all-gather with fused fp32->16-bit cast
+  const float* src_shard; void* peer_dst[kMaxPeers]; uint32_t* peer_flags[kMaxPeers];
+  int64_t shard_n; int rank; int size; uint32_t epoch; int dst_dtype; int n_ctas;
+};
+void shard_all_gather_cast(const AgArgs& a, cudaStream_t s);
+struct A2aArgs {  // MoE dispatch: scatter routed rows into expert-owner buffers
+  const void* src; const int32_t* dst_rank; const int32_t* dst_row; void* peer_buf[kMaxPeers];
+  uint32_t* peer_flags[kMaxPeers]; int64_t rows; int cols; int rank; int size; uint32_t epoch;
+  bool is_bf16; int n_ctas;
+};
+void a2a_scatter_rows(const A2aArgs& a, cudaStream_t s);
+void wait_flags(const uint32_t* flags, int n, uint32_t target, cudaStream_t s);
+void spin_kernel(int64_t cycles, cudaStream_t s);  // MegaScan software slow-rank injector
+void write_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,515 @@
+// PyTorch bindings for the sm_100a kernels (pybind11 module megatronapp_b200._C).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "b200_api.h"
+
+namespace py = pybind11;
+using torch::Tensor;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void count(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int dtype_code(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kBFloat16: return 0;
+    case at::kHalf: return 1;
+    case at::kFloat: return 2;
+    default: TORCH_CHECK(false, "unsupported dtype ", t.scalar_type());
+  }
+}
+bool is_bf16(const Tensor& t) {
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kHalf, "expected bf16/fp16, got ", t.scalar_type());
+  return t.scalar_type() == at::kBFloat16;
+}
+const void* optptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
+
+void check_2d(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.dim() == 2, name, " must be 2-D");
+  TORCH_CHECK(t.stride(1) == 1, name, " must be row-major (inner stride 1)");
+}
+
+void fill_common(b200::GemmArgs& g, const Tensor& A, const Tensor& B, const Tensor& D, bool a_mn,
+                 bool b_mn, int epilogue) {
+  check_2d(A, "A"); check_2d(B, "B"); check_2d(D, "D");
+  g.A = A.data_ptr(); g.B = B.data_ptr(); g.D = D.data_ptr();
+  g.M = static_cast<int>(D.size(0)); g.N = static_cast<int>(D.size(1));
+  g.K = static_cast<int>(a_mn ? A.size(0) : A.size(1));
+  TORCH_CHECK((a_mn ? A.size(1) : A.size(0)) == g.M, "A shape does not match D rows");
+  TORCH_CHECK((b_mn ? B.size(1) : B.size(0)) == g.N, "B shape does not match D cols");
+  TORCH_CHECK((b_mn ? B.size(0) : B.size(1)) == g.K, "A/B reduction dims differ");
+  g.lda = static_cast<int>(A.stride(0)); g.ldb = static_cast<int>(B.stride(0)); g.ldd = static_cast<int>(D.stride(0));
+  g.a_mn_major = a_mn; g.b_mn_major = b_mn;
+  g.is_bf16 = is_bf16(A);
+  TORCH_CHECK(A.scalar_type() == B.scalar_type(), "A and B dtypes differ");
+  g.epilogue = epilogue;
+  if (epilogue == b200::kEpiStore16 || epilogue == b200::kEpiReduceScatter) {
+    TORCH_CHECK(D.scalar_type() == A.scalar_type(), "D dtype must match inputs");
+  } else {
+    TORCH_CHECK(D.scalar_type() == at::kFloat, "fp32 epilogue needs an fp32 D");
+  }
+  g.stream = cur_stream();
+}
+
+void gemm(const Tensor& A, const Tensor& B, Tensor& D, bool a_mn, bool b_mn, int epilogue,
+          const c10::optional<Tensor>& bias, int act, const c10::optional<Tensor>& D_pre, int block_n) {
+  c10::cuda::CUDAGuard guard(A.device());
+  b200::GemmArgs g;
+  fill_common(g, A, B, D, a_mn, b_mn, epilogue);
+  g.bias = optptr(bias); g.act = act;
+  g.D_pre = const_cast<void*>(optptr(D_pre));
+  g.block_n = block_n;
+  int rc = b200::gemm_bf16(g);
+  TORCH_CHECK(rc == 0, "b200 gemm failed (", rc, "): ", b200::gemm_last_error());
+  count();
+}
+
+void gemm_ag(const Tensor& A_local, int64_t gather_ptr, const Tensor& B, Tensor& D, bool b_mn,
+             const c10::optional<Tensor>& bias, int act, std::vector<int64_t> peer_bufs,
+             std::vector<int64_t> peer_flags, int rank, int size, int64_t epoch, int n_comm_ctas,
+             int block_n) {
+  c10::cuda::CUDAGuard guard(A_local.device());
+  check_2d(A_local, "A_local"); check_2d(B, "B"); check_2d(D, "D");
+  b200::GemmArgs g;
+  g.A = reinterpret_cast<const void*>(gather_ptr);
+  g.A_local = A_local.data_ptr(); g.lda_local = static_cast<int>(A_local.stride(0));
+  g.B = B.data_ptr(); g.D = D.data_ptr();
+  g.M = static_cast<int>(D.size(0)); g.N = static_cast<int>(D.size(1)); g.K = static_cast<int>(A_local.size(1));
+  TORCH_CHECK(A_local.size(0) * size == g.M, "A_local rows * tp must equal D rows");
+  g.lda = g.K; g.ldb = static_cast<int>(B.stride(0)); g.ldd = static_cast<int>(D.stride(0));
+  g.a_mn_major = false; g.b_mn_major = b_mn; g.is_bf16 = is_bf16(A_local);
+  g.epilogue = b200::kEpiStore16; g.bias = optptr(bias); g.act = act; g.block_n = block_n;
+  g.comm = b200::kCommAllGather; g.tp_rank = rank; g.tp_size = size; g.epoch = static_cast<uint32_t>(epoch);
+  g.n_comm_ctas = n_comm_ctas;
+  for (int i = 0; i < size; ++i) {
+    g.peer_buf[i] = reinterpret_cast<void*>(peer_bufs[i]);
+    g.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  }
+  g.stream = cur_stream();
+  int rc = b200::gemm_bf16(g);
+  TORCH_CHECK(rc == 0, "b200 gemm_ag failed (", rc, "): ", b200::gemm_last_error());
+  count();
+}
+
+void gemm_rs(const Tensor& A, const Tensor& B, Tensor& D_out, bool b_mn, const c10::optional<Tensor>& bias,
+             std::vector<int64_t> peer_stage, std::vector<int64_t> peer_flags, int rank, int size,
+             int64_t epoch, int block_n) {
+  c10::cuda::CUDAGuard guard(A.device());
+  check_2d(A, "A"); check_2d(B, "B"); check_2d(D_out, "D_out");
+  b200::GemmArgs g;
+  g.A = A.data_ptr(); g.B = B.data_ptr(); g.D = D_out.data_ptr();
+  g.M = static_cast<int>(A.size(0)); g.K = static_cast<int>(A.size(1));
+  g.N = static_cast<int>(D_out.size(1));
+  TORCH_CHECK(D_out.size(0) * size == g.M, "D_out rows * tp must equal A rows");
+  g.lda = static_cast<int>(A.stride(0)); g.ldb = static_cast<int>(B.stride(0)); g.ldd = static_cast<int>(D_out.stride(0));
+  g.a_mn_major = false; g.b_mn_major = b_mn; g.is_bf16 = is_bf16(A);
+  g.epilogue = b200::kEpiReduceScatter; g.bias = optptr(bias); g.block_n = block_n;
+  g.comm = b200::kCommReduceScatter; g.tp_rank = rank; g.tp_size = size; g.epoch = static_cast<uint32_t>(epoch);
+  for (int i = 0; i < size; ++i) {
+    g.peer_buf[i] = reinterpret_cast<void*>(peer_stage[i]);
+    g.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  }
+  g.stream = cur_stream();
+  int rc = b200::gemm_bf16(g);
+  TORCH_CHECK(rc == 0, "b200 gemm_rs failed (", rc, "): ", b200::gemm_last_error());
+  count();
+}
+
+// ---------------------------------------------------------------- norms etc.
+std::vector<Tensor> layernorm_fwd(const Tensor& x, const Tensor& gamma, const c10::optional<Tensor>& beta,
+                                  double eps, bool rms, bool zero_centered) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.size(-1) % 8 == 0, "layernorm: contiguous input with cols % 8 == 0");
+  const int cols = static_cast<int>(x.size(-1));
+  const int rows = static_cast<int>(x.numel() / cols);
+  auto y = torch::empty_like(x);
+  auto fo = x.options().dtype(at::kFloat);
+  auto mean = rms ? torch::empty({0}, fo) : torch::empty({rows}, fo);
+  auto rstd = torch::empty({rows}, fo);
+  b200::layernorm_fwd(x.data_ptr(), gamma.data_ptr(), optptr(beta), y.data_ptr(),
+                      rms ? nullptr : mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, cols,
+                      static_cast<float>(eps), rms, zero_centered, is_bf16(x), cur_stream());
+  count();
+  return {y, mean, rstd};
+}
+
+std::vector<Tensor> layernorm_bwd(const Tensor& dy, const Tensor& x, const Tensor& gamma, const Tensor& mean,
+                                  const Tensor& rstd, bool rms, bool zero_centered, bool has_beta) {
+  c10::cuda::CUDAGuard guard(x.device());
+  const int cols = static_cast<int>(x.size(-1));
+  const int rows = static_cast<int>(x.numel() / cols);
+  TORCH_CHECK(cols <= 8192, "layernorm_bwd supports cols <= 8192");
+  auto dx = torch::empty_like(x);
+  const int np = b200::layernorm_bwd_partials(rows);
+  auto fo = x.options().dtype(at::kFloat);
+  auto pg = torch::empty({np, cols}, fo);
+  auto pb = has_beta ? torch::empty({np, cols}, fo) : torch::empty({0}, fo);
+  auto dgamma = torch::empty({cols}, fo);
+  auto dbeta = has_beta ? torch::empty({cols}, fo) : torch::empty({0}, fo);
+  auto dyc = dy.contiguous();
+  b200::layernorm_bwd(dyc.data_ptr(), x.data_ptr(), gamma.data_ptr(), rms ? nullptr : mean.data_ptr<float>(),
+                      rstd.data_ptr<float>(), dx.data_ptr(), pg.data_ptr<float>(),
+                      has_beta ? pb.data_ptr<float>() : nullptr, rows, cols, rms, zero_centered,
+                      is_bf16(x), np, cur_stream());
+  b200::layernorm_bwd_finalize(pg.data_ptr<float>(), has_beta ? pb.data_ptr<float>() : nullptr,
+                               dgamma.data_ptr<float>(), has_beta ? dbeta.data_ptr<float>() : nullptr, np,
+                               cols, false, cur_stream());
+  count(2);
+  return {dx, dgamma, dbeta};
+}
+
+Tensor bias_gelu_fwd(const Tensor& x, const c10::optional<Tensor>& bias) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.size(-1) % 8 == 0);
+  auto y = torch::empty_like(x);
+  const int cols = static_cast<int>(x.size(-1));
+  b200::bias_gelu_fwd(x.data_ptr(), optptr(bias), y.data_ptr(), x.numel() / cols, cols, is_bf16(x), cur_stream());
+  count();
+  return y;
+}
+Tensor bias_gelu_bwd(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& bias) {
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dyc = dy.contiguous();
+  auto dx = torch::empty_like(x);
+  const int cols = static_cast<int>(x.size(-1));
+  b200::bias_gelu_bwd(dyc.data_ptr(), x.data_ptr(), optptr(bias), dx.data_ptr(), x.numel() / cols, cols, is_bf16(x), cur_stream());
+  count();
+  return dx;
+}
+Tensor swiglu_fwd(const Tensor& x, const c10::optional<Tensor>& bias) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.size(-1) % 16 == 0);
+  auto sizes = x.sizes().vec();
+  const int cols_out = static_cast<int>(sizes.back() / 2);
+  sizes.back() = cols_out;
+  auto y = torch::empty(sizes, x.options());
+  b200::swiglu_fwd(x.data_ptr(), optptr(bias), y.data_ptr(), x.numel() / (2 * cols_out), cols_out, is_bf16(x), cur_stream());
+  count();
+  return y;
+}
+Tensor swiglu_bwd(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& bias) {
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dyc = dy.contiguous();
+  auto dx = torch::empty_like(x);
+  const int cols_out = static_cast<int>(x.size(-1) / 2);
+  b200::swiglu_bwd(dyc.data_ptr(), x.data_ptr(), optptr(bias), dx.data_ptr(), x.numel() / (2 * cols_out), cols_out, is_bf16(x), cur_stream());
+  count();
+  return dx;
+}
+std::vector<Tensor> bias_dropout_add(const Tensor& x, const c10::optional<Tensor>& bias,
+                                     const c10::optional<Tensor>& residual, double p, int64_t seed, int64_t offset) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.size(-1) % 8 == 0);
+  auto out = torch::empty_like(x);
+  Tensor mask = p > 0 ? torch::empty(x.sizes(), x.options().dtype(at::kByte)) : torch::empty({0}, x.options().dtype(at::kByte));
+  const int cols = static_cast<int>(x.size(-1));
+  const void* res = nullptr;
+  Tensor resc;
+  if (residual.has_value() && residual->defined()) { resc = residual->contiguous(); res = resc.data_ptr(); }
+  b200::bias_dropout_add(x.data_ptr(), optptr(bias), res, out.data_ptr(), p > 0 ? mask.data_ptr<uint8_t>() : nullptr,
+                         x.numel() / cols, cols, static_cast<float>(p), static_cast<uint64_t>(seed),
+                         static_cast<uint64_t>(offset), is_bf16(x), cur_stream());
+  count();
+  return {out, mask};
+}
+Tensor dropout_bwd(const Tensor& dy, const Tensor& mask, double p) {
+  c10::cuda::CUDAGuard guard(dy.device());
+  auto dyc = dy.contiguous();
+  auto dx = torch::empty_like(dyc);
+  b200::dropout_bwd(dyc.data_ptr(), mask.data_ptr<uint8_t>(), dx.data_ptr(), dyc.numel(), static_cast<float>(p), is_bf16(dyc), cur_stream());
+  count();
+  return dx;
+}
+Tensor rope_apply(const Tensor& x, const Tensor& cos_sin, bool interleaved, bool inverse) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 4 && x.is_contiguous(), "rope expects contiguous [s, b, h, d]");
+  TORCH_CHECK(cos_sin.scalar_type() == at::kFloat && cos_sin.is_contiguous() && cos_sin.size(0) >= x.size(0));
+  auto y = torch::empty_like(x);
+  b200::rope_apply(x.data_ptr(), cos_sin.data_ptr<float>(), y.data_ptr(), static_cast<int>(x.size(0)),
+                   static_cast<int>(x.size(1)), static_cast<int>(x.size(2)), static_cast<int>(x.size(3)),
+                   static_cast<int>(cos_sin.size(-1)), interleaved, inverse, is_bf16(x), cur_stream());
+  count();
+  return y;
+}
+void bias_grad(const Tensor& dy, Tensor& dbias, bool accumulate) {
+  c10::cuda::CUDAGuard guard(dy.device());
+  TORCH_CHECK(dy.is_contiguous() && dbias.scalar_type() == at::kFloat);
+  const int cols = static_cast<int>(dy.size(-1));
+  TORCH_CHECK(cols % 8 == 0);
+  b200::bias_grad_reduce(dy.data_ptr(), dbias.data_ptr<float>(), dy.numel() / cols, cols, is_bf16(dy), accumulate, cur_stream());
+  count();
+}
+
+std::vector<Tensor> ce_local_stats(const Tensor& logits, const Tensor& labels, int64_t vocab_start) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1 && labels.scalar_type() == at::kLong && labels.is_contiguous());
+  const int64_t rows = logits.size(0);
+  auto fo = logits.options().dtype(at::kFloat);
+  auto mx = torch::empty({rows}, fo), se = torch::empty({rows}, fo), tg = torch::empty({rows}, fo);
+  b200::ce_local_stats(logits.data_ptr(), labels.data_ptr<int64_t>(), mx.data_ptr<float>(), se.data_ptr<float>(),
+                       tg.data_ptr<float>(), rows, static_cast<int>(logits.size(1)), static_cast<int>(vocab_start),
+                       static_cast<int>(logits.stride(0)), dtype_code(logits), cur_stream());
+  count();
+  return {mx, se, tg};
+}
+void ce_rescale(Tensor& sumexp, const Tensor& local_max, const Tensor& global_max) {
+  c10::cuda::CUDAGuard guard(sumexp.device());
+  b200::ce_rescale_sumexp(sumexp.data_ptr<float>(), local_max.data_ptr<float>(), global_max.data_ptr<float>(), sumexp.numel(), cur_stream());
+  count();
+}
+void ce_grad(const Tensor& logits, const Tensor& labels, const Tensor& gmax, const Tensor& gsum,
+             const Tensor& grad_loss, Tensor& dlogits, int64_t vocab_start, double label_smoothing, int64_t vocab_total) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(grad_loss.scalar_type() == at::kFloat && grad_loss.is_contiguous());
+  b200::ce_grad(logits.data_ptr(), labels.data_ptr<int64_t>(), gmax.data_ptr<float>(), gsum.data_ptr<float>(),
+                grad_loss.data_ptr<float>(), dlogits.data_ptr(), logits.size(0), static_cast<int>(logits.size(1)),
+                static_cast<int>(vocab_start), static_cast<int>(logits.stride(0)), dtype_code(logits),
+                static_cast<float>(label_smoothing), vocab_total, cur_stream());
+  count();
+}
+
+void adam_step(Tensor& master, Tensor& exp_avg, Tensor& exp_avg_sq, const Tensor& grad,
+               const c10::optional<Tensor>& param16, double lr, double beta1, double beta2, double eps,
+               double weight_decay, double grad_scale, int64_t step, const c10::optional<Tensor>& found_inf) {
+  c10::cuda::CUDAGuard guard(master.device());
+  b200::AdamArgs a{};
+  a.master = master.data_ptr<float>(); a.exp_avg = exp_avg.data_ptr<float>(); a.exp_avg_sq = exp_avg_sq.data_ptr<float>();
+  a.grad = grad.data_ptr<float>(); a.param16 = const_cast<void*>(optptr(param16)); a.n = master.numel();
+  TORCH_CHECK(grad.numel() == a.n && exp_avg.numel() == a.n);
+  a.lr = static_cast<float>(lr); a.beta1 = static_cast<float>(beta1); a.beta2 = static_cast<float>(beta2);
+  a.eps = static_cast<float>(eps); a.weight_decay = static_cast<float>(weight_decay); a.grad_scale = static_cast<float>(grad_scale);
+  a.bias_correction1 = static_cast<float>(1.0 - std::pow(beta1, static_cast<double>(step)));
+  a.bias_correction2 = static_cast<float>(1.0 - std::pow(beta2, static_cast<double>(step)));
+  a.is_bf16 = param16.has_value() && param16->defined() ? param16->scalar_type() == at::kBFloat16 : true;
+  a.found_inf = found_inf.has_value() && found_inf->defined() ? found_inf->data_ptr<float>() : nullptr;
+  b200::adam_step(a, cur_stream());
+  count();
+}
+void l2norm_sq(const Tensor& x, Tensor& out) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && out.scalar_type() == at::kFloat);
+  b200::l2norm_sq(x.data_ptr(), x.numel(), dtype_code(x), out.data_ptr<float>(), cur_stream());
+  count();
+}
+void scale_(Tensor& x, double scale, const c10::optional<Tensor>& scale_dev) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous());
+  b200::scale_inplace(x.data_ptr(), x.numel(), dtype_code(x), static_cast<float>(scale),
+                      scale_dev.has_value() && scale_dev->defined() ? scale_dev->data_ptr<float>() : nullptr, cur_stream());
+  count();
+}
+void cast_copy(const Tensor& src, Tensor& dst, double scale) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.is_contiguous() && dst.is_contiguous() && src.numel() == dst.numel());
+  b200::cast_copy(src.data_ptr(), dtype_code(src), dst.data_ptr(), dtype_code(dst), src.numel(), static_cast<float>(scale), cur_stream());
+  count();
+}
+void add_into_f32(Tensor& dst, const Tensor& src) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.is_contiguous() && dst.is_contiguous() && dst.scalar_type() == at::kFloat && src.numel() == dst.numel());
+  b200::add_into_f32(dst.data_ptr<float>(), src.data_ptr(), dtype_code(src), src.numel(), cur_stream());
+  count();
+}
+void check_finite(const Tensor& x, Tensor& found) {
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::check_finite(x.data_ptr(), x.numel(), dtype_code(x), found.data_ptr<float>(), cur_stream());
+  count();
+}
+Tensor chunk_mean(const Tensor& x, int64_t pixels) {
+  c10::cuda::CUDAGuard guard(x.device());
+  auto xc = x.contiguous();
+  const int cols = static_cast<int>(xc.size(-1));
+  const int64_t rows = xc.numel() / cols;
+  auto sizes = xc.sizes().vec();
+  sizes.back() = pixels;
+  auto out = torch::empty(sizes, xc.options().dtype(at::kFloat));
+  b200::chunk_mean(xc.data_ptr(), out.data_ptr<float>(), rows, cols, static_cast<int>(pixels), is_bf16(xc), cur_stream());
+  count();
+  return out;
+}
+
+// ---------------------------------------------------------------- attention
+std::vector<Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal, bool want_probs) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous(), "attn expects contiguous [b,h,s,d]");
+  b200::AttnArgs a{};
+  a.b = static_cast<int>(q.size(0)); a.hq = static_cast<int>(q.size(1)); a.sq = static_cast<int>(q.size(2)); a.d = static_cast<int>(q.size(3));
+  a.hkv = static_cast<int>(k.size(1)); a.sk = static_cast<int>(k.size(2));
+  auto o = torch::empty_like(q);
+  auto lse = torch::empty({a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));
+  Tensor probs = want_probs ? torch::empty({a.b, a.hq, a.sq, a.sk}, q.options()) : torch::empty({0}, q.options());
+  a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = o.data_ptr(); a.lse = lse.data_ptr<float>();
+  a.scale = static_cast<float>(scale); a.causal = causal; a.is_bf16 = is_bf16(q);
+  a.probs_out = want_probs ? probs.data_ptr() : nullptr;
+  int rc = b200::attn_fwd(a, cur_stream());
+  TORCH_CHECK(rc == 0, "b200 attn_fwd failed: ", rc);
+  count();
+  return {o, lse, probs};
+}
+std::vector<Tensor> attn_bwd(const Tensor& d_o, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o,
+                             const Tensor& lse, double scale, bool causal) {
+  c10::cuda::CUDAGuard guard(q.device());
+  b200::AttnArgs a{};
+  a.b = static_cast<int>(q.size(0)); a.hq = static_cast<int>(q.size(1)); a.sq = static_cast<int>(q.size(2)); a.d = static_cast<int>(q.size(3));
+  a.hkv = static_cast<int>(k.size(1)); a.sk = static_cast<int>(k.size(2));
+  auto doc = d_o.contiguous();
+  auto dq = torch::empty_like(q);
+  auto dk = torch::empty_like(k);
+  auto dv = torch::empty_like(v);
+  auto delta = torch::empty({a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));
+  auto dq_accum = torch::zeros({a.b, a.hq, a.sq, a.d}, q.options().dtype(at::kFloat));
+  a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = const_cast<void*>(o.data_ptr()); a.lse = lse.data_ptr<float>();
+  a.d_o = doc.data_ptr(); a.dq = dq.data_ptr(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
+  a.delta = delta.data_ptr<float>(); a.dq_accum = dq_accum.data_ptr<float>();
+  a.scale = static_cast<float>(scale); a.causal = causal; a.is_bf16 = is_bf16(q);
+  int rc = b200::attn_bwd(a, cur_stream());
+  TORCH_CHECK(rc == 0, "b200 attn_bwd failed: ", rc);
+  count(3);
+  return {dq, dk, dv};
+}
+
+// ---------------------------------------------------------------- arena / comm
+py::tuple arena_alloc(int64_t nbytes) {
+  void* p = nullptr;
+  auto e = cudaMalloc(&p, static_cast<size_t>(nbytes));
+  TORCH_CHECK(e == cudaSuccess, "arena cudaMalloc failed: ", cudaGetErrorString(e));
+  cudaMemset(p, 0, static_cast<size_t>(nbytes));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  TORCH_CHECK(e == cudaSuccess, "cudaIpcGetMemHandle failed: ", cudaGetErrorString(e));
+  cudaDeviceSynchronize();
+  return py::make_tuple(reinterpret_cast<int64_t>(p), py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)));
+}
+int64_t arena_open(py::bytes handle) {
+  std::string s = handle;
+  TORCH_CHECK(s.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, s.data(), sizeof(h));
+  void* p = nullptr;
+  auto e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  TORCH_CHECK(e == cudaSuccess, "cudaIpcOpenMemHandle failed: ", cudaGetErrorString(e));
+  return reinterpret_cast<int64_t>(p);
+}
+void arena_close(int64_t ptr) { cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr)); }
+void arena_free(int64_t ptr) { cudaFree(reinterpret_cast<void*>(ptr)); }
+Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> shape, py::object dtype, int64_t device) {
+  auto st = torch::python::detail::py_object_to_dtype(dtype);
+  auto opts = torch::TensorOptions().dtype(st).device(torch::kCUDA, static_cast<int>(device));
+  return torch::from_blob(reinterpret_cast<void*>(ptr), shape, [](void*) {}, opts);
+}
+
+void flags_barrier(std::vector<int64_t> peer_flags, int rank, int size, int slot, int64_t epoch) {
+  uint32_t* pf[b200::kMaxPeers] = {nullptr};
+  for (int i = 0; i < size; ++i) pf[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  b200::push_flags_barrier(pf, rank, size, slot, static_cast<uint32_t>(epoch), cur_stream());
+  count();
+}
+void bucket_reduce_scatter(const Tensor& src, Tensor& dst, std::vector<int64_t> peer_stage,
+                           std::vector<int64_t> peer_flags, int rank, int size, double scale, int64_t epoch,
+                           int wire_dtype, int n_ctas) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.scalar_type() == at::kFloat && dst.scalar_type() == at::kFloat && src.is_contiguous() && dst.is_contiguous());
+  TORCH_CHECK(src.numel() % (size * 4) == 0, "bucket size must be a multiple of 4*dp");
+  TORCH_CHECK(dst.numel() == src.numel() / size);
+  b200::RsArgs a{};
+  a.src = src.data_ptr<float>(); a.dst = dst.data_ptr<float>(); a.n = src.numel(); a.rank = rank; a.size = size;
+  a.scale = static_cast<float>(scale); a.epoch = static_cast<uint32_t>(epoch); a.wire_dtype = wire_dtype; a.n_ctas = n_ctas;
+  for (int i = 0; i < size; ++i) { a.peer_stage[i] = reinterpret_cast<void*>(peer_stage[i]); a.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
+  b200::bucket_reduce_scatter(a, cur_stream());
+  count();
+}
+void shard_all_gather_cast(const Tensor& src_shard, std::vector<int64_t> peer_dst, std::vector<int64_t> peer_flags,
+                           int rank, int size, int64_t epoch, int dst_dtype, int n_ctas) {
+  c10::cuda::CUDAGuard guard(src_shard.device());
+  TORCH_CHECK(src_shard.scalar_type() == at::kFloat && src_shard.is_contiguous() && src_shard.numel() % 4 == 0);
+  b200::AgArgs a{};
+  a.src_shard = src_shard.data_ptr<float>(); a.shard_n = src_shard.numel(); a.rank = rank; a.size = size;
+  a.epoch = static_cast<uint32_t>(epoch); a.dst_dtype = dst_dtype; a.n_ctas = n_ctas;
+  for (int i = 0; i < size; ++i) { a.peer_dst[i] = reinterpret_cast<void*>(peer_dst[i]); a.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
+  b200::shard_all_gather_cast(a, cur_stream());
+  count();
+}
+void a2a_scatter_rows(const Tensor& src, const Tensor& dst_rank, const Tensor& dst_row, std::vector<int64_t> peer_buf,
+                      std::vector<int64_t> peer_flags, int rank, int size, int64_t epoch, int n_ctas) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.dim() == 2 && src.is_contiguous() && src.size(1) % 8 == 0);
+  TORCH_CHECK(dst_rank.scalar_type() == at::kInt && dst_row.scalar_type() == at::kInt);
+  b200::A2aArgs a{};
+  a.src = src.data_ptr(); a.dst_rank = dst_rank.data_ptr<int32_t>(); a.dst_row = dst_row.data_ptr<int32_t>();
+  a.rows = src.size(0); a.cols = static_cast<int>(src.size(1)); a.rank = rank; a.size = size;
+  a.epoch = static_cast<uint32_t>(epoch); a.is_bf16 = is_bf16(src); a.n_ctas = n_ctas;
+  for (int i = 0; i < size; ++i) { a.peer_buf[i] = reinterpret_cast<void*>(peer_buf[i]); a.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
+  b200::a2a_scatter_rows(a, cur_stream());
+  count();
+}
+void spin(int64_t cycles) { b200::spin_kernel(cycles, cur_stream()); count(); }
+void write_flag(int64_t flag_ptr, int64_t value) { b200::write_flag(reinterpret_cast<uint32_t*>(flag_ptr), static_cast<uint32_t>(value), cur_stream()); count(); }
+void peer_copy(int64_t dst_ptr, const Tensor& src) {
+  auto e = cudaMemcpyAsync(reinterpret_cast<void*>(dst_ptr), src.data_ptr(), src.nbytes(), cudaMemcpyDeviceToDevice, cur_stream());
+  TORCH_CHECK(e == cudaSuccess, "peer copy failed: ", cudaGetErrorString(e));
+}
+int64_t host_register(int64_t host_ptr, int64_t nbytes) {
+  auto e = cudaHostRegister(reinterpret_cast<void*>(host_ptr), static_cast<size_t>(nbytes), cudaHostRegisterMapped | cudaHostRegisterPortable);
+  TORCH_CHECK(e == cudaSuccess, "cudaHostRegister failed: ", cudaGetErrorString(e));
+  void* dptr = nullptr;
+  e = cudaHostGetDevicePointer(&dptr, reinterpret_cast<void*>(host_ptr), 0);
+  TORCH_CHECK(e == cudaSuccess, "cudaHostGetDevicePointer failed: ", cudaGetErrorString(e));
+  return reinterpret_cast<int64_t>(dptr);
+}
+void host_unregister(int64_t host_ptr) { cudaHostUnregister(reinterpret_cast<void*>(host_ptr)); }
+
+int64_t launch_count() { return g_launches.load(); }
+void reset_launch_count() { g_launches.store(0); }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("gemm", &gemm);
+  m.def("gemm_ag", &gemm_ag);
+  m.def("gemm_rs", &gemm_rs);
+  m.def("gemm_flags_needed", &b200::gemm_flags_needed);
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("bias_gelu_fwd", &bias_gelu_fwd);
+  m.def("bias_gelu_bwd", &bias_gelu_bwd);
+  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("bias_dropout_add", &bias_dropout_add);
+  m.def("dropout_bwd", &dropout_bwd);
+  m.def("rope_apply", &rope_apply);
+  m.def("bias_grad", &bias_grad);
+  m.def("ce_local_stats", &ce_local_stats);
+  m.def("ce_rescale", &ce_rescale);
+  m.def("ce_grad", &ce_grad);
+  m.def("adam_step", &adam_step);
+  m.def("l2norm_sq", &l2norm_sq);
+  m.def("scale_", &scale_);
+  m.def("cast_copy", &cast_copy);
+  m.def("add_into_f32", &add_into_f32);
+  m.def("check_finite", &check_finite);
+  m.def("chunk_mean", &chunk_mean);
+  m.def("attn_fwd", &attn_fwd);
+  m.def("attn_bwd", &attn_bwd);
+  m.def("arena_alloc", &arena_alloc);
+  m.def("arena_open", &arena_open);
+  m.def("arena_close", &arena_close);
+  m.def("arena_free", &arena_free);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("flags_barrier", &flags_barrier);
+  m.def("bucket_reduce_scatter", &bucket_reduce_scatter);
+  m.def("shard_all_gather_cast", &shard_all_gather_cast);
+  m.def("a2a_scatter_rows", &a2a_scatter_rows);
+  m.def("spin", &spin);
+  m.def("write_flag", &write_flag);
+  m.def("peer_copy", &peer_copy);
+  m.def("host_register", &host_register);
+  m.def("host_unregister", &host_unregister);
+  m.def("launch_count", &launch_count);
+  m.def("reset_launch_count", &reset_launch_count);
+}
