@@ -1,0 +1,171 @@
+"""Symmetric-memory arena over CUDA IPC.
+
+Every rank of a group ``cudaMalloc``s one arena (native ``_C.arena_alloc``), exports it with
+``cudaIpcGetMemHandle`` and maps every peer's arena, so the fused kernels
+(``gemm_ag`` / ``gemm_rs`` / ``bucket_reduce_scatter`` / ``a2a_scatter_rows``) can issue plain
+``ld/st`` to peer HBM over NVLink 5 / NVSwitch.  Regions are carved by a deterministic bump
+allocator, so the same name maps to the same offset on every rank ("symmetric").
+
+Synchronisation contract used by all kernels: per-region *epoch* counters (monotonic, one per
+double-buffer slot); writers publish the epoch with ``st.release.sys``, readers poll with
+``ld.acquire.sys``.  Alternating two slots per region makes reuse safe without a barrier:
+a rank can be at most one collective ahead of any peer because every fused kernel needs data
+from all peers before it completes.
+
+This replaces the reference's userbuffer / shm plumbing (``initialize.py:236-292``,
+``shm_tensor_new_rdma*.cpp``) for the single-node NVSwitch case.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+
+_ALIGN = 1024
+
+
+@dataclass
+class Region:
+    name: str
+    offset: int
+    nbytes: int
+    epoch: int = 0
+
+
+class SymmetricArena:
+    def __init__(self, group, nbytes: int, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SymmetricArena needs CUDA")
+        self.group = group
+        self.size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.nbytes = (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        ext = ops.ext()
+        self.local_ptr, handle = ext.arena_alloc(self.nbytes)
+        handles: List[Optional[bytes]] = [None] * self.size
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_ptrs: List[int] = []
+        for r, h in enumerate(handles):
+            self.peer_ptrs.append(self.local_ptr if r == self.rank else ext.arena_open(h))
+        self._cursor = 0
+        self.regions: Dict[str, Region] = {}
+        dist.barrier(group=group)
+
+    # -- allocation -----------------------------------------------------------
+    def region(self, name: str, nbytes: int) -> Region:
+        reg = self.regions.get(name)
+        if reg is not None:
+            if reg.nbytes < nbytes:
+                raise RuntimeError(f"arena region {name!r} was sized {reg.nbytes} < requested {nbytes}")
+            return reg
+        nbytes = (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        if self._cursor + nbytes > self.nbytes:
+            raise RuntimeError(
+                f"symmetric arena exhausted: {self._cursor}+{nbytes} > {self.nbytes} (region {name!r})")
+        reg = Region(name, self._cursor, nbytes)
+        self._cursor += nbytes
+        self.regions[name] = reg
+        return reg
+
+    def ptrs(self, reg: Region, extra_offset: int = 0) -> List[int]:
+        return [p + reg.offset + extra_offset for p in self.peer_ptrs]
+
+    def local(self, reg: Region, shape, dtype) -> torch.Tensor:
+        return ops.ext().tensor_from_ptr(self.local_ptr + reg.offset, list(shape), dtype, self.device.index)
+
+    def next_epoch(self, reg: Region) -> int:
+        reg.epoch += 1
+        return reg.epoch
+
+    def barrier(self, slot: int = 0) -> None:
+        """Device-side barrier over the group (one tiny kernel, no host sync)."""
+        reg = self.region("__barrier__", 4 * 8 * 16)
+        ep = self.next_epoch(reg)
+        ops.ext().flags_barrier(self.ptrs(reg), self.rank, self.size, slot, ep)
+
+    def close(self) -> None:
+        ext = ops.ext()
+        torch.cuda.synchronize()
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank:
+                ext.arena_close(p)
+        ext.arena_free(self.local_ptr)
+        self.peer_ptrs = []
+
+
+_ARENAS: Dict[str, SymmetricArena] = {}
+
+
+def get_arena(kind: str, group=None, nbytes: int = 0) -> Optional[SymmetricArena]:
+    """Per-group arena registry (``kind`` in tp / dp / ep)."""
+    a = _ARENAS.get(kind)
+    if a is None and group is not None and nbytes > 0:
+        a = SymmetricArena(group, nbytes)
+        _ARENAS[kind] = a
+    return a
+
+
+def destroy_arenas() -> None:
+    for a in _ARENAS.values():
+        try:
+            a.close()
+        except Exception:
+            pass
+    _ARENAS.clear()
+
+
+class TPFusedComm:
+    """Book-keeping for the fused AG->GEMM / GEMM->RS kernels of one TP group.
+
+    Two slots per direction (alternating per call); gather buffers sized for the largest
+    ``[tokens, hidden]`` activation, RS staging for the largest ``[tokens, out]`` partial.
+    """
+
+    def __init__(self, arena: SymmetricArena, max_tokens: int, max_in: int, max_out: int,
+                 n_comm_ctas: int = 20):
+        self.arena = arena
+        self.n_comm_ctas = n_comm_ctas
+        self.calls = {"ag": 0, "rs": 0}
+        ext = ops.ext()
+        nflags = max(ext.gemm_flags_needed(max_tokens, max(max_in, max_out), arena.size), 4096)
+        self.ag = [arena.region(f"tp_ag{i}", max_tokens * max_in * 2) for i in range(2)]
+        self.ag_flags = [arena.region(f"tp_ag_flags{i}", nflags * 4) for i in range(2)]
+        self.rs = [arena.region(f"tp_rs{i}", max_tokens * max_out * 2) for i in range(2)]
+        self.rs_flags = [arena.region(f"tp_rs_flags{i}", nflags * 4) for i in range(2)]
+
+    def ag_gemm(self, x_local: torch.Tensor, weight: torch.Tensor, bias=None, b_mn: bool = False,
+                act: int = 0, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``AG(x_local) @ W^T``; returns (out, gathered_x_view).  The gathered view aliases the
+        arena slot and is only valid until the slot is reused two calls later."""
+        a = self.arena
+        slot = self.calls["ag"] & 1
+        self.calls["ag"] += 1
+        reg, freg = self.ag[slot], self.ag_flags[slot]
+        epoch = a.next_epoch(freg)
+        M = x_local.shape[0] * a.size
+        K = x_local.shape[1]
+        N = weight.shape[1] if b_mn else weight.shape[0]
+        if out is None:
+            out = torch.empty(M, N, dtype=x_local.dtype, device=x_local.device)
+        ops.ext().gemm_ag(x_local, a.local_ptr + reg.offset, weight, out, b_mn, bias, act,
+                          a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, self.n_comm_ctas, 0)
+        gathered = a.local(reg, (M, K), x_local.dtype)
+        return out, gathered
+
+    def gemm_rs(self, x: torch.Tensor, weight: torch.Tensor, bias=None, b_mn: bool = False) -> torch.Tensor:
+        """``reduce_scatter(x @ W^T)`` along rows."""
+        a = self.arena
+        slot = self.calls["rs"] & 1
+        self.calls["rs"] += 1
+        reg, freg = self.rs[slot], self.rs_flags[slot]
+        epoch = a.next_epoch(freg)
+        M = x.shape[0]
+        N = weight.shape[1] if b_mn else weight.shape[0]
+        out = torch.empty(M // a.size, N, dtype=x.dtype, device=x.device)
+        ops.ext().gemm_rs(x, weight, out, b_mn, bias, a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, 0)
+        return out

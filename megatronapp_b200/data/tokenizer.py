@@ -1,0 +1,347 @@
+"""Tokenizers behind ``--tokenizer-type`` (reference ``training/tokenizer/tokenizer.py:26-96``).
+
+Implemented natively: ``NullTokenizer``, ``GPT2BPETokenizer`` (byte-level BPE from
+vocab.json/merges.txt, with the ``decoder``/``encoder`` maps MegaScope needs),
+``BertWordPieceLowerCase/Case``; ``SentencePieceTokenizer`` / ``GPTSentencePieceTokenizer`` /
+``Llama2Tokenizer`` wrap the ``sentencepiece`` package; ``HuggingFaceTokenizer`` wraps
+``transformers``; ``TikTokenizer`` is gated on ``tiktoken`` being installed.
+"""
+from __future__ import annotations
+
+import json
+import os
+import unicodedata
+from functools import lru_cache
+from typing import Dict, List
+
+import regex as re
+
+
+def _vocab_size_with_padding(orig_vocab_size: int, args) -> int:
+    mult = args.make_vocab_size_divisible_by * args.tensor_model_parallel_size
+    after = (orig_vocab_size + mult - 1) // mult * mult
+    if getattr(args, "rank", 0) == 0:
+        print(f" > padded vocab (size: {orig_vocab_size}) with {after - orig_vocab_size} dummy tokens "
+              f"(new size: {after})", flush=True)
+    return after
+
+
+class MegatronTokenizer:
+    def __init__(self, name):
+        self.name = name
+
+    @property
+    def vocab_size(self):
+        raise NotImplementedError
+
+    def tokenize(self, text):
+        raise NotImplementedError
+
+    def detokenize(self, ids):
+        raise NotImplementedError
+
+    @property
+    def eod(self):
+        raise NotImplementedError
+
+    @property
+    def eos(self):
+        return self.eod
+
+    @property
+    def pad(self):
+        return self.eod
+
+
+class NullTokenizer(MegatronTokenizer):
+    def __init__(self, vocab_size):
+        super().__init__("NullTokenizer")
+        self._vocab_size_without_eod = int(vocab_size)
+        self._eod_id = int(vocab_size)
+
+    def tokenize(self, text):
+        return [int(x) for x in text.split(" ")]
+
+    def detokenize(self, ids):
+        return " ".join(str(i) for i in ids)
+
+    def offsets(self, ids, text):
+        out, start = [], 0
+        for i in ids:
+            out.append(start)
+            start += 1 + len(str(i))
+        return out
+
+    @property
+    def vocab_size(self):
+        return self._vocab_size_without_eod + 1
+
+    @property
+    def vocab(self):
+        raise NotImplementedError
+
+    @property
+    def eod(self):
+        return self._eod_id
+
+
+@lru_cache()
+def bytes_to_unicode() -> Dict[int, str]:
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(ord("¡"), ord("¬") + 1)) + list(range(ord("®"), ord("ÿ") + 1))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b)
+            cs.append(256 + n)
+            n += 1
+    return dict(zip(bs, [chr(c) for c in cs]))
+
+
+class GPT2BPETokenizer(MegatronTokenizer):
+    def __init__(self, vocab_file, merge_file):
+        super().__init__("GPT2 BPE")
+        with open(vocab_file, encoding="utf-8") as f:
+            self.encoder: Dict[str, int] = json.load(f)
+        self.decoder = {v: k for k, v in self.encoder.items()}
+        self.byte_encoder = bytes_to_unicode()
+        self.byte_decoder = {v: k for k, v in self.byte_encoder.items()}
+        with open(merge_file, encoding="utf-8") as f:
+            merges = [tuple(line.split()) for line in f.read().split("\n")[1:] if line and not line.startswith("#")]
+        self.bpe_ranks = {m: i for i, m in enumerate(merges) if len(m) == 2}
+        self.cache: Dict[str, str] = {}
+        self.pat = re.compile(r"""'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+""")
+        self.eod_id = self.encoder.get("<|endoftext|>", len(self.encoder) - 1)
+
+    def _bpe(self, token: str) -> str:
+        if token in self.cache:
+            return self.cache[token]
+        word = tuple(token)
+        if len(word) < 2:
+            return token
+        while True:
+            pairs = {(word[i], word[i + 1]) for i in range(len(word) - 1)}
+            if not pairs:
+                break
+            bigram = min(pairs, key=lambda p: self.bpe_ranks.get(p, float("inf")))
+            if bigram not in self.bpe_ranks:
+                break
+            first, second = bigram
+            new, i = [], 0
+            while i < len(word):
+                if i < len(word) - 1 and word[i] == first and word[i + 1] == second:
+                    new.append(first + second)
+                    i += 2
+                else:
+                    new.append(word[i])
+                    i += 1
+            word = tuple(new)
+            if len(word) == 1:
+                break
+        out = " ".join(word)
+        self.cache[token] = out
+        return out
+
+    def tokenize(self, text):
+        ids = []
+        for tok in re.findall(self.pat, text):
+            tok = "".join(self.byte_encoder[b] for b in tok.encode("utf-8"))
+            ids.extend(self.encoder[t] for t in self._bpe(tok).split(" "))
+        return ids
+
+    def detokenize(self, ids):
+        text = "".join(self.decoder[i] for i in ids)
+        return bytearray([self.byte_decoder[c] for c in text]).decode("utf-8", errors="replace")
+
+    def offsets(self, ids, text):
+        out, pos = [], 0
+        for i in ids:
+            out.append(pos)
+            pos += len(bytearray([self.byte_decoder[c] for c in self.decoder[i]]).decode("utf-8", errors="replace"))
+        return out
+
+    @property
+    def vocab_size(self):
+        return len(self.encoder)
+
+    @property
+    def vocab(self):
+        return self.encoder
+
+    @property
+    def inv_vocab(self):
+        return self.decoder
+
+    @property
+    def eod(self):
+        return self.eod_id
+
+
+class BertWordPieceTokenizer(MegatronTokenizer):
+    def __init__(self, vocab_file, lower_case=True, vocab_extra_ids=0):
+        super().__init__("BERT Lower Case" if lower_case else "BERT Upper Case")
+        self.vocab_: Dict[str, int] = {}
+        with open(vocab_file, encoding="utf-8") as f:
+            for i, line in enumerate(f):
+                self.vocab_[line.rstrip("\n")] = i
+        self.lower = lower_case
+        for k in range(vocab_extra_ids):
+            self.vocab_.setdefault(f"<extra_id_{k}>", len(self.vocab_))
+        self.inv = {v: k for k, v in self.vocab_.items()}
+        self.cls_id, self.sep_id = self.vocab_["[CLS]"], self.vocab_["[SEP]"]
+        self.pad_id, self.mask_id = self.vocab_["[PAD]"], self.vocab_["[MASK]"]
+        self.unk = self.vocab_.get("[UNK]", 0)
+
+    def _basic(self, text):
+        if self.lower:
+            text = "".join(c for c in unicodedata.normalize("NFD", text.lower()) if unicodedata.category(c) != "Mn")
+        return re.findall(r"\w+|[^\w\s]", text)
+
+    def tokenize(self, text):
+        ids = []
+        for w in self._basic(text):
+            start, sub = 0, []
+            bad = False
+            while start < len(w):
+                end = len(w)
+                cur = None
+                while start < end:
+                    piece = w[start:end] if start == 0 else "##" + w[start:end]
+                    if piece in self.vocab_:
+                        cur = piece
+                        break
+                    end -= 1
+                if cur is None:
+                    bad = True
+                    break
+                sub.append(self.vocab_[cur])
+                start = end
+            ids.extend([self.unk] if bad else sub)
+        return ids
+
+    def detokenize(self, ids):
+        toks = [self.inv[i] for i in ids if i not in (self.pad_id, self.cls_id, self.sep_id)]
+        out = ""
+        for t in toks:
+            out += t[2:] if t.startswith("##") else (" " + t if out else t)
+        return out
+
+    def decode_token_ids(self, ids):
+        return self.detokenize(ids)
+
+    @property
+    def vocab_size(self):
+        return len(self.vocab_)
+
+    @property
+    def vocab(self):
+        return self.vocab_
+
+    @property
+    def inv_vocab(self):
+        return self.inv
+
+    @property
+    def cls(self):
+        return self.cls_id
+
+    @property
+    def sep(self):
+        return self.sep_id
+
+    @property
+    def pad(self):
+        return self.pad_id
+
+    @property
+    def mask(self):
+        return self.mask_id
+
+    @property
+    def eod(self):
+        return self.sep_id
+
+
+class SentencePieceTokenizer(MegatronTokenizer):
+    def __init__(self, model_file, vocab_extra_ids=0, legacy=True):
+        super().__init__("SentencePieceTokenizer")
+        import sentencepiece
+
+        self.sp = sentencepiece.SentencePieceProcessor(model_file=model_file)
+        self._extra = vocab_extra_ids
+        self._eod = self.sp.eos_id() if self.sp.eos_id() >= 0 else self.sp.pad_id()
+
+    def tokenize(self, text):
+        return self.sp.encode(text)
+
+    def detokenize(self, ids):
+        return self.sp.decode([i for i in ids if i < self.sp.get_piece_size()])
+
+    @property
+    def vocab_size(self):
+        return self.sp.get_piece_size() + self._extra
+
+    @property
+    def bos(self):
+        return self.sp.bos_id()
+
+    @property
+    def eod(self):
+        return self._eod
+
+
+class HuggingFaceTokenizer(MegatronTokenizer):
+    def __init__(self, name_or_path, **kw):
+        super().__init__("HuggingFaceTokenizer")
+        import transformers
+
+        self.tk = transformers.AutoTokenizer.from_pretrained(name_or_path, **kw)
+
+    def tokenize(self, text, **kw):
+        return self.tk(text, **kw).input_ids
+
+    def detokenize(self, ids, **kw):
+        return self.tk.decode(ids, **kw)
+
+    @property
+    def vocab_size(self):
+        return len(self.tk)
+
+    @property
+    def vocab(self):
+        return self.tk.get_vocab()
+
+    @property
+    def eod(self):
+        return self.tk.eos_token_id
+
+
+def build_tokenizer(args):
+    ttype = args.tokenizer_type
+    if ttype is None:
+        if args.vocab_size is not None or args.padded_vocab_size is not None or args.mock_data:
+            ttype = "NullTokenizer"
+        else:
+            return None
+    if ttype == "NullTokenizer":
+        vs = args.vocab_size if args.vocab_size is not None else 50256
+        tok = NullTokenizer(vs)
+    elif ttype == "GPT2BPETokenizer":
+        tok = GPT2BPETokenizer(args.vocab_file, args.merge_file)
+    elif ttype in ("BertWordPieceLowerCase", "BertWordPieceCase"):
+        tok = BertWordPieceTokenizer(args.vocab_file, ttype.endswith("LowerCase"), args.vocab_extra_ids)
+    elif ttype in ("SentencePieceTokenizer", "GPTSentencePieceTokenizer", "Llama2Tokenizer"):
+        tok = SentencePieceTokenizer(args.tokenizer_model, args.vocab_extra_ids)
+    elif ttype == "HuggingFaceTokenizer":
+        tok = HuggingFaceTokenizer(args.tokenizer_model)
+    elif ttype == "TikTokenizer":
+        try:
+            import tiktoken  # noqa: F401
+        except ImportError as e:
+            raise ImportError("TikTokenizer needs the tiktoken package, which is not installed") from e
+        raise NotImplementedError("TikTokenizer: provide --tokenizer-model with a tiktoken vocabulary")
+    else:
+        raise NotImplementedError(f"{ttype} tokenizer is not implemented")
+    if getattr(args, "padded_vocab_size", None) is None:
+        args.padded_vocab_size = _vocab_size_with_padding(tok.vocab_size, args)
+    return tok

@@ -1,0 +1,169 @@
+"""Token / position embeddings and rotary position embeddings.
+
+Parity: reference ``models/common/embeddings/language_model_embedding.py`` (word + learned
+absolute position (+ tokentype) embeddings, dropout, scatter to the sequence-parallel region),
+``rotary_pos_embedding.py`` (``RotaryEmbedding`` incl. ``rotary_percent``, linear
+``seq_len_interpolation_factor`` and llama-3 style ``rope_scaling``) and
+``yarn_rotary_pos_embedding.py``.  The rotary table is a fp32 ``[s, rot_dim]`` (cos | sin)
+tensor consumed by the fused RoPE kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ...parallel import state as ps
+from ...parallel.mappings import scatter_to_sequence_parallel_region
+from ...parallel.random import get_cuda_rng_tracker
+from ...parallel.tp_layers import VocabParallelEmbedding
+from ...transformer.module import MegatronModule
+
+
+class LanguageModelEmbedding(MegatronModule):
+    def __init__(self, config, vocab_size: int, max_sequence_length: int,
+                 position_embedding_type: str = "learned_absolute", num_tokentypes: int = 0,
+                 scatter_to_sequence_parallel: bool = True):
+        super().__init__(config)
+        self.vocab_size, self.max_sequence_length = vocab_size, max_sequence_length
+        self.add_position_embedding = position_embedding_type == "learned_absolute"
+        self.num_tokentypes = num_tokentypes
+        self.scatter_to_sequence_parallel = scatter_to_sequence_parallel
+        self.reduce_scatter_embeddings = ((not self.add_position_embedding) and num_tokentypes <= 0
+                                          and config.sequence_parallel and scatter_to_sequence_parallel)
+        self.word_embeddings = VocabParallelEmbedding(
+            vocab_size, config.hidden_size, init_method=config.init_method,
+            reduce_scatter_embeddings=self.reduce_scatter_embeddings, config=config)
+        dev = "cpu" if (config.use_cpu_initialization or not torch.cuda.is_available()) else torch.cuda.current_device()
+        if self.add_position_embedding:
+            self.position_embeddings = nn.Embedding(max_sequence_length, config.hidden_size,
+                                                    dtype=config.params_dtype, device=dev)
+            if config.perform_initialization:
+                config.init_method(self.position_embeddings.weight)
+        if num_tokentypes > 0:
+            self.tokentype_embeddings = nn.Embedding(num_tokentypes, config.hidden_size,
+                                                     dtype=config.params_dtype, device=dev)
+            if config.perform_initialization:
+                config.init_method(self.tokentype_embeddings.weight)
+        else:
+            self.tokentype_embeddings = None
+        self.embedding_dropout = nn.Dropout(config.hidden_dropout)
+
+    def zero_parameters(self):
+        for p in self.parameters():
+            p.data.fill_(0)
+            p.shared = True
+
+    def forward(self, input_ids, position_ids, tokentype_ids=None):
+        emb = self.word_embeddings(input_ids)
+        if self.add_position_embedding:
+            emb = emb + self.position_embeddings(position_ids)
+        if not self.reduce_scatter_embeddings:
+            emb = emb.transpose(0, 1).contiguous()  # [b, s, h] -> [s, b, h]
+        if tokentype_ids is not None and self.tokentype_embeddings is not None:
+            emb = emb + self.tokentype_embeddings(tokentype_ids).permute(1, 0, 2)
+        if self.config.fp32_residual_connection:
+            emb = emb.float()
+        if self.config.sequence_parallel:
+            if not self.reduce_scatter_embeddings and self.scatter_to_sequence_parallel:
+                emb = scatter_to_sequence_parallel_region(emb)
+            if self.config.clone_scatter_output_in_embedding and self.scatter_to_sequence_parallel:
+                emb = emb.clone()
+            tr = get_cuda_rng_tracker()
+            if "model-parallel-rng" in tr.states_ and self.config.hidden_dropout > 0:
+                with tr.fork():
+                    emb = self.embedding_dropout(emb)
+            else:
+                emb = self.embedding_dropout(emb)
+        else:
+            emb = self.embedding_dropout(emb)
+        return emb
+
+
+def _apply_llama3_scaling(inv_freq, factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max=8192):
+    low_wl = original_max / low_freq_factor
+    high_wl = original_max / high_freq_factor
+    wl = 2 * math.pi / inv_freq
+    scaled = torch.where(wl > low_wl, inv_freq / factor, inv_freq)
+    smooth = (original_max / wl - low_freq_factor) / (high_freq_factor - low_freq_factor)
+    smoothed = (1 - smooth) * inv_freq / factor + smooth * inv_freq
+    mid = (wl >= high_wl) & (wl <= low_wl)
+    return torch.where(mid, smoothed, scaled)
+
+
+class RotaryEmbedding(nn.Module):
+    def __init__(self, kv_channels: int, rotary_percent: float = 1.0, rotary_interleaved: bool = False,
+                 seq_len_interpolation_factor: Optional[float] = None, rotary_base: float = 10000.0,
+                 rope_scaling: bool = False, rope_scaling_factor: float = 8.0, use_cpu_initialization: bool = False):
+        super().__init__()
+        dim = kv_channels
+        if rotary_percent < 1.0:
+            dim = int(dim * rotary_percent)
+        self.dim = dim
+        self.rotary_interleaved = rotary_interleaved
+        self.seq_len_interpolation_factor = seq_len_interpolation_factor
+        inv = 1.0 / (rotary_base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim))
+        if rope_scaling:
+            inv = _apply_llama3_scaling(inv, factor=rope_scaling_factor)
+        self.register_buffer("inv_freq", inv, persistent=False)
+        self._cache = {}
+
+    def get_rotary_seq_len(self, inference_context, transformer, transformer_input, transformer_config,
+                           packed_seq_params=None):
+        if inference_context is not None:
+            return inference_context.max_sequence_length
+        if transformer is not None and getattr(transformer, "input_tensor", None) is not None:
+            s = transformer.input_tensor.size(0)
+        else:
+            s = transformer_input.size(0)
+        if transformer_config.sequence_parallel:
+            s *= transformer_config.tensor_model_parallel_size
+        return s * transformer_config.context_parallel_size
+
+    def forward(self, max_seq_len: int, offset: int = 0, device=None) -> torch.Tensor:
+        device = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu")
+        key = (max_seq_len, offset, str(device))
+        t = self._cache.get(key)
+        if t is None:
+            pos = torch.arange(max_seq_len, dtype=torch.float32, device=device) + offset
+            if self.seq_len_interpolation_factor is not None:
+                pos = pos / self.seq_len_interpolation_factor
+            ang = torch.outer(pos, self.inv_freq.to(device))
+            t = torch.cat([ang.cos(), ang.sin()], dim=-1).contiguous()
+            if len(self._cache) > 8:
+                self._cache.clear()
+            self._cache[key] = t
+        return t
+
+
+class YarnRotaryEmbedding(RotaryEmbedding):
+    """YaRN: NTK-by-parts interpolation of the rotary frequencies + attention temperature."""
+
+    def __init__(self, kv_channels, rotary_percent=1.0, rotary_interleaved=False,
+                 seq_len_interpolation_factor=None, rotary_base=10000.0, scaling_factor=1.0,
+                 original_max_position_embeddings=4096, beta_fast=32.0, beta_slow=1.0, mscale=1.0,
+                 mscale_all_dim=0.0, use_cpu_initialization=False):
+        super().__init__(kv_channels, rotary_percent, rotary_interleaved, seq_len_interpolation_factor, rotary_base)
+        dim = self.dim
+
+        def corr_dim(num_rot):
+            return (dim * math.log(original_max_position_embeddings / (num_rot * 2 * math.pi))) / (2 * math.log(rotary_base))
+
+        low = max(math.floor(corr_dim(beta_fast)), 0)
+        high = min(math.ceil(corr_dim(beta_slow)), dim - 1)
+        ramp = ((torch.arange(dim // 2, dtype=torch.float32) - low) / max(high - low, 1e-3)).clamp(0, 1)
+        extra = 1.0 / (rotary_base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim))
+        inter = extra / scaling_factor
+        mask = 1.0 - ramp
+        self.register_buffer("inv_freq", inter * (1 - mask) + extra * mask, persistent=False)
+
+        def get_mscale(scale, m):
+            return 1.0 if scale <= 1 else 0.1 * m * math.log(scale) + 1.0
+
+        self.concentration = get_mscale(scaling_factor, mscale) / get_mscale(scaling_factor, mscale_all_dim)
+
+    def forward(self, max_seq_len, offset=0, device=None):
+        t = super().forward(max_seq_len, offset, device)
+        return t * self.concentration if self.concentration != 1.0 else t

@@ -1,0 +1,53 @@
+"""Shared behaviour of language models: loss computation and tied-embedding setup.
+
+Parity: reference ``models/common/language_module/language_module.py``
+(``compute_language_model_loss``, ``setup_embeddings_and_output_layer``,
+``shared_embedding_or_output_weight``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ...parallel import state as ps
+from ...parallel.cross_entropy import vocab_parallel_cross_entropy
+from ...transformer.module import MegatronModule
+
+
+class LanguageModule(MegatronModule):
+    def compute_language_model_loss(self, labels: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+        # labels [b, s] -> [s, b]; logits [s, b, V/tp]
+        labels = labels.transpose(0, 1).contiguous()
+        loss = vocab_parallel_cross_entropy(logits, labels)
+        return loss.transpose(0, 1).contiguous()  # [b, s]
+
+    def setup_embeddings_and_output_layer(self) -> None:
+        if self.pre_process:
+            self.embedding.word_embeddings.weight.is_embedding_or_output_parameter = True
+        if self.post_process and getattr(self, "output_layer", None) is not None and self.output_layer.weight is not None:
+            self.output_layer.weight.is_embedding_or_output_parameter = True
+        if not self.share_embeddings_and_output_weights:
+            return
+        if ps.get_pipeline_model_parallel_world_size() == 1:
+            self.shared_embedding_or_output_weight().zero_out_wgrad = True
+            return
+        if ps.is_pipeline_first_stage() and self.pre_process and not self.post_process:
+            self.shared_embedding_or_output_weight().shared_embedding = True
+        if self.post_process and not self.pre_process:
+            # last stage keeps its own copy of the word embedding for the output layer,
+            # initialised to zero and filled by an all-reduce with the first stage
+            self.output_layer.weight.data.fill_(0)
+            self.output_layer.weight.shared = True
+            self.output_layer.weight.shared_embedding = True
+        if dist.is_initialized() and ps.is_rank_in_embedding_group():
+            w = self.shared_embedding_or_output_weight()
+            g = ps.get_embedding_group()
+            if g is not None and not isinstance(g, ps._SingleGroup):
+                dist.all_reduce(w.data, group=g)
+
+    def shared_embedding_or_output_weight(self):
+        if self.pre_process:
+            return self.embedding.word_embeddings.weight
+        if self.post_process:
+            return self.output_layer.weight
+        return None

@@ -1,0 +1,154 @@
+"""Pipeline point-to-point transport: unidirectional NCCL/gloo channels.
+
+Capability parity with reference ``core/pipeline_parallel/p2p_communication.py`` (send/recv of
+``[s/(tp if SP), b, h]`` activations and gradients between adjacent stages, optional shape
+handshake, MegaScan ``send-*``/``recv-*`` scopes with ``data`` bytes, FBD twin transfers
+:723-756) -- but instead of ``batch_isend_irecv`` with even/odd ordering tricks, every directed
+edge of the pipeline ring gets its own 2-rank communicator ("channel").  A channel carries
+messages in one direction only, so a blocked send can never sit in front of a receive on the
+same NCCL stream: any schedule whose data-flow graph is acyclic -- 1F1B, interleaved, the
+MegaFBD forward/backward split, MegaDPP's dynamic order -- is deadlock-free by construction,
+without the runtime coordinator the reference needs for FBD (``Controller.py``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import state as ps
+from ..scan.tracer import scope as _scope
+
+_CHANNELS: Dict[Tuple[int, int, str], object] = {}
+_PENDING: Dict[Tuple[int, int, str], Tuple[object, torch.Tensor]] = {}
+
+
+def build_channels() -> None:
+    """Create one group per directed neighbour edge and traffic class; collective over WORLD."""
+    _CHANNELS.clear()
+    if not (dist.is_available() and dist.is_initialized()) or not ps.model_parallel_is_initialized():
+        return
+    topo = ps.get_topology()
+    edges: List[Tuple[int, int, str]] = []
+    for g in topo.groups("pp"):
+        n = len(g)
+        if n < 2:
+            continue
+        for i in range(n):
+            a, b = g[i], g[(i + 1) % n]
+            edges.append((a, b, "fwd"))   # activations a -> b
+            edges.append((b, a, "bwd"))   # gradients  b -> a
+    if topo.fbd:
+        for a, b in topo.groups("fb"):
+            edges.append((a, b, "fbd"))   # forward rank -> backward twin (stage inputs)
+    seen = set()
+    for a, b, kind in edges:
+        if (a, b, kind) in seen:
+            continue
+        seen.add((a, b, kind))
+        grp = dist.new_group(ranks=sorted({a, b}))
+        _CHANNELS[(a, b, kind)] = grp
+
+
+def destroy_channels() -> None:
+    _CHANNELS.clear()
+    _PENDING.clear()
+
+
+def _channel(src: int, dst: int, kind: str):
+    key = (src, dst, kind)
+    if key not in _CHANNELS:
+        raise RuntimeError(f"no p2p channel {key}; call build_channels() after initialize_model_parallel()")
+    return _CHANNELS[key]
+
+
+def send(tensor: torch.Tensor, dst: int, kind: str, name: str = "send") -> None:
+    """Asynchronous send; at most one message in flight per channel (the previous one is
+    waited for first, which also bounds the lifetime of its tensor)."""
+    me = dist.get_rank()
+    key = (me, dst, kind)
+    prev = _PENDING.pop(key, None)
+    if prev is not None:
+        prev[0].wait()
+    t = tensor.contiguous()
+    with _scope(name, data=t.numel() * t.element_size(), peer=dst):
+        h = dist.isend(t, dst=dst, group=_channel(me, dst, kind))
+    _PENDING[key] = (h, t)
+
+
+def recv(shape, dtype, src: int, kind: str, name: str = "recv", device=None, requires_grad: bool = False):
+    me = dist.get_rank()
+    device = device or (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu")
+    buf = torch.empty(shape, dtype=dtype, device=device, requires_grad=False)
+    with _scope(name, data=buf.numel() * buf.element_size(), peer=src):
+        dist.irecv(buf, src=src, group=_channel(src, me, kind)).wait()
+    if requires_grad:
+        buf.requires_grad_(True)
+    return buf
+
+
+def flush() -> None:
+    for key in list(_PENDING):
+        h, _ = _PENDING.pop(key)
+        h.wait()
+
+
+# ---- Megatron-named helpers (non-interleaved convenience API) ---------------------------
+
+def _shape(config, tensor_shape):
+    return tuple(tensor_shape)
+
+
+def recv_forward(tensor_shape, config):
+    if ps.is_pipeline_first_stage(ignore_virtual=True):
+        return None
+    return recv(tensor_shape, config.pipeline_dtype, ps.get_pipeline_model_parallel_prev_rank(), "fwd",
+                "recv-forward", requires_grad=True)
+
+
+def recv_backward(tensor_shape, config):
+    if ps.is_pipeline_last_stage(ignore_virtual=True):
+        return None
+    return recv(tensor_shape, config.pipeline_dtype, ps.get_pipeline_model_parallel_next_rank(), "bwd",
+                "recv-backward")
+
+
+def send_forward(output_tensor, config):
+    if not ps.is_pipeline_last_stage(ignore_virtual=True):
+        send(output_tensor, ps.get_pipeline_model_parallel_next_rank(), "fwd", "send-forward")
+
+
+def send_backward(input_tensor_grad, config):
+    if not ps.is_pipeline_first_stage(ignore_virtual=True):
+        send(input_tensor_grad, ps.get_pipeline_model_parallel_prev_rank(), "bwd", "send-backward")
+
+
+def send_forward_recv_backward(output_tensor, tensor_shape, config):
+    send_forward(output_tensor, config)
+    return recv_backward(tensor_shape, config)
+
+
+def send_backward_recv_forward(input_tensor_grad, tensor_shape, config):
+    send_backward(input_tensor_grad, config)
+    return recv_forward(tensor_shape, config)
+
+
+def send_corresponding_forward(tensor, config=None):
+    """MegaFBD: forward rank ships a stage input to its backward twin."""
+    send(tensor, ps.get_twin_rank(), "fbd", "fbd-send")
+
+
+def recv_corresponding_forward(tensor_shape, dtype):
+    return recv(tensor_shape, dtype, ps.get_twin_rank(), "fbd", "fbd-recv", requires_grad=True)
+
+
+def communicate_shapes(tensor: Optional[torch.Tensor], src_or_dst: int, kind: str, sending: bool):
+    """3-int64 shape handshake for ``variable_seq_lengths`` (reference :27-122)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+    if sending:
+        s = torch.tensor(list(tensor.shape) + [0] * (3 - tensor.dim()), dtype=torch.int64, device=dev)
+        send(s, src_or_dst, kind, "send-shape")
+        return tuple(tensor.shape)
+    s = recv((3,), torch.int64, src_or_dst, kind, "recv-shape", device=dev)
+    return tuple(int(v) for v in s.tolist() if v > 0)

@@ -1,0 +1,329 @@
+"""Forward/backward schedules: no pipelining, 1F1B, interleaved 1F1B -- as *task lists*.
+
+API parity with reference ``core/pipeline_parallel/schedules.py``:
+``get_forward_backward_func()`` (:28-117) returns a callable taking ``forward_step_func,
+data_iterator, model, num_microbatches, seq_length, micro_batch_size, decoder_seq_length,
+forward_only, collect_non_loss_data, first_val_step``; ``forward_step`` / ``backward_step``
+(:179-303, :533-610) keep the ``(output_tensor, loss_func)`` protocol; warm-up counts and the
+interleaved visiting order follow ``get_schedule_table`` (:758-853).
+
+Design: a schedule is a pure function ``(pp, rank, M, C, G) -> [Task]`` (unit-testable without a
+process group); ONE executor runs any task list over the unidirectional p2p channels of
+``parallel/p2p.py``.  MegaDPP (``dpp/scheduler.py``) swaps the static list for a ready-queue,
+MegaFBD (``fbd/schedule.py``) splits it across forward/backward twins -- same executor.
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterator, List, Optional, Tuple, Union
+
+import torch
+
+from . import p2p
+from . import state as ps
+from ..scan.tracer import scope as _scope
+
+
+@dataclass(frozen=True)
+class Task:
+    kind: str        # "F" | "B"
+    microbatch: int
+    chunk: int = 0
+
+
+# ---------------------------------------------------------------------------
+# pure schedule generators
+# ---------------------------------------------------------------------------
+
+def schedule_no_pipelining(M: int, forward_only: bool = False) -> List[Task]:
+    out = []
+    for m in range(M):
+        out.append(Task("F", m))
+        if not forward_only:
+            out.append(Task("B", m))
+    return out
+
+
+def schedule_1f1b(pp: int, rank: int, M: int, forward_only: bool = False) -> List[Task]:
+    if forward_only:
+        return [Task("F", m) for m in range(M)]
+    warm = min(pp - rank - 1, M)
+    out = [Task("F", m) for m in range(warm)]
+    f, b = warm, 0
+    for _ in range(M - warm):
+        out.append(Task("F", f)); f += 1
+        out.append(Task("B", b)); b += 1
+    while b < M:
+        out.append(Task("B", b)); b += 1
+    return out
+
+
+def get_schedule_table(M: int, C: int, G: int) -> List[Tuple[int, int]]:
+    """Virtual-microbatch visiting order: for each group of G microbatches, for each chunk, for
+    each microbatch of the group -> (microbatch, chunk)."""
+    table = []
+    for g0 in range(0, M, G):
+        g1 = min(M, g0 + G)
+        for c in range(C):
+            for m in range(g0, g1):
+                table.append((m, c))
+    return table
+
+
+def interleaved_warmup(pp: int, rank: int, M: int, C: int, G: int) -> int:
+    total = M * C
+    return min(total, (pp - rank - 1) * 2 + (C - 1) * G)
+
+
+def validate_interleaved(pp: int, M: int, C: int, G: int) -> None:
+    if not (pp <= G <= M):
+        raise ValueError(f"need pp <= microbatch_group_size_per_vp_stage <= num_microbatches (pp={pp}, G={G}, M={M})")
+    r = M % G
+    if not (r == 0 or pp <= r < G):
+        raise ValueError(f"num_microbatches % group_size must be 0 or in [pp, G): M={M}, G={G}, pp={pp}")
+
+
+def schedule_interleaved(pp: int, rank: int, M: int, C: int, G: Optional[int] = None,
+                         forward_only: bool = False) -> List[Task]:
+    G = pp if G is None else G
+    validate_interleaved(pp, M, C, G)
+    table = get_schedule_table(M, C, G)
+    total = len(table)
+    if forward_only:
+        return [Task("F", m, c) for m, c in table]
+    warm = interleaved_warmup(pp, rank, M, C, G)
+    out = [Task("F", *table[k]) for k in range(warm)]
+    f, b = warm, 0
+    for _ in range(total - warm):
+        out.append(Task("F", *table[f])); f += 1
+        m, c = table[b]
+        out.append(Task("B", m, C - 1 - c)); b += 1
+    while b < total:
+        m, c = table[b]
+        out.append(Task("B", m, C - 1 - c)); b += 1
+    return out
+
+
+# ---------------------------------------------------------------------------
+# forward / backward steps
+# ---------------------------------------------------------------------------
+
+def deallocate_output_tensor(out: Optional[torch.Tensor], deallocate_pipeline_outputs: bool = False) -> None:
+    """Pseudo-free an activation that was already sent downstream: only its ``grad_fn`` is
+    needed for backward, so replace ``.data`` with a scalar."""
+    if out is None or not deallocate_pipeline_outputs:
+        return
+    out.data = torch.empty((1,), device=out.device, dtype=out.dtype)
+
+
+def custom_backward(output: torch.Tensor, grad_output: Optional[torch.Tensor]) -> None:
+    """Backward that tolerates a deallocated ``output`` (shape check bypassed by calling the
+    engine directly)."""
+    if grad_output is None:
+        grad_output = torch.ones_like(output, memory_format=torch.preserve_format)
+    torch.autograd.Variable._execution_engine.run_backward(
+        tensors=(output,), grad_tensors=(grad_output,), keep_graph=False, create_graph=False,
+        inputs=tuple(), allow_unreachable=True, accumulate_grad=True)
+
+
+def forward_step(forward_step_func, data_iterator, model, num_microbatches, input_tensor, forward_data_store,
+                 config, collect_non_loss_data=False, checkpoint_activations_microbatch=None,
+                 is_first_microbatch=False, current_microbatch=None, is_last_stage=None):
+    if is_first_microbatch and hasattr(model, "set_is_first_microbatch"):
+        model.set_is_first_microbatch()
+    unwrap = model
+    while hasattr(unwrap, "module") and not hasattr(unwrap, "set_input_tensor"):
+        unwrap = unwrap.module
+    model.set_input_tensor(input_tensor) if hasattr(model, "set_input_tensor") else unwrap.set_input_tensor(input_tensor)
+    ctx = torch.autocast("cuda", dtype=config.autocast_dtype) if config.enable_autocast else contextlib.nullcontext()
+    with _scope("forward", microbatch=current_microbatch), ctx:
+        output_tensor, loss_func = forward_step_func(data_iterator, model)
+    last = ps.is_pipeline_last_stage() if is_last_stage is None else is_last_stage
+    num_tokens = torch.tensor(0, dtype=torch.int)
+    if last:
+        if not collect_non_loss_data:
+            with _scope("loss"):
+                outputs = loss_func(output_tensor)
+            if len(outputs) == 3:
+                output_tensor, num_tokens, loss_reduced = outputs
+                if not config.calculate_per_token_loss:
+                    output_tensor = output_tensor / num_tokens
+                    output_tensor = output_tensor / num_microbatches
+            else:
+                output_tensor, loss_reduced = outputs
+                output_tensor = output_tensor / num_microbatches
+            forward_data_store.append(loss_reduced)
+        else:
+            forward_data_store.append(loss_func(output_tensor, non_loss_data=True))
+    return output_tensor, num_tokens
+
+
+def backward_step(input_tensor, output_tensor, output_tensor_grad, model_type, config, microbatch=None):
+    if input_tensor is not None and input_tensor.requires_grad:
+        input_tensor.retain_grad()
+    with _scope("backward", microbatch=microbatch):
+        if output_tensor_grad is None and config.grad_scale_func is not None:
+            output_tensor = config.grad_scale_func(output_tensor)
+        if config.deallocate_pipeline_outputs:
+            custom_backward(output_tensor, output_tensor_grad)
+        else:
+            torch.autograd.backward(output_tensor, grad_tensors=output_tensor_grad)
+    return None if input_tensor is None else input_tensor.grad
+
+
+# ---------------------------------------------------------------------------
+# the executor
+# ---------------------------------------------------------------------------
+
+def _get_config(model):
+    m = model
+    while hasattr(m, "module"):
+        m = m.module
+    return m.config
+
+
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def get_tensor_shapes(seq_length, micro_batch_size, config) -> Tuple[int, int, int]:
+    s = seq_length // max(1, config.context_parallel_size)
+    if config.sequence_parallel:
+        s = s // config.tensor_model_parallel_size
+    return (s, micro_batch_size, config.hidden_size)
+
+
+def run_tasks(tasks: List[Task], *, forward_step_func, data_iterator, model: List, num_microbatches: int,
+              seq_length: int, micro_batch_size: int, forward_only: bool, collect_non_loss_data: bool,
+              first_val_step=None, on_task: Optional[Callable] = None):
+    """Execute a task list on this pipeline rank."""
+    chunks = _as_list(model)
+    C = len(chunks)
+    iters = _as_list(data_iterator) if data_iterator is not None else [None] * C
+    if len(iters) != C:
+        iters = iters * C
+    config = _get_config(chunks[0])
+    pp = ps.get_pipeline_model_parallel_world_size()
+    rank = ps.get_pipeline_model_parallel_rank()
+    shape = get_tensor_shapes(seq_length, micro_batch_size, config)
+    dtype = config.pipeline_dtype or config.params_dtype
+    prev_r = ps.get_pipeline_model_parallel_prev_rank() if pp > 1 else None
+    next_r = ps.get_pipeline_model_parallel_next_rank() if pp > 1 else None
+    forward_data_store: List = []
+    total_num_tokens = torch.zeros((), dtype=torch.int, device=next(chunks[0].parameters()).device)
+    stash: Dict[Tuple[int, int], Tuple] = {}
+    last_b = {c: max((t.microbatch for t in tasks if t.kind == "B" and t.chunk == c), default=-1) for c in range(C)}
+    first_f_done = [False] * C
+    vpp = C if C > 1 else None
+
+    def is_first(c):
+        return rank == 0 and c == 0
+
+    def is_last(c):
+        return rank == pp - 1 and c == C - 1
+
+    for chunk in chunks:
+        if hasattr(chunk, "is_last_microbatch"):
+            chunk.is_last_microbatch = False
+    for t in tasks:
+        c = t.chunk
+        if vpp:
+            ps.set_virtual_pipeline_model_parallel_rank(c)
+        if on_task is not None:
+            on_task(t)
+        if t.kind == "F":
+            inp = None
+            if pp > 1 and not is_first(c):
+                inp = p2p.recv(shape, dtype, prev_r, "fwd", "recv-forward", requires_grad=not forward_only)
+            ctx = torch.no_grad() if forward_only else contextlib.nullcontext()
+            with ctx:
+                out, ntok = forward_step(forward_step_func, iters[c], chunks[c], num_microbatches, inp,
+                                         forward_data_store, config, collect_non_loss_data,
+                                         is_first_microbatch=not first_f_done[c], current_microbatch=t.microbatch,
+                                         is_last_stage=is_last(c))
+            first_f_done[c] = True
+            total_num_tokens += ntok.to(total_num_tokens.device) if torch.is_tensor(ntok) else int(ntok)
+            if pp > 1 and not is_last(c):
+                p2p.send(out, next_r, "fwd", "send-forward")
+                if not forward_only:
+                    deallocate_output_tensor(out, config.deallocate_pipeline_outputs)
+            if not forward_only:
+                stash[(t.microbatch, c)] = (inp, out)
+        else:
+            inp, out = stash.pop((t.microbatch, c))
+            grad = None
+            if pp > 1 and not is_last(c):
+                grad = p2p.recv(shape, dtype, next_r, "bwd", "recv-backward")
+            if hasattr(chunks[c], "is_last_microbatch"):
+                chunks[c].is_last_microbatch = (t.microbatch == last_b[c])
+            in_grad = backward_step(inp, out, grad, None, config, microbatch=t.microbatch)
+            if pp > 1 and not is_first(c):
+                p2p.send(in_grad, prev_r, "bwd", "send-backward")
+    if pp > 1:
+        p2p.flush()
+    if vpp:
+        ps.set_virtual_pipeline_model_parallel_rank(0)
+    for chunk in chunks:
+        if hasattr(chunk, "is_last_microbatch"):
+            chunk.is_last_microbatch = True
+    if not forward_only and config.finalize_model_grads_func is not None:
+        config.finalize_model_grads_func(chunks, total_num_tokens if config.calculate_per_token_loss else None)
+    return forward_data_store
+
+
+def forward_backward_no_pipelining(*, forward_step_func, data_iterator, model, num_microbatches, seq_length,
+                                   micro_batch_size, decoder_seq_length=None, forward_only=False,
+                                   collect_non_loss_data=False, first_val_step=None):
+    return run_tasks(schedule_no_pipelining(num_microbatches, forward_only), forward_step_func=forward_step_func,
+                     data_iterator=data_iterator, model=model, num_microbatches=num_microbatches,
+                     seq_length=seq_length, micro_batch_size=micro_batch_size, forward_only=forward_only,
+                     collect_non_loss_data=collect_non_loss_data, first_val_step=first_val_step)
+
+
+def forward_backward_pipelining_without_interleaving(*, forward_step_func, data_iterator, model, num_microbatches,
+                                                     seq_length, micro_batch_size, decoder_seq_length=None,
+                                                     forward_only=False, collect_non_loss_data=False,
+                                                     first_val_step=None):
+    tasks = schedule_1f1b(ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_rank(),
+                          num_microbatches, forward_only)
+    return run_tasks(tasks, forward_step_func=forward_step_func, data_iterator=data_iterator, model=model,
+                     num_microbatches=num_microbatches, seq_length=seq_length, micro_batch_size=micro_batch_size,
+                     forward_only=forward_only, collect_non_loss_data=collect_non_loss_data,
+                     first_val_step=first_val_step)
+
+
+def forward_backward_pipelining_with_interleaving(*, forward_step_func, data_iterator, model, num_microbatches,
+                                                  seq_length, micro_batch_size, decoder_seq_length=None,
+                                                  forward_only=False, collect_non_loss_data=False,
+                                                  first_val_step=None):
+    chunks = _as_list(model)
+    config = _get_config(chunks[0])
+    tasks = schedule_interleaved(ps.get_pipeline_model_parallel_world_size(),
+                                 ps.get_pipeline_model_parallel_rank(), num_microbatches, len(chunks),
+                                 config.microbatch_group_size_per_vp_stage, forward_only)
+    return run_tasks(tasks, forward_step_func=forward_step_func, data_iterator=data_iterator, model=model,
+                     num_microbatches=num_microbatches, seq_length=seq_length, micro_batch_size=micro_batch_size,
+                     forward_only=forward_only, collect_non_loss_data=collect_non_loss_data,
+                     first_val_step=first_val_step)
+
+
+_SCHEDULE_OVERRIDE: Optional[Callable] = None
+
+
+def set_schedule_override(fn: Optional[Callable]) -> None:
+    """MegaFBD / MegaDPP install their schedule here (``--forward-backward-disaggregating``,
+    ``--use-dpp``) without the core importing the training harness."""
+    global _SCHEDULE_OVERRIDE
+    _SCHEDULE_OVERRIDE = fn
+
+
+def get_forward_backward_func():
+    if _SCHEDULE_OVERRIDE is not None:
+        return _SCHEDULE_OVERRIDE
+    pp = ps.get_pipeline_model_parallel_world_size()
+    if pp > 1:
+        if ps.get_virtual_pipeline_model_parallel_world_size() is not None:
+            return forward_backward_pipelining_with_interleaving
+        return forward_backward_pipelining_without_interleaving
+    return forward_backward_no_pipelining

@@ -1,0 +1,279 @@
+"""Checkpoint save / load in the Megatron layout.
+
+Parity: reference ``training/checkpointing.py`` -- tracker ``latest_checkpointed_iteration.txt``
+(:222-226), directory ``iter_{:07d}`` (:121-124), legacy ``torch`` format
+``mp_rank_{tp:02d}[_{pp:03d}][_{ep:03d}]/model_optim_rng.pt`` (+ ``distrib_optim.pt``)
+(:152-168) with state-dict keys ``args, checkpoint_version (3.0), iteration, model | model{i},
+optimizer, opt_param_scheduler, rng_state, num_floating_point_operations_so_far``
+(:729-780); ``torch_dist`` = sharded checkpoint with resharding (``ckpt/sharded.py``);
+``--async-save`` hands the CPU copy to a background writer; MegaFBD forces the per-rank format.
+"""
+from __future__ import annotations
+
+import os
+import random
+import threading
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..ckpt import sharded
+from ..parallel import state as ps
+from ..parallel.random import get_cuda_rng_tracker
+
+_CHECKPOINT_VERSION = 3.0
+_ASYNC_THREADS: List[threading.Thread] = []
+
+
+def get_checkpoint_tracker_filename(checkpoints_path):
+    return os.path.join(checkpoints_path, "latest_checkpointed_iteration.txt")
+
+
+def get_checkpoint_name(checkpoints_path, iteration, release=False, pipeline_parallel=None, tensor_rank=None,
+                        pipeline_rank=None, expert_parallel=None, expert_rank=None, return_base_dir=False,
+                        basename="model_optim_rng.pt"):
+    directory = "release" if release else "iter_{:07d}".format(iteration)
+    base = os.path.join(checkpoints_path, directory)
+    if return_base_dir:
+        return base
+    if pipeline_parallel is None:
+        pipeline_parallel = ps.get_pipeline_model_parallel_world_size() > 1
+    if tensor_rank is None:
+        tensor_rank = ps.get_tensor_model_parallel_rank()
+    if pipeline_rank is None:
+        pipeline_rank = ps.get_pipeline_model_parallel_rank()
+    if expert_parallel is None:
+        expert_parallel = ps.get_expert_model_parallel_world_size() > 1
+    if expert_rank is None:
+        expert_rank = ps.get_expert_model_parallel_rank()
+    name = f"mp_rank_{tensor_rank:02d}"
+    if pipeline_parallel:
+        name += f"_{pipeline_rank:03d}"
+    if expert_parallel:
+        name += f"_{expert_rank:03d}"
+    return os.path.join(base, name, basename)
+
+
+def read_metadata(tracker_filename):
+    with open(tracker_filename) as f:
+        s = f.read().strip()
+    if s == "release":
+        return 0, True
+    return int(s), False
+
+
+def get_rng_state():
+    st = {"random_rng_state": random.getstate(), "np_rng_state": np.random.get_state(),
+          "torch_rng_state": torch.get_rng_state(),
+          "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
+          "rng_tracker_states": get_cuda_rng_tracker().get_states()}
+    return [st]
+
+
+def _unwrap(m):
+    while hasattr(m, "module"):
+        m = m.module
+    return m
+
+
+def generate_state_dict(args, model, optimizer, opt_param_scheduler, rng_state, iteration=None,
+                        num_floating_point_operations_so_far=0, model_sd_fn=None):
+    sd = {"args": args, "checkpoint_version": _CHECKPOINT_VERSION}
+    if iteration is not None:
+        sd["iteration"] = iteration
+    fn = model_sd_fn or (lambda m: m.state_dict_for_save_checkpoint())
+    if len(model) == 1:
+        sd["model"] = fn(model[0])
+    else:
+        for i, m in enumerate(model):
+            sd[f"model{i}"] = fn(m)
+    if not getattr(args, "no_save_optim", False):
+        if optimizer is not None:
+            sd["optimizer"] = optimizer.state_dict()
+        if opt_param_scheduler is not None:
+            sd["opt_param_scheduler"] = opt_param_scheduler.state_dict()
+    if not getattr(args, "no_save_rng", False):
+        sd["rng_state"] = rng_state
+    sd["num_floating_point_operations_so_far"] = num_floating_point_operations_so_far
+    return sd
+
+
+def _to_cpu(obj):
+    if torch.is_tensor(obj):
+        return obj.detach().to("cpu", copy=True)
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj
+
+
+def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far=0,
+                    args=None, checkpointing_context=None):
+    if args is None:
+        from .global_vars import get_args
+
+        args = get_args()
+    model = model if isinstance(model, (list, tuple)) else [model]
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    base = get_checkpoint_name(args.save, iteration, return_base_dir=True)
+    fmt = args.ckpt_format
+    rng_state = get_rng_state()
+    if fmt == "torch":
+        dp_rank = ps.get_data_parallel_rank(with_context_parallel=True)
+        name = get_checkpoint_name(args.save, iteration)
+        sharded_opt = optimizer is not None and getattr(optimizer, "sharded", False)
+        if dp_rank == 0 or sharded_opt or args.forward_backward_disaggregating:
+            os.makedirs(os.path.dirname(name), exist_ok=True)
+        if dp_rank == 0 or args.forward_backward_disaggregating:
+            sd = generate_state_dict(args, model, None if sharded_opt else optimizer, opt_param_scheduler,
+                                     rng_state, iteration, num_floating_point_operations_so_far)
+            sd = _to_cpu(sd)
+            _write(sd, name, args.async_save)
+        if sharded_opt and not args.no_save_optim:
+            oname = os.path.join(os.path.dirname(name), f"distrib_optim.pt" if dp_rank == 0 else f"distrib_optim_dp{dp_rank:03d}.pt")
+            _write(_to_cpu(optimizer.state_dict()), oname, args.async_save)
+    else:
+        ssd = {}
+        for i, m in enumerate(model):
+            prefix = "" if len(model) == 1 else f"model{i}."
+            ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
+        common = {"args": args, "checkpoint_version": _CHECKPOINT_VERSION, "iteration": iteration,
+                  "num_floating_point_operations_so_far": num_floating_point_operations_so_far,
+                  "opt_param_scheduler": opt_param_scheduler.state_dict() if opt_param_scheduler else None,
+                  "rng_state": rng_state}
+        sharded.save(ssd, base, common)
+        if optimizer is not None and not args.no_save_optim:
+            torch.save(_to_cpu(optimizer.state_dict()), os.path.join(base, f"optim_{rank:05d}.pt"))
+    if dist.is_initialized():
+        dist.barrier()
+    if rank == 0:
+        with open(get_checkpoint_tracker_filename(args.save), "w") as f:
+            f.write(str(iteration))
+        print(f"  successfully saved checkpoint from iteration {iteration:7d} to {args.save}", flush=True)
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def _write(obj, path, async_save):
+    if async_save:
+        t = threading.Thread(target=torch.save, args=(obj, path), daemon=False)
+        t.start()
+        _ASYNC_THREADS.append(t)
+    else:
+        torch.save(obj, path)
+
+
+def maybe_finalize_async_save(blocking: bool = False):
+    for t in list(_ASYNC_THREADS):
+        if blocking:
+            t.join()
+        if not t.is_alive():
+            _ASYNC_THREADS.remove(t)
+
+
+def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", strict=True, args=None):
+    if args is None:
+        from .global_vars import get_args
+
+        args = get_args()
+    load_dir = getattr(args, load_arg)
+    model = model if isinstance(model, (list, tuple)) else [model]
+    tracker = get_checkpoint_tracker_filename(load_dir) if load_dir else None
+    if not load_dir or not os.path.isfile(tracker):
+        if getattr(args, "exit_on_missing_checkpoint", False):
+            raise SystemExit(f">> no checkpoint found in {load_dir}; exiting")
+        return 0, 0
+    iteration, release = read_metadata(tracker)
+    if getattr(args, "ckpt_step", None):
+        iteration = args.ckpt_step
+    base = get_checkpoint_name(load_dir, iteration, release, return_base_dir=True)
+    is_sharded = os.path.exists(os.path.join(base, "metadata.json"))
+    if is_sharded:
+        ssd = {}
+        for i, m in enumerate(model):
+            prefix = "" if len(model) == 1 else f"model{i}."
+            ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
+        sharded.load(ssd, base, strict=strict)
+        sd = sharded.load_common_state_dict(base)
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        op = os.path.join(base, f"optim_{rank:05d}.pt")
+        if optimizer is not None and not args.finetune and not args.no_load_optim and os.path.exists(op):
+            optimizer.load_state_dict(torch.load(op, map_location="cpu", weights_only=False))
+        elif optimizer is not None:
+            optimizer.reload_model_params()
+    else:
+        name = get_checkpoint_name(load_dir, iteration, release)
+        sd = torch.load(name, map_location="cpu", weights_only=False)
+        if len(model) == 1:
+            _unwrap(model[0]).load_state_dict(sd["model"], strict=strict)
+        else:
+            for i, m in enumerate(model):
+                _unwrap(m).load_state_dict(sd[f"model{i}"], strict=strict)
+        if optimizer is not None and not args.finetune and not args.no_load_optim:
+            dp_rank = ps.get_data_parallel_rank(with_context_parallel=True)
+            dop = os.path.join(os.path.dirname(name), "distrib_optim.pt" if dp_rank == 0 else f"distrib_optim_dp{dp_rank:03d}.pt")
+            if "optimizer" in sd:
+                optimizer.load_state_dict(sd["optimizer"])
+            elif os.path.exists(dop):
+                optimizer.load_state_dict(torch.load(dop, map_location="cpu", weights_only=False))
+            else:
+                optimizer.reload_model_params()
+        elif optimizer is not None:
+            optimizer.reload_model_params()
+    if opt_param_scheduler is not None and sd.get("opt_param_scheduler") and not args.finetune:
+        opt_param_scheduler.load_state_dict(sd["opt_param_scheduler"])
+    if not release and not args.finetune and not args.no_load_rng and sd.get("rng_state"):
+        try:
+            st = sd["rng_state"][0]
+            random.setstate(st["random_rng_state"])
+            np.random.set_state(st["np_rng_state"])
+            torch.set_rng_state(st["torch_rng_state"])
+            if torch.cuda.is_available() and st.get("cuda_rng_state") is not None:
+                torch.cuda.set_rng_state(st["cuda_rng_state"])
+            if st.get("rng_tracker_states"):
+                get_cuda_rng_tracker().set_states(st["rng_tracker_states"])
+        except Exception as e:  # noqa: BLE001
+            print(f"WARNING: could not restore rng state: {e}", flush=True)
+    if args.finetune or release:
+        iteration = 0
+    else:
+        ca = sd.get("args")
+        if ca is not None:
+            args.consumed_train_samples = getattr(ca, "consumed_train_samples", 0)
+            args.consumed_valid_samples = getattr(ca, "consumed_valid_samples", 0)
+    if dist.is_initialized():
+        dist.barrier()
+    print(f"  successfully loaded checkpoint from {load_dir} at iteration {iteration}", flush=True) \
+        if (not dist.is_initialized() or dist.get_rank() == 0) else None
+    return iteration, sd.get("num_floating_point_operations_so_far", 0)
+
+
+def load_args_from_checkpoint(args, load_arg="load"):
+    load_dir = getattr(args, load_arg)
+    tracker = get_checkpoint_tracker_filename(load_dir)
+    if not os.path.isfile(tracker):
+        return args
+    iteration, release = read_metadata(tracker)
+    base = get_checkpoint_name(load_dir, iteration, release, return_base_dir=True)
+    if os.path.exists(os.path.join(base, "common.pt")):
+        sd = sharded.load_common_state_dict(base)
+    else:
+        name = get_checkpoint_name(load_dir, iteration, release, tensor_rank=0, pipeline_rank=0,
+                                   pipeline_parallel=os.path.isdir(os.path.join(base, "mp_rank_00_000")),
+                                   expert_parallel=False, expert_rank=0)
+        sd = torch.load(name, map_location="cpu", weights_only=False)
+    ca = sd.get("args")
+    if ca is None:
+        return args
+    for k in ("num_layers", "hidden_size", "ffn_hidden_size", "seq_length", "num_attention_heads", "num_query_groups",
+              "group_query_attention", "kv_channels", "max_position_embeddings", "position_embedding_type",
+              "add_position_embedding", "use_rotary_position_embeddings", "rotary_base", "rotary_percent",
+              "add_bias_linear", "add_qkv_bias", "swiglu", "untie_embeddings_and_output_weights",
+              "apply_layernorm_1p", "normalization", "tokenizer_type", "padded_vocab_size", "apply_query_key_layer_scaling",
+              "num_experts", "moe_router_topk"):
+        if hasattr(ca, k):
+            setattr(args, k, getattr(ca, k))
+    return args

@@ -1,0 +1,94 @@
+"""Process-wide singletons of the training harness (args, tokenizer, timers, writers, tracer).
+
+Parity: reference ``training/global_vars.py`` (``get_args`` :27, ``get_timers`` :61,
+``get_tracer`` :71, ``set_global_variables`` :88).  Only the *harness* reads these -- the core
+(parallel/, transformer/, models/) never calls ``get_args()``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+from ..scan.tracer import get_tracer as _get_tracer
+from ..utils.timers import Timers
+
+_ARGS = None
+_TOKENIZER = None
+_TB_WRITER = None
+_WANDB_WRITER = None
+_TIMERS: Optional[Timers] = None
+_SIGNAL_HANDLER = None
+
+
+def get_args():
+    if _ARGS is None:
+        raise RuntimeError("args is not initialized")
+    return _ARGS
+
+
+def set_args(args):
+    global _ARGS
+    _ARGS = args
+
+
+def get_tokenizer():
+    return _TOKENIZER
+
+
+def get_tensorboard_writer():
+    return _TB_WRITER
+
+
+def get_wandb_writer():
+    return _WANDB_WRITER
+
+
+def get_timers() -> Timers:
+    if _TIMERS is None:
+        raise RuntimeError("timers is not initialized")
+    return _TIMERS
+
+
+def get_tracer():
+    return _get_tracer()
+
+
+def get_signal_handler():
+    return _SIGNAL_HANDLER
+
+
+def set_global_variables(args, build_tokenizer: bool = True):
+    global _ARGS, _TOKENIZER, _TIMERS, _TB_WRITER, _SIGNAL_HANDLER
+    _ARGS = args
+    from ..utils.microbatches import init_num_microbatches_calculator
+
+    init_num_microbatches_calculator(args.rank, args.rampup_batch_size, args.global_batch_size,
+                                     args.micro_batch_size, args.effective_data_parallel_size,
+                                     args.decrease_batch_size_if_needed)
+    if build_tokenizer:
+        from ..data.tokenizer import build_tokenizer as _bt
+
+        _TOKENIZER = _bt(args)
+    _TIMERS = Timers(args.timing_log_level, args.timing_log_option)
+    if args.tensorboard_dir and args.rank == args.world_size - 1:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+
+            _TB_WRITER = SummaryWriter(log_dir=args.tensorboard_dir, max_queue=args.tensorboard_queue_size)
+        except Exception:
+            print("WARNING: TensorBoard writing requested but is not available", flush=True)
+    tracer = _get_tracer()
+    tracer.configure(args.trace, args.trace_dir, args.trace_interval, args.continuous_trace_iterations,
+                     args.trace_granularity)
+    if args.exit_signal_handler:
+        from .signals import DistributedSignalHandler
+
+        _SIGNAL_HANDLER = DistributedSignalHandler().__enter__()
+
+
+def unset_global_variables():
+    global _ARGS, _TOKENIZER, _TIMERS, _TB_WRITER, _SIGNAL_HANDLER
+    _ARGS = _TOKENIZER = _TIMERS = _TB_WRITER = _SIGNAL_HANDLER = None
+    from ..utils.microbatches import destroy_num_microbatches_calculator
+
+    destroy_num_microbatches_calculator()

@@ -1,0 +1,75 @@
+"""Feed-forward block: column-parallel fc1 -> fused bias+activation -> row-parallel fc2.
+
+Parity: reference ``transformer/mlp.py:32-371`` (``MLP``, ``MLPSubmodules``; gelu / geglu /
+swiglu / squared-relu; per-token-scale variant for MoE) with the fused activation kernels of
+``fusions/fused_bias_{gelu,swiglu}.py`` replaced by sm_100a elementwise kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ..scan.tracer import scope as _scope
+from ..scope import hooks as scope_hooks
+from .module import MegatronModule
+from .spec_utils import ModuleSpec, build_module
+
+
+@dataclass
+class MLPSubmodules:
+    linear_fc1: Union[ModuleSpec, type] = None
+    linear_fc2: Union[ModuleSpec, type] = None
+
+
+def squared_relu(x):
+    return torch.pow(F.relu(x), 2)
+
+
+class MLP(MegatronModule):
+    def __init__(self, config, submodules: MLPSubmodules, is_expert: bool = False,
+                 input_size: Optional[int] = None):
+        super().__init__(config)
+        self.input_size = input_size if input_size is not None else config.hidden_size
+        ffn = config.moe_ffn_hidden_size if is_expert else config.ffn_hidden_size
+        fc1_out = ffn * 2 if config.gated_linear_unit else ffn
+        self.linear_fc1 = build_module(
+            submodules.linear_fc1, self.input_size, fc1_out, config=config, init_method=config.init_method,
+            gather_output=False, bias=config.add_bias_linear, skip_bias_add=True, is_expert=is_expert,
+            tp_comm_buffer_name="fc1")
+        self.activation_func = config.activation_func
+        self.linear_fc2 = build_module(
+            submodules.linear_fc2, ffn, config.hidden_size, config=config,
+            init_method=config.output_layer_init_method, bias=config.add_bias_linear,
+            input_is_parallel=True, skip_bias_add=True, is_expert=is_expert, tp_comm_buffer_name="fc2")
+        self.layer_number = None
+
+    def _activation(self, x, bias):
+        cfg = self.config
+        if cfg.gated_linear_unit:
+            if self.activation_func in (F.silu,):
+                # Megatron packs [gate | up] along the last dim of each TP shard
+                return ops.swiglu(x, bias)
+            if bias is not None:
+                x = x + bias
+            g, u = torch.chunk(x, 2, dim=-1)
+            return self.activation_func(g) * u
+        if self.activation_func in (F.gelu,) or getattr(self.activation_func, "__name__", "") == "_gelu":
+            return ops.bias_gelu(x, bias)
+        if bias is not None:
+            x = x + bias
+        return self.activation_func(x)
+
+    def forward(self, hidden_states, per_token_scale=None):
+        with _scope("MLP.forward"):
+            inter, bias = self.linear_fc1(hidden_states)
+            scope_hooks.tik_tensor(4, self.layer_number, inter)
+            inter = self._activation(inter, bias)
+            if per_token_scale is not None:
+                inter = inter * per_token_scale.unsqueeze(-1).to(inter.dtype)
+            out, out_bias = self.linear_fc2(inter)
+            scope_hooks.tik_tensor(5, self.layer_number, out)
+        return out, out_bias

@@ -1,0 +1,88 @@
+"""Pretrain GPT (entry-point name and provider protocol kept from the reference
+``pretrain_gpt.py``: ``model_provider(pre_process, post_process)``, ``forward_step(data_iterator,
+model) -> (output_tensor, partial(loss_func, loss_mask))``, ``loss_func -> (loss, num_tokens,
+{'lm loss': (sum, count)})``, ``train_valid_test_datasets_provider(train_val_test_num_samples)``)."""
+from functools import partial
+
+import torch
+
+from megatronapp_b200.data.mock import MockGPTDataset
+from megatronapp_b200.models.gpt import GPTModel, get_gpt_decoder_block_spec, get_gpt_layer_local_spec
+from megatronapp_b200.parallel import state as mpu
+from megatronapp_b200.training.arguments import core_transformer_config_from_args
+from megatronapp_b200.training.global_vars import get_args, get_timers
+from megatronapp_b200.training.training import pretrain
+from megatronapp_b200.training.utils import get_batch_on_this_tp_rank, print_rank_0
+
+
+def model_provider(pre_process=True, post_process=True):
+    args = get_args()
+    print_rank_0("building GPT model ...")
+    config = core_transformer_config_from_args(args)
+    if args.num_experts:
+        spec = get_gpt_decoder_block_spec(config)
+    else:
+        spec = get_gpt_layer_local_spec(args.num_experts, args.moe_grouped_gemm, args.qk_layernorm,
+                                        args.multi_latent_attention)
+    return GPTModel(config=config, transformer_layer_spec=spec, vocab_size=args.padded_vocab_size,
+                    max_sequence_length=args.max_position_embeddings, pre_process=pre_process,
+                    post_process=post_process, fp16_lm_cross_entropy=args.fp16_lm_cross_entropy,
+                    parallel_output=True,
+                    share_embeddings_and_output_weights=not args.untie_embeddings_and_output_weights,
+                    position_embedding_type=args.position_embedding_type, rotary_percent=args.rotary_percent,
+                    rotary_base=args.rotary_base, rope_scaling=args.use_rope_scaling,
+                    rope_scaling_factor=args.rope_scaling_factor)
+
+
+def get_batch(data_iterator):
+    args = get_args()
+    if (not mpu.is_pipeline_first_stage()) and (not mpu.is_pipeline_last_stage()):
+        return None, None, None, None, None
+    b = get_batch_on_this_tp_rank(data_iterator, args)
+    return b["tokens"], b["labels"], b["loss_mask"], b["attention_mask"], b["position_ids"]
+
+
+def loss_func(loss_mask, output_tensor):
+    args = get_args()
+    losses = output_tensor.float()
+    loss_mask = loss_mask.view(-1).float()
+    total_tokens = loss_mask.sum()
+    loss = torch.cat([torch.sum(losses.view(-1) * loss_mask).view(1), total_tokens.view(1)])
+    if args.context_parallel_size > 1:
+        torch.distributed.all_reduce(loss, group=mpu.get_context_parallel_group())
+    reporting = loss.clone().detach()
+    g = mpu.get_data_parallel_group()
+    if g is not None and not isinstance(g, mpu._SingleGroup) and torch.distributed.get_world_size(g) > 1:
+        torch.distributed.all_reduce(reporting, group=g)
+    local_num_tokens = loss[1].clone().detach().to(torch.int)
+    return loss[0] * args.context_parallel_size, local_num_tokens, {"lm loss": (reporting[0], reporting[1])}
+
+
+def forward_step(data_iterator, model):
+    timers = get_timers()
+    timers("batch-generator", log_level=2).start()
+    tokens, labels, loss_mask, attention_mask, position_ids = get_batch(data_iterator)
+    timers("batch-generator").stop()
+    output_tensor = model(tokens, position_ids, attention_mask, labels=labels)
+    return output_tensor, partial(loss_func, loss_mask)
+
+
+def train_valid_test_datasets_provider(train_val_test_num_samples):
+    args = get_args()
+    print_rank_0("> building train, validation, and test datasets for GPT ...")
+    if args.mock_data or not args.data_path:
+        vs = args.padded_vocab_size
+        mk = lambda n, seed: MockGPTDataset(max(int(n), 1), args.seq_length, vs, seed,  # noqa: E731
+                                            create_attention_mask=args.create_attention_mask_in_dataloader)
+        return mk(train_val_test_num_samples[0], args.seed), mk(train_val_test_num_samples[1], args.seed + 1), \
+            mk(train_val_test_num_samples[2], args.seed + 2)
+    from megatronapp_b200.data.gpt_dataset import build_gpt_datasets
+
+    return build_gpt_datasets(args, train_val_test_num_samples)
+
+
+train_valid_test_datasets_provider.is_distributed = False
+
+if __name__ == "__main__":
+    pretrain(train_valid_test_datasets_provider, model_provider, "encoder_or_decoder", forward_step,
+             args_defaults={"tokenizer_type": "NullTokenizer"})
