@@ -1,0 +1,408 @@
+"""Numerics + performance checks of every sm_100a kernel against PyTorch fp32 references.
+
+Each check runs in its own subprocess with a timeout so a hung / faulting kernel cannot take
+the whole session (or the GPU lease) down; results are merged into one JSON file.
+
+    python tools/gpu_checks.py --out gpurun_out/checks.json [--only gemm_nt,ln] [--perf]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _rel_err(a, b):
+    import torch
+
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-6))
+
+
+def _time(fn, iters=20, warmup=5, flush=None):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+# ---------------------------------------------------------------------------------- checks
+
+def check_gemm(mode, shapes=None, dtype="bf16"):
+    import torch
+    from megatronapp_b200 import ops
+
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    res = {}
+    shapes = shapes or [(128, 128, 64), (256, 256, 128), (384, 512, 320), (2048, 4096, 4096), (300, 520, 264),
+                        (4096, 1024, 2048)]
+    for (M, N, K) in shapes:
+        for bn in (128, 256):
+            torch.manual_seed(M + N + K)
+            A = torch.randn(M, K, device="cuda", dtype=dt) * 0.5
+            B = torch.randn(N, K, device="cuda", dtype=dt) * 0.5
+            bias = torch.randn(N, device="cuda", dtype=dt)
+            ref = A.float() @ B.float().t()
+            key = f"{mode}_{M}x{N}x{K}_bn{bn}"
+            try:
+                if mode == "nt":
+                    out = ops.gemm(A, B, block_n=bn)
+                    res[key] = _rel_err(out, ref)
+                elif mode == "nt_bias_gelu":
+                    pre = torch.empty(M, N, device="cuda", dtype=dt)
+                    out = ops.gemm(A, B, bias=bias, act=1, out_pre=pre, block_n=bn)
+                    r2 = ref + bias.float()
+                    e1 = _rel_err(pre, r2)
+                    e2 = _rel_err(out, torch.nn.functional.gelu(r2, approximate="tanh"))
+                    res[key] = max(e1, e2)
+                elif mode == "nn":   # B stored [K, N]
+                    Bt = B.t().contiguous()
+                    out = ops.gemm(A, Bt, b_mn=True, block_n=bn)
+                    res[key] = _rel_err(out, ref)
+                elif mode == "tn":   # A stored [K, M]
+                    At = A.t().contiguous()
+                    out = ops.gemm(At, B, a_mn=True, block_n=bn)
+                    res[key] = _rel_err(out, ref)
+                elif mode == "tt":   # both transposed: wgrad layout
+                    At, Bt = A.t().contiguous(), B.t().contiguous()
+                    out = ops.gemm(At, Bt, a_mn=True, b_mn=True, block_n=bn)
+                    res[key] = _rel_err(out, ref)
+                elif mode == "tt_accum":
+                    At, Bt = A.t().contiguous(), B.t().contiguous()
+                    if N % 4:
+                        continue
+                    acc = torch.randn(M, N, device="cuda", dtype=torch.float32)
+                    want = acc + ref
+                    ops.gemm(At, Bt, out=acc, a_mn=True, b_mn=True, epilogue=1, block_n=bn)
+                    res[key] = _rel_err(acc, want)
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                res[key] = f"EXC {type(e).__name__}: {str(e)[:200]}"
+    res["_fallbacks"] = dict(ops.fallback_counts)
+    return res
+
+
+def check_elementwise():
+    import torch
+    from megatronapp_b200 import ops
+
+    res = {}
+    dt = torch.bfloat16
+    torch.manual_seed(0)
+    for cols in (512, 4096, 5120):
+        x = torch.randn(777, cols, device="cuda", dtype=dt, requires_grad=True)
+        g = (torch.randn(cols, device="cuda", dtype=dt) * 0.1 + 1).requires_grad_(True)
+        b = (torch.randn(cols, device="cuda", dtype=dt) * 0.1).requires_grad_(True)
+        for rms in (False, True):
+            y = ops.layer_norm(x, g, None if rms else b, 1e-5, rms=rms)
+            dy = torch.randn_like(y)
+            y.backward(dy)
+            gx, gg = x.grad.clone(), g.grad.clone()
+            gb = None if rms else b.grad.clone()
+            x.grad = g.grad = None
+            if not rms:
+                b.grad = None
+            xf, gf = x.detach().float().requires_grad_(True), g.detach().float().requires_grad_(True)
+            bf = None if rms else b.detach().float().requires_grad_(True)
+            yr = ops.norm_ref(xf, gf, bf, 1e-5, rms=rms)
+            yr.backward(dy.float())
+            tag = f"{'rms' if rms else 'ln'}_{cols}"
+            res[tag + "_fwd"] = _rel_err(y, yr)
+            res[tag + "_dx"] = _rel_err(gx, xf.grad)
+            res[tag + "_dgamma"] = _rel_err(gg, gf.grad)
+            if not rms:
+                res[tag + "_dbeta"] = _rel_err(gb, bf.grad)
+    # gelu / swiglu
+    x = torch.randn(1000, 4096, device="cuda", dtype=dt, requires_grad=True)
+    bias = torch.randn(4096, device="cuda", dtype=dt, requires_grad=True)
+    y = ops.bias_gelu(x, bias)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, bf = x.detach().float().requires_grad_(True), bias.detach().float().requires_grad_(True)
+    yr = ops.bias_gelu_ref(xf, bf)
+    yr.backward(dy.float())
+    res["gelu_fwd"], res["gelu_dx"], res["gelu_db"] = _rel_err(y, yr), _rel_err(x.grad, xf.grad), _rel_err(bias.grad, bf.grad)
+    x.grad = bias.grad = None
+    y = ops.swiglu(x, bias)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, bf = x.detach().float().requires_grad_(True), bias.detach().float().requires_grad_(True)
+    yr = ops.swiglu_ref(xf, bf)
+    yr.backward(dy.float())
+    res["swiglu_fwd"], res["swiglu_dx"], res["swiglu_db"] = _rel_err(y, yr), _rel_err(x.grad, xf.grad), _rel_err(bias.grad, bf.grad)
+    # bias dropout add (p = 0 exact; p > 0 statistical)
+    h = torch.randn(64, 8, 1024, device="cuda", dtype=dt)
+    r = torch.randn_like(h)
+    b2 = torch.randn(1024, device="cuda", dtype=dt)
+    o = ops.bias_dropout_add(h, b2, r, 0.0, True)
+    res["bda_p0"] = _rel_err(o, (h.float() + b2.float() + r.float()))
+    o = ops.bias_dropout_add(h, None, None, 0.25, True)
+    kept = (o != 0).float().mean().item()
+    res["bda_keep_frac(expect .75)"] = kept
+    res["bda_scale"] = _rel_err(o[o != 0], (h.float() / 0.75)[o != 0])
+    # rope
+    q = torch.randn(128, 2, 8, 128, device="cuda", dtype=dt, requires_grad=True)
+    cs = ops.rope_cos_sin(128, 128, device="cuda")
+    for inter in (False, True):
+        y = ops.rope(q, cs, inter)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        qf = q.detach().float().requires_grad_(True)
+        yr = ops.rope_ref(qf, cs, inter)
+        yr.backward(dy.float())
+        res[f"rope_fwd_i{int(inter)}"], res[f"rope_bwd_i{int(inter)}"] = _rel_err(y, yr), _rel_err(q.grad, qf.grad)
+        q.grad = None
+    cs2 = ops.rope_cos_sin(128, 64, device="cuda")
+    y = ops.rope(q.detach(), cs2, False)
+    res["rope_partial"] = _rel_err(y, ops.rope_ref(q.detach().float(), cs2, False))
+    # bias grad
+    d = torch.randn(3000, 4096, device="cuda", dtype=dt)
+    res["bias_grad"] = _rel_err(ops.bias_grad(d), d.float().sum(0))
+    # cross entropy
+    for ldt in (torch.bfloat16, torch.float32):
+        lg = (torch.randn(512, 50304, device="cuda", dtype=ldt) * 2).requires_grad_(True)
+        lab = torch.randint(0, 50304, (512,), device="cuda")
+        loss = ops.cross_entropy(lg.clone() if True else lg, lab, inplace_grad=False)
+        lgf = lg.detach().float().requires_grad_(True)
+        ref = ops.cross_entropy_ref(lgf, lab)
+        res[f"ce_fwd_{str(ldt)[6:]}"] = _rel_err(loss, ref)
+        w = torch.rand(512, device="cuda")
+        (loss * w).sum().backward()
+        (ref * w).sum().backward()
+        res[f"ce_bwd_{str(ldt)[6:]}"] = _rel_err(lg.grad, lgf.grad)
+    # adam
+    n = 1_000_003
+    m = torch.randn(n, device="cuda")
+    ea, es = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    p16 = torch.empty(n, device="cuda", dtype=dt)
+    m2, ea2, es2 = m.clone(), ea.clone(), es.clone()
+    for step in (1, 2, 3):
+        ops.adam_step(m, ea, es, g, p16, 1e-2, 0.9, 0.95, 1e-8, 0.1, 0.5, step)
+        ops.adam_step_ref(m2, ea2, es2, g, None, 1e-2, 0.9, 0.95, 1e-8, 0.1, 0.5, step)
+    res["adam_master"], res["adam_p16"] = _rel_err(m, m2), _rel_err(p16, m2)
+    res["l2norm"] = abs(float(ops.l2norm_sq([g, m]).item()) / float((g.float().pow(2).sum() + m.pow(2).sum()).item()) - 1)
+    res["chunk_mean"] = _rel_err(ops.chunk_mean(h, 64), ops.chunk_mean(h.float().cpu(), 64).cuda())
+    res["_fallbacks"] = dict(ops.fallback_counts)
+    return res
+
+
+def check_gemm_perf():
+    import torch
+    from megatronapp_b200 import ops
+
+    res = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    shapes = {"sq8192": (8192, 8192, 8192), "qkv_tp1": (2048, 12288, 4096), "fc1_tp1": (2048, 16384, 4096),
+              "fc2_tp1": (2048, 4096, 16384), "proj_tp1": (2048, 4096, 4096), "fc1_mbs4": (8192, 16384, 4096),
+              "lmhead": (2048, 50304, 4096), "qkv_tp4": (2048, 3072, 4096)}
+    for name, (M, N, K) in shapes.items():
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        fl = 2.0 * M * N * K
+        for bn in (0, 128, 256):
+            try:
+                t = _time(lambda: ops.gemm(A, B, out=out, block_n=bn), flush=flush)
+                res[f"{name}_b200_bn{bn}_tflops"] = round(fl / t / 1e9, 1)
+            except Exception as e:  # noqa: BLE001
+                res[f"{name}_b200_bn{bn}"] = f"EXC {e}"
+        t = _time(lambda: torch.matmul(A, B.t(), out=out), flush=flush)
+        res[f"{name}_cublas_tflops"] = round(fl / t / 1e9, 1)
+        # dgrad / wgrad layouts
+        dY = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+        dX = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+        t = _time(lambda: ops.gemm(dY, B, out=dX, b_mn=True), flush=flush)
+        res[f"{name}_dgrad_tflops"] = round(fl / t / 1e9, 1)
+        mg = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+        t = _time(lambda: ops.gemm(dY, A, out=mg, a_mn=True, b_mn=True, epilogue=1), flush=flush)
+        res[f"{name}_wgrad_accum_tflops"] = round(fl / t / 1e9, 1)
+        del A, B, out, dY, dX, mg
+    return res
+
+
+def check_elementwise_perf():
+    import torch
+    from megatronapp_b200 import ops
+
+    res = {}
+    x = torch.randn(16384, 4096, device="cuda", dtype=torch.bfloat16)
+    g = torch.ones(4096, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(4096, device="cuda", dtype=torch.bfloat16)
+    nb = x.numel() * 2
+    t = _time(lambda: ops.ext().layernorm_fwd(x, g, b, 1e-5, False, False))
+    res["ln_fwd_GBs"] = round(2 * nb / t / 1e6, 1)
+    y, mean, rstd = ops.ext().layernorm_fwd(x, g, b, 1e-5, False, False)
+    t = _time(lambda: ops.ext().layernorm_bwd(x, x, g, mean, rstd, False, False, True))
+    res["ln_bwd_GBs"] = round(3 * nb / t / 1e6, 1)
+    t = _time(lambda: ops.ext().bias_gelu_fwd(x, b))
+    res["gelu_fwd_GBs"] = round(2 * nb / t / 1e6, 1)
+    n = 256 * 1024 * 1024
+    m, ea, es, gr = (torch.zeros(n, device="cuda") for _ in range(4))
+    p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    t = _time(lambda: ops.adam_step(m, ea, es, gr, p16, 1e-3, 0.9, 0.95, 1e-8, 0.1, 1.0, 1), iters=5)
+    res["adam_GBs"] = round(n * 30 / t / 1e6, 1)
+    lg = torch.randn(2048, 50304, device="cuda", dtype=torch.bfloat16)
+    lab = torch.randint(0, 50304, (2048,), device="cuda")
+    t = _time(lambda: ops.ext().ce_local_stats(lg, lab, 0))
+    res["ce_stats_GBs"] = round(lg.numel() * 2 / t / 1e6, 1)
+    return res
+
+
+def check_attention():
+    import torch
+    from megatronapp_b200 import ops
+
+    res = {"native_available": ops.native_attention_available()}
+    if not res["native_available"]:
+        return res
+    for (b, h, hk, s, d, causal) in [(1, 2, 2, 256, 128, True), (2, 4, 4, 512, 128, True), (2, 4, 2, 384, 64, True),
+                                     (1, 2, 2, 256, 128, False), (1, 8, 8, 2048, 128, True)]:
+        torch.manual_seed(s)
+        q = torch.randn(b, h, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        k = torch.randn(b, hk, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        v = torch.randn(b, hk, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        tag = f"attn_b{b}h{h}kv{hk}s{s}d{d}c{int(causal)}"
+        try:
+            o = ops._AttnFn.apply(q, k, v, 1.0 / d ** 0.5, causal)
+            do = torch.randn_like(o)
+            o.backward(do)
+            qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+            orf = ops.attention_ref(qf, kf, vf, None, causal)
+            orf.backward(do.float())
+            res[tag + "_fwd"] = _rel_err(o, orf)
+            res[tag + "_dq"], res[tag + "_dk"], res[tag + "_dv"] = _rel_err(q.grad, qf.grad), _rel_err(k.grad, kf.grad), _rel_err(v.grad, vf.grad)
+        except Exception as e:  # noqa: BLE001
+            res[tag] = f"EXC {type(e).__name__}: {str(e)[:200]}"
+    return res
+
+
+def check_attention_perf():
+    import torch
+    from megatronapp_b200 import ops
+    import torch.nn.functional as F
+
+    res = {"native_available": ops.native_attention_available()}
+    b, h, s, d = 1, 32, 2048, 128
+    q, k, v = (torch.randn(b, h, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
+    fl_f = 4.0 * b * h * s * s * d / 2
+    t = _time(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=True))
+    res["sdpa_fwd_tflops"] = round(fl_f / t / 1e9, 1)
+    o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+    do = torch.randn_like(o)
+    t = _time(lambda: torch.autograd.grad(o, (q, k, v), do, retain_graph=True))
+    res["sdpa_bwd_tflops"] = round(2.5 * fl_f / t / 1e9, 1)
+    if res["native_available"]:
+        t = _time(lambda: ops.ext().attn_fwd(q, k, v, 1.0 / d ** 0.5, True, False))
+        res["b200_fwd_tflops"] = round(fl_f / t / 1e9, 1)
+        o2, lse, _ = ops.ext().attn_fwd(q, k, v, 1.0 / d ** 0.5, True, False)
+        t = _time(lambda: ops.ext().attn_bwd(do, q, k, v, o2, lse, 1.0 / d ** 0.5, True))
+        res["b200_bwd_tflops"] = round(2.5 * fl_f / t / 1e9, 1)
+    return res
+
+
+def check_smoke():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    ge.smoke()
+    return {"ok": True}
+
+
+def check_model_parity():
+    """bf16 GPT step on the native kernels vs the fp32 PyTorch reference path (same weights)."""
+    import torch
+    from megatronapp_b200 import ops
+    from megatronapp_b200.bench_model import build_gpt_for_bench, synthetic_batch, train_step
+    from megatronapp_b200.parallel import state as ps
+
+    st = build_gpt_for_bench(2, 512, 8, 256, 4096, 2, ffn=2048, device="cuda")
+    b = synthetic_batch(st, "cuda")
+    sd = {k: v.detach().float().cpu() for k, v in st.model[0].module.module.state_dict().items()}
+    l_native = [train_step(st, [b, b]) for _ in range(3)]
+    ps.destroy_model_parallel()
+    st2 = build_gpt_for_bench(2, 512, 8, 256, 4096, 2, ffn=2048, device="cpu", dtype=torch.float32)
+    st2.model[0].module.load_state_dict(sd)
+    st2.optimizer.reload_model_params()
+    b2 = {k: v.cpu() for k, v in b.items()}
+    l_ref = [train_step(st2, [b2, b2]) for _ in range(3)]
+    return {"native": l_native, "ref_fp32_cpu": l_ref, "fallbacks": dict(ops.fallback_counts),
+            "max_abs_diff": max(abs(a - c) for a, c in zip(l_native, l_ref))}
+
+
+CHECKS = {
+    "gemm_nt": lambda: check_gemm("nt"),
+    "gemm_nt_bias_gelu": lambda: check_gemm("nt_bias_gelu", [(256, 256, 128), (2048, 4096, 4096), (300, 520, 264)]),
+    "gemm_nn": lambda: check_gemm("nn"),
+    "gemm_tn": lambda: check_gemm("tn"),
+    "gemm_tt": lambda: check_gemm("tt"),
+    "gemm_tt_accum": lambda: check_gemm("tt_accum"),
+    "gemm_nt_fp16": lambda: check_gemm("nt", [(256, 256, 128), (2048, 4096, 4096)], "fp16"),
+    "elementwise": check_elementwise,
+    "attention": check_attention,
+    "model_parity": check_model_parity,
+    "smoke": check_smoke,
+}
+PERF = {"gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "checks.json"))
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--perf", action="store_true")
+    ap.add_argument("--one", default=None)
+    ap.add_argument("--timeout", type=int, default=240)
+    a = ap.parse_args()
+    allc = dict(CHECKS)
+    allc.update(PERF)
+    if a.one:
+        r = allc[a.one]()
+        print("RESULT_JSON " + json.dumps(r))
+        return
+    names = a.only.split(",") if a.only else list(CHECKS) + (list(PERF) if a.perf else [])
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    results = {}
+    if os.path.exists(a.out):
+        try:
+            results = json.load(open(a.out))
+        except Exception:
+            results = {}
+    for n in names:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True,
+                               text=True, timeout=a.timeout, cwd=ROOT)
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT_JSON ")]
+            if line:
+                results[n] = json.loads(line[-1][len("RESULT_JSON "):])
+            else:
+                results[n] = {"error": f"rc={p.returncode}", "stderr": p.stderr[-1500:], "stdout": p.stdout[-500:]}
+        except subprocess.TimeoutExpired:
+            results[n] = {"error": f"TIMEOUT after {a.timeout}s"}
+        results[n + "_secs"] = round(time.time() - t0, 1)
+        json.dump(results, open(a.out, "w"), indent=1)
+        print(n, json.dumps(results[n])[:1500], flush=True)
+
+
+if __name__ == "__main__":
+    main()
