@@ -43,7 +43,7 @@ def main(args, MODELS, layout_for, pad_vocab):
             "--attention-dropout", "0.0", "--hidden-dropout", "0.0",
             "--tokenizer-type", "NullTokenizer", "--vocab-size", str(vocab - 1), "--make-vocab-size-divisible-by", "1",
             "--mock-data", "--no-create-attention-mask-in-dataloader", "--no-gradient-accumulation-fusion",
-            "--no-masked-softmax-fusion", "--distributed-backend", "nccl", "--log-interval", "1000000",
+            "--no-masked-softmax-fusion", "--no-persist-layer-norm", "--distributed-backend", "nccl", "--log-interval", "1000000",
             "--eval-iters", "0", "--no-save-optim", "--no-save-rng", "--ckpt-format", "torch"]
     if tp > 1:
         argv += ["--sequence-parallel"]

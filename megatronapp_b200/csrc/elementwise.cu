@@ -234,18 +234,28 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(
   }
 }
 
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ pg, const float* __restrict__ pb,
+__global__ void __launch_bounds__(512) ln_bwd_finalize_kernel(const float* __restrict__ pg, const float* __restrict__ pb,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int n_partial, int cols, bool accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  // 32 columns x 16 partial-row lanes per CTA: coalesced 128B rows, smem tree over the 16 lanes
+  __shared__ float sg[16][33], sb[16][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float g = 0.f, b = 0.f;
-  for (int i = 0; i < n_partial; ++i) {
-    g += pg[static_cast<size_t>(i) * cols + c];
-    if (pb) b += pb[static_cast<size_t>(i) * cols + c];
+  if (c < cols) {
+    for (int i = ty; i < n_partial; i += 16) {
+      g += pg[static_cast<size_t>(i) * cols + c];
+      if (pb) b += pb[static_cast<size_t>(i) * cols + c];
+    }
   }
-  dgamma[c] = accumulate ? dgamma[c] + g : g;
-  if (pb && dbeta) dbeta[c] = accumulate ? dbeta[c] + b : b;
+  sg[ty][tx] = g; sb[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+#pragma unroll
+    for (int i = 1; i < 16; ++i) { g += sg[i][tx]; b += sb[i][tx]; }
+    dgamma[c] = accumulate ? dgamma[c] + g : g;
+    if (pb && dbeta) dbeta[c] = accumulate ? dbeta[c] + b : b;
+  }
 }
 
 // ------------------------------------------------------------------ activations
@@ -468,24 +478,61 @@ __device__ __forceinline__ float ld_logit(const T* p, int64_t i) { return Cvt<T>
 template <>
 __device__ __forceinline__ float ld_logit<float>(const float* p, int64_t i) { return p[i]; }
 
+template <typename T> struct VecLd {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const T* p, float (&f)[8]) { load8(p, f); }
+  static __device__ __forceinline__ void st(T* p, const float (&f)[8]) { store8(p, f); }
+};
+template <> struct VecLd<float> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const float* p, float (&f)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+// one CTA per row, single pass: per-thread online (max, sum) over 8-wide vectors, then a block merge
 template <typename T>
-__global__ void __launch_bounds__(256) ce_stats_kernel(const T* __restrict__ logits,
+__global__ void __launch_bounds__(512) ce_stats_kernel(const T* __restrict__ logits,
                                                        const int64_t* __restrict__ labels,
                                                        float* __restrict__ row_max,
                                                        float* __restrict__ row_sumexp,
                                                        float* __restrict__ tgt, int64_t rows,
                                                        int vocab_local, int vocab_start, int ldl) {
   __shared__ float red[32];
+  const bool vec_ok = (ldl % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 31) == 0);
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const T* lr = logits + row * ldl;
-    float m = -INFINITY;
-    for (int c = threadIdx.x; c < vocab_local; c += blockDim.x) m = fmaxf(m, ld_logit(lr, c));
-    m = block_max(m, red);
-    float s = 0.f;
-    for (int c = threadIdx.x; c < vocab_local; c += blockDim.x) s += __expf(ld_logit(lr, c) - m);
+    float m = -INFINITY, s = 0.f;
+    const int nvec = vec_ok ? vocab_local / 8 : 0;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      float f[8];
+      VecLd<T>::ld(lr + v * 8, f);
+      float vm = f[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) vm = fmaxf(vm, f[j]);
+      const float nm = fmaxf(m, vm);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += __expf(f[j] - nm);
+      s = s * __expf(m - nm) + acc;
+      m = nm;
+    }
+    for (int c = nvec * 8 + threadIdx.x; c < vocab_local; c += blockDim.x) {
+      const float x = ld_logit(lr, c);
+      const float nm = fmaxf(m, x);
+      s = s * __expf(m - nm) + __expf(x - nm);
+      m = nm;
+    }
+    const float gm = block_max(m, red);
+    s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
     s = block_sum(s, red);
     if (threadIdx.x == 0) {
-      row_max[row] = m;
+      row_max[row] = gm;
       row_sumexp[row] = s;
       const int64_t lab = labels[row] - vocab_start;
       tgt[row] = (lab >= 0 && lab < vocab_local) ? ld_logit(lr, lab) : 0.f;
@@ -501,7 +548,7 @@ template <typename T> __device__ __forceinline__ void st_logit(T* p, int64_t i, 
 template <> __device__ __forceinline__ void st_logit<float>(float* p, int64_t i, float v) { p[i] = v; }
 
 template <typename T>
-__global__ void __launch_bounds__(256) ce_grad_kernel(const T* __restrict__ logits,
+__global__ void __launch_bounds__(512) ce_grad_kernel(const T* __restrict__ logits,
                                                       const int64_t* __restrict__ labels,
                                                       const float* __restrict__ gmax,
                                                       const float* __restrict__ gsum,
@@ -509,6 +556,8 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const T* __restrict__ logi
                                                       T* __restrict__ dlogits, int64_t rows,
                                                       int vocab_local, int vocab_start, int ldl,
                                                       float label_smoothing, int64_t vocab_total) {
+  const bool vec_ok = (ldl % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 31) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(dlogits) & 31) == 0);
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const T* lr = logits + row * ldl;
     T* dr = dlogits + row * ldl;
@@ -516,7 +565,18 @@ __global__ void __launch_bounds__(256) ce_grad_kernel(const T* __restrict__ logi
     const int64_t lab = labels[row] - vocab_start;
     const float smooth = label_smoothing > 0.f ? label_smoothing / static_cast<float>(vocab_total - 1) : 0.f;
     const float on_target = label_smoothing > 0.f ? 1.f - label_smoothing - smooth : 1.f;
-    for (int c = threadIdx.x; c < vocab_local; c += blockDim.x) {
+    const int nvec = vec_ok ? vocab_local / 8 : 0;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      float f[8];
+      VecLd<T>::ld(lr + v * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = (v * 8 + j == lab) ? on_target : 0.f;
+        f[j] = (__expf(f[j] - m) * inv - t - smooth) * g;
+      }
+      VecLd<T>::st(dr + v * 8, f);
+    }
+    for (int c = nvec * 8 + threadIdx.x; c < vocab_local; c += blockDim.x) {
       float pr = __expf(ld_logit(lr, c) - m) * inv;
       float t = (c == lab) ? on_target : 0.f;
       st_logit(dr, c, (pr - t - smooth) * g);
@@ -686,7 +746,7 @@ void layernorm_bwd(const void* dy, const void* x, const void* gamma, const float
 
 void layernorm_bwd_finalize(const float* pg, const float* pb, float* dgamma, float* dbeta,
                             int n_partial, int cols, bool accumulate, cudaStream_t s) {
-  ln_bwd_finalize_kernel<<<(cols + 127) / 128, 128, 0, s>>>(pg, pb, dgamma, dbeta, n_partial, cols,
+  ln_bwd_finalize_kernel<<<(cols + 31) / 32, 512, 0, s>>>(pg, pb, dgamma, dbeta, n_partial, cols,
                                                             accumulate);
 }
 
@@ -752,7 +812,7 @@ void ce_local_stats(const void* logits, const int64_t* labels, float* row_max, f
                     float* tgt_logit, int64_t rows, int vocab_local, int vocab_start, int ldl,
                     int logits_dtype, cudaStream_t s) {
   const int grid = rows < 148 * 8 ? static_cast<int>(rows) : 148 * 8;
-  DISPATCH_ANY(logits_dtype, (ce_stats_kernel<T><<<grid, 256, 0, s>>>((const T*)logits, labels, row_max,
+  DISPATCH_ANY(logits_dtype, (ce_stats_kernel<T><<<grid, 512, 0, s>>>((const T*)logits, labels, row_max,
                                                                       row_sumexp, tgt_logit, rows,
                                                                       vocab_local, vocab_start, ldl)));
 }
@@ -766,7 +826,7 @@ void ce_grad(const void* logits, const int64_t* labels, const float* global_max,
              int vocab_local, int vocab_start, int ldl, int logits_dtype, float label_smoothing,
              int64_t vocab_total, cudaStream_t s) {
   const int grid = rows < 148 * 8 ? static_cast<int>(rows) : 148 * 8;
-  DISPATCH_ANY(logits_dtype, (ce_grad_kernel<T><<<grid, 256, 0, s>>>(
+  DISPATCH_ANY(logits_dtype, (ce_grad_kernel<T><<<grid, 512, 0, s>>>(
                                  (const T*)logits, labels, global_max, global_sumexp, grad_loss,
                                  (T*)dlogits, rows, vocab_local, vocab_start, ldl, label_smoothing,
                                  vocab_total)));

@@ -179,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if constexpr (kEpi == kEpiStore16) tma_prefetch_desc(&tmap_d);
+    if constexpr (kEpi != kEpiReduceScatter) tma_prefetch_desc(&tmap_d);
     if constexpr (kComm == kCommAllGather) tma_prefetch_desc(&tmap_a_local);
   }
   if (warp_idx == 1 && lane == 0) {
@@ -373,23 +373,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             cbuf ^= 1;
           }
         } else if constexpr (kEpi == kEpiAccumF32 || kEpi == kEpiStoreF32) {
-          if (grow < p.M) {
-            float* drow = reinterpret_cast<float*>(p.D) + static_cast<size_t>(grow) * p.ldd + gcol0;
+          // fp32 tile -> smem (two 32-column halves, 128B-swizzled) -> TMA store / TMA reduce-add.
+          // The "+=" happens in L2 (cp.reduce.async.bulk.tensor .add), so no main_grad read
+          // round trip stalls the epilogue warps.
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = gcol0 + j * 4;
-              if (col < p.N) {
-                const uint32_t* s = (j < 8) ? &v0[j * 4] : &v1[(j - 8) * 4];
-                float4 a = make_float4(__uint_as_float(s[0]), __uint_as_float(s[1]),
-                                       __uint_as_float(s[2]), __uint_as_float(s[3]));
-                float4* dp = reinterpret_cast<float4*>(drow + j * 4);
-                if constexpr (kEpi == kEpiAccumF32) {
-                  float4 o = *dp;
-                  a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-                }
-                *dp = a;
-              }
+          for (int hseg = 0; hseg < 2; ++hseg) {
+            const uint32_t* v = hseg == 0 ? v0 : v1;
+            if (epi_tid == 0) tma_store_wait_read<1>();
+            named_bar_sync(1, kNumEpiThreads);
+            uint8_t* sc = smem_c + cbuf * L::kCBytes + row_in_tile * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              *reinterpret_cast<uint4*>(sc + ((j ^ (row_in_tile & 7)) << 4)) =
+                  make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
             }
+            fence_proxy_async_smem();
+            named_bar_sync(2, kNumEpiThreads);
+            if (epi_tid == 0) {
+              if constexpr (kEpi == kEpiAccumF32)
+                tma_reduce_add_2d(&tmap_d, smem_c + cbuf * L::kCBytes, gcol0 + hseg * 32, m_blk * BLOCK_M);
+              else
+                tma_store_2d(&tmap_d, smem_c + cbuf * L::kCBytes, gcol0 + hseg * 32, m_blk * BLOCK_M);
+              tma_store_commit();
+            }
+            cbuf ^= 1;
           }
         } else {  // kEpiReduceScatter: partial tile -> owner's staging buffer [src][rows_per_rank][N]
           const int owner = (m_blk * BLOCK_M) / p.rows_per_rank;
@@ -431,7 +438,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if constexpr (kEpi == kEpiStore16) {
+    if constexpr (kEpi == kEpiStore16 || kEpi == kEpiAccumF32 || kEpi == kEpiStoreF32) {
       if (epi_tid == 0) tma_store_wait_all<0>();
     }
     if constexpr (kEpi == kEpiReduceScatter) {
@@ -523,14 +530,14 @@ EncodeTiledFn get_encode_fn() {
 thread_local std::string g_last_error;
 
 bool make_tmap_2d(CUtensorMap* map, const void* base, bool is_bf16, uint64_t inner, uint64_t outer,
-                  uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+                  uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer, bool is_f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { g_last_error = "cuTensorMapEncodeTiled unavailable"; return false; }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint64_t strides[1] = {ld_elems * (is_f32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+  CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 2,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -689,6 +696,9 @@ int gemm_bf16(const GemmArgs& a) {
     ok = ok && make_tmap_2d(&td, a.D, a.is_bf16, a.N, a.M, a.ldd, 64, BLOCK_M);
     if (a.D_pre) ok = ok && make_tmap_2d(&tdp, a.D_pre, a.is_bf16, a.N, a.M, a.ldd, 64, BLOCK_M);
     else tdp = td;
+  } else if (a.epilogue == kEpiAccumF32 || a.epilogue == kEpiStoreF32) {
+    ok = ok && make_tmap_2d(&td, a.D, a.is_bf16, a.N, a.M, a.ldd, 32, BLOCK_M, /*is_f32=*/true);
+    tdp = td;
   } else { td = ta; tdp = ta; }
   if (!ok) return -5;
 

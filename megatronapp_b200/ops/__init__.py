@@ -172,8 +172,12 @@ def wgrad(dy2, x2, weight, fuse: bool):
     """dW = dY^T X; accumulate into ``weight.main_grad`` when fused (returns None then)."""
     main_grad = getattr(weight, "main_grad", None)
     if fuse and main_grad is not None:
+        first = not getattr(weight, "grad_added_to_main_grad", False) and getattr(weight, "b200_wgrad_store_first", False)
         if main_grad.dtype == torch.float32:
-            gemm(dy2, x2, out=main_grad, a_mn=True, b_mn=True, epilogue=EPI_ACCUM_F32)
+            gemm(dy2, x2, out=main_grad, a_mn=True, b_mn=True,
+                 epilogue=EPI_STORE_F32 if first else EPI_ACCUM_F32)
+        elif first:
+            gemm(dy2, x2, out=main_grad, a_mn=True, b_mn=True)
         else:
             main_grad.add_(gemm(dy2, x2, a_mn=True, b_mn=True))
         weight.grad_added_to_main_grad = True

@@ -116,6 +116,19 @@ class ParamAndGradBuffer:
             p.grad_added_to_main_grad = False
         self.param_to_bucket = {p: self.buckets[self.param_index[p][2]] for p in self.params}
         self._rs_epoch = 0
+        # params whose first wgrad of a step is a plain store (epilogue "=") need no zeroing
+        skip = sorted((self.param_index[p][0], self.param_index[p][1]) for p in self.params
+                      if getattr(p, "b200_wgrad_store_first", False))
+        self._zero_ranges = None
+        if skip:
+            rng, cur = [], 0
+            for s0, e0 in skip:
+                if s0 > cur:
+                    rng.append((cur, s0))
+                cur = e0
+            if cur < self.numel:
+                rng.append((cur, self.numel))
+            self._zero_ranges = rng
 
     # ---- gradient sync ---------------------------------------------------------
     def reset(self):
@@ -125,7 +138,11 @@ class ParamAndGradBuffer:
             b.dispatched = False
 
     def zero(self):
-        self.grad_data.zero_()
+        if self._zero_ranges is None:
+            self.grad_data.zero_()
+        else:
+            for a, b in self._zero_ranges:
+                self.grad_data[a:b].zero_()
         for p in self.params:
             p.grad_added_to_main_grad = False
         self.reset()
@@ -267,11 +284,13 @@ class DistributedDataParallel(nn.Module):
     def _make_hook(self, buf: ParamAndGradBuffer):
         def hook(param):
             if param.grad is not None:
-                if not param.grad_added_to_main_grad:
-                    if param.main_grad.dtype == torch.float32 and param.grad.is_cuda and param.grad.is_contiguous():
-                        ops.ext().add_into_f32(param.main_grad, param.grad)
-                    else:
-                        param.main_grad.add_(param.grad.to(param.main_grad.dtype))
+                # the fused wgrad path returns None (never a dummy), so whatever arrives here is a
+                # real contribution (e.g. the embedding lookup of a tied weight) and is always added
+                if param.main_grad.dtype == torch.float32 and param.grad.is_cuda and param.grad.is_contiguous():
+                    ops.ext().add_into_f32(param.main_grad, param.grad)
+                else:
+                    param.main_grad.add_(param.grad.to(param.main_grad.dtype))
+                param.grad_added_to_main_grad = True
                 param.grad = None
             if self.ddp_config.overlap_grad_reduce and self.is_last_microbatch:
                 buf.register_grad_ready(param)

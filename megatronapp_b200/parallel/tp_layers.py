@@ -214,6 +214,8 @@ class ColumnParallelLinear(nn.Module):
             else:
                 set_tensor_model_parallel_attributes(self.weight, True, 0, stride)
             setattr(self.weight, "allreduce", not (is_expert and config.expert_model_parallel_size > 1))
+            if config.gradient_accumulation_fusion and not is_expert:
+                self.weight.b200_wgrad_store_first = True
         else:
             self.weight = None
         if bias:
@@ -344,6 +346,8 @@ class RowParallelLinear(nn.Module):
         else:
             set_tensor_model_parallel_attributes(self.weight, True, 1, stride)
         setattr(self.weight, "allreduce", not (is_expert and config.expert_model_parallel_size > 1))
+        if config.gradient_accumulation_fusion and not is_expert:
+            self.weight.b200_wgrad_store_first = True
         if bias:
             self.bias = nn.Parameter(torch.zeros(output_size, dtype=config.params_dtype, device=dev))
             setattr(self.bias, "allreduce", not (is_expert and config.expert_model_parallel_size > 1))

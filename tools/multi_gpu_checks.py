@@ -1,0 +1,211 @@
+"""Multi-GPU checks of the fused compute+collective kernels (run under torchrun, N >= 2):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/multi_gpu_checks.py --out gpurun_out/multi.json
+
+Numerics: fused kernel vs (NCCL collective + fp32 matmul); timing: device events, max over
+ranks, against the unfused cuBLAS + NCCL sequence on the same tensors.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def rel_err(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6))
+
+
+def timed(fn, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "multi.json"))
+    ap.add_argument("--skip-model", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    from megatronapp_b200 import ops
+    from megatronapp_b200.comm.arena import SymmetricArena, TPFusedComm
+    from megatronapp_b200.parallel import state as ps
+
+    res = {"world": world}
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    group = ps.get_tensor_model_parallel_group()
+    dt = torch.bfloat16
+
+    def log(k, v):
+        res[k] = v
+        if rank == 0:
+            print(k, v, flush=True)
+
+    try:
+        shapes = [(2048, 4096, 16384 // world, "fc1"), (2048, 4096, 12288 // world, "qkv"), (8192, 4096, 16384 // world, "fc1_mbs4")]
+        arena = SymmetricArena(group, 2 * (2 * 8192 * 16384 * 2) + (8 << 20))
+        fc = TPFusedComm(arena, 8192, 16384, 16384)
+        arena.barrier()
+        torch.cuda.synchronize()
+        log("arena_ok", True)
+        # ---------------- AG -> GEMM (column parallel forward)
+        for (M, K, N, name) in shapes:
+            torch.manual_seed(100 + rank)
+            x_local = torch.randn(M // world, K, device="cuda", dtype=dt) * 0.5
+            torch.manual_seed(7)
+            w = torch.randn(N, K, device="cuda", dtype=dt) * 0.05
+            bias = torch.randn(N, device="cuda", dtype=dt)
+            full = torch.empty(M, K, device="cuda", dtype=dt)
+            dist.all_gather_into_tensor(full, x_local, group=group)
+            ref = full.float() @ w.float().t() + bias.float()
+            out, gathered = fc.ag_gemm(x_local, w, bias)
+            torch.cuda.synchronize()
+            log(f"ag_gemm_{name}_err", rel_err(out, ref))
+            log(f"ag_gemm_{name}_gather_err", rel_err(gathered, full))
+            outb = torch.empty(M, N, device="cuda", dtype=dt)
+
+            def unfused():
+                dist.all_gather_into_tensor(full, x_local, group=group)
+                ops.gemm(full, w, out=outb, bias=bias)
+
+            def cublas_unfused():
+                dist.all_gather_into_tensor(full, x_local, group=group)
+                torch.addmm(bias, full, w.t(), out=outb)
+
+            t_f = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb))
+            t_u = timed(unfused)
+            t_c = timed(cublas_unfused)
+            t_g = timed(lambda: ops.gemm(full, w, out=outb, bias=bias))
+            log(f"ag_gemm_{name}_ms", {"fused": t_f, "nccl+b200gemm": t_u, "nccl+cublas": t_c, "gemm_only": t_g,
+                                         "tflops_fused": 2.0 * M * N * K / t_f / 1e9})
+        # ---------------- GEMM -> RS (row parallel forward)
+        for (M, N, K, name) in [(2048, 4096, 16384 // world, "fc2"), (2048, 4096, 4096 // world, "proj"),
+                                (8192, 4096, 16384 // world, "fc2_mbs4")]:
+            torch.manual_seed(200 + rank)
+            x = torch.randn(M, K, device="cuda", dtype=dt) * 0.5
+            w = torch.randn(N, K, device="cuda", dtype=dt) * 0.05
+            part = (x.float() @ w.float().t())
+            ref = torch.empty(M // world, N, device="cuda", dtype=torch.float32)
+            dist.reduce_scatter_tensor(ref, part, group=group)
+            out = fc.gemm_rs(x, w)
+            torch.cuda.synchronize()
+            log(f"gemm_rs_{name}_err", rel_err(out, ref))
+            pb = torch.empty(M, N, device="cuda", dtype=dt)
+            ob = torch.empty(M // world, N, device="cuda", dtype=dt)
+
+            def unfused():
+                ops.gemm(x, w, out=pb)
+                dist.reduce_scatter_tensor(ob, pb, group=group)
+
+            def cublas_unfused():
+                torch.matmul(x, w.t(), out=pb)
+                dist.reduce_scatter_tensor(ob, pb, group=group)
+
+            t_f = timed(lambda: fc.gemm_rs(x, w))
+            t_u = timed(unfused)
+            t_c = timed(cublas_unfused)
+            t_g = timed(lambda: ops.gemm(x, w, out=pb))
+            log(f"gemm_rs_{name}_ms", {"fused": t_f, "b200gemm+nccl": t_u, "cublas+nccl": t_c, "gemm_only": t_g,
+                                         "tflops_fused": 2.0 * M * N * K / t_f / 1e9})
+        # dgrad duals (B MN-major)
+        M, K, N = 2048, 4096, 16384 // world
+        torch.manual_seed(300 + rank)
+        dy = torch.randn(M, N, device="cuda", dtype=dt) * 0.5
+        w = torch.randn(N, K, device="cuda", dtype=dt) * 0.05
+        part = dy.float() @ w.float()
+        ref = torch.empty(M // world, K, device="cuda", dtype=torch.float32)
+        dist.reduce_scatter_tensor(ref, part, group=group)
+        out = fc.gemm_rs(dy, w, b_mn=True)
+        log("gemm_rs_dgrad_err", rel_err(out, ref))
+        dyl = torch.randn(M // world, K, device="cuda", dtype=dt) * 0.5   # row-parallel dgrad: AG(dy) @ W[K_out, N_in]
+        w2 = torch.randn(K, N, device="cuda", dtype=dt) * 0.05
+        fulldy = torch.empty(M, K, device="cuda", dtype=dt)
+        dist.all_gather_into_tensor(fulldy, dyl, group=group)
+        ref2 = fulldy.float() @ w2.float()
+        out2, _ = fc.ag_gemm(dyl, w2, None, b_mn=True)
+        log("ag_gemm_dgrad_err", rel_err(out2, ref2))
+        # ---------------- fused bucket reduce-scatter (scale + cast + RS)
+        n = 64 * 1024 * 1024
+        torch.manual_seed(400 + rank)
+        g = torch.randn(n, device="cuda")
+        ref = torch.empty(n // world, device="cuda")
+        dist.reduce_scatter_tensor(ref, g / world, group=group)
+        for wire, wname in ((2, "fp32"), (0, "bf16")):
+            stage = arena.region(f"rs_stage_{wname}", n * 4)
+            flags = arena.region(f"rs_flags_{wname}", 4096)
+            outs = torch.empty(n // world, device="cuda")
+            ep = arena.next_epoch(flags)
+            ops.ext().bucket_reduce_scatter(g, outs, arena.ptrs(stage), arena.ptrs(flags), rank, world, 1.0 / world, ep, wire, 32)
+            torch.cuda.synchronize()
+            log(f"bucket_rs_{wname}_err", rel_err(outs, ref))
+
+            def fused():
+                e = arena.next_epoch(flags)
+                ops.ext().bucket_reduce_scatter(g, outs, arena.ptrs(stage), arena.ptrs(flags), rank, world, 1.0 / world, e, wire, 32)
+
+            def nccl():
+                g2 = g * (1.0 / world)
+                dist.reduce_scatter_tensor(ref, g2, group=group)
+
+            tf_, tn_ = timed(fused, 10, 3), timed(nccl, 10, 3)
+            log(f"bucket_rs_{wname}_ms", {"fused": tf_, "mul+nccl": tn_, "GBs_per_rank_fused": n * 4 * (world - 1) / world / tf_ / 1e6})
+        arena.barrier()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        log("EXCEPTION_kernels", traceback.format_exc()[-1500:])
+    # ---------------- model parity: fused TP path vs NCCL path (same weights, same data)
+    if not a.skip_model:
+        try:
+            from megatronapp_b200.bench_model import build_gpt_for_bench, synthetic_batch, train_step
+            from megatronapp_b200.parallel import tp_layers
+
+            ps.destroy_model_parallel()
+            st = build_gpt_for_bench(2, 1024, 8, 1024, 8192, 1, ffn=4096, tp=world, sequence_parallel=True, device="cuda")
+            b = synthetic_batch(st, "cuda")
+            sd = {k: v.clone() for k, v in st.model[0].module.module.state_dict().items()}
+            fused_losses = [train_step(st, [b, b]) for _ in range(3)]
+            log("fused_calls", dict(tp_layers.get_tp_fused_comm().calls) if tp_layers.get_tp_fused_comm() else None)
+            tp_layers.disable_tp_fused_comm()
+            ps.destroy_model_parallel()
+            st2 = build_gpt_for_bench(2, 1024, 8, 1024, 8192, 1, ffn=4096, tp=world, sequence_parallel=True,
+                                      device="cuda", fused_tp_comm=False)
+            st2.model[0].module.module.load_state_dict(sd)
+            st2.optimizer.reload_model_params()
+            nccl_losses = [train_step(st2, [b, b]) for _ in range(3)]
+            log("tp_model_losses", {"fused": fused_losses, "nccl": nccl_losses})
+        except Exception:  # noqa: BLE001
+            import traceback
+
+            log("EXCEPTION_model", traceback.format_exc()[-1500:])
+    if rank == 0:
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        json.dump(res, open(a.out, "w"), indent=1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
