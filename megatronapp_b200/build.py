@@ -64,7 +64,7 @@ def _torch_flags():
 def build_all(verbose: bool = False, force: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
     headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
-    cu_sources = sorted(CSRC.glob("*.cu"))
+    cu_sources = sorted(CSRC.glob("*.cu")) + [p for p in sorted(CSRC.glob("*.cpp")) if p.name != "bindings.cpp"]
     stamp_path = BUILD / "stamps.json"
     stamps = json.loads(stamp_path.read_text()) if stamp_path.exists() else {}
     nvcc = _nvcc()
@@ -106,7 +106,7 @@ def build_all(verbose: bool = False, force: bool = False) -> Path:
     if force or jobs or not so.exists() or stamps.get("_C.so") != link_key:
         cmd = ["g++", "-shared", "-o", str(so), *map(str, objs), f"-L{libdir}", f"-L{cuda_home}/lib64",
                "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
-               "-lcudart", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda_home}/lib64"]
+               "-lcudart", "-lrt", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda_home}/lib64"]
         _run(cmd)
         stamps["_C.so"] = link_key
     # dataset index helpers (pure C++ / pybind11)

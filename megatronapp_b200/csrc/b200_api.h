@@ -163,4 +163,14 @@ void wait_flags(const uint32_t* flags, int n, uint32_t target, cudaStream_t s);
 void spin_kernel(int64_t cycles, cudaStream_t s);  // MegaScan software slow-rank injector
 void write_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
 
+// MegaDPP mailbox (mailbox.cpp)
+int mailbox_create(int n_slots, size_t slot_bytes, const char* shm_name, void* ipc_handle_out64);
+int mailbox_connect(int id, const void* peer_ipc_handle64, const char* peer_shm_name);
+int mailbox_put(int id, int slot, const void* src, size_t nbytes, uint32_t epoch, cudaStream_t s);
+bool mailbox_try_get(int id, int slot, uint32_t epoch);
+void* mailbox_slot_ptr(int id, int slot);
+long mailbox_sent(int id);
+void mailbox_destroy(int id);
+const char* mailbox_last_error();
+
 }  // namespace b200

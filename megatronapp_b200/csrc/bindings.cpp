@@ -464,6 +464,34 @@ int64_t host_register(int64_t host_ptr, int64_t nbytes) {
 }
 void host_unregister(int64_t host_ptr) { cudaHostUnregister(reinterpret_cast<void*>(host_ptr)); }
 
+// ---------------------------------------------------------------- MegaDPP mailbox
+py::tuple mailbox_create(int n_slots, int64_t slot_bytes, const std::string& shm_name) {
+  char h[64];
+  int id = b200::mailbox_create(n_slots, static_cast<size_t>(slot_bytes), shm_name.c_str(), h);
+  TORCH_CHECK(id > 0, "mailbox_create failed: ", b200::mailbox_last_error());
+  return py::make_tuple(id, py::bytes(h, 64));
+}
+void mailbox_connect(int id, py::bytes peer_handle, const std::string& peer_shm) {
+  std::string s = peer_handle;
+  TORCH_CHECK(s.size() == 64, "bad IPC handle");
+  TORCH_CHECK(b200::mailbox_connect(id, s.data(), peer_shm.c_str()) == 0, "mailbox_connect failed: ", b200::mailbox_last_error());
+}
+void mailbox_put(int id, int slot, const Tensor& t, int64_t epoch) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous());
+  c10::cuda::CUDAGuard guard(t.device());
+  TORCH_CHECK(b200::mailbox_put(id, slot, t.data_ptr(), t.nbytes(), static_cast<uint32_t>(epoch), cur_stream()) == 0,
+              "mailbox_put failed: ", b200::mailbox_last_error());
+  count();
+}
+bool mailbox_try_get(int id, int slot, int64_t epoch) { return b200::mailbox_try_get(id, slot, static_cast<uint32_t>(epoch)); }
+Tensor mailbox_slot_tensor(int id, int slot, std::vector<int64_t> shape, py::object dtype, int64_t device) {
+  auto st = torch::python::detail::py_object_to_dtype(dtype);
+  auto opts = torch::TensorOptions().dtype(st).device(torch::kCUDA, static_cast<int>(device));
+  return torch::from_blob(b200::mailbox_slot_ptr(id, slot), shape, [](void*) {}, opts);
+}
+int64_t mailbox_sent(int id) { return b200::mailbox_sent(id); }
+void mailbox_destroy(int id) { b200::mailbox_destroy(id); }
+
 int64_t launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches.store(0); }
 
@@ -510,6 +538,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("peer_copy", &peer_copy);
   m.def("host_register", &host_register);
   m.def("host_unregister", &host_unregister);
+  m.def("mailbox_create", &mailbox_create);
+  m.def("mailbox_connect", &mailbox_connect);
+  m.def("mailbox_put", &mailbox_put);
+  m.def("mailbox_try_get", &mailbox_try_get);
+  m.def("mailbox_slot_tensor", &mailbox_slot_tensor);
+  m.def("mailbox_sent", &mailbox_sent);
+  m.def("mailbox_destroy", &mailbox_destroy);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
 }
