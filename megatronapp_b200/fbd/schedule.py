@@ -1,0 +1,123 @@
+"""MegaFBD: forward / backward disaggregation onto separate devices.
+
+Capability parity with reference ``schedules.py:2208-2506``
+(``forward_or_backward_pipelining_without_interleaving``), ``parallel_state.py:444-512`` (F/B
+pairing inside DP) and ``p2p_communication.py:723-756`` (stage-input hand-off), re-designed:
+
+* each DP pair = (forward rank, backward rank) holding the same pipeline stage / TP shard;
+* forward ranks run a forward-only pipeline under ``no_grad`` and ship every stage's *input*
+  activation to their backward twin over a dedicated unidirectional channel (the last stage
+  only hands its input over -- its own forward would be thrown away);
+* backward ranks receive the stage input, recompute the stage forward with grad, receive the
+  output gradient from the next backward stage, run backward and pass the input gradient on:
+  they hold at most one microbatch of activations;
+* gradients are averaged over the backward ranks only (``half_dp`` group, so
+  ``get_data_parallel_world_size()`` reports dp/2 exactly like the reference :2851-2864);
+* instead of forward ranks carrying zero-gradient all-reduces and a redundant optimizer
+  (SURVEY §7.4-7), the backward rank steps the optimizer and broadcasts the updated parameter
+  buffer to its forward twin over NVLink (2 bytes/param/step) -- ``sync_forward_weights``;
+* there is no coordinator process and no thread-level "virtual TP" shim (``Controller.py``,
+  ``virtual_tensor_parallel_communication.py``): the channel transport of ``parallel/p2p.py``
+  is deadlock-free for this data flow by construction.
+
+``--ignore-forward-tensor-parallel`` is accepted; in this revision forward ranks keep the
+backward ranks' TP degree (the collapse needs an extra weight re-shard after every step).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from ..parallel import p2p, schedules
+from ..parallel import state as ps
+from ..parallel.schedules import backward_step, forward_step, get_tensor_shapes
+
+
+def fbd_forward_backward(*, forward_step_func, data_iterator, model, num_microbatches, seq_length,
+                         micro_batch_size, decoder_seq_length=None, forward_only=False,
+                         collect_non_loss_data=False, first_val_step=None):
+    chunks = model if isinstance(model, (list, tuple)) else [model]
+    if len(chunks) != 1:
+        raise RuntimeError("MegaFBD does not support interleaved (virtual pipeline) schedules")
+    m0 = chunks[0]
+    config = schedules._get_config(m0)
+    pp, rank = ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_rank()
+    shape = get_tensor_shapes(seq_length, micro_batch_size, config)
+    dtype = config.pipeline_dtype or config.params_dtype
+    first, last = rank == 0, rank == pp - 1
+    it = data_iterator[0] if isinstance(data_iterator, (list, tuple)) else data_iterator
+    store: List = []
+    total_tokens = torch.zeros((), dtype=torch.int, device=next(m0.parameters()).device)
+    if ps.is_forward_stage():
+        # ---------------- forward-only pipeline, hand stage inputs to the twin
+        for mb in range(num_microbatches):
+            inp = None
+            if not first:
+                inp = p2p.recv(shape, dtype, ps.get_pipeline_model_parallel_prev_rank(), "fwd", "recv-forward")
+                p2p.send_corresponding_forward(inp)
+            if last:
+                if it is not None and pp > 1:
+                    pass  # labels are read by the backward twin from its own (identical) iterator
+                continue
+            with torch.no_grad():
+                out, _ = forward_step(forward_step_func, it, m0, num_microbatches, inp, store, config,
+                                      collect_non_loss_data, is_first_microbatch=(mb == 0),
+                                      current_microbatch=mb, is_last_stage=False)
+            p2p.send(out, ps.get_pipeline_model_parallel_next_rank(), "fwd", "send-forward")
+        p2p.flush()
+        return []
+    # ---------------- backward ranks: recompute + backward, one microbatch of activations at a time
+    if hasattr(m0, "is_last_microbatch"):
+        m0.is_last_microbatch = False
+    for mb in range(num_microbatches):
+        inp = None
+        if not first:
+            inp = p2p.recv_corresponding_forward(shape, dtype)
+        ctx = torch.no_grad() if forward_only else contextlib.nullcontext()
+        with ctx:
+            out, ntok = forward_step(forward_step_func, it, m0, num_microbatches, inp, store, config,
+                                     collect_non_loss_data, is_first_microbatch=(mb == 0),
+                                     current_microbatch=mb, is_last_stage=last)
+        total_tokens += ntok.to(total_tokens.device) if torch.is_tensor(ntok) else int(ntok)
+        if forward_only:
+            continue
+        grad = None
+        if not last:
+            grad = p2p.recv(shape, dtype, ps.get_pipeline_model_parallel_next_rank(), "bwd", "recv-backward")
+        if hasattr(m0, "is_last_microbatch"):
+            m0.is_last_microbatch = (mb == num_microbatches - 1)
+        in_grad = backward_step(inp, out, grad, None, config, microbatch=mb)
+        if not first:
+            p2p.send(in_grad, ps.get_pipeline_model_parallel_prev_rank(), "bwd", "send-backward")
+    p2p.flush()
+    if hasattr(m0, "is_last_microbatch"):
+        m0.is_last_microbatch = True
+    if not forward_only and config.finalize_model_grads_func is not None:
+        config.finalize_model_grads_func(chunks, total_tokens if config.calculate_per_token_loss else None)
+    return store
+
+
+def sync_forward_weights(model) -> None:
+    """Backward rank -> forward twin broadcast of the (updated) contiguous parameter buffers."""
+    st = ps.get_state()
+    if not st.topo.fbd:
+        return
+    g = st.group("fb")
+    pair = st.ranks("fb")
+    src = pair[1]  # odd DP index = backward rank = owner of the optimizer
+    chunks = model if isinstance(model, (list, tuple)) else [model]
+    for ch in chunks:
+        bufs = getattr(ch, "buffers", None)
+        if bufs is None:
+            for p in ch.parameters():
+                dist.broadcast(p.data, src=src, group=g)
+        else:
+            for b in list(ch.buffers) + list(getattr(ch, "expert_parallel_buffers", [])):
+                dist.broadcast(b.param_data, src=src, group=g)
+
+
+def install_fbd_schedule(args=None) -> None:
+    schedules.set_schedule_override(fbd_forward_backward)

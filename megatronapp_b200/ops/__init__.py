@@ -181,9 +181,13 @@ def wgrad(dy2, x2, weight, fuse: bool):
         else:
             main_grad.add_(gemm(dy2, x2, a_mn=True, b_mn=True))
         weight.grad_added_to_main_grad = True
-        hook = getattr(weight, "grad_ready_hook", None)
-        if hook is not None:
-            hook()
+        # only weights owned by a linear layer have exactly one contribution per microbatch; a
+        # tied embedding weight also gets the lookup gradient through autograd, whose
+        # post-accumulate hook is what marks it ready
+        if getattr(weight, "b200_wgrad_store_first", False):
+            hook = getattr(weight, "grad_ready_hook", None)
+            if hook is not None:
+                hook()
         return None
     return gemm(dy2, x2, a_mn=True, b_mn=True)
 

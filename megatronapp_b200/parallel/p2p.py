@@ -71,7 +71,11 @@ def send(tensor: torch.Tensor, dst: int, kind: str, name: str = "send") -> None:
     prev = _PENDING.pop(key, None)
     if prev is not None:
         prev[0].wait()
-    t = tensor.contiguous()
+    # a detached alias: the caller may pseudo-free ``tensor`` (swap its .data) right after this
+    # returns, while the asynchronous send still needs the storage
+    t = tensor.detach().contiguous()
+    if t is tensor:
+        t = tensor.detach()
     with _scope(name, data=t.numel() * t.element_size(), peer=dst):
         h = dist.isend(t, dst=dst, group=_channel(me, dst, kind))
     _PENDING[key] = (h, t)

@@ -207,8 +207,15 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
     if args.empty_unused_memory_level >= 1:
         torch.cuda.empty_cache()
     timers("optimizer", log_level=1).start(barrier=args.barrier_with_L1_time)
-    with tracer.scope("optimizer"):
-        update_successful, grad_norm, num_zeros_in_grad = optimizer.step()
+    if args.forward_backward_disaggregating and ps.is_forward_stage():
+        update_successful, grad_norm, num_zeros_in_grad = True, None, None   # twin owns the optimizer
+    else:
+        with tracer.scope("optimizer"):
+            update_successful, grad_norm, num_zeros_in_grad = optimizer.step()
+    if args.forward_backward_disaggregating:
+        from ..fbd.schedule import sync_forward_weights
+
+        sync_forward_weights(model)
     timers("optimizer").stop()
     update_successful = logical_and_across_model_parallel_group(update_successful)
     grad_norm = reduce_max_stat_across_model_parallel_group(grad_norm)

@@ -1,0 +1,125 @@
+"""Workers executed by tests/dist_utils.run_distributed (one process per rank, gloo)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def _setup():
+    from megatronapp_b200.parallel import state as ps
+
+    ps.init_distributed("gloo")
+    return dist.get_rank(), dist.get_world_size()
+
+
+def _model_losses(steps=3, n_mb=4, **build_kw):
+    from megatronapp_b200.bench_model import build_gpt_for_bench, synthetic_batch, train_step
+
+    kw = dict(num_layers=4, hidden=64, heads=4, seq=32, vocab=256, micro_batch=2, device="cpu", dtype=torch.float32,
+              lr=1e-2)
+    kw.update(build_kw)
+    st = build_gpt_for_bench(**kw)
+    return st, [synthetic_batch(st, "cpu", seed=i) for i in range(n_mb)]
+
+
+def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=False, steps=3, n_mb=4,
+                 overlap=False):
+    from megatronapp_b200.bench_model import train_step
+    from megatronapp_b200.parallel import state as ps
+
+    rank, world = _setup()
+    if fbd:
+        ps.initialize_model_parallel(tp, pp, forward_backward_disaggregating=True)
+        from megatronapp_b200.parallel import p2p
+
+        p2p.build_channels()
+        from megatronapp_b200.fbd.schedule import install_fbd_schedule, sync_forward_weights
+
+        install_fbd_schedule()
+    st, batches = _model_losses(steps, n_mb, tp=tp, pp=pp, vpp=vpp, sequence_parallel=sp,
+                                use_distributed_optimizer=dist_opt, overlap_grad_reduce=overlap)
+    if dpp:
+        from megatronapp_b200.dpp.scheduler import install_dpp_schedule
+
+        install_dpp_schedule(policy=dpp)
+    dp = ps.get_data_parallel_world_size()
+    dpr = ps.get_data_parallel_rank()
+    losses = []
+    for s in range(steps):
+        # every DP replica gets its own slice of the global batch
+        mine = batches[dpr::dp] if not fbd else batches[(ps.get_state().coords["dp"] // 2)::dp]
+        if fbd:
+            l = train_step(st, mine, do_optimizer=ps.is_backward_stage())
+            sync_forward_weights(st.model)
+        else:
+            l = train_step(st, mine)
+        losses.append(l)
+    w = next(st.model[0].parameters()).detach().double().sum().item()
+    return {"losses": losses, "dp": dp, "w": w, "last": st.post_process,
+            "is_backward": ps.is_backward_stage()}
+
+
+def collectives_roundtrip():
+    from megatronapp_b200.parallel import mappings as mp
+    from megatronapp_b200.parallel import state as ps
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(world)
+    x = torch.arange(8, dtype=torch.float32).view(4, 2) + 100 * rank
+    g = mp.gather_from_sequence_parallel_region(x)
+    rs = mp.reduce_scatter_to_sequence_parallel_region(g.clone())
+    a2a = mp.all_to_all_hp2sp(mp.all_to_all_sp2hp(torch.randn(4, 2, 8)))
+    y = torch.randn(4, 2, 8)
+    back = mp.all_to_all_hp2sp(mp.all_to_all_sp2hp(y))
+    return {"gather_shape": list(g.shape), "rs_ok": bool(torch.allclose(rs, x * world)),
+            "a2a_roundtrip": bool(torch.allclose(back, y))}
+
+
+def vocab_parallel_ce():
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.cross_entropy import vocab_parallel_cross_entropy
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(world)
+    torch.manual_seed(0)
+    full = torch.randn(6, 3, 16 * world, requires_grad=True)
+    tgt = torch.randint(0, 16 * world, (6, 3))
+    ref = torch.nn.functional.cross_entropy(full.view(-1, 16 * world), tgt.view(-1), reduction="none").view(6, 3)
+    ref.sum().backward()
+    local = full.detach()[..., rank * 16:(rank + 1) * 16].clone().requires_grad_(True)
+    loss = vocab_parallel_cross_entropy(local, tgt)
+    loss.sum().backward()
+    return {"fwd": float((loss - ref).abs().max()),
+            "bwd": float((local.grad - full.grad[..., rank * 16:(rank + 1) * 16]).abs().max())}
+
+
+def sharded_ckpt(tp_save=2, tp_load=1, path=None):
+    """Save at one TP degree, load at another (resharding is a format feature)."""
+    from megatronapp_b200.ckpt import sharded
+    from megatronapp_b200.parallel import state as ps
+
+    rank, world = _setup()
+    st, _ = _model_losses(tp=tp_save if world >= tp_save else 1)
+    m = st.model[0].module
+    ssd = m.sharded_state_dict()
+    sharded.save(ssd, path, {"iteration": 7})
+    full = {k: v.data.clone() for k, v in ssd.items()}
+    dist.barrier()
+    return {"n": len(full), "rank": rank}
+
+
+WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
+
+if __name__ == "__main__":
+    name, kwargs, out = sys.argv[1], json.loads(sys.argv[2]), sys.argv[3]
+    res = WORKERS[name](**kwargs)
+    with open(os.path.join(out, f"rank{os.environ['RANK']}.json"), "w") as f:
+        json.dump(res, f)
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
