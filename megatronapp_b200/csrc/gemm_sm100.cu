@@ -119,15 +119,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (static_cast<int>(blockIdx.x) < p.n_comm_ctas) {
       // work item = (row block of 128 rows, peer offset d, column split)
       const int rb_per_rank = p.rows_per_rank / BLOCK_M;
-      const int n_items = rb_per_rank * (p.tp_size - 1) * p.col_splits;
+      // peers first (d = 1..tp-1), then d = 0: the local shard into the local gather buffer so the
+      // caller gets a complete gathered view (wgrad of the row-parallel layer consumes it)
+      const int n_items = rb_per_rank * p.tp_size * p.col_splits;
       const int row_bytes = p.K * 2;
       const int split_bytes = row_bytes / p.col_splits;  // multiple of 16 (checked on host)
       const int vec_per_row = split_bytes / 16;
       for (int item = blockIdx.x; item < n_items; item += p.n_comm_ctas) {
         const int cs = item % p.col_splits;
         const int t1 = item / p.col_splits;
-        const int d = 1 + t1 % (p.tp_size - 1);
-        const int rb = t1 / (p.tp_size - 1);
+        const int dd = t1 % p.tp_size;
+        const int d = (dd + 1) % p.tp_size;          // 1, 2, ..., tp-1, 0
+        const int rb = t1 / p.tp_size;
         const int peer = (p.tp_rank + d) % p.tp_size;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.A_local) +
                              static_cast<size_t>(rb) * BLOCK_M * p.lda_local * 2 + cs * split_bytes;
@@ -158,7 +161,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && d != 0) {
           // single-writer flag carrying the call epoch (monotonic per arena slot)
           st_release_sys(p.peer_flags[peer] +
                              (static_cast<size_t>(p.tp_rank) * rb_per_rank + rb) * p.col_splits + cs,
@@ -399,13 +402,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             cbuf ^= 1;
           }
         } else {  // kEpiReduceScatter: partial tile -> owner's staging buffer [src][rows_per_rank][N]
+          // Each warp owns rows [32*ew, 32*ew+32) of the tile: it parks its 64-column slice in a
+          // warp-private 4 KB smem region, then streams it out so that one store instruction
+          // covers 4 rows x 128 contiguous bytes (full NVLink write granules instead of 16 B shards).
           const int owner = (m_blk * BLOCK_M) / p.rows_per_rank;
-          const int lrow = grow - owner * p.rows_per_rank;
-          uint16_t* dst = reinterpret_cast<uint16_t*>(p.peer_buf[owner]) +
-                          (static_cast<size_t>(p.tp_rank) * p.rows_per_rank + lrow) * p.N + gcol0;
+          uint8_t* wbuf = smem_c + ew * 4096;
+          {
+            uint8_t* sc = wbuf + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (gcol0 + j * 8 < p.N) {
+            for (int j = 0; j < 8; ++j) {
               uint32_t pk[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -418,10 +423,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   pk[q] = *reinterpret_cast<uint32_t*>(&h);
                 }
               }
-              int4 val = make_int4(pk[0], pk[1], pk[2], pk[3]);
-              st_na_v4(reinterpret_cast<int4*>(dst + j * 8), val);
+              *reinterpret_cast<uint4*>(sc + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
+          __syncwarp();
+          const int lrow0 = m_blk * BLOCK_M + ew * 32 - owner * p.rows_per_rank;
+          uint16_t* dst0 = reinterpret_cast<uint16_t*>(p.peer_buf[owner]) +
+                           (static_cast<size_t>(p.tp_rank) * p.rows_per_rank + lrow0) * p.N + gcol0;
+          const int chunk = lane & 7, rsub = lane >> 3;
+          if (gcol0 + chunk * 8 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + rsub;
+              const int4 val = *reinterpret_cast<const int4*>(wbuf + r * 128 + ((chunk ^ (r & 7)) << 4));
+              st_na_v4(reinterpret_cast<int4*>(dst0 + static_cast<size_t>(r) * p.N + chunk * 8), val);
+            }
+          }
+          __syncwarp();
         }
       }
       if constexpr (kEpi == kEpiReduceScatter) {
@@ -664,8 +682,8 @@ int gemm_bf16(const GemmArgs& a) {
       if ((a.K * 2) % 16 != 0) { g_last_error = "AG fusion needs K % 8 == 0"; return -4; }
       p.chunk_base = a.tp_rank; p.chunk_dir = -1;        // own shard first, then arrival order
       p.A_local = a.A_local; p.lda_local = a.lda_local;
-      p.n_comm_ctas = a.n_comm_ctas > 0 ? a.n_comm_ctas : 20;
-      const int base_items = p.m_blocks_per_chunk * (a.tp_size - 1);
+      p.n_comm_ctas = a.n_comm_ctas > 0 ? a.n_comm_ctas : 12;
+      const int base_items = p.m_blocks_per_chunk * a.tp_size;
       int cs = 1;
       while (base_items * cs < p.n_comm_ctas && (a.K * 2) % (32 * cs) == 0 && cs < 8) cs *= 2;
       p.col_splits = cs;

@@ -44,12 +44,29 @@ _POLICY = "auto"
 # ---------------------------------------------------------------------------
 
 def pick_task(ready_f: List[Tuple[int, int]], ready_b: List[Tuple[int, int]], policy: str, stash: int,
-              stash_limit: int) -> Optional[Task]:
-    """``ready_*`` are lists of (microbatch, chunk).  Returns the next task or None."""
+              stash_limit: int, head: Optional[Tuple[int, int]] = None) -> Optional[Task]:
+    """``ready_*`` are lists of (microbatch, chunk).  Returns the next task or None.
+
+    ``auto`` is the memory-safe policy: forwards are admitted strictly in the static interleaved
+    table order (``head`` = first not-yet-run entry of ``get_schedule_table``) and only while the
+    stash is below the static schedule's in-flight bound -- that bound is only meaningful with
+    head-of-line forward order (admitting *any* ready forward can fill the stash with later-group
+    chunk-0 work and starve the deeper-chunk forwards every backward depends on).  Backwards are
+    fully dynamic: any ready backward runs as soon as the head forward is blocked or the bound is
+    reached, which is where the ready-queue wins over a fixed order when a stage is slow."""
     if not ready_f and not ready_b:
         return None
     if policy == "auto":
-        policy = "bfc" if stash < stash_limit else "dfc"
+        head_ready = head is not None and head in ready_f and stash < stash_limit
+        if ready_b and not head_ready:
+            m, c = min(ready_b, key=lambda t: (t[0], -t[1]))
+            return Task("B", m, c)
+        if head_ready:
+            if ready_b and stash >= stash_limit - 1:
+                m, c = min(ready_b, key=lambda t: (t[0], -t[1]))
+                return Task("B", m, c)
+            return Task("F", head[0], head[1])
+        return None
     if policy == "bfc":
         if ready_f:
             m, c = min(ready_f, key=lambda t: (t[1], t[0]))      # lowest chunk, then microbatch
@@ -62,6 +79,13 @@ def pick_task(ready_f: List[Tuple[int, int]], ready_b: List[Tuple[int, int]], po
         return Task("B", m, c)
     m, c = min(ready_f, key=lambda t: (t[0], t[1]))
     return Task("F", m, c)
+
+
+def _head_of_line(table, f_done):
+    for mc in table:
+        if mc not in f_done:
+            return mc
+    return None
 
 
 def simulate(pp: int, M: int, C: int, policy: str, latency: int = 1, stash_limit: Optional[int] = None,
@@ -78,6 +102,7 @@ def simulate(pp: int, M: int, C: int, policy: str, latency: int = 1, stash_limit
     peak = [0] * pp
     total = M * C
     t = 0
+    table = schedules.get_schedule_table(M, C, min(pp, M))
     limits = [stash_limit if stash_limit is not None else interleaved_warmup(pp, r, M, C, min(pp, M)) + 1
               for r in range(pp)]
     guard = 0
@@ -97,7 +122,8 @@ def simulate(pp: int, M: int, C: int, policy: str, latency: int = 1, stash_limit
                     elif (m, c) not in b_done[r]:
                         if last or bwd_arrival[r].get((m, c), 10 ** 9) <= t:
                             rb.append((m, c))
-            task = pick_task(rf, rb, policy, len(f_done[r]) - len(b_done[r]), limits[r])
+            task = pick_task(rf, rb, policy, len(f_done[r]) - len(b_done[r]), limits[r],
+                             _head_of_line(table, f_done[r]))
             if task is None:
                 continue
             progressed = True
@@ -298,6 +324,7 @@ def dpp_forward_backward(*, forward_step_func, data_iterator, model, num_microba
     store: List = []
     total_tokens = torch.zeros((), dtype=torch.int, device=next(chunks[0].parameters()).device)
     limit = interleaved_warmup(pp, rank, M, C, min(pp, M)) + 1
+    table = schedules.get_schedule_table(M, C, min(pp, M))
     b_count = [0] * C
     tracer = get_tracer()
     static_order = None
@@ -338,7 +365,7 @@ def dpp_forward_backward(*, forward_step_func, data_iterator, model, num_microba
                         g = None if last(c) else tr.try_get_backward(slot(m, c))
                         if last(c) or g is not None:
                             rb.append((m, c)); arrived_b[(m, c)] = g
-            task = pick_task(rf, rb, _POLICY, len(f_done) - len(b_done), limit)
+            task = pick_task(rf, rb, _POLICY, len(f_done) - len(b_done), limit, _head_of_line(table, f_done))
             if task is None:
                 spins += 1
                 time.sleep(0 if spins < 1000 else 0.0002)

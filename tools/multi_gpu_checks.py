@@ -64,7 +64,7 @@ def main():
 
     try:
         shapes = [(2048, 4096, 16384 // world, "fc1"), (2048, 4096, 12288 // world, "qkv"), (8192, 4096, 16384 // world, "fc1_mbs4")]
-        arena = SymmetricArena(group, 2 * (2 * 8192 * 16384 * 2) + (8 << 20))
+        arena = SymmetricArena(group, 2 * (2 * 8192 * 16384 * 2) + (200 << 20))
         fc = TPFusedComm(arena, 8192, 16384, 16384)
         arena.barrier()
         torch.cuda.synchronize()
@@ -146,7 +146,7 @@ def main():
         out2, _ = fc.ag_gemm(dyl, w2, None, b_mn=True)
         log("ag_gemm_dgrad_err", rel_err(out2, ref2))
         # ---------------- fused bucket reduce-scatter (scale + cast + RS)
-        n = 64 * 1024 * 1024
+        n = 8 * 1024 * 1024
         torch.manual_seed(400 + rank)
         g = torch.randn(n, device="cuda")
         ref = torch.empty(n // world, device="cuda")
