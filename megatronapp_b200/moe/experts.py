@@ -1,0 +1,98 @@
+"""Expert FFNs: ``SequentialMLP`` (one MLP module per local expert) and ``GroupedMLP`` (stacked
+weights, one tcgen05 GEMM per expert slice of the sorted token buffer).
+
+Parity: reference ``transformer/moe/experts.py`` (``GroupedMLP`` :90-265 with weight1
+``[h, E_local * ffn(*2)]`` / weight2 ``[E_local * ffn, h]``, ``SequentialMLP`` :856).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..parallel import state as ps
+from ..parallel.random import get_cuda_rng_tracker
+from ..transformer.mlp import MLP, MLPSubmodules
+from ..transformer.module import MegatronModule
+
+
+class SequentialMLP(MegatronModule):
+    def __init__(self, num_local_experts, config, submodules: MLPSubmodules):
+        super().__init__(config)
+        self.add_bias = config.add_bias_linear
+        self.num_local_experts = num_local_experts
+        self.local_experts = nn.ModuleList([MLP(config, submodules, is_expert=True) for _ in range(num_local_experts)])
+
+    def forward(self, permuted_local_hidden_states, tokens_per_expert, permuted_probs=None):
+        if self.num_local_experts == 1:
+            out, bias = self.local_experts[0](permuted_local_hidden_states)
+            return out, bias
+        sizes = tokens_per_expert.tolist()
+        outs = []
+        for expert, chunk in zip(self.local_experts, torch.split(permuted_local_hidden_states, sizes)):
+            if chunk.shape[0] == 0:
+                outs.append(chunk.new_zeros(0, self.config.hidden_size))
+                continue
+            o, b = expert(chunk)
+            if b is not None:
+                o = o + b
+            outs.append(o)
+        return torch.cat(outs, dim=0), None
+
+
+class GroupedMLP(MegatronModule):
+    def __init__(self, num_local_experts, config, submodules: Optional[MLPSubmodules] = None):
+        super().__init__(config)
+        self.num_local_experts = num_local_experts
+        if config.add_bias_linear:
+            raise ValueError("bias is not supported in GroupedMLP; use --disable-bias-linear")
+        etp = ps.get_expert_tensor_parallel_world_size()
+        ffn = config.moe_ffn_hidden_size // etp
+        self.ffn = ffn
+        self.glu = config.gated_linear_unit
+        fc1_out = ffn * (2 if self.glu else 1)
+        dev = "cpu" if (config.use_cpu_initialization or not torch.cuda.is_available()) else torch.cuda.current_device()
+        # stored per expert as [out, in] rows (K-major for the forward GEMM)
+        self.weight1 = nn.Parameter(torch.empty(num_local_experts * fc1_out, config.hidden_size,
+                                                dtype=config.params_dtype, device=dev))
+        self.weight2 = nn.Parameter(torch.empty(num_local_experts * config.hidden_size, ffn,
+                                                dtype=config.params_dtype, device=dev))
+        tr = get_cuda_rng_tracker()
+        ctx = tr.fork("expert-parallel-rng") if "expert-parallel-rng" in tr.states_ else torch.random.fork_rng(devices=[])
+        with ctx:
+            config.init_method(self.weight1)
+            config.output_layer_init_method(self.weight2)
+        for w, dim in ((self.weight1, 0), (self.weight2, 1)):
+            w.tensor_model_parallel, w.partition_dim, w.partition_stride = True, dim, 1
+            w.allreduce = not (config.expert_model_parallel_size > 1)
+        self.fc1_out = fc1_out
+
+    def forward(self, permuted_local_hidden_states, tokens_per_expert, permuted_probs=None):
+        x = permuted_local_hidden_states
+        sizes = tokens_per_expert.tolist()
+        h = self.config.hidden_size
+        outs = []
+        off = 0
+        for e, n in enumerate(sizes):
+            chunk = x[off:off + n]
+            off += n
+            if n == 0:
+                outs.append(x.new_zeros(0, h))
+                continue
+            w1 = self.weight1[e * self.fc1_out:(e + 1) * self.fc1_out]
+            w2 = self.weight2[e * h:(e + 1) * h]
+            inter = ops.linear(chunk, w1)
+            inter = ops.swiglu(inter) if (self.glu and self.config.activation_func is F.silu) else (
+                self._glu(inter) if self.glu else self._act(inter))
+            outs.append(ops.linear(inter, w2))
+        return torch.cat(outs, dim=0), None
+
+    def _act(self, t):
+        return ops.bias_gelu(t) if self.config.activation_func is F.gelu else self.config.activation_func(t)
+
+    def _glu(self, t):
+        g, u = t.chunk(2, dim=-1)
+        return self.config.activation_func(g) * u

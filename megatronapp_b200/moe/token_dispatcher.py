@@ -1,0 +1,307 @@
+"""MoE token dispatchers.
+
+Parity: reference ``transformer/moe/token_dispatcher.py`` -- ``MoEAllGatherTokenDispatcher``
+(:114-246), ``MoEAlltoAllTokenDispatcher`` (:248-706: permute -> all_to_all over EP -> optional
+TP all-gather -> sort by local expert -> experts -> reverse) and the DeepEP-style ``flex``
+dispatcher (:753-909) whose role here is taken by ``MoEPeerScatterDispatcher``: routed rows are
+written straight into the expert owner's capacity-padded buffer by the sm_100a
+``a2a_scatter_rows`` kernel over the EP symmetric arena, with device-side offsets (no
+host-synchronised split sizes, reference ``_maybe_dtoh_and_synchronize :669``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..parallel import state as ps
+from ..parallel.mappings import (_gather_along_first_dim, _reduce_scatter_along_first_dim, all_to_all,
+                                 gather_from_sequence_parallel_region, reduce_scatter_to_sequence_parallel_region)
+from .moe_utils import permute, sort_chunks_by_idxs, unpermute
+
+
+def _ws(g):
+    return 1 if (g is None or isinstance(g, ps._SingleGroup) or not dist.is_initialized()) else dist.get_world_size(g)
+
+
+class MoETokenDispatcher:
+    def __init__(self, config):
+        self.config = config
+        self.ep_group = ps.get_expert_model_parallel_group(check_initialized=False)
+        self.ep_size = ps.get_expert_model_parallel_world_size()
+        self.ep_rank = ps.get_expert_model_parallel_rank()
+        self.etp_group = ps.get_expert_tensor_parallel_group(check_initialized=False)
+        self.etp_size = ps.get_expert_tensor_parallel_world_size()
+        self.shared_experts = None
+
+    def set_shared_experts(self, shared):
+        self.shared_experts = shared
+
+
+class MoEAllGatherTokenDispatcher(MoETokenDispatcher):
+    """Gather every token (and its routing) across the TPxEP group; each rank keeps the tokens
+    routed to its local experts; outputs are reduce-scattered back."""
+
+    def __init__(self, num_local_experts, local_expert_indices, config):
+        super().__init__(config)
+        self.num_local_experts, self.local_expert_indices = num_local_experts, local_expert_indices
+        self.tp_ep_group = ps.get_expert_tensor_and_model_parallel_group(check_initialized=False)
+        self.tp_ep_size = _ws(self.tp_ep_group)
+
+    def token_permutation(self, hidden_states, probs, routing_map):
+        self.hidden_shape = hidden_states.shape
+        x = hidden_states.view(-1, self.hidden_shape[-1])
+        if self.tp_ep_size > 1:
+            routing_map = _gather_along_first_dim(routing_map.to(torch.uint8), self.tp_ep_group).bool()
+            probs = _GatherFirstDimAutograd.apply(probs, self.tp_ep_group)
+            x = _GatherFirstDimAutograd.apply(x, self.tp_ep_group)
+        self.hidden_shape_before_permute = x.shape
+        lo, hi = self.local_expert_indices[0], self.local_expert_indices[-1] + 1
+        self.local_map = routing_map[:, lo:hi].contiguous()
+        self.local_probs = probs[:, lo:hi].contiguous()
+        tokens_per_expert = self.local_map.sum(dim=0).long().cpu()
+        permuted, self.rev = permute(x, self.local_map)
+        return permuted, tokens_per_expert
+
+    def token_unpermutation(self, hidden_states, bias=None):
+        out = unpermute(hidden_states, self.rev, self.hidden_shape_before_permute, self.local_probs, self.local_map)
+        if self.tp_ep_size > 1:
+            out = _ReduceScatterFirstDimAutograd.apply(out, self.tp_ep_group)
+        return out.view(self.hidden_shape), None
+
+
+class _GatherFirstDimAutograd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _gather_along_first_dim(x, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _reduce_scatter_along_first_dim(g.contiguous(), ctx.group), None
+
+
+class _ReduceScatterFirstDimAutograd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _reduce_scatter_along_first_dim(x.contiguous(), group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _gather_along_first_dim(g.contiguous(), ctx.group), None
+
+
+class MoEAlltoAllTokenDispatcher(MoETokenDispatcher):
+    def __init__(self, num_local_experts, local_expert_indices, config):
+        super().__init__(config)
+        self.num_local_experts, self.local_expert_indices = num_local_experts, local_expert_indices
+        self.num_experts = config.num_moe_experts
+        # chunk (src rank, local expert) -> (local expert, src rank) ordering tables
+        n = self.num_experts * self.etp_size
+        self.sort_input_by_local_experts = torch.arange(n).reshape(-1, num_local_experts).T.ravel().tolist()
+        self.restore_output_by_local_experts = torch.arange(n).reshape(num_local_experts, -1).T.ravel().tolist()
+
+    def _meta(self, routing_map):
+        E, ep, nl = self.num_experts, self.ep_size, self.num_local_experts
+        local_counts = routing_map.sum(dim=0).long()                      # [E] tokens I send per global expert
+        self.input_splits = local_counts.view(ep, nl).sum(dim=1).cpu().tolist() if ep > 1 else None
+        if ep > 1 or self.etp_size > 1:
+            gathered = local_counts.view(1, E)
+            if ep > 1:
+                gathered = _gather_along_first_dim(local_counts.view(1, E), self.ep_group)   # [ep, E]
+            mine = gathered[:, self.local_expert_indices[0]:self.local_expert_indices[-1] + 1]  # [ep, nl]
+            if self.etp_size > 1:
+                mine_all = _gather_along_first_dim(mine.contiguous().view(1, -1), self.etp_group).view(self.etp_size, -1, nl)
+                self.output_splits_tp = mine_all.sum(dim=(1, 2)).cpu().tolist()
+                self.num_global_tokens_per_local_expert = mine_all.reshape(-1, nl)  # [(etp*ep), nl]
+            else:
+                self.output_splits_tp = None
+                self.num_global_tokens_per_local_expert = mine
+            self.output_splits = mine.sum(dim=1).cpu().tolist() if ep > 1 else None
+            tokens_per_expert = self.num_global_tokens_per_local_expert.sum(dim=0).cpu()
+            self.chunk_sizes = self.num_global_tokens_per_local_expert.reshape(-1).cpu()
+        else:
+            self.output_splits = self.output_splits_tp = None
+            self.num_global_tokens_per_local_expert = None
+            tokens_per_expert = local_counts.cpu()
+        return tokens_per_expert
+
+    def token_permutation(self, hidden_states, probs, routing_map):
+        self.hidden_shape = hidden_states.shape
+        self.probs, self.routing_map = probs, routing_map
+        x = hidden_states.view(-1, self.hidden_shape[-1])
+        tokens_per_expert = self._meta(routing_map)
+        self.hidden_shape_before_permute = x.shape
+        permuted, self.rev = permute(x, routing_map)
+        if self.ep_size > 1:
+            permuted = all_to_all(self.ep_group, permuted, self.output_splits, self.input_splits)
+        if self.etp_size > 1:
+            permuted = _GatherFirstDimVarAutograd.apply(permuted, self.etp_group, self.output_splits_tp)
+        if self.num_local_experts > 1 and self.num_global_tokens_per_local_expert is not None:
+            n_chunks = self.chunk_sizes.numel()
+            order = torch.arange(n_chunks).reshape(-1, self.num_local_experts).T.ravel().tolist()
+            self._restore = torch.arange(n_chunks).reshape(self.num_local_experts, -1).T.ravel().tolist()
+            self._sorted_sizes = self.chunk_sizes[order]
+            permuted = sort_chunks_by_idxs(permuted, self.chunk_sizes, order)
+        return permuted, tokens_per_expert
+
+    def token_unpermutation(self, hidden_states, bias=None):
+        x = hidden_states
+        if self.num_local_experts > 1 and self.num_global_tokens_per_local_expert is not None:
+            x = sort_chunks_by_idxs(x, self._sorted_sizes, self._restore)
+        if self.etp_size > 1:
+            x = _ReduceScatterFirstDimVarAutograd.apply(x, self.etp_group, self.output_splits_tp)
+        if self.ep_size > 1:
+            x = all_to_all(self.ep_group, x, self.input_splits, self.output_splits)
+        out = unpermute(x, self.rev, self.hidden_shape_before_permute, self.probs, self.routing_map)
+        return out.view(self.hidden_shape), None
+
+
+class _GatherFirstDimVarAutograd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group, sizes):
+        ctx.group, ctx.sizes = group, sizes
+        return _gather_along_first_dim(x, group, sizes)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _reduce_scatter_along_first_dim(g.contiguous(), ctx.group, ctx.sizes), None, None
+
+
+class _ReduceScatterFirstDimVarAutograd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group, sizes):
+        ctx.group, ctx.sizes = group, sizes
+        return _reduce_scatter_along_first_dim(x.contiguous(), group, sizes)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _gather_along_first_dim(g.contiguous(), ctx.group, ctx.sizes), None, None
+
+
+class _PeerScatter(torch.autograd.Function):
+    """rows -> owner buffers via the fused NVLink scatter kernel; backward = the reverse scatter."""
+
+    @staticmethod
+    def forward(ctx, x, disp, direction):
+        ctx.disp, ctx.direction = disp, direction
+        return disp._scatter(x, direction)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.disp._scatter(g.contiguous(), 1 - ctx.direction), None, None
+
+
+class MoEPeerScatterDispatcher(MoETokenDispatcher):
+    """``--moe-token-dispatcher-type flex``: sync-free dispatch into capacity-padded expert buffers.
+
+    Every rank computes, on the device, the destination (owner rank, row) of each routed copy from
+    an all-gather of the per-expert counts (tiny, stays on the GPU); rows beyond an expert's
+    capacity are dropped (``dst_rank = -1``).  The expert sees a static ``[E_local * ep * cap, h]``
+    buffer (zero rows where nothing landed), so expert GEMM shapes never depend on the routing and
+    nothing is copied to the host."""
+
+    def __init__(self, num_local_experts, local_expert_indices, config):
+        super().__init__(config)
+        self.num_local_experts, self.local_expert_indices = num_local_experts, local_expert_indices
+        self.num_experts = config.num_moe_experts
+        self.capacity_factor = config.moe_expert_capacity_factor or 1.25
+        self._arena = None
+        self._epoch = 0
+
+    def _get_arena(self, nbytes):
+        from ..comm.arena import get_arena
+
+        a = get_arena("ep", self.ep_group, nbytes)
+        return a
+
+    def _scatter(self, x, direction):
+        """direction 0: tokens -> expert buffers; 1: expert buffers -> token-copy rows."""
+        from .. import ops
+
+        h = x.shape[1]
+        rows_out = self.buf_rows if direction == 0 else self.n_copies
+        if self.ep_size > 1 and not x.is_cuda:
+            raise NotImplementedError("the peer-scatter (flex) dispatcher needs CUDA peers for ep > 1; "
+                                      "use --moe-token-dispatcher-type alltoall on CPU")
+        if self.ep_size == 1:
+            out = torch.zeros(rows_out, h, dtype=x.dtype, device=x.device)
+            keep = self.dst_rank >= 0
+            rows = self.dst_row[keep].long()
+            if direction == 0:
+                out[rows] = x[keep]           # copy i -> buffer row dst_row[i]
+            else:
+                out[keep] = x[rows]           # buffer row -> copy i
+            return out
+        arena = self._get_arena(4 * max(self.buf_rows, self.n_copies) * h * 2 + (1 << 20))
+        slot = self._epoch & 1
+        reg = arena.region(f"moe_buf{slot}_{direction}", max(self.buf_rows, self.n_copies) * h * 2)
+        flags = arena.region(f"moe_flags{slot}_{direction}", 64 * 8 * 4)
+        ep = arena.next_epoch(flags)
+        self._epoch += 1
+        local = arena.local(reg, (rows_out, h), x.dtype)
+        local.zero_()
+        arena.barrier()  # everybody's buffer is cleared before rows start landing
+        if direction == 0:
+            ops.ext().a2a_scatter_rows(x.contiguous(), self.dst_rank, self.dst_row, arena.ptrs(reg), arena.ptrs(flags),
+                                       arena.rank, arena.size, ep, 32)
+        else:
+            ops.ext().a2a_scatter_rows(x.contiguous(), self.back_rank, self.back_row, arena.ptrs(reg), arena.ptrs(flags),
+                                       arena.rank, arena.size, ep, 32)
+        return local.clone()
+
+    def token_permutation(self, hidden_states, probs, routing_map):
+        self.hidden_shape = hidden_states.shape
+        self.probs, self.routing_map = probs, routing_map
+        x = hidden_states.view(-1, self.hidden_shape[-1])
+        n, E, nl, ep = x.shape[0], self.num_experts, self.num_local_experts, self.ep_size
+        dev = x.device
+        cap = int(-(-n * self.config.moe_router_topk * self.capacity_factor // E))
+        cap = (cap + 127) // 128 * 128
+        self.cap = cap
+        rm = routing_map.bool().T.contiguous()                               # [E, n]
+        tok = torch.arange(n, device=dev).unsqueeze(0).expand(E, -1)
+        self.copy_idx = tok.masked_select(rm).int()                          # source token of each routed copy
+        exp_of_copy = torch.arange(E, device=dev).unsqueeze(1).expand(-1, n).masked_select(rm)
+        counts = rm.sum(dim=1).int()                                         # [E]
+        pos = (torch.cumsum(rm.int(), dim=1) - 1).masked_select(rm).int()    # position inside (me, expert)
+        owner = (exp_of_copy // nl).int()
+        le = (exp_of_copy % nl).int()
+        # buffer layout on the owner: [local expert][src rank][cap]
+        self.dst_row = ((le * ep + self.ep_rank) * cap + pos).int()
+        self.dst_rank = torch.where(pos < cap, owner, torch.full_like(owner, -1)).int()
+        self.n_copies = int(self.copy_idx.numel())
+        self.buf_rows = nl * ep * cap
+        # reverse map: for every buffer row, which (rank, copy row) it came from (-1 = empty)
+        if ep > 1 and x.is_cuda:
+            back_rank = torch.full((self.buf_rows,), -1, dtype=torch.int32, device=dev)
+            back_row = torch.zeros(self.buf_rows, dtype=torch.int32, device=dev)
+            meta = torch.stack([self.dst_rank, self.dst_row, torch.arange(self.n_copies, device=dev, dtype=torch.int32)])
+            gathered = [torch.empty_like(meta) for _ in range(ep)] if False else None
+            sizes = torch.tensor([self.n_copies], device=dev)
+            all_sizes = [torch.zeros_like(sizes) for _ in range(ep)]
+            dist.all_gather(all_sizes, sizes, group=self.ep_group)
+            mx = int(max(int(s) for s in all_sizes))
+            pad = torch.full((3, mx), -1, dtype=torch.int32, device=dev)
+            pad[:, :self.n_copies] = meta
+            allm = [torch.empty_like(pad) for _ in range(ep)]
+            dist.all_gather(allm, pad, group=self.ep_group)
+            for r, m in enumerate(allm):
+                sel = m[0] == self.ep_rank
+                back_rank[m[1][sel].long()] = r
+                back_row[m[1][sel].long()] = m[2][sel]
+            self.back_rank, self.back_row = back_rank, back_row
+        copies = x.index_select(0, self.copy_idx.long())
+        buf = _PeerScatter.apply(copies, self, 0)
+        tokens_per_expert = torch.full((nl,), ep * cap, dtype=torch.long)
+        return buf, tokens_per_expert
+
+    def token_unpermutation(self, hidden_states, bias=None):
+        copies = _PeerScatter.apply(hidden_states, self, 1)                   # [n_copies, h]
+        n, h = self.hidden_shape[0] * self.hidden_shape[1] if len(self.hidden_shape) == 3 else self.hidden_shape[0], self.hidden_shape[-1]
+        p = self.probs.T.contiguous().masked_select(self.routing_map.bool().T.contiguous())
+        out = torch.zeros(n, h, dtype=copies.dtype, device=copies.device)
+        out.index_add_(0, self.copy_idx.long(), copies * p.unsqueeze(-1).to(copies.dtype))
+        return out.view(self.hidden_shape), None

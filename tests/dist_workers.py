@@ -113,6 +113,46 @@ def sharded_ckpt(tp_save=2, tp_load=1, path=None):
     return {"n": len(full), "rank": rank}
 
 
+def moe_parity(ep=1, dispatcher="alltoall", grouped=False):
+    """MoE layer output/grad parity between EP=world and a reference computed with EP=1 math."""
+    import torch.nn.functional as F
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.gpt.gpt_layer_specs import get_mlp_module_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+    from megatronapp_b200.transformer.spec_utils import build_module
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(1, 1, expert_model_parallel_size=ep)
+    model_parallel_cuda_manual_seed(123)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, ffn_hidden_size=64,
+                            num_moe_experts=4, moe_router_topk=2, expert_model_parallel_size=ep,
+                            moe_token_dispatcher_type=dispatcher, add_bias_linear=False, activation_func=F.silu,
+                            gated_linear_unit=True, use_cpu_initialization=True, moe_grouped_gemm=grouped,
+                            moe_expert_capacity_factor=4.0 if dispatcher == "flex" else None)
+    torch.manual_seed(5)
+    layer = build_module(get_mlp_module_spec(False, 4, grouped), config=cfg)
+    # identical weights everywhere: router replicated; expert e gets a seed that depends on e only
+    with torch.no_grad():
+        torch.manual_seed(11)
+        layer.router.weight.copy_(torch.randn_like(layer.router.weight) * 0.5)
+        for i, e in enumerate(layer.local_expert_indices):
+            g = torch.Generator().manual_seed(1000 + e)
+            if grouped:
+                f1 = layer.experts.fc1_out
+                layer.experts.weight1[i * f1:(i + 1) * f1].copy_(torch.randn(f1, 32, generator=g) * 0.1)
+                layer.experts.weight2[i * 32:(i + 1) * 32].copy_(torch.randn(32, layer.experts.ffn, generator=g) * 0.1)
+            else:
+                ex = layer.experts.local_experts[i]
+                ex.linear_fc1.weight.copy_(torch.randn(ex.linear_fc1.weight.shape, generator=g) * 0.1)
+                ex.linear_fc2.weight.copy_(torch.randn(ex.linear_fc2.weight.shape, generator=g) * 0.1)
+    g = torch.Generator().manual_seed(77 + (ps.get_data_parallel_rank() if ep == 1 else rank))
+    x = torch.randn(8, 2, 32, generator=g, requires_grad=True)
+    out, _ = layer(x)
+    out.pow(2).sum().backward()
+    return {"out": out.detach().flatten().tolist(), "gx": x.grad.flatten().tolist(), "seed_rank": rank}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":
