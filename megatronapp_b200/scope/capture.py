@@ -1,0 +1,223 @@
+"""MegaScope capture: per-layer flags, whitelisted compressors, TP re-assembly, report callback.
+
+Parity: reference ``megatron/core/tensor_tracer.py`` -- ``FlagType`` integer codes 1-7 (:66-74),
+``TTFlags`` with the same config keys and defaults (:225-266), ``DefaultCompressor`` config
+(``QKV`` 96 px / ``MLP`` 64 px, ``method``) (:76-113), gather to TP rank 0 and shard re-assembly
+(QKV 3-way chunk re-interleave, attention cat on heads, MLP1 cat on hidden, MLP2 from rank 0)
+(:138-173), ``tik_result`` top-20 (:189-209), ``tik_end`` StandardScaler + PCA(2) (:212-223).
+
+Differences by design: the compressor ``method`` is a *whitelist* (the reference ``eval``s a string
+received over a WebSocket bound to 0.0.0.0 -- SURVEY Q6); the legacy spelling
+``"data.mean(dim=-1)"`` is accepted and mapped.  On CUDA the chunked mean runs in the sm_100a
+``chunk_mean`` kernel; captured tensors are detached before any work and nothing runs unless a
+flag is set (``hooks.wants``).
+"""
+from __future__ import annotations
+
+import math
+import re
+from enum import IntEnum
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..parallel import state as ps
+
+
+class FlagType(IntEnum):
+    INVALID_FLAG = 0
+    QKV_mat_mul = 1
+    RawAttentionScore_mat_mul = 2
+    ContextLayer_mat_mul = 3
+    MLP1_mat_mul = 4
+    MLP2_mat_mul = 5
+    Result = 6
+    MLP2_Plot = 7
+
+
+_METHODS: Dict[str, Callable[[torch.Tensor], torch.Tensor]] = {
+    "mean": lambda d: d.mean(dim=-1),
+    "max": lambda d: d.amax(dim=-1),
+    "min": lambda d: d.amin(dim=-1),
+    "absmax": lambda d: d.abs().amax(dim=-1),
+    "absmean": lambda d: d.abs().mean(dim=-1),
+    "std": lambda d: d.std(dim=-1),
+    "rms": lambda d: d.pow(2).mean(dim=-1).sqrt(),
+    "sum": lambda d: d.sum(dim=-1),
+    "first": lambda d: d[..., 0],
+}
+_LEGACY = re.compile(r"^\s*data\.(abs\(\)\.)?(mean|max|min|sum|std|amax|amin)\(\s*dim\s*=\s*-1\s*\)(\.values|\[0\])?\s*$")
+
+
+def resolve_method(method: str) -> str:
+    """Map a client-supplied method string onto the whitelist (never ``eval``)."""
+    m = (method or "mean").strip()
+    if m in _METHODS:
+        return m
+    mt = _LEGACY.match(m)
+    if mt:
+        name = {"amax": "max", "amin": "min"}.get(mt.group(2), mt.group(2))
+        if mt.group(1):
+            name = {"mean": "absmean", "max": "absmax"}.get(name, name)
+        if name in _METHODS:
+            return name
+    raise ValueError(f"compressor method {method!r} is not allowed; choose one of {sorted(_METHODS)}")
+
+
+class DefaultCompressor:
+    def __init__(self):
+        self.configs = {"QKV": {"pixels": 96, "method": "mean"}, "MLP": {"pixels": 64, "method": "mean"}}
+
+    def set_by_configs(self, configs: Dict[str, Any]):
+        out = {}
+        for key in ("QKV", "MLP"):
+            c = dict(self.configs[key])
+            c.update(configs.get(key, {}) or {})
+            c["pixels"] = max(1, min(4096, int(c["pixels"])))
+            c["method"] = resolve_method(str(c["method"]))
+            out[key] = c
+        self.configs = out
+
+    def compress_tensor(self, data_in: torch.Tensor, pixels: int, method: str) -> torch.Tensor:
+        """[B, S, F] -> [B, S, pixels]."""
+        method = resolve_method(method)
+        if method == "mean" and data_in.is_cuda and data_in.dtype in (torch.bfloat16, torch.float16) \
+                and data_in.shape[-1] % pixels == 0:
+            return ops.chunk_mean(data_in, pixels)
+        F = data_in.shape[-1]
+        chunk = math.ceil(F / pixels)
+        padded = torch.nn.functional.pad(data_in.float(), (0, chunk * pixels - F))
+        return _METHODS[method](padded.reshape(*data_in.shape[:-1], pixels, chunk))
+
+    def compress(self, name, data):
+        flag = FlagType(name[1])
+        if flag == FlagType.QKV_mat_mul:
+            return True, [data.shape[1]], data.flatten()
+        if flag == FlagType.RawAttentionScore_mat_mul:
+            return True, [data.shape[1], data.shape[2], data.shape[3]], data.flatten()
+        if flag in (FlagType.MLP1_mat_mul, FlagType.MLP2_mat_mul, FlagType.ContextLayer_mat_mul):
+            return True, [data.shape[1]], data.flatten()
+        return False, [], torch.tensor([])
+
+
+class TTFlags:
+    _KEYS = (("QKV_mat_mul", "False"), ("RawAttentionScore_mat_mul", "False"), ("ContextLayer_mat_mul", "False"),
+             ("MLP1_mat_mul", "True"), ("MLP2_mat_mul", "True"), ("MLP2_Plot", "False"))
+
+    def __init__(self, num_layers: int):
+        self.num_layers = num_layers
+        self.flags: Dict[FlagType, Dict[int, bool]] = {f: {i: False for i in range(1, num_layers + 1)} for f in FlagType}
+
+    def get_flag(self, flag: FlagType, layer: int) -> bool:
+        return self.flags.get(FlagType(flag), {}).get(layer, False)
+
+    def set_by_configs(self, configs: Dict[str, Any]):
+        for key, default in self._KEYS:
+            v = str(configs.get(key, default)).lower() == "true"
+            layers = configs.get(key + "_layers")
+            for i in range(1, self.num_layers + 1):
+                self.flags[FlagType[key]][i] = v and (layers is None or i in layers)
+
+    def any_set(self) -> bool:
+        return any(any(d.values()) for d in self.flags.values())
+
+    def clear(self):
+        for d in self.flags.values():
+            for k in d:
+                d[k] = False
+
+
+class TensorTracers:
+    def __init__(self, num_layers: int, tokenizer=None):
+        self.flags = TTFlags(num_layers)
+        self.compressor = DefaultCompressor()
+        self.report_fn: Optional[Callable] = None
+        self.tokenizer = tokenizer
+        self.mlp2_record: List[Optional[torch.Tensor]] = [None] * (num_layers + 1)
+
+    def set_report(self, fn):
+        self.report_fn = fn
+
+    def any_active(self) -> bool:
+        return self.report_fn is not None and self.flags.any_set()
+
+    def wants(self, flag, layer) -> bool:
+        return self.report_fn is not None and layer is not None and self.flags.get_flag(FlagType(flag), layer)
+
+    # -- capture -----------------------------------------------------------------
+    def tik_tensor(self, name, raw: torch.Tensor):
+        layer, flag = name[0], FlagType(name[1])
+        with torch.no_grad():
+            data = raw.detach()
+            if data.dim() == 3 and flag != FlagType.RawAttentionScore_mat_mul:
+                data = data.transpose(0, 1)  # [s, b, f] -> [b, s, f]
+            cfg = self.compressor.configs
+            if flag == FlagType.QKV_mat_mul:
+                data = self.compressor.compress_tensor(data, cfg["QKV"]["pixels"], cfg["QKV"]["method"])
+            elif flag in (FlagType.MLP1_mat_mul, FlagType.MLP2_mat_mul, FlagType.ContextLayer_mat_mul):
+                data = self.compressor.compress_tensor(data, cfg["MLP"]["pixels"], cfg["MLP"]["method"])
+            data = data.float().contiguous()
+            tp = ps.get_tensor_model_parallel_world_size()
+            rank = ps.get_tensor_model_parallel_rank()
+            parts = [data]
+            if tp > 1:
+                parts = [torch.zeros_like(data) for _ in range(tp)] if rank == 0 else None
+                dist.gather(data, parts, dst=ps.get_tensor_model_parallel_src_rank(),
+                            group=ps.get_tensor_model_parallel_group())
+            if rank != 0:
+                return
+            if flag == FlagType.QKV_mat_mul:
+                q, k, v = [], [], []
+                for p in parts:
+                    a, b, c = torch.tensor_split(p, 3, dim=2)
+                    q.append(a); k.append(b); v.append(c)
+                agg = torch.cat([torch.cat(q, dim=2), torch.cat(k, dim=2), torch.cat(v, dim=2)], dim=2)
+            elif flag == FlagType.RawAttentionScore_mat_mul:
+                agg = torch.cat(parts, dim=1)
+            elif flag in (FlagType.MLP1_mat_mul, FlagType.ContextLayer_mat_mul):
+                agg = torch.cat(parts, dim=2)
+            elif flag == FlagType.MLP2_mat_mul:
+                agg = parts[0]
+                if self.flags.get_flag(FlagType.MLP2_Plot, layer) and 0 < layer < len(self.mlp2_record):
+                    rec = self.mlp2_record[layer]
+                    self.mlp2_record[layer] = agg if rec is None else torch.cat([rec, agg.clone()], dim=1)
+            else:
+                return
+            ok, args, flat = self.compressor.compress(name, agg)
+            if ok and self.report_fn is not None:
+                self.report_fn((layer, flag), args, flat)
+
+    def tik_result(self, result_logits: torch.Tensor, sampled_token_ids: torch.Tensor, top_k: int = 20):
+        if self.report_fn is None:
+            return
+        probs = torch.softmax(result_logits.float(), dim=-1)
+        dec = getattr(self.tokenizer, "decoder", None)
+
+        def fmt(i, logit, p):
+            tok = dec[i] if dec is not None and i in dec else str(i)
+            return {"id": int(i), "token": tok, "logit": float(logit[i]), "probability": float(p[i])}
+
+        sampled = [fmt(int(sampled_token_ids[b]), result_logits[b], probs[b]) for b in range(probs.shape[0])]
+        _, idx = torch.topk(probs, k=min(top_k, probs.shape[-1]), dim=1)
+        top = [fmt(int(t), result_logits[b], probs[b]) for b in range(probs.shape[0]) for t in idx[b].tolist()]
+        self.report_fn((0, FlagType.Result), sampled, top)
+
+    def tik_end(self):
+        if self.report_fn is None:
+            return
+        if dist.is_initialized() and dist.get_rank() != 0:
+            return
+        for i, rec in enumerate(self.mlp2_record):
+            if rec is None or i == 0:
+                continue
+            x = rec.reshape(-1, rec.shape[-1]).float().cpu()
+            x = (x - x.mean(0, keepdim=True)) / (x.std(0, unbiased=False, keepdim=True) + 1e-12)  # StandardScaler
+            if x.shape[0] >= 2:
+                u, s, _ = torch.linalg.svd(x - x.mean(0, keepdim=True), full_matrices=False)
+                red = u[:, :2] * s[:2]
+            else:
+                red = torch.zeros(x.shape[0], 2)
+            self.report_fn((i, FlagType.MLP2_Plot), [rec.shape[0], rec.shape[1]], red.flatten())
+        self.mlp2_record = [None] * len(self.mlp2_record)
