@@ -36,6 +36,8 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 256;
 constexpr int kNumEpiThreads = 128;
 constexpr int kGroupN = 8;    // n-blocks per scheduling group (L2 reuse of A)
+constexpr int kBulkChunk = 32768;  // comm-CTA TMA bulk copy granule
+constexpr int kBulkStages = 6;      // 6 x 32 KB in flight per comm CTA
 
 struct DevParams {
   int M, N, K;
@@ -117,20 +119,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   // ------------------------------------------------------------------ comm CTAs (all-gather push)
   if constexpr (kComm == kCommAllGather) {
     if (static_cast<int>(blockIdx.x) < p.n_comm_ctas) {
-      // work item = (row block of 128 rows, peer offset d, column split)
+      // work item = (row block of 128 rows, destination, column split); all remote destinations
+      // first (they gate the peers' GEMM tiles), the local copy (d == 0: complete gathered view for
+      // the caller's wgrad) last.
       const int rb_per_rank = p.rows_per_rank / BLOCK_M;
-      // peers first (d = 1..tp-1), then d = 0: the local shard into the local gather buffer so the
-      // caller gets a complete gathered view (wgrad of the row-parallel layer consumes it)
-      const int n_items = rb_per_rank * p.tp_size * p.col_splits;
+      const int per_dst = rb_per_rank * p.col_splits;
+      const int n_items = per_dst * p.tp_size;
       const int row_bytes = p.K * 2;
       const int split_bytes = row_bytes / p.col_splits;  // multiple of 16 (checked on host)
+      const bool contiguous = (p.lda_local == p.K) && (p.col_splits == 1) && ((BLOCK_M * row_bytes) % kBulkChunk == 0);
+      if (contiguous) {
+        // TMA bulk pipeline: thread 0 streams gmem -> smem stages, thread 32 streams smem -> peer gmem.
+        uint64_t* c_full = reinterpret_cast<uint64_t*>(smem + kBulkStages * kBulkChunk);
+        uint64_t* c_empty = c_full + kBulkStages;
+        if (threadIdx.x == 0) {
+          for (int i = 0; i < kBulkStages; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 1); }
+          mbar_fence_init();
+        }
+        __syncthreads();
+        const int chunks_per_item = BLOCK_M * row_bytes / kBulkChunk;
+        if (threadIdx.x == 0) {
+          int stage = 0; uint32_t phase = 0;
+          for (int item = blockIdx.x; item < n_items; item += p.n_comm_ctas) {
+            const int rb = (item % per_dst);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.A_local) + static_cast<size_t>(rb) * BLOCK_M * row_bytes;
+            for (int c = 0; c < chunks_per_item; ++c) {
+              mbar_wait(&c_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&c_full[stage], kBulkChunk);
+              bulk_load_1d(smem + stage * kBulkChunk, src + static_cast<size_t>(c) * kBulkChunk, kBulkChunk, &c_full[stage]);
+              if (++stage == kBulkStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else if (threadIdx.x == 32) {
+          int stage = 0; uint32_t phase = 0;
+          int prev_stage = -1;
+          for (int item = blockIdx.x; item < n_items; item += p.n_comm_ctas) {
+            const int di = item / per_dst;                 // 0 .. tp-1
+            const int d = (di + 1) % p.tp_size;            // 1, 2, ..., tp-1, 0
+            const int rb = item % per_dst;
+            const int peer = (p.tp_rank + d) % p.tp_size;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(p.peer_buf[peer]) +
+                           (static_cast<size_t>(p.tp_rank) * p.rows_per_rank + rb * BLOCK_M) * row_bytes;
+            for (int c = 0; c < chunks_per_item; ++c) {
+              mbar_wait(&c_full[stage], phase);
+              bulk_store_1d(dst + static_cast<size_t>(c) * kBulkChunk, smem + stage * kBulkChunk, kBulkChunk);
+              tma_store_commit();
+              if (prev_stage >= 0) {          // the previous store has finished *reading* its stage
+                tma_store_wait_read<1>();
+                mbar_arrive(&c_empty[prev_stage]);
+              }
+              prev_stage = stage;
+              if (++stage == kBulkStages) { stage = 0; phase ^= 1; }
+            }
+            tma_store_wait_all<0>();           // payload of this item is complete at the destination
+            if (prev_stage >= 0) { mbar_arrive(&c_empty[prev_stage]); prev_stage = -1; }
+            if (d != 0) {
+              fence_proxy_async_all();
+              __threadfence_system();
+              st_release_sys(p.peer_flags[peer] + (static_cast<size_t>(p.tp_rank) * rb_per_rank + rb), p.epoch);
+            }
+          }
+        }
+        return;
+      }
       const int vec_per_row = split_bytes / 16;
       for (int item = blockIdx.x; item < n_items; item += p.n_comm_ctas) {
-        const int cs = item % p.col_splits;
-        const int t1 = item / p.col_splits;
-        const int dd = t1 % p.tp_size;
-        const int d = (dd + 1) % p.tp_size;          // 1, 2, ..., tp-1, 0
-        const int rb = t1 / p.tp_size;
+        const int di = item / per_dst;
+        const int d = (di + 1) % p.tp_size;
+        const int r2 = item % per_dst;
+        const int rb = r2 / p.col_splits;
+        const int cs = r2 % p.col_splits;
         const int peer = (p.tp_rank + d) % p.tp_size;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.A_local) +
                              static_cast<size_t>(rb) * BLOCK_M * p.lda_local * 2 + cs * split_bytes;
@@ -138,10 +196,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                        (static_cast<size_t>(p.tp_rank) * p.rows_per_rank + rb * BLOCK_M) * row_bytes +
                        cs * split_bytes;
         const int total_vec = BLOCK_M * vec_per_row;
-        for (int v = threadIdx.x; v < total_vec; v += 4 * kNumThreads) {
-          int4 regs[4];
+        for (int v = threadIdx.x; v < total_vec; v += 8 * kNumThreads) {
+          int4 regs[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int vv = v + u * kNumThreads;
             if (vv < total_vec) {
               const int r = vv / vec_per_row, c = vv - r * vec_per_row;
@@ -150,7 +208,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int vv = v + u * kNumThreads;
             if (vv < total_vec) {
               const int r = vv / vec_per_row, c = vv - r * vec_per_row;
@@ -473,26 +531,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         __threadfence_system();
         named_bar_sync(1, kNumEpiThreads);
         const int vec_per_row = BLOCK_N / 8;
-        for (int v = epi_tid; v < BLOCK_M * vec_per_row; v += kNumEpiThreads) {
-          const int r = v / vec_per_row, cv = v - r * vec_per_row;
-          const int lrow = lm * BLOCK_M + r;
-          const int col = nb * BLOCK_N + cv * 8;
-          if (lrow < p.rows_per_rank && col < p.N) {
+        constexpr int kIlp = 4;
+        for (int v0i = epi_tid; v0i < BLOCK_M * vec_per_row; v0i += kNumEpiThreads * kIlp) {
+          int4 raw[kIlp][kMaxPeers];
+          bool valid[kIlp];
+          int lrows[kIlp], cols[kIlp];
+#pragma unroll
+          for (int u = 0; u < kIlp; ++u) {
+            const int v = v0i + u * kNumEpiThreads;
+            const int r = v / vec_per_row, cv = v - r * vec_per_row;
+            lrows[u] = lm * BLOCK_M + r;
+            cols[u] = nb * BLOCK_N + cv * 8;
+            valid[u] = (v < BLOCK_M * vec_per_row) && lrows[u] < p.rows_per_rank && cols[u] < p.N;
+            if (valid[u]) {
+              for (int s = 0; s < p.tp_size; ++s)
+                raw[u][s] = ld_cg_v4(reinterpret_cast<const int4*>(
+                    stage + (static_cast<size_t>(s) * p.rows_per_rank + lrows[u]) * p.N + cols[u]));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kIlp; ++u) {
+            if (!valid[u]) continue;
             float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int s = 0; s < p.tp_size; ++s) {
-              int4 raw = ld_relaxed_sys_v4(reinterpret_cast<const int4*>(
-                  stage + (static_cast<size_t>(s) * p.rows_per_rank + lrow) * p.N + col));
-              const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw);
+              const uint32_t* uu = reinterpret_cast<const uint32_t*>(&raw[u][s]);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float2 f2 = p.is_bf16 ? unpack_bf16x2(u[q])
-                                      : __half22float2(*reinterpret_cast<const __half2*>(&u[q]));
+                float2 f2 = p.is_bf16 ? unpack_bf16x2(uu[q])
+                                      : __half22float2(*reinterpret_cast<const __half2*>(&uu[q]));
                 accv[2 * q] += f2.x;
                 accv[2 * q + 1] += f2.y;
               }
             }
             if (p.bias != nullptr) {
-              const uint16_t* bp = reinterpret_cast<const uint16_t*>(p.bias) + col;
+              const uint16_t* bp = reinterpret_cast<const uint16_t*>(p.bias) + cols[u];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 accv[q] += p.is_bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(bp + q))
@@ -509,7 +581,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
             *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.D) +
-                                      static_cast<size_t>(lrow) * p.ldd + col) =
+                                      static_cast<size_t>(lrows[u]) * p.ldd + cols[u]) =
                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
@@ -685,7 +757,8 @@ int gemm_bf16(const GemmArgs& a) {
       p.n_comm_ctas = a.n_comm_ctas > 0 ? a.n_comm_ctas : 12;
       const int base_items = p.m_blocks_per_chunk * a.tp_size;
       int cs = 1;
-      while (base_items * cs < p.n_comm_ctas && (a.K * 2) % (32 * cs) == 0 && cs < 8) cs *= 2;
+      const bool bulk_ok = (a.lda_local == a.K) && ((BLOCK_M * a.K * 2) % kBulkChunk == 0);
+      while (!bulk_ok && base_items * cs < p.n_comm_ctas && (a.K * 2) % (32 * cs) == 0 && cs < 8) cs *= 2;
       p.col_splits = cs;
       grid = sms;  // comm CTAs + GEMM CTAs together fill the machine
       if (p.n_comm_ctas >= grid) { g_last_error = "too many comm CTAs"; return -4; }

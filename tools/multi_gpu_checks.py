@@ -93,6 +93,13 @@ def main():
                 dist.all_gather_into_tensor(full, x_local, group=group)
                 torch.addmm(bias, full, w.t(), out=outb)
 
+            sweep = {}
+            for ncc in (4, 8, 16):
+                fc.n_comm_ctas = ncc
+                sweep[ncc] = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb), 10, 3)
+            best = min(sweep, key=sweep.get)
+            fc.n_comm_ctas = best
+            log(f"ag_gemm_{name}_comm_cta_sweep_ms", sweep)
             t_f = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb))
             t_u = timed(unfused)
             t_c = timed(cublas_unfused)
