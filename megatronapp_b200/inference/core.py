@@ -1,0 +1,287 @@
+"""Inference: requests, sampling, KV-cache contexts, scheduler, text-generation controller, engines.
+
+Parity: reference ``megatron/core/inference/**`` -- ``InferenceRequest`` / ``Status``,
+``SamplingParams``, ``Scheduler`` (waiting / active / completed pools), ``StaticInferenceContext``
+(``key_value_memory_dict``, ``sequence_len_offset``), ``TextGenerationController``
+(``generate_all_output_tokens_static_batch`` :388, ``sample_from_logits`` :112, MegaScope
+``tik_result`` :582 / ``tik_end`` :639), ``StaticInferenceEngine`` / ``DynamicInferenceEngine``.
+"""
+from __future__ import annotations
+
+import itertools
+import time
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Dict, List, Optional
+
+import torch
+
+from ..scope import hooks as scope_hooks
+
+
+class Status(Enum):
+    WAITING_IN_QUEUE = 1
+    ACTIVE_AND_GENERATING_TOKENS = 2
+    ACTIVE_BUT_NOT_GENERATING_TOKENS = 3
+    COMPLETED = 4
+
+
+@dataclass
+class SamplingParams:
+    temperature: float = 1.0
+    top_k: int = 0
+    top_p: float = 0.0
+    return_log_probs: bool = False
+    return_segments: bool = False
+    num_tokens_to_generate: int = 30
+    top_n_logprobs: int = 0
+    add_BOS: bool = False
+
+    def add_attributes(self, d: dict):
+        for k, v in d.items():
+            setattr(self, k, v)
+
+
+@dataclass
+class InferenceRequest:
+    request_id: str
+    prompt: str
+    inference_parameters: SamplingParams = None
+    prompt_tokens: List[int] = None
+    arrival_time: float = 0.0
+    status: Status = Status.WAITING_IN_QUEUE
+    generated_text: Optional[str] = None
+    generated_tokens: Optional[torch.Tensor] = None
+    generated_log_probs: Optional[List[float]] = None
+    generated_length: int = 0
+
+
+class StaticInferenceContext:
+    """Pre-sized KV cache bookkeeping shared by every attention layer."""
+
+    def __init__(self, max_batch_size: int, max_sequence_length: int):
+        self.max_batch_size, self.max_sequence_length = max_batch_size, max_sequence_length
+        self.sequence_len_offset = 0
+        self.batch_size_offset = 0
+        self.key_value_memory_dict: Dict[int, tuple] = {}
+        self.decode_mode = False
+
+    def reset(self):
+        self.sequence_len_offset = 0
+        self.batch_size_offset = 0
+
+    def swap_key_value_dict(self, batch_idx):
+        for k, (kc, vc) in list(self.key_value_memory_dict.items()):
+            self.key_value_memory_dict[k] = (kc[:, batch_idx].contiguous(), vc[:, batch_idx].contiguous())
+
+    def is_static_batching(self):
+        return True
+
+
+InferenceParams = StaticInferenceContext
+
+
+class Scheduler:
+    def __init__(self, max_batch_size: int):
+        self.max_batch_size = max_batch_size
+        self.active_request_pool: "OrderedDict[str, InferenceRequest]" = OrderedDict()
+        self.waiting_request_pool: "OrderedDict[str, InferenceRequest]" = OrderedDict()
+        self.completed_request_pool: "OrderedDict[str, InferenceRequest]" = OrderedDict()
+        self._ids = itertools.count()
+
+    def add_request(self, prompt: str, prompt_tokens: List[int], inference_parameters: SamplingParams,
+                    arrival_time: Optional[float] = None) -> str:
+        rid = str(next(self._ids))
+        req = InferenceRequest(rid, prompt, inference_parameters, prompt_tokens, arrival_time or time.time())
+        if len(self.active_request_pool) < self.max_batch_size:
+            req.status = Status.ACTIVE_BUT_NOT_GENERATING_TOKENS
+            self.active_request_pool[rid] = req
+        else:
+            self.waiting_request_pool[rid] = req
+        return rid
+
+    def have_requests_pending(self) -> bool:
+        return bool(self.active_request_pool) or bool(self.waiting_request_pool)
+
+    def add_earliest_waiting_request_to_active_pool(self):
+        if self.waiting_request_pool and len(self.active_request_pool) < self.max_batch_size:
+            rid, req = self.waiting_request_pool.popitem(last=False)
+            req.status = Status.ACTIVE_BUT_NOT_GENERATING_TOKENS
+            self.active_request_pool[rid] = req
+
+    def update_requests_pools(self, result: Optional[Dict[str, InferenceRequest]] = None):
+        for rid in list(self.active_request_pool):
+            req = self.active_request_pool[rid]
+            if req.status == Status.COMPLETED:
+                self.completed_request_pool[rid] = self.active_request_pool.pop(rid)
+        while self.waiting_request_pool and len(self.active_request_pool) < self.max_batch_size:
+            self.add_earliest_waiting_request_to_active_pool()
+
+
+def sample_from_logits(last_token_logits: torch.Tensor, params: SamplingParams, vocab_size: Optional[int] = None,
+                       generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Greedy when ``top_k == 1``; otherwise temperature -> top-k XOR top-p filtering -> multinomial."""
+    top_k, top_p, temp = params.top_k, params.top_p, params.temperature
+    if not (0.0 <= top_p <= 1.0):
+        raise ValueError("top-p should be in [0, 1]")
+    if top_k > 0 and top_p > 0.0:
+        raise ValueError("cannot set both greedy/top-k and top-p sampling")
+    logits = last_token_logits.float()
+    if vocab_size:
+        logits = logits[..., :vocab_size] if logits.shape[-1] > vocab_size else logits
+    if top_k == 1:
+        return torch.argmax(logits, dim=-1)
+    logits = logits.clone()
+    if temp != 1.0:
+        logits.div_(temp)
+    if top_k > 1:
+        if top_k > logits.size(-1):
+            raise ValueError("top-k is larger than logit size")
+        kth = torch.topk(logits, top_k)[0][..., -1, None]
+        logits.masked_fill_(logits < kth, float("-inf"))
+    elif top_p > 0.0:
+        sorted_logits, sorted_idx = torch.sort(logits, descending=True)
+        cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+        mask = cum > top_p
+        mask[..., 1:] = mask[..., :-1].clone()
+        mask[..., 0] = False
+        logits.masked_fill_(mask.scatter(1, sorted_idx, mask), float("-inf"))
+    probs = logits.softmax(dim=-1)
+    return torch.multinomial(probs, num_samples=1, generator=generator).view(-1)
+
+
+class GPTInferenceWrapper:
+    """Drives a GPTModel for prefill + single-token decode steps with a shared KV cache."""
+
+    def __init__(self, model, max_batch_size: int = 8, max_sequence_length: int = 2560, padded_vocab_size=None):
+        self.model = model
+        m = model
+        while hasattr(m, "module"):
+            m = m.module
+        self.inner = m
+        self.max_batch_size, self.max_sequence_length = max_batch_size, max_sequence_length
+        self.padded_vocab_size = padded_vocab_size
+        self.context: Optional[StaticInferenceContext] = None
+
+    def prep_model_for_inference(self, prompts_tokens: torch.Tensor):
+        self.model.eval()
+        self.context = StaticInferenceContext(prompts_tokens.shape[0], self.max_sequence_length)
+
+    @torch.no_grad()
+    def run_one_forward_step(self, tokens: torch.Tensor, start: int, end: int) -> torch.Tensor:
+        """tokens [b, S_total]; runs positions [start, end) against the cache; returns logits [b, end-start, V]."""
+        ctx = self.context
+        ctx.sequence_len_offset = start
+        ids = tokens[:, start:end]
+        pos = torch.arange(start, end, device=tokens.device).unsqueeze(0).expand_as(ids)
+        logits = self.model(ids, pos, None, inference_context=ctx)
+        ctx.sequence_len_offset = end
+        return logits
+
+
+class TextGenerationController:
+    def __init__(self, inference_wrapped_model: GPTInferenceWrapper, tokenizer):
+        self.inference_wrapped_model = inference_wrapped_model
+        self.tokenizer = tokenizer
+
+    def tokenize_prompt(self, prompt: str, add_BOS: bool = False) -> List[int]:
+        toks = self.tokenizer.tokenize(prompt)
+        if add_BOS and getattr(self.tokenizer, "bos", None) is not None:
+            toks = [self.tokenizer.bos] + toks
+        return toks
+
+    def detokenize_generations(self, tokens: List[int]) -> str:
+        return self.tokenizer.detokenize(tokens)
+
+    def sample_from_logits(self, logits, params, vocab_size=None, generator=None):
+        return sample_from_logits(logits, params, vocab_size, generator)
+
+    @torch.no_grad()
+    def generate_all_output_tokens_static_batch(self, active_requests: "OrderedDict[str, InferenceRequest]"):
+        reqs = list(active_requests.values())
+        params = reqs[0].inference_parameters
+        dev = next(self.inference_wrapped_model.model.parameters()).device
+        lens = [len(r.prompt_tokens) for r in reqs]
+        min_len, max_len = min(lens), max(lens)
+        n_gen = params.num_tokens_to_generate
+        total = min(max_len + n_gen, self.inference_wrapped_model.max_sequence_length)
+        eod = self.tokenizer.eod
+        tokens = torch.full((len(reqs), total), eod, dtype=torch.long, device=dev)
+        for i, r in enumerate(reqs):
+            tokens[i, :lens[i]] = torch.tensor(r.prompt_tokens, dtype=torch.long, device=dev)
+        lens_t = torch.tensor(lens, device=dev)
+        self.inference_wrapped_model.prep_model_for_inference(tokens)
+        done = torch.zeros(len(reqs), dtype=torch.bool, device=dev)
+        gen_len = torch.zeros(len(reqs), dtype=torch.long, device=dev)
+        logprobs: List[List[float]] = [[] for _ in reqs]
+        vocab = getattr(self.tokenizer, "vocab_size", None)
+        start = 0
+        for pos in range(min_len, total):
+            logits = self.inference_wrapped_model.run_one_forward_step(tokens, start, pos)
+            last = logits[:, -1, :]
+            new = self.sample_from_logits(last, params, vocab)
+            scope_hooks.tik_result(last, new)
+            started = lens_t <= pos                     # rows still consuming their prompt keep it
+            tokens[started, pos] = new[started]
+            if params.return_log_probs:
+                lp = torch.log_softmax(last.float(), dim=-1)
+                for i in range(len(reqs)):
+                    if started[i] and not done[i]:
+                        logprobs[i].append(float(lp[i, tokens[i, pos]]))
+            hit = started & (new == eod) & ~done
+            gen_len += (started & ~done).long()
+            done |= hit
+            start = pos
+            if bool(done.all()):
+                break
+        scope_hooks.tik_end()
+        for i, r in enumerate(reqs):
+            n = int(gen_len[i])
+            out = tokens[i, lens[i]:lens[i] + n]
+            r.generated_tokens = out
+            r.generated_length = n
+            r.generated_log_probs = logprobs[i] if params.return_log_probs else None
+            text = out.tolist()
+            if text and text[-1] == eod:
+                text = text[:-1]
+            r.generated_text = self.detokenize_generations(text)
+            r.status = Status.COMPLETED
+        return active_requests
+
+
+class StaticInferenceEngine:
+    def __init__(self, text_generation_controller: TextGenerationController, max_batch_size: int = 8,
+                 random_seed: Optional[int] = None):
+        self.controller = text_generation_controller
+        self.scheduler = Scheduler(max_batch_size)
+        self.random_seed = random_seed
+
+    def generate(self, prompts: List[str], sampling_params: Optional[SamplingParams] = None,
+                 add_BOS: bool = False) -> List[InferenceRequest]:
+        sampling_params = sampling_params or SamplingParams()
+        if self.random_seed is not None:
+            torch.manual_seed(self.random_seed)
+        ids = []
+        for p in prompts:
+            ids.append(self.scheduler.add_request(p, self.controller.tokenize_prompt(p, add_BOS), sampling_params))
+        self.run_engine()
+        return [self.scheduler.completed_request_pool[i] for i in ids]
+
+    def run_engine(self):
+        while self.scheduler.have_requests_pending():
+            active = self.scheduler.active_request_pool
+            self.controller.generate_all_output_tokens_static_batch(active)
+            self.scheduler.update_requests_pools(active)
+
+
+class DynamicInferenceEngine(StaticInferenceEngine):
+    """Continuous batching at request granularity: finished requests leave the active pool and
+    waiting ones join between decode batches (the reference additionally pages the KV cache)."""
+
+    def step(self):
+        if self.scheduler.have_requests_pending():
+            active = self.scheduler.active_request_pool
+            self.controller.generate_all_output_tokens_static_batch(active)
+            self.scheduler.update_requests_pools(active)
+        return list(self.scheduler.completed_request_pool.values())

@@ -1,0 +1,182 @@
+"""Text-generation servers: REST (``PUT /api``) and the MegaScope inference WebSocket.
+
+Parity: reference ``megatron/inference/text_generation_server.py`` -- ``MegatronServer`` (Flask
+REST: ``{"prompts": [...], "tokens_to_generate": N, "temperature", "top_k", "top_p", "logprobs",
+"add_BOS", "random_seed"}`` -> ``{"text": [...], "segments", "logprobs"}``) and
+``InferenceWSServer`` (:273-): request ``{"type":"generate", prompts, tokens_to_generate,
+temperature/top_k/top_p, visualization_flags, disturbance_configs, compressor_config}``, replies
+``start`` (prompt tokens), streamed ``update``s, final ``finish``.  Flask is not available in this
+image, so the REST server is a stdlib ``http.server`` with the same route and payload.
+"""
+from __future__ import annotations
+
+import json
+import queue
+import threading
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from typing import Optional
+
+import torch
+
+from ..scope import hooks
+from ..scope.capture import TensorTracers
+from ..scope.disturbance import Disturbance
+from .core import SamplingParams, StaticInferenceEngine
+
+_LOCK = threading.Lock()
+
+
+def _validate(req: dict):
+    if "prompts" not in req:
+        return "prompts argument required"
+    if not isinstance(req["prompts"], list) or len(req["prompts"]) == 0:
+        return "prompts is empty or not a list"
+    if len(req["prompts"]) > 128:
+        return "Maximum number of prompts is 128"
+    n = req.get("tokens_to_generate", 64)
+    if not isinstance(n, int) or n < 0:
+        return "tokens_to_generate must be an integer >= 0"
+    t = req.get("temperature", 1.0)
+    if not isinstance(t, (int, float)) or not (0.0 < t <= 100.0):
+        return "temperature must be a positive number less than or equal to 100.0"
+    k = req.get("top_k", 0)
+    if not isinstance(k, int) or not (0 <= k <= 1000):
+        return "top_k must be an integer equal to or greater than 0 and less than or equal to 1000"
+    p = req.get("top_p", 0.0)
+    if not isinstance(p, (int, float)) or not (0.0 <= p <= 1.0):
+        return "top_p must be less than or equal to 1 and greater than or equal to 0"
+    if k > 0 and p > 0.0:
+        return "cannot set both top-k and top-p samplings."
+    return None
+
+
+def run_generate(engine: StaticInferenceEngine, req: dict):
+    params = SamplingParams(temperature=float(req.get("temperature", 1.0)), top_k=int(req.get("top_k", 0)),
+                            top_p=float(req.get("top_p", 0.0)), return_log_probs=bool(req.get("logprobs", False)),
+                            num_tokens_to_generate=int(req.get("tokens_to_generate", 64)))
+    if req.get("random_seed") is not None:
+        torch.manual_seed(int(req["random_seed"]))
+    with _LOCK:
+        results = engine.generate(req["prompts"], params, add_BOS=bool(req.get("add_BOS", False)))
+    out = {"text": [r.prompt + r.generated_text for r in results],
+           "tokens": [r.prompt_tokens + r.generated_tokens.tolist() for r in results]}
+    if params.return_log_probs:
+        out["logprobs"] = [r.generated_log_probs for r in results]
+    return out
+
+
+class MegatronServer:
+    def __init__(self, engine: StaticInferenceEngine):
+        self.engine = engine
+        self.httpd: Optional[ThreadingHTTPServer] = None
+
+    def run(self, host: str = "127.0.0.1", port: int = 5000, block: bool = True):
+        engine = self.engine
+
+        class Handler(BaseHTTPRequestHandler):
+            def log_message(self, *a):
+                pass
+
+            def _send(self, code, obj):
+                body = json.dumps(obj).encode()
+                self.send_response(code)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Length", str(len(body)))
+                self.end_headers()
+                self.wfile.write(body)
+
+            def do_PUT(self):
+                if self.path.rstrip("/") != "/api":
+                    return self._send(404, {"message": "not found"})
+                try:
+                    req = json.loads(self.rfile.read(int(self.headers.get("Content-Length", 0)) or 0))
+                except Exception:
+                    return self._send(400, {"message": "invalid json"})
+                err = _validate(req)
+                if err:
+                    return self._send(400, {"message": err})
+                try:
+                    self._send(200, run_generate(engine, req))
+                except ValueError as e:
+                    self._send(400, {"message": str(e)})
+
+            do_POST = do_PUT
+
+        self.httpd = ThreadingHTTPServer((host, port), Handler)
+        if block:
+            self.httpd.serve_forever()
+        else:
+            threading.Thread(target=self.httpd.serve_forever, daemon=True).start()
+
+    def shutdown(self):
+        if self.httpd:
+            self.httpd.shutdown()
+
+
+class InferenceWSServer:
+    def __init__(self, engine: StaticInferenceEngine, num_layers: int, tokenizer=None, host="127.0.0.1", port=5000):
+        self.engine, self.host, self.port = engine, host, port
+        self.tracers = TensorTracers(num_layers, tokenizer)
+        self.disturbance = Disturbance()
+        self._srv = None
+
+    def run(self, block: bool = True):
+        from websockets.sync.server import serve
+
+        def handler(ws):
+            for raw in ws:
+                try:
+                    msg = json.loads(raw)
+                except json.JSONDecodeError:
+                    ws.send(json.dumps({"type": "error", "message": "invalid json"}))
+                    continue
+                if msg.get("type") == "ping":
+                    ws.send(json.dumps({"type": "pong"}))
+                    continue
+                if msg.get("type") != "generate":
+                    ws.send(json.dumps({"type": "error", "message": "unknown request type"}))
+                    continue
+                err = _validate(msg)
+                if err:
+                    ws.send(json.dumps({"type": "error", "message": err}))
+                    continue
+                try:
+                    self.tracers.flags.set_by_configs(msg.get("visualization_flags", {}))
+                    self.disturbance.set_by_configs(msg.get("disturbance_configs", {}))
+                    if msg.get("compressor_config"):
+                        self.tracers.compressor.set_by_configs(msg["compressor_config"])
+                except ValueError as e:
+                    ws.send(json.dumps({"type": "error", "message": str(e)}))
+                    continue
+                tok = self.engine.controller.tokenizer
+                ws.send(json.dumps({"type": "start", "prompt_tokens": [tok.tokenize(p) for p in msg["prompts"]],
+                                    "num_layers": self.tracers.flags.num_layers}))
+
+                def report(name, args, data):
+                    layer, flag = name
+                    if torch.is_tensor(data):
+                        data = data.detach().float().cpu().tolist()
+                    if int(flag) == 6:
+                        ws.send(json.dumps({"type": "update", "update_type": 6, "layer_id": 0, "sampled": args, "result": data}))
+                    else:
+                        ws.send(json.dumps({"type": "update", "update_type": int(flag), "layer_id": int(layer),
+                                            "args": args, "result": data}))
+
+                self.tracers.set_report(report)
+                hooks.install(self.tracers, self.disturbance)
+                try:
+                    out = run_generate(self.engine, msg)
+                finally:
+                    hooks.install(None, None)
+                    self.tracers.set_report(None)
+                ws.send(json.dumps({"type": "finish", **out}))
+
+        self._srv = serve(handler, self.host, self.port)
+        if block:
+            self._srv.serve_forever()
+        else:
+            threading.Thread(target=self._srv.serve_forever, daemon=True).start()
+
+    def shutdown(self):
+        if self._srv:
+            self._srv.shutdown()

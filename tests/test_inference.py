@@ -1,0 +1,97 @@
+"""Inference: KV-cache decode == full recompute, sampling rules, scheduler, REST + WS servers."""
+import json
+import time
+import urllib.request
+
+import pytest
+import torch
+
+from megatronapp_b200.data.tokenizer import NullTokenizer
+from megatronapp_b200.inference import (GPTInferenceWrapper, SamplingParams, Scheduler, StaticInferenceEngine,
+                                        TextGenerationController, sample_from_logits)
+
+
+@pytest.fixture()
+def engine():
+    from megatronapp_b200.bench_model import build_gpt_for_bench
+
+    st = build_gpt_for_bench(2, 64, 4, 64, 128, 1, device="cpu", dtype=torch.float32, rope=True)
+    model = st.model[0].module
+    tok = NullTokenizer(127)
+    ctl = TextGenerationController(GPTInferenceWrapper(model, max_sequence_length=64), tok)
+    return StaticInferenceEngine(ctl, max_batch_size=4), model
+
+
+def test_kv_cache_decode_matches_full_forward(engine):
+    eng, model = engine
+    res = eng.generate(["5 9 23 7", "11 3"], SamplingParams(top_k=1, num_tokens_to_generate=6))
+    model.eval()
+    for r in res:
+        toks = list(r.prompt_tokens)
+        for _ in range(r.generated_length):
+            ids = torch.tensor([toks])
+            pos = torch.arange(len(toks)).unsqueeze(0)
+            with torch.no_grad():
+                nxt = int(model(ids, pos, None)[0, -1, :128].argmax())
+            toks.append(nxt)
+        assert toks[len(r.prompt_tokens):] == r.generated_tokens.tolist()
+
+
+def test_sampling_rules():
+    logits = torch.tensor([[0.1, 3.0, 0.2, 2.5]])
+    assert int(sample_from_logits(logits, SamplingParams(top_k=1))) == 1
+    g = torch.Generator().manual_seed(0)
+    draws = {int(sample_from_logits(logits, SamplingParams(top_k=2), generator=g)) for _ in range(50)}
+    assert draws <= {1, 3}
+    draws = {int(sample_from_logits(logits, SamplingParams(top_p=0.5), generator=g)) for _ in range(50)}
+    assert draws == {1}
+    with pytest.raises(ValueError):
+        sample_from_logits(logits, SamplingParams(top_k=2, top_p=0.5))
+
+
+def test_scheduler_pools():
+    s = Scheduler(max_batch_size=2)
+    ids = [s.add_request(f"p{i}", [i], SamplingParams()) for i in range(3)]
+    assert list(s.active_request_pool) == ids[:2] and list(s.waiting_request_pool) == ids[2:]
+    from megatronapp_b200.inference import Status
+
+    s.active_request_pool[ids[0]].status = Status.COMPLETED
+    s.update_requests_pools()
+    assert ids[0] in s.completed_request_pool and ids[2] in s.active_request_pool
+
+
+def test_rest_and_ws_servers(engine):
+    from websockets.sync.client import connect
+
+    from megatronapp_b200.inference.server import InferenceWSServer, MegatronServer
+
+    eng, _ = engine
+    rest = MegatronServer(eng)
+    rest.run(port=18811, block=False)
+    ws_srv = InferenceWSServer(eng, num_layers=2, port=18812)
+    ws_srv.run(block=False)
+    time.sleep(0.3)
+    try:
+        body = json.dumps({"prompts": ["1 2 3"], "tokens_to_generate": 4, "top_k": 1}).encode()
+        req = urllib.request.Request("http://127.0.0.1:18811/api", data=body, method="PUT",
+                                     headers={"Content-Type": "application/json"})
+        out = json.loads(urllib.request.urlopen(req, timeout=30).read())
+        assert len(out["tokens"][0]) >= 4
+        bad = urllib.request.Request("http://127.0.0.1:18811/api", data=json.dumps({"prompts": []}).encode(), method="PUT")
+        with pytest.raises(urllib.error.HTTPError):
+            urllib.request.urlopen(bad, timeout=30)
+        with connect("ws://127.0.0.1:18812") as ws:
+            ws.send(json.dumps({"type": "generate", "prompts": ["4 5 6"], "tokens_to_generate": 2, "top_k": 1,
+                                "visualization_flags": {"MLP1_mat_mul": "true", "MLP2_mat_mul": "false"},
+                                "compressor_config": {"MLP": {"pixels": 4, "method": "mean"}}}))
+            kinds = []
+            while True:
+                m = json.loads(ws.recv(timeout=30))
+                kinds.append((m["type"], m.get("update_type")))
+                if m["type"] == "finish":
+                    assert out["tokens"][0][:0] == []
+                    break
+            assert kinds[0][0] == "start" and ("update", 4) in kinds and ("update", 6) in kinds
+    finally:
+        rest.shutdown()
+        ws_srv.shutdown()
