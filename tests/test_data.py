@@ -1,0 +1,126 @@
+"""Data: .bin/.idx round trip (byte format), native index builders, GPT dataset, blending, samplers,
+tokenizers, preprocess tool."""
+import json
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from megatronapp_b200.data.gpt_dataset import BlendedDataset, GPTDataset, _helpers, parse_blend, parse_split, split_document_ranges
+from megatronapp_b200.data.indexed_dataset import IndexedDataset, IndexedDatasetBuilder
+from megatronapp_b200.data.samplers import MegatronPretrainingRandomSampler, MegatronPretrainingSampler
+from megatronapp_b200.data.tokenizer import GPT2BPETokenizer, NullTokenizer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _make_corpus(tmp_path, n_docs=40, seed=0, name="c"):
+    rng = np.random.default_rng(seed)
+    prefix = str(tmp_path / name)
+    b = IndexedDatasetBuilder(prefix + ".bin", dtype=np.uint16)
+    docs = []
+    for _ in range(n_docs):
+        d = rng.integers(1, 1000, size=int(rng.integers(5, 60))).astype(np.uint16)
+        docs.append(d)
+        b.add_document(d, [len(d)])
+    b.finalize(prefix + ".idx")
+    return prefix, docs
+
+
+def test_idx_file_format_and_roundtrip(tmp_path):
+    prefix, docs = _make_corpus(tmp_path)
+    raw = open(prefix + ".idx", "rb").read()
+    assert raw[:9] == b"MMIDIDX\x00\x00"
+    assert struct.unpack("<Q", raw[9:17])[0] == 1 and raw[17] == 8          # version 1, dtype code 8 = uint16
+    assert struct.unpack("<Q", raw[18:26])[0] == len(docs) and struct.unpack("<Q", raw[26:34])[0] == len(docs) + 1
+    ds = IndexedDataset(prefix)
+    assert len(ds) == len(docs)
+    for i in (0, 7, len(docs) - 1):
+        assert np.array_equal(ds[i], docs[i])
+    assert np.array_equal(ds.get(3, 2, 3), docs[3][2:5])
+
+
+def test_build_sample_idx_matches_python_reference(tmp_path):
+    h = _helpers()
+    sizes = np.array([5, 3, 9, 4, 7], dtype=np.int32)
+    doc_idx = np.array([2, 0, 4, 1, 3, 0, 1, 2, 3, 4], dtype=np.int32)
+    seq, epochs, tpe = 4, 2, int(sizes.sum())
+    got = h.build_sample_idx_int32(sizes, doc_idx, seq, epochs, tpe, True, 1)
+    # python reference: walk the concatenated token stream
+    stream = np.concatenate([np.full(sizes[d], i) for i, d in enumerate(doc_idx)])   # doc position per token
+    n = (epochs * tpe - 1) // seq
+    assert got.shape == (n + 1, 2)
+    starts = np.concatenate([[0], np.cumsum(sizes[doc_idx])])
+    for i in range(n + 1):
+        tok = i * seq
+        di = int(stream[tok]) if tok < len(stream) else len(doc_idx) - 1
+        assert got[i, 0] == di and got[i, 1] == tok - starts[di]
+
+
+def test_gpt_dataset_samples_are_contiguous_token_windows(tmp_path):
+    prefix, docs = _make_corpus(tmp_path)
+    ds = IndexedDataset(prefix)
+    g = GPTDataset(ds, (0, 30), num_samples=50, seq_length=16, seed=1, cache_dir=str(tmp_path / "cache"))
+    assert len(g) >= 50
+    item = g[3]
+    assert item["tokens"].shape == (16,) and torch.equal(item["tokens"][1:], item["labels"][:-1])
+    g2 = GPTDataset(ds, (0, 30), num_samples=50, seq_length=16, seed=1, cache_dir=str(tmp_path / "cache"))
+    assert torch.equal(g2[3]["tokens"], item["tokens"])        # index cache reload is identical
+    seen = set()
+    for i in range(len(g)):
+        seen.add(int(g.shuffle_idx[i]))
+    assert len(seen) == len(g)
+
+
+def test_blending_respects_weights(tmp_path):
+    p1, _ = _make_corpus(tmp_path, 40, 0, "a")
+    p2, _ = _make_corpus(tmp_path, 40, 1, "b")
+    d1 = GPTDataset(IndexedDataset(p1), (0, 40), 100, 8, 1)
+    d2 = GPTDataset(IndexedDataset(p2), (0, 40), 100, 8, 1)
+    b = BlendedDataset([d1, d2], [0.75, 0.25], 200)
+    frac = float((b.dataset_index == 0).mean())
+    assert abs(frac - 0.75) < 0.02 and b[5]["tokens"].shape == (8,)
+    assert parse_blend(["0.3", "x", "0.7", "y"]) == (["x", "y"], [0.3, 0.7])
+    assert parse_split("969,30,1") == [0.969, 0.03, 0.001]
+    assert split_document_ranges(1000, [0.969, 0.03, 0.001]) == [(0, 969), (969, 999), (999, 1000)]
+
+
+def test_samplers_partition_batches_across_dp():
+    a = list(MegatronPretrainingSampler(32, 0, 2, 0, 2))
+    b = list(MegatronPretrainingSampler(32, 0, 2, 1, 2))
+    assert a[0] == [0, 1] and b[0] == [2, 3] and len(a) == 8
+    assert not set(sum(a, [])) & set(sum(b, []))
+    r = MegatronPretrainingRandomSampler(list(range(32)), 32, 0, 2, 0, 2, seed=3)
+    assert len(list(r)) == 8
+
+
+def test_gpt2_bpe_tokenizer_roundtrip(tmp_path):
+    from megatronapp_b200.data.tokenizer import bytes_to_unicode
+
+    be = bytes_to_unicode()
+    vocab = {c: i for i, c in enumerate(sorted(set(be.values())))}
+    for tok in ("he", "ll", "hell", "hello", "Ġw", "Ġwo"):
+        vocab[tok] = len(vocab)
+    vocab["<|endoftext|>"] = len(vocab)
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\nh e\nl l\nhe ll\nhell o\nĠ w\nĠw o\n")
+    t = GPT2BPETokenizer(str(tmp_path / "vocab.json"), str(tmp_path / "merges.txt"))
+    ids = t.tokenize("hello world")
+    assert ids[0] == vocab["hello"] and t.detokenize(ids) == "hello world"
+    assert t.decoder[vocab["hello"]] == "hello" and t.eod == vocab["<|endoftext|>"]
+    assert NullTokenizer(100).tokenize("3 7 9") == [3, 7, 9]
+
+
+def test_preprocess_tool(tmp_path):
+    src = tmp_path / "in.jsonl"
+    src.write_text("\n".join(json.dumps({"text": " ".join(str(x) for x in range(i, i + 12))}) for i in range(20)))
+    out = tmp_path / "corp"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "preprocess_data.py"), "--input", str(src),
+                           "--tokenizer-type", "NullTokenizer", "--vocab-size", "500", "--append-eod",
+                           "--output-prefix", str(out)])
+    ds = IndexedDataset(str(out) + "_text_document")
+    assert len(ds) == 20 and ds[2].tolist() == list(range(2, 14)) + [500]
