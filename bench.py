@@ -212,7 +212,10 @@ def main():
     ap.add_argument("--microbatches-per-gpu", type=int, default=8)
     ap.add_argument("--tp", type=int, default=None)
     ap.add_argument("--no-fused-tp-comm", action="store_true", help="NCCL collectives instead of fused AG/RS GEMMs")
+    ap.add_argument("--fused-rs", action="store_true", help="also fuse GEMM->reduce-scatter (default: AG->GEMM only)")
     args = ap.parse_args()
+    if args.fused_rs:
+        os.environ["B200_FUSED_RS"] = "1"
     if args.impl == "reference":
         from baseline.reference_arm import run_reference
 

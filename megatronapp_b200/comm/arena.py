@@ -127,9 +127,15 @@ class TPFusedComm:
     """
 
     def __init__(self, arena: SymmetricArena, max_tokens: int, max_in: int, max_out: int,
-                 n_comm_ctas: int = 20):
+                 n_comm_ctas: int = 8):
         self.arena = arena
         self.n_comm_ctas = n_comm_ctas
+        # GEMM->RS fusion is numerically validated but (round 1) ~20 % slower than tcgen05 GEMM +
+        # NCCL reduce-scatter on 2 GPUs; AG->GEMM fusion wins 8-16 % -- see profiles/.  Opt in with
+        # B200_FUSED_RS=1 / bench.py --fused-rs.
+        import os
+
+        self.use_fused_rs = os.environ.get("B200_FUSED_RS", "0") == "1"
         self.calls = {"ag": 0, "rs": 0}
         ext = ops.ext()
         nflags = max(ext.gemm_flags_needed(max_tokens, max(max_in, max_out), arena.size), 4096)

@@ -417,8 +417,8 @@ def attention_ref(q, k, v, scale=None, causal=True, dropout_p=0.0, return_probs=
     if causal:
         cm = torch.ones(sq, sk, dtype=torch.bool, device=q.device).tril(diagonal=sk - sq)
         s = s.masked_fill(~cm, float("-inf"))
-    if mask is not None:  # True = masked out (Megatron convention)
-        s = s.masked_fill(mask, float("-inf"))
+    if mask is not None:  # True = masked out (Megatron convention); finite fill keeps fully
+        s = s.masked_fill(mask, -10000.0)  # masked (padding) query rows NaN-free, as in the reference
     p = torch.softmax(s, dim=-1)
     if dropout_p > 0.0:
         p = F.dropout(p, p=dropout_p)
@@ -477,7 +477,7 @@ def attention(q, k, v, scale=None, causal=True, dropout_p=0.0, training=True, ma
     if impl == "ref":
         return attention_ref(q, k, v, scale, causal, p, mask=mask)
     fallback_counts["attention_sdpa"] += 1
-    am = None if mask is None else ~mask
+    am = None if mask is None else torch.zeros(mask.shape, dtype=q.dtype, device=q.device).masked_fill(mask, -10000.0)
     return F.scaled_dot_product_attention(q, k, v, attn_mask=am, dropout_p=p,
                                           is_causal=causal and mask is None, scale=scale,
                                           enable_gqa=(k.shape[1] != q.shape[1]))

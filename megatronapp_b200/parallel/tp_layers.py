@@ -44,7 +44,7 @@ from ..scope import hooks as scope_hooks
 _FUSED_COMM = None  # TPFusedComm for the tensor-parallel group (installed by setup_tp_fused_comm)
 
 
-def setup_tp_fused_comm(max_tokens: int, hidden: int, max_out: int, n_comm_ctas: int = 20):
+def setup_tp_fused_comm(max_tokens: int, hidden: int, max_out: int, n_comm_ctas: int = 8):
     """Create the TP symmetric arena and enable the fused AG/RS GEMM kernels."""
     global _FUSED_COMM
     from ..comm.arena import SymmetricArena, TPFusedComm
@@ -150,7 +150,7 @@ class _ColumnParallelFn(torch.autograd.Function):
         ar_handle = None
         if ctx.needs_input_grad[0]:
             if ctx.sp and tp > 1:
-                if ctx.fused and _fusable(dy2.shape[0], dy2, weight):
+                if ctx.fused and _FUSED_COMM.use_fused_rs and _fusable(dy2.shape[0], dy2, weight):
                     with _scope("gemm_rs_dgrad", data=dy2.shape[0] * weight.shape[1] * 2):
                         dx = _FUSED_COMM.gemm_rs(dy2, weight, b_mn=True)
                 else:
@@ -276,10 +276,13 @@ class _RowParallelFn(torch.autograd.Function):
         tp = ps.get_tensor_model_parallel_world_size()
         ctx.fused = False
         if sequence_parallel and tp > 1 and do_reduce:
-            if _fusable(x2.shape[0], x2, weight):
+            if _fusable(x2.shape[0], x2, weight) and _FUSED_COMM.use_fused_rs:
                 with _scope("gemm_rs", data=x2.shape[0] * weight.shape[0] * 2):
                     out = _FUSED_COMM.gemm_rs(x2, weight)
                 ctx.fused = True
+            elif _fusable(x2.shape[0], x2, weight):
+                out = _reduce_scatter_along_first_dim(ops.gemm(x2, weight))
+                ctx.fused = True   # backward still uses the fused AG->GEMM dgrad
             else:
                 out = _reduce_scatter_along_first_dim(ops.gemm(x2, weight))
             out_shape = (x.shape[0] // tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
