@@ -33,6 +33,8 @@ def initialize_megatron(extra_args_provider=None, args_defaults=None, ignore_unk
         if not allow_no_cuda:
             raise RuntimeError("this entry point requires CUDA")
         args.distributed_backend = "gloo"
+        if "OMP_NUM_THREADS" not in os.environ:
+            torch.set_num_threads(max(1, min(4, (os.cpu_count() or 2) // max(1, args.world_size))))
     validate_args(args, args_defaults or {})
     set_global_variables(args)
     if not skip_mpu_initialization:

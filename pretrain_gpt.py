@@ -2,6 +2,11 @@
 ``pretrain_gpt.py``: ``model_provider(pre_process, post_process)``, ``forward_step(data_iterator,
 model) -> (output_tensor, partial(loss_func, loss_mask))``, ``loss_func -> (loss, num_tokens,
 {'lm loss': (sum, count)})``, ``train_valid_test_datasets_provider(train_val_test_num_samples)``)."""
+import os
+
+if not os.path.exists("/dev/nvidia0"):   # CPU/gloo mode: avoid OpenMP oversubscription
+    os.environ.setdefault("OMP_NUM_THREADS", "2")
+
 from functools import partial
 
 import torch
