@@ -57,6 +57,10 @@ struct GemmArgs {
 int gemm_bf16(const GemmArgs& args);
 const char* gemm_last_error();
 int gemm_flags_needed(int M, int N, int tp_size);
+// cta_group::2 variant (gemm2_sm100.cu); gemm_bf16 dispatches to it when profitable
+bool gemm2_supported(const GemmArgs& args);
+int gemm2_bf16(const GemmArgs& args);
+const char* gemm2_last_error();
 
 // ---------------------------------------------------------------- elementwise / norm
 void layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,

@@ -705,8 +705,30 @@ int gemm_flags_needed(int M, int N, int tp_size) {
   return mb * (nb > 8 ? nb : 8) + 64;
 }
 
+static int prefer_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_GEMM_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;   // default on; B200_GEMM_2CTA=0 forces the 1-CTA kernel
+  }
+  return v;
+}
+
 int gemm_bf16(const GemmArgs& a) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { g_last_error = "empty problem"; return -1; }
+  // block_n: 2 = force the cta_group::2 kernel, 128 / 256 = force the 1-CTA kernel, 0 = auto
+  if ((a.block_n == 2 || (a.block_n == 0 && prefer_2cta())) && gemm2_supported(a)) {
+    if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15) ||
+        (reinterpret_cast<uintptr_t>(a.D) & 15) || (a.lda % 8) || (a.ldb % 8) ||
+        (a.epilogue == kEpiStore16 ? (a.ldd % 8) : ((a.ldd % 4) || (a.N % 4)))) {
+      g_last_error = "alignment: pointers 16B, lda/ldb % 8, ldd % 8 (16-bit) or % 4 (fp32)";
+      return -2;
+    }
+    int rc = gemm2_bf16(a);
+    if (rc != 0) g_last_error = gemm2_last_error();
+    return rc;
+  }
+  if (a.block_n == 2) { g_last_error = "2-CTA kernel does not support this problem"; return -3; }
   if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15) ||
       (reinterpret_cast<uintptr_t>(a.D) & 15)) { g_last_error = "pointers must be 16B aligned"; return -2; }
   if ((a.lda % 8) || (a.ldb % 8)) { g_last_error = "lda/ldb must be multiples of 8 elements"; return -2; }

@@ -56,7 +56,9 @@ def check_gemm(mode, shapes=None, dtype="bf16"):
     shapes = shapes or [(128, 128, 64), (256, 256, 128), (384, 512, 320), (2048, 4096, 4096), (300, 520, 264),
                         (4096, 1024, 2048)]
     for (M, N, K) in shapes:
-        for bn in (128, 256):
+        for bn in (128, 256, 2):   # 2 = cta_group::2 kernel
+            if bn == 2 and (M < 256 or N < 128):
+                continue
             torch.manual_seed(M + N + K)
             A = torch.randn(M, K, device="cuda", dtype=dt) * 0.5
             B = torch.randn(N, K, device="cuda", dtype=dt) * 0.5
@@ -220,12 +222,24 @@ def check_gemm_perf():
         B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         fl = 2.0 * M * N * K
-        for bn in (0, 128, 256):
+        for bn in (0, 256, 2):
             try:
                 t = _time(lambda: ops.gemm(A, B, out=out, block_n=bn), flush=flush)
                 res[f"{name}_b200_bn{bn}_tflops"] = round(fl / t / 1e9, 1)
             except Exception as e:  # noqa: BLE001
                 res[f"{name}_b200_bn{bn}"] = f"EXC {e}"
+        try:
+            dYp = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+            dXp = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+            mgp = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+            for bn in (256, 2):
+                t = _time(lambda: ops.gemm(dYp, B, out=dXp, b_mn=True, block_n=bn), flush=flush)
+                res[f"{name}_dgrad_bn{bn}_tflops"] = round(fl / t / 1e9, 1)
+                t = _time(lambda: ops.gemm(dYp, A, out=mgp, a_mn=True, b_mn=True, epilogue=1, block_n=bn), flush=flush)
+                res[f"{name}_wgrad_bn{bn}_tflops"] = round(fl / t / 1e9, 1)
+            del dYp, dXp, mgp
+        except Exception as e:  # noqa: BLE001
+            res[f"{name}_bwd_2cta"] = f"EXC {e}"
         t = _time(lambda: torch.matmul(A, B.t(), out=out), flush=flush)
         res[f"{name}_cublas_tflops"] = round(fl / t / 1e9, 1)
         # dgrad / wgrad layouts
