@@ -27,7 +27,10 @@ from ..parallel.ddp import DistributedDataParallel, DistributedDataParallelConfi
 from ..scan.tracer import get_tracer
 from ..transformer.module import Float16Module
 from ..utils.microbatches import get_current_global_batch_size, get_num_microbatches, update_num_microbatches
+from ..utils.straggler import get_straggler_detector
 from . import checkpointing
+from .rerun_state_machine import (RerunDataIterator, RerunErrorInjector, get_rerun_state_machine,
+                                  initialize_rerun_state_machine)
 from .arguments import core_transformer_config_from_args
 from .global_vars import get_args, get_tensorboard_writer, get_timers, get_signal_handler
 from .initialize import initialize_megatron
@@ -200,10 +203,24 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
         m.zero_grad_buffer()
     optimizer.zero_grad()
     fb = schedules.get_forward_backward_func()
-    losses_reduced = fb(forward_step_func=forward_step_func, data_iterator=data_iterator, model=model,
-                        num_microbatches=get_num_microbatches(), seq_length=args.seq_length,
-                        micro_batch_size=args.micro_batch_size, decoder_seq_length=args.decoder_seq_length,
-                        forward_only=False)
+    rsm = get_rerun_state_machine()
+    first = True
+    losses_reduced = []
+    # the state machine may ask for the same step to be re-executed on identical data (fault
+    # classification, reference training.py:1322 / rerun_state_machine.py:258)
+    while rsm.should_run_forward_backward(data_iterator):
+        if not first:
+            for m in model:
+                m.zero_grad_buffer()
+            optimizer.zero_grad()
+        first = False
+        losses_reduced = fb(forward_step_func=forward_step_func, data_iterator=data_iterator, model=model,
+                            num_microbatches=get_num_microbatches(), seq_length=args.seq_length,
+                            micro_batch_size=args.micro_batch_size, decoder_seq_length=args.decoder_seq_length,
+                            forward_only=False)
+    should_ckpt, should_exit, exit_code = rsm.should_checkpoint_and_exit()
+    if should_exit:
+        return {}, True, should_ckpt, should_exit, exit_code, None, None
     if args.empty_unused_memory_level >= 1:
         torch.cuda.empty_cache()
     timers("optimizer", log_level=1).start(barrier=args.barrier_with_L1_time)
@@ -240,7 +257,7 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
                 loss_reduced[key] = num / den
             else:
                 loss_reduced[key] = sum(vals) / len(vals)
-    return loss_reduced, skipped_iter, grad_norm, num_zeros_in_grad
+    return loss_reduced, skipped_iter, False, False, 0, grad_norm, num_zeros_in_grad
 
 
 def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scale, report_memory_flag, skipped_iter,
@@ -337,6 +354,9 @@ def evaluate(forward_step_func, data_iterator, model, config, verbose=False):
                         if torch.is_tensor(v) and v.numel() == 2:
                             acc = total.get(k, torch.zeros(2, device=v.device))
                             total[k] = acc + v
+                        elif isinstance(v, (tuple, list)) and len(v) == 2:
+                            acc = total.get(k, torch.zeros(2))
+                            total[k] = acc + torch.tensor([float(v[0]), float(v[1])])
                         else:
                             acc = total.get(k, torch.zeros(2))
                             total[k] = acc + torch.tensor([float(v), 1.0])
@@ -399,6 +419,10 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             slow = int(cyc)
     exit_flag = False
     start_time = time.time()
+    stimer = get_straggler_detector()
+    if args.log_straggler:
+        stimer.configure(args.world_size, args.rank, mmcnt=args.straggler_minmax_count,
+                         enabled=not args.disable_straggler_on_startup, port=args.straggler_ctrlr_port)
     if args.manual_gc:
         gc.disable()
         gc.collect()
@@ -418,8 +442,20 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             from .. import ops
 
             ops.ext().spin(slow)
-        loss_dict, skipped_iter, grad_norm, num_zeros = train_step(
-            forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler, config)
+        _maybe_simulate_fault(args, iteration)
+        if getattr(args, '_fault_deadline', None) and time.time() > args._fault_deadline:
+            while True:
+                time.sleep(3600)
+        with stimer:
+            loss_dict, skipped_iter, should_ckpt, should_exit, exit_code, grad_norm, num_zeros = train_step(
+                forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler, config)
+        if should_exit:
+            if should_ckpt and args.save:
+                save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, nflops)
+            print_rank_0(f"rerun state machine requested exit (code {exit_code})")
+            args.rerun_exit_code = exit_code
+            exit_flag = True
+            break
         iteration += 1
         batch_size = ps.get_data_parallel_world_size() * args.micro_batch_size * get_num_microbatches()
         args.consumed_train_samples += batch_size
@@ -434,6 +470,8 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
                 break
         report_memory_flag = training_log(loss_dict, total_loss_dict, lr or 0.0, iteration, loss_scale,
                                           report_memory_flag, skipped_iter, grad_norm, params_norm, num_zeros)
+        if args.log_straggler and iteration % args.log_interval == 0:
+            stimer.report(num_floating_point_operations(args, batch_size) * args.log_interval, args.log_interval)
         if args.eval_interval and iteration % args.eval_interval == 0 and valid_data_iterator is not None:
             timers("interval-time").stop()
             evaluate_and_print_results(f"iteration {iteration}", forward_step_func, valid_data_iterator, model,
@@ -479,6 +517,33 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         ws_server.shutdown()
     args.num_floating_point_operations_so_far = nflops
     return iteration, nflops, exit_flag
+
+
+def _maybe_simulate_fault(args, iteration):
+    """``--simulated-fault kind:rank:delay_s`` (reference training.py ``--simulated-fault``): hang or
+    kill one rank after a delay so failure detection / restart logic can be exercised."""
+    spec = getattr(args, "simulated_fault", None)
+    if not spec or getattr(args, "_fault_armed", False):
+        return
+    kind, rank, delay = (spec.replace(";", ":").split(":") + ["0", "0"])[:3]
+    if int(rank) != args.rank:
+        return
+    args._fault_armed = True
+    import threading
+
+    def fire():
+        time.sleep(float(delay))
+        if kind == "rank_killed":
+            os.kill(os.getpid(), 9)
+        else:   # rank_hung
+            while True:
+                time.sleep(3600)
+
+    if kind == "rank_killed":
+        threading.Thread(target=fire, daemon=True).start()
+    else:
+        # a hung rank blocks its main thread at the next iteration boundary after the delay
+        args._fault_deadline = time.time() + float(delay)
 
 
 def cyclic_iter(it):
@@ -545,6 +610,12 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     print_rank_0("done with setup ...")
     timers.log(["model-and-optimizer-setup", "train/valid/test-data-iterators-setup"], barrier=True)
     iteration, nflops = args.iteration, args.num_floating_point_operations_so_far
+    initialize_rerun_state_machine(
+        mode=args.rerun_mode,
+        error_injector=RerunErrorInjector(args.error_injection_rate, args.error_injection_type, seed=args.seed))
+    if args.rerun_mode != "disabled":
+        wrap = lambda it: RerunDataIterator(it) if it is not None else None
+        train_it = [wrap(i) for i in train_it] if isinstance(train_it, list) else wrap(train_it)
     if not args.skip_train and args.train_iters and args.train_iters > 0:
         print_rank_0("training ...")
         iteration, nflops, exited = train(forward_step_func, model, optimizer, scheduler, train_it, valid_it,

@@ -7,6 +7,7 @@ import os
 if not os.path.exists("/dev/nvidia0"):   # CPU/gloo mode: avoid OpenMP oversubscription
     os.environ.setdefault("OMP_NUM_THREADS", "2")
 
+import math
 from functools import partial
 
 import torch
@@ -16,6 +17,7 @@ from megatronapp_b200.models.gpt import GPTModel, get_gpt_decoder_block_spec, ge
 from megatronapp_b200.parallel import state as mpu
 from megatronapp_b200.training.arguments import core_transformer_config_from_args
 from megatronapp_b200.training.global_vars import get_args, get_timers
+from megatronapp_b200.training.rerun_state_machine import get_rerun_state_machine
 from megatronapp_b200.training.training import pretrain
 from megatronapp_b200.training.utils import get_batch_on_this_tp_rank, print_rank_0
 
@@ -55,6 +57,10 @@ def loss_func(loss_mask, output_tensor):
     loss = torch.cat([torch.sum(losses.view(-1) * loss_mask).view(1), total_tokens.view(1)])
     if args.context_parallel_size > 1:
         torch.distributed.all_reduce(loss, group=mpu.get_context_parallel_group())
+    rsm = get_rerun_state_machine()
+    if rsm.mode != "disabled":
+        # NaN / Inf / spiky-loss checks with re-execution (reference pretrain_gpt.py loss_func)
+        rsm.validate_result(loss[0] / loss[1].clamp(min=1), lambda v: not math.isfinite(v), "found NaN/Inf in local loss")
     reporting = loss.clone().detach()
     g = mpu.get_data_parallel_group()
     if g is not None and not isinstance(g, mpu._SingleGroup) and torch.distributed.get_world_size(g) > 1:

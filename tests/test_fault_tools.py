@@ -1,0 +1,70 @@
+"""Rerun state machine (fault classification + injection) and straggler detector."""
+import math
+
+from megatronapp_b200.training.rerun_state_machine import (EXIT_CODE_FAILED_ON_RESULT_VALIDATION,
+                                                          EXIT_CODE_RESUME_TO_DISAMBIGUATE, RerunDataIterator,
+                                                          RerunErrorInjector, RerunMode, RerunStateMachine)
+from megatronapp_b200.utils.straggler import StragglerDetector
+
+
+def _run_step(rsm, it, compute):
+    runs = 0
+    while rsm.should_run_forward_backward(it):
+        batch = next(it)
+        runs += 1
+        rsm.validate_result(compute(batch, runs), lambda v: math.isnan(v) or v > 100, "loss check")
+    return runs
+
+
+def test_disabled_mode_runs_once():
+    rsm = RerunStateMachine(RerunMode.DISABLED)
+    it = RerunDataIterator(iter(range(10)))
+    assert _run_step(rsm, it, lambda b, r: float("nan")) == 1 and next(it) == 1
+
+
+def test_transient_error_is_rerun_on_same_data_and_classified():
+    rsm = RerunStateMachine(RerunMode.VALIDATE_RESULTS)
+    it = RerunDataIterator(iter(range(10)))
+    seen = []
+    assert _run_step(rsm, it, lambda b, r: (seen.append(b), float("nan") if r == 1 else 1.0)[1]) == 2
+    assert seen == [0, 0]                                   # replayed the identical batch
+    assert rsm.diagnostics[-1][1] == "transient_error"
+    assert rsm.should_checkpoint_and_exit() == (False, True, EXIT_CODE_FAILED_ON_RESULT_VALIDATION)
+
+
+def test_persistent_and_correct_results():
+    rsm = RerunStateMachine(RerunMode.VALIDATE_RESULTS)
+    it = RerunDataIterator(iter(range(10)))
+    _run_step(rsm, it, lambda b, r: 1e6)                    # reproducible but rejected value
+    assert rsm.diagnostics[-1][1] == "persistent_error"
+    assert rsm.should_checkpoint_and_exit() == (True, True, EXIT_CODE_RESUME_TO_DISAMBIGUATE)
+    rsm2 = RerunStateMachine(RerunMode.VALIDATE_RESULTS)
+    it2 = RerunDataIterator(iter(range(10)))
+    assert _run_step(rsm2, it2, lambda b, r: 2.0) == 1 and not rsm2.diagnostics   # healthy step: one run
+
+
+def test_error_injector_exercises_recovery():
+    inj = RerunErrorInjector(error_injection_rate=1, error_injection_type="transient_error")
+    rsm = RerunStateMachine(RerunMode.VALIDATE_RESULTS, inj)
+    it = RerunDataIterator(iter(range(10)))
+    assert _run_step(rsm, it, lambda b, r: 1.0) == 2
+    assert rsm.diagnostics[-1][1] == "transient_error" and inj.injected == 1
+
+
+def test_determinism_stats_mode():
+    rsm = RerunStateMachine(RerunMode.REPORT_DETERMINISM_STATS)
+    it = RerunDataIterator(iter(range(10)))
+    assert _run_step(rsm, it, lambda b, r: 1.0 + 1e-3 * (r - 1)) == 2
+    assert abs(rsm.stats["max_rel_diff"] - 1e-3) < 1e-9
+
+
+def test_straggler_detector_single_rank():
+    d = StragglerDetector()
+    d.configure(1, 0, enabled=True)
+    for _ in range(3):
+        with d(bdata=True):
+            pass
+        with d:
+            sum(range(1000))
+    rep = d.report(total_flops=1e9, log_interval=3)
+    assert rep.max_rank == 0 and rep.max_elapsed > 0
