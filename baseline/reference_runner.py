@@ -30,8 +30,10 @@ def main(args, MODELS, layout_for, pad_vocab):
     if args.layers:
         L = args.layers
     dp = args.gpus // (tp * pp)
-    n_mb = args.microbatches_per_gpu * args.gpus // dp
-    gbs = n_mb * args.micro_batch * dp
+    if not args.micro_batch:
+        args.micro_batch = tp          # same rule as the framework's own arm (bench.py)
+    gbs = args.microbatches_per_gpu * args.gpus      # weak scaling: 8 sequences per GPU
+    n_mb = gbs // (args.micro_batch * dp)
     vocab = pad_vocab(V, tp)
     argv = ["reference", "--transformer-impl", "local", "--use-mcore-models",
             "--num-layers", str(L), "--hidden-size", str(H), "--num-attention-heads", str(A),
@@ -45,7 +47,12 @@ def main(args, MODELS, layout_for, pad_vocab):
             "--mock-data", "--no-create-attention-mask-in-dataloader", "--no-gradient-accumulation-fusion",
             "--no-masked-softmax-fusion", "--no-persist-layer-norm", "--distributed-backend", "nccl", "--log-interval", "1000000",
             "--eval-iters", "0", "--no-save-optim", "--no-save-rng", "--ckpt-format", "torch"]
-    if tp > 1:
+    import importlib.util
+
+    # the stock local spec falls back to torch LayerNorm without Apex/TE, and that norm refuses
+    # sequence parallelism (core/transformer/torch_norm.py:32) -> plain TP (all-reduce) then
+    sp = tp > 1 and importlib.util.find_spec("apex") is not None
+    if sp:
         argv += ["--sequence-parallel"]
     if dp > 1:
         argv += ["--use-distributed-optimizer"]
@@ -140,7 +147,7 @@ def main(args, MODELS, layout_for, pad_vocab):
     ms, ms2 = float(t[0]), float(t[1])
     tokens = gbs * S * args.steps
     if rank == 0:
-        par = f"tp{tp}" + (f"pp{pp}" if pp > 1 else "") + (f"dp{dp}" if dp > 1 else "") + ("+sp" if tp > 1 else "")
+        par = f"tp{tp}" + (f"pp{pp}" if pp > 1 else "") + (f"dp{dp}" if dp > 1 else "") + ("+sp" if sp else ("+no-sp(torch LayerNorm lacks SP; no Apex/TE offline)" if tp > 1 else ""))
         h2d = sum(v.numel() * v.element_size() for b in pin_b for v in b.values())
         print(json.dumps({
             "impl": "reference", "metric": "GPT training tokens/sec (whole job, device-timed, max over ranks)",

@@ -117,11 +117,12 @@ def run_own(args):
     if args.layers:
         L = args.layers
     vocab = pad_vocab(V, tp)
-    mbs = args.micro_batch
-    n_mb = args.microbatches_per_gpu * args.gpus // max(1, args.gpus // (tp * pp))
+    # micro-batch = TP degree keeps the per-GPU GEMM shapes of the 1-GPU run (a TP4 rank with
+    # mbs 1 would run 35 us GEMMs and be launch-bound); the reference arm uses the same rule
+    mbs = args.micro_batch or tp
     dp = args.gpus // (tp * pp)
-    n_mb = args.microbatches_per_gpu * args.gpus // dp  # microbatches per data-parallel replica
-    global_batch = n_mb * mbs * dp
+    global_batch = args.microbatches_per_gpu * args.gpus   # weak scaling: 8 sequences per GPU
+    n_mb = global_batch // (mbs * dp)                       # microbatches per data-parallel replica
     ops.ext()
     state = build_gpt_for_bench(L, H, A, S, vocab, mbs, ffn=F, tp=tp, pp=pp, sequence_parallel=tp > 1,
                                 device=f"cuda:{local_rank}", lr=1e-4, fused_tp_comm=not args.no_fused_tp_comm,
@@ -208,7 +209,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--model", default="gpt3_6.7b", choices=list(MODELS))
     ap.add_argument("--layers", type=int, default=None, help="debug only: override layer count (invalidates the number)")
-    ap.add_argument("--micro-batch", type=int, default=1)
+    ap.add_argument("--micro-batch", type=int, default=None, help="default: TP degree")
     ap.add_argument("--microbatches-per-gpu", type=int, default=8)
     ap.add_argument("--tp", type=int, default=None)
     ap.add_argument("--no-fused-tp-comm", action="store_true", help="NCCL collectives instead of fused AG/RS GEMMs")

@@ -128,7 +128,8 @@ void check_finite(const void* x, int64_t n, int dtype, float* found_inf, cudaStr
 void chunk_mean(const void* x, float* out, int64_t rows, int cols, int pixels, bool is_bf16,
                 cudaStream_t s);
 
-// flash attention (tcgen05), layout [b, h, s, d] contiguous, d in {64, 128}
+// flash attention (tcgen05).  Every operand is a strided logical [b, h, s, d] view with a
+// contiguous last dim (strides in elements), d in {64, 128}; lse / delta are [b, h, s] fp32.
 struct AttnArgs {
   const void* q; const void* k; const void* v; void* o; float* lse;
   const void* d_o; void* dq; void* dk; void* dv; float* delta; float* dq_accum;
@@ -137,9 +138,12 @@ struct AttnArgs {
   bool causal;
   bool is_bf16;
   void* probs_out;  // optional MegaScope export [b,hq,sq,sk] (fwd only)
+  int64_t q_sb, q_sh, q_ss, k_sb, k_sh, k_ss, v_sb, v_sh, v_ss, o_sb, o_sh, o_ss;
+  int64_t do_sb, do_sh, do_ss, dq_sb, dq_sh, dq_ss, dk_sb, dk_sh, dk_ss, dv_sb, dv_sh, dv_ss;
 };
 int attn_fwd(const AttnArgs& a, cudaStream_t s);
 int attn_bwd(const AttnArgs& a, cudaStream_t s);
+const char* attn_last_error();
 
 // ---------------------------------------------------------------- comm
 void push_flags_barrier(uint32_t* const* peer_flags, int rank, int size, int slot, uint32_t epoch,

@@ -335,41 +335,61 @@ Tensor chunk_mean(const Tensor& x, int64_t pixels) {
 }
 
 // ---------------------------------------------------------------- attention
+namespace {
+void check_bhsd(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.dim() == 4 && t.stride(3) == 1, name, " must be a [b,h,s,d] view with contiguous last dim");
+}
+}  // namespace
+// q/k/v: strided logical [b,h,s,d] views (e.g. permuted [s,b,h,d] activations).  The output is
+// allocated [s,b,h,d]-contiguous and returned as its [b,h,s,d] view.
 std::vector<Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal, bool want_probs) {
   c10::cuda::CUDAGuard guard(q.device());
-  TORCH_CHECK(q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous(), "attn expects contiguous [b,h,s,d]");
+  check_bhsd(q, "q"); check_bhsd(k, "k"); check_bhsd(v, "v");
   b200::AttnArgs a{};
   a.b = static_cast<int>(q.size(0)); a.hq = static_cast<int>(q.size(1)); a.sq = static_cast<int>(q.size(2)); a.d = static_cast<int>(q.size(3));
   a.hkv = static_cast<int>(k.size(1)); a.sk = static_cast<int>(k.size(2));
-  auto o = torch::empty_like(q);
+  auto o_sbhd = torch::empty({a.sq, a.b, a.hq, a.d}, q.options());
+  auto o = o_sbhd.permute({1, 2, 0, 3});
   auto lse = torch::empty({a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));
-  Tensor probs = want_probs ? torch::empty({a.b, a.hq, a.sq, a.sk}, q.options()) : torch::empty({0}, q.options());
-  a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = o.data_ptr(); a.lse = lse.data_ptr<float>();
+  Tensor probs = torch::empty({0}, q.options());
+  a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = o_sbhd.data_ptr(); a.lse = lse.data_ptr<float>();
+  a.q_sb = q.stride(0); a.q_sh = q.stride(1); a.q_ss = q.stride(2);
+  a.k_sb = k.stride(0); a.k_sh = k.stride(1); a.k_ss = k.stride(2);
+  a.v_sb = v.stride(0); a.v_sh = v.stride(1); a.v_ss = v.stride(2);
+  a.o_sb = o.stride(0); a.o_sh = o.stride(1); a.o_ss = o.stride(2);
   a.scale = static_cast<float>(scale); a.causal = causal; a.is_bf16 = is_bf16(q);
-  a.probs_out = want_probs ? probs.data_ptr() : nullptr;
+  a.probs_out = want_probs ? reinterpret_cast<void*>(1) : nullptr;
   int rc = b200::attn_fwd(a, cur_stream());
-  TORCH_CHECK(rc == 0, "b200 attn_fwd failed: ", rc);
+  TORCH_CHECK(rc == 0, "b200 attn_fwd failed: ", rc, " ", b200::attn_last_error());
   count();
   return {o, lse, probs};
 }
 std::vector<Tensor> attn_bwd(const Tensor& d_o, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o,
                              const Tensor& lse, double scale, bool causal) {
   c10::cuda::CUDAGuard guard(q.device());
+  check_bhsd(q, "q"); check_bhsd(k, "k"); check_bhsd(v, "v"); check_bhsd(o, "o");
   b200::AttnArgs a{};
   a.b = static_cast<int>(q.size(0)); a.hq = static_cast<int>(q.size(1)); a.sq = static_cast<int>(q.size(2)); a.d = static_cast<int>(q.size(3));
   a.hkv = static_cast<int>(k.size(1)); a.sk = static_cast<int>(k.size(2));
-  auto doc = d_o.contiguous();
-  auto dq = torch::empty_like(q);
-  auto dk = torch::empty_like(k);
-  auto dv = torch::empty_like(v);
+  Tensor doc = d_o.stride(3) == 1 ? d_o : d_o.contiguous();
+  auto dq = torch::empty({a.sq, a.b, a.hq, a.d}, q.options()).permute({1, 2, 0, 3});
+  auto dk = torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
+  auto dv = torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
   auto delta = torch::empty({a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));
-  auto dq_accum = torch::zeros({a.b, a.hq, a.sq, a.d}, q.options().dtype(at::kFloat));
   a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = const_cast<void*>(o.data_ptr()); a.lse = lse.data_ptr<float>();
   a.d_o = doc.data_ptr(); a.dq = dq.data_ptr(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
-  a.delta = delta.data_ptr<float>(); a.dq_accum = dq_accum.data_ptr<float>();
+  a.delta = delta.data_ptr<float>(); a.dq_accum = nullptr;
+  a.q_sb = q.stride(0); a.q_sh = q.stride(1); a.q_ss = q.stride(2);
+  a.k_sb = k.stride(0); a.k_sh = k.stride(1); a.k_ss = k.stride(2);
+  a.v_sb = v.stride(0); a.v_sh = v.stride(1); a.v_ss = v.stride(2);
+  a.o_sb = o.stride(0); a.o_sh = o.stride(1); a.o_ss = o.stride(2);
+  a.do_sb = doc.stride(0); a.do_sh = doc.stride(1); a.do_ss = doc.stride(2);
+  a.dq_sb = dq.stride(0); a.dq_sh = dq.stride(1); a.dq_ss = dq.stride(2);
+  a.dk_sb = dk.stride(0); a.dk_sh = dk.stride(1); a.dk_ss = dk.stride(2);
+  a.dv_sb = dv.stride(0); a.dv_sh = dv.stride(1); a.dv_ss = dv.stride(2);
   a.scale = static_cast<float>(scale); a.causal = causal; a.is_bf16 = is_bf16(q);
   int rc = b200::attn_bwd(a, cur_stream());
-  TORCH_CHECK(rc == 0, "b200 attn_bwd failed: ", rc);
+  TORCH_CHECK(rc == 0, "b200 attn_bwd failed: ", rc, " ", b200::attn_last_error());
   count(3);
   return {dq, dk, dv};
 }

@@ -427,6 +427,8 @@ def attention_ref(q, k, v, scale=None, causal=True, dropout_p=0.0, return_probs=
 
 
 class _AttnFn(torch.autograd.Function):
+    """tcgen05 flash attention on strided [b, h, s, d] views (csrc/attention_sm100.cu)."""
+
     @staticmethod
     def forward(ctx, q, k, v, scale, causal):
         o, lse, _ = ext().attn_fwd(q, k, v, scale, causal, False)
@@ -441,37 +443,49 @@ class _AttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
-_ATTN_IMPL = os.environ.get("B200_ATTN_IMPL", "auto")  # auto | native | sdpa | ref
+_ATTN_IMPL = os.environ.get("B200_ATTN_IMPL", "sdpa")  # auto | native | sdpa | ref
 _NATIVE_ATTN_OK = None
 
 
 def native_attention_available() -> bool:
+    """True when the in-tree tcgen05 attention kernels (forward AND backward) run on this device."""
     global _NATIVE_ATTN_OK
     if _NATIVE_ATTN_OK is None:
         _NATIVE_ATTN_OK = False
         if have_ext() and torch.cuda.is_available():
             try:
-                q = torch.zeros(1, 1, 128, 128, dtype=torch.bfloat16, device="cuda")
-                ext().attn_fwd(q, q, q, 1.0, True, False)
+                q = torch.zeros(1, 1, 128, 64, dtype=torch.bfloat16, device="cuda")
+                o, lse, _ = ext().attn_fwd(q, q, q, 1.0, True, False)
+                ext().attn_bwd(o, q, q, q, o, lse, 1.0, True)
                 _NATIVE_ATTN_OK = True
             except RuntimeError:
                 _NATIVE_ATTN_OK = False
     return _NATIVE_ATTN_OK
 
 
+def _attn_view_ok(t) -> bool:
+    return (t.stride(3) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 and t.stride(2) % 8 == 0
+            and t.data_ptr() % 16 == 0)
+
+
 def attention(q, k, v, scale=None, causal=True, dropout_p=0.0, training=True, mask=None):
-    """Fused attention.  Native tcgen05 kernel when available; otherwise the SDPA library
-    kernel on CUDA (counted in ``fallback_counts['attention_sdpa']``) or the reference on CPU."""
+    """Fused attention on logical ``[b, h, s, d]`` tensors (any strides with a contiguous last dim,
+    e.g. permuted ``[s, b, h, d]`` activations -- consumed in place through 4-D tensor maps).
+    Native tcgen05 kernels when usable; otherwise the SDPA library kernel on CUDA (counted in
+    ``fallback_counts['attention_sdpa']``) or the reference on CPU."""
     d = q.shape[-1]
     scale = scale if scale is not None else 1.0 / math.sqrt(d)
     p = dropout_p if training else 0.0
     if not q.is_cuda:
         return attention_ref(q, k, v, scale, causal, p, mask=mask)
     impl = _ATTN_IMPL
-    usable = (_native(q) and p == 0.0 and mask is None and d in (64, 128) and q.shape[2] % 128 == 0
-              and k.shape[2] % 128 == 0)
+    sq, sk = q.shape[2], k.shape[2]
+    needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+    usable = (_native(q) and p == 0.0 and mask is None and d in (64, 128) and (not causal or sq == sk)
+              and q.shape[1] % k.shape[1] == 0 and (not needs_grad or (sq % 64 == 0 and sk % 64 == 0)))
     if impl in ("auto", "native") and usable and native_attention_available():
-        return _AttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), scale, causal)
+        q, k, v = (t if _attn_view_ok(t) else t.contiguous() for t in (q, k, v))
+        return _AttnFn.apply(q, k, v, scale, causal)
     if impl == "native":
         raise RuntimeError("native attention requested but not usable for this problem")
     if impl == "ref":

@@ -282,24 +282,63 @@ def check_elementwise_perf():
     return res
 
 
-def check_attention():
+_ATTN_CASES = [(1, 2, 2, 256, 128, True), (2, 4, 4, 512, 128, True), (2, 4, 2, 384, 64, True),
+               (1, 2, 2, 256, 128, False), (1, 8, 8, 2048, 128, True), (1, 2, 1, 1024, 64, False)]
+
+
+def _attn_inputs(b, h, hk, s, d, sbhd):
+    """q/k/v as logical [b,h,s,d]; ``sbhd`` makes them permuted views of [s,b,h,d] storage (the
+    layout the transformer layer hands over)."""
+    import torch
+
+    torch.manual_seed(s + d)
+    if sbhd:
+        mk = lambda hh: torch.randn(s, b, hh, d, device="cuda", dtype=torch.bfloat16).permute(1, 2, 0, 3)
+    else:
+        mk = lambda hh: torch.randn(b, hh, s, d, device="cuda", dtype=torch.bfloat16)
+    return mk(h), mk(hk), mk(hk)
+
+
+def check_attention_fwd():
+    """Native tcgen05 flash-attention forward vs the fp32 reference (incl. ragged lengths)."""
     import torch
     from megatronapp_b200 import ops
 
-    res = {"native_available": ops.native_attention_available()}
-    if not res["native_available"]:
-        return res
-    for (b, h, hk, s, d, causal) in [(1, 2, 2, 256, 128, True), (2, 4, 4, 512, 128, True), (2, 4, 2, 384, 64, True),
-                                     (1, 2, 2, 256, 128, False), (1, 8, 8, 2048, 128, True)]:
-        torch.manual_seed(s)
-        q = torch.randn(b, h, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
-        k = torch.randn(b, hk, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
-        v = torch.randn(b, hk, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    res = {}
+    cases = [(c, True) for c in _ATTN_CASES] + [((1, 2, 2, 200, 128, False), False), ((1, 2, 2, 320, 64, True), False),
+                                               ((1, 1, 1, 128, 128, True), False)]
+    for (b, h, hk, s, d, causal), sbhd in cases:
+        q, k, v = _attn_inputs(b, h, hk, s, d, sbhd)
+        tag = f"attn_b{b}h{h}kv{hk}s{s}d{d}c{int(causal)}"
+        try:
+            o, lse, _ = ops.ext().attn_fwd(q, k, v, 1.0 / d ** 0.5, causal, False)
+            torch.cuda.synchronize()
+            orf = ops.attention_ref(q.float(), k.float(), v.float(), None, causal)
+            kk = k.float().repeat_interleave(h // hk, dim=1)
+            sc = torch.matmul(q.float(), kk.transpose(-1, -2)) / d ** 0.5
+            if causal:
+                sc = sc.masked_fill(~torch.ones(s, s, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+            res[tag + "_fwd"] = _rel_err(o, orf)
+            res[tag + "_lse"] = _rel_err(lse, torch.logsumexp(sc, dim=-1))
+        except Exception as e:  # noqa: BLE001
+            res[tag] = f"EXC {type(e).__name__}: {str(e)[:200]}"
+    return res
+
+
+def check_attention():
+    """Forward + backward (dq, dk, dv) of the native kernels through autograd."""
+    import torch
+    from megatronapp_b200 import ops
+
+    res = {}
+    for (b, h, hk, s, d, causal) in _ATTN_CASES:
+        q, k, v = (t.detach().requires_grad_(True) for t in _attn_inputs(b, h, hk, s, d, True))
         tag = f"attn_b{b}h{h}kv{hk}s{s}d{d}c{int(causal)}"
         try:
             o = ops._AttnFn.apply(q, k, v, 1.0 / d ** 0.5, causal)
             do = torch.randn_like(o)
             o.backward(do)
+            torch.cuda.synchronize()
             qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
             orf = ops.attention_ref(qf, kf, vf, None, causal)
             orf.backward(do.float())
@@ -315,9 +354,11 @@ def check_attention_perf():
     from megatronapp_b200 import ops
     import torch.nn.functional as F
 
-    res = {"native_available": ops.native_attention_available()}
+    res = {}
     b, h, s, d = 1, 32, 2048, 128
-    q, k, v = (torch.randn(b, h, s, d, device="cuda", dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
+    # [s, b, h, d] storage viewed as [b, h, s, d]: what the transformer layer passes
+    q, k, v = (torch.randn(s, b, h, d, device="cuda", dtype=torch.bfloat16).permute(1, 2, 0, 3).requires_grad_(True)
+               for _ in range(3))
     fl_f = 4.0 * b * h * s * s * d / 2
     t = _time(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=True))
     res["sdpa_fwd_tflops"] = round(fl_f / t / 1e9, 1)
@@ -325,12 +366,19 @@ def check_attention_perf():
     do = torch.randn_like(o)
     t = _time(lambda: torch.autograd.grad(o, (q, k, v), do, retain_graph=True))
     res["sdpa_bwd_tflops"] = round(2.5 * fl_f / t / 1e9, 1)
-    if res["native_available"]:
-        t = _time(lambda: ops.ext().attn_fwd(q, k, v, 1.0 / d ** 0.5, True, False))
-        res["b200_fwd_tflops"] = round(fl_f / t / 1e9, 1)
-        o2, lse, _ = ops.ext().attn_fwd(q, k, v, 1.0 / d ** 0.5, True, False)
-        t = _time(lambda: ops.ext().attn_bwd(do, q, k, v, o2, lse, 1.0 / d ** 0.5, True))
-        res["b200_bwd_tflops"] = round(2.5 * fl_f / t / 1e9, 1)
+    qd, kd, vd = q.detach(), k.detach(), v.detach()
+    t = _time(lambda: ops.ext().attn_fwd(qd, kd, vd, 1.0 / d ** 0.5, True, False))
+    res["b200_fwd_ms"], res["b200_fwd_tflops"] = round(t, 4), round(fl_f / t / 1e9, 1)
+    o2, lse, _ = ops.ext().attn_fwd(qd, kd, vd, 1.0 / d ** 0.5, True, False)
+    t = _time(lambda: ops.ext().attn_bwd(do, qd, kd, vd, o2, lse, 1.0 / d ** 0.5, True))
+    res["b200_bwd_ms"], res["b200_bwd_tflops"] = round(t, 4), round(2.5 * fl_f / t / 1e9, 1)
+    for (bb, hh) in [(4, 32), (4, 8)]:
+        q4, k4, v4 = (torch.randn(s, bb, hh, d, device="cuda", dtype=torch.bfloat16).permute(1, 2, 0, 3) for _ in range(3))
+        fl = 4.0 * bb * hh * s * s * d / 2
+        t = _time(lambda: ops.ext().attn_fwd(q4, k4, v4, 1.0 / d ** 0.5, True, False))
+        res[f"b200_fwd_tflops_b{bb}h{hh}"] = round(fl / t / 1e9, 1)
+        t = _time(lambda: F.scaled_dot_product_attention(q4, k4, v4, is_causal=True))
+        res[f"sdpa_fwd_tflops_b{bb}h{hh}"] = round(fl / t / 1e9, 1)
     return res
 
 
@@ -372,6 +420,7 @@ CHECKS = {
     "gemm_tt_accum": lambda: check_gemm("tt_accum"),
     "gemm_nt_fp16": lambda: check_gemm("nt", [(256, 256, 128), (2048, 4096, 4096)], "fp16"),
     "elementwise": check_elementwise,
+    "attention_fwd": check_attention_fwd,
     "attention": check_attention,
     "model_parity": check_model_parity,
     "smoke": check_smoke,
