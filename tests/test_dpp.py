@@ -53,3 +53,23 @@ def test_pick_task_policies():
     assert pick_task(rf, rb, "dfc", 0, 10) == Task("B", 0, 0)
     assert pick_task(rf, rb, "auto", 10, 10) == Task("B", 0, 0)
     assert pick_task([], [], "auto", 0, 1) is None
+
+
+def test_dpp_profiling_metrics():
+    """Trace post-processing (profiling toolkit): iteration time, reduce window, ratios."""
+    from megatronapp_b200.dpp.profiling import analyze
+
+    ev = []
+    for pid in (0, 1):
+        for it in range(3):
+            t0 = it * 1000.0
+            ev.append({"name": "iteration", "ph": "X", "ts": t0, "dur": 900.0, "pid": pid, "args": {"iteration": it}})
+            ev.append({"name": "forward", "ph": "X", "ts": t0 + 10, "dur": 300.0, "pid": pid, "args": {}})
+            ev.append({"name": "backward", "ph": "X", "ts": t0 + 400, "dur": 300.0, "pid": pid, "args": {}})
+            ev.append({"name": "send_forward", "ph": "X", "ts": t0 + 320, "dur": 45.0, "pid": pid, "args": {}})
+            ev.append({"name": "reduce", "ph": "i", "ts": t0 + 700 + 50 * pid, "pid": pid, "args": {}})
+    r = analyze(ev, skip_first=1)
+    assert abs(r["iteration_ms"] - 0.9) < 1e-9
+    assert abs(r["ranks"][0]["reduce_window_ms"] - 0.2) < 1e-9 and abs(r["ranks"][1]["reduce_window_ms"] - 0.15) < 1e-9
+    assert abs(r["ranks"][0]["computing_ratio"] - 600.0 / 900.0) < 1e-9
+    assert abs(r["ranks"][0]["sending_ratio"] - 0.05) < 1e-9
