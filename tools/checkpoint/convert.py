@@ -1,0 +1,334 @@
+"""Checkpoint format / parallelism converter.
+
+    python tools/checkpoint/convert.py --loader core --saver core --load-dir A --save-dir B \
+        --target-tensor-parallel-size 4 --target-pipeline-parallel-size 2
+    python tools/checkpoint/convert.py --loader hf_llama --saver core --load-dir <hf dir> --save-dir B ...
+    python tools/checkpoint/convert.py --loader core --saver hf_llama --load-dir A --save-dir <hf dir>
+
+Parity: reference ``tools/checkpoint/convert.py`` + ``loader_{mcore,llama_mistral,...}.py`` /
+``saver_{mcore,...}.py`` (plugin pairs exchanging a canonical, unsharded description of the
+model) and ``test_scripts/gpt2_convert.py`` (HF GPT-2 -> Megatron).  Here the interchange object is
+a plain dict ``{"config": {...}, "weights": {canonical name: full tensor}}`` using this
+framework's parameter names with global layer indices; loaders merge TP/PP shards into it and
+savers re-shard it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import sys
+from types import SimpleNamespace
+from typing import Dict
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+COLUMN = ("linear_qkv.weight", "linear_qkv.bias", "linear_fc1.weight", "linear_fc1.bias", "word_embeddings.weight",
+          "output_layer.weight", "linear_q.weight", "linear_kv.weight")
+ROW = ("linear_proj.weight", "linear_fc2.weight")
+
+
+def _kind(name: str) -> str:
+    if name.endswith(COLUMN):
+        return "col"
+    if name.endswith(ROW):
+        return "row"
+    return "rep"
+
+
+# ------------------------------------------------------------------------------- TP split / merge
+def split_tp(name: str, w: torch.Tensor, tp: int, glu: bool):
+    k = _kind(name)
+    if tp == 1 or k == "rep":
+        return [w.clone() for _ in range(tp)]
+    if k == "row":
+        return [c.contiguous() for c in torch.chunk(w, tp, dim=1)]
+    if glu and "linear_fc1" in name:
+        gate, up = torch.chunk(w, 2, dim=0)
+        return [torch.cat([g, u], dim=0).contiguous() for g, u in zip(torch.chunk(gate, tp, 0), torch.chunk(up, tp, 0))]
+    return [c.contiguous() for c in torch.chunk(w, tp, dim=0)]
+
+
+def merge_tp(name: str, shards, glu: bool):
+    k = _kind(name)
+    if len(shards) == 1 or k == "rep":
+        return shards[0]
+    if k == "row":
+        return torch.cat(shards, dim=1)
+    if glu and "linear_fc1" in name:
+        gates, ups = zip(*(torch.chunk(s, 2, dim=0) for s in shards))
+        return torch.cat(list(gates) + list(ups), dim=0)
+    return torch.cat(shards, dim=0)
+
+
+_LAYER = re.compile(r"^(.*decoder\.layers\.)(\d+)(\..*)$")
+
+
+def layers_per_stage(num_layers: int, pp: int):
+    assert num_layers % pp == 0, "num_layers must divide by the pipeline size"
+    return num_layers // pp
+
+
+# ------------------------------------------------------------------------------------- core format
+def load_core(load_dir: str, iteration=None) -> Dict:
+    from megatronapp_b200.training import checkpointing as ck
+
+    if iteration is None:
+        with open(ck.get_checkpoint_tracker_filename(load_dir)) as f:
+            txt = f.read().strip()
+        iteration = 0 if txt == "release" else int(txt)
+    base = ck.get_checkpoint_name(load_dir, iteration, release=(iteration == 0), return_base_dir=True)
+    dirs = sorted(d for d in os.listdir(base) if d.startswith("mp_rank_"))
+    tp = 1 + max(int(d.split("_")[2]) for d in dirs)
+    pp = 1 + max((int(d.split("_")[3]) for d in dirs if len(d.split("_")) > 3), default=0)
+    shards = {}
+    args = None
+    for d in dirs:
+        parts = d.split("_")
+        t, p = int(parts[2]), (int(parts[3]) if len(parts) > 3 else 0)
+        sd = torch.load(os.path.join(base, d, "model_optim_rng.pt"), map_location="cpu", weights_only=False)
+        shards[(t, p)] = sd["model"]
+        args = args or sd.get("args")
+    cfg = _config_from_args(args)
+    glu = cfg["gated_linear_unit"]
+    lps = layers_per_stage(cfg["num_layers"], pp)
+    weights = {}
+    for p in range(pp):
+        for name in shards[(0, p)]:
+            if name.endswith("_extra_state"):
+                continue
+            full = merge_tp(name, [shards[(t, p)][name] for t in range(tp)], glu)
+            m = _LAYER.match(name)
+            gname = f"{m.group(1)}{int(m.group(2)) + p * lps}{m.group(3)}" if m else name
+            if gname in weights:      # tied embedding copy on the last stage
+                continue
+            weights[gname] = full
+    return {"config": cfg, "weights": weights, "iteration": iteration, "args": args}
+
+
+def _config_from_args(args) -> Dict:
+    g = lambda k, d=None: getattr(args, k, d)
+    return {"num_layers": g("num_layers"), "hidden_size": g("hidden_size"), "num_attention_heads": g("num_attention_heads"),
+            "num_query_groups": g("num_query_groups") or g("num_attention_heads"), "ffn_hidden_size": g("ffn_hidden_size"),
+            "kv_channels": g("kv_channels") or g("hidden_size") // g("num_attention_heads"),
+            "gated_linear_unit": bool(g("swiglu", False)), "normalization": g("normalization", "LayerNorm"),
+            "add_bias_linear": not g("disable_bias_linear", False), "padded_vocab_size": g("padded_vocab_size"),
+            "max_position_embeddings": g("max_position_embeddings"), "position_embedding_type": g("position_embedding_type", "learned_absolute"),
+            "untie_embeddings_and_output_weights": bool(g("untie_embeddings_and_output_weights", False)),
+            "rotary_base": g("rotary_base", 10000), "layernorm_epsilon": g("norm_epsilon", g("layernorm_epsilon", 1e-5))}
+
+
+def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int):
+    from megatronapp_b200.training import checkpointing as ck
+
+    cfg, weights = ckpt["config"], ckpt["weights"]
+    glu = cfg["gated_linear_unit"]
+    lps = layers_per_stage(cfg["num_layers"], pp)
+    it = ckpt.get("iteration", 0)
+    args = ckpt.get("args") or SimpleNamespace()
+    args = SimpleNamespace(**{**vars(args), **_args_from_config(cfg), "tensor_model_parallel_size": tp,
+                              "pipeline_model_parallel_size": pp})
+    vocab = weights["embedding.word_embeddings.weight"].shape[0]
+    assert vocab % tp == 0, f"vocab {vocab} must divide by target TP {tp} (re-pad first)"
+    for p in range(pp):
+        stage = {}
+        for name, w in weights.items():
+            m = _LAYER.match(name)
+            if m:
+                li = int(m.group(2))
+                if li // lps != p:
+                    continue
+                lname = f"{m.group(1)}{li - p * lps}{m.group(3)}"
+            elif name.startswith("embedding."):
+                if p != 0:
+                    continue
+                lname = name
+            else:      # final norm / output layer live on the last stage
+                if p != pp - 1:
+                    continue
+                lname = name
+            stage[lname] = split_tp(name, w, tp, glu)
+        for t in range(tp):
+            path = ck.get_checkpoint_name(save_dir, it, release=(it == 0), pipeline_parallel=pp > 1, tensor_rank=t,
+                                          pipeline_rank=p, expert_parallel=False, expert_rank=0)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            torch.save({"model": {k: v[t] for k, v in stage.items()}, "args": args, "iteration": it,
+                        "checkpoint_version": 3.0}, path)
+    with open(ck.get_checkpoint_tracker_filename(save_dir), "w") as f:
+        f.write(str(it) if it else "release")
+
+
+def _args_from_config(cfg):
+    return {"num_layers": cfg["num_layers"], "hidden_size": cfg["hidden_size"], "num_attention_heads": cfg["num_attention_heads"],
+            "num_query_groups": cfg["num_query_groups"], "group_query_attention": cfg["num_query_groups"] != cfg["num_attention_heads"],
+            "ffn_hidden_size": cfg["ffn_hidden_size"], "kv_channels": cfg["kv_channels"], "swiglu": cfg["gated_linear_unit"],
+            "normalization": cfg["normalization"], "disable_bias_linear": not cfg["add_bias_linear"],
+            "padded_vocab_size": cfg["padded_vocab_size"], "max_position_embeddings": cfg["max_position_embeddings"],
+            "position_embedding_type": cfg["position_embedding_type"],
+            "untie_embeddings_and_output_weights": cfg["untie_embeddings_and_output_weights"],
+            "rotary_base": cfg["rotary_base"], "norm_epsilon": cfg["layernorm_epsilon"]}
+
+
+# ------------------------------------------------------------------------------------ HF: Llama
+def _hf_state(load_dir):
+    sd = {}
+    files = sorted(f for f in os.listdir(load_dir) if f.endswith((".safetensors", ".bin", ".pt")))
+    for f in files:
+        p = os.path.join(load_dir, f)
+        if f.endswith(".safetensors"):
+            from safetensors.torch import load_file
+
+            sd.update(load_file(p))
+        else:
+            sd.update(torch.load(p, map_location="cpu", weights_only=True))
+    return sd
+
+
+def qkv_from_separate(q, k, v, nh, ng, hn):
+    """[nh*hn, h], [ng*hn, h] x2 -> Megatron's per-group interleaved [ng * (nh/ng + 2) * hn, h]."""
+    qpg = nh // ng
+    q = q.view(ng, qpg * hn, -1)
+    k = k.view(ng, hn, -1)
+    v = v.view(ng, hn, -1)
+    return torch.cat([q, k, v], dim=1).reshape(ng * (qpg + 2) * hn, -1)
+
+
+def qkv_to_separate(w, nh, ng, hn):
+    qpg = nh // ng
+    w = w.view(ng, (qpg + 2) * hn, -1)
+    q, k, v = torch.split(w, [qpg * hn, hn, hn], dim=1)
+    return q.reshape(nh * hn, -1), k.reshape(ng * hn, -1), v.reshape(ng * hn, -1)
+
+
+def load_hf_llama(load_dir: str) -> Dict:
+    hc = json.load(open(os.path.join(load_dir, "config.json")))
+    sd = _hf_state(load_dir)
+    nh, ng = hc["num_attention_heads"], hc.get("num_key_value_heads", hc["num_attention_heads"])
+    h, L = hc["hidden_size"], hc["num_hidden_layers"]
+    hn = hc.get("head_dim") or h // nh
+    w = {"embedding.word_embeddings.weight": sd["model.embed_tokens.weight"],
+         "decoder.final_layernorm.weight": sd["model.norm.weight"]}
+    tied = hc.get("tie_word_embeddings", False) or "lm_head.weight" not in sd
+    if not tied:
+        w["output_layer.weight"] = sd["lm_head.weight"]
+    for i in range(L):
+        a, b = f"model.layers.{i}.", f"decoder.layers.{i}."
+        w[b + "input_layernorm.weight"] = sd[a + "input_layernorm.weight"]
+        w[b + "self_attention.linear_qkv.weight"] = qkv_from_separate(
+            sd[a + "self_attn.q_proj.weight"], sd[a + "self_attn.k_proj.weight"], sd[a + "self_attn.v_proj.weight"], nh, ng, hn)
+        w[b + "self_attention.linear_proj.weight"] = sd[a + "self_attn.o_proj.weight"]
+        w[b + "pre_mlp_layernorm.weight"] = sd[a + "post_attention_layernorm.weight"]
+        w[b + "mlp.linear_fc1.weight"] = torch.cat([sd[a + "mlp.gate_proj.weight"], sd[a + "mlp.up_proj.weight"]], dim=0)
+        w[b + "mlp.linear_fc2.weight"] = sd[a + "mlp.down_proj.weight"]
+    cfg = {"num_layers": L, "hidden_size": h, "num_attention_heads": nh, "num_query_groups": ng,
+           "ffn_hidden_size": hc["intermediate_size"], "kv_channels": hn, "gated_linear_unit": True,
+           "normalization": "RMSNorm", "add_bias_linear": False, "padded_vocab_size": hc["vocab_size"],
+           "max_position_embeddings": hc.get("max_position_embeddings", 4096), "position_embedding_type": "rope",
+           "untie_embeddings_and_output_weights": not tied, "rotary_base": hc.get("rope_theta", 10000.0),
+           "layernorm_epsilon": hc.get("rms_norm_eps", 1e-5)}
+    return {"config": cfg, "weights": w, "iteration": 0}
+
+
+def save_hf_llama(ckpt: Dict, save_dir: str):
+    cfg, w = ckpt["config"], ckpt["weights"]
+    nh, ng, hn = cfg["num_attention_heads"], cfg["num_query_groups"], cfg["kv_channels"]
+    sd = {"model.embed_tokens.weight": w["embedding.word_embeddings.weight"], "model.norm.weight": w["decoder.final_layernorm.weight"]}
+    if "output_layer.weight" in w:
+        sd["lm_head.weight"] = w["output_layer.weight"]
+    for i in range(cfg["num_layers"]):
+        a, b = f"model.layers.{i}.", f"decoder.layers.{i}."
+        q, k, v = qkv_to_separate(w[b + "self_attention.linear_qkv.weight"], nh, ng, hn)
+        sd[a + "self_attn.q_proj.weight"], sd[a + "self_attn.k_proj.weight"], sd[a + "self_attn.v_proj.weight"] = q, k, v
+        sd[a + "self_attn.o_proj.weight"] = w[b + "self_attention.linear_proj.weight"]
+        sd[a + "input_layernorm.weight"] = w[b + "input_layernorm.weight"]
+        sd[a + "post_attention_layernorm.weight"] = w[b + "pre_mlp_layernorm.weight"]
+        gate, up = torch.chunk(w[b + "mlp.linear_fc1.weight"], 2, dim=0)
+        sd[a + "mlp.gate_proj.weight"], sd[a + "mlp.up_proj.weight"] = gate, up
+        sd[a + "mlp.down_proj.weight"] = w[b + "mlp.linear_fc2.weight"]
+    os.makedirs(save_dir, exist_ok=True)
+    torch.save({k: v.contiguous() for k, v in sd.items()}, os.path.join(save_dir, "pytorch_model.bin"))
+    json.dump({"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": cfg["hidden_size"],
+               "num_hidden_layers": cfg["num_layers"], "num_attention_heads": nh, "num_key_value_heads": ng,
+               "intermediate_size": cfg["ffn_hidden_size"], "vocab_size": cfg["padded_vocab_size"], "head_dim": hn,
+               "max_position_embeddings": cfg["max_position_embeddings"], "rope_theta": cfg["rotary_base"],
+               "rms_norm_eps": cfg["layernorm_epsilon"], "tie_word_embeddings": "output_layer.weight" not in w,
+               "hidden_act": "silu", "torch_dtype": "bfloat16"}, open(os.path.join(save_dir, "config.json"), "w"), indent=1)
+
+
+# ------------------------------------------------------------------------------------ HF: GPT-2
+def load_hf_gpt2(load_dir: str) -> Dict:
+    """HF GPT-2 (Conv1D weights are [in, out]; fused c_attn is [q | k | v] by columns)."""
+    hc = json.load(open(os.path.join(load_dir, "config.json")))
+    sd = {k.removeprefix("transformer."): v for k, v in _hf_state(load_dir).items()}
+    h, L, nh = hc["n_embd"], hc["n_layer"], hc["n_head"]
+    hn = h // nh
+    w = {"embedding.word_embeddings.weight": sd["wte.weight"], "embedding.position_embeddings.weight": sd["wpe.weight"],
+         "decoder.final_layernorm.weight": sd["ln_f.weight"], "decoder.final_layernorm.bias": sd["ln_f.bias"]}
+    for i in range(L):
+        a, b = f"h.{i}.", f"decoder.layers.{i}."
+        for hf, mg in (("ln_1", "input_layernorm"), ("ln_2", "pre_mlp_layernorm")):
+            w[b + mg + ".weight"], w[b + mg + ".bias"] = sd[a + hf + ".weight"], sd[a + hf + ".bias"]
+        cw, cb = sd[a + "attn.c_attn.weight"].t(), sd[a + "attn.c_attn.bias"]     # [3h, h]
+        q, k, v = torch.chunk(cw, 3, dim=0)
+        w[b + "self_attention.linear_qkv.weight"] = qkv_from_separate(q, k, v, nh, nh, hn)
+        qb, kb, vb = torch.chunk(cb, 3, dim=0)
+        w[b + "self_attention.linear_qkv.bias"] = qkv_from_separate(qb.unsqueeze(1), kb.unsqueeze(1), vb.unsqueeze(1), nh, nh, hn).squeeze(1)
+        w[b + "self_attention.linear_proj.weight"] = sd[a + "attn.c_proj.weight"].t().contiguous()
+        w[b + "self_attention.linear_proj.bias"] = sd[a + "attn.c_proj.bias"]
+        w[b + "mlp.linear_fc1.weight"] = sd[a + "mlp.c_fc.weight"].t().contiguous()
+        w[b + "mlp.linear_fc1.bias"] = sd[a + "mlp.c_fc.bias"]
+        w[b + "mlp.linear_fc2.weight"] = sd[a + "mlp.c_proj.weight"].t().contiguous()
+        w[b + "mlp.linear_fc2.bias"] = sd[a + "mlp.c_proj.bias"]
+    cfg = {"num_layers": L, "hidden_size": h, "num_attention_heads": nh, "num_query_groups": nh, "ffn_hidden_size": 4 * h,
+           "kv_channels": hn, "gated_linear_unit": False, "normalization": "LayerNorm", "add_bias_linear": True,
+           "padded_vocab_size": hc["vocab_size"], "max_position_embeddings": hc["n_positions"],
+           "position_embedding_type": "learned_absolute", "untie_embeddings_and_output_weights": False,
+           "rotary_base": 10000, "layernorm_epsilon": hc.get("layer_norm_epsilon", 1e-5)}
+    return {"config": cfg, "weights": w, "iteration": 0}
+
+
+def pad_vocab(ckpt: Dict, multiple: int):
+    """Zero-pad the vocabulary dimension so it divides by ``multiple`` (TP x 128 by default)."""
+    for k in ("embedding.word_embeddings.weight", "output_layer.weight"):
+        if k in ckpt["weights"]:
+            w = ckpt["weights"][k]
+            v = (w.shape[0] + multiple - 1) // multiple * multiple
+            if v != w.shape[0]:
+                ckpt["weights"][k] = torch.cat([w, w.new_zeros(v - w.shape[0], w.shape[1])], dim=0)
+                ckpt["config"]["padded_vocab_size"] = v
+
+
+LOADERS = {"core": load_core, "hf_llama": load_hf_llama, "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2}
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="checkpoint converter")
+    ap.add_argument("--model-type", default="GPT", choices=["GPT"])
+    ap.add_argument("--loader", default="core", choices=list(LOADERS))
+    ap.add_argument("--saver", default="core", choices=["core", "hf_llama"])
+    ap.add_argument("--load-dir", required=True)
+    ap.add_argument("--save-dir", required=True)
+    ap.add_argument("--target-tensor-parallel-size", type=int, default=1)
+    ap.add_argument("--target-pipeline-parallel-size", type=int, default=1)
+    ap.add_argument("--make-vocab-size-divisible-by", type=int, default=128)
+    ap.add_argument("--dtype", default=None, choices=[None, "bf16", "fp16", "fp32"])
+    a = ap.parse_args(argv)
+    ckpt = LOADERS[a.loader](a.load_dir)
+    if a.dtype:
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
+        ckpt["weights"] = {k: v.to(dt) for k, v in ckpt["weights"].items()}
+    if a.saver == "core":
+        pad_vocab(ckpt, a.make_vocab_size_divisible_by * a.target_tensor_parallel_size)
+        save_core(ckpt, a.save_dir, a.target_tensor_parallel_size, a.target_pipeline_parallel_size)
+    else:
+        save_hf_llama(ckpt, a.save_dir)
+    print(f"converted {a.loader} -> {a.saver}: {len(ckpt['weights'])} tensors, "
+          f"tp={a.target_tensor_parallel_size} pp={a.target_pipeline_parallel_size} -> {a.save_dir}")
+
+
+if __name__ == "__main__":
+    main()
