@@ -72,6 +72,10 @@ class GPTModel(LanguageModule):
         if self.position_embedding_type == "rope" and not self.config.multi_latent_attention:
             s = self.rotary_pos_emb.get_rotary_seq_len(inference_context, self.decoder, decoder_input, self.config)
             rotary = self.rotary_pos_emb(s)
+            if self.config.context_parallel_size > 1:
+                from ...parallel.context_parallel import get_pos_emb_on_this_cp_rank
+
+                rotary = get_pos_emb_on_this_cp_rank(rotary, 0)
         with _scope("decoder"):
             hidden = self.decoder(hidden_states=decoder_input, attention_mask=attention_mask,
                                   inference_context=inference_context, rotary_pos_emb=rotary,

@@ -64,6 +64,18 @@ class DotProductAttention(MegatronModule):
             # the extra 1/layer_number coefficient cancels inside the fp32 softmax
             pass
         self.dropout_p = config.attention_dropout if attention_dropout is None else attention_dropout
+        cct = cp_comm_type if cp_comm_type is not None else config.cp_comm_type
+        if isinstance(cct, (list, tuple)):
+            cct = cct[self.layer_number - 1]
+        self.cp_comm_type = cct or "p2p"
+        self.cp_size = config.context_parallel_size
+
+    def _attend(self, q, k, v, causal, dropout_p, mask):
+        if self.cp_size > 1 and self.attention_type == "self":
+            from ..parallel.context_parallel import cp_attention
+
+            return cp_attention(q, k, v, self.softmax_scale, causal, self.cp_comm_type, dropout_p, self.training)
+        return ops.attention(q, k, v, self.softmax_scale, causal, dropout_p, self.training, mask)
 
     def forward(self, query, key, value, attention_mask=None, attn_mask_type=None, attention_bias=None,
                 packed_seq_params=None):
@@ -84,9 +96,9 @@ class DotProductAttention(MegatronModule):
             if self.dropout_p > 0.0 and self.training:
                 with get_cuda_rng_tracker().fork() if "model-parallel-rng" in get_cuda_rng_tracker().states_ \
                         else torch.random.fork_rng(devices=[]):
-                    o = ops.attention(q, k, v, self.softmax_scale, causal, self.dropout_p, self.training, mask)
+                    o = self._attend(q, k, v, causal, self.dropout_p, mask)
             else:
-                o = ops.attention(q, k, v, self.softmax_scale, causal, 0.0, self.training, mask)
+                o = self._attend(q, k, v, causal, 0.0, mask)
         ctx = o.permute(2, 0, 1, 3).reshape(sq, b, self.np * self.hn)
         scope_hooks.tik_tensor(3, self.layer_number, ctx)
         return ctx

@@ -46,6 +46,10 @@ def get_batch(data_iterator):
     if (not mpu.is_pipeline_first_stage()) and (not mpu.is_pipeline_last_stage()):
         return None, None, None, None, None
     b = get_batch_on_this_tp_rank(data_iterator, args)
+    if args.context_parallel_size > 1:
+        from megatronapp_b200.parallel.context_parallel import get_batch_on_this_cp_rank
+
+        b = get_batch_on_this_cp_rank(b)
     return b["tokens"], b["labels"], b["loss_mask"], b["attention_mask"], b["position_ids"]
 
 

@@ -153,6 +153,29 @@ def moe_parity(ep=1, dispatcher="alltoall", grouped=False):
     return {"out": out.detach().flatten().tolist(), "gx": x.grad.flatten().tolist(), "seed_rank": rank}
 
 
+def cp_attention_parity(comm="a2a", causal=True):
+    """Context-parallel attention (cp = world) vs. full-sequence attention on one rank."""
+    from megatronapp_b200 import ops
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.context_parallel import cp_attention, slice_for_cp_rank
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(1, 1, context_parallel_size=world)
+    torch.manual_seed(0)
+    b, h, s, d = 2, 4, 32, 16
+    q, k, v = (torch.randn(b, h, s, d, dtype=torch.float64) for _ in range(3))
+    do = torch.randn(b, h, s, d, dtype=torch.float64)
+    qf, kf, vf = (t.clone().requires_grad_(True) for t in (q, k, v))
+    of = ops.attention_ref(qf, kf, vf, None, causal)
+    of.backward(do)
+    ql, kl, vl = (slice_for_cp_rank(t, 2).clone().requires_grad_(True) for t in (q, k, v))
+    ol = cp_attention(ql, kl, vl, 1.0 / d ** 0.5, causal, comm, 0.0, True,
+                      attn_fn=lambda q_, k_, v_, sc, ca, p, tr, m: ops.attention_ref(q_, k_, v_, sc, ca, 0.0, mask=m))
+    ol.backward(slice_for_cp_rank(do, 2))
+    err = lambda a, full: float((a - slice_for_cp_rank(full, 2)).abs().max())
+    return {"fwd": err(ol, of.detach()), "dq": err(ql.grad, qf.grad), "dk": err(kl.grad, kf.grad), "dv": err(vl.grad, vf.grad)}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":

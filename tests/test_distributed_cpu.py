@@ -82,3 +82,9 @@ def test_fbd_matches_plain_pipeline():
     base = _last_stage_losses(run_distributed("train_parity", 2, pp=2))
     res = run_distributed("train_parity", 4, pp=2, fbd=True)
     _close(_last_stage_losses(res), base, 1e-5)
+
+
+@pytest.mark.parametrize("comm", ["a2a", "all_gather", "p2p"])
+def test_context_parallel_attention(comm):
+    for r in run_distributed("cp_attention_parity", 2, comm=comm):
+        assert max(r["fwd"], r["dq"], r["dk"], r["dv"]) < 1e-5, r   # reference attention runs in fp32
