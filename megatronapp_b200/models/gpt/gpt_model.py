@@ -54,6 +54,16 @@ class GPTModel(LanguageModule):
                 config.hidden_size, vocab_size, config=config, init_method=config.init_method, bias=False,
                 skip_bias_add=False, gather_output=not parallel_output,
                 skip_weight_param_allocation=pre_process and share_embeddings_and_output_weights)
+        self.mtp = None
+        if post_process and (mtp_block_spec is not None or config.mtp_num_layers):
+            from ...transformer.multi_token_prediction import MultiTokenPredictionBlock, get_mtp_block_spec
+
+            spec = mtp_block_spec or get_mtp_block_spec(config, transformer_layer_spec if isinstance(
+                transformer_layer_spec, ModuleSpec) else transformer_layer_spec.layer_specs[-1])
+            self.mtp = MultiTokenPredictionBlock(config, spec)
+            if not pre_process:   # the last stage needs its own embedding to feed the MTP depths
+                self.embedding = LanguageModelEmbedding(config, vocab_size, max_sequence_length, position_embedding_type,
+                                                        scatter_to_sequence_parallel=scatter_embedding_sequence_parallel)
         if pre_process or post_process:
             self.setup_embeddings_and_output_layer()
 
@@ -83,6 +93,11 @@ class GPTModel(LanguageModule):
         if not self.post_process:
             return hidden
         w = self.shared_embedding_or_output_weight() if self.share_embeddings_and_output_weights else None
+        if self.mtp is not None and labels is not None and self.training:
+            hidden = self.mtp(input_ids=input_ids, position_ids=position_ids, hidden_states=hidden,
+                              attention_mask=attention_mask, labels=labels, loss_mask=loss_mask, rotary_pos_emb=rotary,
+                              embedding=self.embedding, output_layer=self.output_layer, output_weight=w,
+                              compute_loss=self.compute_language_model_loss)
         logits, _ = self.output_layer(hidden, weight=w, runtime_gather_output=runtime_gather_output)
         if labels is None:
             return logits.transpose(0, 1).contiguous()  # [s, b, V] -> [b, s, V]

@@ -103,3 +103,59 @@ def test_hybrid_mamba_model_and_allocation():
     pos = torch.arange(16).unsqueeze(0).expand(2, -1)
     ls = _train(m, lambda: m(ids, pos, labels=ids).mean(), steps=6)
     assert ls[-1] < ls[0]
+
+
+def test_gpt_multi_token_prediction():
+    """MTP heads add an auxiliary loss whose gradient reaches both the MTP layers and the trunk."""
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+    from megatronapp_b200.transformer.multi_token_prediction import MTPLossLoggingHelper
+
+    _init()
+    cfg = _cfg(mtp_num_layers=2, mtp_loss_scaling_factor=0.3, kernel_backend="torch")
+    m = GPTModel(cfg, get_gpt_layer_local_spec(), 64, 16, position_embedding_type="rope")
+    toks = torch.randint(0, 64, (2, 16))
+    pos = torch.arange(16).unsqueeze(0).expand(2, -1)
+    labels = torch.roll(toks, -1, 1)
+    m.train()
+    loss = m(toks, pos, None, labels=labels).mean()
+    loss.backward()
+    g = [p.grad for n, p in m.named_parameters() if n.startswith("mtp.")]
+    assert g and all(x is not None and torch.isfinite(x).all() for x in g) and any(float(x.abs().sum()) > 0 for x in g)
+    assert float(MTPLossLoggingHelper.tracker["values"].sum()) > 0
+    # trunk gradient differs from the no-MTP gradient (aux loss flows into the decoder)
+    g_with = m.decoder.layers[0].mlp.linear_fc1.weight.grad.clone()
+    m.zero_grad()
+    m.eval()
+    m(toks, pos, None, labels=labels).mean().backward()
+    assert not torch.allclose(g_with, m.decoder.layers[0].mlp.linear_fc1.weight.grad)
+
+
+def test_gpt_multi_latent_attention():
+    """MLA GPT trains, and incremental decoding through the MLA KV cache matches a full forward."""
+    from megatronapp_b200.config.transformer_config import MLATransformerConfig
+    from megatronapp_b200.inference.core import StaticInferenceContext as InferenceContext
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+
+    _init()
+    cfg = MLATransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                               hidden_dropout=0.0, attention_dropout=0.0, q_lora_rank=16, kv_lora_rank=16,
+                               qk_head_dim=8, qk_pos_emb_head_dim=4, v_head_dim=8, max_position_embeddings=32,
+                               rotary_scaling_factor=1.0, kernel_backend="torch")
+    m = GPTModel(cfg, get_gpt_layer_local_spec(multi_latent_attention=True, qk_layernorm=True), 64, 32,
+                 position_embedding_type="rope")
+    toks = torch.randint(0, 64, (2, 12))
+    pos = torch.arange(12).unsqueeze(0).expand(2, -1)
+    losses = _train(m, lambda: m(toks, pos, None, labels=torch.roll(toks, -1, 1)).mean(), steps=10, lr=1e-2)
+    assert losses[-1] < losses[0]
+    m.eval()
+    with torch.no_grad():
+        full = m(toks, pos, None)
+        ctx = InferenceContext(max_batch_size=2, max_sequence_length=32)
+        a = m(toks[:, :8], pos[:, :8], None, inference_context=ctx)
+        ctx.sequence_len_offset = 8
+        outs = [a]
+        for t in range(8, 12):
+            outs.append(m(toks[:, t:t + 1], pos[:, t:t + 1], None, inference_context=ctx))
+            ctx.sequence_len_offset += 1
+    inc = torch.cat(outs, dim=1)
+    assert torch.allclose(inc, full, atol=1e-4), float((inc - full).abs().max())
