@@ -114,8 +114,14 @@ def get_model(model_provider_func: Callable, model_type=None, wrap_with_ddp: boo
             bucket_size=args.ddp_bucket_size,
             average_in_collective=args.ddp_average_in_collective,
             fused_grad_reduce_scatter=args.fused_grad_reduce_scatter)
-        model = [DistributedDataParallel(config, ddp_config, m, disable_bucketing=(i > 0))
-                 for i, m in enumerate(model)]
+        if args.use_custom_fsdp or args.use_torch_fsdp2:
+            from ..parallel.fsdp import FullyShardedDataParallel, TorchFullyShardedDataParallel
+
+            cls = FullyShardedDataParallel if args.use_custom_fsdp else TorchFullyShardedDataParallel
+            model = [cls(config, ddp_config, m) for m in model]
+        else:
+            model = [DistributedDataParallel(config, ddp_config, m, disable_bucketing=(i > 0))
+                     for i, m in enumerate(model)]
         if args.data_parallel_random_init:
             for m in model:
                 m.broadcast_params()

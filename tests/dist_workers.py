@@ -176,6 +176,63 @@ def cp_attention_parity(comm="a2a", causal=True):
     return {"fwd": err(ol, of.detach()), "dq": err(ql.grad, qf.grad), "dk": err(kl.grad, kf.grad), "dv": err(vl.grad, vf.grad)}
 
 
+def fsdp_parity(steps=3):
+    """ZeRO-3 wrapper (dp = world) vs. the same model trained unsharded on the full batch."""
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.fsdp import FullyShardedDataParallel
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+
+    def build():
+        torch.manual_seed(0)
+        cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                                hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch")
+        return GPTModel(cfg, get_gpt_layer_local_spec(), 64, 16), cfg
+
+    torch.manual_seed(5)
+    toks = torch.randint(0, 64, (2 * world, 16))
+    pos = torch.arange(16).unsqueeze(0).expand(2 * world, -1)
+    lab = torch.roll(toks, -1, 1)
+    ref, _ = build()
+    init_sd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ref.state_dict().items()}
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    ref_losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        l = ref(toks, pos, None, labels=lab).mean()
+        l.backward()
+        opt.step()
+        ref_losses.append(float(l))
+    m, cfg = build()
+    m.load_state_dict(init_sd)
+    f = FullyShardedDataParallel(cfg, None, m)
+    sharded_numel = sum(u.shard_numel for u in f.units)
+    opt = torch.optim.Adam(f.shard_parameters(), lr=1e-2)
+    sl = slice(2 * rank, 2 * rank + 2)
+    losses = []
+    resident = []
+    for _ in range(steps):
+        f.zero_grad_buffer()
+        l = f(toks[sl], pos[sl], None, labels=lab[sl]).mean()
+        l.backward()
+        f.finish_grad_sync()
+        resident.append(sum(u.flat.untyped_storage().size() for u in f.units))
+        opt.step()
+        f.post_optimizer_step()
+        lt = l.detach().clone()
+        dist.all_reduce(lt)
+        losses.append(float(lt) / world)
+    full = f.state_dict()
+    err = max(float((full[k] - v).abs().max()) for k, v in ref.state_dict().items() if torch.is_tensor(v) and v.is_floating_point())
+    return {"ref": ref_losses, "losses": losses, "param_err": err, "resident_bytes_after_step": max(resident),
+            "shard_fraction": sharded_numel / sum(p.numel() for p in ref.parameters())}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":

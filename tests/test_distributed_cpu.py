@@ -88,3 +88,11 @@ def test_fbd_matches_plain_pipeline():
 def test_context_parallel_attention(comm):
     for r in run_distributed("cp_attention_parity", 2, comm=comm):
         assert max(r["fwd"], r["dq"], r["dk"], r["dv"]) < 1e-5, r   # reference attention runs in fp32
+
+
+def test_fsdp_zero3_matches_unsharded_training():
+    for r in run_distributed("fsdp_parity", 2):
+        _close(r["losses"], r["ref"], 2e-4)
+        assert r["param_err"] < 2e-4
+        assert r["resident_bytes_after_step"] == 0            # every unit is freed between steps
+        assert 0.5 <= r["shard_fraction"] < 0.56               # each rank owns ~1/2 of the parameters
