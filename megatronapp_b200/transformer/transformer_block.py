@@ -102,7 +102,18 @@ class TransformerBlock(MegatronModule):
             hidden_states = self._checkpointed_forward(hidden_states, attention_mask, context, context_mask,
                                                        rotary_pos_emb, packed_seq_params)
         else:
+            graphable = (self.config.enable_cuda_graph and inference_context is None and attention_mask is None
+                         and context is None and packed_seq_params is None and hidden_states.is_cuda)
+            if graphable and not hasattr(self.layers[0], "cuda_graph_manager"):
+                from .cuda_graphs import graph_transformer_block
+
+                graph_transformer_block(self, self.config.cuda_graph_warmup_steps)
             for layer in self.layers:
+                if graphable:
+                    extra = (rotary_pos_emb,) if torch.is_tensor(rotary_pos_emb) else ()
+                    hidden_states = layer.cuda_graph_manager(hidden_states, *extra)
+                    hidden_states = scope_hooks.perturb_system(hidden_states)
+                    continue
                 hidden_states, context = layer(
                     hidden_states, attention_mask=attention_mask, context=context, context_mask=context_mask,
                     rotary_pos_emb=rotary_pos_emb, attention_bias=attention_bias,

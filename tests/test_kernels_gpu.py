@@ -42,14 +42,56 @@ def test_elementwise_kernels():
     _assert_small(res, 3e-2)
 
 
-def test_attention_kernels():
+def test_attention_forward_kernel():
+    """tcgen05 flash-attention forward (strided [s,b,h,d] views, GQA, ragged lengths) vs fp32 reference."""
+    _assert_small(gc.check_attention_fwd(), 2e-2)
+
+
+def test_attention_backward_kernels():
+    """dQ / dK / dV of the native kernels through autograd vs the fp32 reference."""
+    _assert_small(gc.check_attention(), 3e-2)
+
+
+def test_attention_op_uses_native_kernel():
     from megatronapp_b200 import ops
 
-    if not ops.native_attention_available():
-        pytest.skip("native attention kernel not built in this revision")
-    res = gc.check_attention()
-    res.pop("native_available")
-    _assert_small(res, 3e-2)
+    assert ops.native_attention_available()
+    before = ops.fallback_counts.get("attention_sdpa", 0)
+    q, k, v = (torch.randn(256, 2, 4, 128, device="cuda", dtype=torch.bfloat16).permute(1, 2, 0, 3).requires_grad_(True)
+               for _ in range(3))
+    o = ops.attention(q, k, v, None, True, 0.0, True, None)
+    o.float().sum().backward()
+    assert ops.fallback_counts.get("attention_sdpa", 0) == before       # no library fallback
+    assert o.permute(2, 0, 1, 3).is_contiguous()                          # written in [s, b, h, d]
+
+
+def test_cuda_graph_layer_matches_eager():
+    """--enable-cuda-graph: a graphed transformer layer reproduces eager outputs and input gradients."""
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.models.gpt import get_gpt_layer_local_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+    from megatronapp_b200.transformer.cuda_graphs import CudaGraphManager
+    from megatronapp_b200.transformer.spec_utils import build_module
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    cfg = TransformerConfig(num_layers=1, hidden_size=512, num_attention_heads=4, bf16=True, params_dtype=torch.bfloat16,
+                            hidden_dropout=0.0, attention_dropout=0.0)
+    layer = build_module(get_gpt_layer_local_spec(), config=cfg, layer_number=1).cuda()
+    mgr = CudaGraphManager(layer, warmup_steps=1)
+    outs = []
+    for i in range(4):
+        torch.manual_seed(i)
+        x = torch.randn(256, 2, 512, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        y = mgr(x)
+        y.float().pow(2).sum().backward()
+        xe = x.detach().clone().requires_grad_(True)
+        ye = layer(xe)[0]
+        ye.float().pow(2).sum().backward()
+        outs.append((float((y - ye).abs().max()), float((x.grad - xe.grad).abs().max())))
+    assert mgr.replays >= 2 and mgr.refused is None
+    assert max(a for a, _ in outs) < 2e-2 and max(b for _, b in outs) < 2e-1, outs
 
 
 def test_model_step_matches_fp32_reference():
