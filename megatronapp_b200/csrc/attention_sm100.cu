@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 #include "b200_api.h"
 #include "common.cuh"
@@ -108,16 +109,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int qblk2 = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
   const int h = blockIdx.y, bi = blockIdx.z;
   const int hk = h / (p.hq / p.hkv);
-  const int q0[2] = {qblk2 * 2 * kBlockQ, qblk2 * 2 * kBlockQ + kBlockQ};
+  const int q0_0 = qblk2 * 2 * kBlockQ, q0_1 = q0_0 + kBlockQ;
   const int nkv_all = (p.sk + kBlockKV - 1) / kBlockKV;
-  int nkv[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    if (q0[t] >= p.sq) nkv[t] = 0;
-    else if (p.causal) nkv[t] = min(nkv_all, q0[t] / kBlockKV + 1);
-    else nkv[t] = nkv_all;
-  }
-  const int nmax = max(nkv[0], nkv[1]);
+  auto blocks_for = [&](int q0) {
+    if (q0 >= p.sq) return 0;
+    return p.causal ? min(nkv_all, q0 / kBlockKV + 1) : nkv_all;
+  };
+  const int nkv_0 = blocks_for(q0_0), nkv_1 = blocks_for(q0_1);
+  const int nmax = max(nkv_0, nkv_1);
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -140,11 +139,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp_idx == 0) {
     // ============================================================ TMA producer
     if (lane == 0) {
-      const int ntiles = (nkv[1] > 0) ? 2 : 1;
+      const int ntiles = (nkv_1 > 0) ? 2 : 1;
       mbar_arrive_expect_tx(q_full, ntiles * L::kTile);
       for (int t = 0; t < ntiles; ++t)
         for (int c = 0; c < L::kDC; ++c)
-          tma_load_4d(&tmap_q, q_full, sQ + t * L::kTile + c * (kBlockQ * 128), c * 64, h, bi, q0[t]);
+          tma_load_4d(&tmap_q, q_full, sQ + t * L::kTile + c * (kBlockQ * 128), c * 64, h, bi, t == 0 ? q0_0 : q0_1);
       for (int j = 0; j < nmax; ++j) {
         const int ks = j % L::kKStages, vs = j % L::kVStages;
         mbar_wait(&k_empty[ks], ((j / L::kKStages) & 1) ^ 1);
@@ -190,19 +189,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      for (int t = 0; t < 2; ++t)
-        if (nkv[t] > 0) issue_S(t, 0);
+      if (nkv_0 > 0) issue_S(0, 0);
+      if (nkv_1 > 0) issue_S(1, 0);
       umma_commit(&k_empty[0]);
       for (int j = 0; j < nmax; ++j) {
         const int vs = j % L::kVStages;
         mbar_wait(&v_full[vs], (j / L::kVStages) & 1);
         if (j + 1 < nmax) mbar_wait(&k_full[(j + 1) % L::kKStages], ((j + 1) / L::kKStages) & 1);
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (j >= nkv[t]) continue;
+          const int nt = t == 0 ? nkv_0 : nkv_1;
+          if (j >= nt) continue;
           mbar_wait(&p_ready[t], j & 1);
           tc_fence_after();
           issue_PV(t, j);
-          if (j + 1 < nkv[t]) issue_S(t, j + 1);
+          if (j + 1 < nt) issue_S(t, j + 1);
         }
         umma_commit(&v_empty[vs]);
         if (j + 1 < nmax) umma_commit(&k_empty[(j + 1) % L::kKStages]);
@@ -213,38 +214,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int t = (warp_idx - 4) >> 2;            // q tile of this warpgroup
     const int quad = warp_idx & 3;                // TMEM lane quadrant
     const int r = quad * 32 + lane;               // row inside the tile
-    const int qrow = q0[t] + r;
+    const int q0 = t == 0 ? q0_0 : q0_1;
+    const int qrow = q0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_S + t * 128 + lane_addr;
     const uint32_t tO = tmem_O + t * D + lane_addr;
     uint8_t* sPt = sP + t * L::kP;
-    float m = -INFINITY, l = 0.f;
-    const int n = nkv[t];
-    for (int j = 0; j < n; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
+    float m = -INFINITY, l = 0.f;   // running max (exp2 domain, already scaled) and row sum
+    const int n = t == 0 ? nkv_0 : nkv_1;
+    const float sc = p.scale_log2;
+    const bool bf = p.is_bf16 != 0;
+
+    // one key block: two sweeps over the S tile in TMEM (row max, then exp2 / pack / store P)
+    auto block = [&](int j, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       const int kbase = j * kBlockKV;
-      // does this block need masking (diagonal block of a causal tile, or the ragged tail)?
-      const bool need_mask = (p.causal && kbase + kBlockKV - 1 > q0[t]) || (kbase + kBlockKV > p.sk);
-      const int col_limit = need_mask ? min(p.sk, p.causal ? qrow + 1 : p.sk) : (1 << 30);  // valid: col < limit
+      const int limit = (kMasked ? min(p.sk, p.causal ? qrow + 1 : p.sk) : 0) - kbase;   // valid: col < limit
       float mx = -INFINITY;
+      {
+        uint32_t v[2][32];
+        tmem_ld_32x32(tS, v[0]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(tS + (c + 1) * 32, v[(c + 1) & 1]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) * p.scale_log2;
-          if (need_mask && kbase + c * 32 + i >= col_limit) x = -INFINITY;
-          mx = fmaxf(mx, x);
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[c & 1][i]);
+            if (kMasked && c * 32 + i >= limit) x = -INFINITY;
+            mx = fmaxf(mx, x);
+          }
         }
       }
-      float m_new = fmaxf(m, mx);
-      if (m_new == -INFINITY) m_new = 0.f;      // fully masked row so far: keep everything finite
-      const bool grow = (m_new - m) > kRescaleThreshold;   // also true for the first block (m = -inf)
+      float m_new = fmaxf(m, mx * sc);             // softmax scale is positive
+      if (m_new == -INFINITY) m_new = 0.f;         // fully masked so far: keep everything finite
+      const bool grow = (m_new - m) > kRescaleThreshold;   // also true on the first block (m = -inf)
       const float m_cur = grow ? m_new : m;
-      const float alpha = grow ? fast_exp2(m - m_cur) : 1.f;   // exp2(-inf) = 0 on the first block
+      const float alpha = grow ? fast_exp2(m - m_cur) : 1.f;
       if (j > 0) {
         mbar_wait(&pv_done[t], (j - 1) & 1);
         tc_fence_after();
@@ -262,38 +268,50 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
       l *= alpha;
-      float rs = 0.f;
+      float rs0 = 0.f, rs1 = 0.f;
+      {
+        uint32_t v[2][32];
+        tmem_ld_32x32(tS, v[0]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(tS + (c + 1) * 32, v[(c + 1) & 1]);
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float x0 = __uint_as_float(v[i]) * p.scale_log2 - m_cur;
-          float x1 = __uint_as_float(v[i + 1]) * p.scale_log2 - m_cur;
-          float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-          if (need_mask) {
-            if (kbase + c * 32 + i >= col_limit) p0 = 0.f;
-            if (kbase + c * 32 + i + 1 >= col_limit) p1 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[c & 1][i]), sc, -m_cur));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[c & 1][i + 1]), sc, -m_cur));
+            if (kMasked) {
+              if (c * 32 + i >= limit) p0 = 0.f;
+              if (c * 32 + i + 1 >= limit) p1 = 0.f;
+            }
+            rs0 += p0;
+            rs1 += p1;
+            pk[i >> 1] = pack16(p0, p1, bf);
           }
-          rs += p0 + p1;
-          pk[i >> 1] = pack16(p0, p1, p.is_bf16 != 0);
-        }
-        // keys c*32 .. c*32+31 -> chunk (c>>1), 16-byte units (c&1)*4 .. +3 of row r
-        uint8_t* chunk = sPt + (c >> 1) * (kBlockQ * 128);
+          // keys c*32 .. c*32+31 -> chunk (c>>1), 16-byte units (c&1)*4 .. +3 of row r
+          uint8_t* chunk = sPt + (c >> 1) * (kBlockQ * 128);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) =
-              make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) =
+                make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
         }
       }
-      l += rs;
+      l += rs0 + rs1;
       m = m_cur;
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_ready[t]);
+    };
+
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const int kbase = j * kBlockKV;
+      // diagonal block of a causal tile, or the ragged tail of the key sequence
+      const bool need_mask = (p.causal && kbase + kBlockKV - 1 > q0) || (kbase + kBlockKV > p.sk);
+      if (need_mask) block(j, std::true_type{});
+      else block(j, std::false_type{});
     }
     if (n > 0) {
       mbar_wait(&pv_done[t], (n - 1) & 1);
@@ -312,10 +330,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint4 w;
-            w.x = pack16(__uint_as_float(v[u * 8 + 0]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l, p.is_bf16 != 0);
-            w.y = pack16(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l, p.is_bf16 != 0);
-            w.z = pack16(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l, p.is_bf16 != 0);
-            w.w = pack16(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l, p.is_bf16 != 0);
+            w.x = pack16(__uint_as_float(v[u * 8 + 0]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l, bf);
+            w.y = pack16(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l, bf);
+            w.z = pack16(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l, bf);
+            w.w = pack16(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l, bf);
             *reinterpret_cast<uint4*>(orow + c * 64 + u * 16) = w;
           }
         }
@@ -333,7 +351,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // ------------------------------------------------------------------------------------ backward
 // delta[b, h, s] = sum_d O * dO   (one warp per row)
 __global__ void attn_delta_kernel(const void* __restrict__ o, const void* __restrict__ d_o, float* __restrict__ delta,
-                                  int b, int h, int s, int d, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                                  const float* __restrict__ lse, float* __restrict__ lse2, int b, int h, int s, int d, int64_t o_sb, int64_t o_sh, int64_t o_ss,
                                   int64_t do_sb, int64_t do_sh, int64_t do_ss, int is_bf16) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t total = static_cast<int64_t>(b) * h * s;
@@ -352,11 +370,15 @@ __global__ void attn_delta_kernel(const void* __restrict__ o, const void* __rest
     acc += fa.x * fc.x + fa.y * fc.y;
   }
   acc = warp_sum(acc);
-  if (lane_id() == 0) delta[row] = acc;
+  if (lane_id() == 0) {
+    delta[row] = acc;
+    const float lv = lse[row];
+    lse2[row] = (lv == -INFINITY) ? INFINITY : lv * kLog2e;   // exp2-domain LSE; fully masked rows give P = 0
+  }
 }
 
 struct BwdParams {
-  const float* lse;     // [b, hq, sq] natural-log LSE from the forward
+  const float* lse;     // [b, hq, sq] LSE in the exp2 domain (lse * log2e)
   const float* delta;   // [b, hq, sq]
   void* out1;           // dq (kDQ) or dv
   void* out2;           // unused (kDQ) or dk
@@ -546,64 +568,69 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
     const int r = quad * 32 + lane;
     const int grow = r0 + r;                       // global row (key for dK/dV, query for dQ)
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    float row_lse2 = 0.f, row_delta = 0.f;
+    const bool bf = p.is_bf16 != 0;
+    const float sc = p.scale_log2;
+    float row_lse2 = 0.f, row_delta = 0.f;         // dQ mode: statistics of this thread's query row
     if (kDQ) {
       const int64_t idx = (static_cast<int64_t>(bi) * p.hq + blockIdx.y) * p.sq + min(grow, p.sq - 1);
-      const float lv = p.lse[idx];
-      row_lse2 = (lv == -INFINITY) ? INFINITY : lv * kLog2e;
+      row_lse2 = p.lse[idx];                       // already in the exp2 domain (-inf mapped to +inf)
       row_delta = p.delta[idx];
     }
-    for (int it = 0; it < n_iter; ++it) {
+    // one streamed block: P = exp2(T1 * scale - lse2), dS = P * (T2 - delta); both to swizzled smem
+    auto block = [&](int it, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       const int st = it & 1;
       const int c0 = (col_blk0 + it % n_col) * kBwdCols;
-      mbar_wait(&t_full[st], (it >> 1) & 1);
-      tc_fence_after();
-      if (it >= 2) mbar_wait(&pds_free[st], ((it >> 1) - 1) & 1);
-      // masking: key index > query index is masked (causal); also ragged tails
-      bool need_mask;
-      if (kDQ) need_mask = (p.causal && c0 + kBwdCols - 1 > r0) || (c0 + kBwdCols > p.sk);
-      else need_mask = (p.causal && c0 < r0 + kBwdRows - 1) || (c0 + kBwdCols > p.sq);
-      const float* s_lse = sStat + st * 128;
-      const float* s_delta = s_lse + 64;
+      const float4* s_lse4 = reinterpret_cast<const float4*>(sStat + st * 128);
+      const float4* s_delta4 = s_lse4 + 16;
+      uint8_t* dst_ds = sDS + st * L::kPD;
+      uint8_t* dst_p = sP + st * L::kPD;
+      uint32_t t1[2][32], t2[2][32];
+      tmem_ld_32x32(tmem_T1 + st * 64 + lane_addr, t1[0]);
+      tmem_ld_32x32(tmem_T2 + st * 64 + lane_addr, t2[0]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t t1[32], t2[32];
-        tmem_ld_32x32(tmem_T1 + st * 64 + c * 32 + lane_addr, t1);
-        tmem_ld_32x32(tmem_T2 + st * 64 + c * 32 + lane_addr, t2);
         tmem_ld_wait();
+        if (c == 0) {
+          tmem_ld_32x32(tmem_T1 + st * 64 + 32 + lane_addr, t1[1]);
+          tmem_ld_32x32(tmem_T2 + st * 64 + 32 + lane_addr, t2[1]);
+        }
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2], dv[2];
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float l2[4], dl[4];
+          if (kDQ) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = c0 + c * 32 + i + e;   // global column (query for dK/dV, key for dQ)
-            float l2, dl;
-            if (kDQ) { l2 = row_lse2; dl = row_delta; }
-            else {
-              const float lv = s_lse[c * 32 + i + e];
-              l2 = (lv == -INFINITY) ? INFINITY : lv * kLog2e;
-              dl = s_delta[c * 32 + i + e];
-            }
-            float pe = fast_exp2(__uint_as_float(t1[i + e]) * p.scale_log2 - l2);
-            if (need_mask) {
+            for (int e = 0; e < 4; ++e) { l2[e] = row_lse2; dl[e] = row_delta; }
+          } else {
+            const float4 a = s_lse4[c * 8 + i4], d4 = s_delta4[c * 8 + i4];
+            l2[0] = a.x; l2[1] = a.y; l2[2] = a.z; l2[3] = a.w;
+            dl[0] = d4.x; dl[1] = d4.y; dl[2] = d4.z; dl[3] = d4.w;
+          }
+          float pv[4], dv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i4 * 4 + e;
+            float pe = fast_exp2(fmaf(__uint_as_float(t1[c][i]), sc, -l2[e]));
+            if (kMasked) {
+              const int col = c0 + c * 32 + i;     // global column (query for dK/dV, key for dQ)
               const int key = kDQ ? col : grow;
               const int qry = kDQ ? grow : col;
               if ((p.causal && key > qry) || key >= p.sk || qry >= p.sq) pe = 0.f;
             }
             pv[e] = pe;
-            dv[e] = pe * (__uint_as_float(t2[i + e]) - dl);
+            dv[e] = pe * (__uint_as_float(t2[c][i]) - dl[e]);
           }
-          pk[i >> 1] = pack16(pv[0], pv[1], p.is_bf16 != 0);
-          dk[i >> 1] = pack16(dv[0], dv[1], p.is_bf16 != 0);
+          pk[i4 * 2] = pack16(pv[0], pv[1], bf);
+          pk[i4 * 2 + 1] = pack16(pv[2], pv[3], bf);
+          dk[i4 * 2] = pack16(dv[0], dv[1], bf);
+          dk[i4 * 2 + 1] = pack16(dv[2], dv[3], bf);
         }
-        uint8_t* dst_ds = sDS + st * L::kPD;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           *reinterpret_cast<uint4*>(dst_ds + sw128_off(r, c * 4 + u)) =
               make_uint4(dk[u * 4], dk[u * 4 + 1], dk[u * 4 + 2], dk[u * 4 + 3]);
         if (!kDQ) {
-          uint8_t* dst_p = sP + st * L::kPD;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             *reinterpret_cast<uint4*>(dst_p + sw128_off(r, c * 4 + u)) =
@@ -613,6 +640,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&pds_ready[st]);
+    };
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it & 1;
+      const int c0 = (col_blk0 + it % n_col) * kBwdCols;
+      mbar_wait(&t_full[st], (it >> 1) & 1);
+      tc_fence_after();
+      if (it >= 2) mbar_wait(&pds_free[st], ((it >> 1) - 1) & 1);
+      // masking: key index > query index is masked (causal); also ragged tails
+      bool need_mask;
+      if (kDQ) need_mask = (p.causal && c0 + kBwdCols - 1 > r0) || (c0 + kBwdCols > p.sk) || (r0 + kBwdRows > p.sq);
+      else need_mask = (p.causal && c0 < r0 + kBwdRows - 1) || (c0 + kBwdCols > p.sq) || (r0 + kBwdRows > p.sk);
+      if (need_mask) block(it, std::true_type{});
+      else block(it, std::false_type{});
     }
     if (n_iter > 0) {
       mbar_wait(acc_done, 0);
@@ -753,7 +793,8 @@ int launch_bwd_one(const AttnArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   BwdParams p{};
-  p.lse = a.lse; p.delta = a.delta;
+  p.lse = a.delta + static_cast<int64_t>(a.b) * a.hq * a.sq;   // exp2-domain LSE written by attn_delta_kernel
+  p.delta = a.delta;
   if (kDQ) { p.out1 = a.dq; p.o1_sb = a.dq_sb; p.o1_sh = a.dq_sh; p.o1_ss = a.dq_ss; }
   else {
     p.out1 = a.dv; p.o1_sb = a.dv_sb; p.o1_sh = a.dv_sh; p.o1_ss = a.dv_ss;
@@ -772,7 +813,7 @@ template <int D>
 int launch_bwd(const AttnArgs& a, cudaStream_t s) {
   const int64_t rows = static_cast<int64_t>(a.b) * a.hq * a.sq;
   attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
-      a.o, a.d_o, a.delta, a.b, a.hq, a.sq, D, a.o_sb, a.o_sh, a.o_ss, a.do_sb, a.do_sh, a.do_ss, a.is_bf16 ? 1 : 0);
+      a.o, a.d_o, a.delta, a.lse, a.delta + rows, a.b, a.hq, a.sq, D, a.o_sb, a.o_sh, a.o_ss, a.do_sb, a.do_sh, a.do_ss, a.is_bf16 ? 1 : 0);
   int rc = launch_bwd_one<D, false>(a, s);
   if (rc != 0) return rc;
   return launch_bwd_one<D, true>(a, s);

@@ -375,7 +375,7 @@ std::vector<Tensor> attn_bwd(const Tensor& d_o, const Tensor& q, const Tensor& k
   auto dq = torch::empty({a.sq, a.b, a.hq, a.d}, q.options()).permute({1, 2, 0, 3});
   auto dk = torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
   auto dv = torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
-  auto delta = torch::empty({a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));
+  auto delta = torch::empty({2, a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));   // [delta ; lse * log2e]
   a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = const_cast<void*>(o.data_ptr()); a.lse = lse.data_ptr<float>();
   a.d_o = doc.data_ptr(); a.dq = dq.data_ptr(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
   a.delta = delta.data_ptr<float>(); a.dq_accum = nullptr;
