@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -65,13 +66,16 @@ struct FwdParams {
   int is_bf16;
 };
 
-template <int D>
+// kPTmem: P (bf16) overwrites the S columns in TMEM and feeds the PV product as the TMEM A operand
+// (halves the shared-memory traffic of a key block and frees room for a second V stage);
+// otherwise P goes through swizzled shared memory.
+template <int D, bool kPTmem>
 struct FwdSmem {
   static constexpr int kDC = D / 64;                    // 64-element (128 B) chunks along d
   static constexpr int kTile = kBlockQ * 128 * kDC;     // bytes of a [128 x D] 16-bit tile
   static constexpr int kKStages = 2;
-  static constexpr int kVStages = (D == 64) ? 2 : 1;
-  static constexpr int kP = kBlockQ * kBlockKV * 2;     // 32 KB
+  static constexpr int kVStages = (D == 64 || kPTmem) ? 2 : 1;
+  static constexpr int kP = kPTmem ? 0 : kBlockQ * kBlockKV * 2;     // 32 KB
   static constexpr int kQOff = 0;
   static constexpr int kKOff = kQOff + 2 * kTile;
   static constexpr int kVOff = kKOff + kKStages * kTile;
@@ -81,11 +85,11 @@ struct FwdSmem {
 };
 
 // ------------------------------------------------------------------------------------ forward
-template <int D>
+template <int D, bool kPTmem>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const FwdParams p) {
-  using L = FwdSmem<D>;
+  using L = FwdSmem<D, kPTmem>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + L::kQOff;
@@ -177,12 +181,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t a0 = smem_u32(sP + t * L::kP), b0 = smem_u32(sV + vs * L::kTile);
 #pragma unroll
         for (int k = 0; k < kBlockKV / 16; ++k) {
-          const uint32_t aoff = (k >> 2) * (kBlockQ * 128) + (k & 3) * 32;
           // V is MN-major for this product (N = d contiguous): 16 key rows per k-step,
           // LBO = next 64-wide d chunk
-          umma_f16_ss(tmem_O + t * D, make_smem_desc_sw128(a0 + aoff, 1024, 0),
-                      make_smem_desc_sw128(b0 + k * 16 * 128, 1024, kBlockKV * 128), idesc_o,
-                      (j | k) != 0 ? 1u : 0u);
+          const uint64_t bdesc = make_smem_desc_sw128(b0 + k * 16 * 128, 1024, kBlockKV * 128);
+          if constexpr (kPTmem) {
+            // A = P from TMEM: row = lane, 16 keys = 8 packed 32-bit columns per k-step
+            umma_f16_ts(tmem_O + t * D, tmem_S + t * 128 + k * 8, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          } else {
+            const uint32_t aoff = (k >> 2) * (kBlockQ * 128) + (k & 3) * 32;
+            umma_f16_ss(tmem_O + t * D, make_smem_desc_sw128(a0 + aoff, 1024, 0), bdesc, idesc_o,
+                        (j | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&pv_done[t]);
       };
@@ -289,18 +298,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             rs1 += p1;
             pk[i >> 1] = pack16(p0, p1, bf);
           }
-          // keys c*32 .. c*32+31 -> chunk (c>>1), 16-byte units (c&1)*4 .. +3 of row r
-          uint8_t* chunk = sPt + (c >> 1) * (kBlockQ * 128);
+          if constexpr (kPTmem) {
+            // packed P chunk c -> TMEM columns [16c, 16c+16) of this tile's S region; the fp32 S
+            // columns it overwrites ([32c', ...) with c' < c, or chunk 0 itself) are already consumed
+            tmem_st_32x16(tS + c * 16, pk);
+          } else {
+            // keys c*32 .. c*32+31 -> chunk (c>>1), 16-byte units (c&1)*4 .. +3 of row r
+            uint8_t* chunk = sPt + (c >> 1) * (kBlockQ * 128);
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) =
-                make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(chunk + sw128_off(r, (c & 1) * 4 + u)) =
+                  make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+          }
         }
       }
       l += rs0 + rs1;
       m = m_cur;
+      if constexpr (kPTmem) tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
+      if constexpr (!kPTmem) fence_proxy_async_smem();
       mbar_arrive(&p_ready[t]);
     };
 
@@ -742,14 +758,14 @@ bool strides_ok(int64_t sb, int64_t sh, int64_t ss, const void* ptr) {
   return (sb % 8 == 0) && (sh % 8 == 0) && (ss % 8 == 0) && (reinterpret_cast<uintptr_t>(ptr) % 16 == 0);
 }
 
-template <int D>
+template <int D, bool kPTmem>
 int launch_fwd(const AttnArgs& a, cudaStream_t s) {
-  using L = FwdSmem<D>;
+  using L = FwdSmem<D, kPTmem>;
   CUtensorMap tq{}, tk{}, tv{};
   if (!make_tmap_bhsd(&tq, a.q, a.is_bf16, D, a.hq, a.b, a.sq, a.q_sh, a.q_sb, a.q_ss, kBlockQ)) return -5;
   if (!make_tmap_bhsd(&tk, a.k, a.is_bf16, D, a.hkv, a.b, a.sk, a.k_sh, a.k_sb, a.k_ss, kBlockKV)) return -5;
   if (!make_tmap_bhsd(&tv, a.v, a.is_bf16, D, a.hkv, a.b, a.sk, a.v_sh, a.v_sb, a.v_ss, kBlockKV)) return -5;
-  auto kern = attn_fwd_kernel<D>;
+  auto kern = attn_fwd_kernel<D, kPTmem>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -833,7 +849,12 @@ int attn_fwd(const AttnArgs& a, cudaStream_t s) {
     g_attn_error = "q/k/v/o need 16-byte aligned base and strides";
     return -4;
   }
-  return a.d == 128 ? launch_fwd<128>(a, s) : launch_fwd<64>(a, s);
+  static const bool p_tmem = [] {
+    const char* e = getenv("B200_ATTN_P_TMEM");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (p_tmem) return a.d == 128 ? launch_fwd<128, true>(a, s) : launch_fwd<64, true>(a, s);
+  return a.d == 128 ? launch_fwd<128, false>(a, s) : launch_fwd<64, false>(a, s);
 }
 
 int attn_bwd(const AttnArgs& a, cudaStream_t s) {

@@ -124,3 +124,65 @@ def test_preprocess_tool(tmp_path):
                            "--output-prefix", str(out)])
     ds = IndexedDataset(str(out) + "_text_document")
     assert len(ds) == 20 and ds[2].tolist() == list(range(2, 14)) + [500]
+
+
+def _sentence_corpus(tmp_path, n_docs=12):
+    import numpy as np
+
+    from megatronapp_b200.data.indexed_dataset import IndexedDatasetBuilder, get_bin_path, get_idx_path
+
+    prefix = str(tmp_path / "sent")
+    b = IndexedDatasetBuilder(get_bin_path(prefix), dtype=np.int32)
+    rng = np.random.RandomState(0)
+    for _ in range(n_docs):
+        for _ in range(rng.randint(3, 7)):
+            b.add_item(torch.from_numpy(rng.randint(10, 200, size=rng.randint(5, 20)).astype(np.int64)))
+        b.end_document()
+    b.finalize(get_idx_path(prefix))
+    return prefix
+
+
+class _Tok:
+    vocab_size, cls, sep, mask, pad, bos, eos = 256, 1, 2, 3, 0, 4, 5
+    inv_vocab = None
+
+
+def test_bert_masked_dataset(tmp_path):
+    from megatronapp_b200.data.indexed_dataset import IndexedDataset
+    from megatronapp_b200.data.masked_dataset import BERTMaskedWordPieceDataset, MaskedWordPieceDatasetConfig
+
+    ds = BERTMaskedWordPieceDataset(IndexedDataset(_sentence_corpus(tmp_path)), 40,
+                                    MaskedWordPieceDatasetConfig(sequence_length=64), _Tok())
+    assert len(ds) == 40
+    frac, rnd = [], 0
+    for i in range(len(ds)):
+        s = ds[i]
+        n = int(s["padding_mask"].sum())
+        assert s["text"][0] == 1 and (s["text"][:n] == 2).sum() == 2 and (s["text"][n:] == 0).all()
+        assert s["types"][:n].max() == 1 and int(s["loss_mask"].sum()) >= 1
+        m = s["loss_mask"].bool()
+        assert ((s["text"][m] == 3) | (s["labels"][m] > 0)).all()
+        frac.append(float(m.sum()) / (n - 3))
+        rnd += int(s["is_random"])
+        a, b = ds[i], ds[i]
+        assert torch.equal(a["text"], b["text"])          # deterministic per index
+    assert 0.08 < sum(frac) / len(frac) < 0.25 and 5 < rnd < 35
+
+
+def test_t5_masked_dataset(tmp_path):
+    from megatronapp_b200.data.indexed_dataset import IndexedDataset
+    from megatronapp_b200.data.masked_dataset import MaskedWordPieceDatasetConfig, T5MaskedWordPieceDataset
+
+    sent = list(range(240, 256))
+    ds = T5MaskedWordPieceDataset(IndexedDataset(_sentence_corpus(tmp_path)), 20,
+                                  MaskedWordPieceDatasetConfig(sequence_length=64, sequence_length_decoder=32), _Tok(),
+                                  sentinel_tokens=sent)
+    for i in range(len(ds)):
+        s = ds[i]
+        enc, dec, lab = s["text_enc"].tolist(), s["text_dec"].tolist(), s["labels"].tolist()
+        k = sum(t in sent for t in enc)
+        assert k >= 1 and dec[0] == 4 and dec[1] == sent[0]
+        n_out = int(s["loss_mask"].sum())
+        assert lab[n_out - 1] == 5 and lab[:n_out - 1] == dec[1:n_out]           # teacher forcing shift
+        assert s["dec_mask"][0, 1] == 0 and s["dec_mask"][1, 0] == 1               # causal decoder mask
+        assert s["enc_dec_mask"].shape == (32, 64)
