@@ -410,45 +410,42 @@ constexpr int kBwdCols = 64;    // streamed rows per iteration (queries for dK/d
 template <int D, bool kDQ>
 struct BwdSmem {
   static constexpr int kDC = D / 64;
+  static constexpr int kStages = 4;                     // streamed-tile ring depth (hides TMA latency)
   static constexpr int kX = kBwdRows * 128 * kDC;       // resident tile bytes
   static constexpr int kY = kBwdCols * 128 * kDC;       // streamed tile bytes
-  static constexpr int kStage = 2 * kY + 512;           // Y1, Y2, lse[64], delta[64]
-  static constexpr int kPD = kBwdRows * 128;            // [128 x 64] 16-bit tile, one swizzle chunk
   static constexpr int kX1Off = 0;
   static constexpr int kX2Off = kX;
-  static constexpr int kStageOff = 2 * kX;
-  static constexpr int kDSOff = kStageOff + 2 * 2 * kY;        // two stages of (Y1, Y2)
-  static constexpr int kPOff = kDSOff + 2 * kPD;
-  static constexpr int kStatOff = kPOff + (kDQ ? 0 : 2 * kPD);  // 2 x (lse[64] + delta[64]) floats
-  static constexpr int kBarOff = kStatOff + 2 * 512;
+  static constexpr int kStageOff = 2 * kX;              // stage s: Y1 at s*2*kY, Y2 at s*2*kY + kY
+  static constexpr int kStatOff = kStageOff + kStages * 2 * kY;   // stage s: lse2[64], delta[64] floats
+  static constexpr int kBarOff = kStatOff + kStages * 512;
   static constexpr int kTotal = kBarOff + 256 + 1024;
 };
 
 // kDQ = false: rows are keys   (X1 = K, X2 = V, Y1 = Q_i, Y2 = dO_i): acc1 = dV, acc2 = dK
 // kDQ = true : rows are queries (X1 = Q, X2 = dO, Y1 = K_j, Y2 = V_j): acc1 = dQ
+// P / dS (16-bit) overwrite the T1 / T2 accumulator columns in TMEM and feed the accumulate MMAs as
+// the TMEM A operand, so the only shared-memory traffic is the operand tiles themselves.
 template <int D, bool kDQ>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_x2,
                 const __grid_constant__ CUtensorMap tmap_y1, const __grid_constant__ CUtensorMap tmap_y2,
                 const BwdParams p) {
   using L = BwdSmem<D, kDQ>;
+  constexpr int kS = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX1 = smem + L::kX1Off;
   uint8_t* sX2 = smem + L::kX2Off;
-  uint8_t* sY = smem + L::kStageOff;     // stage s: Y1 at s*2*kY, Y2 at s*2*kY + kY
-  uint8_t* sDS = smem + L::kDSOff;
-  uint8_t* sP = smem + L::kPOff;
-  float* sStat = reinterpret_cast<float*>(smem + L::kStatOff);   // stage s: lse at s*128, delta at s*128+64
+  uint8_t* sY = smem + L::kStageOff;
+  float* sStat = reinterpret_cast<float*>(smem + L::kStatOff);   // stage s: lse2 at s*128, delta at s*128+64
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* x_full = bars;           // 1
-  uint64_t* y_full = bars + 1;       // 2
-  uint64_t* y_empty = bars + 3;      // 2
-  uint64_t* t_full = bars + 5;       // 2
-  uint64_t* pds_ready = bars + 7;    // 2
-  uint64_t* pds_free = bars + 9;     // 2
-  uint64_t* acc_done = bars + 11;    // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* x_full = bars;               // 1
+  uint64_t* y_full = bars + 1;           // kS
+  uint64_t* y_empty = bars + 1 + kS;     // kS
+  uint64_t* t_full = bars + 1 + 2 * kS;  // 2
+  uint64_t* pds_ready = t_full + 2;      // 2
+  uint64_t* acc_done = pds_ready + 2;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -458,14 +455,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
   // iteration space
   int col_blk0, n_col, n_heads, head0;
   if (kDQ) {
-    const int h = blockIdx.y;
-    head0 = h; n_heads = 1;
+    head0 = blockIdx.y; n_heads = 1;
     col_blk0 = 0;
     const int kmax = p.causal ? min(p.sk, r0 + kBwdRows) : p.sk;
     n_col = (kmax + kBwdCols - 1) / kBwdCols;
   } else {
-    const int hk = blockIdx.y;
-    head0 = hk * G; n_heads = G;
+    head0 = blockIdx.y * G; n_heads = G;
     col_blk0 = p.causal ? r0 / kBwdCols : 0;
     n_col = (p.sq + kBwdCols - 1) / kBwdCols - col_blk0;
     if (n_col < 0) n_col = 0;
@@ -474,10 +469,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(x_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&t_full[i], 1);
-      mbar_init(&pds_ready[i], 128); mbar_init(&pds_free[i], 1);
-    }
+    for (int i = 0; i < kS; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&pds_ready[i], 128); }
     mbar_init(acc_done, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmap_x1); tma_prefetch_desc(&tmap_x2); tma_prefetch_desc(&tmap_y1); tma_prefetch_desc(&tmap_y2);
@@ -487,36 +480,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_T1 = tmem_base;          // T1[buf] at col buf*64
-  const uint32_t tmem_T2 = tmem_base + 128;    // T2[buf] at col 128 + buf*64
+  const uint32_t tmem_T1 = tmem_base;          // T1[buf] at col buf*64  (P overwrites its first 32 cols)
+  const uint32_t tmem_T2 = tmem_base + 128;    // T2[buf] at col 128 + buf*64 (dS overwrites its first 32 cols)
   const uint32_t tmem_A1 = tmem_base + 256;    // dV or dQ
   const uint32_t tmem_A2 = tmem_base + 256 + D;  // dK
 
   if (warp_idx == 0) {
     // ============================================================ TMA producer
     if (lane == 0 && n_iter > 0) {
-      const int hx = kDQ ? head0 : blockIdx.y;   // head of the resident tiles
+      const int hx = blockIdx.y;   // head of the resident tiles (kv head for dK/dV, q head for dQ)
       mbar_arrive_expect_tx(x_full, 2 * L::kX);
       for (int c = 0; c < L::kDC; ++c) {
         tma_load_4d(&tmap_x1, x_full, sX1 + c * (kBwdRows * 128), c * 64, hx, bi, r0);
         tma_load_4d(&tmap_x2, x_full, sX2 + c * (kBwdRows * 128), c * 64, hx, bi, r0);
       }
       for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
+        const int ys = it % kS;
         const int head = kDQ ? blockIdx.y / G : head0 + it / n_col;   // head of the streamed tiles
         const int c0 = (col_blk0 + it % n_col) * kBwdCols;
-        mbar_wait(&y_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&y_full[st], 2 * L::kY + (kDQ ? 0 : 512));
-        uint8_t* y1 = sY + st * 2 * L::kY;
+        mbar_wait(&y_empty[ys], ((it / kS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&y_full[ys], 2 * L::kY + (kDQ ? 0 : 512));
+        uint8_t* y1 = sY + ys * 2 * L::kY;
         uint8_t* y2 = y1 + L::kY;
         for (int c = 0; c < L::kDC; ++c) {
-          tma_load_4d(&tmap_y1, &y_full[st], y1 + c * (kBwdCols * 128), c * 64, head, bi, c0);
-          tma_load_4d(&tmap_y2, &y_full[st], y2 + c * (kBwdCols * 128), c * 64, head, bi, c0);
+          tma_load_4d(&tmap_y1, &y_full[ys], y1 + c * (kBwdCols * 128), c * 64, head, bi, c0);
+          tma_load_4d(&tmap_y2, &y_full[ys], y2 + c * (kBwdCols * 128), c * 64, head, bi, c0);
         }
         if (!kDQ) {
           const int64_t base = (static_cast<int64_t>(bi) * p.hq + head) * p.sq + c0;
-          bulk_load_1d(sStat + st * 128, p.lse + base, 256, &y_full[st]);
-          bulk_load_1d(sStat + st * 128 + 64, p.delta + base, 256, &y_full[st]);
+          bulk_load_1d(sStat + ys * 128, p.lse + base, 256, &y_full[ys]);
+          bulk_load_1d(sStat + ys * 128 + 64, p.delta + base, 256, &y_full[ys]);
         }
       }
     }
@@ -526,55 +519,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
       const uint32_t idesc_t = make_idesc_f16(p.is_bf16 != 0, kBwdRows, kBwdCols, false, false);
       const uint32_t idesc_a = make_idesc_f16(p.is_bf16 != 0, kBwdRows, D, false, true);
       auto issue_T = [&](int it) {
-        const int st = it & 1;
+        const int ys = it % kS, tb = it & 1;
         const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
-        const uint32_t y1 = smem_u32(sY + st * 2 * L::kY), y2 = y1 + L::kY;
+        const uint32_t y1 = smem_u32(sY + ys * 2 * L::kY), y2 = y1 + L::kY;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t xo = (k >> 2) * (kBwdRows * 128) + (k & 3) * 32;
           const uint32_t yo = (k >> 2) * (kBwdCols * 128) + (k & 3) * 32;
-          umma_f16_ss(tmem_T1 + st * 64, make_smem_desc_sw128(x1 + xo, 1024, 0), make_smem_desc_sw128(y1 + yo, 1024, 0),
+          umma_f16_ss(tmem_T1 + tb * 64, make_smem_desc_sw128(x1 + xo, 1024, 0), make_smem_desc_sw128(y1 + yo, 1024, 0),
                       idesc_t, k != 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t xo = (k >> 2) * (kBwdRows * 128) + (k & 3) * 32;
           const uint32_t yo = (k >> 2) * (kBwdCols * 128) + (k & 3) * 32;
-          umma_f16_ss(tmem_T2 + st * 64, make_smem_desc_sw128(x2 + xo, 1024, 0), make_smem_desc_sw128(y2 + yo, 1024, 0),
+          umma_f16_ss(tmem_T2 + tb * 64, make_smem_desc_sw128(x2 + xo, 1024, 0), make_smem_desc_sw128(y2 + yo, 1024, 0),
                       idesc_t, k != 0 ? 1u : 0u);
         }
-        umma_commit(&t_full[st]);
+        umma_commit(&t_full[tb]);
       };
       mbar_wait(x_full, 0);
       mbar_wait(&y_full[0], 0);
       tc_fence_after();
       issue_T(0);
       for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
+        const int ys = it % kS, tb = it & 1;
         if (it + 1 < n_iter) {
-          mbar_wait(&y_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+          mbar_wait(&y_full[(it + 1) % kS], ((it + 1) / kS) & 1);
           tc_fence_after();
-          issue_T(it + 1);
+          issue_T(it + 1);     // overwrites T[(it+1)&1]: its P/dS were consumed by the accumulate MMAs of it-1
         }
-        mbar_wait(&pds_ready[st], (it >> 1) & 1);
+        mbar_wait(&pds_ready[tb], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t y1 = smem_u32(sY + st * 2 * L::kY), y2 = y1 + L::kY;
-        const uint32_t ds = smem_u32(sDS + st * L::kPD);
+        const uint32_t y1 = smem_u32(sY + ys * 2 * L::kY), y2 = y1 + L::kY;
 #pragma unroll
         for (int k = 0; k < kBwdCols / 16; ++k) {
-          // streamed tile as MN-major B (N = d contiguous, K = its 64 rows)
+          // streamed tile as MN-major B (N = d contiguous, K = its 64 rows); A = P / dS from TMEM
+          // (row = lane, 16 k-values = 8 packed 32-bit columns per step)
           const uint64_t bdesc1 = make_smem_desc_sw128(y1 + k * 16 * 128, 1024, kBwdCols * 128);
           if (kDQ) {
-            umma_f16_ss(tmem_A1, make_smem_desc_sw128(ds + k * 32, 1024, 0), bdesc1, idesc_a, (it | k) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_A1, tmem_T2 + tb * 64 + k * 8, bdesc1, idesc_a, (it | k) != 0 ? 1u : 0u);
           } else {
-            const uint32_t pp = smem_u32(sP + st * L::kPD);
             const uint64_t bdesc2 = make_smem_desc_sw128(y2 + k * 16 * 128, 1024, kBwdCols * 128);
-            umma_f16_ss(tmem_A1, make_smem_desc_sw128(pp + k * 32, 1024, 0), bdesc2, idesc_a, (it | k) != 0 ? 1u : 0u);
-            umma_f16_ss(tmem_A2, make_smem_desc_sw128(ds + k * 32, 1024, 0), bdesc1, idesc_a, (it | k) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_A1, tmem_T1 + tb * 64 + k * 8, bdesc2, idesc_a, (it | k) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_A2, tmem_T2 + tb * 64 + k * 8, bdesc1, idesc_a, (it | k) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&y_empty[st]);
-        umma_commit(&pds_free[st]);
+        umma_commit(&y_empty[ys]);
       }
       umma_commit(acc_done);
     }
@@ -592,24 +583,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
       row_lse2 = p.lse[idx];                       // already in the exp2 domain (-inf mapped to +inf)
       row_delta = p.delta[idx];
     }
-    // one streamed block: P = exp2(T1 * scale - lse2), dS = P * (T2 - delta); both to swizzled smem
+    // one streamed block: P = exp2(T1 * scale - lse2), dS = P * (T2 - delta), written back to TMEM
     auto block = [&](int it, auto masked_tag) {
       constexpr bool kMasked = decltype(masked_tag)::value;
-      const int st = it & 1;
+      const int tb = it & 1, ys = it % kS;
       const int c0 = (col_blk0 + it % n_col) * kBwdCols;
-      const float4* s_lse4 = reinterpret_cast<const float4*>(sStat + st * 128);
+      const float4* s_lse4 = reinterpret_cast<const float4*>(sStat + ys * 128);
       const float4* s_delta4 = s_lse4 + 16;
-      uint8_t* dst_ds = sDS + st * L::kPD;
-      uint8_t* dst_p = sP + st * L::kPD;
+      const uint32_t a1 = tmem_T1 + tb * 64 + lane_addr, a2 = tmem_T2 + tb * 64 + lane_addr;
       uint32_t t1[2][32], t2[2][32];
-      tmem_ld_32x32(tmem_T1 + st * 64 + lane_addr, t1[0]);
-      tmem_ld_32x32(tmem_T2 + st * 64 + lane_addr, t2[0]);
+      tmem_ld_32x32(a1, t1[0]);
+      tmem_ld_32x32(a2, t2[0]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tmem_ld_wait();
         if (c == 0) {
-          tmem_ld_32x32(tmem_T1 + st * 64 + 32 + lane_addr, t1[1]);
-          tmem_ld_32x32(tmem_T2 + st * 64 + 32 + lane_addr, t2[1]);
+          tmem_ld_32x32(a1 + 32, t1[1]);
+          tmem_ld_32x32(a2 + 32, t2[1]);
         }
         uint32_t pk[16], dk[16];
 #pragma unroll
@@ -642,27 +632,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
           dk[i4 * 2] = pack16(dv[0], dv[1], bf);
           dk[i4 * 2 + 1] = pack16(dv[2], dv[3], bf);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(dst_ds + sw128_off(r, c * 4 + u)) =
-              make_uint4(dk[u * 4], dk[u * 4 + 1], dk[u * 4 + 2], dk[u * 4 + 3]);
-        if (!kDQ) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(dst_p + sw128_off(r, c * 4 + u)) =
-                make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
-        }
+        // packed chunk c -> columns [16c, 16c+16) of the same accumulator buffer; only fp32 columns that
+        // are already in registers are overwritten (chunk 1 was loaded before chunk 0 is stored)
+        tmem_st_32x16(a2 + c * 16, dk);
+        if (!kDQ) tmem_st_32x16(a1 + c * 16, pk);
       }
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(&pds_ready[st]);
+      mbar_arrive(&pds_ready[tb]);
     };
     for (int it = 0; it < n_iter; ++it) {
-      const int st = it & 1;
+      const int tb = it & 1;
       const int c0 = (col_blk0 + it % n_col) * kBwdCols;
-      mbar_wait(&t_full[st], (it >> 1) & 1);
+      mbar_wait(&t_full[tb], (it >> 1) & 1);
       tc_fence_after();
-      if (it >= 2) mbar_wait(&pds_free[st], ((it >> 1) - 1) & 1);
       // masking: key index > query index is masked (causal); also ragged tails
       bool need_mask;
       if (kDQ) need_mask = (p.causal && c0 + kBwdCols - 1 > r0) || (c0 + kBwdCols > p.sk) || (r0 + kBwdRows > p.sq);
@@ -694,10 +677,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_consta
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint4 w;
-            w.x = pack16(__uint_as_float(v[u * 8 + 0]) * mul, __uint_as_float(v[u * 8 + 1]) * mul, p.is_bf16 != 0);
-            w.y = pack16(__uint_as_float(v[u * 8 + 2]) * mul, __uint_as_float(v[u * 8 + 3]) * mul, p.is_bf16 != 0);
-            w.z = pack16(__uint_as_float(v[u * 8 + 4]) * mul, __uint_as_float(v[u * 8 + 5]) * mul, p.is_bf16 != 0);
-            w.w = pack16(__uint_as_float(v[u * 8 + 6]) * mul, __uint_as_float(v[u * 8 + 7]) * mul, p.is_bf16 != 0);
+            w.x = pack16(__uint_as_float(v[u * 8 + 0]) * mul, __uint_as_float(v[u * 8 + 1]) * mul, bf);
+            w.y = pack16(__uint_as_float(v[u * 8 + 2]) * mul, __uint_as_float(v[u * 8 + 3]) * mul, bf);
+            w.z = pack16(__uint_as_float(v[u * 8 + 4]) * mul, __uint_as_float(v[u * 8 + 5]) * mul, bf);
+            w.w = pack16(__uint_as_float(v[u * 8 + 6]) * mul, __uint_as_float(v[u * 8 + 7]) * mul, bf);
             *reinterpret_cast<uint4*>(orow + c * 64 + u * 16) = w;
           }
         }

@@ -443,7 +443,7 @@ class _AttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
-_ATTN_IMPL = os.environ.get("B200_ATTN_IMPL", "sdpa")  # auto | native | sdpa | ref
+_ATTN_IMPL = os.environ.get("B200_ATTN_IMPL", "auto")  # auto | native | sdpa | ref
 _NATIVE_ATTN_OK = None
 
 

@@ -159,3 +159,35 @@ def test_gpt_multi_latent_attention():
             ctx.sequence_len_offset += 1
     inc = torch.cat(outs, dim=1)
     assert torch.allclose(inc, full, atol=1e-4), float((inc - full).abs().max())
+
+
+def test_llava_splices_image_embeddings():
+    """LLaVA: image tokens are replaced by projected ViT embeddings; labels/loss mask are rebuilt."""
+    import copy
+
+    from megatronapp_b200.models.gpt import get_gpt_layer_local_spec
+    from megatronapp_b200.models.multimodal import DEFAULT_IMAGE_TOKEN_INDEX, LLaVAModel
+    from megatronapp_b200.models.vision import get_num_image_embeddings, get_vit_layer_spec
+    from megatronapp_b200.parallel.tp_layers import ColumnParallelLinear, RowParallelLinear
+    from megatronapp_b200.transformer.mlp import MLPSubmodules
+
+    _init()
+    lcfg = _cfg(kernel_backend="torch")
+    vcfg = copy.deepcopy(lcfg)
+    vcfg.num_layers = 1
+    pcfg = copy.deepcopy(lcfg)
+    pcfg.ffn_hidden_size = lcfg.hidden_size
+    m = LLaVAModel(lcfg, get_gpt_layer_local_spec(), 64, 48, vcfg, get_vit_layer_spec(), True, pcfg,
+                   MLPSubmodules(linear_fc1=ColumnParallelLinear, linear_fc2=RowParallelLinear), img_h=14, img_w=14,
+                   patch_dim=7)
+    n_img = get_num_image_embeddings(14, 14, 7, "clip", True)
+    assert n_img == 4
+    toks = torch.randint(1, 64, (2, 10))
+    toks[:, 2] = DEFAULT_IMAGE_TOKEN_INDEX
+    labels = torch.randint(1, 64, (2, 10))
+    pos = torch.arange(10).unsqueeze(0).expand(2, -1)
+    loss, mask = m(torch.rand(2, 3, 14, 14), toks, pos, None, labels=labels, loss_mask=torch.ones(2, 10))
+    assert loss.shape == (2, 10 - 1 + n_img) and mask.shape == loss.shape
+    assert mask[:, 2:2 + n_img].sum() == 0 and mask[:, 1].sum() == 0 and mask[:, 0].sum() == 2
+    (loss * mask).sum().backward()
+    assert m.vision_model.conv1.weight.grad.abs().sum() > 0 and m.vision_projection.encoder.linear_fc1.weight.grad is not None
