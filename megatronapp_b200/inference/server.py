@@ -86,7 +86,10 @@ class MegatronServer:
                 self.wfile.write(body)
 
             def do_PUT(self):
-                if self.path.rstrip("/") != "/api":
+                path = self.path.rstrip("/")
+                if path in ("/completions", "/v1/completions"):
+                    return self._completions()
+                if path != "/api":
                     return self._send(404, {"message": "not found"})
                 try:
                     req = json.loads(self.rfile.read(int(self.headers.get("Content-Length", 0)) or 0))
@@ -99,6 +102,35 @@ class MegatronServer:
                     self._send(200, run_generate(engine, req))
                 except ValueError as e:
                     self._send(400, {"message": str(e)})
+
+            def _completions(self):
+                """OpenAI-style ``POST /v1/completions`` (reference ``inference/endpoints/completions.py``)."""
+                try:
+                    req = json.loads(self.rfile.read(int(self.headers.get("Content-Length", 0)) or 0))
+                except Exception:
+                    return self._send(400, {"error": "invalid json"})
+                prompts = req.get("prompt", "")
+                prompts = [prompts] if isinstance(prompts, str) else list(prompts)
+                temp = float(req.get("temperature", 1.0))
+                inner = {"prompts": prompts, "tokens_to_generate": int(req.get("max_tokens", 16)),
+                         "temperature": temp if temp > 0 else 1.0, "top_k": 1 if temp == 0 else int(req.get("top_k", 0)),
+                         "top_p": float(req.get("top_p", 0.0)) if temp > 0 and not req.get("top_k") else 0.0,
+                         "logprobs": bool(req.get("logprobs")), "random_seed": req.get("seed")}
+                if inner["top_p"] >= 1.0:
+                    inner["top_p"] = 0.0
+                err = _validate(inner)
+                if err:
+                    return self._send(400, {"error": err})
+                out = run_generate(engine, inner)
+                echo = bool(req.get("echo", False))
+                choices = []
+                for i, (p_, full) in enumerate(zip(prompts, out["text"])):
+                    c = {"index": i, "text": full if echo else full[len(p_):], "finish_reason": "length"}
+                    if "logprobs" in out:
+                        c["logprobs"] = {"token_logprobs": [float(x) for x in out["logprobs"][i]]}
+                    choices.append(c)
+                self._send(200, {"object": "text_completion", "model": req.get("model", "megatronapp_b200"),
+                                 "choices": choices})
 
             do_POST = do_PUT
 

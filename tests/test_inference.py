@@ -95,3 +95,43 @@ def test_rest_and_ws_servers(engine):
     finally:
         rest.shutdown()
         ws_srv.shutdown()
+
+
+def test_beam_search_finds_higher_likelihood_than_greedy(engine):
+    from megatronapp_b200.inference.beam_search import beam_search
+
+    _, model = engine
+    w = GPTInferenceWrapper(model, 4, 32, None)
+    prompt = [3, 7, 11]
+    hyps, scores = beam_search(w, prompt, beam_size=4, tokens_to_generate=6, stop_token=10 ** 6, num_return_gen=2)
+    assert len(hyps) == 2 and hyps[0].shape[0] == 9 and scores[0] >= scores[1]
+    # greedy continuation likelihood under the same model
+    toks = torch.tensor([prompt + [0] * 6])
+    w.prep_model_for_inference(toks)
+    lp, start = 0.0, 0
+    for t in range(3, 9):
+        logit = w.run_one_forward_step(toks, start, t)[:, -1].float()
+        p = torch.log_softmax(logit, -1)
+        nxt = int(p.argmax())
+        lp += float(p[0, nxt])
+        toks[0, t] = nxt
+        start = t
+    assert float(scores[0]) * 6 >= lp - 1e-4       # beam search never does worse than greedy (length penalty 1)
+
+
+def test_openai_completions_endpoint(engine):
+    from megatronapp_b200.inference.server import MegatronServer
+
+    eng, _ = engine
+    srv = MegatronServer(eng)
+    srv.run(port=5093, block=False)
+    time.sleep(0.3)
+    try:
+        req = urllib.request.Request("http://127.0.0.1:5093/v1/completions", method="POST",
+                                     data=json.dumps({"prompt": "5 9 23", "max_tokens": 4, "temperature": 0}).encode(),
+                                     headers={"Content-Type": "application/json"})
+        out = json.loads(urllib.request.urlopen(req).read())
+        assert out["object"] == "text_completion" and len(out["choices"]) == 1
+        assert len(out["choices"][0]["text"].split()) == 4
+    finally:
+        srv.shutdown()
