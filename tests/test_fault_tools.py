@@ -68,3 +68,27 @@ def test_straggler_detector_single_rank():
             sum(range(1000))
     rep = d.report(total_flops=1e9, log_interval=3)
     assert rep.max_rank == 0 and rep.max_elapsed > 0
+
+
+def test_yaml_arguments_and_config_logger(tmp_path):
+    from types import SimpleNamespace
+
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.training.yaml_arguments import args_from_yaml, load_yaml
+    from megatronapp_b200.utils.config_logger import log_config_to_disk
+
+    y = tmp_path / "cfg.yaml"
+    y.write_text("language_model:\n  num_layers: 4\n  hidden_size: 128\nmodel_parallel:\n  tensor_model_parallel_size: 2\nlr: 0.001\n")
+    args = args_from_yaml(str(y), SimpleNamespace(num_layers=1, hidden_size=8, tensor_model_parallel_size=1, lr=0.1))
+    assert (args.num_layers, args.hidden_size, args.tensor_model_parallel_size, args.lr) == (4, 128, 2, 0.001)
+    assert load_yaml(str(y)).language_model.hidden_size == 128
+    import pytest
+
+    y.write_text("bogus_option: 3\n")
+    with pytest.raises(ValueError):
+        args_from_yaml(str(y), SimpleNamespace(num_layers=1))
+    cfg = TransformerConfig(num_layers=1, hidden_size=8, num_attention_heads=2, config_logger_dir=str(tmp_path / "log"))
+    fn = log_config_to_disk(cfg, {"config": cfg, "n": 3}, prefix="TransformerBlock", rank_str="0")
+    import json
+
+    assert json.load(open(fn))["config"]["hidden_size"] == 8
