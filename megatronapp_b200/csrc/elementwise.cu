@@ -234,6 +234,192 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(
   }
 }
 
+// ---- fast path: cols == 8 * VPT * blockDim.x; every thread owns VPT 8-element vectors of a row,
+// gamma/beta live in registers across the persistent row loop and the next row's loads are issued
+// before the reductions of the current row (more bytes in flight per SM -> closer to HBM peak)
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = make_float2(a, b);
+  __syncthreads();
+  float2 t = (l < nw) ? red[l] : make_float2(0.f, 0.f);
+  t.x = warp_sum(t.x);
+  t.y = warp_sum(t.y);
+  return t;
+}
+
+template <typename T, bool kRms, int VPT>
+__global__ void __launch_bounds__(512) ln_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                          const T* __restrict__ beta, T* __restrict__ y,
+                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                          int rows, int cols, float eps, bool zero_centered) {
+  __shared__ float2 red[32];
+  float g[VPT][8], b[VPT][8];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    load8(gamma + v * 8, g[i]);
+    if (beta) load8(beta + v * 8, b[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (zero_centered) g[i][j] += 1.f;
+      if (!beta) b[i][j] = 0.f;
+    }
+  }
+  uint4 nxt[VPT];
+  int row = blockIdx.x;
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      nxt[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * cols + (threadIdx.x + i * blockDim.x) * 8);
+  }
+  const float inv_cols = 1.f / cols;
+  for (; row < rows; row += gridDim.x) {
+    float c[VPT][8];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const uint4 u = nxt[i];
+      float2 p0 = Cvt<T>::up(u.x), p1 = Cvt<T>::up(u.y), p2 = Cvt<T>::up(u.z), p3 = Cvt<T>::up(u.w);
+      c[i][0] = p0.x; c[i][1] = p0.y; c[i][2] = p1.x; c[i][3] = p1.y;
+      c[i][4] = p2.x; c[i][5] = p2.y; c[i][6] = p3.x; c[i][7] = p3.y;
+    }
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i)
+        nxt[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(nrow) * cols + (threadIdx.x + i * blockDim.x) * 8);
+    }
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += c[i][j]; q += c[i][j] * c[i][j]; }
+    float mean = 0.f, rstd;
+    if (kRms) {
+      const float2 t = block_sum2(q, 0.f, red);
+      rstd = rsqrtf(t.x * inv_cols + eps);
+    } else {
+      // two-pass variance on register-resident values (exact, no E[x^2]-mean^2 cancellation)
+      const float2 t = block_sum2(s, 0.f, red);
+      mean = t.x * inv_cols;
+      float d2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = c[i][j] - mean; d2 += d * d; }
+      const float2 t2 = block_sum2(d2, 0.f, red);
+      rstd = rsqrtf(t2.x * inv_cols + eps);
+    }
+    if (threadIdx.x == 0) {
+      if (mean_out) mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    T* yr = y + static_cast<size_t>(row) * cols;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (c[i][j] - mean) * rstd * g[i][j] + b[i][j];
+      store8(yr + (threadIdx.x + i * blockDim.x) * 8, o);
+    }
+  }
+}
+
+template <typename T, bool kRms, int VPT>
+__global__ void __launch_bounds__(512) ln_bwd_fast_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ rstd, T* __restrict__ dx, float* __restrict__ dgamma_partial,
+    float* __restrict__ dbeta_partial, int rows, int cols, bool zero_centered) {
+  __shared__ float2 red[32];
+  float g[VPT][8], dg_acc[VPT][8], db_acc[VPT][8];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    load8(gamma + (threadIdx.x + i * blockDim.x) * 8, g[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (zero_centered) g[i][j] += 1.f;
+      dg_acc[i][j] = 0.f;
+      db_acc[i][j] = 0.f;
+    }
+  }
+  uint4 nx[VPT], nd[VPT];
+  float nmu = 0.f, nrs = 0.f;
+  int row = blockIdx.x;
+  auto prefetch = [&](int r) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const size_t off = static_cast<size_t>(r) * cols + (threadIdx.x + i * blockDim.x) * 8;
+      nx[i] = *reinterpret_cast<const uint4*>(x + off);
+      nd[i] = *reinterpret_cast<const uint4*>(dy + off);
+    }
+    nmu = kRms ? 0.f : mean[r];
+    nrs = rstd[r];
+  };
+  if (row < rows) prefetch(row);
+  const float inv_cols = 1.f / cols;
+  for (; row < rows; row += gridDim.x) {
+    float xh[VPT][8], gd[VPT][8];
+    const float mu = nmu, rs = nrs;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const uint4 ux = nx[i], ud = nd[i];
+      const float2 x0 = Cvt<T>::up(ux.x), x1 = Cvt<T>::up(ux.y), x2 = Cvt<T>::up(ux.z), x3 = Cvt<T>::up(ux.w);
+      const float2 d0 = Cvt<T>::up(ud.x), d1 = Cvt<T>::up(ud.y), d2 = Cvt<T>::up(ud.z), d3 = Cvt<T>::up(ud.w);
+      const float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+      const float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xv[j] - mu) * rs;
+        gd[i][j] = g[i][j] * dv[j];
+        s1 += gd[i][j];
+        s2 += gd[i][j] * xh[i][j];
+        dg_acc[i][j] += dv[j] * xh[i][j];
+        db_acc[i][j] += dv[j];
+      }
+    }
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) prefetch(nrow);
+    const float2 t = block_sum2(s1, s2, red);
+    const float m1 = kRms ? 0.f : t.x * inv_cols, m2 = t.y * inv_cols;
+    T* dxr = dx + static_cast<size_t>(row) * cols;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rs * (gd[i][j] - m1 - xh[i][j] * m2);
+      store8(dxr + (threadIdx.x + i * blockDim.x) * 8, o);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    float* pg = dgamma_partial + static_cast<size_t>(blockIdx.x) * cols + v * 8;
+    *reinterpret_cast<float4*>(pg) = make_float4(dg_acc[i][0], dg_acc[i][1], dg_acc[i][2], dg_acc[i][3]);
+    *reinterpret_cast<float4*>(pg + 4) = make_float4(dg_acc[i][4], dg_acc[i][5], dg_acc[i][6], dg_acc[i][7]);
+    if (dbeta_partial) {
+      float* pb = dbeta_partial + static_cast<size_t>(blockIdx.x) * cols + v * 8;
+      *reinterpret_cast<float4*>(pb) = make_float4(db_acc[i][0], db_acc[i][1], db_acc[i][2], db_acc[i][3]);
+      *reinterpret_cast<float4*>(pb + 4) = make_float4(db_acc[i][4], db_acc[i][5], db_acc[i][6], db_acc[i][7]);
+    }
+  }
+}
+
+// vectors-per-thread / block size for the fast path; vpt = 0 -> generic kernels
+static inline void ln_fast_shape(int cols, int& vpt, int& threads) {
+  vpt = 0; threads = 0;
+  if (cols % 8) return;
+  const int nvec = cols / 8;
+  for (int v : {1, 2, 4}) {
+    if (nvec % v == 0) {
+      const int t = nvec / v;
+      if (t <= 512 && t % 32 == 0) { vpt = v; threads = t; return; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512) ln_bwd_finalize_kernel(const float* __restrict__ pg, const float* __restrict__ pb,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int n_partial, int cols, bool accumulate) {
@@ -717,6 +903,23 @@ int layernorm_bwd_partials(int rows) { return rows < 296 ? rows : 296; }
 void layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
                    float* rstd, int rows, int cols, float eps, bool rms, bool zero_centered,
                    bool is_bf16, cudaStream_t s) {
+  int vpt, threads;
+  ln_fast_shape(cols, vpt, threads);
+  if (vpt) {
+    // enough CTAs to fill every SM to its register/thread limit; rows are grid-strided
+    const int per_sm = 2048 / threads > 4 ? 4 : (2048 / threads < 1 ? 1 : 2048 / threads);
+    const int grid = rows < 148 * per_sm ? rows : 148 * per_sm;
+#define LN_FWD_FAST(V)                                                                                     \
+    DISPATCH_16(is_bf16, {                                                                                 \
+      if (rms) ln_fwd_fast_kernel<T, true, V><<<grid, threads, 0, s>>>((const T*)x, (const T*)gamma,      \
+               (const T*)beta, (T*)y, mean, rstd, rows, cols, eps, zero_centered);                        \
+      else ln_fwd_fast_kernel<T, false, V><<<grid, threads, 0, s>>>((const T*)x, (const T*)gamma,         \
+               (const T*)beta, (T*)y, mean, rstd, rows, cols, eps, zero_centered);                        \
+    })
+    if (vpt == 1) { LN_FWD_FAST(1); } else if (vpt == 2) { LN_FWD_FAST(2); } else { LN_FWD_FAST(4); }
+#undef LN_FWD_FAST
+    return;
+  }
   const int grid = rows < 148 * 8 ? rows : 148 * 8;
   DISPATCH_16(is_bf16, {
     if (rms)
@@ -732,6 +935,22 @@ void layernorm_bwd(const void* dy, const void* x, const void* gamma, const float
                    const float* rstd, void* dx, float* dgamma_partial, float* dbeta_partial,
                    int rows, int cols, bool rms, bool zero_centered, bool is_bf16, int n_partial,
                    cudaStream_t s) {
+  int vpt, threads;
+  ln_fast_shape(cols, vpt, threads);
+  if (vpt == 1 || vpt == 2) {   // 4 vectors per thread would spill under the 512-thread register cap
+#define LN_BWD_FAST(V)                                                                                     \
+    DISPATCH_16(is_bf16, {                                                                                 \
+      if (rms) ln_bwd_fast_kernel<T, true, V><<<n_partial, threads, 0, s>>>((const T*)dy, (const T*)x,    \
+               (const T*)gamma, mean, rstd, (T*)dx, dgamma_partial, dbeta_partial, rows, cols,            \
+               zero_centered);                                                                            \
+      else ln_bwd_fast_kernel<T, false, V><<<n_partial, threads, 0, s>>>((const T*)dy, (const T*)x,       \
+               (const T*)gamma, mean, rstd, (T*)dx, dgamma_partial, dbeta_partial, rows, cols,            \
+               zero_centered);                                                                            \
+    })
+    if (vpt == 1) { LN_BWD_FAST(1); } else { LN_BWD_FAST(2); }
+#undef LN_BWD_FAST
+    return;
+  }
   DISPATCH_16(is_bf16, {
     if (rms)
       ln_bwd_kernel<T, true><<<n_partial, kLnThreads, 0, s>>>((const T*)dy, (const T*)x, (const T*)gamma,
