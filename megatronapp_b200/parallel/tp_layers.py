@@ -109,9 +109,10 @@ def _init_weight(weight, init_method, partition_dim, stride=1, is_expert=False):
 
 class _ColumnParallelFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, sequence_parallel, fuse_wgrad, allreduce_dgrad):
+    def forward(ctx, x, weight, bias, sequence_parallel, fuse_wgrad, allreduce_dgrad, act=0):
         ctx.sp, ctx.fuse_wgrad, ctx.allreduce_dgrad = sequence_parallel, fuse_wgrad, allreduce_dgrad
         ctx.has_bias = bias is not None
+        ctx.act = act
         ctx.x_shape = x.shape
         x2 = x.reshape(-1, x.shape[-1])
         tp = ps.get_tensor_model_parallel_world_size()
@@ -127,18 +128,30 @@ class _ColumnParallelFn(torch.autograd.Function):
                 out = ops.gemm(total, weight, bias=bias)
             out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
         else:
-            out = ops.gemm(x2, weight, bias=bias)
+            pre = None
+            if act:
+                # bias + tanh-GELU applied in the GEMM epilogue; the pre-activation is kept for backward
+                pre = torch.empty(x2.shape[0], weight.shape[0], dtype=x2.dtype, device=x2.device)
+            out = ops.gemm(x2, weight, bias=bias, act=act, out_pre=pre)
             out_shape = tuple(x.shape[:-1]) + (weight.shape[0],)
+            if act:
+                ctx.save_for_backward(x2, weight, pre)
+                return out.view(out_shape)
         ctx.save_for_backward(x2, weight)
         return out.view(out_shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, weight = ctx.saved_tensors
+        if ctx.act:
+            x2, weight, pre = ctx.saved_tensors
+        else:
+            x2, weight = ctx.saved_tensors
         tp = ps.get_tensor_model_parallel_world_size()
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
+        if ctx.act:
+            dy2 = ops.ext().bias_gelu_bwd(dy2, pre, None)    # d(pre); the bias is already inside ``pre``
         handle = None
         total = x2
         group = ps.get_tensor_model_parallel_group()
@@ -170,7 +183,7 @@ class _ColumnParallelFn(torch.autograd.Function):
             db = ops.bias_grad(dy2).to(dy.dtype)
         if ar_handle is not None:
             ar_handle.wait()
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 def linear_with_grad_accumulation_and_async_allreduce(
@@ -230,7 +243,14 @@ class ColumnParallelLinear(nn.Module):
         self.gradient_accumulation_fusion = config.gradient_accumulation_fusion
         self.layer_number = None
 
-    def forward(self, input_, weight=None, runtime_gather_output=None):
+    def can_fuse_gelu(self, input_) -> bool:
+        """bias + tanh-GELU can ride in the GEMM epilogue (not on the fused all-gather path, whose
+        launcher has no second output for the pre-activation)."""
+        return (input_.is_cuda and input_.dtype in (torch.bfloat16, torch.float16) and not self.gather_output
+                and not (self.sequence_parallel and self.tp_size > 1) and self.weight is not None
+                and self.weight.shape[0] % 64 == 0 and not self.explicit_expert_comm)
+
+    def forward(self, input_, weight=None, runtime_gather_output=None, fused_gelu: bool = False):
         if weight is None:
             if self.weight is None:
                 raise RuntimeError("weight was not allocated and none was passed to forward()")
@@ -241,6 +261,11 @@ class ColumnParallelLinear(nn.Module):
                 raise RuntimeError(f"supplied weight has shape {tuple(weight.shape)}, expected {exp}")
         weight = scope_hooks.perturb_weight(weight, self)  # MegaScope "storage" perturbation
         bias = self.bias if not self.skip_bias_add else None
+        if fused_gelu:
+            out = _ColumnParallelFn.apply(input_, weight, self.bias, self.sequence_parallel,
+                                          self.gradient_accumulation_fusion and weight.requires_grad,
+                                          self.allreduce_dgrad, 1)
+            return out, None
         out = _ColumnParallelFn.apply(input_, weight, bias, self.sequence_parallel,
                                       self.gradient_accumulation_fusion and weight.requires_grad,
                                       self.allreduce_dgrad)

@@ -65,9 +65,15 @@ class MLP(MegatronModule):
 
     def forward(self, hidden_states, per_token_scale=None):
         with _scope("MLP.forward"):
-            inter, bias = self.linear_fc1(hidden_states)
-            scope_hooks.tik_tensor(4, self.layer_number, inter)
-            inter = self._activation(inter, bias)
+            is_gelu = (not self.config.gated_linear_unit and
+                       (self.activation_func in (F.gelu,) or getattr(self.activation_func, "__name__", "") == "_gelu"))
+            if (is_gelu and hasattr(self.linear_fc1, "can_fuse_gelu") and self.linear_fc1.can_fuse_gelu(hidden_states)
+                    and not scope_hooks.wants(4, self.layer_number)):
+                inter, _ = self.linear_fc1(hidden_states, fused_gelu=True)   # bias + GELU in the GEMM epilogue
+            else:
+                inter, bias = self.linear_fc1(hidden_states)
+                scope_hooks.tik_tensor(4, self.layer_number, inter)
+                inter = self._activation(inter, bias)
             if per_token_scale is not None:
                 inter = inter * per_token_scale.unsqueeze(-1).to(inter.dtype)
             out, out_bias = self.linear_fc2(inter)
