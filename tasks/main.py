@@ -1,0 +1,29 @@
+"""Downstream-task entry point (reference ``tasks/main.py``): ``--task {WIKITEXT103, LAMBADA}`` run the
+zero-shot GPT evaluations; the model / parallel flags are the normal training arguments."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def get_tasks_args(parser):
+    g = parser.add_argument_group("tasks")
+    g.add_argument("--task", type=str, required=True, help="WIKITEXT103 | LAMBADA")
+    g.add_argument("--valid-data", nargs="*", default=None, help="path(s) to the evaluation text")
+    g.add_argument("--overlapping-eval", type=int, default=32, help="sliding window stride for perplexity")
+    g.add_argument("--strict-lambada", action="store_true", help="whole-word LAMBADA (all word pieces must match)")
+    g.add_argument("--eval-micro-batch-size", type=int, default=None)
+    return parser
+
+
+if __name__ == "__main__":
+    from megatronapp_b200.training.global_vars import get_args
+    from megatronapp_b200.training.initialize import initialize_megatron
+
+    initialize_megatron(extra_args_provider=get_tasks_args)
+    args = get_args()
+    if args.task in ("LAMBADA", "WIKITEXT103"):
+        from tasks.zeroshot_gpt.evaluate import main
+    else:
+        raise NotImplementedError(f"Task {args.task} is not implemented.")
+    main()

@@ -1,0 +1,55 @@
+"""Zero-shot evaluation plumbing (tasks/zeroshot_gpt)."""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from tasks.zeroshot_gpt.evaluate import LMDataset, build_dataset, evaluate, summarize, wikitext_detokenizer  # noqa: E402
+
+
+class _Tok:
+    eod = 0
+
+    def tokenize(self, text):
+        return [1 + (sum(map(ord, w)) % 60) for w in text.split()]
+
+
+def _model():
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch")
+    return GPTModel(cfg, get_gpt_layer_local_spec(), 64, 16)
+
+
+def test_sliding_window_scores_every_token_once():
+    ds = LMDataset(list(range(1, 60)), seq_len=16, pad_idx=0, num_original_tokens=50, num_tokenized_tokens=59,
+                   overlapping_eval=4)
+    scored = sum(float(ds[i]["pad_mask"].sum()) for i in range(len(ds)))
+    assert scored == 58           # every target token exactly once
+    assert wikitext_detokenizer("a @-@ b , c . ") == "a-b, c. "
+
+
+def test_wikitext_perplexity_and_lambada_accuracy(tmp_path):
+    m = _model()
+    p = tmp_path / "wiki.txt"
+    p.write_text(" ".join(f"w{i % 17}" for i in range(200)))
+    ds = build_dataset("WIKITEXT103", str(p), _Tok(), 16, overlapping_eval=8)
+    out = evaluate(m, torch.utils.data.DataLoader(ds, batch_size=4), "loss")
+    res = summarize("WIKITEXT103", out, ds)
+    assert 3.0 < res["avg loss"] < 5.5 and abs(res["ppl"] - math.exp(res["avg loss"])) < 1e-6   # ~ln(64) at init
+    lam = tmp_path / "lambada.jsonl"
+    lam.write_text("\n".join(json.dumps({"text": " ".join(f"x{j}" for j in range(i + 5))}) for i in range(6)))
+    ds2 = build_dataset("LAMBADA", str(lam), _Tok(), 16)
+    acc = summarize("LAMBADA", evaluate(m, torch.utils.data.DataLoader(ds2, batch_size=3), "accuracy"), ds2)
+    assert acc["total examples"] == 6 and 0.0 <= acc["avg accuracy"] <= 1.0
