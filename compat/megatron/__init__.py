@@ -2,6 +2,10 @@
 B200-native implementation, so existing user scripts (``from megatron.core import mpu,
 tensor_parallel``, ``from megatron.training import get_args, pretrain`` ...) keep working.
 
+It lives under ``compat/`` (add that directory to ``PYTHONPATH``) rather than at the repository root so
+that it never shadows a real Megatron checkout -- in particular the unmodified reference that the
+benchmark's ``--impl reference`` arm imports from ``baseline/_ref``.
+
 Only aliases live here -- no logic.  ``import megatron`` installs lazy module aliases in
 ``sys.modules``; the real code is in ``megatronapp_b200``.
 """

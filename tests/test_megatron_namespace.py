@@ -1,4 +1,8 @@
-"""The ``megatron`` compatibility namespace resolves the reference's import paths."""
+"""The ``megatron`` compatibility namespace (``compat/`` on PYTHONPATH) resolves the reference's import paths."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat"))
 
 
 def test_reference_import_paths_resolve():
