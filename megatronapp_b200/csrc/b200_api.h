@@ -62,6 +62,30 @@ bool gemm2_supported(const GemmArgs& args);
 int gemm2_bf16(const GemmArgs& args);
 const char* gemm2_last_error();
 
+// ---------------------------------------------------------------- fp8 (gemm_fp8_sm100.cu)
+struct Fp8GemmArgs {
+  // D[M,N] = scale_a_inv * scale_b_inv * (A8[M,K] . B8[N,K]^T) (+ bias); operands one byte / element
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* D = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0, ldd = 0;
+  bool a_e5m2 = false, b_e5m2 = false;
+  const float* scale_a_inv = nullptr;   // device scalars
+  const float* scale_b_inv = nullptr;
+  const void* bias = nullptr;           // optional 16-bit [N] (store epilogue only)
+  bool out_bf16 = true;                 // 16-bit output dtype (store epilogue)
+  bool accum_f32 = false;               // D is fp32 and receives "+=" (wgrad into main_grad)
+  cudaStream_t stream = nullptr;
+};
+int gemm_fp8(const Fp8GemmArgs& a);
+const char* gemm_fp8_last_error();
+void fp8_amax(const void* x, int64_t n, bool is_bf16, float* amax, cudaStream_t s);
+void fp8_scale_from_amax(const float* amax, bool e5m2, int margin, float* scale, float* scale_inv, cudaStream_t s);
+// q [rows, cols] and (optionally) qt [cols, rows] fp8 copies of a 16-bit matrix, x * scale
+void fp8_cast_transpose(const void* x, const float* scale, void* q, void* qt, int rows, int cols, bool is_bf16,
+                        bool e5m2, cudaStream_t s);
+
 // ---------------------------------------------------------------- elementwise / norm
 void layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
                    float* rstd, int rows, int cols, float eps, bool rms, bool zero_centered,

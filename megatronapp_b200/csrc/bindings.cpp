@@ -334,6 +334,54 @@ Tensor chunk_mean(const Tensor& x, int64_t pixels) {
   return out;
 }
 
+// ---------------------------------------------------------------- fp8
+// Quantise a 16-bit matrix with current (tensor-wise) scaling entirely on the device:
+// amax -> scale -> cast (+ transposed copy).  Returns {q, qt (or empty), scale_inv, amax}.
+std::vector<Tensor> fp8_quantize(const Tensor& x, bool e5m2, bool want_transpose, int64_t margin,
+                                 const c10::optional<Tensor>& amax_in) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.size(1) % 8 == 0, "fp8_quantize expects contiguous [rows, cols], cols % 8 == 0");
+  const int rows = static_cast<int>(x.size(0)), cols = static_cast<int>(x.size(1));
+  auto fopt = x.options().dtype(at::kFloat);
+  Tensor amax = amax_in.has_value() ? amax_in.value() : torch::zeros({1}, fopt);
+  if (!amax_in.has_value()) b200::fp8_amax(x.data_ptr(), x.numel(), is_bf16(x), amax.data_ptr<float>(), cur_stream());
+  auto scales = torch::empty({2}, fopt);
+  b200::fp8_scale_from_amax(amax.data_ptr<float>(), e5m2, static_cast<int>(margin), scales.data_ptr<float>(),
+                            scales.data_ptr<float>() + 1, cur_stream());
+  auto bopt = x.options().dtype(at::kByte);
+  auto q = torch::empty({rows, cols}, bopt);
+  Tensor qt = want_transpose ? torch::empty({cols, rows}, bopt) : torch::empty({0}, bopt);
+  b200::fp8_cast_transpose(x.data_ptr(), scales.data_ptr<float>(), q.data_ptr(), want_transpose ? qt.data_ptr() : nullptr,
+                           rows, cols, is_bf16(x), e5m2, cur_stream());
+  count(3);
+  return {q, qt, scales.slice(0, 1, 2), amax};
+}
+
+// D = sa_inv * sb_inv * A8 @ B8^T (+bias).  ``D`` 16-bit (store) or fp32 (accumulate=true: "+=").
+void gemm_fp8(const Tensor& A8, const Tensor& B8, Tensor& D, const Tensor& sa_inv, const Tensor& sb_inv, bool a_e5m2,
+              bool b_e5m2, const c10::optional<Tensor>& bias, bool accumulate) {
+  c10::cuda::CUDAGuard guard(A8.device());
+  TORCH_CHECK(A8.dim() == 2 && B8.dim() == 2 && A8.size(1) == B8.size(1), "fp8 gemm: A[M,K], B[N,K]");
+  TORCH_CHECK(A8.scalar_type() == at::kByte && B8.scalar_type() == at::kByte, "fp8 operands are uint8 storage");
+  b200::Fp8GemmArgs a;
+  a.A = A8.data_ptr(); a.B = B8.data_ptr(); a.D = D.data_ptr();
+  a.M = static_cast<int>(A8.size(0)); a.N = static_cast<int>(B8.size(0)); a.K = static_cast<int>(A8.size(1));
+  a.lda = static_cast<int>(A8.stride(0)); a.ldb = static_cast<int>(B8.stride(0)); a.ldd = static_cast<int>(D.stride(0));
+  a.a_e5m2 = a_e5m2; a.b_e5m2 = b_e5m2;
+  a.scale_a_inv = sa_inv.data_ptr<float>(); a.scale_b_inv = sb_inv.data_ptr<float>();
+  a.bias = optptr(bias);
+  a.accum_f32 = accumulate;
+  if (accumulate) {
+    TORCH_CHECK(D.scalar_type() == at::kFloat, "accumulate needs an fp32 output");
+  } else {
+    a.out_bf16 = is_bf16(D);
+  }
+  a.stream = cur_stream();
+  int rc = b200::gemm_fp8(a);
+  TORCH_CHECK(rc == 0, "b200 gemm_fp8 failed: ", rc, " ", b200::gemm_fp8_last_error());
+  count();
+}
+
 // ---------------------------------------------------------------- attention
 namespace {
 void check_bhsd(const Tensor& t, const char* name) {
@@ -519,6 +567,8 @@ void reset_launch_count() { g_launches.store(0); }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm);
+  m.def("gemm_fp8", &gemm_fp8);
+  m.def("fp8_quantize", &fp8_quantize);
   m.def("gemm_ag", &gemm_ag);
   m.def("gemm_rs", &gemm_rs);
   m.def("gemm_flags_needed", &b200::gemm_flags_needed);

@@ -1,0 +1,161 @@
+"""FP8 training primitives: device-side tensor-wise quantisation and an fp8 linear layer function whose
+three GEMMs (fprop, dgrad, wgrad) run on the block ``tcgen05.mma.kind::f8f6f4`` kernel.
+
+Parity: reference ``core/fp8_utils.py`` (recipes ``tensorwise`` = current scaling and ``delayed`` =
+amax history, ``get_fp8_context :384-400``; formats ``e4m3`` / ``hybrid`` = E4M3 forward + E5M2 gradients)
+and the TE linear layers it delegates to (``extensions/transformer_engine.py TELinear``).  Everything
+(amax, scale, cast, transposed copies, GEMM, dequantisation) stays on the device -- no host sync.
+
+On CPU (tests) the same arithmetic is emulated with ``torch.float8_*`` dtypes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _native, ext, fallback_counts, have_ext
+
+E4M3_MAX, E5M2_MAX = 448.0, 57344.0
+
+
+@dataclass
+class Fp8Recipe:
+    fmt: str = "hybrid"            # "e4m3" | "hybrid"
+    recipe: str = "tensorwise"     # "tensorwise" (current scaling) | "delayed"
+    margin: int = 0
+    amax_history_len: int = 1
+    amax_compute_algo: str = "most_recent"   # | "max"
+    wgrad: bool = True             # False: keep the weight-gradient GEMM in bf16
+
+
+@dataclass
+class Fp8Meta:
+    """Per-tensor-role delayed-scaling state (amax history) of one linear layer."""
+    history: List[torch.Tensor] = field(default_factory=list)
+
+    def amax_for_scale(self, recipe: Fp8Recipe) -> Optional[torch.Tensor]:
+        if not self.history:
+            return None
+        if recipe.amax_compute_algo == "max":
+            return torch.stack(self.history).max(dim=0).values
+        return self.history[-1]
+
+    def push(self, amax: torch.Tensor, recipe: Fp8Recipe):
+        self.history.append(amax.detach().clone())
+        del self.history[:-max(1, recipe.amax_history_len)]
+
+
+def quantize(x: torch.Tensor, e5m2: bool = False, transpose: bool = False, margin: int = 0,
+             amax: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor, torch.Tensor]:
+    """``x [rows, cols]`` -> ``(q, q_t, scale_inv, amax)``; ``q`` / ``q_t`` are uint8 storage of the fp8
+    values ``x * scale`` with ``scale = fp8_max / amax * 2^-margin`` (``amax`` measured now unless given)."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if _native(x2) and have_ext() and x2.shape[1] % 8 == 0:
+        q, qt, sinv, am = ext().fp8_quantize(x2.contiguous(), e5m2, transpose, margin, amax)
+        return q, (qt if transpose else None), sinv, am
+    if x2.is_cuda:
+        fallback_counts["fp8_quantize"] += 1
+    am = x2.detach().abs().max().float().reshape(1) if amax is None else amax
+    fmax = E5M2_MAX if e5m2 else E4M3_MAX
+    scale = torch.where((am > 0) & torch.isfinite(am), fmax / am * (2.0 ** -margin), torch.ones_like(am))
+    dt = torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn
+    q = (x2.float() * scale).clamp(-fmax, fmax).to(dt).view(torch.uint8)
+    qt = q.t().contiguous() if transpose else None
+    return q, qt, (1.0 / scale).float(), am
+
+
+def dequantize(q: torch.Tensor, scale_inv: torch.Tensor, e5m2: bool = False) -> torch.Tensor:
+    dt = torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn
+    return q.view(dt).float() * scale_inv
+
+
+def gemm_fp8(a8, b8, sa_inv, sb_inv, *, a_e5m2=False, b_e5m2=False, bias=None, out=None, out_dtype=torch.bfloat16,
+             accumulate=False):
+    """``D = sa_inv * sb_inv * A8 @ B8^T (+ bias)``; ``accumulate`` adds into an fp32 ``out``."""
+    M, N = a8.shape[0], b8.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if accumulate else out_dtype, device=a8.device)
+    ok = (a8.is_cuda and have_ext() and a8.shape[1] % 16 == 0 and a8.stride(1) == 1 and b8.stride(1) == 1
+          and a8.stride(0) % 16 == 0 and b8.stride(0) % 16 == 0 and out.stride(1) == 1
+          and out.stride(0) % (4 if accumulate else 8) == 0)
+    if ok:
+        ext().gemm_fp8(a8, b8, out, sa_inv, sb_inv, a_e5m2, b_e5m2, bias, accumulate)
+        return out
+    if a8.is_cuda:
+        fallback_counts["gemm_fp8"] += 1
+    d = dequantize(a8, sa_inv, a_e5m2) @ dequantize(b8, sb_inv, b_e5m2).t()
+    if bias is not None:
+        d = d + bias.float()
+    if accumulate:
+        out.add_(d)
+    else:
+        out.copy_(d.to(out.dtype))
+    return out
+
+
+class _WeightCache:
+    """fp8 (and transposed fp8) copies of a weight, rebuilt only when the parameter changes (once per
+    optimizer step, not per micro-batch)."""
+
+    def __init__(self):
+        self.version, self.data_ptr, self.val = -1, 0, None
+
+    def get(self, w: torch.Tensor, margin: int):
+        if self.val is None or self.version != w._version or self.data_ptr != w.data_ptr():
+            self.val = quantize(w.detach(), False, True, margin)
+            self.version, self.data_ptr = w._version, w.data_ptr()
+        return self.val
+
+
+class Fp8LinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) with fp8 fprop / dgrad / wgrad.  ``weight.main_grad`` (fp32) receives the weight
+    gradient in place when ``fuse_wgrad`` (same contract as ``ops._LinearFn``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, recipe: Fp8Recipe, cache: _WeightCache, fuse_wgrad: bool):
+        x2 = x.reshape(-1, x.shape[-1])
+        x8, x8t, xs, _ = quantize(x2, False, True, recipe.margin)
+        w8, w8t, ws, _ = cache.get(weight, recipe.margin)
+        y = gemm_fp8(x8, w8, xs, ws, bias=bias, out_dtype=x.dtype)
+        ctx.save_for_backward(x8t, xs, w8t, ws, x2 if not recipe.wgrad else None)
+        ctx.recipe, ctx.fuse_wgrad, ctx.weight = recipe, fuse_wgrad, weight
+        ctx.x_shape, ctx.has_bias, ctx.dtype = x.shape, bias is not None, x.dtype
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x8t, xs, w8t, ws, x2 = ctx.saved_tensors
+        rec, weight = ctx.recipe, ctx.weight
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        e5 = rec.fmt == "hybrid"
+        d8, d8t, ds, _ = quantize(dy2, e5, rec.wgrad, rec.margin)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_fp8(d8, w8t, ds, ws, a_e5m2=e5, out_dtype=ctx.dtype).view(ctx.x_shape)     # dy @ W
+        if ctx.needs_input_grad[1]:
+            main = getattr(weight, "main_grad", None)
+            if rec.wgrad:
+                if ctx.fuse_wgrad and main is not None:
+                    gemm_fp8(d8t, x8t, ds, xs, a_e5m2=e5, out=main, accumulate=True)              # main_grad += dy^T @ x
+                    weight.grad_added_to_main_grad = True
+                    hook = getattr(weight, "grad_ready_hook", None)
+                    if hook is not None and getattr(weight, "b200_wgrad_store_first", False):
+                        hook()
+                else:
+                    dw = gemm_fp8(d8t, x8t, ds, xs, a_e5m2=e5, out_dtype=weight.dtype)
+            else:
+                from . import wgrad as _wgrad
+
+                dw = _wgrad(dy2, x2, weight, ctx.fuse_wgrad)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            from . import bias_grad
+
+            db = bias_grad(dy2).to(dy.dtype)
+        return dx, dw, db, None, None, None
+
+
+def fp8_linear(x, weight, bias=None, recipe: Optional[Fp8Recipe] = None, cache: Optional[_WeightCache] = None,
+               fuse_wgrad: bool = False):
+    return Fp8LinearFn.apply(x, weight, bias, recipe or Fp8Recipe(), cache or _WeightCache(), fuse_wgrad)

@@ -191,3 +191,27 @@ def test_llava_splices_image_embeddings():
     assert mask[:, 2:2 + n_img].sum() == 0 and mask[:, 1].sum() == 0 and mask[:, 0].sum() == 2
     (loss * mask).sum().backward()
     assert m.vision_model.conv1.weight.grad.abs().sum() > 0 and m.vision_projection.encoder.linear_fc1.weight.grad is not None
+
+
+def test_fp8_linear_emulation_matches_bf16_within_quantisation_error():
+    """fp8 quantise / GEMM / linear (CPU emulation of the device arithmetic)."""
+    from megatronapp_b200.ops import fp8
+
+    torch.manual_seed(0)
+    x = torch.randn(64, 128, requires_grad=True)
+    w = (torch.randn(96, 128) * 0.1).requires_grad_(True)
+    b = torch.randn(96)
+    q, qt, sinv, am = fp8.quantize(x.detach(), transpose=True)
+    assert q.dtype == torch.uint8 and qt.shape == (128, 64) and abs(float(am) - float(x.abs().max())) < 1e-6
+    assert (fp8.dequantize(q, sinv) - x.detach()).abs().max() < 0.07 * x.detach().abs().max()
+    y = fp8.fp8_linear(x, w, b)
+    ref = x @ w.t() + b
+    assert ((y - ref).abs().max() / ref.abs().max()) < 0.06
+    dy = torch.randn_like(ref)
+    y.backward(dy)
+    gx, gw = x.grad.clone(), w.grad.clone()
+    x.grad = None
+    w.grad = None
+    ref.backward(dy)
+    assert ((gx - x.grad).abs().max() / x.grad.abs().max()) < 0.08
+    assert ((gw - w.grad).abs().max() / w.grad.abs().max()) < 0.08

@@ -384,6 +384,76 @@ def check_attention_perf():
     return res
 
 
+def check_fp8():
+    """fp8 quantise kernels and the kind::f8f6f4 GEMM vs the dequantised fp32 product."""
+    import torch
+    from megatronapp_b200 import ops
+    from megatronapp_b200.ops import fp8
+
+    res = {}
+    for (M, N, K) in [(256, 256, 128), (2048, 4096, 4096), (384, 520, 272), (4096, 1024, 2048)]:
+        torch.manual_seed(M + K)
+        a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.05
+        bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+        key = f"{M}x{N}x{K}"
+        try:
+            a8, a8t, sa, am = fp8.quantize(a, False, True)
+            b8, b8t, sb, _ = fp8.quantize(b, False, True)
+            res[key + "_amax"] = abs(float(am) - float(a.float().abs().max())) / float(a.float().abs().max())
+            ref_q = a.float() * (1.0 / sa)
+            res[key + "_cast"] = _rel_err(fp8.dequantize(a8, sa), ref_q.clamp(-448, 448).to(torch.float8_e4m3fn).float() * sa)
+            res[key + "_transpose"] = float((a8t != a8.t()).float().mean())
+            ref = fp8.dequantize(a8, sa) @ fp8.dequantize(b8, sb).t()
+            out = fp8.gemm_fp8(a8, b8, sa, sb, bias=bias)
+            res[key + "_gemm"] = _rel_err(out, ref + bias.float())
+            acc = torch.randn(M, N, device="cuda", dtype=torch.float32) if N % 4 == 0 else None
+            if acc is not None:
+                want = acc + ref
+                fp8.gemm_fp8(a8, b8, sa, sb, out=acc, accumulate=True)
+                res[key + "_accum"] = _rel_err(acc, want)
+            d = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+            d8, d8t, ds, _ = fp8.quantize(d, True, True)       # E5M2 gradient operand
+            refd = fp8.dequantize(d8, ds, True) @ fp8.dequantize(b8t, sb).t()
+            res[key + "_dgrad_e5m2"] = _rel_err(fp8.gemm_fp8(d8, b8t, ds, sb, a_e5m2=True), refd)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            res[key] = f"EXC {type(e).__name__}: {str(e)[:200]}"
+    # end-to-end linear vs bf16 reference (quantisation-level error)
+    x = torch.randn(2048, 4096, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(4096, 4096, device="cuda", dtype=torch.bfloat16) * 0.02).requires_grad_(True)
+    y = fp8.fp8_linear(x, w)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ref = x.detach().float() @ w.detach().float().t()
+    res["linear_fwd_vs_bf16"] = _rel_err(y, ref)
+    res["linear_dx_vs_bf16"] = _rel_err(x.grad, dy.float() @ w.detach().float())
+    res["linear_dw_vs_bf16"] = _rel_err(w.grad, dy.float().t() @ x.detach().float())
+    res["_fallbacks"] = {k: v for k, v in ops.fallback_counts.items() if "fp8" in k}
+    return res
+
+
+def check_fp8_perf():
+    import torch
+    from megatronapp_b200 import ops
+    from megatronapp_b200.ops import fp8
+
+    res = {}
+    for name, (M, N, K) in {"sq8192": (8192, 8192, 8192), "fc1": (2048, 16384, 4096), "fc1_mbs4": (8192, 16384, 4096)}.items():
+        a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        a8, _, sa, _ = fp8.quantize(a)
+        b8, _, sb, _ = fp8.quantize(b)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        t = _time(lambda: fp8.gemm_fp8(a8, b8, sa, sb, out=out))
+        res[name + "_fp8_tflops"] = round(2.0 * M * N * K / t / 1e9, 1)
+        t = _time(lambda: ops.gemm(a, b, out=out))
+        res[name + "_bf16_tflops"] = round(2.0 * M * N * K / t / 1e9, 1)
+        t = _time(lambda: fp8.quantize(a, False, True))
+        res[name + "_quantize_GBs"] = round(a.numel() * 2 * 2 / t / 1e6, 1)    # amax read + cast read
+    return res
+
+
 def check_smoke():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as ge
@@ -424,10 +494,11 @@ CHECKS = {
     "elementwise": check_elementwise,
     "attention_fwd": check_attention_fwd,
     "attention": check_attention,
+    "fp8": check_fp8,
     "model_parity": check_model_parity,
     "smoke": check_smoke,
 }
-PERF = {"gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
+PERF = {"fp8_perf": check_fp8_perf, "gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
 
 
 def main():
