@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from . import state as ps
 from .mappings import (
+    gather_from_sequence_parallel_region,
     _gather_along_first_dim,
     _reduce_scatter_along_first_dim,
     copy_to_tensor_model_parallel_region,
@@ -101,6 +102,22 @@ def _init_weight(weight, init_method, partition_dim, stride=1, is_expert=False):
             init_method(weight)
     else:
         init_method(weight)
+
+
+def _fp8_recipe_from_config(config, is_expert: bool = False):
+    """``config.fp8`` in {"e4m3", "hybrid"} turns the linear layers' GEMMs into fp8 (reference
+    ``fp8_utils.get_fp8_context``); the embedding / output layer stay in 16-bit like TE."""
+    fmt = getattr(config, "fp8", None)
+    if not fmt:
+        return None
+    from ..ops.fp8 import Fp8Recipe
+
+    rec = getattr(config, "fp8_recipe", "delayed")
+    return Fp8Recipe(fmt="hybrid" if fmt == "hybrid" else "e4m3", recipe="tensorwise" if rec != "delayed" else "delayed",
+                     margin=int(getattr(config, "fp8_margin", 0) or 0),
+                     amax_history_len=int(getattr(config, "fp8_amax_history_len", 1) or 1),
+                     amax_compute_algo=getattr(config, "fp8_amax_compute_algo", "most_recent"),
+                     wgrad=bool(getattr(config, "fp8_wgrad", True)))
 
 
 # ---------------------------------------------------------------------------
@@ -242,11 +259,30 @@ class ColumnParallelLinear(nn.Module):
             and not self.explicit_expert_comm
         self.gradient_accumulation_fusion = config.gradient_accumulation_fusion
         self.layer_number = None
+        self.fp8_recipe = None if skip_weight_param_allocation else _fp8_recipe_from_config(config, is_expert)
+        self._fp8_cache = None
+
+    def _fp8_forward(self, input_, weight):
+        """fp8 GEMMs around explicit TP collectives (all-gather / copy in front, nothing behind)."""
+        from ..ops.fp8 import _WeightCache, fp8_linear
+
+        if self._fp8_cache is None:
+            self._fp8_cache = _WeightCache()
+        if self.sequence_parallel and self.tp_size > 1:
+            x = gather_from_sequence_parallel_region(input_, tensor_parallel_output_grad=True)
+        elif self.allreduce_dgrad:
+            x = copy_to_tensor_model_parallel_region(input_)
+        else:
+            x = input_
+        bias = self.bias if not self.skip_bias_add else None
+        return fp8_linear(x, weight, bias, self.fp8_recipe, self._fp8_cache,
+                          self.gradient_accumulation_fusion and weight.requires_grad)
 
     def can_fuse_gelu(self, input_) -> bool:
         """bias + tanh-GELU can ride in the GEMM epilogue (not on the fused all-gather path, whose
         launcher has no second output for the pre-activation)."""
-        return (input_.is_cuda and input_.dtype in (torch.bfloat16, torch.float16) and not self.gather_output
+        return (self.fp8_recipe is None and input_.is_cuda and input_.dtype in (torch.bfloat16, torch.float16)
+                and not self.gather_output
                 and not (self.sequence_parallel and self.tp_size > 1) and self.weight is not None
                 and self.weight.shape[0] % 64 == 0 and not self.explicit_expert_comm)
 
@@ -260,6 +296,13 @@ class ColumnParallelLinear(nn.Module):
             if tuple(weight.shape) != exp:
                 raise RuntimeError(f"supplied weight has shape {tuple(weight.shape)}, expected {exp}")
         weight = scope_hooks.perturb_weight(weight, self)  # MegaScope "storage" perturbation
+        if self.fp8_recipe is not None and not fused_gelu and weight is self.weight and input_.shape[-1] % 16 == 0 \
+                and weight.shape[0] % 16 == 0 and not self.explicit_expert_comm:
+            out = self._fp8_forward(input_, weight)
+            gather = self.gather_output if runtime_gather_output is None else runtime_gather_output
+            if gather:
+                out = gather_from_tensor_model_parallel_region(out)
+            return out, (self.bias if self.skip_bias_add else None)
         bias = self.bias if not self.skip_bias_add else None
         if fused_gelu:
             out = _ColumnParallelFn.apply(input_, weight, self.bias, self.sequence_parallel,
@@ -383,11 +426,27 @@ class RowParallelLinear(nn.Module):
         else:
             self.register_parameter("bias", None)
         self.gradient_accumulation_fusion = config.gradient_accumulation_fusion
+        self.fp8_recipe = _fp8_recipe_from_config(config, is_expert)
+        self._fp8_cache = None
 
     def forward(self, input_):
         if not self.input_is_parallel:
             input_ = scatter_to_tensor_model_parallel_region(input_)
         do_reduce = not self.explicit_expert_comm
+        if self.fp8_recipe is not None and input_.shape[-1] % 16 == 0 and self.weight.shape[0] % 16 == 0 \
+                and not self.explicit_expert_comm:
+            from ..ops.fp8 import _WeightCache, fp8_linear
+
+            if self._fp8_cache is None:
+                self._fp8_cache = _WeightCache()
+            out = fp8_linear(input_, self.weight, None, self.fp8_recipe, self._fp8_cache,
+                             self.gradient_accumulation_fusion and self.weight.requires_grad)
+            if self.tp_size > 1:
+                out = reduce_scatter_to_sequence_parallel_region(out) if self.sequence_parallel \
+                    else reduce_from_tensor_model_parallel_region(out)
+            if not self.skip_bias_add:
+                return (out + self.bias if self.bias is not None else out), None
+            return out, self.bias
         out = _RowParallelFn.apply(input_, self.weight, self.sequence_parallel and do_reduce,
                                    self.gradient_accumulation_fusion and self.weight.requires_grad, do_reduce)
         if not self.skip_bias_add:
