@@ -5,7 +5,7 @@
 N > 1 is launched by the driver through ``torch.distributed.run`` (one rank per GPU, NCCL).
 Layout per N (BASELINE.json config #2 is the N=8 row): 1 -> TP1, 2 -> TP2+SP, 4 -> TP4+SP,
 8 -> TP4 x PP2 + SP.  Weak scaling: ``global_batch = 8 * N`` sequences of 2048 tokens,
-micro-batch 1.  Synthetic tokens, random-init weights, bf16 compute, fp32 main grads + Adam.
+micro-batch = TP degree (same per-GPU GEMM shapes at every N).  Synthetic tokens, random-init weights, bf16 compute, fp32 main grads + Adam.
 
 Timed region = exactly K optimizer steps (forward + backward + grad finalize + clip + Adam),
 bracketed by barrier + ``cuda.synchronize``, measured with CUDA events, MAX over ranks.
@@ -162,6 +162,32 @@ def run_own(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    scope_ms = None
+    if args.trace_scopes:
+        # one extra (untimed) step under the MegaScan tracer: per-scope device time on this rank
+        from megatronapp_b200.scan.tracer import get_tracer
+
+        tr = get_tracer()
+        tr.configure(True, trace_dir="/tmp/b200_bench_trace", interval=1, continuous_iterations=1)
+        tr.log = lambda: None
+        tr.iteration_begin(0)
+        train_step(state, dev_batches, sync_loss=False)
+        tr.iteration_end()
+        tot, cnt, stack = {}, {}, []
+        for r in tr._records:
+            if r["ph"] == "B":
+                stack.append(r)
+            elif r["ph"] == "E":
+                for k in range(len(stack) - 1, -1, -1):
+                    if stack[k]["name"] == r["name"]:
+                        b = stack.pop(k)
+                        tot[r["name"]] = tot.get(r["name"], 0.0) + (r["rel_ts"] - b["rel_ts"]) / 1e6
+                        cnt[r["name"]] = cnt.get(r["name"], 0) + 1
+                        break
+        scope_ms = {k: {"ms": round(v, 3), "calls": cnt[k]} for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
+        tr.configure(False)
+        barrier()
+    last_loss = _finite_from_any_rank(last_loss, world)
     t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -191,10 +217,28 @@ def run_own(args):
             "library_fallbacks": dict(ops.fallback_counts),
             "tflops_per_gpu": 6.0 * _param_count(L, H, F, vocab) * tokens / (ms / 1e3) / 1e12 / args.gpus,
         }
+        if scope_ms is not None:
+            out["rank0_scope_ms_one_step"] = scope_ms
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _finite_from_any_rank(x, world):
+    """The loss lives on the last pipeline stage; rank 0 prints, so fetch a finite copy."""
+    import math
+
+    import torch.distributed as dist
+
+    if world <= 1:
+        return x
+    vals = [None] * world
+    dist.all_gather_object(vals, x)
+    for v in reversed(vals):
+        if v is not None and isinstance(v, float) and math.isfinite(v):
+            return v
+    return x
 
 
 def _param_count(L, H, F, V):
@@ -213,6 +257,7 @@ def main():
     ap.add_argument("--microbatches-per-gpu", type=int, default=8)
     ap.add_argument("--tp", type=int, default=None)
     ap.add_argument("--no-fused-tp-comm", action="store_true", help="NCCL collectives instead of fused AG/RS GEMMs")
+    ap.add_argument("--trace-scopes", action="store_true", help="add one untimed traced step; per-scope device ms in the JSON")
     ap.add_argument("--fused-rs", action="store_true", help="also fuse GEMM->reduce-scatter (default: AG->GEMM only)")
     args = ap.parse_args()
     if args.fused_rs:

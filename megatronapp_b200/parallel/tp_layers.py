@@ -177,15 +177,21 @@ class _ColumnParallelFn(torch.autograd.Function):
             total = torch.empty((x2.shape[0] * tp, x2.shape[1]), dtype=x2.dtype, device=x2.device)
             handle = dist.all_gather_into_tensor(total, x2, group=group, async_op=True)
         dx = None
-        ar_handle = None
+        ar_handle = rs_handle = None
         if ctx.needs_input_grad[0]:
             if ctx.sp and tp > 1:
                 if ctx.fused and _FUSED_COMM.use_fused_rs and _fusable(dy2.shape[0], dy2, weight):
                     with _scope("gemm_rs_dgrad", data=dy2.shape[0] * weight.shape[1] * 2):
                         dx = _FUSED_COMM.gemm_rs(dy2, weight, b_mn=True)
                 else:
+                    # dgrad reduce-scatter runs on the NCCL stream underneath the wgrad GEMM
+                    # (reference layers.py:496-507,548-552)
                     dfull = ops.gemm(dy2, weight, b_mn=True)
-                    dx = _reduce_scatter_along_first_dim(dfull)
+                    dx = torch.empty((dfull.shape[0] // tp, dfull.shape[1]), dtype=dfull.dtype, device=dfull.device)
+                    if dfull.is_cuda and dist.get_backend(group) != "gloo":
+                        rs_handle = dist.reduce_scatter_tensor(dx, dfull, group=group, async_op=True)
+                    else:
+                        dx = _reduce_scatter_along_first_dim(dfull)
             else:
                 dx = ops.gemm(dy2, weight, b_mn=True)
                 if ctx.allreduce_dgrad and tp > 1:
@@ -200,6 +206,8 @@ class _ColumnParallelFn(torch.autograd.Function):
             db = ops.bias_grad(dy2).to(dy.dtype)
         if ar_handle is not None:
             ar_handle.wait()
+        if rs_handle is not None:
+            rs_handle.wait()
         return dx, dw, db, None, None, None, None
 
 
