@@ -83,3 +83,49 @@ def test_core_reshard_roundtrip(tmp_path):
     conv.main(["--loader", "core", "--saver", "core", "--load-dir", a, "--save-dir", b])
     again = conv.load_core(b)
     assert all(torch.equal(again["weights"][k], v) for k, v in ck["weights"].items())
+
+
+def test_trtllm_export_layout(tmp_path):
+    """TRT-LLM export: [q|k|v] regrouping, gated-MLP split, TP sharding, config."""
+    from types import SimpleNamespace
+
+    from megatronapp_b200.export import TRTLLMHelper, export_trtllm_checkpoint
+
+    _, d = _tiny_hf_llama(str(tmp_path))
+    ck = conv.load_hf_llama(d)
+    c = ck["config"]
+    cfg = SimpleNamespace(num_layers=c["num_layers"], hidden_size=c["hidden_size"], num_attention_heads=c["num_attention_heads"],
+                          num_query_groups=c["num_query_groups"], kv_channels=c["kv_channels"], ffn_hidden_size=c["ffn_hidden_size"],
+                          gated_linear_unit=True, layernorm_epsilon=1e-5, add_bias_linear=False, num_moe_experts=None,
+                          moe_router_topk=2)
+    h = TRTLLMHelper(cfg, model_type="llama", activation="silu")
+    out = export_trtllm_checkpoint(h, ck["weights"], str(tmp_path / "trt"), 256, export_tensor_parallel_size=2, dtype=torch.float32)
+    import json
+
+    conf = json.load(open(os.path.join(out, "config.json")))
+    assert conf["architecture"] == "LlamaForCausalLM" and conf["mapping"]["tp_size"] == 2 and conf["num_key_value_heads"] == 2
+    full = h.convert(ck["weights"], torch.float32)
+    hf = torch.load(os.path.join(d, "pytorch_model.bin"))
+    qkv = full["transformer.layers.0.attention.qkv.weight"]
+    assert torch.equal(qkv[:64], hf["model.layers.0.self_attn.q_proj.weight"])
+    assert torch.equal(qkv[64:96], hf["model.layers.0.self_attn.k_proj.weight"])
+    assert torch.equal(full["transformer.layers.1.mlp.gate.weight"], hf["model.layers.1.mlp.up_proj.weight"])
+    s0, s1 = h.shard(full, 2, 0), h.shard(full, 2, 1)
+    assert s0["transformer.layers.0.attention.qkv.weight"].shape == (64, 64)
+    assert torch.equal(torch.cat([s0["transformer.layers.0.mlp.proj.weight"], s1["transformer.layers.0.mlp.proj.weight"]], 1),
+                       full["transformer.layers.0.mlp.proj.weight"])
+
+
+def test_distillation_losses():
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.post_training import DistillationLossBalancer, LogitsKLLoss
+
+    ps.initialize_model_parallel(1, 1)
+    torch.manual_seed(0)
+    s, t = torch.randn(4, 2, 32, requires_grad=True), torch.randn(4, 2, 32)
+    kl = LogitsKLLoss(temperature=2.0)(s, t)
+    ref = torch.nn.functional.kl_div(torch.log_softmax(s / 2, -1), torch.softmax(t / 2, -1), reduction="none").sum(-1) * 4
+    assert torch.allclose(kl, ref, atol=1e-5) and float(LogitsKLLoss()(t, t).abs().max()) < 1e-6
+    total = DistillationLossBalancer(kd_loss_scale=0.5)(torch.tensor(2.0), {"logits": kl})
+    total.backward()
+    assert s.grad is not None and abs(float(total) - (2.0 + 0.5 * float(kl.mean()))) < 1e-5
