@@ -719,6 +719,7 @@ thread_local std::string g_attn_error;
 // 4-D map over a strided [b, h, s, d] view: dims (d, h, b, s); box (64, 1, 1, rows)
 bool make_tmap_bhsd(CUtensorMap* map, const void* base, bool is_bf16, int d, int h, int b, int s, int64_t sh,
                     int64_t sb, int64_t ss, int rows) {
+  ensure_cuda_context();
   EncodeFn fn = encode_fn();
   if (!fn) { g_attn_error = "cuTensorMapEncodeTiled unavailable"; return false; }
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(b),

@@ -6,6 +6,19 @@
 
 namespace b200 {
 
+// cuTensorMapEncodeTiled is a driver-API call and needs a current context on the calling thread.  The
+// autograd worker thread may reach a launcher before any runtime call bound the primary context
+// (notably under CUDA-graph capture, where allocations come from a pre-built pool): bind it once.
+inline void ensure_cuda_context() {
+  thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(dev);
+    bound = true;
+  }
+}
+
 constexpr int kMaxPeers = 8;
 
 enum GemmEpilogue : int {

@@ -365,6 +365,7 @@ thread_local std::string g_err2;
 
 bool tmap2(CUtensorMap* map, const void* base, int dtype /*0 bf16 1 f16 2 f32*/, uint64_t inner, uint64_t outer,
            uint64_t ld, uint32_t bi, uint32_t bo) {
+  ensure_cuda_context();
   auto fn = encode2();
   if (!fn) { g_err2 = "cuTensorMapEncodeTiled unavailable"; return false; }
   const int es = dtype == 2 ? 4 : 2;

@@ -349,6 +349,7 @@ thread_local std::string g_err8;
 
 bool tmap8(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem, uint64_t inner, uint64_t outer,
            uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  ensure_cuda_context();
   EncodeFn8 fn = encode8();
   if (!fn) { g_err8 = "cuTensorMapEncodeTiled unavailable"; return false; }
   cuuint64_t dims[2] = {inner, outer};

@@ -621,6 +621,7 @@ thread_local std::string g_last_error;
 
 bool make_tmap_2d(CUtensorMap* map, const void* base, bool is_bf16, uint64_t inner, uint64_t outer,
                   uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer, bool is_f32 = false) {
+  ensure_cuda_context();
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { g_last_error = "cuTensorMapEncodeTiled unavailable"; return false; }
   cuuint64_t dims[2] = {inner, outer};

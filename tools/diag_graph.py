@@ -15,6 +15,11 @@ def run(case):
     from megatronapp_b200 import ops
 
     dev = "cuda"
+    from megatronapp_b200.parallel import state as _ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed as _seed
+
+    _ps.initialize_model_parallel(1, 1)
+    _seed(1)
     torch.manual_seed(0)
     x = torch.randn(256, 2, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
     w = torch.randn(1024, 512, device=dev, dtype=torch.bfloat16, requires_grad=True)
@@ -57,9 +62,7 @@ def run(case):
             from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
             from megatronapp_b200.transformer.spec_utils import build_module
 
-            if not ps.model_parallel_is_initialized():
-                ps.initialize_model_parallel(1, 1)
-                model_parallel_cuda_manual_seed(1)
+            if not hasattr(run, "layer"):
                 cfg = TransformerConfig(num_layers=1, hidden_size=512, num_attention_heads=4, bf16=True, params_dtype=torch.bfloat16,
                                         hidden_dropout=0.0, attention_dropout=0.0)
                 run.layer = build_module(get_gpt_layer_local_spec(), config=cfg, layer_number=1).cuda()
@@ -92,7 +95,8 @@ if __name__ == "__main__":
     else:
         for c in CASES:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), c], capture_output=True, text=True, timeout=180,
-                               env=dict(os.environ, CUDA_LAUNCH_BLOCKING="1"))
-            tail = [l for l in (p.stdout + p.stderr).splitlines() if l.strip()]
+                               env=dict(os.environ))
+            lines = [l for l in (p.stdout + p.stderr).splitlines() if l.strip()]
+            keep = [l for l in lines if " OK" in l or "Error" in l or "error" in l][:6]
             status = "OK" if p.returncode == 0 else "FAIL"
-            print(f"[{status}] {c}: " + " | ".join(tail[-3:])[:600], flush=True)
+            print(f"[{status}] {c}: " + " | ".join(keep)[:700], flush=True)
