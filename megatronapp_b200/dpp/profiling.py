@@ -28,7 +28,40 @@ def load_trace(path: str) -> List[dict]:
         return benchmark_to_chrome_trace(read_benchmark_dir(path))
     with open(path) as f:
         data = json.load(f)
-    return data["traceEvents"] if isinstance(data, dict) else data
+    events = data["traceEvents"] if isinstance(data, dict) else data
+    return normalize_marker_trace(events)
+
+
+def normalize_marker_trace(events: List[dict]) -> List[dict]:
+    """The reference's DPP tracer (``core/trace.py``) writes B/E pairs plus ``iteration begin`` /
+    ``iteration end`` instant markers instead of complete events; convert that dialect (its committed
+    ``profiling/*-aggregated.json`` files) into ``X`` events with one ``iteration`` span per rank."""
+    if not any(e.get("name") == "iteration begin" for e in events):
+        return events
+    out: List[dict] = []
+    open_ev = {}
+    begins = {}
+    for e in sorted(events, key=lambda x: x["ts"]):
+        pid, name, ph = e.get("pid", 0), e.get("name"), e.get("ph")
+        if name == "iteration begin":
+            begins[pid] = e
+        elif name == "iteration end":
+            b = begins.pop(pid, None)
+            if b is not None:
+                out.append({"name": "iteration", "ph": "X", "ts": b["ts"], "dur": e["ts"] - b["ts"], "pid": pid,
+                            "tid": 0, "args": dict(b.get("args", {}))})
+        elif ph == "B":
+            open_ev.setdefault((pid, name), []).append(e)
+        elif ph == "E":
+            st = open_ev.get((pid, name))
+            if st:
+                b = st.pop()
+                out.append({"name": name, "ph": "X", "ts": b["ts"], "dur": e["ts"] - b["ts"], "pid": pid, "tid": 0,
+                            "args": {**b.get("args", {}), **e.get("args", {})}})
+        else:
+            out.append(dict(e))
+    out.sort(key=lambda x: x["ts"])
+    return out
 
 
 def _union_length(intervals):

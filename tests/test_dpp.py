@@ -73,3 +73,24 @@ def test_dpp_profiling_metrics():
     assert abs(r["ranks"][0]["reduce_window_ms"] - 0.2) < 1e-9 and abs(r["ranks"][1]["reduce_window_ms"] - 0.15) < 1e-9
     assert abs(r["ranks"][0]["computing_ratio"] - 600.0 / 900.0) < 1e-9
     assert abs(r["ranks"][0]["sending_ratio"] - 0.05) < 1e-9
+
+
+def test_reference_committed_traces_reproduce_baseline_numbers():
+    """The reference's committed DPP traces (fixtures, read-only) through our analysis toolkit reproduce the
+    iteration times recorded in BASELINE.md section A (722.2 ms static interleaved vs 954.7 ms MegaDPP)."""
+    import os
+
+    import pytest
+
+    from megatronapp_b200.dpp.profiling import compare
+
+    base = "/root/reference/profiling"
+    a, b = (os.path.join(base, f"data-1-pipeline-4-tensor-1-{k}-aggregated.json") for k in ("pp", "dpp"))
+    if not (os.path.exists(a) and os.path.exists(b)):
+        pytest.skip("reference traces not mounted")
+    r = compare(a, b, skip_first=1)
+    assert abs(r["static"]["iteration_ms"] - 722.2) < 1.5, r["static"]["iteration_ms"]
+    assert abs(r["dpp"]["iteration_ms"] - 954.7) < 1.5, r["dpp"]["iteration_ms"]
+    assert 0.74 < r["dpp_speedup"] < 0.78                      # the reference's DPP is 1.32x slower
+    rw = [r["static"]["ranks"][k]["reduce_window_ms"] for k in sorted(r["static"]["ranks"])]
+    assert all(abs(x - y) < 1.0 for x, y in zip(rw, [44.4, 51.9, 61.6, 69.5])), rw
