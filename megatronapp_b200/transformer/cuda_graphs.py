@@ -60,7 +60,7 @@ class _TensorOnly(nn.Module):
 class CudaGraphManager:
     """Eager for ``warmup_steps`` calls, then capture once per (shape, dtype, training) and replay."""
 
-    def __init__(self, layer: nn.Module, warmup_steps: int = 3, share_pool: bool = True):
+    def __init__(self, layer: nn.Module, warmup_steps: int = 3, share_pool: bool = False):
         self.layer = layer
         self.warmup_steps = warmup_steps
         self.calls = 0
@@ -85,7 +85,7 @@ class CudaGraphManager:
                 self.refused = why
                 return _TensorOnly(self.layer)(*args)
             sample = tuple(torch.zeros_like(a).requires_grad_(a.requires_grad) for a in args)
-            g = torch.cuda.make_graphed_callables(_TensorOnly(self.layer), sample, num_warmup_iters=1, pool=self.pool)
+            g = torch.cuda.make_graphed_callables(_TensorOnly(self.layer), sample, num_warmup_iters=3, pool=self.pool)
             self.graphs[key] = g
         self.replays += 1
         return g(*args)

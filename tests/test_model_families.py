@@ -215,3 +215,34 @@ def test_fp8_linear_emulation_matches_bf16_within_quantisation_error():
     ref.backward(dy)
     assert ((gx - x.grad).abs().max() / x.grad.abs().max()) < 0.08
     assert ((gw - w.grad).abs().max() / w.grad.abs().max()) < 0.08
+
+
+def test_retro_chunked_cross_attention_is_causal_and_trains():
+    """Retro: neighbours of chunk i may only influence tokens from the last position of chunk i onwards."""
+    from megatronapp_b200.models.retro import RetroConfig, RetroModel
+
+    _init()
+    cfg = RetroConfig(num_layers=2, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0,
+                      attention_dropout=0.0, retro_chunk_length=4, retro_num_neighbors=2, retro_retrieved_length=6,
+                      retro_encoder_num_layers=1, retro_encoder_hidden_dropout=0.0, retro_encoder_attention_dropout=0.0,
+                      kernel_backend="torch")
+    assert cfg.retro_layer_numbers() == [1]
+    m = RetroModel(cfg, vocab_size=64, max_sequence_length=16)
+    b, s, mch, k, r = 2, 16, 4, 2, 6
+    l = s // mch
+    toks = torch.randint(0, 64, (b, s))
+    pos = torch.arange(s).unsqueeze(0).expand(b, -1)
+    nb = torch.randint(0, 64, (b, l, k, r))
+    m.eval()
+    with torch.no_grad():
+        base = m(toks, pos, None, context_input_ids=nb)
+        nb2 = nb.clone()
+        nb2[:, 2] = torch.randint(0, 64, (b, k, r))                 # change the neighbours of chunk 2 (tokens 8..11)
+        out = m(toks, pos, None, context_input_ids=nb2)
+    changed = (out - base).abs().amax(dim=(0, 2)) > 1e-6            # per position
+    assert not changed[: 2 * mch + mch - 1].any()                   # nothing before the last token of chunk 2
+    assert changed[2 * mch + mch - 1:].any()
+    m.train()
+    losses = _train(m, lambda: m(toks, pos, None, context_input_ids=nb, labels=torch.roll(toks, -1, 1)).mean(), steps=10, lr=1e-2)
+    assert losses[-1] < losses[0]
+    assert m.retro_encoder.layers[0].cross_attention.linear_q.weight.grad is not None
