@@ -85,6 +85,12 @@ class CudaGraphManager:
                 self.refused = why
                 return _TensorOnly(self.layer)(*args)
             sample = tuple(torch.zeros_like(a).requires_grad_(a.requires_grad) for a in args)
+            # capture at a quiescent point: drop dead autograd graphs / cross-stream blocks first so that no
+            # deferred free lands inside the capture (it would touch the legacy stream and invalidate it)
+            import gc
+
+            gc.collect()
+            torch.cuda.synchronize()
             g = torch.cuda.make_graphed_callables(_TensorOnly(self.layer), sample, num_warmup_iters=3, pool=self.pool)
             self.graphs[key] = g
         self.replays += 1
@@ -135,3 +141,16 @@ def graph_transformer_block(block: nn.Module, warmup_steps: int = 3) -> List[Cud
         layer.cuda_graph_manager = m
         managers.append(m)
     return managers
+
+
+def capture_block_upfront(block: nn.Module, hidden_states: torch.Tensor, *extra: torch.Tensor) -> None:
+    """Capture every layer of the block with zero-filled sample inputs *before* any of them runs in this
+    forward pass (all layers of a block see the same shapes), instead of lazily in the middle of it."""
+    for layer in block.layers:
+        m = layer.cuda_graph_manager
+        args = (hidden_states,) + tuple(extra)
+        if m.refused is None and m._key(args) not in m.graphs and m.calls >= m.warmup_steps:
+            m.calls += 1
+            saved = m.calls
+            m(*(torch.zeros_like(a).requires_grad_(a.requires_grad) for a in args))   # triggers the capture
+            m.calls, m.replays = saved, max(0, m.replays - 1)
