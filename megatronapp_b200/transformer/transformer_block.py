@@ -108,9 +108,13 @@ class TransformerBlock(MegatronModule):
                 from .cuda_graphs import graph_transformer_block
 
                 graph_transformer_block(self, self.config.cuda_graph_warmup_steps)
+            if graphable:
+                from .cuda_graphs import capture_block_upfront
+
+                extra = (rotary_pos_emb,) if torch.is_tensor(rotary_pos_emb) else ()
+                capture_block_upfront(self, hidden_states, *extra)
             for layer in self.layers:
                 if graphable:
-                    extra = (rotary_pos_emb,) if torch.is_tensor(rotary_pos_emb) else ()
                     hidden_states = layer.cuda_graph_manager(hidden_states, *extra)
                     hidden_states = scope_hooks.perturb_system(hidden_states)
                     continue
