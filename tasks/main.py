@@ -8,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def get_tasks_args(parser):
     g = parser.add_argument_group("tasks")
-    g.add_argument("--task", type=str, required=True, help="WIKITEXT103 | LAMBADA")
+    g.add_argument("--task", type=str, required=True, help="WIKITEXT103 | LAMBADA | MNLI | QQP")
+    g.add_argument("--train-data", nargs="*", default=None)
+    g.add_argument("--epochs", type=int, default=3)
     g.add_argument("--valid-data", nargs="*", default=None, help="path(s) to the evaluation text")
     g.add_argument("--overlapping-eval", type=int, default=32, help="sliding window stride for perplexity")
     g.add_argument("--strict-lambada", action="store_true", help="whole-word LAMBADA (all word pieces must match)")
@@ -24,6 +26,8 @@ if __name__ == "__main__":
     args = get_args()
     if args.task in ("LAMBADA", "WIKITEXT103"):
         from tasks.zeroshot_gpt.evaluate import main
+    elif args.task in ("MNLI", "QQP"):
+        from tasks.glue.finetune import main
     else:
         raise NotImplementedError(f"Task {args.task} is not implemented.")
     main()

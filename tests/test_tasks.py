@@ -53,3 +53,51 @@ def test_wikitext_perplexity_and_lambada_accuracy(tmp_path):
     ds2 = build_dataset("LAMBADA", str(lam), _Tok(), 16)
     acc = summarize("LAMBADA", evaluate(m, torch.utils.data.DataLoader(ds2, batch_size=3), "accuracy"), ds2)
     assert acc["total examples"] == 6 and 0.0 <= acc["avg accuracy"] <= 1.0
+
+
+def test_glue_classification_finetune_learns(tmp_path):
+    """Classification head + finetune loop: a separable synthetic sentence-pair task reaches high accuracy."""
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.models.bert.bert_model import bert_layer_local_spec
+    from megatronapp_b200.models.bert.classification import Classification, MultipleChoice
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+    from tasks.finetune_utils import finetune
+    from tasks.glue.data import GLUEDataset, build_tokens_types_paddings
+
+    ids, types, pad = build_tokens_types_paddings([5, 6, 7, 8], [9, 10, 11], 8, 1, 2, 0)
+    assert ids == [1, 5, 6, 7, 2, 9, 10, 2] and types == [0, 0, 0, 0, 0, 1, 1, 1] and pad == [1] * 8
+
+    class Tok:
+        cls, sep, pad, vocab_size = 1, 2, 0, 64
+
+        def tokenize(self, t):
+            return [3 + (sum(map(ord, w)) % 60) for w in t.split()]
+
+    def write(path, n, seed):
+        import random
+
+        r = random.Random(seed)
+        with open(path, "w") as f:
+            f.write("id\tquestion1\tquestion2\tis_duplicate\n")
+            for i in range(n):
+                lab = r.randint(0, 1)
+                a = " ".join(r.choice(["red", "blue", "green"]) for _ in range(4))
+                b = a if lab else " ".join(r.choice(["cat", "dog", "bird"]) for _ in range(4))
+                f.write(f"{i}\t{a}\t{b}\t{lab}\n")
+
+    write(tmp_path / "train.tsv", 256, 0)
+    write(tmp_path / "dev.tsv", 64, 1)
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch")
+    m = Classification(cfg, bert_layer_local_spec(), 64, 16, num_classes=2)
+    tr = GLUEDataset("QQP", "training", [str(tmp_path / "train.tsv")], Tok(), 12)
+    va = GLUEDataset("QQP", "validation", [str(tmp_path / "dev.tsv")], Tok(), 12)
+    hist = finetune(m, tr, va, epochs=4, batch_size=32, lr=3e-3, log_interval=0)
+    assert hist[-1]["accuracy"] > 0.9, hist
+    mc = MultipleChoice(cfg, bert_layer_local_spec(), 64, 16)
+    scores = mc(torch.randint(3, 64, (2, 4, 12)), torch.ones(2, 4, 12, dtype=torch.long), torch.zeros(2, 4, 12, dtype=torch.long))
+    assert scores.shape == (2, 4)
