@@ -61,6 +61,12 @@ struct DevParams {
   uint32_t* peer_flags[kMaxPeers];
 };
 
+// reduce-scatter epilogue: one tensor map per owner rank over that rank's staging buffer
+// [src rank][rows_per_rank][N], so partial tiles leave through asynchronous TMA stores to peer memory
+struct PeerMaps {
+  CUtensorMap m[kMaxPeers];
+};
+
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.79788456f, k1 = 0.044715f;
   float inner = k0 * x * (1.f + k1 * x * x);
@@ -99,7 +105,8 @@ template <bool kAMn, bool kBMn, int BLOCK_N, int kStages, int kEpi, int kComm>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_local,
             const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_d,
-            const __grid_constant__ CUtensorMap tmap_d_pre, const DevParams p) {
+            const __grid_constant__ CUtensorMap tmap_d_pre, const __grid_constant__ PeerMaps peer_maps,
+            const DevParams p) {
   using L = SmemLayout<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -358,6 +365,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     int cbuf = 0;
+    uint32_t* pending_flag = nullptr;   // reduce-scatter: flag of the previous tile, not yet published
     for (int tile = cta; tile < num_tiles; tile += n_ctas) {
       int m_blk, n_blk;
       tile_coords(p, tile, m_blk, n_blk);
@@ -460,56 +468,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             cbuf ^= 1;
           }
         } else {  // kEpiReduceScatter: partial tile -> owner's staging buffer [src][rows_per_rank][N]
-          // Each warp owns rows [32*ew, 32*ew+32) of the tile: it parks its 64-column slice in a
-          // warp-private 4 KB smem region, then streams it out so that one store instruction
-          // covers 4 rows x 128 contiguous bytes (full NVLink write granules instead of 16 B shards).
+          // Same swizzled-smem staging as the plain store epilogue, but the TMA store targets the
+          // owner's arena over NVLink: the epilogue warps never wait on a remote write.
           const int owner = (m_blk * BLOCK_M) / p.rows_per_rank;
-          uint8_t* wbuf = smem_c + ew * 4096;
-          {
-            uint8_t* sc = wbuf + lane * 128;
+          if (epi_tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, kNumEpiThreads);
+          uint8_t* sc = smem_c + cbuf * L::kCBytes + row_in_tile * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint32_t pk[4];
+          for (int j = 0; j < 8; ++j) {
+            uint32_t pk[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int i = j * 8 + 2 * q;
-                float a = __uint_as_float(i < 32 ? v0[i] : v1[i - 32]);
-                float b = __uint_as_float(i + 1 < 32 ? v0[i + 1] : v1[i + 1 - 32]);
-                if (p.is_bf16) pk[q] = pack_bf16x2(a, b);
-                else {
-                  __half2 h = __floats2half2_rn(a, b);
-                  pk[q] = *reinterpret_cast<uint32_t*>(&h);
-                }
+            for (int q = 0; q < 4; ++q) {
+              const int i = j * 8 + 2 * q;
+              float a = __uint_as_float(i < 32 ? v0[i] : v1[i - 32]);
+              float b = __uint_as_float(i + 1 < 32 ? v0[i + 1] : v1[i + 1 - 32]);
+              if (p.is_bf16) pk[q] = pack_bf16x2(a, b);
+              else {
+                __half2 h = __floats2half2_rn(a, b);
+                pk[q] = *reinterpret_cast<uint32_t*>(&h);
               }
-              *reinterpret_cast<uint4*>(sc + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+            *reinterpret_cast<uint4*>(sc + ((j ^ (row_in_tile & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          __syncwarp();
-          const int lrow0 = m_blk * BLOCK_M + ew * 32 - owner * p.rows_per_rank;
-          uint16_t* dst0 = reinterpret_cast<uint16_t*>(p.peer_buf[owner]) +
-                           (static_cast<size_t>(p.tp_rank) * p.rows_per_rank + lrow0) * p.N + gcol0;
-          const int chunk = lane & 7, rsub = lane >> 3;
-          if (gcol0 + chunk * 8 < p.N) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + rsub;
-              const int4 val = *reinterpret_cast<const int4*>(wbuf + r * 128 + ((chunk ^ (r & 7)) << 4));
-              st_na_v4(reinterpret_cast<int4*>(dst0 + static_cast<size_t>(r) * p.N + chunk * 8), val);
-            }
+          fence_proxy_async_smem();
+          named_bar_sync(2, kNumEpiThreads);
+          if (epi_tid == 0) {
+            const int row0 = p.tp_rank * p.rows_per_rank + (m_blk * BLOCK_M - owner * p.rows_per_rank);
+            tma_store_2d(&peer_maps.m[owner], smem_c + cbuf * L::kCBytes, gcol0, row0);
+            tma_store_commit();
           }
-          __syncwarp();
+          cbuf ^= 1;
         }
       }
       if constexpr (kEpi == kEpiReduceScatter) {
-        const int owner = (m_blk * BLOCK_M) / p.rows_per_rank;
-        const int lm = m_blk - owner * p.m_blocks_per_chunk;
-        __threadfence_system();
-        named_bar_sync(1, kNumEpiThreads);
+        // The flag of a tile is published one tile later: bulk-store groups retire in order, so once at
+        // most this tile's BLOCK_N/64 groups are pending the previous tile's data has landed at its owner.
         if (epi_tid == 0) {
+          if (pending_flag != nullptr) {
+            tma_store_wait_all<BLOCK_N / 64>();
+            __threadfence_system();
+            st_release_sys(pending_flag, p.epoch);
+          }
+          const int owner = (m_blk * BLOCK_M) / p.rows_per_rank;
+          const int lm = m_blk - owner * p.m_blocks_per_chunk;
           // flags layout on the owner: [src rank][local m block][n block]
-          uint32_t* flag = p.peer_flags[owner] +
-                           (static_cast<size_t>(p.tp_rank) * p.m_blocks_per_chunk + lm) * p.num_n_blocks + n_blk;
-          st_release_sys(flag, p.epoch);
+          pending_flag = p.peer_flags[owner] +
+                         (static_cast<size_t>(p.tp_rank) * p.m_blocks_per_chunk + lm) * p.num_n_blocks + n_blk;
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -518,6 +522,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (epi_tid == 0) tma_store_wait_all<0>();
     }
     if constexpr (kEpi == kEpiReduceScatter) {
+      if (epi_tid == 0) {
+        tma_store_wait_all<0>();
+        if (pending_flag != nullptr) {
+          __threadfence_system();
+          st_release_sys(pending_flag, p.epoch);
+        }
+      }
       // ============================================================== reduce phase (owned rows)
       const int own_tiles = p.m_blocks_per_chunk * p.num_n_blocks;
       const uint32_t* my_flags = p.peer_flags[p.tp_rank];
@@ -653,7 +664,7 @@ int num_sms() {
 
 template <bool kAMn, bool kBMn, int BLOCK_N, int kStages, int kEpi, int kComm>
 int launch(const GemmArgs& a, const DevParams& p, const CUtensorMap& ta, const CUtensorMap& tal,
-           const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdp, int grid) {
+           const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdp, const PeerMaps& pm, int grid) {
   using L = SmemLayout<BLOCK_N, kStages>;
   auto kern = gemm_kernel<kAMn, kBMn, BLOCK_N, kStages, kEpi, kComm>;
   static bool attr_set = false;
@@ -662,7 +673,7 @@ int launch(const GemmArgs& a, const DevParams& p, const CUtensorMap& ta, const C
     if (e != cudaSuccess) { g_last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -10; }
     attr_set = true;
   }
-  kern<<<grid, kNumThreads, L::kTotal, a.stream>>>(ta, tal, tb, td, tdp, p);
+  kern<<<grid, kNumThreads, L::kTotal, a.stream>>>(ta, tal, tb, td, tdp, pm, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_error = std::string("launch: ") + cudaGetErrorString(e); return -11; }
   return 0;
@@ -670,10 +681,10 @@ int launch(const GemmArgs& a, const DevParams& p, const CUtensorMap& ta, const C
 
 template <int BLOCK_N, int kStages>
 int dispatch(const GemmArgs& a, const DevParams& p, const CUtensorMap& ta, const CUtensorMap& tal,
-             const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdp, int grid) {
+             const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tdp, const PeerMaps& pm, int grid) {
 #define B200_GEMM_CASE(AM, BM, EPI, COMM)                                                   \
   if (a.a_mn_major == AM && a.b_mn_major == BM && a.epilogue == EPI && a.comm == COMM)      \
-    return launch<AM, BM, BLOCK_N, kStages, EPI, COMM>(a, p, ta, tal, tb, td, tdp, grid);
+    return launch<AM, BM, BLOCK_N, kStages, EPI, COMM>(a, p, ta, tal, tb, td, tdp, pm, grid);
   // forward / generic
   B200_GEMM_CASE(false, false, kEpiStore16, kCommNone)
   B200_GEMM_CASE(false, true, kEpiStore16, kCommNone)
@@ -816,8 +827,17 @@ int gemm_bf16(const GemmArgs& a) {
   } else { td = ta; tdp = ta; }
   if (!ok) return -5;
 
-  if (block_n == 256) return dispatch<256, 4>(a, p, ta, tal, tb, td, tdp, grid);
-  return dispatch<128, 6>(a, p, ta, tal, tb, td, tdp, grid);
+  PeerMaps pm{};
+  for (int s = 0; s < kMaxPeers; ++s) pm.m[s] = ta;
+  if (a.comm == kCommReduceScatter) {
+    for (int s = 0; s < a.tp_size; ++s) {
+      if (!make_tmap_2d(&pm.m[s], a.peer_buf[s], a.is_bf16, a.N, static_cast<uint64_t>(a.tp_size) * p.rows_per_rank, a.N, 64,
+                        BLOCK_M))
+        return -5;
+    }
+  }
+  if (block_n == 256) return dispatch<256, 4>(a, p, ta, tal, tb, td, tdp, pm, grid);
+  return dispatch<128, 6>(a, p, ta, tal, tb, td, tdp, pm, grid);
 }
 
 }  // namespace b200
