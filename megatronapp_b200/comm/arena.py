@@ -129,7 +129,10 @@ class TPFusedComm:
     def __init__(self, arena: SymmetricArena, max_tokens: int, max_in: int, max_out: int,
                  n_comm_ctas: int = 8):
         self.arena = arena
-        self.n_comm_ctas = n_comm_ctas
+        # comm CTAs push the local shard to tp-1 peers with TMA bulk copies; the bytes in flight per CTA are
+        # fixed (6 x 32 KB), so the count scales with the number of destinations (override: B200_AG_COMM_CTAS)
+        env = os.environ.get("B200_AG_COMM_CTAS")
+        self.n_comm_ctas = int(env) if env else (n_comm_ctas if arena.size <= 2 else 16)
         # GEMM->RS fusion is numerically validated but (round 1) ~20 % slower than tcgen05 GEMM +
         # NCCL reduce-scatter on 2 GPUs; AG->GEMM fusion wins 8-16 % -- see profiles/.  Opt in with
         # B200_FUSED_RS=1 / bench.py --fused-rs.

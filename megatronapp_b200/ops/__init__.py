@@ -627,3 +627,33 @@ def chunk_mean(x: torch.Tensor, pixels: int) -> torch.Tensor:
         c0, c1 = px * cols // pixels, (px + 1) * cols // pixels
         outs.append(x[..., c0:max(c1, c0 + 1)].float().mean(-1))
     return torch.stack(outs, dim=-1)
+
+
+# ---------------------------------------------------------------------------
+# MegaScan software slow-rank injection: burn ``cycles`` SM clocks in front of every transformer layer,
+# forward and backward, on the rank under test (what a clock-capped GPU looks like to its peers)
+# ---------------------------------------------------------------------------
+_SLOW_SPIN_CYCLES = 0
+
+
+def set_slow_rank_spin(cycles: int) -> None:
+    global _SLOW_SPIN_CYCLES
+    _SLOW_SPIN_CYCLES = int(cycles)
+
+
+class _SlowSpinFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        if x.is_cuda:
+            ext().spin(_SLOW_SPIN_CYCLES)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if g.is_cuda:
+            ext().spin(_SLOW_SPIN_CYCLES)
+        return g
+
+
+def slow_spin(x):
+    return _SlowSpinFn.apply(x) if _SLOW_SPIN_CYCLES > 0 else x

@@ -423,6 +423,9 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         r, cyc = args.slow_rank_inject.split(":")
         if int(r) == args.rank:
             slow = int(cyc)
+            from .. import ops
+
+            ops.set_slow_rank_spin(slow)      # spins in front of every layer, forward and backward
     exit_flag = False
     start_time = time.time()
     stimer = get_straggler_detector()
@@ -444,10 +447,6 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             args.consumed_train_samples += get_current_global_batch_size()
             tracer.iteration_end()
             continue
-        if slow is not None and torch.cuda.is_available():
-            from .. import ops
-
-            ops.ext().spin(slow)
         _maybe_simulate_fault(args, iteration)
         if getattr(args, '_fault_deadline', None) and time.time() > args._fault_deadline:
             while True:

@@ -88,6 +88,7 @@ class TransformerLayer(MegatronModule):
                 inference_params=None):
         inference_context = inference_context or inference_params
         with _scope("transformer_layer", layer=self.layer_number):
+            hidden_states = ops.slow_spin(hidden_states)      # MegaScan slow-rank injection (no-op unless armed)
             with _scope("_forward_attention"):
                 residual = hidden_states
                 x = self.input_layernorm(hidden_states)
