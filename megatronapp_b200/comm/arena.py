@@ -17,6 +17,8 @@ This replaces the reference's userbuffer / shm plumbing (``initialize.py:236-292
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -136,8 +138,6 @@ class TPFusedComm:
         # GEMM->RS fusion is numerically validated but (round 1) ~20 % slower than tcgen05 GEMM +
         # NCCL reduce-scatter on 2 GPUs; AG->GEMM fusion wins 8-16 % -- see profiles/.  Opt in with
         # B200_FUSED_RS=1 / bench.py --fused-rs.
-        import os
-
         self.use_fused_rs = os.environ.get("B200_FUSED_RS", "0") == "1"
         self.calls = {"ag": 0, "rs": 0}
         ext = ops.ext()
