@@ -413,16 +413,20 @@ std::vector<Tensor> attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, 
   return {o, lse, probs};
 }
 std::vector<Tensor> attn_bwd(const Tensor& d_o, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o,
-                             const Tensor& lse, double scale, bool causal) {
+                             const Tensor& lse, double scale, bool causal, const c10::optional<Tensor>& dq_out,
+                             const c10::optional<Tensor>& dk_out, const c10::optional<Tensor>& dv_out) {
   c10::cuda::CUDAGuard guard(q.device());
   check_bhsd(q, "q"); check_bhsd(k, "k"); check_bhsd(v, "v"); check_bhsd(o, "o");
   b200::AttnArgs a{};
   a.b = static_cast<int>(q.size(0)); a.hq = static_cast<int>(q.size(1)); a.sq = static_cast<int>(q.size(2)); a.d = static_cast<int>(q.size(3));
   a.hkv = static_cast<int>(k.size(1)); a.sk = static_cast<int>(k.size(2));
   Tensor doc = d_o.stride(3) == 1 ? d_o : d_o.contiguous();
-  auto dq = torch::empty({a.sq, a.b, a.hq, a.d}, q.options()).permute({1, 2, 0, 3});
-  auto dk = torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
-  auto dv = torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
+  // gradients go either to fresh [s,b,h,d] buffers or straight into caller-provided strided views
+  // (e.g. the three slices of one packed d(qkv) tensor: no concatenation afterwards)
+  Tensor dq = dq_out.has_value() ? dq_out.value() : torch::empty({a.sq, a.b, a.hq, a.d}, q.options()).permute({1, 2, 0, 3});
+  Tensor dk = dk_out.has_value() ? dk_out.value() : torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
+  Tensor dv = dv_out.has_value() ? dv_out.value() : torch::empty({a.sk, a.b, a.hkv, a.d}, q.options()).permute({1, 2, 0, 3});
+  check_bhsd(dq, "dq"); check_bhsd(dk, "dk"); check_bhsd(dv, "dv");
   auto delta = torch::empty({2, a.b, a.hq, a.sq}, q.options().dtype(at::kFloat));   // [delta ; lse * log2e]
   a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr(); a.o = const_cast<void*>(o.data_ptr()); a.lse = lse.data_ptr<float>();
   a.d_o = doc.data_ptr(); a.dq = dq.data_ptr(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();

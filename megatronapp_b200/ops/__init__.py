@@ -439,8 +439,44 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = ext().attn_bwd(do, q, k, v, o, lse, ctx.scale, ctx.causal)
+        dq, dk, dv = ext().attn_bwd(do, q, k, v, o, lse, ctx.scale, ctx.causal, None, None, None)
         return dq, dk, dv, None, None
+
+
+class _PackedQKVAttnFn(torch.autograd.Function):
+    """Self-attention straight on the packed projection output ``[s, b, np, 3*hn]`` (MHA): q / k / v are
+    strided views of it, and the backward kernels write dq / dk / dv into the three slices of one packed
+    gradient tensor -- no split copies forward, no concatenation backward."""
+
+    @staticmethod
+    def forward(ctx, mixed, scale, causal):
+        hn = mixed.shape[-1] // 3
+        q, k, v = (mixed[..., i * hn:(i + 1) * hn].permute(1, 2, 0, 3) for i in range(3))
+        o, lse, _ = ext().attn_fwd(q, k, v, scale, causal, False)
+        ctx.save_for_backward(mixed, o, lse)
+        ctx.scale, ctx.causal = scale, causal
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        mixed, o, lse = ctx.saved_tensors
+        hn = mixed.shape[-1] // 3
+        q, k, v = (mixed[..., i * hn:(i + 1) * hn].permute(1, 2, 0, 3) for i in range(3))
+        dmixed = torch.empty_like(mixed)
+        dq, dk, dv = (dmixed[..., i * hn:(i + 1) * hn].permute(1, 2, 0, 3) for i in range(3))
+        ext().attn_bwd(do, q, k, v, o, lse, ctx.scale, ctx.causal, dq, dk, dv)
+        return dmixed, None, None
+
+
+def attention_packed_qkv(mixed, scale=None, causal=True):
+    """``mixed``: ``[s, b, np, 3*hn]`` (q | k | v per head).  Returns ``[b, np, s, hn]`` or ``None`` when the
+    native packed path does not apply (caller falls back to split + ``attention``)."""
+    hn = mixed.shape[-1] // 3
+    if not (_native(mixed) and _ATTN_IMPL in ("auto", "native") and hn in (64, 128) and mixed.is_contiguous()
+            and mixed.shape[0] % 64 == 0 and native_attention_available()):
+        return None
+    scale = scale if scale is not None else 1.0 / math.sqrt(hn)
+    return _PackedQKVAttnFn.apply(mixed, scale, causal)
 
 
 _ATTN_IMPL = os.environ.get("B200_ATTN_IMPL", "auto")  # auto | native | sdpa | ref
@@ -456,7 +492,7 @@ def native_attention_available() -> bool:
             try:
                 q = torch.zeros(1, 1, 128, 64, dtype=torch.bfloat16, device="cuda")
                 o, lse, _ = ext().attn_fwd(q, q, q, 1.0, True, False)
-                ext().attn_bwd(o, q, q, q, o, lse, 1.0, True)
+                ext().attn_bwd(o, q, q, q, o, lse, 1.0, True, None, None, None)
                 _NATIVE_ATTN_OK = True
             except RuntimeError:
                 _NATIVE_ATTN_OK = False

@@ -105,6 +105,9 @@ class DotProductAttention(MegatronModule):
 
 
 class Attention(MegatronModule):
+    def _packed_self_attention(self, *a, **k):
+        return None
+
     def __init__(self, config, submodules, layer_number: int, attn_mask_type, attention_type: str,
                  cp_comm_type: Optional[str] = None):
         super().__init__(config)
@@ -151,6 +154,11 @@ class Attention(MegatronModule):
                 packed_seq_params=None, sequence_len_offset=None, inference_params=None):
         inference_context = inference_context or inference_params
         with _scope("attention"):
+            packed = self._packed_self_attention(hidden_states, attention_mask, rotary_pos_emb, inference_context,
+                                                 packed_seq_params)
+            if packed is not None:
+                output, bias = self.linear_proj(packed)
+                return output, bias
             query, key, value = self.get_query_key_value_tensors(hidden_states, key_value_states)
             if rotary_pos_emb is not None:
                 q_cs, k_cs = rotary_pos_emb if isinstance(rotary_pos_emb, tuple) else (rotary_pos_emb, rotary_pos_emb)
@@ -177,6 +185,26 @@ class Attention(MegatronModule):
 
 
 class SelfAttention(Attention):
+    def _packed_self_attention(self, hidden_states, attention_mask, rotary_pos_emb, inference_context, packed_seq_params):
+        """MHA training fast path: attention directly on the packed QKV projection (no split / concat)."""
+        core = self.core_attention
+        if (self.num_query_groups_per_partition != self.num_attention_heads_per_partition or rotary_pos_emb is not None
+                or inference_context is not None or packed_seq_params is not None or self.q_layernorm is not None
+                or not isinstance(core, DotProductAttention) or core.cp_size > 1 or self.checkpoint_core_attention
+                or not str(self.attn_mask_type).endswith("causal") or (core.dropout_p > 0.0 and self.training)
+                or scope_hooks.wants(1, self.layer_number) or scope_hooks.wants(2, self.layer_number)
+                or scope_hooks.wants(3, self.layer_number) or not hidden_states.is_cuda):
+            return None
+        mixed, _ = self.linear_qkv(hidden_states)
+        s_, b_ = mixed.shape[0], mixed.shape[1]
+        np_, hn = self.num_attention_heads_per_partition, self.hidden_size_per_attention_head
+        o = ops.attention_packed_qkv(mixed.view(s_, b_, np_, 3 * hn), core.softmax_scale, True)
+        if o is None:
+            self._mixed_cache = mixed        # reuse the projection in the generic path
+            return None
+        return o.permute(2, 0, 1, 3).reshape(s_, b_, np_ * hn)
+
+
     def __init__(self, config, submodules: SelfAttentionSubmodules, layer_number: int,
                  attn_mask_type="causal", cp_comm_type=None):
         super().__init__(config, submodules, layer_number, attn_mask_type, "self", cp_comm_type)
@@ -194,7 +222,10 @@ class SelfAttention(Attention):
             self.q_layernorm = self.k_layernorm = None
 
     def get_query_key_value_tensors(self, hidden_states, key_value_states=None):
-        mixed, _ = self.linear_qkv(hidden_states)  # [s, b, ng*(np/ng+2)*hn]
+        mixed = getattr(self, "_mixed_cache", None)
+        self._mixed_cache = None
+        if mixed is None:
+            mixed, _ = self.linear_qkv(hidden_states)  # [s, b, ng*(np/ng+2)*hn]
         scope_hooks.tik_tensor(1, self.layer_number, mixed)
         ng = self.num_query_groups_per_partition
         hn = self.hidden_size_per_attention_head

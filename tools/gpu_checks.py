@@ -372,7 +372,7 @@ def check_attention_perf():
     t = _time(lambda: ops.ext().attn_fwd(qd, kd, vd, 1.0 / d ** 0.5, True, False))
     res["b200_fwd_ms"], res["b200_fwd_tflops"] = round(t, 4), round(fl_f / t / 1e9, 1)
     o2, lse, _ = ops.ext().attn_fwd(qd, kd, vd, 1.0 / d ** 0.5, True, False)
-    t = _time(lambda: ops.ext().attn_bwd(do, qd, kd, vd, o2, lse, 1.0 / d ** 0.5, True))
+    t = _time(lambda: ops.ext().attn_bwd(do, qd, kd, vd, o2, lse, 1.0 / d ** 0.5, True, None, None, None))
     res["b200_bwd_ms"], res["b200_bwd_tflops"] = round(t, 4), round(2.5 * fl_f / t / 1e9, 1)
     for (bb, hh) in [(4, 32), (4, 8)]:
         q4, k4, v4 = (torch.randn(s, bb, hh, d, device="cuda", dtype=torch.bfloat16).permute(1, 2, 0, 3) for _ in range(3))

@@ -27,7 +27,7 @@ for _ in range(3):
     ops.gemm(x, w1, block_n=256)                                         # 1-CTA kernel
     fp8.gemm_fp8(x8, w8, sx, sw)                                         # fp8 kernel
     o, lse, _ = ops.ext().attn_fwd(q, k, v, 128 ** -0.5, True, False)
-    ops.ext().attn_bwd(torch.randn_like(o), q, k, v, o, lse, 128 ** -0.5, True)
+    ops.ext().attn_bwd(torch.randn_like(o), q, k, v, o, lse, 128 ** -0.5, True, None, None, None)
     y, mean, rstd = ops.ext().layernorm_fwd(x, g, b, 1e-5, False, False)
     ops.ext().layernorm_bwd(x, x, g, mean, rstd, False, False, True)
 torch.cuda.synchronize()
