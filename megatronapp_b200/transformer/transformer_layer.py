@@ -104,6 +104,7 @@ class TransformerLayer(MegatronModule):
                                                            key_value_states=context,
                                                            inference_context=inference_context)
                     hidden_states = self._bda(ca_out, ca_bias, residual)
+            hidden_states = ops.slow_spin(hidden_states)      # second injection point: a slow GPU is late at every collective
             with _scope("_forward_mlp"):
                 residual = hidden_states
                 x = self.pre_mlp_layernorm(hidden_states)
