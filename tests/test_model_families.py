@@ -246,3 +246,27 @@ def test_retro_chunked_cross_attention_is_causal_and_trains():
     losses = _train(m, lambda: m(toks, pos, None, context_input_ids=nb, labels=torch.roll(toks, -1, 1)).mean(), steps=10, lr=1e-2)
     assert losses[-1] < losses[0]
     assert m.retro_encoder.layers[0].cross_attention.linear_q.weight.grad is not None
+
+
+def test_heterogeneous_gpt_layers():
+    """Per-layer NAS configs: skipped attention, linear-replaced MLP, per-layer GQA / FFN sizes."""
+    from megatronapp_b200.models.gpt import GPTModel
+    from megatronapp_b200.models.gpt.heterogeneous import get_gpt_heterogeneous_layer_spec, parse_heterogeneous_config
+
+    _init()
+    cfg = _cfg(num_layers=4, kernel_backend="torch")
+    blocks = parse_heterogeneous_config({"block_configs": [
+        {"attention": {"n_heads_in_group": 2}, "ffn": {"intermediate_size": 64}},
+        {"attention": {"no_op": True}, "ffn": {"ffn_mult": 1.5}},
+        {"attention": {"replace_with_linear": True}, "ffn": {"replace_with_linear": True}},
+        {"attention": {}, "ffn": {"no_op": True}}]}, cfg.num_attention_heads, cfg.hidden_size)
+    assert blocks[0].num_query_groups == 2 and blocks[1].attn_no_op and blocks[1].ffn_hidden_size == 256
+    m = GPTModel(cfg, get_gpt_heterogeneous_layer_spec(cfg, blocks), 64, 16)
+    L = m.decoder.layers
+    assert L[0].mlp.linear_fc1.weight.shape[0] == 64 and L[0].self_attention.linear_qkv.weight.shape[0] == 32 + 2 * 16
+    assert not any(p.requires_grad for p in L[1].self_attention.parameters()) and L[1].mlp.linear_fc1.weight.shape[0] == 256
+    assert not list(L[3].mlp.parameters())
+    toks = torch.randint(0, 64, (2, 16))
+    pos = torch.arange(16).unsqueeze(0).expand(2, -1)
+    losses = _train(m, lambda: m(toks, pos, None, labels=torch.roll(toks, -1, 1)).mean(), steps=8, lr=1e-2)
+    assert losses[-1] < losses[0]
