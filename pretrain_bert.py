@@ -67,8 +67,24 @@ def forward_step(data_iterator, model):
 
 def train_valid_test_datasets_provider(num_samples):
     args = get_args()
+    if getattr(args, "data_path", None) and not args.mock_data:
+        # sentence-level .bin/.idx corpus (tools/preprocess_data.py --split-sentences) -> masked LM samples
+        from megatronapp_b200.data.gpt_dataset import parse_split, split_document_ranges
+        from megatronapp_b200.data.indexed_dataset import IndexedDataset
+        from megatronapp_b200.data.masked_dataset import BERTMaskedWordPieceDataset, MaskedWordPieceDatasetConfig
+        from megatronapp_b200.training.global_vars import get_tokenizer
+
+        prefix = args.data_path[0] if len(args.data_path) == 1 else args.data_path[1]
+        idx = IndexedDataset(prefix)
+        cfg = MaskedWordPieceDatasetConfig(sequence_length=args.seq_length, masking_probability=args.mask_prob,
+                                           short_sequence_probability=args.short_seq_prob, random_seed=args.seed,
+                                           classification_head=args.bert_binary_head)
+        ranges = split_document_ranges(len(idx.document_indices) - 1, parse_split(args.split))
+        tok = get_tokenizer()
+        return tuple(BERTMaskedWordPieceDataset(idx, max(int(n), 1), cfg, tok, doc_range=r) if r[1] > r[0] else None
+                     for n, r in zip(num_samples, ranges))
     mk = lambda n, s: MockBertDataset(max(int(n), 1), args.seq_length, args.padded_vocab_size, s, args.mask_prob, args.bert_binary_head)  # noqa: E731
-    return mk(num_samples[0], args.seed), mk(num_samples[1], args.seed + 1), mk(num_samples[2], args.seed + 2)
+    return mk(num_samples[0], 1), mk(num_samples[1], 2), mk(num_samples[2], 3)
 
 
 if __name__ == "__main__":
