@@ -22,6 +22,23 @@ from .arguments import parse_args, validate_args
 from .global_vars import set_global_variables
 
 
+def _apply_deterministic_mode(args):
+    """``--deterministic-mode``: bitwise-reproducible runs (reference arguments.py / initialize.py): deterministic
+    torch algorithms, no TF32 surprises, NCCL algorithm pinned.  Our own kernels are deterministic by
+    construction (no atomics in GEMM / attention / norm reductions; the fused reduce-scatter reduces in rank order)."""
+    if not getattr(args, "deterministic_mode", False):
+        return
+    import os
+
+    import torch
+
+    os.environ.setdefault("NCCL_ALGO", "Ring")
+    os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+
 def initialize_megatron(extra_args_provider=None, args_defaults=None, ignore_unknown_args=False,
                         allow_no_cuda=True, skip_mpu_initialization=False, args_list=None, parsed_args=None):
     args = parsed_args if parsed_args is not None else parse_args(extra_args_provider, ignore_unknown_args, args_list)
@@ -37,6 +54,7 @@ def initialize_megatron(extra_args_provider=None, args_defaults=None, ignore_unk
             torch.set_num_threads(max(1, min(4, (os.cpu_count() or 2) // max(1, args.world_size))))
     validate_args(args, args_defaults or {})
     set_global_variables(args)
+    _apply_deterministic_mode(args)
     if not skip_mpu_initialization:
         _initialize_distributed(args)
         _set_random_seed(args.seed, args.data_parallel_random_init)

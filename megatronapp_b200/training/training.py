@@ -435,7 +435,9 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
     if args.manual_gc:
         gc.disable()
         gc.collect()
+    prof = _Profiling(args)
     while iteration < args.train_iters:
+        prof.step_begin(iteration)
         if ws_server is not None:
             ws_server.wait_for_step_request(model)
         tracer.iteration_begin(iteration)
@@ -475,6 +477,11 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
                 break
         report_memory_flag = training_log(loss_dict, total_loss_dict, lr or 0.0, iteration, loss_scale,
                                           report_memory_flag, skipped_iter, grad_norm, params_norm, num_zeros)
+        prof.step_end(iteration)
+        if args.check_weight_hash_across_dp_replicas_interval and \
+                iteration % args.check_weight_hash_across_dp_replicas_interval == 0:
+            assert check_param_hashes_across_dp_replicas(model), "parameter hashes differ across data-parallel replicas"
+            print_rank_0(f">>> weight hashes match across DP replicas at iteration {iteration}")
         if args.log_straggler and iteration % args.log_interval == 0:
             stimer.report(num_floating_point_operations(args, batch_size) * args.log_interval, args.log_interval)
         if args.eval_interval and iteration % args.eval_interval == 0 and valid_data_iterator is not None:
@@ -522,6 +529,75 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         ws_server.shutdown()
     args.num_floating_point_operations_so_far = nflops
     return iteration, nflops, exit_flag
+
+
+class _Profiling:
+    """``--profile`` (CUDA profiler range for nsys/ncu capture windows), ``--use-pytorch-profiler`` (Kineto
+    trace to ``--tensorboard-dir``), ``--record-memory-history`` (allocator snapshot dumped at the end of the
+    window or on OOM) -- reference training.py:2134-2177."""
+
+    def __init__(self, args):
+        self.args = args
+        self.on = bool(args.profile) and args.rank in (args.profile_ranks or [0])
+        self.torch_prof = None
+        self.active = False
+        if getattr(args, "record_memory_history", False) and torch.cuda.is_available():
+            torch.cuda.memory._record_memory_history(max_entries=100000)
+            self.mem = True
+        else:
+            self.mem = False
+
+    def step_begin(self, iteration):
+        a = self.args
+        if not self.on or iteration != a.profile_step_start or self.active:
+            return
+        self.active = True
+        if a.use_pytorch_profiler:
+            import torch.profiler as tp
+
+            acts = [tp.ProfilerActivity.CPU] + ([tp.ProfilerActivity.CUDA] if torch.cuda.is_available() else [])
+            out = a.tensorboard_dir or "."
+            self.torch_prof = tp.profile(activities=acts, record_shapes=True, with_stack=False,
+                                         on_trace_ready=tp.tensorboard_trace_handler(out))
+            self.torch_prof.start()
+        elif torch.cuda.is_available():
+            torch.cuda.cudart().cudaProfilerStart()
+
+    def step_end(self, iteration):
+        a = self.args
+        if self.active and self.torch_prof is not None:
+            self.torch_prof.step()
+        if not self.active or iteration < a.profile_step_end:
+            return
+        self.active = False
+        if self.torch_prof is not None:
+            self.torch_prof.stop()
+            self.torch_prof = None
+        elif torch.cuda.is_available():
+            torch.cuda.cudart().cudaProfilerStop()
+        if self.mem:
+            torch.cuda.memory._dump_snapshot(a.memory_snapshot_path)
+            print_rank_0(f"memory snapshot written to {a.memory_snapshot_path}")
+
+
+def check_param_hashes_across_dp_replicas(model) -> bool:
+    """Every data-parallel replica must hold bit-identical parameters (reference
+    ``core/utils.py check_param_hashes_across_dp_replicas``): compare a cheap order-sensitive fp64 checksum."""
+    g = ps.get_data_parallel_group()
+    if g is None or isinstance(g, ps._SingleGroup) or dist.get_world_size(g) == 1:
+        return True
+    sums = []
+    for m in model:
+        for p in m.parameters():
+            d = p.detach().double().flatten()
+            idx = torch.arange(1, d.numel() + 1, device=d.device, dtype=torch.float64)
+            sums.append((d * (idx % 1021 + 1)).sum())
+    local = torch.stack(sums) if sums else torch.zeros(1, dtype=torch.float64)
+    dev = "cuda" if (torch.cuda.is_available() and dist.get_backend(g) == "nccl") else "cpu"
+    local = local.to(dev)
+    gathered = [torch.zeros_like(local) for _ in range(dist.get_world_size(g))]
+    dist.all_gather(gathered, local, group=g)
+    return all(torch.equal(gathered[0], x) for x in gathered[1:])
 
 
 def _maybe_simulate_fault(args, iteration):
