@@ -233,6 +233,48 @@ def fsdp_parity(steps=3):
             "shard_fraction": sharded_numel / sum(p.numel() for p in ref.parameters())}
 
 
+def cp_model_parity(comm="a2a"):
+    """GPT (rope) with context parallel = world: loss and embedding gradient match the cp = 1 model."""
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.context_parallel import get_batch_on_this_cp_rank
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+
+    rank, world = _setup()
+
+    def build(cp):
+        ps.destroy_model_parallel() if ps.model_parallel_is_initialized() else None
+        ps.initialize_model_parallel(1, 1, context_parallel_size=cp)
+        model_parallel_cuda_manual_seed(1)
+        torch.manual_seed(0)
+        cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                                hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch",
+                                context_parallel_size=cp, cp_comm_type=comm)
+        return GPTModel(cfg, get_gpt_layer_local_spec(), 64, 32, position_embedding_type="rope")
+
+    torch.manual_seed(3)
+    toks = torch.randint(0, 64, (2, 32))
+    batch = {"tokens": toks, "labels": torch.roll(toks, -1, 1), "position_ids": torch.arange(32).unsqueeze(0).expand(2, -1).contiguous(),
+             "loss_mask": torch.ones(2, 32), "attention_mask": None}
+    ref = build(1)
+    sd = {k: v.clone() for k, v in ref.state_dict().items() if torch.is_tensor(v)}
+    full = ref(batch["tokens"], batch["position_ids"], None, labels=batch["labels"])
+    full.mean().backward()
+    g_ref = ref.embedding.word_embeddings.weight.grad.clone()
+    m = build(world)
+    m.load_state_dict(sd, strict=False)
+    local = get_batch_on_this_cp_rank(dict(batch))
+    loss = m(local["tokens"], local["position_ids"], None, labels=local["labels"])
+    (loss.sum() / full.numel()).backward()
+    tot = loss.sum().detach().clone()
+    dist.all_reduce(tot)
+    g = m.embedding.word_embeddings.weight.grad.clone()
+    dist.all_reduce(g)
+    return {"loss_full": float(full.mean()), "loss_cp": float(tot) / full.numel(), "grad_err": float((g - g_ref).abs().max()),
+            "grad_ref_max": float(g_ref.abs().max())}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":

@@ -96,3 +96,10 @@ def test_fsdp_zero3_matches_unsharded_training():
         assert r["param_err"] < 2e-4
         assert r["resident_bytes_after_step"] == 0            # every unit is freed between steps
         assert 0.5 <= r["shard_fraction"] < 0.56               # each rank owns ~1/2 of the parameters
+
+
+@pytest.mark.parametrize("comm", ["a2a", "p2p"])
+def test_context_parallel_gpt_matches_single_rank(comm):
+    for r in run_distributed("cp_model_parity", 2, comm=comm):
+        assert abs(r["loss_full"] - r["loss_cp"]) < 1e-4, r
+        assert r["grad_err"] < 1e-4 * max(1.0, r["grad_ref_max"]) + 1e-5, r
