@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def get_tasks_args(parser):
     g = parser.add_argument_group("tasks")
-    g.add_argument("--task", type=str, required=True, help="WIKITEXT103 | LAMBADA | MNLI | QQP")
+    g.add_argument("--task", type=str, required=True, help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE")
     g.add_argument("--train-data", nargs="*", default=None)
     g.add_argument("--epochs", type=int, default=3)
     g.add_argument("--valid-data", nargs="*", default=None, help="path(s) to the evaluation text")
@@ -28,6 +28,8 @@ if __name__ == "__main__":
         from tasks.zeroshot_gpt.evaluate import main
     elif args.task in ("MNLI", "QQP"):
         from tasks.glue.finetune import main
+    elif args.task == "RACE":
+        from tasks.race.finetune import main
     else:
         raise NotImplementedError(f"Task {args.task} is not implemented.")
     main()

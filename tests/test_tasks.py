@@ -101,3 +101,22 @@ def test_glue_classification_finetune_learns(tmp_path):
     mc = MultipleChoice(cfg, bert_layer_local_spec(), 64, 16)
     scores = mc(torch.randint(3, 64, (2, 4, 12)), torch.ones(2, 4, 12, dtype=torch.long), torch.zeros(2, 4, 12, dtype=torch.long))
     assert scores.shape == (2, 4)
+
+
+def test_race_dataset_rows(tmp_path):
+    from tasks.race.data import RaceDataset
+
+    class Tok:
+        cls, sep, pad = 1, 2, 0
+
+        def tokenize(self, t):
+            return [3 + (sum(map(ord, w)) % 60) for w in t.split()]
+
+    p = tmp_path / "r.txt"
+    p.write_text(json.dumps({"article": "the cat sat on the mat " * 5, "questions": ["where did the cat sit ?", "the cat sat on the _ ."],
+                             "options": [["mat", "roof", "car", "tree"]] * 2, "answers": ["A", "A"]}) + "\n")
+    ds = RaceDataset("validation", [str(p)], Tok(), 24)
+    assert len(ds) == 2
+    s = ds[1]
+    assert s["text"].shape == (4, 24) and int(s["label"]) == 0 and s["text"][:, 0].eq(1).all()
+    assert (s["types"][0] == 1).sum() > 0 and s["padding_mask"].shape == (4, 24)
