@@ -186,3 +186,37 @@ def test_t5_masked_dataset(tmp_path):
         assert lab[n_out - 1] == 5 and lab[:n_out - 1] == dec[1:n_out]           # teacher forcing shift
         assert s["dec_mask"][0, 1] == 0 and s["dec_mask"][1, 0] == 1               # causal decoder mask
         assert s["enc_dec_mask"].shape == (32, 64)
+
+
+def test_retro_neighbor_database(tmp_path):
+    """tools/retro/build_db.py: chunking, exact neighbour search, same-document exclusion."""
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    from megatronapp_b200.data.indexed_dataset import IndexedDatasetBuilder, get_bin_path, get_idx_path
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("retro_build_db", os.path.join(root, "tools", "retro", "build_db.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    prefix = str(tmp_path / "corpus")
+    b = IndexedDatasetBuilder(get_bin_path(prefix), dtype=np.int32)
+    rng = np.random.RandomState(0)
+    base = rng.randint(5, 50, size=32)
+    base2 = rng.randint(50, 100, size=32)
+    for d in range(6):
+        # documents 0/1 and 2/3 share their opening chunk (near duplicates); 4, 5 are unrelated
+        head = base if d < 2 else (base2 if d < 4 else rng.randint(100, 200, size=32))
+        b.add_item(torch.from_numpy(np.concatenate([head, rng.randint(200, 250, size=32)]).astype(np.int64)))
+        b.end_document()
+    b.finalize(get_idx_path(prefix))
+    nbr, retrieved = mod.main(["--data-prefix", prefix, "--out", str(tmp_path / "work"), "--chunk-length", "32",
+                               "--num-neighbors", "1", "--retrieved-length", "48", "--vocab-size", "256"])
+    doc = np.load(tmp_path / "work" / "chunk_doc_ids.npy")
+    assert len(doc) == 12 and retrieved.shape == (12, 1, 48)
+    first = {d: int(np.where(doc == d)[0][0]) for d in range(6)}
+    assert doc[nbr[first[0], 0]] == 1 and doc[nbr[first[1], 0]] == 0        # near-duplicate openings find each other
+    assert doc[nbr[first[2], 0]] == 3
+    assert all(doc[nbr[i, 0]] != doc[i] for i in range(12))                  # never the same document
