@@ -270,3 +270,25 @@ def test_heterogeneous_gpt_layers():
     pos = torch.arange(16).unsqueeze(0).expand(2, -1)
     losses = _train(m, lambda: m(toks, pos, None, labels=torch.roll(toks, -1, 1)).mean(), steps=8, lr=1e-2)
     assert losses[-1] < losses[0]
+
+
+def test_bert_embedder_mean_pools_non_padding():
+    import importlib.util
+    import os
+
+    from megatronapp_b200.models.bert.bert_model import BertModel, bert_layer_local_spec
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bert_embed", os.path.join(root, "tools", "bert_embedding", "embed.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _init()
+    m = BertModel(_cfg(kernel_backend="torch"), 2, bert_layer_local_spec(), 64, 16)
+    emb = mod.BertEmbedder(m, batch_size=2)
+    ids = torch.randint(1, 64, (3, 16))
+    ids[0, 10:] = 0
+    e = emb(ids)
+    assert e.shape == (3, 32) and torch.isfinite(e).all()
+    ids2 = ids.clone()
+    ids2[0, 10:] = 0                      # identical -> identical embedding; padding content is masked out
+    assert torch.allclose(emb(ids2)[0], e[0], atol=1e-6)
