@@ -1,3 +1,4 @@
-from .core import (DynamicInferenceEngine, GPTInferenceWrapper, InferenceParams, InferenceRequest, SamplingParams,  # noqa: F401
+from .core import (GPTInferenceWrapper, InferenceParams, InferenceRequest, SamplingParams,  # noqa: F401
                    Scheduler, StaticInferenceContext, StaticInferenceEngine, Status, TextGenerationController,
                    sample_from_logits)
+from .dynamic import BlockAllocator, DynamicInferenceContext, DynamicInferenceEngine  # noqa: F401

@@ -273,15 +273,3 @@ class StaticInferenceEngine:
             active = self.scheduler.active_request_pool
             self.controller.generate_all_output_tokens_static_batch(active)
             self.scheduler.update_requests_pools(active)
-
-
-class DynamicInferenceEngine(StaticInferenceEngine):
-    """Continuous batching at request granularity: finished requests leave the active pool and
-    waiting ones join between decode batches (the reference additionally pages the KV cache)."""
-
-    def step(self):
-        if self.scheduler.have_requests_pending():
-            active = self.scheduler.active_request_pool
-            self.controller.generate_all_output_tokens_static_batch(active)
-            self.scheduler.update_requests_pools(active)
-        return list(self.scheduler.completed_request_pool.values())

@@ -390,6 +390,14 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--bert-embedder-type", default="megatron", choices=["megatron", "huggingface"])
     _add(g, "--flash-decode", action="store_true")
     _add(g, "--inference-max-seq-length", type=int, default=2560, dest="inference_max_seq_length")
+    _add(g, "--inference-dynamic-batching", action="store_true")
+    _add(g, "--inference-dynamic-batching-buffer-size-gb", type=float, default=40.0)
+    _add(g, "--inference-dynamic-batching-buffer-guaranteed-fraction", type=float, default=0.2)
+    _add(g, "--inference-dynamic-batching-buffer-overflow-factor", type=float, default=None)
+    _add(g, "--inference-dynamic-batching-max-requests-override", type=int, default=None)
+    _add(g, "--inference-dynamic-batching-max-tokens-override", type=int, default=None)
+    _add(g, "--inference-dynamic-batching-chunk-size", type=int, default=256,
+         help="tokens per KV block of the paged cache")
     _add(g, "--inference-max-batch-size", type=int, default=8, dest="inference_max_requests")
     g = p.add_argument_group("MegaScan")
     _add(g, "--trace", action="store_true")

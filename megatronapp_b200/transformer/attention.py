@@ -160,6 +160,8 @@ class Attention(MegatronModule):
                 output, bias = self.linear_proj(packed)
                 return output, bias
             query, key, value = self.get_query_key_value_tensors(hidden_states, key_value_states)
+            if inference_context is not None and not inference_context.is_static_batching():
+                return self._dynamic_batch_attention(query, key, value, rotary_pos_emb, inference_context)
             if rotary_pos_emb is not None:
                 q_cs, k_cs = rotary_pos_emb if isinstance(rotary_pos_emb, tuple) else (rotary_pos_emb, rotary_pos_emb)
                 if inference_context is not None:
@@ -182,6 +184,16 @@ class Attention(MegatronModule):
                                            packed_seq_params=packed_seq_params)
             output, bias = self.linear_proj(core)
         return output, bias
+
+
+    def _dynamic_batch_attention(self, query, key, value, rotary_pos_emb, ctx):
+        """Packed token batch ``[T, 1, ...]`` against the paged KV cache (``inference/dynamic.py``)."""
+        if rotary_pos_emb is not None:
+            q_cs, k_cs = rotary_pos_emb if isinstance(rotary_pos_emb, tuple) else (rotary_pos_emb, rotary_pos_emb)
+            query = ops.rope(query, q_cs[ctx.positions].contiguous(), self.config.rotary_interleaved)
+            key = ops.rope(key, k_cs[ctx.positions].contiguous(), self.config.rotary_interleaved)
+        o = ctx.attend(self.layer_number, query[:, 0], key[:, 0], value[:, 0], self.core_attention.softmax_scale)
+        return self.linear_proj(o.reshape(o.shape[0], 1, -1))
 
 
 class SelfAttention(Attention):

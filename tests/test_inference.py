@@ -135,3 +135,63 @@ def test_openai_completions_endpoint(engine):
         assert len(out["choices"][0]["text"].split()) == 4
     finally:
         srv.shutdown()
+
+
+def test_dynamic_engine_paged_kv_matches_static(engine):
+    """Continuous batching + chunked prefill + paged KV give the same greedy tokens as the static engine."""
+    from megatronapp_b200.inference import DynamicInferenceEngine
+
+    eng, model = engine
+    prompts = ["5 9 23 7 8 1 2 3 4 6 10 12", "11 3", "40 41 42 43 44", "7"]
+    sp = SamplingParams(top_k=1, num_tokens_to_generate=7)
+    ref = [eng.generate([p], sp)[0].generated_tokens.tolist() for p in prompts]
+    dyn = DynamicInferenceEngine(model, NullTokenizer(127), max_sequence_length=64, num_blocks=32, block_size=4,
+                                 max_tokens_per_step=6, max_requests=3)
+    out = dyn.generate(prompts, sp)
+    assert [o.generated_tokens.tolist() for o in out] == ref
+    assert dyn.context.allocator.free == 32 and not dyn.context.seqs        # every block returned
+    assert dyn.steps < sum(len(p.split()) + 7 for p in prompts)                # requests really shared steps
+
+
+def test_dynamic_engine_preempts_and_recovers_when_out_of_blocks(engine):
+    from megatronapp_b200.inference import DynamicInferenceEngine
+
+    eng, model = engine
+    prompts = ["5 9 23 7", "11 3 8 2", "1 2 3 4"]
+    sp = SamplingParams(top_k=1, num_tokens_to_generate=10)
+    ref = [eng.generate([p], sp)[0].generated_tokens.tolist() for p in prompts]
+    # 3 requests x (4 + 10) tokens need 12 blocks of 4; give 8 so that decode growth forces an eviction
+    dyn = DynamicInferenceEngine(model, NullTokenizer(127), max_sequence_length=64, num_blocks=8, block_size=4,
+                                 max_tokens_per_step=16, max_requests=3)
+    out = dyn.generate(prompts, sp)
+    assert [o.generated_tokens.tolist() for o in out] == ref
+    assert dyn.num_preemptions >= 1 and dyn.context.allocator.free == 8
+
+
+def test_dynamic_engine_behind_rest_server(engine):
+    from types import SimpleNamespace
+
+    from megatronapp_b200.inference import DynamicInferenceEngine
+    from megatronapp_b200.inference.server import MegatronServer
+
+    eng, model = engine
+    args = SimpleNamespace(inference_dynamic_batching_chunk_size=8, bf16=False, fp16=False, tensor_model_parallel_size=1,
+                           pipeline_model_parallel_size=1, inference_dynamic_batching_buffer_size_gb=1e-3,
+                           inference_dynamic_batching_buffer_overflow_factor=None,
+                           inference_dynamic_batching_max_requests_override=4,
+                           inference_dynamic_batching_max_tokens_override=32, inference_max_seq_length=64, seed=1)
+    dyn = DynamicInferenceEngine.from_args(model, NullTokenizer(127), args, model.config)
+    per_tok = 2 * 2 * 4 * 16 * 4
+    assert dyn.context.num_blocks == int(1e-3 * (1 << 30)) // (per_tok * 8)
+    srv = MegatronServer(dyn)
+    srv.run(port=18813, block=False)
+    time.sleep(0.3)
+    try:
+        body = json.dumps({"prompts": ["1 2 3", "9 8"], "tokens_to_generate": 4, "top_k": 1}).encode()
+        req = urllib.request.Request("http://127.0.0.1:18813/api", data=body, method="PUT",
+                                     headers={"Content-Type": "application/json"})
+        out = json.loads(urllib.request.urlopen(req, timeout=30).read())
+        ref = eng.generate(["1 2 3"], SamplingParams(top_k=1, num_tokens_to_generate=4))[0]
+        assert out["tokens"][0][3:] == ref.generated_tokens.tolist()
+    finally:
+        srv.shutdown()

@@ -23,7 +23,13 @@ def main():
         checkpointing.load_checkpoint(model, None, None)
     tok = get_tokenizer()
     wrapper = GPTInferenceWrapper(model[0], args.inference_max_requests, args.inference_max_seq_length, args.padded_vocab_size)
-    engine = StaticInferenceEngine(TextGenerationController(wrapper, tok), args.inference_max_requests)
+    if args.inference_dynamic_batching:
+        from megatronapp_b200.inference import DynamicInferenceEngine
+        from megatronapp_b200.training.arguments import core_transformer_config_from_args
+
+        engine = DynamicInferenceEngine.from_args(model[0], tok, args, core_transformer_config_from_args(args))
+    else:
+        engine = StaticInferenceEngine(TextGenerationController(wrapper, tok), args.inference_max_requests)
     if args.enable_ws_server:
         InferenceWSServer(engine, args.num_layers, tok, port=args.ws_port).run()
     else:
