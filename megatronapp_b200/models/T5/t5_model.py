@@ -64,7 +64,8 @@ class T5Model(LanguageModule):
     def __init__(self, config, encoder_config, transformer_encoder_layer_spec, transformer_decoder_layer_spec,
                  vocab_size: int, max_sequence_length: int, pre_process=True, post_process=True,
                  fp16_lm_cross_entropy=False, parallel_output=True, share_embeddings_and_output_weights=True,
-                 position_embedding_type="learned_absolute", add_encoder=True, add_decoder=True):
+                 position_embedding_type="learned_absolute", add_encoder=True, add_decoder=True,
+                 relative_attention_num_buckets: int = 32, relative_attention_max_distance: int = 128):
         super().__init__(config)
         self.pre_process, self.post_process = pre_process, post_process
         self.add_encoder, self.add_decoder = add_encoder, add_decoder
@@ -72,6 +73,18 @@ class T5Model(LanguageModule):
         self.encoder_hidden_state = None
         if pre_process:
             self.embedding = LanguageModelEmbedding(config, vocab_size, max_sequence_length, position_embedding_type)
+        self.position_embedding_type = position_embedding_type
+        if position_embedding_type == "relative":       # reference t5_model.py: one bias table per stack
+            from ..common.embeddings import RelativePositionEmbedding
+
+            if add_encoder:
+                self.encoder_relative_pos_emb = RelativePositionEmbedding(
+                    True, config.init_method, config.num_attention_heads, relative_attention_num_buckets,
+                    relative_attention_max_distance)
+            if add_decoder:
+                self.decoder_relative_pos_emb = RelativePositionEmbedding(
+                    False, config.init_method, config.num_attention_heads, relative_attention_num_buckets,
+                    relative_attention_max_distance)
         if add_encoder:
             self.encoder = TransformerBlock(encoder_config or config, transformer_encoder_layer_spec,
                                             pre_process=pre_process, post_process=True)
@@ -110,14 +123,22 @@ class T5Model(LanguageModule):
                                                                   encoder_decoder_attn_mask])
         if self.add_encoder and encoder_hidden_states is None:
             x = self.embedding(encoder_input_ids, pos(encoder_input_ids)) if self.pre_process else None
-            enc = self.encoder(hidden_states=x, attention_mask=enc_mask)
+            enc_bias = None
+            if self.position_embedding_type == "relative":
+                n = self.encoder_relative_pos_emb.get_relative_seq_len(None, self.encoder, x, self.config)
+                enc_bias = self.encoder_relative_pos_emb(n, n)
+            enc = self.encoder(hidden_states=x, attention_mask=enc_mask, attention_bias=enc_bias)
         else:
             enc = encoder_hidden_states if encoder_hidden_states is not None else self.encoder_hidden_state
         if not self.add_decoder or output_encoder_hidden_only:
             return enc
         y = self.embedding(decoder_input_ids, pos(decoder_input_ids)) if self.pre_process else None
+        dec_bias = None
+        if self.position_embedding_type == "relative":
+            n = self.decoder_relative_pos_emb.get_relative_seq_len(inference_context, self.decoder, y, self.config)
+            dec_bias = self.decoder_relative_pos_emb(n, n)
         dec = self.decoder(hidden_states=y, attention_mask=dec_mask, context=enc, context_mask=ed_mask,
-                           inference_context=inference_context)
+                           attention_bias=dec_bias, inference_context=inference_context)
         if not self.post_process:
             return dec
         w = self.shared_embedding_or_output_weight() if self.share_embeddings_and_output_weights else None

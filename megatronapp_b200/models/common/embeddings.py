@@ -167,3 +167,46 @@ class YarnRotaryEmbedding(RotaryEmbedding):
     def forward(self, max_seq_len, offset=0, device=None):
         t = super().forward(max_seq_len, offset, device)
         return t * self.concentration if self.concentration != 1.0 else t
+
+
+class RelativePositionEmbedding(torch.nn.Module):
+    """T5 bucketed relative position bias (reference ``models/common/embeddings/relative_pos_embedding.py:19``):
+    ``forward(sq, sk) -> [1, heads, sq, sk]`` added to the attention scores.  Half of the buckets are exact
+    small offsets, the rest are log-spaced up to ``max_distance``; the bidirectional (encoder) variant spends
+    half of the buckets on each sign, the causal (decoder) variant only looks backwards."""
+
+    def __init__(self, bidirectional: bool, init_method, num_attention_heads: int,
+                 relative_attention_num_buckets: int = 32, relative_attention_max_distance: int = 128):
+        super().__init__()
+        self.bidirectional = bidirectional
+        self.num_buckets, self.max_distance = relative_attention_num_buckets, relative_attention_max_distance
+        self.relative_attention_bias = torch.nn.Embedding(self.num_buckets, num_attention_heads)
+        init_method(self.relative_attention_bias.weight)
+
+    def bucket(self, rel: torch.Tensor) -> torch.Tensor:
+        """``rel = key_pos - query_pos`` (long) -> bucket id in ``[0, num_buckets)``."""
+        n = self.num_buckets
+        base = torch.zeros_like(rel)
+        if self.bidirectional:
+            n //= 2
+            base = (rel > 0).long() * n
+            dist = rel.abs()
+        else:
+            dist = (-rel).clamp_min(0)
+        exact = n // 2
+        log_b = exact + (torch.log(dist.clamp_min(1).float() / exact) / math.log(self.max_distance / exact)
+                         * (n - exact)).long()
+        return base + torch.where(dist < exact, dist, log_b.clamp_max(n - 1))
+
+    def forward(self, query_seq_length: int, key_seq_length: int) -> torch.Tensor:
+        dev = self.relative_attention_bias.weight.device
+        rel = torch.arange(key_seq_length, device=dev)[None, :] - torch.arange(query_seq_length, device=dev)[:, None]
+        return self.relative_attention_bias(self.bucket(rel)).permute(2, 0, 1).unsqueeze(0)
+
+    @staticmethod
+    def get_relative_seq_len(inference_context, transformer, transformer_input, transformer_config) -> int:
+        if inference_context is not None:
+            return inference_context.max_sequence_length
+        t = getattr(transformer, "input_tensor", None)
+        s = (t if t is not None else transformer_input).size(0)
+        return s * transformer_config.tensor_model_parallel_size if transformer_config.sequence_parallel else s

@@ -405,7 +405,7 @@ def rope(x, cos_sin, interleaved=False):
 # attention.  q,k,v: [b, h, s, d]
 # ---------------------------------------------------------------------------
 
-def attention_ref(q, k, v, scale=None, causal=True, dropout_p=0.0, return_probs=False, mask=None):
+def attention_ref(q, k, v, scale=None, causal=True, dropout_p=0.0, return_probs=False, mask=None, bias=None):
     b, hq, sq, d = q.shape
     hkv = k.shape[1]
     if hkv != hq:
@@ -413,6 +413,8 @@ def attention_ref(q, k, v, scale=None, causal=True, dropout_p=0.0, return_probs=
         v = v.repeat_interleave(hq // hkv, dim=1)
     scale = scale if scale is not None else 1.0 / math.sqrt(d)
     s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
+    if bias is not None:                    # additive [1|b, h, sq, sk] (T5 relative position bias)
+        s = s + bias.float()
     sk = k.shape[2]
     if causal:
         cm = torch.ones(sq, sk, dtype=torch.bool, device=q.device).tril(diagonal=sk - sq)
@@ -504,7 +506,7 @@ def _attn_view_ok(t) -> bool:
             and t.data_ptr() % 16 == 0)
 
 
-def attention(q, k, v, scale=None, causal=True, dropout_p=0.0, training=True, mask=None):
+def attention(q, k, v, scale=None, causal=True, dropout_p=0.0, training=True, mask=None, bias=None):
     """Fused attention on logical ``[b, h, s, d]`` tensors (any strides with a contiguous last dim,
     e.g. permuted ``[s, b, h, d]`` activations -- consumed in place through 4-D tensor maps).
     Native tcgen05 kernels when usable; otherwise the SDPA library kernel on CUDA (counted in
@@ -512,8 +514,8 @@ def attention(q, k, v, scale=None, causal=True, dropout_p=0.0, training=True, ma
     d = q.shape[-1]
     scale = scale if scale is not None else 1.0 / math.sqrt(d)
     p = dropout_p if training else 0.0
-    if not q.is_cuda:
-        return attention_ref(q, k, v, scale, causal, p, mask=mask)
+    if not q.is_cuda or bias is not None:       # a learned additive bias needs d(bias): autograd through the reference
+        return attention_ref(q, k, v, scale, causal, p, mask=mask, bias=bias)
     impl = _ATTN_IMPL
     sq, sk = q.shape[2], k.shape[2]
     needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)

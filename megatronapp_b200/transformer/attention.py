@@ -70,7 +70,12 @@ class DotProductAttention(MegatronModule):
         self.cp_comm_type = cct or "p2p"
         self.cp_size = config.context_parallel_size
 
-    def _attend(self, q, k, v, causal, dropout_p, mask):
+    def _attend(self, q, k, v, causal, dropout_p, mask, bias=None):
+        if bias is not None:
+            if bias.shape[1] != q.shape[1]:        # full-head bias under TP: this rank's head slice
+                r = ps.get_tensor_model_parallel_rank()
+                bias = bias[:, r * q.shape[1]:(r + 1) * q.shape[1]]
+            return ops.attention(q, k, v, self.softmax_scale, causal, dropout_p, self.training, mask, bias=bias)
         if self.cp_size > 1 and self.attention_type == "self":
             from ..parallel.context_parallel import cp_attention
 
@@ -90,15 +95,16 @@ class DotProductAttention(MegatronModule):
         want_probs = scope_hooks.wants(2, self.layer_number)
         mask = None if causal else attention_mask
         if want_probs:
-            o, probs = ops.attention_ref(q, k, v, self.softmax_scale, causal, 0.0, return_probs=True, mask=mask)
+            o, probs = ops.attention_ref(q, k, v, self.softmax_scale, causal, 0.0, return_probs=True, mask=mask,
+                                         bias=attention_bias)
             scope_hooks.tik_tensor(2, self.layer_number, probs)
         else:
             if self.dropout_p > 0.0 and self.training:
                 with get_cuda_rng_tracker().fork() if "model-parallel-rng" in get_cuda_rng_tracker().states_ \
                         else torch.random.fork_rng(devices=[]):
-                    o = self._attend(q, k, v, causal, self.dropout_p, mask)
+                    o = self._attend(q, k, v, causal, self.dropout_p, mask, attention_bias)
             else:
-                o = self._attend(q, k, v, causal, 0.0, mask)
+                o = self._attend(q, k, v, causal, 0.0, mask, attention_bias)
         ctx = o.permute(2, 0, 1, 3).reshape(sq, b, self.np * self.hn)
         scope_hooks.tik_tensor(3, self.layer_number, ctx)
         return ctx
@@ -154,8 +160,8 @@ class Attention(MegatronModule):
                 packed_seq_params=None, sequence_len_offset=None, inference_params=None):
         inference_context = inference_context or inference_params
         with _scope("attention"):
-            packed = self._packed_self_attention(hidden_states, attention_mask, rotary_pos_emb, inference_context,
-                                                 packed_seq_params)
+            packed = None if attention_bias is not None else self._packed_self_attention(
+                hidden_states, attention_mask, rotary_pos_emb, inference_context, packed_seq_params)
             if packed is not None:
                 output, bias = self.linear_proj(packed)
                 return output, bias
@@ -177,11 +183,12 @@ class Attention(MegatronModule):
             if self.checkpoint_core_attention and self.training:
                 from ..parallel.random import checkpoint
 
-                core = checkpoint(lambda q, k, v: self.core_attention(q, k, v, attention_mask, mask_type),
+                core = checkpoint(lambda q, k, v: self.core_attention(q, k, v, attention_mask, mask_type,
+                                                                      attention_bias=attention_bias),
                                   False, query, key, value)
             else:
                 core = self.core_attention(query, key, value, attention_mask, attn_mask_type=mask_type,
-                                           packed_seq_params=packed_seq_params)
+                                           attention_bias=attention_bias, packed_seq_params=packed_seq_params)
             output, bias = self.linear_proj(core)
         return output, bias
 

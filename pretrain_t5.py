@@ -41,6 +41,7 @@ def model_provider(pre_process=True, post_process=True, add_encoder=True, add_de
                    vocab_size=args.padded_vocab_size, max_sequence_length=args.max_position_embeddings,
                    pre_process=pre_process, post_process=post_process, parallel_output=True,
                    share_embeddings_and_output_weights=not args.untie_embeddings_and_output_weights,
+                   position_embedding_type=args.position_embedding_type,
                    add_encoder=add_encoder, add_decoder=add_decoder)
 
 

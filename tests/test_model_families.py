@@ -292,3 +292,34 @@ def test_bert_embedder_mean_pools_non_padding():
     ids2 = ids.clone()
     ids2[0, 10:] = 0                      # identical -> identical embedding; padding content is masked out
     assert torch.allclose(emb(ids2)[0], e[0], atol=1e-6)
+
+
+def test_relative_position_embedding_buckets_and_t5_relative():
+    from megatronapp_b200.models.common.embeddings import RelativePositionEmbedding
+    from megatronapp_b200.models.T5 import T5Model, get_t5_decoder_block_spec, get_t5_encoder_block_spec
+
+    init = lambda w: torch.nn.init.normal_(w, std=0.5)
+    bi = RelativePositionEmbedding(True, init, 4, 32, 128)
+    rel = torch.tensor([0, 1, -1, 7, 8, 20, 60, 128, 500, -500])
+    b = bi.bucket(rel)
+    # bidirectional: 16 buckets per sign, 8 exact, log-spaced afterwards, saturating at max_distance
+    assert b.tolist()[:5] == [0, 17, 1, 23, 24] and b[6] < b[7] == b[8] == 31 and b[9] == 15
+    uni = RelativePositionEmbedding(False, init, 4, 32, 128)
+    u = uni.bucket(torch.tensor([3, 0, -1, -15, -16, -1000]))
+    assert u.tolist()[:4] == [0, 0, 1, 15] and u[4] == 16 and u[5] == 31
+    bias = bi(6, 9)
+    assert bias.shape == (1, 4, 6, 9)
+    assert torch.equal(bias[0, :, 2, 5], bias[0, :, 0, 3])        # depends on the offset only
+
+    _init()
+    cfg = _cfg()
+    m = T5Model(cfg, cfg, get_t5_encoder_block_spec(2), get_t5_decoder_block_spec(2), vocab_size=64, max_sequence_length=16,
+                position_embedding_type="relative")
+    assert not any("position_embeddings" in n for n, _ in m.named_parameters())
+    enc, dec = torch.randint(0, 64, (2, 12)), torch.randint(0, 64, (2, 8))
+    em = torch.ones(2, 12, 12)
+    dm = torch.tril(torch.ones(8, 8)).unsqueeze(0).expand(2, -1, -1)
+    edm = torch.ones(2, 8, 12)
+    ls = _train(m, lambda: m(enc, dec, em, dm, edm, lm_labels=dec).mean())
+    assert ls[-1] < ls[0]
+    assert m.encoder_relative_pos_emb.relative_attention_bias.weight.grad is not None
