@@ -335,11 +335,20 @@ def build_tokenizer(args):
     elif ttype == "HuggingFaceTokenizer":
         tok = HuggingFaceTokenizer(args.tokenizer_model)
     elif ttype == "TikTokenizer":
-        try:
-            import tiktoken  # noqa: F401
-        except ImportError as e:
-            raise ImportError("TikTokenizer needs the tiktoken package, which is not installed") from e
-        raise NotImplementedError("TikTokenizer: provide --tokenizer-model with a tiktoken vocabulary")
+        from .tokenizer_extra import TikTokenizer
+
+        tok = TikTokenizer(args.tokenizer_model, getattr(args, "tiktoken_pattern", None) or "v2", args.vocab_size,
+                           getattr(args, "tiktoken_num_special_tokens", 1000), getattr(args, "tiktoken_special_tokens", None))
+    elif ttype == "MultimodalTokenizer":
+        from .tokenizer_extra import MultimodalTokenizer
+
+        inner = HuggingFaceTokenizer(args.tokenizer_model) if args.tokenizer_model else NullTokenizer(args.vocab_size or 50256)
+        tok = MultimodalTokenizer(inner, getattr(args, "tokenizer_prompt_format", None) or "chatml",
+                                  getattr(args, "special_tokens", None), getattr(args, "image_tag_type", None) or "")
+    elif ttype == "NullMultimodalTokenizer":
+        from .tokenizer_extra import NullMultimodalTokenizer
+
+        tok = NullMultimodalTokenizer(args.vocab_size if args.vocab_size is not None else 50256)
     else:
         raise NotImplementedError(f"{ttype} tokenizer is not implemented")
     if getattr(args, "padded_vocab_size", None) is None:

@@ -351,6 +351,9 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--tiktoken-pattern", type=str, default=None)
     _add(g, "--tiktoken-num-special-tokens", type=int, default=1000)
     _add(g, "--tiktoken-special-tokens", type=str, nargs="+", default=None)
+    _add(g, "--tokenizer-prompt-format", type=str, default=None)
+    _add(g, "--special-tokens", type=str, nargs="*", default=None)
+    _add(g, "--image-tag-type", type=str, default=None, choices=["nvlm", "internvl", ""])
     g = p.add_argument_group("logging")
     _add(g, "--log-params-norm", action="store_true")
     _add(g, "--log-num-zeros-in-grad", action="store_true")

@@ -220,3 +220,44 @@ def test_retro_neighbor_database(tmp_path):
     assert doc[nbr[first[0], 0]] == 1 and doc[nbr[first[1], 0]] == 0        # near-duplicate openings find each other
     assert doc[nbr[first[2], 0]] == 3
     assert all(doc[nbr[i, 0]] != doc[i] for i in range(12))                  # never the same document
+
+
+def test_tiktokenizer_rank_bpe_and_multimodal_tokenizers(tmp_path):
+    import base64
+    import json
+
+    from megatronapp_b200.data.tokenizer_extra import (DEFAULT_IMAGE_TOKEN_INDEX, IGNORE_INDEX, MultimodalTokenizer,
+                                                       NullMultimodalTokenizer, TikTokenizer)
+
+    # 256 byte tokens + a few merges, in the reference's JSON layout
+    merges = [b"he", b"ll", b"hell", b"hello", b" w", b"or", b" wor", b"ld", b" world"]
+    vocab = [bytes([i]) for i in range(256)] + merges
+    path = tmp_path / "tok.json"
+    path.write_text(json.dumps([{"rank": i, "token_bytes": base64.b64encode(t).decode(), "token_str": repr(t)}
+                                for i, t in enumerate(vocab)]))
+    tk = TikTokenizer(str(path), "v2", None, num_special_tokens=8)
+    assert tk.vocab_size == 8 + len(vocab) and (tk.unk, tk.bos, tk.eos) == (0, 1, 2)
+    ids = tk.tokenize("hello world", bos=True, eos=True)
+    assert ids == [1, 8 + 256 + 3, 8 + 256 + 8, 2]                    # <s> "hello" " world" </s>
+    assert tk.detokenize(ids) == "<s>hello world</s>"
+    s = "héllo wörld ☃ 12 x"
+    assert tk.detokenize(tk.tokenize(s)) == s                          # byte fallback round-trips any utf-8
+    # lowest-rank pair merges first: "hel" -> "he" + "l" (not "h" + "el")
+    assert tk.tokenize("hel") == [8 + 256, 8 + ord("l")]
+
+    mm = MultimodalTokenizer(tk, "chatml", special_tokens=["<|im_start|>", "<|im_end|>"], image_tag_type="internvl")
+    conv = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "<image>\nwhat?"},
+            {"role": "assistant", "content": "a cat"}]
+    toks, tgt = mm.tokenize_conversation(conv, True, False)
+    assert len(toks) == len(tgt) and DEFAULT_IMAGE_TOKEN_INDEX in toks
+    kept = tgt != IGNORE_INDEX
+    assert mm.detokenize(toks[kept]) == "a cat<|im_end|>\n"             # only the assistant answer is a target
+    assert mm.detokenize(toks).startswith("<|im_start|>system\nbe brief<|im_end|>\n<|im_start|>user\n<img><image></img>")
+    gen = mm.tokenize(conv[:2])
+    assert mm.detokenize(gen).endswith("<|im_start|>assistant\n")
+    assert mm.convert_tokens_to_ids("<image>") == DEFAULT_IMAGE_TOKEN_INDEX
+    assert mm.vocab_size == tk.vocab_size + 2
+
+    nm = NullMultimodalTokenizer(100)
+    assert nm.tokenize("5 <image> 7") == [5, DEFAULT_IMAGE_TOKEN_INDEX, 7] and nm.detokenize([5, -200, 7]) == "5 <image> 7"
+    assert nm.vocab_size == 101 and nm.eod == 100
