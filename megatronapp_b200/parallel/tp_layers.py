@@ -221,6 +221,18 @@ def linear_with_grad_accumulation_and_async_allreduce(
                                    allreduce_dgrad)
 
 
+def linear_with_frozen_weight(input, weight, bias, gradient_accumulation_fusion=False, allreduce_dgrad=None,
+                              sequence_parallel=False, tp_group=None, grad_output_buffer=None,
+                              wgrad_deferral_limit=None, async_grad_allreduce=None):
+    """Column-parallel linear whose weight does not train (reference ``tensor_parallel/layers.py:295-401``):
+    same forward and dgrad (+ its collective) as the trainable path, no wgrad GEMM and no activation re-gather."""
+    if weight.requires_grad:
+        raise RuntimeError("linear_with_frozen_weight: weight.requires_grad must be False")
+    if allreduce_dgrad is None:
+        allreduce_dgrad = bool(async_grad_allreduce)
+    return _ColumnParallelFn.apply(input, weight, bias, sequence_parallel, False, allreduce_dgrad)
+
+
 class ColumnParallelLinear(nn.Module):
     """Y = X A^T + b with A split along its output dim: A = [A_1; ...; A_p]."""
 

@@ -143,6 +143,8 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--exit-interval", type=int, default=None)
     _add(g, "--exit-duration-in-mins", type=int, default=None)
     _add(g, "--exit-signal-handler", action="store_true")
+    _add(g, "--adlr-autoresume", action="store_true")
+    _add(g, "--adlr-autoresume-interval", type=int, default=1000)
     _add(g, "--tensorboard-dir", type=str, default=None)
     _add(g, "--no-masked-softmax-fusion", action="store_false", dest="masked_softmax_fusion")
     _add(g, "--no-bias-gelu-fusion", action="store_false", dest="bias_gelu_fusion")

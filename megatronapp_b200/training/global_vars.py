@@ -80,6 +80,10 @@ def set_global_variables(args, build_tokenizer: bool = True):
     tracer = _get_tracer()
     tracer.configure(args.trace, args.trace_dir, args.trace_interval, args.continuous_trace_iterations,
                      args.trace_granularity)
+    if getattr(args, "adlr_autoresume", False):
+        from .autoresume import build_autoresume
+
+        build_autoresume()
     if args.exit_signal_handler:
         from .signals import DistributedSignalHandler
 

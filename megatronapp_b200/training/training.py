@@ -500,6 +500,16 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             print_rank_0("exiting program after receiving SIGTERM.")
             exit_flag = True
             break
+        if getattr(args, "adlr_autoresume", False) and iteration % args.adlr_autoresume_interval == 0:
+            from .autoresume import check_adlr_autoresume_termination
+
+            def _save(it, m, o, s_):
+                if args.save:
+                    save_checkpoint_and_time(it, m, o, s_, nflops)
+
+            if check_adlr_autoresume_termination(iteration, model, optimizer, opt_param_scheduler, _save):
+                exit_flag = True
+                break
         if args.save and args.save_interval and iteration % args.save_interval == 0:
             timers("interval-time").stop()
             save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, nflops)

@@ -261,3 +261,30 @@ def test_tiktokenizer_rank_bpe_and_multimodal_tokenizers(tmp_path):
     nm = NullMultimodalTokenizer(100)
     assert nm.tokenize("5 <image> 7") == [5, DEFAULT_IMAGE_TOKEN_INDEX, 7] and nm.detokenize([5, -200, 7]) == "5 <image> 7"
     assert nm.vocab_size == 101 and nm.eod == 100
+
+
+def test_blended_megatron_dataset_builder(tmp_path):
+    from megatronapp_b200.data.blended_builder import (BlendedMegatronDatasetBuilder, GPTDatasetConfig,
+                                                      get_blend_from_list)
+
+    p1, _ = _make_corpus(tmp_path, 60, 0, "a")
+    p2, _ = _make_corpus(tmp_path, 60, 1, "b")
+    assert get_blend_from_list(["0.3", p1, "0.7", p2]) == ([p1, p2], [0.3, 0.7])
+    assert get_blend_from_list([p1, p2]) == ([p1, p2], None)
+    cfg = GPTDatasetConfig(random_seed=1, sequence_length=8, blend=([p1, p2], [0.25, 0.75]), split="8,1,1",
+                           path_to_cache=str(tmp_path / "cache"))
+    assert cfg.split_matrix[0] == (0.0, 0.8) and abs(cfg.split_matrix[2][1] - 1.0) < 1e-9
+    tr, va, te = BlendedMegatronDatasetBuilder(GPTDataset, [200, 20, None], lambda: True, cfg).build()
+    assert len(tr) == 200 and abs(float((tr.dataset_index == 1).mean()) - 0.75) < 0.02
+    assert len(va) == 20 and te is not None and te[0]["tokens"].shape == (8,)      # None size = one exhaustive epoch
+    assert BlendedMegatronDatasetBuilder(GPTDataset, [200, 20, 5], lambda: False, cfg).build() == [None, None, None]
+    # independent blends per split
+    cfg2 = GPTDatasetConfig(random_seed=1, sequence_length=8, blend_per_split=[([p1], None), ([p2], None), None])
+    tr2, va2, te2 = BlendedMegatronDatasetBuilder(GPTDataset, [50, 10, 10], lambda: True, cfg2).build()
+    assert len(tr2) >= 50 and len(va2) >= 10 and te2 is None
+    with pytest.raises(ValueError):
+        GPTDatasetConfig(random_seed=1, sequence_length=8, blend=([p1], None), blend_per_split=[([p1], None), None, None])
+    # no blend at all -> mock data
+    cfg3 = GPTDatasetConfig(random_seed=1, sequence_length=8, tokenizer=NullTokenizer(99))
+    tr3, _, _ = BlendedMegatronDatasetBuilder(GPTDataset, [7, 0, 0], lambda: True, cfg3).build()
+    assert cfg3.mock and len(tr3) == 7 and int(tr3[0]["tokens"].max()) < 100

@@ -92,3 +92,20 @@ def test_yaml_arguments_and_config_logger(tmp_path):
     import json
 
     assert json.load(open(fn))["config"]["hidden_size"] == 8
+
+
+def test_file_autoresume_protocol(tmp_path):
+    from megatronapp_b200.training import autoresume as ar
+
+    sentinel = str(tmp_path / "stop")
+    obj = ar.FileAutoResume(sentinel)
+    ar.set_adlr_autoresume(obj)
+    saved = []
+    try:
+        assert not ar.check_adlr_autoresume_termination(3, None, None, None, lambda *a: saved.append(a[0]))
+        open(sentinel, "w").close()
+        assert ar.check_adlr_autoresume_termination(4, None, None, None, lambda *a: saved.append(a[0]))
+        assert saved == [4] and obj.resume_requested and (tmp_path / "stop.resume").exists()
+        assert ar.FileAutoResume(None, deadline=1.0).termination_requested()
+    finally:
+        ar.set_adlr_autoresume(None)

@@ -1,4 +1,5 @@
 """BERT, T5 and Mamba/hybrid models build, run forward+backward and learn on CPU."""
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -323,3 +324,18 @@ def test_relative_position_embedding_buckets_and_t5_relative():
     ls = _train(m, lambda: m(enc, dec, em, dm, edm, lm_labels=dec).mean())
     assert ls[-1] < ls[0]
     assert m.encoder_relative_pos_emb.relative_attention_bias.weight.grad is not None
+
+
+def test_linear_with_frozen_weight_grads_input_only():
+    from megatronapp_b200.parallel.tp_layers import linear_with_frozen_weight
+
+    _init()
+    x = torch.randn(5, 2, 16, requires_grad=True)
+    w, b = torch.randn(24, 16), torch.randn(24)
+    y = linear_with_frozen_weight(x, w, b)
+    y.square().sum().backward()
+    xr = x.detach().clone().requires_grad_()
+    torch.nn.functional.linear(xr, w, b).square().sum().backward()
+    assert torch.allclose(x.grad, xr.grad, atol=1e-4) and w.grad is None
+    with pytest.raises(RuntimeError):
+        linear_with_frozen_weight(x, w.requires_grad_(), b)
