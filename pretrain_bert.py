@@ -39,6 +39,12 @@ def model_provider(pre_process=True, post_process=True):
     args = get_args()
     print_rank_0("building BERT model ...")
     config = core_transformer_config_from_args(args)
+    if args.use_legacy_models:
+        from megatronapp_b200.legacy.model import BertModel as LegacyBertModel
+
+        return LegacyBertModel(config, num_tokentypes=2 if args.bert_binary_head else 0,
+                               add_binary_head=args.bert_binary_head, parallel_output=True, pre_process=pre_process,
+                               post_process=post_process)
     return BertModel(config=config, num_tokentypes=2 if args.bert_binary_head else 0,
                      transformer_layer_spec=bert_layer_local_spec(), vocab_size=args.padded_vocab_size,
                      max_sequence_length=args.max_position_embeddings, pre_process=pre_process,

@@ -26,6 +26,11 @@ def model_provider(pre_process=True, post_process=True):
     args = get_args()
     print_rank_0("building GPT model ...")
     config = core_transformer_config_from_args(args)
+    if args.use_legacy_models:
+        from megatronapp_b200.legacy.model import GPTModel as LegacyGPTModel
+
+        return LegacyGPTModel(config, num_tokentypes=0, parallel_output=True, pre_process=pre_process,
+                              post_process=post_process)
     if args.num_experts:
         spec = get_gpt_decoder_block_spec(config)
     else:

@@ -83,6 +83,13 @@ def test_core_reshard_roundtrip(tmp_path):
     conv.main(["--loader", "core", "--saver", "core", "--load-dir", a, "--save-dir", b])
     again = conv.load_core(b)
     assert all(torch.equal(again["weights"][k], v) for k, v in ck["weights"].items())
+    # legacy (pre-mcore) naming round trip: core -> legacy tp2 -> core
+    c = os.path.join(str(tmp_path), "legacy_tp2")
+    conv.main(["--loader", "core", "--saver", "legacy", "--load-dir", b, "--save-dir", c, "--target-tensor-parallel-size", "2"])
+    leg = torch.load(os.path.join(c, "release", "mp_rank_01", "model_optim_rng.pt"), weights_only=False)["model"]
+    assert "layers.0.self_attention.query_key_value.weight" in leg["language_model"]["encoder"]
+    from_legacy = conv.LOADERS["legacy"](c)
+    assert all(torch.equal(from_legacy["weights"][k], v) for k, v in ck["weights"].items())
 
 
 def test_trtllm_export_layout(tmp_path):

@@ -339,3 +339,43 @@ def test_linear_with_frozen_weight_grads_input_only():
     assert torch.allclose(x.grad, xr.grad, atol=1e-4) and w.grad is None
     with pytest.raises(RuntimeError):
         linear_with_frozen_weight(x, w.requires_grad_(), b)
+
+
+def test_legacy_model_shells_and_state_dict_naming():
+    from types import SimpleNamespace
+
+    from megatronapp_b200.legacy.model import BertModel as LBert, GPTModel as LGPT
+    from megatronapp_b200.legacy.state_dict import core_to_legacy, legacy_to_core
+
+    _init()
+    args = SimpleNamespace(padded_vocab_size=64, max_position_embeddings=16, position_embedding_type="learned_absolute",
+                           untie_embeddings_and_output_weights=False, rotary_percent=1.0, rotary_base=10000)
+    torch.manual_seed(0)
+    m = LGPT(_cfg(), args=args)
+    sd = m.state_dict_for_save_checkpoint()
+    enc = sd["language_model"]["encoder"]
+    assert "weight" in sd["language_model"]["embedding"]["word_embeddings"]
+    for k in ("layers.0.input_norm.weight", "layers.1.self_attention.query_key_value.weight", "layers.0.self_attention.dense.bias",
+              "layers.0.post_attention_norm.weight", "layers.1.mlp.dense_h_to_4h.weight", "layers.1.mlp.dense_4h_to_h.weight",
+              "final_norm.weight"):
+        assert k in enc, k
+    # rename is a bijection on the core keys
+    core_sd = {k: v for k, v in m.language_model.state_dict().items() if not k.endswith("_extra_state")}
+    back = legacy_to_core(core_to_legacy(core_sd))
+    assert back.keys() == core_sd.keys() and all(back[k] is core_sd[k] for k in back)
+    # a second, differently initialised shell reproduces the logits after loading the legacy dict
+    torch.manual_seed(1)
+    m2 = LGPT(_cfg(), args=args)
+    ids = torch.randint(0, 64, (2, 8))
+    pos = torch.arange(8).unsqueeze(0).expand(2, -1)
+    m.eval(), m2.eval()
+    with torch.no_grad():
+        a = m(ids, pos, None)
+        assert not torch.allclose(a, m2(ids, pos, None))
+        m2.load_state_dict(sd)
+        assert torch.allclose(a, m2(ids, pos, None))
+    lb = LBert(_cfg(kernel_backend="torch"), args=args)
+    bsd = lb.state_dict_for_save_checkpoint()
+    assert "layers.0.self_attention.query_key_value.weight" in bsd["language_model"]["encoder"]
+    assert "lm_head" in bsd and "binary_head" in bsd and "pooler" in bsd["language_model"]
+    lb.load_state_dict(bsd)

@@ -91,7 +91,12 @@ def load_core(load_dir: str, iteration=None) -> Dict:
         parts = d.split("_")
         t, p = int(parts[2]), (int(parts[3]) if len(parts) > 3 else 0)
         sd = torch.load(os.path.join(base, d, "model_optim_rng.pt"), map_location="cpu", weights_only=False)
-        shards[(t, p)] = sd["model"]
+        model_sd = sd["model"]
+        if isinstance(model_sd.get("language_model"), dict):       # legacy (pre-mcore) nested naming
+            from megatronapp_b200.legacy.state_dict import legacy_to_core
+
+            model_sd = legacy_to_core(model_sd)
+        shards[(t, p)] = model_sd
         args = args or sd.get("args")
     cfg = _config_from_args(args)
     glu = cfg["gated_linear_unit"]
@@ -122,7 +127,7 @@ def _config_from_args(args) -> Dict:
             "rotary_base": g("rotary_base", 10000), "layernorm_epsilon": g("norm_epsilon", g("layernorm_epsilon", 1e-5))}
 
 
-def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int):
+def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int, legacy: bool = False):
     from megatronapp_b200.training import checkpointing as ck
 
     cfg, weights = ckpt["config"], ckpt["weights"]
@@ -156,7 +161,12 @@ def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int):
             path = ck.get_checkpoint_name(save_dir, it, release=(it == 0), pipeline_parallel=pp > 1, tensor_rank=t,
                                           pipeline_rank=p, expert_parallel=False, expert_rank=0)
             os.makedirs(os.path.dirname(path), exist_ok=True)
-            torch.save({"model": {k: v[t] for k, v in stage.items()}, "args": args, "iteration": it,
+            model_sd = {k: v[t] for k, v in stage.items()}
+            if legacy:
+                from megatronapp_b200.legacy.state_dict import core_to_legacy
+
+                model_sd = core_to_legacy(model_sd)
+            torch.save({"model": model_sd, "args": args, "iteration": it,
                         "checkpoint_version": 3.0}, path)
     with open(ck.get_checkpoint_tracker_filename(save_dir), "w") as f:
         f.write(str(it) if it else "release")
@@ -302,14 +312,14 @@ def pad_vocab(ckpt: Dict, multiple: int):
                 ckpt["config"]["padded_vocab_size"] = v
 
 
-LOADERS = {"core": load_core, "hf_llama": load_hf_llama, "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2}
+LOADERS = {"core": load_core, "legacy": load_core, "hf_llama": load_hf_llama, "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2}
 
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description="checkpoint converter")
     ap.add_argument("--model-type", default="GPT", choices=["GPT"])
     ap.add_argument("--loader", default="core", choices=list(LOADERS))
-    ap.add_argument("--saver", default="core", choices=["core", "hf_llama"])
+    ap.add_argument("--saver", default="core", choices=["core", "legacy", "hf_llama"])
     ap.add_argument("--load-dir", required=True)
     ap.add_argument("--save-dir", required=True)
     ap.add_argument("--target-tensor-parallel-size", type=int, default=1)
@@ -321,9 +331,10 @@ def main(argv=None):
     if a.dtype:
         dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
         ckpt["weights"] = {k: v.to(dt) for k, v in ckpt["weights"].items()}
-    if a.saver == "core":
+    if a.saver in ("core", "legacy"):
         pad_vocab(ckpt, a.make_vocab_size_divisible_by * a.target_tensor_parallel_size)
-        save_core(ckpt, a.save_dir, a.target_tensor_parallel_size, a.target_pipeline_parallel_size)
+        save_core(ckpt, a.save_dir, a.target_tensor_parallel_size, a.target_pipeline_parallel_size,
+                  legacy=a.saver == "legacy")
     else:
         save_hf_llama(ckpt, a.save_dir)
     print(f"converted {a.loader} -> {a.saver}: {len(ckpt['weights'])} tensors, "
