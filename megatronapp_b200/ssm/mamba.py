@@ -94,9 +94,20 @@ class MambaMixerSubmodules:
 
 
 class MambaMixer(MegatronModule):
+    """Mamba-2 mixer, tensor-parallel over heads (reference ``core/ssm/mamba_mixer.py``).
+
+    Under TP every rank owns ``nheads / tp`` heads and ``ngroups / tp`` B/C groups: ``in_proj`` is column-parallel and
+    its local rows are ordered ``[z | x | B | C | dt]`` *of this rank's heads*; the depth-wise conv, ``dt_bias``,
+    ``A_log``, ``D`` and the gated RMS norm (normalised per group of ``d_inner / ngroups`` channels, hence local) are
+    sharded the same way; ``out_proj`` is row-parallel, so one layer costs one all-gather/all-reduce pair (or, with
+    sequence parallelism, the all-gather inside ``in_proj`` and the reduce-scatter inside ``out_proj``)."""
+
     def __init__(self, config, submodules: MambaMixerSubmodules = None, d_model=None, d_conv=4, expand=2,
                  layer_number=None, chunk_size=64):
         super().__init__(config)
+        from ..parallel import state as ps
+        from ..parallel.tp_layers import set_tensor_model_parallel_attributes
+
         submodules = submodules or MambaMixerSubmodules()
         self.d_model = d_model or config.hidden_size
         self.d_state, self.headdim, self.ngroups = config.mamba_state_dim, config.mamba_head_dim, config.mamba_num_groups
@@ -104,40 +115,79 @@ class MambaMixer(MegatronModule):
         self.nheads = self.d_inner // self.headdim
         self.ngroups = min(self.ngroups, self.nheads)
         self.d_conv, self.chunk_size, self.layer_number = d_conv, chunk_size, layer_number
-        conv_dim = self.d_inner + 2 * self.ngroups * self.d_state
+        tp = self.tp = ps.get_tensor_model_parallel_world_size()
+        if self.nheads % tp or self.ngroups % tp or self.nheads % self.ngroups:
+            raise ValueError(f"mamba: nheads={self.nheads} and ngroups={self.ngroups} must divide by tp={tp} "
+                             f"(and nheads by ngroups)")
+        self.nheads_local, self.ngroups_local, self.d_inner_local = self.nheads // tp, self.ngroups // tp, self.d_inner // tp
+        conv_dim = self.d_inner_local + 2 * self.ngroups_local * self.d_state
         # z, x, B, C, dt
         self.in_proj = build_module(submodules.in_proj, self.d_model, 2 * self.d_inner + 2 * self.ngroups * self.d_state + self.nheads,
-                                    config=config, init_method=config.init_method, gather_output=True, bias=False,
+                                    config=config, init_method=config.init_method, gather_output=False, bias=False,
                                     skip_bias_add=False)
         dev, dt_ = self.in_proj.weight.device, config.params_dtype
         self.conv1d = nn.Conv1d(conv_dim, conv_dim, d_conv, groups=conv_dim, padding=d_conv - 1, bias=True, device=dev, dtype=dt_)
-        self.dt_bias = nn.Parameter(torch.log(torch.expm1(torch.exp(torch.rand(self.nheads, device=dev) * (math.log(0.1) - math.log(0.001)) + math.log(0.001)))).to(dt_))
-        self.A_log = nn.Parameter(torch.log(torch.empty(self.nheads, device=dev).uniform_(1, 16)).to(dt_))
-        self.D = nn.Parameter(torch.ones(self.nheads, device=dev, dtype=dt_))
-        self.norm_weight = nn.Parameter(torch.ones(self.d_inner, device=dev, dtype=dt_))
+        self.dt_bias = nn.Parameter(torch.log(torch.expm1(torch.exp(torch.rand(self.nheads_local, device=dev) * (math.log(0.1) - math.log(0.001)) + math.log(0.001)))).to(dt_))
+        self.A_log = nn.Parameter(torch.log(torch.empty(self.nheads_local, device=dev).uniform_(1, 16)).to(dt_))
+        self.D = nn.Parameter(torch.ones(self.nheads_local, device=dev, dtype=dt_))
+        self.norm_weight = nn.Parameter(torch.ones(self.d_inner_local, device=dev, dtype=dt_))
         self.out_proj = build_module(submodules.out_proj, self.d_inner, self.d_model, config=config,
-                                     init_method=config.output_layer_init_method, bias=False, input_is_parallel=False,
+                                     init_method=config.output_layer_init_method, bias=False, input_is_parallel=True,
                                      skip_bias_add=True)
         for p in (self.dt_bias, self.A_log, self.D):
             p._no_weight_decay = True
+        for p in (self.dt_bias, self.A_log, self.D, self.norm_weight, self.conv1d.weight, self.conv1d.bias):
+            set_tensor_model_parallel_attributes(p, True, 0, 1)
+
+    def _segments(self):
+        """Local row counts of the ``[z | x | B | C | dt]`` segments of ``in_proj`` and ``[x | B | C]`` of the conv."""
+        gn = self.ngroups_local * self.d_state
+        return ([("z", self.d_inner_local), ("x", self.d_inner_local), ("B", gn), ("C", gn), ("dt", self.nheads_local)],
+                [("x", self.d_inner_local), ("B", gn), ("C", gn)])
 
     def forward(self, hidden_states, inference_context=None):
-        s, b, _ = hidden_states.shape
-        zxbcdt, _ = self.in_proj(hidden_states)
+        zxbcdt, _ = self.in_proj(hidden_states)                         # [s, b, local]  (s is the full sequence)
+        s, b, _ = zxbcdt.shape
         zxbcdt = zxbcdt.transpose(0, 1)                                # [b, s, ...]
-        di, gn = self.d_inner, self.ngroups * self.d_state
-        z, xBC, dt = torch.split(zxbcdt, [di, di + 2 * gn, self.nheads], dim=-1)
+        di, gn, nh, ng = self.d_inner_local, self.ngroups_local * self.d_state, self.nheads_local, self.ngroups_local
+        z, xBC, dt = torch.split(zxbcdt, [di, di + 2 * gn, nh], dim=-1)
         xBC = F.silu(self.conv1d(xBC.transpose(1, 2))[..., :s].transpose(1, 2))
         x, B, C = torch.split(xBC, [di, gn, gn], dim=-1)
         dt = F.softplus(dt.float() + self.dt_bias.float())
-        y, _ = ssd_scan(x.reshape(b, s, self.nheads, self.headdim), dt, -torch.exp(self.A_log.float()),
-                        B.reshape(b, s, self.ngroups, self.d_state), C.reshape(b, s, self.ngroups, self.d_state),
+        y, _ = ssd_scan(x.reshape(b, s, nh, self.headdim), dt, -torch.exp(self.A_log.float()),
+                        B.reshape(b, s, ng, self.d_state), C.reshape(b, s, ng, self.d_state),
                         self.D, self.chunk_size)
         y = y.reshape(b, s, di)
-        y = y * F.silu(z)                                             # gated RMSNorm
-        y = (y.float() * torch.rsqrt(y.float().pow(2).mean(-1, keepdim=True) + 1e-5) * self.norm_weight.float()).to(hidden_states.dtype)
-        out, bias = self.out_proj(y.transpose(0, 1).contiguous())
+        y = (y * F.silu(z)).float().view(b, s, ng, di // ng)            # gated RMSNorm, one statistic per B/C group
+        y = (y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-5)).view(b, s, di) * self.norm_weight.float()
+        out, bias = self.out_proj(y.to(hidden_states.dtype).transpose(0, 1).contiguous())
         return out, bias
+
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        """``in_proj`` / ``conv1d`` are stored as their logical segments (``...in_proj.weight.z`` etc.), each sharded
+        over TP on its own, so a checkpoint reshards to any TP degree (reference ``mamba_mixer.py`` does the same
+        with split factories)."""
+        from ..ckpt.sharded import make_tp_sharded_tensor_for_checkpoint
+
+        off = tuple(sharded_offsets)
+        sd = {}
+        seg_in, seg_conv = self._segments()
+
+        def split(t, key, segs):
+            o = 0
+            for name, n in segs:
+                sd[f"{key}.{name}"] = make_tp_sharded_tensor_for_checkpoint(t.narrow(0, o, n), f"{key}.{name}", 0,
+                                                                            prepend_offsets=off)
+                o += n
+
+        split(self.in_proj.weight, f"{prefix}in_proj.weight", seg_in)
+        split(self.conv1d.weight, f"{prefix}conv1d.weight", seg_conv)
+        split(self.conv1d.bias, f"{prefix}conv1d.bias", seg_conv)
+        for name in ("dt_bias", "A_log", "D", "norm_weight"):
+            key = f"{prefix}{name}"
+            sd[key] = make_tp_sharded_tensor_for_checkpoint(getattr(self, name), key, 0, prepend_offsets=off)
+        sd.update(self.out_proj.sharded_state_dict(f"{prefix}out_proj.", off, metadata))
+        return sd
 
 
 class MambaLayer(MegatronModule):

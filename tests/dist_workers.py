@@ -275,6 +275,56 @@ def cp_model_parity(comm="a2a"):
             "grad_ref_max": float(g_ref.abs().max())}
 
 
+def mamba_tp_reshard(path=None, sp=False):
+    """Head-sharded Mamba mixer at tp=2 == the same weights resharded (through the checkpoint) to tp=1."""
+    from megatronapp_b200.ckpt import sharded
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+    from megatronapp_b200.ssm.mamba import MambaMixer
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+
+    rank, world = _setup()
+
+    def cfg(tp, sp_):
+        return TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, tensor_model_parallel_size=tp,
+                                 sequence_parallel=sp_, mamba_state_dim=8, mamba_head_dim=8, mamba_num_groups=2,
+                                 kernel_backend="torch", use_cpu_initialization=True, params_dtype=torch.float32)
+
+    ps.initialize_model_parallel(world, 1)
+    model_parallel_cuda_manual_seed(123)
+    torch.manual_seed(5 + rank)
+    m = MambaMixer(cfg(world, sp), chunk_size=4)
+    with torch.no_grad():                      # make every sharded vector non-trivial
+        for p_ in (m.D, m.norm_weight, m.conv1d.bias):
+            p_.copy_(torch.randn_like(p_))
+    torch.manual_seed(0)
+    x = torch.randn(12, 2, 32)
+    xin = x.chunk(world, 0)[rank].clone().requires_grad_(True) if sp else x.clone().requires_grad_(True)
+    y, _ = m(xin)
+    y.square().sum().backward()
+    if sp:
+        ys = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(ys, y.detach())
+        y_tp = torch.cat(ys, 0)
+        gs = [torch.empty_like(xin.grad) for _ in range(world)]
+        dist.all_gather(gs, xin.grad)
+        gx_tp = torch.cat(gs, 0)
+    else:
+        y_tp, gx_tp = y.detach(), xin.grad.clone()          # in_proj's dgrad is all-reduced inside the linear
+    sharded.save(m.sharded_state_dict(prefix="mixer."), path, {})
+    dist.barrier()
+    ps.destroy_model_parallel()
+    ps.initialize_model_parallel(1, 1)
+    torch.manual_seed(99)
+    m1 = MambaMixer(cfg(1, False), chunk_size=4)
+    sharded.load(m1.sharded_state_dict(prefix="mixer."), path)
+    x1 = x.clone().requires_grad_(True)
+    y1, _ = m1(x1)
+    y1.square().sum().backward()
+    return {"fwd": float((y1.detach() - y_tp).abs().max()), "gx": float((x1.grad - gx_tp).abs().max()),
+            "scale": float(y1.detach().abs().max()), "local_heads": m.nheads_local, "full_heads": m1.nheads_local}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":

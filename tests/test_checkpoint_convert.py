@@ -136,3 +136,47 @@ def test_distillation_losses():
     total = DistillationLossBalancer(kd_loss_scale=0.5)(torch.tensor(2.0), {"logits": kl})
     total.backward()
     assert s.grad is not None and abs(float(total) - (2.0 + 0.5 * float(kl.mean()))) < 1e-5
+
+
+def test_hybrid_mamba_reshard_roundtrip(tmp_path):
+    import importlib.util
+    from types import SimpleNamespace
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.mamba.mamba_model import MambaModel
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.training import checkpointing as ck
+
+    spec = importlib.util.spec_from_file_location("hybrid_conversion", os.path.join(ROOT, "tools", "checkpoint", "hybrid_conversion.py"))
+    hc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hc)
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+    cfg = TransformerConfig(num_layers=4, hidden_size=32, num_attention_heads=4, mamba_state_dim=8, mamba_head_dim=8,
+                            mamba_num_groups=2, kernel_backend="torch", use_cpu_initialization=True,
+                            params_dtype=torch.float32)
+    m = MambaModel(cfg, vocab_size=64, max_sequence_length=16, hybrid_override_pattern="M*-M")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items() if not k.endswith("_extra_state")}
+    args = SimpleNamespace(num_layers=4, hidden_size=32, mamba_state_dim=8, mamba_head_dim=8, mamba_num_groups=2, swiglu=False,
+                           tensor_model_parallel_size=1, pipeline_model_parallel_size=1)
+    src = str(tmp_path / "tp1")
+    path = ck.get_checkpoint_name(src, 0, release=True, pipeline_parallel=False, tensor_rank=0, pipeline_rank=0,
+                                  expert_parallel=False, expert_rank=0)
+    os.makedirs(os.path.dirname(path))
+    torch.save({"model": sd, "args": args, "iteration": 0}, path)
+    with open(ck.get_checkpoint_tracker_filename(src), "w") as f:
+        f.write("release")
+    mid, back = str(tmp_path / "tp2pp2"), str(tmp_path / "back")
+    hc.main(["--load-dir", src, "--save-dir", mid, "--target-tp-size", "2", "--target-pp-size", "2"])
+    shard = torch.load(os.path.join(mid, "release", "mp_rank_01_000", "model_optim_rng.pt"), weights_only=False)["model"]
+    w_full = sd["decoder.layers.0.mixer.in_proj.weight"]
+    z, x, B, C, dt = torch.split(w_full, [64, 64, 16, 16, 8], dim=0)
+    want = torch.cat([t.chunk(2, 0)[1] for t in (z, x, B, C, dt)], 0)          # rank 1: its slice of EVERY segment
+    assert torch.equal(shard["decoder.layers.0.mixer.in_proj.weight"], want)
+    assert shard["decoder.layers.0.mixer.out_proj.weight"].shape == (32, 32)
+    assert shard["decoder.layers.1.self_attention.linear_qkv.weight"].shape[0] * 2 == sd["decoder.layers.1.self_attention.linear_qkv.weight"].shape[0]
+    assert "decoder.layers.2.mixer.A_log" not in shard                          # stage 0 holds layers 0-1 only
+    hc.main(["--load-dir", mid, "--save-dir", back, "--target-tp-size", "1", "--target-pp-size", "1"])
+    again = torch.load(os.path.join(back, "release", "mp_rank_00", "model_optim_rng.pt"), weights_only=False)["model"]
+    assert again.keys() == sd.keys() and all(torch.equal(again[k], sd[k]) for k in sd)

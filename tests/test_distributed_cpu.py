@@ -103,3 +103,11 @@ def test_context_parallel_gpt_matches_single_rank(comm):
     for r in run_distributed("cp_model_parity", 2, comm=comm):
         assert abs(r["loss_full"] - r["loss_cp"]) < 1e-4, r
         assert r["grad_err"] < 1e-4 * max(1.0, r["grad_ref_max"]) + 1e-5, r
+
+
+@pytest.mark.parametrize("sp", [False, True])
+def test_mamba_mixer_tensor_parallel_and_reshard(tmp_path, sp):
+    res = run_distributed("mamba_tp_reshard", 2, path=str(tmp_path / "ck"), sp=sp)
+    for r in res:
+        assert r["local_heads"] * 2 == r["full_heads"]
+        assert r["fwd"] < 1e-4 * max(1.0, r["scale"]) and r["gx"] < 1e-3, r
