@@ -23,7 +23,7 @@ E4M3_MAX, E5M2_MAX = 448.0, 57344.0
 @dataclass
 class Fp8Recipe:
     fmt: str = "hybrid"            # "e4m3" | "hybrid"
-    recipe: str = "tensorwise"     # "tensorwise" (current scaling) | "delayed"
+    recipe: str = "tensorwise"     # "tensorwise" (current scaling) | "delayed" | "mxfp8" (1x32 block scaling)
     margin: int = 0
     amax_history_len: int = 1
     amax_compute_algo: str = "most_recent"   # | "max"
@@ -156,6 +156,123 @@ class Fp8LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None, None
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# MXFP8: OCP micro-scaling -- every 32 consecutive elements along the GEMM's K axis share one power-of-two (E8M0) scale
+# ---------------------------------------------------------------------------------------------------------------
+MX_BLOCK = 32
+
+
+def quantize_mx(x: torch.Tensor, e5m2: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``x [rows, K]`` (K % 32 == 0) -> ``(q uint8 [rows, K], scale_e8m0 uint8 [rows, K/32])``.  The shared exponent
+    of a block is ``floor(log2(amax)) - emax_elem`` (OCP MX v1.0 sec. 6.3), stored biased by 127; the elements are
+    the saturating fp8 cast of ``x * 2^-shared``."""
+    rows, K = x.shape
+    if K % MX_BLOCK:
+        raise ValueError(f"mxfp8 needs the contraction dim to be a multiple of {MX_BLOCK}, got {K}")
+    xb = x.detach().float().view(rows, K // MX_BLOCK, MX_BLOCK)
+    amax = xb.abs().amax(dim=-1)
+    emax_elem = 15 if e5m2 else 8
+    shared = torch.floor(torch.log2(amax.clamp_min(2.0 ** -127))) - emax_elem
+    shared = torch.where(amax > 0, shared, torch.full_like(shared, -127.0)).clamp(-127, 127)
+    fmax = E5M2_MAX if e5m2 else E4M3_MAX
+    dt = torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn
+    q = (xb * torch.exp2(-shared).unsqueeze(-1)).clamp(-fmax, fmax).to(dt).view(torch.uint8).view(rows, K)
+    return q, (shared + 127).to(torch.uint8)
+
+
+def dequantize_mx(q: torch.Tensor, scale_e8m0: torch.Tensor, e5m2: bool = False, dtype=torch.float32) -> torch.Tensor:
+    dt = torch.float8_e5m2 if e5m2 else torch.float8_e4m3fn
+    rows, K = q.shape
+    s = torch.exp2(scale_e8m0.float() - 127.0).unsqueeze(-1)
+    return (q.view(dt).float().view(rows, K // MX_BLOCK, MX_BLOCK) * s).view(rows, K).to(dtype)
+
+
+def gemm_mx(a8, sa, b8, sb, *, a_e5m2=False, b_e5m2=False, bias=None, out_dtype=torch.bfloat16):
+    """``D = deq(A) @ deq(B)^T``; both operands are block-scaled along K.  The block scales are exact powers of two,
+    so dequantising to bf16 is lossless (fp8 mantissas fit) and the product runs on the bf16 tcgen05 GEMM; a native
+    ``tcgen05.mma.kind::mxf8f6f4.block_scale`` kernel only changes the speed, not the numbers."""
+    if a8.is_cuda:
+        from . import gemm as _gemm
+
+        fallback_counts["mxfp8_via_bf16_gemm"] += 1
+        d = _gemm(dequantize_mx(a8, sa, a_e5m2, torch.bfloat16), dequantize_mx(b8, sb, b_e5m2, torch.bfloat16))
+        d = d.float()
+    else:
+        d = dequantize_mx(a8, sa, a_e5m2) @ dequantize_mx(b8, sb, b_e5m2).t()
+    if bias is not None:
+        d = d + bias.float()
+    return d.to(out_dtype)
+
+
+class _MxWeightCache(_WeightCache):
+    """Row-wise (blocks along ``in``: fprop) and column-wise (blocks along ``out``: dgrad) mxfp8 copies of a weight."""
+
+    def get(self, w: torch.Tensor, margin: int = 0):
+        if self.val is None or self.version != w._version or self.data_ptr != w.data_ptr():
+            wd = w.detach()
+            ok_t = wd.shape[0] % MX_BLOCK == 0
+            self.val = (*quantize_mx(wd), *(quantize_mx(wd.t().contiguous()) if ok_t else (None, None)))
+            self.version, self.data_ptr = w._version, w.data_ptr()
+        return self.val
+
+
+class MxFp8LinearFn(torch.autograd.Function):
+    """Linear layer under the ``mxfp8`` recipe (reference ``fp8_utils.get_fp8_context``: ``MXFP8BlockScaling``).
+    Each GEMM quantises its two operands along ITS contraction axis: fprop along ``in``, dgrad along ``out``, wgrad
+    along tokens -- so activations and gradients are quantised twice (row- and column-wise), like TE does."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, recipe: Fp8Recipe, cache: _MxWeightCache, fuse_wgrad: bool):
+        x2 = x.reshape(-1, x.shape[-1])
+        xq, xs = quantize_mx(x2)
+        wq, ws, wtq, wts = cache.get(weight)
+        y = gemm_mx(xq, xs, wq, ws, bias=bias, out_dtype=x.dtype)
+        ctx.save_for_backward(x2, wtq, wts)
+        ctx.recipe, ctx.fuse_wgrad, ctx.weight = recipe, fuse_wgrad, weight
+        ctx.x_shape, ctx.has_bias, ctx.dtype = x.shape, bias is not None, x.dtype
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wtq, wts = ctx.saved_tensors
+        rec, weight = ctx.recipe, ctx.weight
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        e5 = rec.fmt == "hybrid"
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if wtq is not None:
+                dq, ds = quantize_mx(dy2, e5)                                        # blocks along ``out``
+                dx = gemm_mx(dq, ds, wtq, wts, a_e5m2=e5, out_dtype=ctx.dtype)       # dy @ W
+            else:
+                dx = (dy2.float() @ weight.detach().float()).to(ctx.dtype)
+            dx = dx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            rows = dy2.shape[0]
+            if rec.wgrad and rows % MX_BLOCK == 0:
+                dtq, dts = quantize_mx(dy2.t().contiguous(), e5)                     # blocks along tokens
+                xtq, xts = quantize_mx(x2.t().contiguous())
+                dw = gemm_mx(dtq, dts, xtq, xts, a_e5m2=e5, out_dtype=torch.float32)  # dy^T @ x
+            else:
+                dw = dy2.float().t() @ x2.float()
+            main = getattr(weight, "main_grad", None)
+            if ctx.fuse_wgrad and main is not None:
+                main.add_(dw)
+                weight.grad_added_to_main_grad = True
+                dw = None
+            else:
+                dw = dw.to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            from . import bias_grad
+
+            db = bias_grad(dy2).to(dy.dtype)
+        return dx, dw, db, None, None, None
+
+
 def fp8_linear(x, weight, bias=None, recipe: Optional[Fp8Recipe] = None, cache: Optional[_WeightCache] = None,
                fuse_wgrad: bool = False):
+    recipe = recipe or Fp8Recipe()
+    if recipe.recipe == "mxfp8" and x.shape[-1] % MX_BLOCK == 0:
+        if not isinstance(cache, _MxWeightCache):
+            cache = _MxWeightCache()
+        return MxFp8LinearFn.apply(x, weight, bias, recipe, cache, fuse_wgrad)
     return Fp8LinearFn.apply(x, weight, bias, recipe or Fp8Recipe(), cache or _WeightCache(), fuse_wgrad)

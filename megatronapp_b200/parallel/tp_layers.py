@@ -113,7 +113,7 @@ def _fp8_recipe_from_config(config, is_expert: bool = False):
     from ..ops.fp8 import Fp8Recipe
 
     rec = getattr(config, "fp8_recipe", "delayed")
-    return Fp8Recipe(fmt="hybrid" if fmt == "hybrid" else "e4m3", recipe="tensorwise" if rec != "delayed" else "delayed",
+    return Fp8Recipe(fmt="hybrid" if fmt == "hybrid" else "e4m3", recipe=rec if rec in ("delayed", "mxfp8") else "tensorwise",
                      margin=int(getattr(config, "fp8_margin", 0) or 0),
                      amax_history_len=int(getattr(config, "fp8_amax_history_len", 1) or 1),
                      amax_compute_algo=getattr(config, "fp8_amax_compute_algo", "most_recent"),
@@ -284,10 +284,10 @@ class ColumnParallelLinear(nn.Module):
 
     def _fp8_forward(self, input_, weight):
         """fp8 GEMMs around explicit TP collectives (all-gather / copy in front, nothing behind)."""
-        from ..ops.fp8 import _WeightCache, fp8_linear
+        from ..ops.fp8 import _MxWeightCache, _WeightCache, fp8_linear
 
         if self._fp8_cache is None:
-            self._fp8_cache = _WeightCache()
+            self._fp8_cache = _MxWeightCache() if self.fp8_recipe.recipe == "mxfp8" else _WeightCache()
         if self.sequence_parallel and self.tp_size > 1:
             x = gather_from_sequence_parallel_region(input_, tensor_parallel_output_grad=True)
         elif self.allreduce_dgrad:
@@ -455,10 +455,10 @@ class RowParallelLinear(nn.Module):
         do_reduce = not self.explicit_expert_comm
         if self.fp8_recipe is not None and input_.shape[-1] % 16 == 0 and self.weight.shape[0] % 16 == 0 \
                 and not self.explicit_expert_comm:
-            from ..ops.fp8 import _WeightCache, fp8_linear
+            from ..ops.fp8 import _MxWeightCache, _WeightCache, fp8_linear
 
             if self._fp8_cache is None:
-                self._fp8_cache = _WeightCache()
+                self._fp8_cache = _MxWeightCache() if self.fp8_recipe.recipe == "mxfp8" else _WeightCache()
             out = fp8_linear(input_, self.weight, None, self.fp8_recipe, self._fp8_cache,
                              self.gradient_accumulation_fusion and self.weight.requires_grad)
             if self.tp_size > 1:

@@ -379,3 +379,52 @@ def test_legacy_model_shells_and_state_dict_naming():
     assert "layers.0.self_attention.query_key_value.weight" in bsd["language_model"]["encoder"]
     assert "lm_head" in bsd and "binary_head" in bsd and "pooler" in bsd["language_model"]
     lb.load_state_dict(bsd)
+
+
+def test_mxfp8_block_scaling_quantisation_and_linear():
+    from megatronapp_b200.ops import fp8
+
+    torch.manual_seed(0)
+    x = torch.randn(64, 128)
+    x[:, 32:64] *= 1.0e6                       # a hot block: block scaling keeps the neighbours alive
+    x[3, 96:128] = 0.0
+    q, s = fp8.quantize_mx(x)
+    assert q.shape == (64, 128) and s.shape == (64, 4) and s.dtype == torch.uint8
+    deq = fp8.dequantize_mx(q, s)
+    blk = lambda t: t.view(64, 4, 32)
+    rel = (blk(deq) - blk(x)).abs().amax(-1) / blk(x).abs().amax(-1).clamp_min(1e-30)
+    assert float(rel.max()) < 2 ** -3                                  # e4m3: 3 mantissa bits, every block on its own
+    assert torch.equal(deq[3, 96:], torch.zeros(32)) and int(s[3, 3]) == 0
+    # power-of-two scales: the largest element of a block lands in [2^8, 2^9) (e4m3 emax = 8)
+    top = (blk(x).abs().amax(-1) * torch.exp2(127.0 - s.float()))[s > 0]
+    assert float(top.min()) >= 256.0 and float(top.max()) < 512.0
+    tens, _, sinv, _ = fp8.quantize(x)
+    err_tensorwise = (fp8.dequantize(tens, sinv) - x)[:, :32].abs().max()
+    assert (deq - x)[:, :32].abs().max() < 0.1 * err_tensorwise          # what the per-tensor scale loses next to the hot block
+
+    rec = fp8.Fp8Recipe(fmt="hybrid", recipe="mxfp8")
+    xx = torch.randn(64, 128, requires_grad=True)
+    w = (torch.randn(96, 128) * 0.1).requires_grad_(True)
+    b = torch.randn(96)
+    y = fp8.fp8_linear(xx, w, b, rec)
+    ref = xx @ w.t() + b
+    assert ((y - ref).abs().max() / ref.abs().max()) < 0.06
+    dy = torch.randn_like(ref)
+    y.backward(dy)
+    gx, gw = xx.grad.clone(), w.grad.clone()
+    xx.grad = w.grad = None
+    ref.backward(dy)
+    assert ((gx - xx.grad).abs().max() / xx.grad.abs().max()) < 0.1
+    assert ((gw - w.grad).abs().max() / w.grad.abs().max()) < 0.1
+
+    from megatronapp_b200.parallel.tp_layers import ColumnParallelLinear
+
+    _init()
+    cfg = _cfg(fp8="hybrid", fp8_recipe="mxfp8")
+    lin = ColumnParallelLinear(128, 96, config=cfg, init_method=cfg.init_method, bias=True, skip_bias_add=False)
+    assert lin.fp8_recipe.recipe == "mxfp8"
+    inp = torch.randn(8, 4, 128)
+    out, _ = lin(inp)
+    want = torch.nn.functional.linear(inp, lin.weight, lin.bias)
+    assert 0 < float((out - want).abs().max()) < 0.06 * float(want.abs().max())      # quantised, and close
+    assert type(lin._fp8_cache).__name__ == "_MxWeightCache"
