@@ -180,3 +180,53 @@ def test_hybrid_mamba_reshard_roundtrip(tmp_path):
     hc.main(["--load-dir", mid, "--save-dir", back, "--target-tp-size", "1", "--target-pp-size", "1"])
     again = torch.load(os.path.join(back, "release", "mp_rank_00", "model_optim_rng.pt"), weights_only=False)["model"]
     assert again.keys() == sd.keys() and all(torch.equal(again[k], sd[k]) for k in sd)
+
+
+@pytest.mark.parametrize("name,tol", [("fp8", 0.08), ("int8_sq", 0.05), ("int4_awq", 0.35), ("w4a8_awq", 0.4), ("nvfp4", 0.45)])
+def test_post_training_quantization(name, tol):
+    from megatronapp_b200.bench_model import build_gpt_for_bench
+    from megatronapp_b200.post_training import quantization as ptq
+
+    def build():
+        torch.manual_seed(0)
+        return build_gpt_for_bench(2, 128, 4, 32, 128, 1, device="cpu", dtype=torch.float32, rope=True).model[0].module
+
+    m = build()
+    ids = torch.randint(0, 128, (4, 32))
+    pos = torch.arange(32).unsqueeze(0).expand(4, -1)
+    m.eval()
+    with torch.no_grad():
+        ref = m(ids, pos, None)
+    calib = [torch.randint(0, 128, (4, 32)) for _ in range(3)] + [ids]
+    loop = lambda mod: [mod(c, pos, None) for c in calib]
+    ptq.quantize(m, name, loop)
+    with torch.no_grad():
+        out = m(ids, pos, None)
+    rel = float((out - ref).abs().max() / ref.abs().max())
+    assert 0 < rel < tol, rel                                            # quantised for real, still the same model
+    lin = m.decoder.layers[0].mlp.linear_fc1
+    cfg = ptq.QUANT_CFG_CHOICES[name]
+    w = lin.weight.detach()
+    assert torch.allclose(ptq.fake_quant(w, lin.weight_quantizer._amax, cfg.weight), w, atol=1e-6)   # folded onto the grid
+    levels = {"fp8": 256, "int8_sq": 256, "int4_awq": 16, "w4a8_awq": 16, "nvfp4": 15}[name]
+    row = w[0, :cfg.weight.block] if cfg.weight.block else w[0]
+    assert row.unique().numel() <= levels
+    # checkpoint round trip: fresh model + same weights + quantiser state == quantised model
+    state = ptq.quantizer_state_dict(m)
+    assert any(k.endswith("weight_quantizer._amax") for k in state)
+    m2 = build()
+    m2.load_state_dict(m.state_dict(), strict=False)
+    ptq.restore_quantizers(m2, name, state)
+    m2.eval()
+    with torch.no_grad():
+        assert torch.allclose(m2(ids, pos, None), out, atol=1e-5)
+    real = ptq.export_quantized_weights(m)
+    k = "decoder.layers.0.mlp.linear_fc1"
+    assert real[f"{k}.weight"].dtype in (torch.int8, torch.uint8)
+    if cfg.weight.bits == 4:
+        assert real[f"{k}.weight"].shape == (w.shape[0], w.shape[1] // 2)
+        assert real[f"{k}.weights_scaling_factor"].shape == (w.shape[0], w.shape[1] // cfg.weight.block)
+    if name == "int8_sq":
+        s = real[f"{k}.weights_scaling_factor"]
+        assert torch.allclose(real[f"{k}.weight"].float() * s.unsqueeze(1), w, atol=1e-5)
+        assert f"{k}.prequant_scaling_factor" in real and f"{k}.activation_scaling_factor" in real
