@@ -34,7 +34,8 @@ class LLaVAModel(MegatronModule):
                  add_encoder: bool = True, add_decoder: bool = True, img_h: int = 336, img_w: int = 336,
                  patch_dim: int = 14, language_rotary_base: int = 10000, language_rope_scaling: bool = False,
                  image_token_index: int = DEFAULT_IMAGE_TOKEN_INDEX, pixel_shuffle: bool = False,
-                 tile_tags: Optional[list] = None):
+                 tile_tags: Optional[list] = None, vision_model_type: str = "clip", max_img_h: int = 2048,
+                 max_img_w: int = 2048, class_token_len: Optional[int] = None):
         super().__init__(language_transformer_config)
         self.pre_process, self.post_process = pre_process, post_process
         self.add_encoder, self.add_decoder = add_encoder, add_decoder
@@ -53,11 +54,24 @@ class LLaVAModel(MegatronModule):
                 scatter_embedding_sequence_parallel=False)
             self.share_embeddings_and_output_weights = self.language_model.share_embeddings_and_output_weights
         if add_encoder:
-            self.vision_model = CLIPViTModel(vision_transformer_config, vision_transformer_layer_spec, img_h=img_h,
-                                             img_w=img_w, patch_dim=patch_dim)
+            if vision_model_type == "radio":
+                from ..vision.radio import RADIOViTModel
+
+                self.vision_model = RADIOViTModel(vision_transformer_config, vision_transformer_layer_spec, img_h=img_h,
+                                                  img_w=img_w, patch_dim=patch_dim, max_img_h=max_img_h, max_img_w=max_img_w,
+                                                  class_token_len=class_token_len or 8)
+            elif vision_model_type in ("clip", "siglip"):
+                self.vision_model = CLIPViTModel(vision_transformer_config, vision_transformer_layer_spec, img_h=img_h,
+                                                 img_w=img_w, patch_dim=patch_dim, model_subtype=vision_model_type,
+                                                 add_class_token=vision_model_type == "clip",
+                                                 class_token_len=class_token_len or 1)
+            else:
+                raise ValueError(f"unknown vision_model_type {vision_model_type!r}")
             self.vision_projection = MultimodalProjector(vision_projection_config, vision_projection_layer_spec,
                                                          vision_projection_type, vision_transformer_config.hidden_size)
-        self.img_seq_len = get_num_image_embeddings(img_h, img_w, patch_dim, "clip", drop_vision_class_token, 1,
+        self.vision_model_type = vision_model_type
+        self.img_seq_len = get_num_image_embeddings(img_h, img_w, patch_dim, vision_model_type, drop_vision_class_token,
+                                                    class_token_len or (8 if vision_model_type == "radio" else 1),
                                                     pixel_shuffle)
 
     def shared_embedding_or_output_weight(self):
@@ -148,7 +162,7 @@ class LLaVAModel(MegatronModule):
         image_embeddings = None
         if self.add_encoder and not use_cache and images is not None and images.shape[0] > 0:
             x = self.vision_model(images)                                   # [tiles, img_seq(+cls), hv]
-            if self.drop_vision_class_token:
+            if self.drop_vision_class_token and getattr(self.vision_model, "add_class_token", False):
                 x = x[:, self.vision_model.class_token_len:, :]
             image_embeddings = self.vision_projection(x)                   # [tiles, img_seq, h]
         elif not self.add_encoder and self.pre_process:

@@ -36,7 +36,7 @@ def get_num_image_embeddings(img_h: int, img_w: int, patch_dim: int, vision_mode
     n = (img_h // patch_dim) * (img_w // patch_dim)
     if pixel_shuffle:
         n //= 4
-    if vision_model_type == "clip" and not disable_vision_class_token:
+    if vision_model_type in ("clip", "radio") and not disable_vision_class_token:
         n += class_token_len
     return n
 

@@ -27,6 +27,9 @@ def add_vlm_extra_args(parser):
     g.add_argument("--img-h", type=int, default=336)
     g.add_argument("--img-w", type=int, default=336)
     g.add_argument("--patch-dim", type=int, default=14)
+    g.add_argument("--vision-model-type", default="clip", choices=["clip", "siglip", "radio"])
+    g.add_argument("--max-img-h", type=int, default=2048)
+    g.add_argument("--max-img-w", type=int, default=2048)
     g.add_argument("--vision-num-layers", type=int, default=None)
     g.add_argument("--vision-hidden-size", type=int, default=None)
     g.add_argument("--vision-num-attention-heads", type=int, default=None)
@@ -67,7 +70,8 @@ def model_provider(pre_process=True, post_process=True, add_encoder=True, add_de
         vision_projection_type="mlp", parallel_output=True,
         language_position_embedding_type=args.position_embedding_type, pre_process=pre_process,
         post_process=post_process, add_encoder=add_encoder, add_decoder=add_decoder, img_h=args.img_h, img_w=args.img_w,
-        patch_dim=args.patch_dim, language_rotary_base=args.rotary_base)
+        patch_dim=args.patch_dim, language_rotary_base=args.rotary_base, vision_model_type=args.vision_model_type,
+        max_img_h=args.max_img_h, max_img_w=args.max_img_w)
     m.freeze(args.freeze_LM, args.freeze_ViT, False)
     return m
 

@@ -192,6 +192,13 @@ def test_llava_splices_image_embeddings():
     assert mask[:, 2:2 + n_img].sum() == 0 and mask[:, 1].sum() == 0 and mask[:, 0].sum() == 2
     (loss * mask).sum().backward()
     assert m.vision_model.conv1.weight.grad.abs().sum() > 0 and m.vision_projection.encoder.linear_fc1.weight.grad is not None
+    # RADIO tower: 8 summary tokens kept in front of the 4 patch embeddings
+    r = LLaVAModel(lcfg, get_gpt_layer_local_spec(), 64, 48, vcfg, get_vit_layer_spec(), False, pcfg,
+                   MLPSubmodules(linear_fc1=ColumnParallelLinear, linear_fc2=RowParallelLinear), img_h=14, img_w=14,
+                   patch_dim=7, vision_model_type="radio", max_img_h=28, max_img_w=28)
+    assert r.img_seq_len == 12
+    loss, mask = r(torch.rand(2, 3, 14, 14), toks, pos, None, labels=labels, loss_mask=torch.ones(2, 10))
+    assert loss.shape == (2, 10 - 1 + 12)
 
 
 def test_fp8_linear_emulation_matches_bf16_within_quantisation_error():
@@ -428,3 +435,32 @@ def test_mxfp8_block_scaling_quantisation_and_linear():
     want = torch.nn.functional.linear(inp, lin.weight, lin.bias)
     assert 0 < float((out - want).abs().max()) < 0.06 * float(want.abs().max())      # quantised, and close
     assert type(lin._fp8_cache).__name__ == "_MxWeightCache"
+
+
+def test_radio_vit_resolution_agnostic_position_embeddings():
+    from megatronapp_b200.models.vision.radio import RADIOViTModel, patchify
+
+    _init()
+    torch.manual_seed(0)
+    cfg = _cfg(kernel_backend="torch")
+    m = RADIOViTModel(cfg, patch_dim=4, img_h=16, img_w=16, max_img_h=32, max_img_w=32, class_token_len=3)
+    img = torch.arange(2 * 3 * 8 * 8, dtype=torch.float32).view(2, 3, 8, 8)
+    p = patchify(img, 4)
+    assert p.shape == (2, 4, 48) and torch.equal(p[1, 3].view(3, 4, 4), img[1, :, 4:, 4:])
+    m.eval()
+    with torch.no_grad():
+        assert m(torch.randn(2, 3, 16, 16)).shape == (2, 3 + 16, 32)
+        assert m(torch.randn(2, 3, 8, 24)).shape == (2, 3 + 12, 32)          # other resolutions just work
+        full = m.get_pos_enc(1, input_size=(32, 32))
+        assert full.data_ptr() == m.position_embeddings.data_ptr()           # max grid: the table itself
+        a, b = m.get_pos_enc(2, input_size=(16, 16)), m.get_pos_enc(2, input_size=(16, 16))
+        assert torch.equal(a, b)                                             # eval: deterministic resize
+    m.train()
+    a, b = m.get_pos_enc(2, input_size=(16, 16)), m.get_pos_enc(2, input_size=(16, 16))
+    assert a.shape == (2, 16, 32) and not torch.equal(a, b) and not torch.equal(a[0], a[1])     # CPE: random windows
+    idx = torch.tensor([[0, 5], [7, 2]])
+    g = m.get_pos_enc(2, idx, input_size=(32, 32))
+    assert torch.equal(g[1, 0], m.position_embeddings[0, 7])
+    out = m(torch.randn(2, 3, 16, 16))
+    out.square().mean().backward()
+    assert m.position_embeddings.grad is not None and m.class_token.grad is not None
