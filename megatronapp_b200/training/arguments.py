@@ -342,6 +342,22 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--no-create-attention-mask-in-dataloader", action="store_false", dest="create_attention_mask_in_dataloader")
     _add(g, "--num-dataset-builder-threads", type=int, default=1)
     _add(g, "--s3-cache-path", type=str, default=None)
+    g = p.add_argument_group("biencoder")       # reference _add_biencoder_args
+    _add(g, "--ict-head-size", type=int, default=None)
+    _add(g, "--biencoder-projection-dim", type=int, default=0)
+    _add(g, "--biencoder-shared-query-context-model", action="store_true")
+    _add(g, "--ict-load", type=str, default=None)
+    _add(g, "--bert-load", type=str, default=None)
+    _add(g, "--titles-data-path", type=str, default=None)
+    _add(g, "--query-in-block-prob", type=float, default=0.1)
+    _add(g, "--use-one-sent-docs", action="store_true")
+    _add(g, "--evidence-data-path", type=str, default=None)
+    _add(g, "--retriever-report-topk-accuracies", nargs="+", type=int, default=[])
+    _add(g, "--retriever-score-scaling", action="store_true")
+    _add(g, "--block-data-path", type=str, default=None)
+    _add(g, "--embedding-path", type=str, default=None)
+    _add(g, "--indexer-batch-size", type=int, default=128)
+    _add(g, "--indexer-log-interval", type=int, default=1000)
     g = p.add_argument_group("tokenizer")
     _add(g, "--vocab-size", type=int, default=None)
     _add(g, "--padded-vocab-size", type=int, default=None)

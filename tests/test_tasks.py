@@ -120,3 +120,56 @@ def test_race_dataset_rows(tmp_path):
     s = ds[1]
     assert s["text"].shape == (4, 24) and int(s["label"]) == 0 and s["text"][:, 0].eq(1).all()
     assert (s["types"][0] == 1).sum() > 0 and s["padding_mask"].shape == (4, 24)
+
+
+def test_biencoder_ict_learns_in_batch_retrieval(tmp_path):
+    import numpy as np
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.data.ict_dataset import ICTDataset
+    from megatronapp_b200.data.indexed_dataset import IndexedDataset, IndexedDatasetBuilder, get_bin_path, get_idx_path
+    from megatronapp_b200.legacy.model.biencoder_model import BiEncoderModel, ict_loss
+    from megatronapp_b200.parallel import state as ps
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+    # 12 documents; every document talks about its own small vocabulary slice -> a sentence identifies its block
+    rng = np.random.default_rng(0)
+    prefix = str(tmp_path / "sents")
+    b = IndexedDatasetBuilder(get_bin_path(prefix), dtype=np.int32)
+    for d in range(12):
+        for _ in range(4):
+            b.add_item(rng.integers(10 + 8 * d, 18 + 8 * d, size=6).astype(np.int32))
+        b.end_document()
+    b.finalize(get_idx_path(prefix))
+    ds = ICTDataset(IndexedDataset(prefix), None, None, max_seq_length=32, query_in_block_prob=0.0, seed=1, cls_id=1,
+                    sep_id=2, pad_id=0)
+    assert len(ds) == 12
+    s = ds[0]
+    q_body = s["query_tokens"][1:7].tolist()
+    assert s["query_tokens"][0] == 1 and s["query_tokens"][7] == 2 and s["query_pad_mask"].sum() == 8
+    assert s["context_pad_mask"].sum() == 2 + 18                      # the query sentence was removed from its block
+    blk = ds.get_block(0, 4, 0)[0]
+    assert any(blk[i:i + 6].tolist() == q_body for i in range(1, 20))   # ... and it did come from that block
+
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch", params_dtype=torch.float32)
+    m = BiEncoderModel(cfg, 128, 32, biencoder_projection_dim=16)
+    assert m.query_model is not m.context_model and m.query_model.projection_enc.out_features == 16
+    batch = {k: torch.from_numpy(np.stack([ds[i][k] for i in range(12)])) for k in ds[0]}
+    opt = torch.optim.Adam(m.parameters(), lr=3e-3)
+    first = None
+    for _ in range(40):
+        q, c = m(batch["query_tokens"], batch["query_pad_mask"], None, batch["context_tokens"], batch["context_pad_mask"], None)
+        loss, stats = ict_loss(q, c, 32, score_scaling=True, topk=(1, 5))
+        first = first if first is not None else float(loss)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    assert float(loss) < 0.5 * first and float(stats["top1_acc"]) > 80.0
+    sd = m.state_dict_for_save_checkpoint()
+    assert set(sd) == {"query_model", "context_model"}
+    shared = BiEncoderModel(cfg, 128, 32, biencoder_shared_query_context_model=True)
+    assert set(shared.state_dict_for_save_checkpoint()) == {"model"}
