@@ -8,7 +8,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def get_tasks_args(parser):
     g = parser.add_argument_group("tasks")
-    g.add_argument("--task", type=str, required=True, help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE")
+    g.add_argument("--task", type=str, required=True,
+                   help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE | RETRIEVER-EVAL (MSDP-*: tasks/msdp/main.py)")
+    g.add_argument("--qa-data-test", type=str, default=None, help="NQ-open style TSV: question \\t [answers]")
+    g.add_argument("--faiss-match", type=str, default="string", choices=["regex", "string"])
+    g.add_argument("--faiss-topk-retrievals", type=int, default=100)
     g.add_argument("--train-data", nargs="*", default=None)
     g.add_argument("--epochs", type=int, default=3)
     g.add_argument("--valid-data", nargs="*", default=None, help="path(s) to the evaluation text")
@@ -30,6 +34,22 @@ if __name__ == "__main__":
         from tasks.glue.finetune import main
     elif args.task == "RACE":
         from tasks.race.finetune import main
+    elif args.task == "RETRIEVER-EVAL":
+        def main():
+            from megatronapp_b200.training import checkpointing
+            from megatronapp_b200.training.global_vars import get_tokenizer
+            from megatronapp_b200.training.training import get_model
+            from pretrain_ict import model_provider
+            from tasks.orqa.evaluate import ORQAEvaluator, read_evidence, read_nq_questions
+
+            model = get_model(model_provider, wrap_with_ddp=False)
+            if args.load:
+                checkpointing.load_checkpoint(model, None, None)
+            ev = ORQAEvaluator(model[0], get_tokenizer(), args.retriever_seq_length, args.indexer_batch_size)
+            docs = read_evidence(args.evidence_data_path)
+            ev.index_evidence(docs)
+            qs, ans = read_nq_questions(args.qa_data_test)
+            ev.evaluate(qs, ans, docs, args.retriever_report_topk_accuracies or (1, 5, 20), args.faiss_match)
     else:
         raise NotImplementedError(f"Task {args.task} is not implemented.")
     main()

@@ -173,3 +173,80 @@ def test_biencoder_ict_learns_in_batch_retrieval(tmp_path):
     assert set(sd) == {"query_model", "context_model"}
     shared = BiEncoderModel(cfg, 128, 32, biencoder_shared_query_context_model=True)
     assert set(shared.state_dict_for_save_checkpoint()) == {"model"}
+
+
+def test_msdp_metrics_prompting_and_orqa_matching(tmp_path):
+    import json
+
+    from tasks.msdp import prompt
+    from tasks.msdp.evaluate import evaluate_f1
+    from tasks.msdp.metrics import corpus_prf1, normalize_answer, prf1
+    from tasks.orqa.qa_utils import calculate_matches, has_answer
+
+    assert normalize_answer("The  Cat, sat -- on an APPLE!") == "cat sat on apple"
+    assert prf1("the cat sat", "a cat sat down") == (1.0, 2 / 3, 0.8)
+    assert prf1("x", "") is None and prf1("", "y") == (0.0, 0.0, 0.0)
+    assert corpus_prf1(["cat", "dog", "z"], ["cat", "cat", ""]) == (0.5, 0.5, 0.5)
+    (tmp_path / "g.txt").write_text("a red fox<|endoftext|>\nnothing\n")
+    (tmp_path / "a.txt").write_text("red fox\nno_passages_used\n")
+    assert evaluate_f1(str(tmp_path / "g.txt"), str(tmp_path / "a.txt"))[2] == 1.0
+
+    # stage-1 prompt: few-shot block chosen by "<topic> <last turn>", query in the "( turn ) topic =>" form
+    (tmp_path / "kp.jsonl").write_text(json.dumps({"Cats do cats purr?": ["( hi ) Cats => cats are felids", "e2", "e3"]}) + "\n")
+    (tmp_path / "in.txt").write_text("Cats\thello [SEP] do cats purr?\tCats purr when content.\n")
+    seen = []
+
+    def fake_generate(prompts, n):
+        seen.extend(prompts)
+        return [" they purr \n( next ) X => junk"] * len(prompts)
+
+    n = prompt.generate_samples(fake_generate, str(tmp_path / "in.txt"), str(tmp_path / "out.txt"), str(tmp_path / "kp.jsonl"),
+                                "knowledge", num_prompt_examples=2)
+    assert n == 1 and (tmp_path / "out.txt").read_text() == "they purr\n"
+    assert seen[0] == "( hi ) Cats => cats are felids \ne2 \n( do cats purr? ) Cats =>"
+    (tmp_path / "rp.txt").write_text("shot one\nshot two\nshot three\n")
+    seen.clear()
+    prompt.generate_samples(fake_generate, str(tmp_path / "in.txt"), str(tmp_path / "out2.txt"), str(tmp_path / "rp.txt"),
+                            "response", num_prompt_examples=2)
+    assert seen[0] == ("shot one \nshot two \nTopic: Cats. User says: do cats purr? We know that: Cats purr when content. "
+                       "System replies:")
+
+    assert has_answer(["New York"], "He moved to new york, in 1990.") and not has_answer(["York New"], "new york")
+    assert has_answer([r"19\d\d"], "born in 1987", "regex") and not has_answer(["(unclosed"], "text", "regex")
+    docs = {1: ("paris is the capital of france", ""), 2: ("berlin", ""), 3: ("the seine flows through paris", "")}
+    top_k, per_q = calculate_matches(docs, [["Paris"], ["Rome"]], [([2, 3, 1], [3., 2., 1.]), ([1, 2, 3], [3., 2., 1.])])
+    assert top_k == [0, 1, 1] and per_q[0] == [False, True, True] and per_q[1] == [False] * 3
+
+
+def test_orqa_evaluator_retrieves_with_biencoder():
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.legacy.model.biencoder_model import BiEncoderModel
+    from megatronapp_b200.parallel import state as ps
+    from tasks.orqa.evaluate import ORQAEvaluator
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+
+    class Tok:                      # word-level toy tokenizer
+        cls, sep, pad = 1, 2, 0
+
+        def __init__(self):
+            self.v = {}
+
+        def tokenize(self, t):
+            return [self.v.setdefault(w, 3 + len(self.v)) for w in t.lower().split()]
+
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch", params_dtype=torch.float32)
+    m = BiEncoderModel(cfg, 128, 16, biencoder_shared_query_context_model=True)     # shared tower: same text -> same vector
+    docs = {i: (f"passage number {w} about {w}", "") for i, w in enumerate(["zebra", "quartz", "lemon", "violin", "harbor"])}
+    ev = ORQAEvaluator(m, Tok(), seq_length=16, batch_size=2)
+    ev.index_evidence(docs)
+    assert ev.doc_emb.shape == (5, 32)
+    closest = ev.search(["passage number lemon about lemon"], top_k=3)
+    assert closest[0][0][0] == 2 and closest[0][1][0] >= closest[0][1][1]            # identical text ranks first
+    acc = ev.evaluate(["passage number lemon about lemon", "passage number harbor about harbor"], [["lemon"], ["nowhere"]], docs,
+                      report_topk=(1, 3))
+    assert acc[1] == 50.0 and acc[3] == 50.0
