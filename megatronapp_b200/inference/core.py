@@ -72,8 +72,12 @@ class StaticInferenceContext:
         self.batch_size_offset = 0
 
     def swap_key_value_dict(self, batch_idx):
-        for k, (kc, vc) in list(self.key_value_memory_dict.items()):
-            self.key_value_memory_dict[k] = (kc[:, batch_idx].contiguous(), vc[:, batch_idx].contiguous())
+        for k, v in list(self.key_value_memory_dict.items()):
+            if isinstance(k, tuple) and k[0] == "mamba":           # [conv_state, ssm_state], batch-major
+                self.key_value_memory_dict[k] = [t[batch_idx].contiguous() for t in v]
+            else:
+                kc, vc = v
+                self.key_value_memory_dict[k] = (kc[:, batch_idx].contiguous(), vc[:, batch_idx].contiguous())
 
     def is_static_batching(self):
         return True

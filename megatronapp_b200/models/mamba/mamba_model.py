@@ -81,8 +81,11 @@ class MambaModel(LanguageModule):
             x = self.embedding(input_ids=input_ids, position_ids=position_ids)
         rope = None
         if self.position_embedding_type == "rope":
-            n = (x if x is not None else self.decoder.input_tensor).size(0)
-            rope = self.rotary_pos_emb(n * (self.config.tensor_model_parallel_size if self.config.sequence_parallel else 1))
+            if inference_context is not None:
+                rope = self.rotary_pos_emb(inference_context.max_sequence_length)       # attention slices by offset
+            else:
+                n = (x if x is not None else self.decoder.input_tensor).size(0)
+                rope = self.rotary_pos_emb(n * (self.config.tensor_model_parallel_size if self.config.sequence_parallel else 1))
         h = self.decoder(x, attention_mask=attention_mask, inference_context=inference_context, rotary_pos_emb=rope)
         if not self.post_process:
             return h

@@ -151,12 +151,31 @@ class MambaMixer(MegatronModule):
         zxbcdt = zxbcdt.transpose(0, 1)                                # [b, s, ...]
         di, gn, nh, ng = self.d_inner_local, self.ngroups_local * self.d_state, self.nheads_local, self.ngroups_local
         z, xBC, dt = torch.split(zxbcdt, [di, di + 2 * gn, nh], dim=-1)
-        xBC = F.silu(self.conv1d(xBC.transpose(1, 2))[..., :s].transpose(1, 2))
+        ssm_state = None
+        if inference_context is not None:
+            # recurrent decode: carry the last (d_conv - 1) conv inputs and the SSM state between calls
+            # (reference mamba_mixer.py keeps conv_state / ssm_state in the inference context the same way)
+            cache = inference_context.key_value_memory_dict
+            key = ("mamba", self.layer_number)
+            b0 = inference_context.batch_size_offset
+            if inference_context.sequence_len_offset == 0 or key not in cache:
+                cache[key] = [xBC.new_zeros(inference_context.max_batch_size, self.d_conv - 1, xBC.shape[-1]),
+                              torch.zeros(inference_context.max_batch_size, nh, self.headdim, self.d_state,
+                                          dtype=torch.float32, device=xBC.device)]
+            conv_state, ssm_all = cache[key]
+            seq = torch.cat([conv_state[b0:b0 + b], xBC], dim=1)                       # [b, d_conv-1+s, c]
+            conv_state[b0:b0 + b] = seq[:, -(self.d_conv - 1):]
+            xBC = F.silu(F.conv1d(seq.transpose(1, 2), self.conv1d.weight, self.conv1d.bias, groups=seq.shape[-1]).transpose(1, 2))
+            ssm_state = ssm_all[b0:b0 + b]
+        else:
+            xBC = F.silu(self.conv1d(xBC.transpose(1, 2))[..., :s].transpose(1, 2))
         x, B, C = torch.split(xBC, [di, gn, gn], dim=-1)
         dt = F.softplus(dt.float() + self.dt_bias.float())
-        y, _ = ssd_scan(x.reshape(b, s, nh, self.headdim), dt, -torch.exp(self.A_log.float()),
-                        B.reshape(b, s, ng, self.d_state), C.reshape(b, s, ng, self.d_state),
-                        self.D, self.chunk_size)
+        y, new_state = ssd_scan(x.reshape(b, s, nh, self.headdim), dt, -torch.exp(self.A_log.float()),
+                                B.reshape(b, s, ng, self.d_state), C.reshape(b, s, ng, self.d_state),
+                                self.D, self.chunk_size, initial_state=ssm_state)
+        if inference_context is not None:
+            ssm_all[b0:b0 + b] = new_state
         y = y.reshape(b, s, di)
         y = (y * F.silu(z)).float().view(b, s, ng, di // ng)            # gated RMSNorm, one statistic per B/C group
         y = (y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-5)).view(b, s, di) * self.norm_weight.float()

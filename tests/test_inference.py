@@ -195,3 +195,31 @@ def test_dynamic_engine_behind_rest_server(engine):
         assert out["tokens"][0][3:] == ref.generated_tokens.tolist()
     finally:
         srv.shutdown()
+
+
+def test_mamba_hybrid_recurrent_decode_matches_full_forward():
+    """Conv + SSM state caching (Mamba layers) next to the KV cache (attention layers) == recomputing the prefix."""
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.mamba.mamba_model import MambaModel
+    from megatronapp_b200.parallel import state as ps
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=4, hidden_size=32, num_attention_heads=4, mamba_state_dim=8, mamba_head_dim=8,
+                            mamba_num_groups=2, kernel_backend="torch", use_cpu_initialization=True, hidden_dropout=0.0,
+                            attention_dropout=0.0, params_dtype=torch.float32)
+    m = MambaModel(cfg, vocab_size=128, max_sequence_length=64, hybrid_override_pattern="M*-M", position_embedding_type="rope")
+    tok = NullTokenizer(127)
+    eng = StaticInferenceEngine(TextGenerationController(GPTInferenceWrapper(m, max_sequence_length=64), tok), max_batch_size=4)
+    res = eng.generate(["5 9 23 7 11", "3 4"], SamplingParams(top_k=1, num_tokens_to_generate=6))
+    m.eval()
+    for r in res:
+        toks = list(r.prompt_tokens)
+        for _ in range(r.generated_length):
+            ids = torch.tensor([toks])
+            with torch.no_grad():
+                nxt = int(m(ids, torch.arange(len(toks)).unsqueeze(0), None)[0, -1, :128].argmax())
+            toks.append(nxt)
+        assert toks[len(r.prompt_tokens):] == r.generated_tokens.tolist()
