@@ -184,6 +184,49 @@ class GPTInferenceWrapper:
         return logits
 
 
+class VLMInferenceWrapper(GPTInferenceWrapper):
+    """LLaVA-style generation (reference ``inference/model_inference_wrappers/multimodal/vlm_inference_wrapper.py``):
+    the prefill runs the vision tower and splices the image embeddings in, which makes the cached sequence longer
+    than the token sequence by ``image_tokens_count``; decode steps feed text tokens only and shift the cache /
+    rotary offset by that amount (embedding position ids stay those of the text stream)."""
+
+    def __init__(self, model, max_batch_size: int = 8, max_sequence_length: int = 2560, padded_vocab_size=None):
+        super().__init__(model, max_batch_size, max_sequence_length, padded_vocab_size)
+        self.images = self.num_image_tiles = None
+        self._extra = 0
+
+    def set_images(self, images: torch.Tensor, num_image_tiles: Optional[torch.Tensor] = None):
+        self.images, self.num_image_tiles = images, num_image_tiles
+
+    def prep_model_for_inference(self, prompts_tokens: torch.Tensor):
+        super().prep_model_for_inference(prompts_tokens)
+        self._extra = 0
+
+    @torch.no_grad()
+    def run_one_forward_step(self, tokens: torch.Tensor, start: int, end: int) -> torch.Tensor:
+        ctx, m = self.context, self.inner
+        ids = tokens[:, start:end]
+        pos = torch.arange(start, end, device=tokens.device).unsqueeze(0).expand_as(ids)
+        if start == 0:
+            n_img = (ids == m.image_token_index).sum(dim=1)
+            if int((tokens == m.image_token_index).sum()) != int(n_img.sum()):
+                raise ValueError("every image token must lie inside the shortest prompt of the batch (prefill window)")
+            if len(set(n_img.tolist())) > 1:
+                raise ValueError("all prompts of a batch must carry the same number of images")
+            tiles = self.num_image_tiles
+            per_img = m.img_seq_len if tiles is None else None
+            self._extra = int(n_img[0]) * (m.img_seq_len - 1) if per_img else \
+                int(tiles.sum()) // ids.shape[0] * m.img_seq_len - int(n_img[0])
+            ctx.sequence_len_offset = 0
+            logits = self.model(self.images, ids, pos, None, inference_params=ctx, num_image_tiles=tiles)
+            ctx.key_value_memory_dict["image_tokens_count"] = self._extra
+        else:
+            ctx.sequence_len_offset = start + self._extra
+            logits = self.model(None, ids, pos, None, inference_params=ctx)
+        ctx.sequence_len_offset = end + self._extra
+        return logits
+
+
 class TextGenerationController:
     def __init__(self, inference_wrapped_model: GPTInferenceWrapper, tokenizer):
         self.inference_wrapped_model = inference_wrapped_model

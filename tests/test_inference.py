@@ -223,3 +223,46 @@ def test_mamba_hybrid_recurrent_decode_matches_full_forward():
                 nxt = int(m(ids, torch.arange(len(toks)).unsqueeze(0), None)[0, -1, :128].argmax())
             toks.append(nxt)
         assert toks[len(r.prompt_tokens):] == r.generated_tokens.tolist()
+
+
+def test_vlm_generation_with_kv_cache_matches_full_forward():
+    import copy
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.inference import VLMInferenceWrapper
+    from megatronapp_b200.models.gpt import get_gpt_layer_local_spec
+    from megatronapp_b200.models.multimodal import DEFAULT_IMAGE_TOKEN_INDEX, LLaVAModel
+    from megatronapp_b200.models.vision import get_vit_layer_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.tp_layers import ColumnParallelLinear, RowParallelLinear
+    from megatronapp_b200.transformer.mlp import MLPSubmodules
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+    torch.manual_seed(0)
+    lcfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, kernel_backend="torch",
+                             use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0, params_dtype=torch.float32)
+    vcfg = copy.deepcopy(lcfg)
+    vcfg.num_layers = 1
+    pcfg = copy.deepcopy(lcfg)
+    pcfg.ffn_hidden_size = 32
+    m = LLaVAModel(lcfg, get_gpt_layer_local_spec(), 128, 64, vcfg, get_vit_layer_spec(), True, pcfg,
+                   MLPSubmodules(linear_fc1=ColumnParallelLinear, linear_fc2=RowParallelLinear), img_h=14, img_w=14,
+                   patch_dim=7, language_position_embedding_type="rope")
+    m.eval()
+    images = torch.rand(2, 3, 14, 14)
+    w = VLMInferenceWrapper(m, max_batch_size=2, max_sequence_length=64)
+    w.set_images(images)
+    eng = StaticInferenceEngine(TextGenerationController(w, NullTokenizer(127)), max_batch_size=2)
+    img = str(DEFAULT_IMAGE_TOKEN_INDEX)
+    res = eng.generate([f"5 {img} 9 23", f"7 {img} 11 3 8"], SamplingParams(top_k=1, num_tokens_to_generate=5))
+    assert w._extra == 3                                           # one image -> 4 embeddings in place of 1 token
+    for i, r in enumerate(res):
+        toks = list(r.prompt_tokens)
+        for _ in range(r.generated_length):
+            ids = torch.tensor([toks])
+            with torch.no_grad():
+                logits = m(images[i:i + 1], ids, torch.arange(len(toks)).unsqueeze(0), None)
+            toks.append(int(logits[0, -1, :128].argmax()))
+        assert toks[len(r.prompt_tokens):] == r.generated_tokens.tolist()
