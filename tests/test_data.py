@@ -288,3 +288,25 @@ def test_blended_megatron_dataset_builder(tmp_path):
     cfg3 = GPTDatasetConfig(random_seed=1, sequence_length=8, tokenizer=NullTokenizer(99))
     tr3, _, _ = BlendedMegatronDatasetBuilder(GPTDataset, [7, 0, 0], lambda: True, cfg3).build()
     assert cfg3.mock and len(tr3) == 7 and int(tr3[0]["tokens"].max()) < 100
+
+
+def test_preprocess_mmdata_roundtrip(tmp_path):
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location("preprocess_mmdata", os.path.join(ROOT, "tools", "preprocess_mmdata.py"))
+    mm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mm)
+    (tmp_path / "img").mkdir()
+    blobs = [bytes(range(7)), bytes(range(100, 112))]                 # 7 bytes (needs padding) and 12 bytes
+    for i, b in enumerate(blobs):
+        (tmp_path / "img" / f"{i:03d}.jpg").write_bytes(b)
+    (tmp_path / "cap.jsonl").write_text("\n".join(json.dumps({"text": t}) for t in ["5 6 7", "8 9 10 11 12 13"]) + "\n")
+    prefix = str(tmp_path / "mm")
+    mm.main(["--input", str(tmp_path / "cap.jsonl"), "--input-image", str(tmp_path / "img"), "--pad-length", "4",
+             "--tokenizer-type", "NullTokenizer", "--vocab-size", "50", "--output-prefix", prefix])
+    ds = IndexedDataset(prefix, multimodal=True)
+    assert len(ds) == 4 and ds.document_indices.tolist() == [0, 2, 4]
+    assert ds.index.sequence_modes.tolist() == [0, 1, 0, 1]
+    assert ds[0].tolist() == [5, 6, 7, 50] and ds[2].tolist() == [8, 9, 10, 11]     # padded with eod / truncated
+    assert mm.words_to_image_bytes(ds[1]) == blobs[0] and mm.words_to_image_bytes(ds[3]) == blobs[1]
