@@ -173,15 +173,63 @@ class GPTInferenceWrapper:
         self.context = StaticInferenceContext(prompts_tokens.shape[0], self.max_sequence_length)
 
     @torch.no_grad()
-    def run_one_forward_step(self, tokens: torch.Tensor, start: int, end: int) -> torch.Tensor:
-        """tokens [b, S_total]; runs positions [start, end) against the cache; returns logits [b, end-start, V]."""
+    def run_one_forward_step(self, tokens: torch.Tensor, start: int, end: int) -> Optional[torch.Tensor]:
+        """tokens [b, S_total]; runs positions [start, end) against the cache; returns logits [b, end-start, V]
+        (full vocabulary) on the last pipeline stage and ``None`` elsewhere.  Under pipeline parallelism the hidden
+        states hop stage to stage over the p2p channels (reference ``inference/communication_utils.py``); under
+        tensor parallelism the vocab-parallel logits are gathered."""
+        from ..parallel import p2p, state as ps
+
         ctx = self.context
         ctx.sequence_len_offset = start
         ids = tokens[:, start:end]
         pos = torch.arange(start, end, device=tokens.device).unsqueeze(0).expand_as(ids)
-        logits = self.model(ids, pos, None, inference_context=ctx)
+        pp = ps.get_pipeline_model_parallel_world_size() if ps.model_parallel_is_initialized() else 1
+        if pp > 1:
+            cfg = self.inner.config
+            if not ps.is_pipeline_first_stage():
+                h = p2p.recv((end - start, ids.shape[0], cfg.hidden_size), cfg.pipeline_dtype or cfg.params_dtype,
+                             ps.get_pipeline_model_parallel_prev_rank(), "fwd", "recv-forward")
+                self.inner.set_input_tensor(h)
+            out = self.model(ids, pos, None, inference_context=ctx)
+            if not ps.is_pipeline_last_stage():
+                p2p.send(out, ps.get_pipeline_model_parallel_next_rank(), "fwd", "send-forward")
+                p2p.flush()
+                out = None
+        else:
+            out = self.model(ids, pos, None, inference_context=ctx)
         ctx.sequence_len_offset = end
-        return logits
+        return self._full_vocab(out)
+
+    def _full_vocab(self, logits):
+        from ..parallel import state as ps
+
+        if logits is None or not ps.model_parallel_is_initialized() or ps.get_tensor_model_parallel_world_size() == 1:
+            return logits
+        full = self.padded_vocab_size or getattr(self.inner, "vocab_size", None)
+        if full is not None and logits.shape[-1] >= full:
+            return logits                                  # the model already gathered (parallel_output=False)
+        from ..parallel.mappings import gather_from_tensor_model_parallel_region
+
+        return gather_from_tensor_model_parallel_region(logits)
+
+
+def sync_sampled_tokens(new: Optional[torch.Tensor], batch: int, device) -> torch.Tensor:
+    """Every model-parallel rank continues with the SAME next tokens: the last pipeline stage samples, then the
+    tokens go to the other stages (PP group) and, inside each stage, from TP rank 0 to its peers."""
+    from ..parallel import state as ps
+
+    if not ps.model_parallel_is_initialized():
+        return new
+    import torch.distributed as dist
+
+    if new is None:
+        new = torch.zeros(batch, dtype=torch.long, device=device)
+    if ps.get_pipeline_model_parallel_world_size() > 1:
+        dist.broadcast(new, ps.get_pipeline_model_parallel_last_rank(), group=ps.get_pipeline_model_parallel_group())
+    if ps.get_tensor_model_parallel_world_size() > 1:
+        dist.broadcast(new, ps.get_tensor_model_parallel_src_rank(), group=ps.get_tensor_model_parallel_group())
+    return new
 
 
 class VLMInferenceWrapper(GPTInferenceWrapper):
@@ -266,19 +314,22 @@ class TextGenerationController:
         start = 0
         for pos in range(min_len, total):
             logits = self.inference_wrapped_model.run_one_forward_step(tokens, start, pos)
-            last = logits[:, -1, :]
-            new = self.sample_from_logits(last, params, vocab)
-            scope_hooks.tik_result(last, new)
+            last = new = None
+            if logits is not None:                      # last pipeline stage
+                last = logits[:, -1, :]
+                new = self.sample_from_logits(last, params, vocab)
+                scope_hooks.tik_result(last, new)
+            new = sync_sampled_tokens(new, len(reqs), dev)
             started = lens_t <= pos                     # rows still consuming their prompt keep it
             tokens[started, pos] = new[started]
-            if params.return_log_probs:
+            if params.return_log_probs and last is not None:
                 lp = torch.log_softmax(last.float(), dim=-1)
                 for i in range(len(reqs)):
                     if started[i] and not done[i]:
                         logprobs[i].append(float(lp[i, tokens[i, pos]]))
             hit = started & (new == eod) & ~done
             gen_len += (started & ~done).long()
-            done |= hit
+            done |= hit | (gen_len >= n_gen)            # a short prompt in a ragged batch still stops after n_gen tokens
             start = pos
             if bool(done.all()):
                 break

@@ -50,13 +50,46 @@ def _validate(req: dict):
     return None
 
 
-def run_generate(engine: StaticInferenceEngine, req: dict):
+_GENERATE, _SHUTDOWN = 0, 1
+
+
+def _world():
+    import torch.distributed as dist
+
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def _announce(kind: int, req: Optional[dict] = None):
+    """Rank 0 tells the other model-parallel ranks what to run next (reference ``text_generation_server.py``:
+    ``send_do_generate`` / the ``while True: choice = broadcast(...)`` loop in ``run_text_generation_server.py``)."""
+    import torch.distributed as dist
+
+    if _world() > 1:
+        dist.broadcast_object_list([kind, req], src=0)
+
+
+def serve_worker_ranks(engine) -> None:
+    """Ranks > 0: block on rank 0's announcements and take part in every generation (all ranks must execute the
+    model-parallel forward passes); returns on shutdown."""
+    import torch.distributed as dist
+
+    while True:
+        box = [None, None]
+        dist.broadcast_object_list(box, src=0)
+        if box[0] == _SHUTDOWN:
+            return
+        run_generate(engine, box[1], announce=False)
+
+
+def run_generate(engine: StaticInferenceEngine, req: dict, announce: bool = True):
     params = SamplingParams(temperature=float(req.get("temperature", 1.0)), top_k=int(req.get("top_k", 0)),
                             top_p=float(req.get("top_p", 0.0)), return_log_probs=bool(req.get("logprobs", False)),
                             num_tokens_to_generate=int(req.get("tokens_to_generate", 64)))
     if req.get("random_seed") is not None:
         torch.manual_seed(int(req["random_seed"]))
-    with _LOCK:
+    with _LOCK:                                   # one generation at a time; the announcement is part of it
+        if announce:
+            _announce(_GENERATE, req)
         results = engine.generate(req["prompts"], params, add_BOS=bool(req.get("add_BOS", False)))
     out = {"text": [r.prompt + r.generated_text for r in results],
            "tokens": [r.prompt_tokens + r.generated_tokens.tolist() for r in results]}
@@ -143,6 +176,8 @@ class MegatronServer:
     def shutdown(self):
         if self.httpd:
             self.httpd.shutdown()
+            with _LOCK:
+                _announce(_SHUTDOWN)
 
 
 class InferenceWSServer:

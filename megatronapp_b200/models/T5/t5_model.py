@@ -67,6 +67,10 @@ class T5Model(LanguageModule):
                  position_embedding_type="learned_absolute", add_encoder=True, add_decoder=True,
                  relative_attention_num_buckets: int = 32, relative_attention_max_distance: int = 128):
         super().__init__(config)
+        # under a pipeline split, ``post_process`` of an encoder-only stage means "apply the encoder's final norm";
+        # the LM head (and the tied-embedding bookkeeping of LanguageModule) exists on decoder stages only
+        enc_post = post_process
+        post_process = post_process and add_decoder
         self.pre_process, self.post_process = pre_process, post_process
         self.add_encoder, self.add_decoder = add_encoder, add_decoder
         self.share_embeddings_and_output_weights = share_embeddings_and_output_weights
@@ -87,7 +91,7 @@ class T5Model(LanguageModule):
                     relative_attention_max_distance)
         if add_encoder:
             self.encoder = TransformerBlock(encoder_config or config, transformer_encoder_layer_spec,
-                                            pre_process=pre_process, post_process=True)
+                                            pre_process=pre_process, post_process=True if add_decoder else enc_post)
         if add_decoder:
             self.decoder = TransformerBlock(config, transformer_decoder_layer_spec, pre_process=pre_process,
                                             post_process=post_process)

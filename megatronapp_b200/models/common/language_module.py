@@ -33,6 +33,14 @@ class LanguageModule(MegatronModule):
             return
         if ps.is_pipeline_first_stage() and self.pre_process and not self.post_process:
             self.shared_embedding_or_output_weight().shared_embedding = True
+        if self.pre_process and not ps.is_pipeline_first_stage():
+            # first decoder stage of an encoder-decoder split: a second copy of the input embedding, zeroed so that
+            # the all-reduce below leaves every copy equal to the first stage's initialisation
+            self.embedding.word_embeddings.weight.data.fill_(0)
+            self.embedding.word_embeddings.weight.shared = True
+            self.embedding.word_embeddings.weight.shared_embedding = True
+            if getattr(self.embedding, "position_embeddings", None) is not None:
+                self.embedding.position_embeddings.weight.data.fill_(0)
         if self.post_process and not self.pre_process:
             # last stage keeps its own copy of the word embedding for the output layer,
             # initialised to zero and filled by an all-reduce with the first stage
@@ -44,6 +52,11 @@ class LanguageModule(MegatronModule):
             g = ps.get_embedding_group()
             if g is not None and not isinstance(g, ps._SingleGroup):
                 dist.all_reduce(w.data, group=g)
+        if dist.is_initialized() and ps.get_pipeline_model_parallel_split_rank() is not None and self.pre_process \
+                and ps.is_rank_in_position_embedding_group() and getattr(self.embedding, "position_embeddings", None) is not None:
+            g = ps.get_position_embedding_group()
+            if g is not None and not isinstance(g, ps._SingleGroup):
+                dist.all_reduce(self.embedding.position_embeddings.weight.data, group=g)
 
     def shared_embedding_or_output_weight(self):
         if self.pre_process:

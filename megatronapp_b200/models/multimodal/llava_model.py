@@ -180,6 +180,15 @@ class LLaVAModel(MegatronModule):
                                                                       loss_mask, labels, num_image_tiles)
             else:
                 combined = text.transpose(0, 1).contiguous()
+        elif self.post_process and labels is not None and loss_mask is not None:
+            # later pipeline stage: the hidden states arrive already spliced; only labels / loss mask must be expanded
+            # the same way (zero-width embeddings reuse the splice logic without touching any activation)
+            n_tiles = int(num_image_tiles.sum()) if num_image_tiles is not None else int((input_ids == self.image_token_index).sum())
+            if n_tiles > 0:
+                z = torch.zeros(0, device=input_ids.device)
+                _, new_labels, new_mask = self._preprocess_data(z.new_zeros(n_tiles, self.img_seq_len, 0),
+                                                                z.new_zeros(*input_ids.shape, 0), input_ids, loss_mask,
+                                                                labels, num_image_tiles)
         train_labels = None
         if new_labels is not None:
             train_labels = new_labels.clone()

@@ -393,16 +393,27 @@ def _allreduce_word_embedding_grads(model: List[nn.Module], config):
     g = ps.get_embedding_group()
     if not _is_real_group(g):
         return
-    if ps.is_pipeline_first_stage(ignore_virtual=True):
-        m = _unwrap(model[0])
-    elif ps.is_pipeline_last_stage(ignore_virtual=True):
-        m = _unwrap(model[-1])
-    else:
-        return
+    # first stage, last stage, and (encoder-decoder split) the first decoder stage each hold a copy
+    m = _unwrap(model[-1]) if ps.is_pipeline_last_stage(ignore_virtual=True) else _unwrap(model[0])
     if getattr(m, "share_embeddings_and_output_weights", False):
         w = m.shared_embedding_or_output_weight()
         grad = w.main_grad if hasattr(w, "main_grad") else w.grad
         dist.all_reduce(grad, group=g)
+
+
+def _allreduce_position_embedding_grads(model: List[nn.Module], config):
+    """Encoder and decoder halves of a pipeline-split T5 share the learned position table (reference
+    ``finalize_model_grads._allreduce_position_embedding_grads``)."""
+    if ps.get_pipeline_model_parallel_split_rank() is None or not ps.is_rank_in_position_embedding_group():
+        return
+    g = ps.get_position_embedding_group()
+    if not _is_real_group(g):
+        return
+    emb = getattr(_unwrap(model[0]), "embedding", None)
+    pos = getattr(emb, "position_embeddings", None) if emb is not None else None
+    if pos is not None:
+        w = pos.weight
+        dist.all_reduce(w.main_grad if hasattr(w, "main_grad") else w.grad, group=g)
 
 
 def finalize_model_grads(model: List[nn.Module], num_tokens: Optional[torch.Tensor] = None):
@@ -413,6 +424,7 @@ def finalize_model_grads(model: List[nn.Module], num_tokens: Optional[torch.Tens
                 chunk.finish_grad_sync()
     _allreduce_layernorm_grads(model, config)
     _allreduce_word_embedding_grads(model, config)
+    _allreduce_position_embedding_grads(model, config)
     if num_tokens is not None:
         # per-token loss: broadcast the token count from the last stage, sum over DP, rescale
         last = ps.get_pipeline_model_parallel_last_rank() if ps.model_parallel_is_initialized() else 0

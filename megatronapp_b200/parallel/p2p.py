@@ -21,7 +21,8 @@ from . import state as ps
 from ..scan.tracer import scope as _scope
 
 _CHANNELS: Dict[Tuple[int, int, str], object] = {}
-_PENDING: Dict[Tuple[int, int, str], Tuple[object, torch.Tensor]] = {}
+_PENDING: Dict[Tuple[int, int, str], list] = {}          # channel -> [(work handle, tensor kept alive)]
+_MAX_IN_FLIGHT = 8
 
 
 def build_channels() -> None:
@@ -64,13 +65,17 @@ def _channel(src: int, dst: int, kind: str):
 
 
 def send(tensor: torch.Tensor, dst: int, kind: str, name: str = "send") -> None:
-    """Asynchronous send; at most one message in flight per channel (the previous one is
-    waited for first, which also bounds the lifetime of its tensor)."""
+    """Asynchronous send.  Messages of one channel stay ordered; a short queue of in-flight sends is kept per channel
+    (completed ones are retired, the oldest is waited for only when ``_MAX_IN_FLIGHT`` is exceeded) -- a stage that
+    sends two tensors per boundary (encoder-decoder split) must not block on its first send while its peer is
+    itself sending."""
     me = dist.get_rank()
     key = (me, dst, kind)
-    prev = _PENDING.pop(key, None)
-    if prev is not None:
-        prev[0].wait()
+    q = _PENDING.setdefault(key, [])
+    while q and q[0][0].is_completed():
+        q.pop(0)
+    while len(q) >= _MAX_IN_FLIGHT:
+        q.pop(0)[0].wait()
     # a detached alias: the caller may pseudo-free ``tensor`` (swap its .data) right after this
     # returns, while the asynchronous send still needs the storage
     t = tensor.detach().contiguous()
@@ -78,7 +83,7 @@ def send(tensor: torch.Tensor, dst: int, kind: str, name: str = "send") -> None:
         t = tensor.detach()
     with _scope(name, data=t.numel() * t.element_size(), peer=dst):
         h = dist.isend(t, dst=dst, group=_channel(me, dst, kind))
-    _PENDING[key] = (h, t)
+    q.append((h, t))
 
 
 def recv(shape, dtype, src: int, kind: str, name: str = "recv", device=None, requires_grad: bool = False):
@@ -94,8 +99,8 @@ def recv(shape, dtype, src: int, kind: str, name: str = "recv", device=None, req
 
 def flush() -> None:
     for key in list(_PENDING):
-        h, _ = _PENDING.pop(key)
-        h.wait()
+        for h, _ in _PENDING.pop(key):
+            h.wait()
 
 
 # ---- Megatron-named helpers (non-interleaved convenience API) ---------------------------

@@ -172,6 +172,34 @@ def backward_step(input_tensor, output_tensor, output_tensor_grad, model_type, c
     return None if input_tensor is None else input_tensor.grad
 
 
+def _backward_step_encdec(inputs, outputs, output_grads, config, microbatch=None):
+    """Backward of one stage of a pipeline-split encoder-decoder model.  ``inputs`` / ``outputs`` / ``output_grads``
+    are lists (or None on the first / last stage).  A decoder stage forwards the encoder output unchanged, so the
+    gradient that comes back for it is added to this stage's own cross-attention gradient (reference
+    ``schedules.backward_step``, encoder_and_decoder branch)."""
+    inputs = [] if inputs is None else _as_list(inputs)
+    outs = _as_list(outputs)
+    grads = [None] * len(outs) if output_grads is None else _as_list(output_grads)
+    for x in inputs:
+        if x is not None and x.requires_grad:
+            x.retain_grad()
+    with _scope("backward", microbatch=microbatch):
+        head = outs[0]
+        if grads[0] is None and config.grad_scale_func is not None:
+            head = config.grad_scale_func(head)
+        torch.autograd.backward(head, grad_tensors=grads[0])
+    in_grads = [None if x is None else x.grad for x in inputs]
+    if len(grads) > 1 and grads[1] is not None and in_grads:
+        in_grads[-1] = grads[1] if in_grads[-1] is None else in_grads[-1].add_(grads[1])
+    return in_grads
+
+
+def _unwrap_chunk(m):
+    while hasattr(m, "module"):
+        m = m.module
+    return m
+
+
 # ---------------------------------------------------------------------------
 # the executor
 # ---------------------------------------------------------------------------
@@ -194,9 +222,19 @@ def get_tensor_shapes(seq_length, micro_batch_size, config) -> Tuple[int, int, i
     return (s, micro_batch_size, config.hidden_size)
 
 
+def _encdec_shapes(rank: int, seq_length: int, decoder_seq_length: int, micro_batch_size: int, config) -> List[Tuple]:
+    """Activations crossing the boundary AFTER pipeline stage ``rank`` of an encoder-decoder model (reference
+    ``schedules.get_tensor_shapes``): encoder stages pass the encoder stream; decoder stages pass the decoder stream
+    AND the (finished) encoder output, which every decoder stage needs for cross attention."""
+    enc = get_tensor_shapes(seq_length, micro_batch_size, config)
+    if ps.is_inside_encoder(rank):
+        return [enc]
+    return [get_tensor_shapes(decoder_seq_length, micro_batch_size, config), enc]
+
+
 def run_tasks(tasks: List[Task], *, forward_step_func, data_iterator, model: List, num_microbatches: int,
               seq_length: int, micro_batch_size: int, forward_only: bool, collect_non_loss_data: bool,
-              first_val_step=None, on_task: Optional[Callable] = None):
+              first_val_step=None, on_task: Optional[Callable] = None, decoder_seq_length: Optional[int] = None):
     """Execute a task list on this pipeline rank."""
     chunks = _as_list(model)
     C = len(chunks)
@@ -207,6 +245,13 @@ def run_tasks(tasks: List[Task], *, forward_step_func, data_iterator, model: Lis
     pp = ps.get_pipeline_model_parallel_world_size()
     rank = ps.get_pipeline_model_parallel_rank()
     shape = get_tensor_shapes(seq_length, micro_batch_size, config)
+    encdec = pp > 1 and ps.get_pipeline_model_parallel_split_rank() is not None \
+        and str(getattr(chunks[0], "model_type", None) or getattr(_unwrap_chunk(chunks[0]), "model_type", None)) == "encoder_and_decoder"
+    if encdec:
+        if C > 1:
+            raise ValueError("interleaved schedule is not supported for encoder-decoder models")
+        recv_shapes = _encdec_shapes(rank - 1, seq_length, decoder_seq_length or seq_length, micro_batch_size, config) if rank > 0 else []
+        send_shapes = _encdec_shapes(rank, seq_length, decoder_seq_length or seq_length, micro_batch_size, config)
     dtype = config.pipeline_dtype or config.params_dtype
     prev_r = ps.get_pipeline_model_parallel_prev_rank() if pp > 1 else None
     next_r = ps.get_pipeline_model_parallel_next_rank() if pp > 1 else None
@@ -234,7 +279,9 @@ def run_tasks(tasks: List[Task], *, forward_step_func, data_iterator, model: Lis
             on_task(t)
         if t.kind == "F":
             inp = None
-            if pp > 1 and not is_first(c):
+            if encdec and not is_first(c):
+                inp = [p2p.recv(sh, dtype, prev_r, "fwd", "recv-forward", requires_grad=not forward_only) for sh in recv_shapes]
+            elif pp > 1 and not is_first(c):
                 inp = p2p.recv(shape, dtype, prev_r, "fwd", "recv-forward", requires_grad=not forward_only)
             ctx = torch.no_grad() if forward_only else contextlib.nullcontext()
             with ctx:
@@ -244,7 +291,12 @@ def run_tasks(tasks: List[Task], *, forward_step_func, data_iterator, model: Lis
                                          is_last_stage=is_last(c))
             first_f_done[c] = True
             total_num_tokens += ntok.to(total_num_tokens.device) if torch.is_tensor(ntok) else int(ntok)
-            if pp > 1 and not is_last(c):
+            if encdec and not is_last(c):
+                if ps.is_inside_decoder(rank):
+                    out = [out, inp[-1]]                 # hand the encoder output on to the next decoder stage
+                for o in _as_list(out):
+                    p2p.send(o, next_r, "fwd", "send-forward")
+            elif pp > 1 and not is_last(c):
                 p2p.send(out, next_r, "fwd", "send-forward")
                 if not forward_only:
                     deallocate_output_tensor(out, config.deallocate_pipeline_outputs)
@@ -253,10 +305,17 @@ def run_tasks(tasks: List[Task], *, forward_step_func, data_iterator, model: Lis
         else:
             inp, out = stash.pop((t.microbatch, c))
             grad = None
-            if pp > 1 and not is_last(c):
+            if encdec and not is_last(c):
+                grad = [p2p.recv(sh, dtype, next_r, "bwd", "recv-backward") for sh in send_shapes]
+            elif pp > 1 and not is_last(c):
                 grad = p2p.recv(shape, dtype, next_r, "bwd", "recv-backward")
             if hasattr(chunks[c], "is_last_microbatch"):
                 chunks[c].is_last_microbatch = (t.microbatch == last_b[c])
+            if encdec:
+                in_grad = _backward_step_encdec(inp, out, grad, config, microbatch=t.microbatch)
+                for g_ in (in_grad if not is_first(c) else []):
+                    p2p.send(g_, prev_r, "bwd", "send-backward")
+                continue
             in_grad = backward_step(inp, out, grad, None, config, microbatch=t.microbatch)
             if pp > 1 and not is_first(c):
                 p2p.send(in_grad, prev_r, "bwd", "send-backward")
@@ -278,7 +337,8 @@ def forward_backward_no_pipelining(*, forward_step_func, data_iterator, model, n
     return run_tasks(schedule_no_pipelining(num_microbatches, forward_only), forward_step_func=forward_step_func,
                      data_iterator=data_iterator, model=model, num_microbatches=num_microbatches,
                      seq_length=seq_length, micro_batch_size=micro_batch_size, forward_only=forward_only,
-                     collect_non_loss_data=collect_non_loss_data, first_val_step=first_val_step)
+                     collect_non_loss_data=collect_non_loss_data, first_val_step=first_val_step,
+                     decoder_seq_length=decoder_seq_length)
 
 
 def forward_backward_pipelining_without_interleaving(*, forward_step_func, data_iterator, model, num_microbatches,
@@ -290,7 +350,7 @@ def forward_backward_pipelining_without_interleaving(*, forward_step_func, data_
     return run_tasks(tasks, forward_step_func=forward_step_func, data_iterator=data_iterator, model=model,
                      num_microbatches=num_microbatches, seq_length=seq_length, micro_batch_size=micro_batch_size,
                      forward_only=forward_only, collect_non_loss_data=collect_non_loss_data,
-                     first_val_step=first_val_step)
+                     first_val_step=first_val_step, decoder_seq_length=decoder_seq_length)
 
 
 def forward_backward_pipelining_with_interleaving(*, forward_step_func, data_iterator, model, num_microbatches,

@@ -168,6 +168,8 @@ def initialize_model_parallel(
         order=order,
         fbd=forward_backward_disaggregating,
         num_distributed_optimizer_instances=num_distributed_optimizer_instances,
+        split_rank=(encoder_pipeline_model_parallel_size or pipeline_model_parallel_split_rank or None)
+        if pipeline_model_parallel_size > 1 else None,
     )
     backend = dist.get_backend() if (dist.is_available() and dist.is_initialized()) else None
     _STATE = ParallelState(topo, rk, backend=backend,
@@ -361,6 +363,40 @@ def is_rank_in_embedding_group(ignore_virtual: bool = False) -> bool:
     if _STATE is None:
         return True
     return _STATE.rank in _STATE.ranks("embd")
+
+
+# ---- encoder / decoder pipeline split (T5-style models; reference parallel_state.is_inside_encoder ...) --------
+def get_pipeline_model_parallel_split_rank() -> Optional[int]:
+    return None if _STATE is None else _STATE.topo.split_rank
+
+
+def is_inside_encoder(rank: Optional[int] = None) -> bool:
+    split = get_pipeline_model_parallel_split_rank()
+    if split is None:
+        return True
+    return (get_pipeline_model_parallel_rank() if rank is None else rank) < split
+
+
+def is_inside_decoder(rank: Optional[int] = None) -> bool:
+    split = get_pipeline_model_parallel_split_rank()
+    if split is None:
+        return True
+    return (get_pipeline_model_parallel_rank() if rank is None else rank) >= split
+
+
+def is_pipeline_stage_before_split(rank: Optional[int] = None) -> bool:
+    return get_pipeline_model_parallel_world_size() == 1 or is_inside_encoder(rank) or \
+        get_pipeline_model_parallel_split_rank() is None
+
+
+def is_pipeline_stage_after_split(rank: Optional[int] = None) -> bool:
+    return get_pipeline_model_parallel_world_size() == 1 or is_inside_decoder(rank) or \
+        get_pipeline_model_parallel_split_rank() is None
+
+
+def is_pipeline_stage_at_split() -> bool:
+    r = get_pipeline_model_parallel_rank()
+    return is_pipeline_stage_before_split(r) and is_pipeline_stage_after_split(r + 1)
 
 
 def is_rank_in_position_embedding_group() -> bool:

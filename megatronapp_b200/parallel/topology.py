@@ -126,8 +126,11 @@ class Topology:
     order: str = "tp-cp-ep-dp-pp"
     fbd: bool = False
     num_distributed_optimizer_instances: int = 1
+    split_rank: int | None = None   # first pipeline stage of the decoder (encoder-decoder models)
 
     def __post_init__(self):
+        if self.split_rank is not None and not (0 < self.split_rank < self.pp):
+            raise ValueError(f"pipeline split rank {self.split_rank} must lie strictly inside [1, pp={self.pp})")
         mp = self.tp * self.pp * self.cp
         if self.world_size % mp != 0:
             raise ValueError(
@@ -214,7 +217,7 @@ class Topology:
         if kind == "embd":
             return [self.embedding_ranks(g) for g in d.groups("pp")]
         if kind == "pos_embd":
-            return [[g[0]] for g in d.groups("pp")]
+            return [self.position_embedding_ranks(g) for g in d.groups("pp")]
         if kind == "fb":  # forward/backward twins (size-2 groups inside each dp group)
             out = []
             for g in d.groups("dp"):
@@ -248,10 +251,20 @@ class Topology:
         raise ValueError(f"rank {rank} is in no {kind} group")
 
     def embedding_ranks(self, pp_group: Sequence[int]) -> List[int]:
-        """First and last pipeline stage share the tied embedding gradient."""
+        """First and last pipeline stage share the tied embedding gradient; with an encoder-decoder split the
+        first decoder stage holds a third copy (reference ``parallel_state.default_embedding_ranks``)."""
         if len(pp_group) == 1:
             return [pp_group[0]]
-        return [pp_group[0], pp_group[-1]]
+        out = [pp_group[0], pp_group[-1]]
+        if self.split_rank is not None and pp_group[self.split_rank] not in out:
+            out.insert(1, pp_group[self.split_rank])
+        return out
+
+    def position_embedding_ranks(self, pp_group: Sequence[int]) -> List[int]:
+        out = [pp_group[0]]
+        if self.split_rank is not None and len(pp_group) > 1 and pp_group[self.split_rank] not in out:
+            out.append(pp_group[self.split_rank])
+        return out
 
     # ---- convenience ---------------------------------------------------
     @property

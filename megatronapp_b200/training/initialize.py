@@ -81,9 +81,14 @@ def _initialize_distributed(args):
             dist.all_reduce(t)
     if ps.model_parallel_is_initialized():
         return
+    split = args.pipeline_model_parallel_split_rank or args.encoder_pipeline_model_parallel_size or None
+    if split is None and getattr(args, "model_type_hint", None) == "encoder_and_decoder" \
+            and args.pipeline_model_parallel_size > 1:
+        split = args.pipeline_model_parallel_size // 2          # half of the stages each, like the reference's T5 recipes
+    args.pipeline_model_parallel_split_rank = split
     ps.initialize_model_parallel(
         args.tensor_model_parallel_size, args.pipeline_model_parallel_size,
-        args.virtual_pipeline_model_parallel_size, args.pipeline_model_parallel_split_rank,
+        args.virtual_pipeline_model_parallel_size, split,
         context_parallel_size=args.context_parallel_size,
         hierarchical_context_parallel_sizes=args.hierarchical_context_parallel_sizes,
         expert_model_parallel_size=args.expert_model_parallel_size,

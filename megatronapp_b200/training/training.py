@@ -84,6 +84,18 @@ def get_model(model_provider_func: Callable, model_type=None, wrap_with_ddp: boo
             m.model_type = model_type
             model.append(m)
         ps.set_virtual_pipeline_model_parallel_rank(0)
+    elif pp > 1 and str(model_type) == "encoder_and_decoder":
+        # encoder stages [0, split), decoder stages [split, pp): embeddings on the first stage of each half, heads /
+        # final norms on the last stage of each half (reference training.py get_model, encoder_and_decoder branch)
+        if vpp is not None:
+            raise ValueError("interleaved schedule is not supported for encoder-decoder models")
+        rank, split = ps.get_pipeline_model_parallel_rank(), ps.get_pipeline_model_parallel_split_rank()
+        if split is None:
+            raise ValueError("encoder-decoder model with pp > 1 needs --pipeline-model-parallel-split-rank")
+        m = model_provider_func(pre_process=rank in (0, split), post_process=rank in (split - 1, pp - 1),
+                                add_encoder=ps.is_inside_encoder(rank), add_decoder=ps.is_inside_decoder(rank))
+        m.model_type = model_type
+        model = [m]
     else:
         m = model_provider_func(pre_process=ps.is_pipeline_first_stage(), post_process=ps.is_pipeline_last_stage())
         m.model_type = model_type
@@ -484,7 +496,7 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             print_rank_0(f">>> weight hashes match across DP replicas at iteration {iteration}")
         if args.log_straggler and iteration % args.log_interval == 0:
             stimer.report(num_floating_point_operations(args, batch_size) * args.log_interval, args.log_interval)
-        if args.eval_interval and iteration % args.eval_interval == 0 and valid_data_iterator is not None:
+        if args.eval_interval and iteration % args.eval_interval == 0 and getattr(args, "do_valid", valid_data_iterator is not None):
             timers("interval-time").stop()
             evaluate_and_print_results(f"iteration {iteration}", forward_step_func, valid_data_iterator, model,
                                        iteration, config)
@@ -663,13 +675,23 @@ def build_train_valid_test_data_iterators(provider):
                                                args.dataloader_type, args.num_workers, args.seed)
             if dl is not None:
                 iters[i] = iter(dl) if args.dataloader_type == "single" else iter(cyclic_iter(dl))
+    # every rank must agree on whether a split exists (only TP rank 0 holds iterators): reference
+    # training.py build_train_valid_test_data_loaders broadcasts do_train / do_valid / do_test the same way
+    flags = torch.tensor([int(it is not None) for it in iters], dtype=torch.long,
+                         device="cuda" if (torch.cuda.is_available() and args.distributed_backend == "nccl") else "cpu")
+    if dist.is_initialized():
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+    args.do_train = bool(flags[0]) or bool(getattr(args, "do_train", False))
+    args.do_valid = bool(flags[1]) or bool(getattr(args, "do_valid", False))
+    args.do_test = bool(flags[2]) or bool(getattr(args, "do_test", False))
     return tuple(iters)
 
 
 def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forward_step_func,
              process_non_loss_data_func=None, extra_args_provider=None, args_defaults=None,
              get_embedding_ranks=None, get_position_embedding_ranks=None, non_loss_data_func=None, args_list=None):
-    initialize_megatron(extra_args_provider=extra_args_provider, args_defaults=args_defaults or {},
+    initialize_megatron(extra_args_provider=extra_args_provider,
+                        args_defaults={**(args_defaults or {}), "model_type_hint": str(model_type)},
                         args_list=args_list)
     args = get_args()
     timers = get_timers()
@@ -717,7 +739,7 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     tracer = get_tracer()
     if tracer.enabled:
         tracer.shutdown()
-    if args.eval_iters and valid_it is not None and not args.skip_train and args.eval_interval:
+    if args.eval_iters and getattr(args, "do_valid", valid_it is not None) and not args.skip_train and args.eval_interval:
         evaluate_and_print_results(f"the end of training for val data", forward_step_func, valid_it, model,
                                    iteration, config)
     if args.use_dpp:

@@ -129,3 +129,20 @@ def get_batch_on_this_tp_rank(data_iterator, args, pinned_stage=None):
             if batch.get(k) is not None:
                 dist.broadcast(batch[k], src, group=tp_group)
     return batch
+
+
+def broadcast_batch(data_iterator, int_keys, float_keys=()):
+    """Fetch the next micro-batch on TP rank 0 and broadcast it over the TP group (the other TP ranks hold no data
+    iterator) -- the ``tensor_parallel.broadcast_data`` idiom of the reference's ``pretrain_bert / pretrain_t5``."""
+    from ..parallel import state as ps
+    from ..parallel.data import broadcast_data
+
+    data = None
+    if data_iterator is not None and ps.get_tensor_model_parallel_rank() == 0:
+        raw = next(data_iterator)
+        data = {k: torch.as_tensor(raw[k]) for k in list(int_keys) + list(float_keys)}
+        data = {k: (v.long() if k in int_keys else v.float()) for k, v in data.items()}
+    out = broadcast_data(list(int_keys), data, torch.int64)
+    if float_keys:
+        out.update(broadcast_data(list(float_keys), data, torch.float32))
+    return out

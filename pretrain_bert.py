@@ -14,7 +14,7 @@ from megatronapp_b200.parallel import state as mpu
 from megatronapp_b200.training.arguments import core_transformer_config_from_args
 from megatronapp_b200.training.global_vars import get_args
 from megatronapp_b200.training.training import pretrain
-from megatronapp_b200.training.utils import print_rank_0
+from megatronapp_b200.training.utils import broadcast_batch, print_rank_0
 
 
 class MockBertDataset(torch.utils.data.Dataset):
@@ -65,7 +65,7 @@ def loss_func(loss_mask, sentence_order, output_tensor):
 
 def forward_step(data_iterator, model):
     dev = next(model.parameters()).device
-    d = next(data_iterator)
+    d = broadcast_batch(data_iterator, ("text", "types", "labels", "is_random", "padding_mask"), ("loss_mask",))
     tokens, types, labels = d["text"].to(dev), d["types"].to(dev), d["labels"].to(dev)
     out = model(tokens, d["padding_mask"].to(dev), tokentype_ids=types, lm_labels=labels)
     return out, partial(loss_func, d["loss_mask"].to(dev), d["is_random"].to(dev))

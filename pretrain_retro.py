@@ -27,8 +27,14 @@ def add_retro_args(parser):
     return parser
 
 
+def _check_parallelism(args):
+    if args.pipeline_model_parallel_size != 1:
+        raise ValueError("retro currently does not support pipeline parallelism (same restriction as the reference)")
+
+
 def model_provider(pre_process=True, post_process=True):
     args = get_args()
+    _check_parallelism(args)
     print_rank_0("building Retro model ...")
     config = core_transformer_config_from_args(args, RetroConfig)
     config.retro_chunk_length, config.retro_num_neighbors = args.retro_chunk_length, args.retro_num_neighbors

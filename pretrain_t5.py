@@ -9,10 +9,11 @@ from functools import partial
 import torch
 
 from megatronapp_b200.models.T5 import T5Model, get_t5_decoder_block_spec, get_t5_encoder_block_spec
+from megatronapp_b200.parallel import state as mpu
 from megatronapp_b200.training.arguments import core_transformer_config_from_args
 from megatronapp_b200.training.global_vars import get_args
 from megatronapp_b200.training.training import pretrain
-from megatronapp_b200.training.utils import print_rank_0
+from megatronapp_b200.training.utils import broadcast_batch, print_rank_0
 
 
 class MockT5Dataset(torch.utils.data.Dataset):
@@ -37,6 +38,11 @@ def model_provider(pre_process=True, post_process=True, add_encoder=True, add_de
     config = core_transformer_config_from_args(args)
     n_enc = args.encoder_num_layers or args.num_layers
     n_dec = args.decoder_num_layers or args.num_layers
+    pp, split = mpu.get_pipeline_model_parallel_world_size(), mpu.get_pipeline_model_parallel_split_rank()
+    if pp > 1:                       # encoder layers over stages [0, split), decoder layers over [split, pp)
+        if n_enc % split or n_dec % (pp - split):
+            raise ValueError(f"encoder/decoder layers ({n_enc}/{n_dec}) must divide by their stage counts ({split}/{pp - split})")
+        n_enc, n_dec = n_enc // split, n_dec // (pp - split)
     return T5Model(config, config, get_t5_encoder_block_spec(n_enc), get_t5_decoder_block_spec(n_dec),
                    vocab_size=args.padded_vocab_size, max_sequence_length=args.max_position_embeddings,
                    pre_process=pre_process, post_process=post_process, parallel_output=True,
@@ -53,7 +59,8 @@ def loss_func(loss_mask, output_tensor):
 
 def forward_step(data_iterator, model):
     dev = next(model.parameters()).device
-    d = {k: v.to(dev) for k, v in next(data_iterator).items()}
+    d = broadcast_batch(data_iterator, ("text_enc", "text_dec", "labels", "enc_mask", "dec_mask", "enc_dec_mask"), ("loss_mask",))
+    d = {k: v.to(dev) for k, v in d.items()}
     out = model(d["text_enc"], d["text_dec"], d["enc_mask"], d["dec_mask"], d["enc_dec_mask"], lm_labels=d["labels"])
     return out, partial(loss_func, d["loss_mask"])
 

@@ -43,6 +43,10 @@ def add_vlm_extra_args(parser):
 def model_provider(pre_process=True, post_process=True, add_encoder=True, add_decoder=True):
     args = get_args()
     print_rank_0("building a multimodal (LLaVA) model ...")
+    if args.pipeline_model_parallel_size > 1:
+        # the vision tower and projector live with the text embedding on the first pipeline stage (reference
+        # pretrain_vlm.py: add_encoder = is_pipeline_first_stage() when no separate encoder pipeline is configured)
+        add_encoder = pre_process
     lcfg = core_transformer_config_from_args(args)
     vcfg = copy.deepcopy(lcfg)
     vcfg.num_layers = args.vision_num_layers or args.num_layers

@@ -325,6 +325,126 @@ def mamba_tp_reshard(path=None, sp=False):
             "scale": float(y1.detach().abs().max()), "local_heads": m.nheads_local, "full_heads": m1.nheads_local}
 
 
+def t5_pp_parity(pp=1, split=None, steps=2, n_mb=4):
+    """Pipeline-split T5 (encoder stages [0, split), decoder stages [split, pp)) trains exactly like the unsplit model."""
+    import re
+    import zlib
+    from functools import partial
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.T5 import T5Model, get_t5_decoder_block_spec, get_t5_encoder_block_spec
+    from megatronapp_b200.parallel import p2p, state as ps
+    from megatronapp_b200.parallel.ddp import finalize_model_grads
+    from megatronapp_b200.parallel.schedules import get_forward_backward_func
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(1, pp, pipeline_model_parallel_split_rank=split)
+    p2p.build_channels()
+    r = ps.get_pipeline_model_parallel_rank()
+    n_enc = n_dec = 2
+    enc_per, dec_per = (n_enc // split, n_dec // (pp - split)) if pp > 1 else (n_enc, n_dec)
+    cfg = TransformerConfig(num_layers=12, hidden_size=32, num_attention_heads=4, pipeline_model_parallel_size=pp,
+                            kernel_backend="torch", use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0,
+                            params_dtype=torch.float32, pipeline_dtype=torch.float32)
+    cfg.finalize_model_grads_func = finalize_model_grads
+    if pp > 1:
+        flags = dict(pre_process=r in (0, split), post_process=r in (split - 1, pp - 1),
+                     add_encoder=ps.is_inside_encoder(r), add_decoder=ps.is_inside_decoder(r))
+    else:
+        flags = dict(pre_process=True, post_process=True, add_encoder=True, add_decoder=True)
+    m = T5Model(cfg, cfg, get_t5_encoder_block_spec(enc_per), get_t5_decoder_block_spec(dec_per), vocab_size=64,
+                max_sequence_length=16, **flags)
+    m.model_type = "encoder_and_decoder"
+
+    def global_name(n):
+        mt = re.match(r"(encoder|decoder)\.layers\.(\d+)\.(.*)", n)
+        if n == "output_layer.weight":           # the last stage's private copy of the tied embedding
+            return "embedding.word_embeddings.weight"
+        if not mt:
+            return n
+        stack, i, rest = mt.group(1), int(mt.group(2)), mt.group(3)
+        base = (r * enc_per if stack == "encoder" else (r - split) * dec_per) if pp > 1 else 0
+        return f"{stack}.layers.{base + i}.{rest}"
+
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            g = torch.Generator().manual_seed(zlib.crc32(global_name(n).encode()))
+            v = torch.randn(p_.shape, generator=g) * 0.05
+            p_.copy_(1.0 + v if ("layernorm" in n or "layer_norm" in n) and n.endswith("weight") else v)
+
+    gb = torch.Generator().manual_seed(7)
+    batches = []
+    for _ in range(n_mb):
+        enc, dec = torch.randint(0, 64, (2, 12), generator=gb), torch.randint(0, 64, (2, 9), generator=gb)
+        batches.append({"enc": enc, "dec": dec[:, :-1], "labels": dec[:, 1:], "em": torch.ones(2, 12, 12),
+                        "dm": torch.tril(torch.ones(8, 8)).unsqueeze(0).expand(2, -1, -1), "edm": torch.ones(2, 8, 12)})
+
+    def loss_func(out):
+        l = out.float().mean()
+        return l, {"lm loss": l.detach()}
+
+    def fstep(it, model):
+        d = next(it)
+        return model(d["enc"], d["dec"], d["em"], d["dm"], d["edm"], lm_labels=d["labels"]), partial(loss_func)
+
+    fb = get_forward_backward_func()
+    losses = []
+    for _ in range(steps):
+        for p_ in m.parameters():
+            p_.grad = None
+        out = fb(forward_step_func=fstep, data_iterator=iter(batches), model=[m], num_microbatches=n_mb, seq_length=12,
+                 micro_batch_size=2, decoder_seq_length=8, forward_only=False)
+        if ps.is_pipeline_last_stage():
+            losses.append(float(sum(o["lm loss"] for o in out) / len(out)))
+        with torch.no_grad():
+            for p_ in m.parameters():
+                if p_.grad is not None:
+                    p_.sub_(0.5 * p_.grad)
+    emb = m.embedding.word_embeddings.weight.detach().double().sum().item() if flags["pre_process"] else None
+    pos = m.embedding.position_embeddings.weight.detach().double().sum().item() if flags["pre_process"] else None
+    return {"losses": losses, "emb": emb, "pos": pos, "rank": r}
+
+
+def generation_parity(tp=1, pp=1):
+    """Greedy generation under TP / PP gives the single-rank tokens (same deterministic weights)."""
+    from megatronapp_b200.data.tokenizer import NullTokenizer
+    from megatronapp_b200.inference import GPTInferenceWrapper, SamplingParams, StaticInferenceEngine, TextGenerationController
+
+    import re
+    import zlib
+
+    from megatronapp_b200.parallel import state as ps
+
+    rank, world = _setup()
+    st, _ = _model_losses(tp=tp, pp=pp, num_layers=2)
+    m = st.model[0]
+    # layout-independent weights: every parameter is a slice of a full tensor seeded by its GLOBAL name
+    tpr, ppr = ps.get_tensor_model_parallel_rank(), ps.get_pipeline_model_parallel_rank()
+    per_stage = 2 // pp
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            n = n.replace("module.", "")
+            mt = re.match(r"decoder\.layers\.(\d+)\.(.*)", n)
+            gname = f"decoder.layers.{int(mt.group(1)) + ppr * per_stage}.{mt.group(2)}" if mt else n
+            if gname == "output_layer.weight":
+                gname = "embedding.word_embeddings.weight"
+            shape = list(p_.shape)
+            dim = getattr(p_, "partition_dim", -1) if getattr(p_, "tensor_model_parallel", False) else -1
+            if dim >= 0:
+                shape[dim] *= tp
+            g = torch.Generator().manual_seed(zlib.crc32(gname.encode()))
+            full = torch.randn(shape, generator=g) * 0.08
+            if "layernorm" in gname and gname.endswith("weight"):
+                full = 1.0 + full
+            p_.copy_(full.chunk(tp, dim)[tpr] if dim >= 0 else full)
+    w = GPTInferenceWrapper(m, max_batch_size=4, max_sequence_length=32, padded_vocab_size=256)
+    eng = StaticInferenceEngine(TextGenerationController(w, NullTokenizer(255)), max_batch_size=4)
+    res = eng.generate(["5 9 23 7 100", "11 3", "200 201 202"], SamplingParams(top_k=1, num_tokens_to_generate=6,
+                                                                             return_log_probs=True))
+    return {"tokens": [r.generated_tokens.tolist() for r in res], "rank": rank,
+            "logprobs": [r.generated_log_probs for r in res]}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":

@@ -111,3 +111,28 @@ def test_mamba_mixer_tensor_parallel_and_reshard(tmp_path, sp):
     for r in res:
         assert r["local_heads"] * 2 == r["full_heads"]
         assert r["fwd"] < 1e-4 * max(1.0, r["scale"]) and r["gx"] < 1e-3, r
+
+
+def test_t5_encoder_decoder_pipeline_split_matches_unsplit():
+    base = run_distributed("t5_pp_parity", 1)[0]
+    assert len(base["losses"]) == 2 and base["losses"][1] < base["losses"][0]
+    for pp, split in ((2, 1), (4, 2), (3, 1)):
+        res = run_distributed("t5_pp_parity", pp, pp=pp, split=split)
+        last = [r for r in res if r["losses"]][0]
+        assert last["losses"] == pytest.approx(base["losses"], rel=1e-5), (pp, split, last["losses"], base["losses"])
+        # the tied word embedding (stage 0 / first decoder stage) and the shared position table stay identical copies
+        embs = [r["emb"] for r in res if r["emb"] is not None]
+        assert len(embs) == 2 and embs[0] == pytest.approx(embs[1], rel=1e-9) and embs[0] == pytest.approx(base["emb"], rel=1e-6)
+        poss = [r["pos"] for r in res if r["pos"] is not None]
+        assert poss[0] == pytest.approx(poss[1], rel=1e-9) and poss[0] == pytest.approx(base["pos"], rel=1e-6)
+
+
+def test_generation_under_tensor_and_pipeline_parallelism():
+    base = run_distributed("generation_parity", 1)[0]
+    assert all(1 <= len(t) <= 6 for t in base["tokens"]) and max(len(t) for t in base["tokens"]) > 2, base["tokens"]
+    for kw in ({"tp": 2}, {"pp": 2}):
+        res = run_distributed("generation_parity", 2, **kw)
+        for r in res:
+            assert r["tokens"] == base["tokens"], (kw, r["rank"])          # every rank ends with the same continuation
+        lp = [r["logprobs"] for r in res if r["logprobs"][0]]
+        assert lp and all(abs(a - b) < 1e-3 for x, y in zip(lp[-1], base["logprobs"]) for a, b in zip(x, y))

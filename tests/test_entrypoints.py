@@ -60,3 +60,76 @@ def test_pretrain_entrypoint_runs(case):
     loss = float(m.group(1))
     assert loss == loss and 0.0 < loss < 50.0
     assert "validation loss at the end of training" in out
+
+
+MULTI = {
+    "mamba_tp2_sp": ["pretrain_mamba.py", "--hybrid-override-pattern", "M*", "--tensor-model-parallel-size", "2",
+                     "--sequence-parallel", "--mamba-num-groups", "2", "--mamba-head-dim", "8", "--mamba-state-dim", "8"],
+    "bert_tp2": ["pretrain_bert.py", "--tensor-model-parallel-size", "2"],
+    "t5_tp2": ["pretrain_t5.py", "--encoder-seq-length", "32", "--decoder-seq-length", "16", "--tensor-model-parallel-size", "2"],
+    "t5_pp2_split": ["pretrain_t5.py", "--encoder-seq-length", "32", "--decoder-seq-length", "16",
+                     "--pipeline-model-parallel-size", "2"],
+    "gpt_moe_ep2": ["pretrain_gpt.py", "--num-experts", "4", "--moe-router-topk", "2", "--expert-model-parallel-size", "2"],
+    "gpt_tp2_sp": ["pretrain_gpt.py", "--tensor-model-parallel-size", "2", "--sequence-parallel"],
+    "vlm_pp2": ["pretrain_vlm.py", "--img-h", "14", "--img-w", "14", "--patch-dim", "7", "--pipeline-model-parallel-size", "2"],
+}
+
+
+@pytest.mark.parametrize("case", sorted(MULTI))
+def test_pretrain_entrypoint_two_ranks(case):
+    """Two gloo ranks through torchrun: only TP rank 0 owns data iterators, so batches must be broadcast and every rank
+    must agree on whether to evaluate; the T5 case exercises the encoder/decoder pipeline split."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    script, *extra = MULTI[case]
+    common = [("8" if a == "4" and COMMON[i - 1] == "--global-batch-size" else a) for i, a in enumerate(COMMON)]
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, script), *common, *extra],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    assert re.search(r"iteration\s+3/\s+3 \|", out) and "validation loss at the end of training" in out, out[-2000:]
+
+
+def test_text_generation_server_two_tensor_parallel_ranks():
+    """Rank 0 serves HTTP, rank 1 follows its announcements; both run the TP=2 forward passes of every request."""
+    import json
+    import signal
+    import time
+    import urllib.request
+
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    port = _port()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_port()), os.path.join(ROOT, "tools", "run_text_generation_server.py"),
+           "--tensor-model-parallel-size", "2", "--num-layers", "2", "--hidden-size", "32", "--num-attention-heads", "4",
+           "--seq-length", "32", "--max-position-embeddings", "64", "--micro-batch-size", "1", "--vocab-size", "200",
+           "--distributed-backend", "gloo", "--port", str(port), "--inference-max-seq-length", "64"]
+    proc = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                            start_new_session=True)
+    try:
+        def ask(prompts, n):
+            body = json.dumps({"prompts": prompts, "tokens_to_generate": n, "top_k": 1}).encode()
+            req = urllib.request.Request(f"http://127.0.0.1:{port}/api", data=body, method="PUT",
+                                         headers={"Content-Type": "application/json"})
+            return json.loads(urllib.request.urlopen(req, timeout=60).read())
+
+        out = None
+        for _ in range(90):
+            if proc.poll() is not None:
+                break
+            try:
+                out = ask(["5 6 7", "9 10"], 5)
+                break
+            except OSError:
+                time.sleep(1.0)
+        assert out is not None, proc.stdout.read()[-2000:] if proc.poll() is not None else "server never came up"
+        assert [len(t) for t in out["tokens"]] == [8, 7]
+        again = ask(["5 6 7"], 3)                                     # the worker rank keeps following
+        assert again["tokens"][0] == out["tokens"][0][:6]
+    finally:
+        os.killpg(proc.pid, signal.SIGTERM)                          # exactly the process group started above
+        proc.wait(timeout=30)

@@ -24,6 +24,10 @@ def main():
     tok = get_tokenizer()
     wrapper = GPTInferenceWrapper(model[0], args.inference_max_requests, args.inference_max_seq_length, args.padded_vocab_size)
     engine = StaticInferenceEngine(TextGenerationController(wrapper, tok), args.inference_max_requests)
+    if args.rank != 0:                       # model-parallel peers follow rank 0's announcements
+        from megatronapp_b200.inference.server import serve_worker_ranks
+
+        return serve_worker_ranks(engine)
     if args.enable_ws_server:
         InferenceWSServer(engine, args.num_layers, tok, port=args.ws_port).run()
     else:

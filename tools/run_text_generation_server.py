@@ -30,6 +30,10 @@ def main():
         engine = DynamicInferenceEngine.from_args(model[0], tok, args, core_transformer_config_from_args(args))
     else:
         engine = StaticInferenceEngine(TextGenerationController(wrapper, tok), args.inference_max_requests)
+    if args.rank != 0:                       # model-parallel peers follow rank 0's announcements
+        from megatronapp_b200.inference.server import serve_worker_ranks
+
+        return serve_worker_ranks(engine)
     if args.enable_ws_server:
         InferenceWSServer(engine, args.num_layers, tok, port=args.ws_port).run()
     else:
