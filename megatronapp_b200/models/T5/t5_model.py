@@ -95,6 +95,7 @@ class T5Model(LanguageModule):
         if add_decoder:
             self.decoder = TransformerBlock(config, transformer_decoder_layer_spec, pre_process=pre_process,
                                             post_process=post_process)
+        self._renumber_layers()
         if post_process:
             self.output_layer = ColumnParallelLinear(config.hidden_size, vocab_size, config=config,
                                                      init_method=config.init_method, bias=share_embeddings_and_output_weights,
@@ -102,6 +103,24 @@ class T5Model(LanguageModule):
                                                      skip_weight_param_allocation=pre_process and share_embeddings_and_output_weights)
         if pre_process or post_process:
             self.setup_embeddings_and_output_layer()
+
+    def _renumber_layers(self):
+        """Layer numbers (MegaScope hooks, checkpoint keys) count within the encoder resp. decoder stack.  The generic
+        pipeline offset assumes one stack split evenly over all stages, which is wrong under the encoder/decoder split."""
+        from ...parallel import state as ps
+
+        pp, split = ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_split_rank()
+        r = ps.get_pipeline_model_parallel_rank()
+        for name, stage in (("encoder", r), ("decoder", r - (split or 0))):
+            block = getattr(self, name, None)
+            if block is None:
+                continue
+            base = stage * len(block.layers) if (pp > 1 and split is not None) else 0
+            for i, layer in enumerate(block.layers):
+                old, new = layer.layer_number, base + i + 1
+                for mod in layer.modules():
+                    if getattr(mod, "layer_number", None) == old:
+                        mod.layer_number = new
 
     def set_input_tensor(self, t):
         t = t if isinstance(t, (list, tuple)) else [t]

@@ -58,6 +58,21 @@ class LanguageModule(MegatronModule):
             if g is not None and not isinstance(g, ps._SingleGroup):
                 dist.all_reduce(self.embedding.position_embeddings.weight.data, group=g)
 
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        """Tied embeddings: the last pipeline stage's private copy of the word embedding is stored under the
+        EMBEDDING's key as a non-main replica, so one tensor lands in the checkpoint and any PP layout can load it
+        (reference ``LanguageModule.tie_embeddings_and_output_weights_state_dict``)."""
+        import dataclasses
+
+        sd = super().sharded_state_dict(prefix, sharded_offsets, metadata)
+        k_out, k_emb = f"{prefix}output_layer.weight", f"{prefix}embedding.word_embeddings.weight"
+        if getattr(self, "share_embeddings_and_output_weights", False) and self.post_process and not self.pre_process \
+                and k_out in sd:
+            t = sd.pop(k_out)
+            rid = t.replica_id if isinstance(t.replica_id, tuple) else (t.replica_id,)
+            sd[k_out] = dataclasses.replace(t, key=k_emb, replica_id=(1,) + tuple(rid[1:]), allow_shape_mismatch=True)
+        return sd
+
     def shared_embedding_or_output_weight(self):
         if self.pre_process:
             return self.embedding.word_embeddings.weight

@@ -19,12 +19,45 @@ from ..transformer.mlp import MLP, MLPSubmodules
 from ..transformer.module import MegatronModule
 
 
+
+def _expert_replica(sd: dict) -> dict:
+    """Expert weights are replicated over the EXPERT data-parallel group, not the dense one: the main replica is the
+    one with expert-DP rank 0."""
+    import dataclasses
+
+    edp = ps.get_expert_data_parallel_rank()
+    out = {}
+    for k, t in sd.items():
+        rid = tuple(t.replica_id) if isinstance(t.replica_id, (tuple, list)) else (t.replica_id,)
+        out[k] = dataclasses.replace(t, replica_id=rid[:-1] + (edp,)) if len(rid) >= 1 else t
+    return out
+
+
+def _expert_offset(num_local: int) -> int:
+    return ps.get_expert_model_parallel_rank() * num_local
+
+
+def _check_etp():
+    if ps.get_expert_tensor_parallel_world_size() not in (1, ps.get_tensor_model_parallel_world_size()):
+        raise NotImplementedError("sharded checkpoints need expert-tensor-parallel size 1 or equal to the dense TP size")
+
+
 class SequentialMLP(MegatronModule):
     def __init__(self, num_local_experts, config, submodules: MLPSubmodules):
         super().__init__(config)
         self.add_bias = config.add_bias_linear
         self.num_local_experts = num_local_experts
         self.local_experts = nn.ModuleList([MLP(config, submodules, is_expert=True) for _ in range(num_local_experts)])
+
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        """Keys carry the GLOBAL expert index, so checkpoints reshard over the expert-parallel degree."""
+        from ..transformer.module import sharded_state_dict_of
+
+        _check_etp()
+        sd, off = {}, _expert_offset(self.num_local_experts)
+        for i, ex in enumerate(self.local_experts):
+            sd.update(sharded_state_dict_of(ex, f"{prefix}local_experts.{off + i}.", sharded_offsets, metadata))
+        return _expert_replica(sd)
 
     def forward(self, permuted_local_hidden_states, tokens_per_expert, permuted_probs=None):
         if self.num_local_experts == 1:
@@ -69,6 +102,22 @@ class GroupedMLP(MegatronModule):
             w.tensor_model_parallel, w.partition_dim, w.partition_stride = True, dim, 1
             w.allreduce = not (config.expert_model_parallel_size > 1)
         self.fc1_out = fc1_out
+
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        """One entry per (global expert, matrix): the stacked parameters are exposed as per-expert views with the same
+        keys ``SequentialMLP`` uses, so grouped and sequential checkpoints are interchangeable."""
+        from ..ckpt.sharded import make_sharded_tensor_for_checkpoint, make_tp_sharded_tensor_for_checkpoint
+
+        _check_etp()
+        etp = ps.get_expert_tensor_parallel_world_size()
+        sd, off, h = {}, _expert_offset(self.num_local_experts), self.config.hidden_size
+        for i in range(self.num_local_experts):
+            for name, view, axis in (("linear_fc1.weight", self.weight1.narrow(0, i * self.fc1_out, self.fc1_out), 0),
+                                     ("linear_fc2.weight", self.weight2.narrow(0, i * h, h), 1)):
+                key = f"{prefix}local_experts.{off + i}.{name}"
+                sd[key] = (make_tp_sharded_tensor_for_checkpoint(view, key, axis, prepend_offsets=tuple(sharded_offsets))
+                           if etp > 1 else make_sharded_tensor_for_checkpoint(view, key, prepend_offsets=tuple(sharded_offsets)))
+        return _expert_replica(sd)
 
     def forward(self, permuted_local_hidden_states, tokens_per_expert, permuted_probs=None):
         x = permuted_local_hidden_states

@@ -228,12 +228,24 @@ class MambaStack(MegatronModule):
         super().__init__(config)
         self.pre_process, self.post_process = pre_process, post_process
         self.input_tensor = None
-        self.layer_types = allocate_layers(config.num_layers, hybrid_attention_ratio, hybrid_mlp_ratio, hybrid_override_pattern)
+        from ..parallel import state as ps
+
+        all_types = allocate_layers(config.num_layers, hybrid_attention_ratio, hybrid_mlp_ratio, hybrid_override_pattern)
+        # this pipeline stage owns a contiguous slice of the layer pattern (reference MambaStack: pp_layer_offset)
+        pp = ps.get_pipeline_model_parallel_world_size()
+        if pp > 1:
+            if ps.get_virtual_pipeline_model_parallel_world_size() is not None:
+                raise ValueError("interleaved pipeline schedule is not supported for Mamba stacks")
+            if config.num_layers % pp:
+                raise ValueError(f"num_layers ({config.num_layers}) must divide by the pipeline size ({pp})")
+        n_local = config.num_layers // pp
+        self.layer_offset = ps.get_pipeline_model_parallel_rank() * n_local if pp > 1 else 0
+        self.layer_types = all_types[self.layer_offset:self.layer_offset + n_local]
         layers = []
         for i, t in enumerate(self.layer_types):
             if t == Symbols.MAMBA:
-                layers.append(MambaLayer(config, layer_number=i + 1))
-            elif t == Symbols.ATTENTION:
+                layers.append(MambaLayer(config, layer_number=self.layer_offset + i + 1))
+            elif t == Symbols.ATTENTION:        # TransformerLayer adds the pipeline offset to its layer number itself
                 layers.append(build_module(attention_layer_spec, config=config, layer_number=i + 1))
             else:
                 layers.append(build_module(mlp_layer_spec, config=config, layer_number=i + 1))
@@ -242,6 +254,16 @@ class MambaStack(MegatronModule):
 
     def set_input_tensor(self, t):
         self.input_tensor = t
+
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        from ..transformer.module import sharded_state_dict_of
+
+        sd = {}
+        for i, layer in enumerate(self.layers):            # checkpoint keys carry the GLOBAL layer index
+            sd.update(sharded_state_dict_of(layer, f"{prefix}layers.{self.layer_offset + i}.", sharded_offsets, metadata))
+        if self.final_norm is not None:
+            sd.update(sharded_state_dict_of(self.final_norm, f"{prefix}final_norm.", sharded_offsets, metadata))
+        return sd
 
     def forward(self, hidden_states, attention_mask=None, inference_context=None, rotary_pos_emb=None):
         if not self.pre_process:

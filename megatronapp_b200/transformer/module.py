@@ -14,6 +14,32 @@ def param_is_not_shared(param):
     return not getattr(param, "shared", False)
 
 
+def sharded_state_dict_of(module, prefix: str, sharded_offsets=(), metadata=None) -> dict:
+    """``module``'s sharded state dict whether or not it implements the protocol itself: containers
+    (``ModuleList`` / ``Sequential`` / ``ModuleDict``) are walked so that tensor-parallel leaves below them keep
+    their TP axes; plain torch modules contribute replicated tensors."""
+    import torch.nn as nn
+
+    from ..ckpt.sharded import make_sharded_tensors_for_checkpoint
+
+    if hasattr(module, "sharded_state_dict"):
+        return module.sharded_state_dict(prefix, sharded_offsets, metadata)
+    if isinstance(module, (nn.ModuleList, nn.Sequential, nn.ModuleDict)):
+        out = {}
+        for name, child in module.named_children():
+            out.update(sharded_state_dict_of(child, f"{prefix}{name}.", sharded_offsets, metadata))
+        return out
+    amap = {n: p.partition_dim for n, p in module.named_parameters(recurse=False)
+            if getattr(p, "tensor_model_parallel", False) and getattr(p, "partition_dim", -1) >= 0}
+    out = make_sharded_tensors_for_checkpoint(
+        {**{k: v for k, v in module._parameters.items() if v is not None},
+         **{k: v for k, v in module._buffers.items() if v is not None and k not in module._non_persistent_buffers_set}},
+        prefix, amap, sharded_offsets)
+    for name, child in module.named_children():
+        out.update(sharded_state_dict_of(child, f"{prefix}{name}.", sharded_offsets, metadata))
+    return out
+
+
 class MegatronModule(nn.Module):
     def __init__(self, config=None):
         super().__init__()
@@ -31,11 +57,7 @@ class MegatronModule(nn.Module):
         if own:
             sd.update(make_sharded_tensors_for_checkpoint(own, prefix, {}, sharded_offsets))
         for name, child in self.named_children():
-            if hasattr(child, "sharded_state_dict"):
-                sd.update(child.sharded_state_dict(f"{prefix}{name}.", sharded_offsets, metadata))
-            else:
-                sub = child.state_dict(prefix="", keep_vars=True)
-                sd.update(make_sharded_tensors_for_checkpoint(sub, f"{prefix}{name}.", {}, sharded_offsets))
+            sd.update(sharded_state_dict_of(child, f"{prefix}{name}.", sharded_offsets, metadata))
         return sd
 
     def set_is_first_microbatch(self):

@@ -60,6 +60,19 @@ class TransformerBlock(MegatronModule):
     def set_input_tensor(self, input_tensor):
         self.input_tensor = input_tensor
 
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        """Checkpoint keys use the GLOBAL layer index (``layer_number - 1`` already includes the pipeline / virtual
+        pipeline offset), so a checkpoint written at one PP degree loads at another."""
+        from .module import sharded_state_dict_of
+
+        sd = {}
+        for i, layer in enumerate(self.layers):
+            g = getattr(layer, "layer_number", i + 1) - 1
+            sd.update(sharded_state_dict_of(layer, f"{prefix}layers.{g}.", sharded_offsets, metadata))
+        if self.final_layernorm is not None:
+            sd.update(sharded_state_dict_of(self.final_layernorm, f"{prefix}final_layernorm.", sharded_offsets, metadata))
+        return sd
+
     def _checkpointed_forward(self, hidden_states, attention_mask, context, context_mask, rotary_pos_emb,
                               packed_seq_params):
         cfg = self.config

@@ -445,6 +445,84 @@ def generation_parity(tp=1, pp=1):
             "logprobs": [r.generated_log_probs for r in res]}
 
 
+def reshard_logits(tp=1, pp=1, path=None, mode="save", tied=True):
+    """Save a sharded checkpoint under one (tp, pp) layout / load it under another; returns the eval logits of a fixed
+    batch (from the last pipeline stage, gathered over TP) so that layouts can be compared."""
+    from megatronapp_b200.ckpt import sharded
+    from megatronapp_b200.parallel import p2p, state as ps
+    from megatronapp_b200.parallel.mappings import gather_from_tensor_model_parallel_region
+
+    rank, world = _setup()
+    torch.manual_seed(1234 if mode == "save" else 99)          # the loader starts from DIFFERENT weights
+    st, _ = _model_losses(tp=tp, pp=pp, num_layers=4)
+    m = st.model[0]
+    inner = m
+    while hasattr(inner, "module"):
+        inner = inner.module
+    if mode == "save":
+        with torch.no_grad():
+            for p_ in m.parameters():                             # break every symmetry the init may have
+                p_.add_(torch.randn_like(p_) * 0.02)
+        if pp > 1 and tied and ps.is_rank_in_embedding_group():   # keep the tied copies identical after the noise
+            w = inner.shared_embedding_or_output_weight()
+            dist.broadcast(w.data, ps.get_pipeline_model_parallel_first_rank(), group=ps.get_embedding_group())
+        sharded.save(inner.sharded_state_dict(), path, {"iteration": 1})
+    else:
+        sharded.load(inner.sharded_state_dict(), path)
+    dist.barrier()
+    m.eval()
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 256, (2, 16), generator=g)
+    pos = torch.arange(16).unsqueeze(0).expand(2, -1)
+    with torch.no_grad():
+        if pp > 1 and not ps.is_pipeline_first_stage():
+            h = p2p.recv((16, 2, 64), torch.float32, ps.get_pipeline_model_parallel_prev_rank(), "fwd")
+            inner.set_input_tensor(h)
+        out = m(ids, pos, None)
+        if pp > 1 and not ps.is_pipeline_last_stage():
+            p2p.send(out, ps.get_pipeline_model_parallel_next_rank(), "fwd")
+            p2p.flush()
+            return {"logits": None}
+        if tp > 1:
+            out = gather_from_tensor_model_parallel_region(out)
+    return {"logits": out[..., :256].flatten().tolist()}
+
+
+def moe_reshard(ep=1, path=None, mode="save", grouped=False):
+    """MoE layer checkpoint written at one expert-parallel degree (sequential experts) and read at another (grouped)."""
+    import torch.nn.functional as F
+    from megatronapp_b200.ckpt import sharded
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.gpt.gpt_layer_specs import get_mlp_module_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+    from megatronapp_b200.transformer.spec_utils import build_module
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(1, 1, expert_model_parallel_size=ep)
+    model_parallel_cuda_manual_seed(123 if mode == "save" else 7)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, ffn_hidden_size=64, num_moe_experts=4,
+                            moe_router_topk=2, expert_model_parallel_size=ep, moe_token_dispatcher_type="alltoall",
+                            add_bias_linear=False, activation_func=F.silu, gated_linear_unit=True,
+                            use_cpu_initialization=True, moe_grouped_gemm=grouped)
+    torch.manual_seed(5 if mode == "save" else 6)
+    layer = build_module(get_mlp_module_spec(False, 4, grouped), config=cfg)
+    if mode == "save":
+        with torch.no_grad():
+            torch.manual_seed(11)
+            layer.router.weight.copy_(torch.randn_like(layer.router.weight) * 0.5)       # replicated: same on every rank
+        sharded.save(layer.sharded_state_dict(prefix="mlp."), path, {})
+    else:
+        sharded.load(layer.sharded_state_dict(prefix="mlp."), path)
+    dist.barrier()
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(8, 2, 32, generator=g)                     # the same tokens on every rank
+    with torch.no_grad():
+        out, _ = layer(x)
+    keys = sorted(k for k in layer.sharded_state_dict(prefix="mlp.") if "local_experts" in k)
+    return {"out": out.flatten().tolist(), "keys": keys}
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":
