@@ -133,3 +133,32 @@ def test_text_generation_server_two_tensor_parallel_ranks():
     finally:
         os.killpg(proc.pid, signal.SIGTERM)                          # exactly the process group started above
         proc.wait(timeout=30)
+
+
+@pytest.mark.parametrize("fmt", ["torch_dist", "torch"])
+def test_checkpoint_resume_is_exact(tmp_path, fmt):
+    """4 iterations straight == 2 iterations, save (distributed optimizer, dp=2), exit, resume for 2 more: same losses and
+    gradient norms to the printed precision (weights, optimizer shards, LR schedule, data position, RNG all restored)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    base = ("--num-layers 2 --hidden-size 32 --num-attention-heads 4 --seq-length 32 --max-position-embeddings 32 "
+            "--micro-batch-size 2 --global-batch-size 8 --lr 1e-2 --vocab-size 200 --mock-data --log-interval 1 --eval-iters 1 "
+            "--eval-interval 100 --distributed-backend gloo --no-gradient-accumulation-fusion --lr-decay-iters 100 "
+            "--train-iters 4 --attention-dropout 0 --hidden-dropout 0 --use-distributed-optimizer").split()
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "pretrain_gpt.py"),
+                            *base, *extra], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-3000:]
+        return re.findall(r"\] iteration\s+(\d+)/.*?lm loss: ([0-9.E+\-]+).*?grad norm: ([0-9.]+)", out)
+
+    straight = run()
+    assert [r[0] for r in straight] == ["1", "2", "3", "4"]
+    ck = str(tmp_path / "ck")
+    first = run("--exit-interval", "2", "--save", ck, "--ckpt-format", fmt)
+    assert first == straight[:2]
+    resumed = run("--load", ck, "--ckpt-format", fmt)
+    assert resumed == straight[2:], (resumed, straight)
