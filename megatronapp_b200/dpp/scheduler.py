@@ -323,7 +323,8 @@ def dpp_forward_backward(*, forward_step_func, data_iterator, model, num_microba
     f_done, b_done, stash = set(), set(), {}
     store: List = []
     total_tokens = torch.zeros((), dtype=torch.int, device=next(chunks[0].parameters()).device)
-    limit = interleaved_warmup(pp, rank, M, C, min(pp, M)) + 1
+    # in-flight cap (forwards not yet matched by a backward); evaluation has no backwards to drain it, so no cap
+    limit = (M * C + 1) if forward_only else interleaved_warmup(pp, rank, M, C, min(pp, M)) + 1
     table = schedules.get_schedule_table(M, C, min(pp, M))
     b_count = [0] * C
     tracer = get_tracer()

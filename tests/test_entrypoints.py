@@ -71,18 +71,25 @@ MULTI = {
                      "--pipeline-model-parallel-size", "2"],
     "gpt_moe_ep2": ["pretrain_gpt.py", "--num-experts", "4", "--moe-router-topk", "2", "--expert-model-parallel-size", "2"],
     "gpt_tp2_sp": ["pretrain_gpt.py", "--tensor-model-parallel-size", "2", "--sequence-parallel"],
+    "gpt_dpp_vpp_eval": ["pretrain_gpt.py", "--num-layers", "4", "--pipeline-model-parallel-size", "2",
+                         "--num-layers-per-virtual-pipeline-stage", "1", "--use-dpp", "--eval-interval", "2"],
+    "gpt_fbd": ["pretrain_gpt.py", "--forward-backward-disaggregating"],
+    "gpt_trace_pp2": ["pretrain_gpt.py", "--pipeline-model-parallel-size", "2", "--trace", "--trace-interval", "1",
+                      "--continuous-trace-iterations", "2"],
     "vlm_pp2": ["pretrain_vlm.py", "--img-h", "14", "--img-w", "14", "--patch-dim", "7", "--pipeline-model-parallel-size", "2"],
 }
 
 
 @pytest.mark.parametrize("case", sorted(MULTI))
-def test_pretrain_entrypoint_two_ranks(case):
+def test_pretrain_entrypoint_two_ranks(case, tmp_path):
     """Two gloo ranks through torchrun: only TP rank 0 owns data iterators, so batches must be broadcast and every rank
     must agree on whether to evaluate; the T5 case exercises the encoder/decoder pipeline split."""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     script, *extra = MULTI[case]
+    if "--trace" in extra:
+        extra += ["--trace-dir", str(tmp_path / "trace")]
     common = [("8" if a == "4" and COMMON[i - 1] == "--global-batch-size" else a) for i, a in enumerate(COMMON)]
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, script), *common, *extra],
