@@ -35,7 +35,13 @@ def calculate_correct_answers(model, loader) -> Dict[str, float]:
     model.eval()
     correct = total = 0
     dev = next(model.parameters()).device
-    for batch in loader:
+    from megatronapp_b200.parallel import state as ps
+
+    mp = ps.model_parallel_is_initialized()
+    dp_rank, dp_size = (ps.get_data_parallel_rank(), ps.get_data_parallel_world_size()) if mp else (0, 1)
+    for i, batch in enumerate(loader):
+        if i % dp_size != dp_rank:               # every replica scores its share; the counts are summed below
+            continue
         tokens, types, labels, mask = process_batch(batch, dev)
         pred = model(tokens, mask, tokentype_ids=types).argmax(dim=-1)
         correct += int((pred == labels).sum())
@@ -52,6 +58,30 @@ def calculate_correct_answers(model, loader) -> Dict[str, float]:
             correct, total = int(t[0]), int(t[1])
     model.train(was_training)
     return {"correct": correct, "total": total, "accuracy": correct / max(total, 1)}
+
+
+def clip_grad_norm_model_parallel(params, max_norm: float) -> float:
+    """Global L2 clipping that is consistent across tensor-parallel ranks: sharded parameters contribute their shard,
+    replicated ones are counted once (on TP rank 0), and the squared norm is summed over the model-parallel group."""
+    import torch.distributed as dist
+
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.tp_layers import param_is_not_tensor_parallel_duplicate
+
+    grads = [p.grad for p in params if p.grad is not None and
+             (not ps.model_parallel_is_initialized() or param_is_not_tensor_parallel_duplicate(p))]
+    sq = torch.stack([g.float().pow(2).sum() for g in grads]).sum() if grads else torch.zeros(())
+    if ps.model_parallel_is_initialized() and dist.is_initialized():
+        g = ps.get_model_parallel_group()
+        if g is not None and not isinstance(g, ps._SingleGroup):
+            dist.all_reduce(sq, group=g)
+    norm = float(sq.sqrt())
+    coef = max_norm / (norm + 1e-6)
+    if coef < 1.0:
+        for p in params:
+            if p.grad is not None:
+                p.grad.mul_(coef)
+    return norm
 
 
 def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: int = 16, lr: float = 2e-5,
@@ -90,13 +120,14 @@ def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: i
                         dist.all_reduce(p.grad, group=g)
                         p.grad.div_(dp_size)
             if clip_grad:
-                torch.nn.utils.clip_grad_norm_(params, clip_grad)
+                clip_grad_norm_model_parallel(params, clip_grad)
             opt.step()
             sched.step()
             running += float(loss)
             step += 1
             if log_interval and step % log_interval == 0:
-                print(f" epoch {epoch} step {step}/{total_steps} | loss {running / log_interval:.4f} | lr {sched.get_last_lr()[0]:.3e}", flush=True)
+                if not dist.is_initialized() or dist.get_rank() == 0:
+                    print(f" epoch {epoch} step {step}/{total_steps} | loss {running / log_interval:.4f} | lr {sched.get_last_lr()[0]:.3e}", flush=True)
                 running = 0.0
         metrics = calculate_correct_answers(model, vloader)
         metrics["epoch"] = epoch

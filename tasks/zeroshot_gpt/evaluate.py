@@ -107,41 +107,71 @@ def build_dataset(task: str, path: str, tokenizer, seq_len: int, overlapping_eva
 
 
 # ------------------------------------------------------------------------------ evaluation
+def _pipeline_forward(model, inp, pos, labels):
+    """One forward through all pipeline stages; returns the model output on the last stage and ``None`` elsewhere."""
+    from megatronapp_b200.parallel import p2p, state as ps
+
+    if not ps.model_parallel_is_initialized() or ps.get_pipeline_model_parallel_world_size() == 1:
+        return model(inp, pos, None, labels=labels)
+    inner = model
+    while hasattr(inner, "module"):
+        inner = inner.module
+    cfg = inner.config
+    if not ps.is_pipeline_first_stage():
+        h = p2p.recv((inp.shape[1], inp.shape[0], cfg.hidden_size), cfg.pipeline_dtype or cfg.params_dtype,
+                     ps.get_pipeline_model_parallel_prev_rank(), "fwd", "recv-forward")
+        inner.set_input_tensor(h)
+    out = model(inp, pos, None, labels=labels if ps.is_pipeline_last_stage() else None)
+    if not ps.is_pipeline_last_stage():
+        p2p.send(out, ps.get_pipeline_model_parallel_next_rank(), "fwd", "send-forward")
+        p2p.flush()
+        return None
+    return out
+
+
 @torch.no_grad()
 def evaluate(model, loader, eval_metric: str, device=None) -> float:
     """``loss``: summed token NLL over scored positions; ``accuracy``: number of samples whose every
-    scored position is predicted correctly (LAMBADA)."""
+    scored position is predicted correctly (LAMBADA).  Batches are dealt round-robin to the data-parallel replicas,
+    pipeline stages pass activations along, and every rank returns the global total."""
+    import torch.distributed as dist
+
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.mappings import gather_from_tensor_model_parallel_region
+
     model.eval()
     total = 0.0
     dev = device or next(model.parameters()).device
-    for batch in loader:
+    mp = ps.model_parallel_is_initialized()
+    dp_rank, dp_size = (ps.get_data_parallel_rank(), ps.get_data_parallel_world_size()) if mp else (0, 1)
+    for i, batch in enumerate(loader):
+        if i % dp_size != dp_rank:
+            continue
         toks = batch["text"].to(dev)
         mask = batch["pad_mask"].to(dev)
         inp, labels = toks[:, :-1].contiguous(), toks[:, 1:].contiguous()
         pos = torch.arange(inp.shape[1], device=dev).unsqueeze(0).expand_as(inp)
         if eval_metric == "loss":
-            loss = model(inp, pos, None, labels=labels).float()
-            total += float((loss * mask).sum())
+            loss = _pipeline_forward(model, inp, pos, labels)
+            if loss is not None:
+                total += float((loss.float() * mask).sum())
         else:
-            logits = model(inp, pos, None).float()
-            from megatronapp_b200.parallel import state as ps
-            from megatronapp_b200.parallel.mappings import gather_from_tensor_model_parallel_region
-
-            if ps.get_tensor_model_parallel_world_size() > 1:
+            logits = _pipeline_forward(model, inp, pos, None)
+            if logits is None:
+                continue
+            logits = logits.float()
+            if mp and ps.get_tensor_model_parallel_world_size() > 1:
                 logits = gather_from_tensor_model_parallel_region(logits)
             correct = (logits.argmax(-1) == labels).float()
             correct[mask == 0] = 1.0
             total += float(correct.prod(-1).sum())
-    import torch.distributed as dist
-
-    if dist.is_initialized():
-        from megatronapp_b200.parallel import state as ps
-
-        g = ps.get_data_parallel_group()
-        if g is not None and not isinstance(g, ps._SingleGroup):
-            t = torch.tensor([total], device=dev)
-            dist.all_reduce(t, group=g)
-            total = float(t)
+    if mp and dist.is_initialized():
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        for g in (ps.get_data_parallel_group(), ps.get_pipeline_model_parallel_group()):
+            # DP: partial sums of the replicas; PP: only the last stage counted anything
+            if g is not None and not isinstance(g, ps._SingleGroup):
+                dist.all_reduce(t, group=g)
+        total = float(t)
     return total
 
 
