@@ -67,6 +67,7 @@ class T5Model(LanguageModule):
                  position_embedding_type="learned_absolute", add_encoder=True, add_decoder=True,
                  relative_attention_num_buckets: int = 32, relative_attention_max_distance: int = 128):
         super().__init__(config)
+        self.log_constructor_args(locals())
         # under a pipeline split, ``post_process`` of an encoder-only stage means "apply the encoder's final norm";
         # the LM head (and the tied-embedding bookkeeping of LanguageModule) exists on decoder stages only
         enc_post = post_process

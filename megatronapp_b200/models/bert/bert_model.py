@@ -77,6 +77,7 @@ class BertModel(LanguageModule):
                  share_embeddings_and_output_weights=True, position_embedding_type="learned_absolute",
                  add_binary_head=True, return_embeddings=False):
         super().__init__(config)
+        self.log_constructor_args(locals())
         self.pre_process, self.post_process = pre_process, post_process
         self.add_binary_head, self.return_embeddings = add_binary_head, return_embeddings
         self.share_embeddings_and_output_weights = share_embeddings_and_output_weights

@@ -30,6 +30,7 @@ class GPTModel(LanguageModule):
                  scatter_embedding_sequence_parallel: bool = True,
                  seq_len_interpolation_factor: Optional[float] = None, mtp_block_spec=None):
         super().__init__(config)
+        self.log_constructor_args(locals())
         self.transformer_layer_spec = transformer_layer_spec
         self.vocab_size, self.max_sequence_length = vocab_size, max_sequence_length
         self.pre_process, self.post_process = pre_process, post_process

@@ -54,6 +54,7 @@ class MambaModel(LanguageModule):
                  position_embedding_type="none", rotary_percent=1.0, rotary_base=10000,
                  seq_len_interpolation_factor=None):
         super().__init__(config)
+        self.log_constructor_args(locals())
         self.pre_process, self.post_process = pre_process, post_process
         self.share_embeddings_and_output_weights = share_embeddings_and_output_weights
         self.position_embedding_type = position_embedding_type

@@ -25,7 +25,8 @@ def _add(group, *names, **kw):
 
 
 def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.ArgumentParser:
-    p = argparse.ArgumentParser(description="megatronapp_b200 arguments", allow_abbrev=False)
+    # "resolve": an entry script may re-declare a flag (with its own default) without tripping over the central one
+    p = argparse.ArgumentParser(description="megatronapp_b200 arguments", allow_abbrev=False, conflict_handler="resolve")
     g = p.add_argument_group("network size")
     _add(g, "--num-layers", type=int, default=None)
     _add(g, "--encoder-num-layers", type=int, default=None)
@@ -60,6 +61,15 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--bert-no-binary-head", action="store_false", dest="bert_binary_head")
     _add(g, "--untie-embeddings-and-output-weights", action="store_true")
     _add(g, "--multi-latent-attention", action="store_true")
+    # reference _add_mla_args: low-rank q / kv projections, decoupled rope head, YaRN scale factors
+    _add(g, "--q-lora-rank", type=int, default=None)
+    _add(g, "--kv-lora-rank", type=int, default=32)
+    _add(g, "--qk-head-dim", type=int, default=128)
+    _add(g, "--qk-pos-emb-head-dim", type=int, default=64)
+    _add(g, "--v-head-dim", type=int, default=128)
+    _add(g, "--rotary-scaling-factor", type=float, default=1.0)
+    _add(g, "--mscale", type=float, default=1.0)
+    _add(g, "--mscale-all-dim", type=float, default=1.0)
     _add(g, "--qk-layernorm", action="store_true")
     _add(g, "--disable-bias-linear", action="store_false", dest="add_bias_linear")
     _add(g, "--add-qkv-bias", action="store_true")
@@ -358,6 +368,93 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--embedding-path", type=str, default=None)
     _add(g, "--indexer-batch-size", type=int, default=128)
     _add(g, "--indexer-log-interval", type=int, default=1000)
+    g = p.add_argument_group("reference CLI surface")   # flags of the reference parser that had no home above
+    # -- deprecated / renamed (validate_args maps them) --
+    _add(g, "--checkpoint-activations", action="store_true", help="deprecated: --recompute-granularity full --recompute-method uniform")
+    _add(g, "--warmup", type=int, default=None, help="deprecated: use --lr-warmup-fraction")
+    _add(g, "--inference-max-requests", type=int, default=8, dest="inference_max_requests")
+    # -- model / heterogeneous / vision --
+    _add(g, "--heterogeneous-layers-config-path", type=str, default=None)
+    _add(g, "--heterogeneous-layers-config-encoded-json", type=str, default=None)
+    _add(g, "--relative-attention-num-buckets", type=int, default=32)
+    _add(g, "--relative-attention-max-distance", type=int, default=128)
+    _add(g, "--mrope-section", type=int, nargs="+", default=None)
+    _add(g, "--num-classes", type=int, default=1000)
+    _add(g, "--img-h", type=int, default=224)
+    _add(g, "--img-w", type=int, default=224)
+    _add(g, "--num-channels", type=int, default=3)
+    _add(g, "--patch-dim", type=int, default=16)
+    _add(g, "--classes-fraction", type=float, default=1.0)
+    _add(g, "--data-per-class-fraction", type=float, default=1.0)
+    _add(g, "--no-data-sharding", action="store_false", dest="data_sharding")
+    _add(g, "--head-lr-mult", type=float, default=1.0)
+    _add(g, "--vision-pretraining", action="store_true")
+    _add(g, "--vision-pretraining-type", type=str, default="classify", choices=["classify", "inpaint", "dino"])
+    _add(g, "--vision-backbone-type", type=str, default="vit", choices=["vit", "mit", "swin"])
+    _add(g, "--swin-backbone-type", type=str, default="tiny", choices=["tiny", "base", "h3"])
+    _add(g, "--mask-type", type=str, default="random", choices=["random", "row"])
+    _add(g, "--mask-factor", type=float, default=1.0)
+    _add(g, "--iter-per-epoch", type=int, default=1250)
+    for name, typ, dflt in (("local-img-size", int, 96), ("local-crops-number", int, 10), ("head-hidden-size", int, 2048),
+                            ("bottleneck-size", int, 256), ("freeze-last-layer", float, 1), ("warmup-teacher-temp", float, 0.04),
+                            ("teacher-temp", float, 0.07), ("warmup-teacher-temp-epochs", int, 30)):
+        _add(g, f"--dino-{name}", type=typ, default=dflt)
+    _add(g, "--dino-norm-last-layer", action="store_true")
+    # -- retro --
+    _add(g, "--retro-project-dir", type=str, default=None)
+    _add(g, "--retro-add-retriever", action="store_true")
+    _add(g, "--retro-cyclic-train-iters", type=int, default=None)
+    _add(g, "--retro-encoder-layers", type=int, default=2)
+    _add(g, "--retro-encoder-hidden-dropout", type=float, default=0.1)
+    _add(g, "--retro-encoder-attention-dropout", type=float, default=0.1)
+    # -- optimizer precision / offload --
+    _add(g, "--use-precision-aware-optimizer", action="store_true")
+    _add(g, "--main-grads-dtype", default="fp32", choices=["fp32", "bf16"])
+    _add(g, "--main-params-dtype", default="fp32", choices=["fp32", "fp16"])
+    _add(g, "--exp-avg-dtype", default="fp32", choices=["fp32", "fp16", "bf16", "fp8"])
+    _add(g, "--exp-avg-sq-dtype", default="fp32", choices=["fp32", "fp16", "bf16", "fp8"])
+    _add(g, "--grad-reduce-in-bf16", action="store_true")
+    _add(g, "--optimizer-cpu-offload", action="store_true")
+    _add(g, "--optimizer-offload-fraction", type=float, default=1.0)
+    _add(g, "--use-torch-optimizer-for-cpu-offload", action="store_true")
+    _add(g, "--overlap-cpu-optimizer-d2h-h2d", action="store_true")
+    _add(g, "--no-pin-cpu-grads", action="store_false", dest="pin_cpu_grads")
+    _add(g, "--no-pin-cpu-params", action="store_false", dest="pin_cpu_params")
+    # -- distributed / runtime knobs (several are NCCL- or TE-specific in the reference; accepted, recorded in args) --
+    _add(g, "--pipeline-model-parallel-comm-backend", type=str, default=None, choices=["nccl", "ucc"])
+    _add(g, "--disable-gloo-process-groups", action="store_false", dest="enable_gloo_process_groups")
+    _add(g, "--ddp-pad-buckets-for-high-nccl-busbw", action="store_true")
+    _add(g, "--suggested-communication-unit-size", type=int, default=None)
+    _add(g, "--no-gradient-reduce-div-fusion", action="store_false", dest="gradient_reduce_div_fusion")
+    _add(g, "--no-clone-scatter-output-in-embedding", action="store_false", dest="clone_scatter_output_in_embedding")
+    _add(g, "--disable-bf16-reduced-precision-matmul", action="store_true")
+    _add(g, "--cross-entropy-fusion-impl", type=str, default="native", choices=["native", "te"])
+    _add(g, "--cuda-graph-scope", type=str, default="full", choices=["full", "attn", "full_iteration"])
+    _add(g, "--external-cuda-graph", action="store_true")
+    _add(g, "--te-rng-tracker", action="store_true")
+    _add(g, "--inference-rng-tracker", action="store_true")
+    _add(g, "--init-model-with-meta-device", action="store_true")
+    _add(g, "--keep-fp8-transpose-cache-when-using-custom-fsdp", action="store_true")
+    _add(g, "--train-sync-interval", type=int, default=None)
+    _add(g, "--run-workload-inspector-server", action="store_true")
+    # -- checkpointing extras --
+    _add(g, "--ckpt-convert-update-legacy-dist-opt-format", action="store_true")
+    _add(g, "--use-mp-args-from-checkpoint-args", action="store_true")
+    _add(g, "--no-use-tokenizer-model-from-checkpoint-args", action="store_false", dest="use_tokenizer_model_from_checkpoint_args")
+    _add(g, "--use-persistent-ckpt-worker", action="store_true")
+    _add(g, "--non-persistent-local-ckpt-dir", type=str, default=None)
+    _add(g, "--non-persistent-local-ckpt-algo", type=str, default="fully_parallel", choices=["fully_parallel", "atomic"])
+    _add(g, "--replication-jump", type=int, default=None)
+    _add(g, "--replication-factor", type=int, default=2)
+    _add(g, "--result-rejected-tracker-filename", type=str, default=None)
+    # -- logging --
+    _add(g, "--config-logger-dir", type=str, default="")
+    _add(g, "--no-one-logger", action="store_false", dest="enable_one_logger")
+    _add(g, "--one-logger-project", type=str, default="megatron-lm")
+    _add(g, "--one-logger-run-name", type=str, default=None)
+    _add(g, "--one-logger-async", action="store_true")
+    _add(g, "--app-tag-run-name", type=str, default=None)
+    _add(g, "--app-tag-run-version", type=str, default="0.0.0")
     g = p.add_argument_group("tokenizer")
     _add(g, "--vocab-size", type=int, default=None)
     _add(g, "--padded-vocab-size", type=int, default=None)
@@ -480,6 +577,12 @@ def validate_args(args, defaults=None):
     for k, v in (defaults or {}).items():
         if getattr(args, k, None) is None:
             setattr(args, k, v)
+    if getattr(args, "checkpoint_activations", False):     # deprecated spelling of full uniform recompute
+        args.recompute_granularity = args.recompute_granularity or "full"
+        args.recompute_method = args.recompute_method or "uniform"
+        args.recompute_num_layers = args.recompute_num_layers or 1
+    if getattr(args, "warmup", None) is not None:
+        raise ValueError("--warmup is no longer valid, use --lr-warmup-fraction instead")
     if args.model_parallel_size is not None:
         args.tensor_model_parallel_size = args.model_parallel_size
     if args.batch_size is not None and args.micro_batch_size is None:
@@ -642,7 +745,7 @@ def core_transformer_config_from_args(args, config_class=None) -> TransformerCon
         kw["num_query_groups"] = args.num_query_groups
     else:
         kw["num_query_groups"] = None
-    kw["config_logger_dir"] = ""
+    kw["config_logger_dir"] = getattr(args, "config_logger_dir", "") or ""
     if len(args.cp_comm_type) == 1:
         kw["cp_comm_type"] = args.cp_comm_type[0]
     kw["kernel_backend"] = args.kernel_backend

@@ -48,6 +48,15 @@ class MegatronModule(nn.Module):
     def state_dict_for_save_checkpoint(self, prefix="", keep_vars=False):
         return self.state_dict(prefix=prefix, keep_vars=keep_vars)
 
+    def log_constructor_args(self, ctor_locals: dict):
+        """``--config-logger-dir``: dump the constructor arguments (and through them the full config) of a model
+        to disk, one JSON per rank (reference: ``log_config_to_disk(config, locals(), prefix=type(self).__name__)``)."""
+        from ..utils.config_logger import has_config_logger_enabled, log_config_to_disk
+
+        if has_config_logger_enabled(self.config):
+            data = {k: v for k, v in ctor_locals.items() if k not in ("self", "__class__")}
+            log_config_to_disk(self.config, data, prefix=type(self).__name__)
+
     def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
         from ..ckpt.sharded import make_sharded_tensors_for_checkpoint
 

@@ -31,7 +31,17 @@ def model_provider(pre_process=True, post_process=True):
 
         return LegacyGPTModel(config, num_tokentypes=0, parallel_output=True, pre_process=pre_process,
                               post_process=post_process)
-    if args.num_experts:
+    het = getattr(args, "heterogeneous_layers_config_path", None) or getattr(args, "heterogeneous_layers_config_encoded_json", None)
+    if het:
+        import json
+
+        from megatronapp_b200.models.gpt.heterogeneous.heterogeneous_layer_specs import (
+            get_gpt_heterogeneous_layer_spec, parse_heterogeneous_config)
+
+        cfg = het if args.heterogeneous_layers_config_path else json.loads(het)
+        spec = get_gpt_heterogeneous_layer_spec(config, parse_heterogeneous_config(cfg, config.num_attention_heads,
+                                                                                   config.hidden_size))
+    elif args.num_experts:
         spec = get_gpt_decoder_block_spec(config)
     else:
         spec = get_gpt_layer_local_spec(args.num_experts, args.moe_grouped_gemm, args.qk_layernorm,

@@ -48,6 +48,8 @@ def model_provider(pre_process=True, post_process=True, add_encoder=True, add_de
                    pre_process=pre_process, post_process=post_process, parallel_output=True,
                    share_embeddings_and_output_weights=not args.untie_embeddings_and_output_weights,
                    position_embedding_type=args.position_embedding_type,
+                   relative_attention_num_buckets=args.relative_attention_num_buckets,
+                   relative_attention_max_distance=args.relative_attention_max_distance,
                    add_encoder=add_encoder, add_decoder=add_decoder)
 
 

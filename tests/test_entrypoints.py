@@ -22,6 +22,12 @@ CASES = {
                             "--num-query-groups", "2", "--normalization", "RMSNorm", "--disable-bias-linear",
                             "--untie-embeddings-and-output-weights"],
     "gpt_moe": ["pretrain_gpt.py", "--num-experts", "4", "--moe-router-topk", "2", "--moe-aux-loss-coeff", "0.01"],
+    "gpt_mla_mtp": ["pretrain_gpt.py", "--multi-latent-attention", "--q-lora-rank", "16", "--kv-lora-rank", "16", "--qk-head-dim", "8",
+                    "--qk-pos-emb-head-dim", "8", "--v-head-dim", "8", "--position-embedding-type", "rope", "--mtp-num-layers", "1"],
+    "gpt_mxfp8_recompute": ["pretrain_gpt.py", "--fp8-format", "hybrid", "--fp8-recipe", "mxfp8", "--checkpoint-activations"],
+    "gpt_heterogeneous": ["pretrain_gpt.py", "--heterogeneous-layers-config-encoded-json",
+                          '{"block_configs": [{"attention": {"n_heads_in_group": 2}, "ffn": {"ffn_mult": 1.5}}, '
+                          '{"attention": {"no_op": true}, "ffn": {"intermediate_size": 48}}]}'],
     "bert": ["pretrain_bert.py"],
     "bert_legacy": ["pretrain_bert.py", "--use-legacy-models"],
     "t5": ["pretrain_t5.py", "--encoder-seq-length", "32", "--decoder-seq-length", "16"],
