@@ -136,7 +136,7 @@ class _Range:
 class _BufferState:
     """Optimizer state for one ParamAndGradBuffer (full, or this rank's shards under ZeRO-1)."""
 
-    def __init__(self, buf: ParamAndGradBuffer, ranges: List[_Range], sharded: bool):
+    def __init__(self, buf: ParamAndGradBuffer, ranges: List[_Range], sharded: bool, offload_fraction: float = 0.0):
         self.buf, self.sharded = buf, sharded
         dev = buf.param_data.device
         if sharded:
@@ -154,13 +154,41 @@ class _BufferState:
             self.master[o:o + e - s].copy_(buf.param_data[s:e])
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
+        # --optimizer-cpu-offload: the tail [cpu_from, local_numel) of master / moments lives in (pinned) host memory and
+        # is stepped on the CPU (reference optimizer/cpu_offloading/hybrid_optimizer.py: HybridDeviceOptimizer)
+        self.cpu_from = off
+        self.master_cpu = self.exp_avg_cpu = self.exp_avg_sq_cpu = None
+        if offload_fraction > 0.0 and off > 0:
+            keep = int(off * (1.0 - min(1.0, offload_fraction))) // 128 * 128
+            pin = dev.type == "cuda"
+            host = lambda t: (t.cpu().pin_memory() if pin else t.cpu().clone())  # noqa: E731
+            self.master_cpu = host(self.master[keep:])
+            self.exp_avg_cpu, self.exp_avg_sq_cpu = host(self.exp_avg[keep:]), host(self.exp_avg_sq[keep:])
+            self.master, self.exp_avg, self.exp_avg_sq = (t[:keep].clone() for t in (self.master, self.exp_avg, self.exp_avg_sq))
+            self.cpu_from = keep
         # intersect (wd, lr) ranges with owned segments -> launch list of (buf_start, buf_end, local_off, wd, lr)
         self.launches: List[Tuple[int, int, int, float, float]] = []
         for (s, e), o in zip(self.segments, self.seg_offsets):
             for r in ranges:
                 a, b = max(s, r.start), min(e, r.end)
                 if a < b:
-                    self.launches.append((a, b, o + (a - s), r.wd_mult, r.lr_mult))
+                    lo = o + (a - s)
+                    cut = min(max(self.cpu_from - lo, 0), b - a)        # elements of this launch that stay on the device
+                    if cut > 0:
+                        self.launches.append((a, a + cut, lo, r.wd_mult, r.lr_mult))
+                    if cut < b - a:
+                        self.launches.append((a + cut, b, lo + cut, r.wd_mult, r.lr_mult))
+
+    def full(self, name: str) -> torch.Tensor:
+        """Device part + offloaded part of ``master`` / ``exp_avg`` / ``exp_avg_sq`` as one CPU-or-device tensor."""
+        dev_part, cpu_part = getattr(self, name), getattr(self, name + "_cpu")
+        return dev_part if cpu_part is None else torch.cat([dev_part.cpu(), cpu_part])
+
+    def load_full(self, name: str, value: torch.Tensor):
+        dev_part, cpu_part = getattr(self, name), getattr(self, name + "_cpu")
+        dev_part.copy_(value[: dev_part.numel()])
+        if cpu_part is not None:
+            cpu_part.copy_(value[dev_part.numel():])
 
 
 class MegatronOptimizer:
@@ -202,7 +230,8 @@ class MegatronOptimizer:
                         merged[-1].end = r.end  # swallow alignment padding in between
                     else:
                         merged.append(_Range(r.start, r.end, r.wd_mult, r.lr_mult))
-                self.states.append(_BufferState(buf, merged, self.sharded and _is_real_group(buf.group)))
+                self.states.append(_BufferState(buf, merged, self.sharded and _is_real_group(buf.group),
+                                                config.optimizer_offload_fraction if config.optimizer_cpu_offload else 0.0))
         if config.fp16:
             if config.loss_scale:
                 self.grad_scaler = ConstantGradScaler(config.loss_scale)
@@ -322,6 +351,13 @@ class MegatronOptimizer:
                 grad = buf.grad_data[a:b]
                 if grad.dtype != torch.float32:
                     grad = grad.float()
+                if lo >= st.cpu_from:                      # offloaded slice: D2H grad, CPU Adam, H2D parameter
+                    c = lo - st.cpu_from
+                    ops.adam_step(st.master_cpu[c:c + n], st.exp_avg_cpu[c:c + n], st.exp_avg_sq_cpu[c:c + n],
+                                  grad.to("cpu", non_blocking=False), None, lr, cfg.adam_beta1, cfg.adam_beta2,
+                                  cfg.adam_eps, wd, gs, self.step_count)
+                    buf.param_data[a:b].copy_(st.master_cpu[c:c + n], non_blocking=True)
+                    continue
                 p16 = buf.param_data[a:b] if buf.param_dtype != torch.float32 else None
                 ops.adam_step(st.master[lo:lo + n], st.exp_avg[lo:lo + n], st.exp_avg_sq[lo:lo + n], grad, p16,
                               lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, wd, gs, self.step_count)
@@ -344,13 +380,15 @@ class MegatronOptimizer:
     # -- (de)serialisation ----------------------------------------------------------------
     def reload_model_params(self):
         for st in self.states:
+            full = torch.empty(st.local_numel, dtype=torch.float32, device=st.buf.param_data.device)
             for (s, e), o in zip(st.segments, st.seg_offsets):
-                st.master[o:o + e - s].copy_(st.buf.param_data[s:e])
+                full[o:o + e - s].copy_(st.buf.param_data[s:e])
+            st.load_full("master", full)
 
     def state_dict(self):
         sd = {"step": self.step_count,
               "param_groups": [{k: v for k, v in g.items()} for g in self.param_groups],
-              "buffers": [{"master": st.master, "exp_avg": st.exp_avg, "exp_avg_sq": st.exp_avg_sq,
+              "buffers": [{"master": st.full("master"), "exp_avg": st.full("exp_avg"), "exp_avg_sq": st.full("exp_avg_sq"),
                            "segments": st.segments} for st in self.states]}
         if self.grad_scaler is not None:
             sd["grad_scaler"] = self.grad_scaler.state_dict()
@@ -361,9 +399,9 @@ class MegatronOptimizer:
         for g, sg in zip(self.param_groups, sd.get("param_groups", [])):
             g.update({k: v for k, v in sg.items() if k in ("lr", "weight_decay")})
         for st, s in zip(self.states, sd["buffers"]):
-            st.master.copy_(s["master"])
-            st.exp_avg.copy_(s["exp_avg"])
-            st.exp_avg_sq.copy_(s["exp_avg_sq"])
+            st.load_full("master", s["master"])
+            st.load_full("exp_avg", s["exp_avg"])
+            st.load_full("exp_avg_sq", s["exp_avg_sq"])
         if self.grad_scaler is not None and "grad_scaler" in sd:
             self.grad_scaler.load_state_dict(sd["grad_scaler"])
 

@@ -175,3 +175,26 @@ def test_checkpoint_resume_is_exact(tmp_path, fmt):
     assert first == straight[:2]
     resumed = run("--load", ck, "--ckpt-format", fmt)
     assert resumed == straight[2:], (resumed, straight)
+
+
+def test_optimizer_cpu_offload_matches_device_optimizer(tmp_path):
+    """--optimizer-cpu-offload keeps 60 % of the master weights / Adam moments in host memory and steps them there:
+    same losses and gradient norms as the all-device optimizer, before and after a checkpoint round trip."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="",
+               OMP_NUM_THREADS="2")
+    base = COMMON + ["--train-iters", "4", "--attention-dropout", "0", "--hidden-dropout", "0",
+                                                     "--lr", "1e-2", "--lr-decay-iters", "100"]
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *base, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-3000:]
+        return re.findall(r"\] iteration\s+(\d+)/.*?lm loss: ([0-9.E+\-]+).*?grad norm: ([0-9.]+)", out)
+
+    ref = run()
+    off = ["--optimizer-cpu-offload", "--optimizer-offload-fraction", "0.6"]
+    assert run(*off) == ref and len(ref) == 4
+    ck = str(tmp_path / "ck")
+    assert run(*off, "--exit-interval", "2", "--save", ck) == ref[:2]
+    assert run(*off, "--load", ck) == ref[2:]
