@@ -573,7 +573,26 @@ def _vocab_size_with_padding(orig: int, args) -> int:
     return (orig + mult - 1) // mult * mult
 
 
+_UNSUPPORTED = (
+    # (predicate on args, message) -- flags that are parsed for CLI compatibility but would silently change nothing
+    (lambda a: a.use_precision_aware_optimizer and any(getattr(a, k) != "fp32" for k in
+                                                       ("main_grads_dtype", "main_params_dtype", "exp_avg_dtype", "exp_avg_sq_dtype")),
+     "--use-precision-aware-optimizer with non-fp32 state dtypes is not implemented (the fused Adam kernel keeps fp32 state)"),
+    (lambda a: a.init_model_with_meta_device, "--init-model-with-meta-device is not implemented"),
+    (lambda a: a.external_cuda_graph, "--external-cuda-graph is not implemented; use --enable-cuda-graph"),
+    (lambda a: a.pipeline_model_parallel_comm_backend == "ucc", "the UCC pipeline backend is not available; p2p runs on NCCL/gloo channels"),
+    (lambda a: a.non_persistent_local_ckpt_dir is not None, "local non-persistent checkpoints are not implemented"),
+    (lambda a: a.vision_backbone_type != "vit", "only the ViT vision backbone is implemented (no MiT / Swin)"),
+    (lambda a: a.vision_pretraining_type != "classify", "only classification vision pre-training is implemented (no inpainting / DINO)"),
+    (lambda a: a.optimizer_cpu_offload and not (0.0 < a.optimizer_offload_fraction <= 1.0),
+     "--optimizer-offload-fraction must lie in (0, 1]"),
+)
+
+
 def validate_args(args, defaults=None):
+    for bad, msg in _UNSUPPORTED:
+        if bad(args):
+            raise NotImplementedError(msg)
     for k, v in (defaults or {}).items():
         if getattr(args, k, None) is None:
             setattr(args, k, v)
