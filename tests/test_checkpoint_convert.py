@@ -230,3 +230,68 @@ def test_post_training_quantization(name, tol):
         s = real[f"{k}.weights_scaling_factor"]
         assert torch.allclose(real[f"{k}.weight"].float() * s.unsqueeze(1), w, atol=1e-5)
         assert f"{k}.prequant_scaling_factor" in real and f"{k}.activation_scaling_factor" in real
+
+
+def test_hf_mixtral_to_core_logit_parity_and_expert_parallel_layout(tmp_path):
+    """HF Mixtral -> core: logits match transformers; the per-rank files of an expert-parallel layout hold each rank's
+    experts under local indices, merge back losslessly, and core -> HF restores the original tensors."""
+    import json
+
+    from transformers import MixtralConfig, MixtralForCausalLM
+
+    from megatronapp_b200.config import TransformerConfig
+    from megatronapp_b200.models.gpt import GPTModel
+    from megatronapp_b200.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+
+    torch.manual_seed(0)
+    hcfg = MixtralConfig(vocab_size=256, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=64, rms_norm_eps=1e-5, num_local_experts=4,
+                         num_experts_per_tok=2, tie_word_embeddings=False, attn_implementation="eager",
+                         router_jitter_noise=0.0, sliding_window=None)
+    hf = MixtralForCausalLM(hcfg).float().eval()
+    d = str(tmp_path / "hf")
+    os.makedirs(d)
+    torch.save(hf.state_dict(), os.path.join(d, "pytorch_model.bin"))
+    json.dump(hcfg.to_dict(), open(os.path.join(d, "config.json"), "w"))
+    ck = conv.load_hf_mixtral(d)
+    cfg = ck["config"]
+    assert cfg["num_experts"] == 4 and "decoder.layers.1.mlp.experts.local_experts.3.linear_fc2.weight" in ck["weights"]
+
+    if not ps.model_parallel_is_initialized():
+        ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    tc = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=4, num_query_groups=2, ffn_hidden_size=96,
+                           moe_ffn_hidden_size=96, num_moe_experts=4, moe_router_topk=2, gated_linear_unit=True,
+                           normalization="RMSNorm", add_bias_linear=False, layernorm_epsilon=1e-5, kernel_backend="torch",
+                           use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0,
+                           activation_func=torch.nn.functional.silu, moe_token_dispatcher_type="allgather",
+                           moe_router_pre_softmax=False)
+    m = GPTModel(tc, get_gpt_layer_local_spec(4, False), 256, 64, position_embedding_type="rope", rotary_base=cfg["rotary_base"],
+                 share_embeddings_and_output_weights=False).float().eval()
+    missing = m.load_state_dict(ck["weights"], strict=False)
+    assert not [k for k in missing.missing_keys if "_extra_state" not in k], missing
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    toks = torch.randint(0, 256, (2, 16))
+    pos = torch.arange(16).unsqueeze(0).expand(2, -1)
+    with torch.no_grad():
+        ours, ref = m(toks, pos, None), hf(toks).logits
+    assert torch.allclose(ours, ref, atol=3e-4, rtol=1e-3), float((ours - ref).abs().max())
+
+    ep_dir = str(tmp_path / "ep2")
+    conv.save_core(ck, ep_dir, tp=1, pp=1, ep=2)
+    r1 = torch.load(os.path.join(ep_dir, "release", "mp_rank_00_001", "model_optim_rng.pt"), weights_only=False)["model"]
+    assert torch.equal(r1["decoder.layers.0.mlp.experts.local_experts.0.linear_fc1.weight"],
+                       ck["weights"]["decoder.layers.0.mlp.experts.local_experts.2.linear_fc1.weight"])
+    assert "decoder.layers.0.mlp.experts.local_experts.2.linear_fc1.weight" not in r1 and "decoder.layers.0.mlp.router.weight" in r1
+    merged = conv.load_core(ep_dir)
+    assert merged["weights"].keys() == ck["weights"].keys()
+    assert all(torch.equal(merged["weights"][k], v) for k, v in ck["weights"].items())
+    out = str(tmp_path / "hf_out")
+    conv.save_hf_mixtral(merged, out)                              # written in the hub layout (block_sparse_moe ... w1/w2/w3)
+    back = torch.load(os.path.join(out, "pytorch_model.bin"))
+    assert "model.layers.1.block_sparse_moe.experts.3.w2.weight" in back
+    again = conv.load_hf_mixtral(out)
+    assert all(torch.equal(again["weights"][k], v) for k, v in ck["weights"].items())
+    assert json.load(open(os.path.join(out, "config.json")))["num_local_experts"] == 4

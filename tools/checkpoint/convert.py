@@ -66,6 +66,7 @@ def merge_tp(name: str, shards, glu: bool):
 
 
 _LAYER = re.compile(r"^(.*decoder\.layers\.)(\d+)(\..*)$")
+_EXPERT = re.compile(r"^(.*\.experts\.local_experts\.)(\d+)(\..*)$")
 
 
 def layers_per_stage(num_layers: int, pp: int):
@@ -83,20 +84,35 @@ def load_core(load_dir: str, iteration=None) -> Dict:
         iteration = 0 if txt == "release" else int(txt)
     base = ck.get_checkpoint_name(load_dir, iteration, release=(iteration == 0), return_base_dir=True)
     dirs = sorted(d for d in os.listdir(base) if d.startswith("mp_rank_"))
+    first = torch.load(os.path.join(base, dirs[0], "model_optim_rng.pt"), map_location="cpu", weights_only=False)
+    a0 = first.get("args")
+    ep = int(getattr(a0, "expert_model_parallel_size", 1) or 1)
     tp = 1 + max(int(d.split("_")[2]) for d in dirs)
-    pp = 1 + max((int(d.split("_")[3]) for d in dirs if len(d.split("_")) > 3), default=0)
+    n_extra = max(len(d.split("_")) - 3 for d in dirs)            # trailing fields: [pp rank][ep rank]
+    has_pp = n_extra == 2 or (n_extra == 1 and ep == 1)
+    pp = 1 + max((int(d.split("_")[3]) for d in dirs), default=0) if has_pp else 1
     shards = {}
     args = None
     for d in dirs:
         parts = d.split("_")
-        t, p = int(parts[2]), (int(parts[3]) if len(parts) > 3 else 0)
-        sd = torch.load(os.path.join(base, d, "model_optim_rng.pt"), map_location="cpu", weights_only=False)
+        t = int(parts[2])
+        p = int(parts[3]) if has_pp else 0
+        e = int(parts[-1]) if ep > 1 else 0
+        sd = first if d == dirs[0] else torch.load(os.path.join(base, d, "model_optim_rng.pt"), map_location="cpu", weights_only=False)
         model_sd = sd["model"]
         if isinstance(model_sd.get("language_model"), dict):       # legacy (pre-mcore) nested naming
             from megatronapp_b200.legacy.state_dict import legacy_to_core
 
             model_sd = legacy_to_core(model_sd)
-        shards[(t, p)] = model_sd
+        n_local = 1 + max((int(m.group(2)) for m in map(_EXPERT.match, model_sd) if m), default=-1)
+        glob = {}
+        for k, v in model_sd.items():                              # local expert index -> global
+            m = _EXPERT.match(k)
+            glob[f"{m.group(1)}{int(m.group(2)) + e * n_local}{m.group(3)}" if m else k] = v
+        if e == 0:
+            shards[(t, p)] = glob
+        else:
+            shards[(t, p)].update({k: v for k, v in glob.items() if _EXPERT.match(k)})
         args = args or sd.get("args")
     cfg = _config_from_args(args)
     glu = cfg["gated_linear_unit"]
@@ -124,10 +140,12 @@ def _config_from_args(args) -> Dict:
             "add_bias_linear": not g("disable_bias_linear", False), "padded_vocab_size": g("padded_vocab_size"),
             "max_position_embeddings": g("max_position_embeddings"), "position_embedding_type": g("position_embedding_type", "learned_absolute"),
             "untie_embeddings_and_output_weights": bool(g("untie_embeddings_and_output_weights", False)),
-            "rotary_base": g("rotary_base", 10000), "layernorm_epsilon": g("norm_epsilon", g("layernorm_epsilon", 1e-5))}
+            "rotary_base": g("rotary_base", 10000), "layernorm_epsilon": g("norm_epsilon", g("layernorm_epsilon", 1e-5)),
+            "num_experts": g("num_experts"), "moe_router_topk": g("moe_router_topk", 2),
+            "moe_ffn_hidden_size": g("moe_ffn_hidden_size") or g("ffn_hidden_size")}
 
 
-def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int, legacy: bool = False):
+def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int, legacy: bool = False, ep: int = 1):
     from megatronapp_b200.training import checkpointing as ck
 
     cfg, weights = ckpt["config"], ckpt["weights"]
@@ -136,7 +154,10 @@ def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int, legacy: bool = False)
     it = ckpt.get("iteration", 0)
     args = ckpt.get("args") or SimpleNamespace()
     args = SimpleNamespace(**{**vars(args), **_args_from_config(cfg), "tensor_model_parallel_size": tp,
-                              "pipeline_model_parallel_size": pp})
+                              "pipeline_model_parallel_size": pp, "expert_model_parallel_size": ep})
+    n_exp = cfg.get("num_experts") or 0
+    assert ep == 1 or (n_exp and n_exp % ep == 0), f"{n_exp} experts do not divide over expert-parallel size {ep}"
+    n_local = n_exp // ep if n_exp else 0
     vocab = weights["embedding.word_embeddings.weight"].shape[0]
     assert vocab % tp == 0, f"vocab {vocab} must divide by target TP {tp} (re-pad first)"
     for p in range(pp):
@@ -157,11 +178,19 @@ def save_core(ckpt: Dict, save_dir: str, tp: int, pp: int, legacy: bool = False)
                     continue
                 lname = name
             stage[lname] = split_tp(name, w, tp, glu)
-        for t in range(tp):
+        for t, e in ((t, e) for t in range(tp) for e in range(ep)):
             path = ck.get_checkpoint_name(save_dir, it, release=(it == 0), pipeline_parallel=pp > 1, tensor_rank=t,
-                                          pipeline_rank=p, expert_parallel=False, expert_rank=0)
+                                          pipeline_rank=p, expert_parallel=ep > 1, expert_rank=e)
             os.makedirs(os.path.dirname(path), exist_ok=True)
-            model_sd = {k: v[t] for k, v in stage.items()}
+            model_sd = {}
+            for k, v in stage.items():                   # dense tensors on every EP rank, experts on their owner only
+                m = _EXPERT.match(k)
+                if m is None:
+                    model_sd[k] = v[t]
+                elif ep == 1:
+                    model_sd[k] = v[t]
+                elif int(m.group(2)) // n_local == e:
+                    model_sd[f"{m.group(1)}{int(m.group(2)) - e * n_local}{m.group(3)}"] = v[t]
             if legacy:
                 from megatronapp_b200.legacy.state_dict import core_to_legacy
 
@@ -180,7 +209,9 @@ def _args_from_config(cfg):
             "padded_vocab_size": cfg["padded_vocab_size"], "max_position_embeddings": cfg["max_position_embeddings"],
             "position_embedding_type": cfg["position_embedding_type"],
             "untie_embeddings_and_output_weights": cfg["untie_embeddings_and_output_weights"],
-            "rotary_base": cfg["rotary_base"], "norm_epsilon": cfg["layernorm_epsilon"]}
+            "rotary_base": cfg["rotary_base"], "norm_epsilon": cfg["layernorm_epsilon"],
+            "num_experts": cfg.get("num_experts"), "moe_router_topk": cfg.get("moe_router_topk", 2),
+            "moe_ffn_hidden_size": cfg.get("moe_ffn_hidden_size")}
 
 
 # ------------------------------------------------------------------------------------ HF: Llama
@@ -214,7 +245,8 @@ def qkv_to_separate(w, nh, ng, hn):
     return q.reshape(nh * hn, -1), k.reshape(ng * hn, -1), v.reshape(ng * hn, -1)
 
 
-def load_hf_llama(load_dir: str) -> Dict:
+def _hf_llama_trunk(load_dir: str):
+    """Everything Llama / Mistral / Mixtral share: embeddings, norms, attention.  Returns (hf config, hf state, weights, cfg)."""
     hc = json.load(open(os.path.join(load_dir, "config.json")))
     sd = _hf_state(load_dir)
     nh, ng = hc["num_attention_heads"], hc.get("num_key_value_heads", hc["num_attention_heads"])
@@ -232,18 +264,50 @@ def load_hf_llama(load_dir: str) -> Dict:
             sd[a + "self_attn.q_proj.weight"], sd[a + "self_attn.k_proj.weight"], sd[a + "self_attn.v_proj.weight"], nh, ng, hn)
         w[b + "self_attention.linear_proj.weight"] = sd[a + "self_attn.o_proj.weight"]
         w[b + "pre_mlp_layernorm.weight"] = sd[a + "post_attention_layernorm.weight"]
-        w[b + "mlp.linear_fc1.weight"] = torch.cat([sd[a + "mlp.gate_proj.weight"], sd[a + "mlp.up_proj.weight"]], dim=0)
-        w[b + "mlp.linear_fc2.weight"] = sd[a + "mlp.down_proj.weight"]
     cfg = {"num_layers": L, "hidden_size": h, "num_attention_heads": nh, "num_query_groups": ng,
            "ffn_hidden_size": hc["intermediate_size"], "kv_channels": hn, "gated_linear_unit": True,
            "normalization": "RMSNorm", "add_bias_linear": False, "padded_vocab_size": hc["vocab_size"],
            "max_position_embeddings": hc.get("max_position_embeddings", 4096), "position_embedding_type": "rope",
-           "untie_embeddings_and_output_weights": not tied, "rotary_base": hc.get("rope_theta", 10000.0),
+           "untie_embeddings_and_output_weights": not tied, "rotary_base": hc.get("rope_theta") or (hc.get("rope_parameters") or {}).get("rope_theta", 10000.0),
            "layernorm_epsilon": hc.get("rms_norm_eps", 1e-5)}
+    return hc, sd, w, cfg
+
+
+def load_hf_llama(load_dir: str) -> Dict:
+    hc, sd, w, cfg = _hf_llama_trunk(load_dir)
+    for i in range(cfg["num_layers"]):
+        a, b = f"model.layers.{i}.", f"decoder.layers.{i}."
+        w[b + "mlp.linear_fc1.weight"] = torch.cat([sd[a + "mlp.gate_proj.weight"], sd[a + "mlp.up_proj.weight"]], dim=0)
+        w[b + "mlp.linear_fc2.weight"] = sd[a + "mlp.down_proj.weight"]
     return {"config": cfg, "weights": w, "iteration": 0}
 
 
-def save_hf_llama(ckpt: Dict, save_dir: str):
+def load_hf_mixtral(load_dir: str) -> Dict:
+    """HF Mixtral (reference ``loader_mixtral_hf.py``): the Llama trunk + ``block_sparse_moe`` (router ``gate``; per
+    expert ``w1`` = gate projection, ``w3`` = up projection, ``w2`` = down projection)."""
+    hc, sd, w, cfg = _hf_llama_trunk(load_dir)
+    E = hc["num_local_experts"]
+    fused = "model.layers.0.mlp.experts.gate_up_proj" in sd      # transformers >= 5 in-memory layout (stacked experts)
+    for i in range(cfg["num_layers"]):
+        b = f"decoder.layers.{i}.mlp."
+        if fused:
+            a = f"model.layers.{i}.mlp."
+            w[b + "router.weight"] = sd[a + "gate.weight"]
+            for e in range(E):
+                w[f"{b}experts.local_experts.{e}.linear_fc1.weight"] = sd[a + "experts.gate_up_proj"][e]     # [gate ; up]
+                w[f"{b}experts.local_experts.{e}.linear_fc2.weight"] = sd[a + "experts.down_proj"][e]
+            continue
+        a = f"model.layers.{i}.block_sparse_moe."                # hub checkpoint layout
+        w[b + "router.weight"] = sd[a + "gate.weight"]
+        for e in range(E):
+            w[f"{b}experts.local_experts.{e}.linear_fc1.weight"] = torch.cat([sd[f"{a}experts.{e}.w1.weight"],
+                                                                             sd[f"{a}experts.{e}.w3.weight"]], dim=0)
+            w[f"{b}experts.local_experts.{e}.linear_fc2.weight"] = sd[f"{a}experts.{e}.w2.weight"]
+    cfg.update(num_experts=E, moe_router_topk=hc.get("num_experts_per_tok", 2), moe_ffn_hidden_size=hc["intermediate_size"])
+    return {"config": cfg, "weights": w, "iteration": 0}
+
+
+def _hf_llama_trunk_out(ckpt: Dict):
     cfg, w = ckpt["config"], ckpt["weights"]
     nh, ng, hn = cfg["num_attention_heads"], cfg["num_query_groups"], cfg["kv_channels"]
     sd = {"model.embed_tokens.weight": w["embedding.word_embeddings.weight"], "model.norm.weight": w["decoder.final_layernorm.weight"]}
@@ -256,17 +320,46 @@ def save_hf_llama(ckpt: Dict, save_dir: str):
         sd[a + "self_attn.o_proj.weight"] = w[b + "self_attention.linear_proj.weight"]
         sd[a + "input_layernorm.weight"] = w[b + "input_layernorm.weight"]
         sd[a + "post_attention_layernorm.weight"] = w[b + "pre_mlp_layernorm.weight"]
+    hc = {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": cfg["hidden_size"],
+          "num_hidden_layers": cfg["num_layers"], "num_attention_heads": nh, "num_key_value_heads": ng,
+          "intermediate_size": cfg["ffn_hidden_size"], "vocab_size": cfg["padded_vocab_size"], "head_dim": hn,
+          "max_position_embeddings": cfg["max_position_embeddings"], "rope_theta": cfg["rotary_base"],
+          "rms_norm_eps": cfg["layernorm_epsilon"], "tie_word_embeddings": "output_layer.weight" not in w,
+          "hidden_act": "silu", "torch_dtype": "bfloat16"}
+    return sd, hc
+
+
+def _write_hf(sd: Dict, hc: Dict, save_dir: str):
+    os.makedirs(save_dir, exist_ok=True)
+    torch.save({k: v.contiguous() for k, v in sd.items()}, os.path.join(save_dir, "pytorch_model.bin"))
+    json.dump(hc, open(os.path.join(save_dir, "config.json"), "w"), indent=1)
+
+
+def save_hf_llama(ckpt: Dict, save_dir: str):
+    sd, hc = _hf_llama_trunk_out(ckpt)
+    w = ckpt["weights"]
+    for i in range(ckpt["config"]["num_layers"]):
+        a, b = f"model.layers.{i}.", f"decoder.layers.{i}."
         gate, up = torch.chunk(w[b + "mlp.linear_fc1.weight"], 2, dim=0)
         sd[a + "mlp.gate_proj.weight"], sd[a + "mlp.up_proj.weight"] = gate, up
         sd[a + "mlp.down_proj.weight"] = w[b + "mlp.linear_fc2.weight"]
-    os.makedirs(save_dir, exist_ok=True)
-    torch.save({k: v.contiguous() for k, v in sd.items()}, os.path.join(save_dir, "pytorch_model.bin"))
-    json.dump({"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": cfg["hidden_size"],
-               "num_hidden_layers": cfg["num_layers"], "num_attention_heads": nh, "num_key_value_heads": ng,
-               "intermediate_size": cfg["ffn_hidden_size"], "vocab_size": cfg["padded_vocab_size"], "head_dim": hn,
-               "max_position_embeddings": cfg["max_position_embeddings"], "rope_theta": cfg["rotary_base"],
-               "rms_norm_eps": cfg["layernorm_epsilon"], "tie_word_embeddings": "output_layer.weight" not in w,
-               "hidden_act": "silu", "torch_dtype": "bfloat16"}, open(os.path.join(save_dir, "config.json"), "w"), indent=1)
+    _write_hf(sd, hc, save_dir)
+
+
+def save_hf_mixtral(ckpt: Dict, save_dir: str):
+    sd, hc = _hf_llama_trunk_out(ckpt)
+    cfg, w = ckpt["config"], ckpt["weights"]
+    E = cfg["num_experts"]
+    for i in range(cfg["num_layers"]):
+        a, b = f"model.layers.{i}.block_sparse_moe.", f"decoder.layers.{i}.mlp."
+        sd[a + "gate.weight"] = w[b + "router.weight"]
+        for e in range(E):
+            g, u = torch.chunk(w[f"{b}experts.local_experts.{e}.linear_fc1.weight"], 2, dim=0)
+            sd[f"{a}experts.{e}.w1.weight"], sd[f"{a}experts.{e}.w3.weight"] = g, u
+            sd[f"{a}experts.{e}.w2.weight"] = w[f"{b}experts.local_experts.{e}.linear_fc2.weight"]
+    hc.update({"architectures": ["MixtralForCausalLM"], "model_type": "mixtral", "num_local_experts": E,
+               "num_experts_per_tok": cfg.get("moe_router_topk", 2), "intermediate_size": cfg["moe_ffn_hidden_size"]})
+    _write_hf(sd, hc, save_dir)
 
 
 # ------------------------------------------------------------------------------------ HF: GPT-2
@@ -312,18 +405,19 @@ def pad_vocab(ckpt: Dict, multiple: int):
                 ckpt["config"]["padded_vocab_size"] = v
 
 
-LOADERS = {"core": load_core, "legacy": load_core, "hf_llama": load_hf_llama, "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2}
+LOADERS = {"core": load_core, "legacy": load_core, "hf_mixtral": load_hf_mixtral, "hf_llama": load_hf_llama, "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2}
 
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description="checkpoint converter")
     ap.add_argument("--model-type", default="GPT", choices=["GPT"])
     ap.add_argument("--loader", default="core", choices=list(LOADERS))
-    ap.add_argument("--saver", default="core", choices=["core", "legacy", "hf_llama"])
+    ap.add_argument("--saver", default="core", choices=["core", "legacy", "hf_llama", "hf_mixtral"])
     ap.add_argument("--load-dir", required=True)
     ap.add_argument("--save-dir", required=True)
     ap.add_argument("--target-tensor-parallel-size", type=int, default=1)
     ap.add_argument("--target-pipeline-parallel-size", type=int, default=1)
+    ap.add_argument("--target-expert-parallel-size", type=int, default=1)
     ap.add_argument("--make-vocab-size-divisible-by", type=int, default=128)
     ap.add_argument("--dtype", default=None, choices=[None, "bf16", "fp16", "fp32"])
     a = ap.parse_args(argv)
@@ -334,7 +428,9 @@ def main(argv=None):
     if a.saver in ("core", "legacy"):
         pad_vocab(ckpt, a.make_vocab_size_divisible_by * a.target_tensor_parallel_size)
         save_core(ckpt, a.save_dir, a.target_tensor_parallel_size, a.target_pipeline_parallel_size,
-                  legacy=a.saver == "legacy")
+                  legacy=a.saver == "legacy", ep=a.target_expert_parallel_size)
+    elif a.saver == "hf_mixtral":
+        save_hf_mixtral(ckpt, a.save_dir)
     else:
         save_hf_llama(ckpt, a.save_dir)
     print(f"converted {a.loader} -> {a.saver}: {len(ckpt['weights'])} tensors, "
