@@ -125,9 +125,12 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
         dp_rank = ps.get_data_parallel_rank(with_context_parallel=True)
         name = get_checkpoint_name(args.save, iteration)
         sharded_opt = optimizer is not None and getattr(optimizer, "sharded", False)
-        if dp_rank == 0 or sharded_opt or args.forward_backward_disaggregating:
+        # one writer per (tp, pp, ep) coordinate: with expert parallelism the experts differ across the dense DP group,
+        # so the writer is the rank with EXPERT-data-parallel rank 0 (reference checkpointing.py: same condition)
+        writer = (ps.get_expert_data_parallel_rank() == 0) if ps.get_expert_model_parallel_world_size() > 1 else dp_rank == 0
+        if writer or sharded_opt or args.forward_backward_disaggregating:
             os.makedirs(os.path.dirname(name), exist_ok=True)
-        if dp_rank == 0 or args.forward_backward_disaggregating:
+        if writer or args.forward_backward_disaggregating:
             sd = generate_state_dict(args, model, None if sharded_opt else optimizer, opt_param_scheduler,
                                      rng_state, iteration, num_floating_point_operations_so_far)
             sd = _to_cpu(sd)

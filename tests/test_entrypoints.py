@@ -148,8 +148,8 @@ def test_text_generation_server_two_tensor_parallel_ranks():
         proc.wait(timeout=30)
 
 
-@pytest.mark.parametrize("fmt", ["torch_dist", "torch"])
-def test_checkpoint_resume_is_exact(tmp_path, fmt):
+@pytest.mark.parametrize("fmt,model", [("torch_dist", "dense"), ("torch", "dense"), ("torch", "moe_ep2"), ("torch_dist", "moe_ep2")])
+def test_checkpoint_resume_is_exact(tmp_path, fmt, model):
     """4 iterations straight == 2 iterations, save (distributed optimizer, dp=2), exit, resume for 2 more: same losses and
     gradient norms to the printed precision (weights, optimizer shards, LR schedule, data position, RNG all restored)."""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
@@ -158,7 +158,10 @@ def test_checkpoint_resume_is_exact(tmp_path, fmt):
     base = ("--num-layers 2 --hidden-size 32 --num-attention-heads 4 --seq-length 32 --max-position-embeddings 32 "
             "--micro-batch-size 2 --global-batch-size 8 --lr 1e-2 --vocab-size 200 --mock-data --log-interval 1 --eval-iters 1 "
             "--eval-interval 100 --distributed-backend gloo --no-gradient-accumulation-fusion --lr-decay-iters 100 "
-            "--train-iters 4 --attention-dropout 0 --hidden-dropout 0 --use-distributed-optimizer").split()
+            "--train-iters 4 --attention-dropout 0 --hidden-dropout 0").split()
+    # dense: ZeRO-1 optimizer shards over dp=2;  moe_ep2: every rank owns two of the four experts (and must write them)
+    base += ["--use-distributed-optimizer"] if model == "dense" else ["--num-experts", "4", "--moe-router-topk", "2",
+                                                                      "--expert-model-parallel-size", "2"]
 
     def run(*extra):
         p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
