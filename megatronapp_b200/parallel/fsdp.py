@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Callable, Iterable, List, Optional
 
+import contextlib
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -193,6 +195,25 @@ class FullyShardedDataParallel(nn.Module):
 
     def broadcast_params(self):
         pass
+
+    @contextlib.contextmanager
+    def summon_full_params(self, writeback: bool = False):
+        """All-gather every unit so that the wrapped module's parameters are whole (checkpoint save / load, export);
+        with ``writeback`` the possibly modified full parameters are folded back into the local shards on exit."""
+        for u in self.units:
+            u.unshard()
+        try:
+            yield self.module
+        finally:
+            for u in self.units:
+                if writeback:
+                    lo = u.rank * u.shard_numel
+                    u.shard.copy_(u.flat[lo:lo + u.shard_numel])
+                    u.main_shard.data.copy_(u.shard.float())
+                u.reshard()
+
+    def state_dict_for_save_checkpoint(self, prefix="", keep_vars=False):
+        return self.state_dict()
 
     def state_dict(self, *a, **k):
         for u in self.units:

@@ -10,6 +10,7 @@ optimizer, opt_param_scheduler, rng_state, num_floating_point_operations_so_far`
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import random
 import threading
@@ -78,6 +79,25 @@ def _unwrap(m):
     return m
 
 
+def _fsdp_wrapper(m):
+    """The ZeRO-3 wrapper around ``m`` (or None): its parameters only exist in full inside ``summon_full_params``."""
+    while m is not None:
+        if hasattr(m, "summon_full_params"):
+            return m
+        m = getattr(m, "module", None)
+    return None
+
+
+@contextlib.contextmanager
+def _full_params(model, writeback: bool):
+    with contextlib.ExitStack() as stack:
+        for m in model:
+            w = _fsdp_wrapper(m)
+            if w is not None:
+                stack.enter_context(w.summon_full_params(writeback=writeback))
+        yield
+
+
 def generate_state_dict(args, model, optimizer, opt_param_scheduler, rng_state, iteration=None,
                         num_floating_point_operations_so_far=0, model_sd_fn=None):
     sd = {"args": args, "checkpoint_version": _CHECKPOINT_VERSION}
@@ -130,9 +150,14 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
         writer = (ps.get_expert_data_parallel_rank() == 0) if ps.get_expert_model_parallel_world_size() > 1 else dp_rank == 0
         if writer or sharded_opt or args.forward_backward_disaggregating:
             os.makedirs(os.path.dirname(name), exist_ok=True)
+        gathered = None
+        if any(_fsdp_wrapper(m) is not None for m in model):
+            # ZeRO-3: assembling the full parameters is a collective -- every rank takes part, the writer keeps the result
+            gathered = iter([m.state_dict_for_save_checkpoint() for m in model])
         if writer or args.forward_backward_disaggregating:
             sd = generate_state_dict(args, model, None if sharded_opt else optimizer, opt_param_scheduler,
-                                     rng_state, iteration, num_floating_point_operations_so_far)
+                                     rng_state, iteration, num_floating_point_operations_so_far,
+                                     model_sd_fn=(lambda m: next(gathered)) if gathered is not None else None)
             sd = _to_cpu(sd)
             _write(sd, name, args.async_save)
         if sharded_opt and not args.no_save_optim:
@@ -140,14 +165,15 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
             _write(_to_cpu(optimizer.state_dict()), oname, args.async_save)
     else:
         ssd = {}
-        for i, m in enumerate(model):
-            prefix = "" if len(model) == 1 else f"model{i}."
-            ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
         common = {"args": args, "checkpoint_version": _CHECKPOINT_VERSION, "iteration": iteration,
                   "num_floating_point_operations_so_far": num_floating_point_operations_so_far,
                   "opt_param_scheduler": opt_param_scheduler.state_dict() if opt_param_scheduler else None,
                   "rng_state": rng_state}
-        sharded.save(ssd, base, common)
+        with _full_params(model, writeback=False):
+            for i, m in enumerate(model):
+                prefix = "" if len(model) == 1 else f"model{i}."
+                ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
+            sharded.save(ssd, base, common)
         if optimizer is not None and not args.no_save_optim:
             torch.save(_to_cpu(optimizer.state_dict()), os.path.join(base, f"optim_{rank:05d}.pt"))
     if dist.is_initialized():
@@ -196,10 +222,11 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
     is_sharded = os.path.exists(os.path.join(base, "metadata.json"))
     if is_sharded:
         ssd = {}
-        for i, m in enumerate(model):
-            prefix = "" if len(model) == 1 else f"model{i}."
-            ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
-        sharded.load(ssd, base, strict=strict)
+        with _full_params(model, writeback=True):
+            for i, m in enumerate(model):
+                prefix = "" if len(model) == 1 else f"model{i}."
+                ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
+            sharded.load(ssd, base, strict=strict)
         sd = sharded.load_common_state_dict(base)
         rank = dist.get_rank() if dist.is_initialized() else 0
         op = os.path.join(base, f"optim_{rank:05d}.pt")
@@ -210,11 +237,9 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
     else:
         name = get_checkpoint_name(load_dir, iteration, release)
         sd = torch.load(name, map_location="cpu", weights_only=False)
-        if len(model) == 1:
-            _unwrap(model[0]).load_state_dict(sd["model"], strict=strict)
-        else:
-            for i, m in enumerate(model):
-                _unwrap(m).load_state_dict(sd[f"model{i}"], strict=strict)
+        for i, m in enumerate(model):
+            target = _fsdp_wrapper(m) or _unwrap(m)          # ZeRO-3: load through the wrapper (gathers, loads, re-shards)
+            target.load_state_dict(sd["model" if len(model) == 1 else f"model{i}"], strict=strict)
         if optimizer is not None and not args.finetune and not args.no_load_optim:
             dp_rank = ps.get_data_parallel_rank(with_context_parallel=True)
             dop = os.path.join(os.path.dirname(name), "distrib_optim.pt" if dp_rank == 0 else f"distrib_optim_dp{dp_rank:03d}.pt")

@@ -148,7 +148,8 @@ def test_text_generation_server_two_tensor_parallel_ranks():
         proc.wait(timeout=30)
 
 
-@pytest.mark.parametrize("fmt,model", [("torch_dist", "dense"), ("torch", "dense"), ("torch", "moe_ep2"), ("torch_dist", "moe_ep2")])
+@pytest.mark.parametrize("fmt,model", [("torch_dist", "dense"), ("torch", "dense"), ("torch", "moe_ep2"), ("torch_dist", "moe_ep2"),
+                                       ("torch", "fsdp"), ("torch_dist", "fsdp")])
 def test_checkpoint_resume_is_exact(tmp_path, fmt, model):
     """4 iterations straight == 2 iterations, save (distributed optimizer, dp=2), exit, resume for 2 more: same losses and
     gradient norms to the printed precision (weights, optimizer shards, LR schedule, data position, RNG all restored)."""
@@ -160,8 +161,9 @@ def test_checkpoint_resume_is_exact(tmp_path, fmt, model):
             "--eval-interval 100 --distributed-backend gloo --no-gradient-accumulation-fusion --lr-decay-iters 100 "
             "--train-iters 4 --attention-dropout 0 --hidden-dropout 0").split()
     # dense: ZeRO-1 optimizer shards over dp=2;  moe_ep2: every rank owns two of the four experts (and must write them)
-    base += ["--use-distributed-optimizer"] if model == "dense" else ["--num-experts", "4", "--moe-router-topk", "2",
-                                                                      "--expert-model-parallel-size", "2"]
+    # fsdp: ZeRO-3 -- parameters exist in full only while gathered, so saving / loading is a collective
+    base += {"dense": ["--use-distributed-optimizer"], "fsdp": ["--use-custom-fsdp"],
+             "moe_ep2": ["--num-experts", "4", "--moe-router-topk", "2", "--expert-model-parallel-size", "2"]}[model]
 
     def run(*extra):
         p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
