@@ -148,8 +148,7 @@ def test_text_generation_server_two_tensor_parallel_ranks():
         proc.wait(timeout=30)
 
 
-@pytest.mark.parametrize("fmt,model", [("torch_dist", "dense"), ("torch", "dense"), ("torch", "moe_ep2"), ("torch_dist", "moe_ep2"),
-                                       ("torch", "fsdp"), ("torch_dist", "fsdp")])
+@pytest.mark.parametrize("fmt,model", [("torch_dist", "dense"), ("torch", "moe_ep2"), ("torch", "fsdp"), ("torch_dist", "fsdp")])
 def test_checkpoint_resume_is_exact(tmp_path, fmt, model):
     """4 iterations straight == 2 iterations, save (distributed optimizer, dp=2), exit, resume for 2 more: same losses and
     gradient norms to the printed precision (weights, optimizer shards, LR schedule, data position, RNG all restored)."""
