@@ -178,40 +178,51 @@ class GPTInferenceWrapper:
         (full vocabulary) on the last pipeline stage and ``None`` elsewhere.  Under pipeline parallelism the hidden
         states hop stage to stage over the p2p channels (reference ``inference/communication_utils.py``); under
         tensor parallelism the vocab-parallel logits are gathered."""
-        from ..parallel import p2p, state as ps
-
         ctx = self.context
         ctx.sequence_len_offset = start
         ids = tokens[:, start:end]
         pos = torch.arange(start, end, device=tokens.device).unsqueeze(0).expand_as(ids)
-        pp = ps.get_pipeline_model_parallel_world_size() if ps.model_parallel_is_initialized() else 1
-        if pp > 1:
-            cfg = self.inner.config
-            if not ps.is_pipeline_first_stage():
-                h = p2p.recv((end - start, ids.shape[0], cfg.hidden_size), cfg.pipeline_dtype or cfg.params_dtype,
-                             ps.get_pipeline_model_parallel_prev_rank(), "fwd", "recv-forward")
-                self.inner.set_input_tensor(h)
-            out = self.model(ids, pos, None, inference_context=ctx)
-            if not ps.is_pipeline_last_stage():
-                p2p.send(out, ps.get_pipeline_model_parallel_next_rank(), "fwd", "send-forward")
-                p2p.flush()
-                out = None
-        else:
-            out = self.model(ids, pos, None, inference_context=ctx)
+        out = pipeline_forward(self.model, self.inner, ids, pos, ctx, (end - start, ids.shape[0]))
         ctx.sequence_len_offset = end
         return self._full_vocab(out)
 
     def _full_vocab(self, logits):
-        from ..parallel import state as ps
+        return gather_full_vocab(logits, self.padded_vocab_size or getattr(self.inner, "vocab_size", None))
 
-        if logits is None or not ps.model_parallel_is_initialized() or ps.get_tensor_model_parallel_world_size() == 1:
-            return logits
-        full = self.padded_vocab_size or getattr(self.inner, "vocab_size", None)
-        if full is not None and logits.shape[-1] >= full:
-            return logits                                  # the model already gathered (parallel_output=False)
-        from ..parallel.mappings import gather_from_tensor_model_parallel_region
 
-        return gather_from_tensor_model_parallel_region(logits)
+def pipeline_forward(model, inner, ids, pos, ctx, seq_batch):
+    """One forward of ``ids`` through every pipeline stage: the hidden states hop stage to stage over the p2p channels.
+    Returns the model output on the last stage and ``None`` on the others.  ``seq_batch`` = (tokens, batch) of the
+    ``[s, b, h]`` activation that crosses the stage boundaries."""
+    from ..parallel import p2p, state as ps
+
+    pp = ps.get_pipeline_model_parallel_world_size() if ps.model_parallel_is_initialized() else 1
+    if pp == 1:
+        return model(ids, pos, None, inference_context=ctx)
+    cfg = inner.config
+    if not ps.is_pipeline_first_stage():
+        h = p2p.recv((seq_batch[0], seq_batch[1], cfg.hidden_size), cfg.pipeline_dtype or cfg.params_dtype,
+                     ps.get_pipeline_model_parallel_prev_rank(), "fwd", "recv-forward")
+        inner.set_input_tensor(h)
+    out = model(ids, pos, None, inference_context=ctx)
+    if not ps.is_pipeline_last_stage():
+        p2p.send(out, ps.get_pipeline_model_parallel_next_rank(), "fwd", "send-forward")
+        p2p.flush()
+        return None
+    return out
+
+
+def gather_full_vocab(logits, full_vocab: Optional[int]):
+    """Vocab-parallel logits -> full vocabulary (no-op without TP or when the model already gathered)."""
+    from ..parallel import state as ps
+
+    if logits is None or not ps.model_parallel_is_initialized() or ps.get_tensor_model_parallel_world_size() == 1:
+        return logits
+    if full_vocab is not None and logits.shape[-1] >= full_vocab:
+        return logits
+    from ..parallel.mappings import gather_from_tensor_model_parallel_region
+
+    return gather_from_tensor_model_parallel_region(logits)
 
 
 def sync_sampled_tokens(new: Optional[torch.Tensor], batch: int, device) -> torch.Tensor:

@@ -20,7 +20,8 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .core import InferenceRequest, SamplingParams, Status, sample_from_logits
+from .core import (InferenceRequest, SamplingParams, Status, gather_full_vocab, pipeline_forward, sample_from_logits,
+                   sync_sampled_tokens)
 
 
 class BlockAllocator:
@@ -183,6 +184,7 @@ class DynamicInferenceEngine:
             self.generator = torch.Generator().manual_seed(random_seed)
         self.num_preemptions = 0
         self.steps = 0
+        self.padded_vocab_size = None
 
     # -- API -----------------------------------------------------------------------
     def add_request(self, prompt: str, sampling_params: Optional[SamplingParams] = None,
@@ -209,8 +211,9 @@ class DynamicInferenceEngine:
         over = args.inference_dynamic_batching_buffer_overflow_factor or 1.0
         max_req = args.inference_dynamic_batching_max_requests_override or max(1, int(blocks * over))
         max_tok = args.inference_dynamic_batching_max_tokens_override or min(16384, int(blocks * bs * over))
-        return cls(model, tokenizer, args.inference_max_seq_length, blocks, bs, max_tok, max_req,
-                   getattr(args, "seed", None))
+        eng = cls(model, tokenizer, args.inference_max_seq_length, blocks, bs, max_tok, max_req, getattr(args, "seed", None))
+        eng.padded_vocab_size = getattr(args, "padded_vocab_size", None)
+        return eng
 
     @property
     def controller(self):            # the servers reach the tokenizer through engine.controller.tokenizer
@@ -283,23 +286,35 @@ class DynamicInferenceEngine:
         positions = ctx.begin_step(work, dev)
         ids = torch.tensor([t for rid, n in work for t in self.running[rid].tokens[self.running[rid].fed:self.running[rid].fed + n]],
                            dtype=torch.long, device=dev).unsqueeze(0)
-        logits = self.model(ids, positions.unsqueeze(0), None, inference_context=ctx)[0]       # [T, V]
+        inner = self.model
+        while hasattr(inner, "module"):
+            inner = inner.module
+        out = pipeline_forward(self.model, inner, ids, positions.unsqueeze(0), ctx, (ids.shape[1], 1))
+        out = gather_full_vocab(out, self.padded_vocab_size or getattr(inner, "vocab_size", None))
+        logits = out[0] if out is not None else None                                          # [T, V] on the last stage
         last = ctx.last_token_index()
         ctx.end_step()
         self.steps += 1
         finished = []
         vocab = getattr(self.tokenizer, "vocab_size", None)
         eod = self.tokenizer.eod
+        sampling = [rid for rid, n in work if self.running[rid].fed + n >= len(self.running[rid].tokens)]
+        picked = None
+        if logits is not None and sampling:                            # last pipeline stage samples ...
+            picked = torch.stack([sample_from_logits(logits[last[rid]].unsqueeze(0), self.running[rid].req.inference_parameters,
+                                                     vocab, self.generator).view(()) for rid in sampling]).to(dev)
+        if sampling:                                                   # ... every model-parallel rank gets the same tokens
+            picked = sync_sampled_tokens(picked, len(sampling), dev)
+        chosen = dict(zip(sampling, picked.tolist())) if sampling else {}
         for rid, n in work:
             r = self.running[rid]
             r.fed += n
             if r.fed < len(r.tokens):
                 continue                                              # still prefilling
             p = r.req.inference_parameters
-            row = logits[last[rid]].unsqueeze(0)
-            new = int(sample_from_logits(row, p, vocab, self.generator))
-            if p.return_log_probs:
-                r.logprobs.append(float(torch.log_softmax(row.float(), -1)[0, new]))
+            new = int(chosen[rid])
+            if p.return_log_probs and logits is not None:
+                r.logprobs.append(float(torch.log_softmax(logits[last[rid]].float(), -1)[new]))
             r.tokens.append(new)
             r.req.status = Status.ACTIVE_AND_GENERATING_TOKENS
             n_gen = len(r.tokens) - r.n_prompt

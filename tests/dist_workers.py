@@ -441,8 +441,14 @@ def generation_parity(tp=1, pp=1):
     eng = StaticInferenceEngine(TextGenerationController(w, NullTokenizer(255)), max_batch_size=4)
     res = eng.generate(["5 9 23 7 100", "11 3", "200 201 202"], SamplingParams(top_k=1, num_tokens_to_generate=6,
                                                                              return_log_probs=True))
+    from megatronapp_b200.inference import DynamicInferenceEngine
+
+    dyn = DynamicInferenceEngine(m, NullTokenizer(255), max_sequence_length=32, num_blocks=16, block_size=4,
+                                 max_tokens_per_step=6, max_requests=3)
+    dyn.padded_vocab_size = 256
+    dres = dyn.generate(["5 9 23 7 100", "11 3", "200 201 202"], SamplingParams(top_k=1, num_tokens_to_generate=6))
     return {"tokens": [r.generated_tokens.tolist() for r in res], "rank": rank,
-            "logprobs": [r.generated_log_probs for r in res]}
+            "logprobs": [r.generated_log_probs for r in res], "dynamic": [r.generated_tokens.tolist() for r in dres]}
 
 
 def reshard_logits(tp=1, pp=1, path=None, mode="save", tied=True):

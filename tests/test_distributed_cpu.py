@@ -130,10 +130,12 @@ def test_t5_encoder_decoder_pipeline_split_matches_unsplit():
 def test_generation_under_tensor_and_pipeline_parallelism():
     base = run_distributed("generation_parity", 1)[0]
     assert all(1 <= len(t) <= 6 for t in base["tokens"]) and max(len(t) for t in base["tokens"]) > 2, base["tokens"]
+    assert base["dynamic"] == base["tokens"]
     for kw in ({"tp": 2}, {"pp": 2}):
         res = run_distributed("generation_parity", 2, **kw)
         for r in res:
             assert r["tokens"] == base["tokens"], (kw, r["rank"])          # every rank ends with the same continuation
+            assert r["dynamic"] == base["tokens"], (kw, r["rank"])         # paged-KV continuous batching too
         lp = [r["logprobs"] for r in res if r["logprobs"][0]]
         assert lp and all(abs(a - b) < 1e-3 for x, y in zip(lp[-1], base["logprobs"]) for a, b in zip(x, y))
 
