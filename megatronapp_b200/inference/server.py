@@ -78,7 +78,28 @@ def serve_worker_ranks(engine) -> None:
         dist.broadcast_object_list(box, src=0)
         if box[0] == _SHUTDOWN:
             return
-        run_generate(engine, box[1], announce=False)
+        req = box[1]
+        scope = req.get("_megascope")
+        if scope is None:
+            run_generate(engine, req, announce=False)
+            continue
+        # a MegaScope request: this rank must run the same capture hooks (their TP gathers are collectives) and the
+        # same perturbations as rank 0; only rank 0 reports to the client (reference broadcasts the configs per request)
+        from ..scope import hooks
+        from ..scope.capture import TensorTracers
+        from ..scope.disturbance import Disturbance
+
+        tracers, dis = TensorTracers(scope["num_layers"], None), Disturbance()
+        tracers.flags.set_by_configs(req.get("visualization_flags", {}))
+        dis.set_by_configs(req.get("disturbance_configs", {}))
+        if req.get("compressor_config"):
+            tracers.compressor.set_by_configs(req["compressor_config"])
+        tracers.set_report(lambda *a, **k: None)
+        hooks.install(tracers, dis)
+        try:
+            run_generate(engine, req, announce=False)
+        finally:
+            hooks.install(None, None)
 
 
 def run_generate(engine: StaticInferenceEngine, req: dict, announce: bool = True):
@@ -231,6 +252,7 @@ class InferenceWSServer:
 
                 self.tracers.set_report(report)
                 hooks.install(self.tracers, self.disturbance)
+                msg["_megascope"] = {"num_layers": self.tracers.flags.num_layers}      # tells worker ranks to mirror the hooks
                 try:
                     out = run_generate(self.engine, msg)
                 finally:

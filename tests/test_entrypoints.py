@@ -202,3 +202,58 @@ def test_optimizer_cpu_offload_matches_device_optimizer(tmp_path):
     ck = str(tmp_path / "ck")
     assert run(*off, "--exit-interval", "2", "--save", ck) == ref[:2]
     assert run(*off, "--load", ck) == ref[2:]
+
+
+def test_megascope_ws_server_two_tensor_parallel_ranks():
+    """MegaScope capture over TP=2: the worker rank mirrors the capture hooks (their TP gathers are collectives), rank 0
+    streams the compressed tensors of every requested kind back to the WebSocket client."""
+    import json
+    import signal
+    import time
+
+    from websockets.sync.client import connect
+
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    port = _port()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_port()), os.path.join(ROOT, "tools", "run_text_generation_server.py"),
+           "--tensor-model-parallel-size", "2", "--enable-ws-server", "--ws-port", str(port), "--num-layers", "2",
+           "--hidden-size", "32", "--num-attention-heads", "4", "--seq-length", "32", "--max-position-embeddings", "64",
+           "--micro-batch-size", "1", "--vocab-size", "200", "--distributed-backend", "gloo", "--inference-max-seq-length", "64"]
+    proc = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                            start_new_session=True)
+    try:
+        ws = None
+        for _ in range(90):
+            if proc.poll() is not None:
+                break
+            try:
+                ws = connect(f"ws://127.0.0.1:{port}")
+                break
+            except OSError:
+                time.sleep(1.0)
+        assert ws is not None, "ws server never came up"
+        ws.send(json.dumps({"type": "generate", "prompts": ["4 5 6"], "tokens_to_generate": 3, "top_k": 1,
+                            "visualization_flags": {"MLP1_mat_mul": "true", "QKV_mat_mul": "true",
+                                                    "RawAttentionScore_mat_mul": "true", "Result": "true"},
+                            "compressor_config": {"MLP": {"pixels": 4, "method": "mean"}, "QKV": {"pixels": 6, "method": "mean"}}}))
+        kinds, qkv = set(), None
+        while True:
+            m = json.loads(ws.recv(timeout=120))
+            kinds.add((m["type"], m.get("update_type")))
+            if m["type"] == "update" and m["update_type"] == 1 and qkv is None:
+                qkv = m["result"]
+            if m["type"] in ("finish", "error"):
+                break
+        assert m["type"] == "finish" and len(m["tokens"][0]) == 6
+        assert {("update", 1), ("update", 2), ("update", 4), ("update", 6)} <= kinds
+        flat = qkv
+        while isinstance(flat[0], list):
+            flat = flat[-1]
+        assert len(flat) > 0 and all(isinstance(v, float) for v in flat)   # compressed QKV row assembled from both TP shards
+        ws.close()
+    finally:
+        os.killpg(proc.pid, signal.SIGTERM)
+        proc.wait(timeout=30)
