@@ -527,7 +527,7 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, nflops)
             saved = True
             timers("interval-time", log_level=0).start(barrier=True)
-        if args.exit_duration_in_mins:
+        if args.exit_duration_in_mins is not None:
             mins = (time.time() - _TRAIN_START_TIME) / 60.0
             flag = torch.tensor([int(mins > args.exit_duration_in_mins)], dtype=torch.int,
                                 device="cuda" if (torch.cuda.is_available() and args.distributed_backend == "nccl") else "cpu")
@@ -739,8 +739,12 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     tracer = get_tracer()
     if tracer.enabled:
         tracer.shutdown()
-    if args.eval_iters and getattr(args, "do_valid", valid_it is not None) and not args.skip_train and args.eval_interval:
+    # final evaluation on the validation and the test split -- also the whole job of an evaluation-only run (--skip-train)
+    if args.eval_iters and getattr(args, "do_valid", valid_it is not None) and (args.eval_interval or args.skip_train):
         evaluate_and_print_results(f"the end of training for val data", forward_step_func, valid_it, model,
+                                   iteration, config)
+    if args.eval_iters and getattr(args, "do_test", False) and (args.eval_interval or args.skip_train):
+        evaluate_and_print_results(f"the end of training for test data", forward_step_func, test_it, model,
                                    iteration, config)
     if args.use_dpp:
         from ..dpp.scheduler import shutdown_dpp
