@@ -257,3 +257,27 @@ def test_megascope_ws_server_two_tensor_parallel_ranks():
     finally:
         os.killpg(proc.pid, signal.SIGTERM)
         proc.wait(timeout=30)
+
+
+def test_example_scripts_only_use_flags_that_exist():
+    """Every ``--flag`` in the shipped launch scripts is accepted by the parser of the program it launches."""
+    import glob
+
+    sys.path.insert(0, ROOT)
+    from megatronapp_b200.training.arguments import build_parser
+
+    known = set(build_parser()._option_string_actions)
+    declared = set()                                   # flags declared by the individual entry points / tools
+    for f in glob.glob(os.path.join(ROOT, "*.py")) + glob.glob(os.path.join(ROOT, "tools", "**", "*.py"), recursive=True) \
+            + glob.glob(os.path.join(ROOT, "tasks", "**", "*.py"), recursive=True) \
+            + glob.glob(os.path.join(ROOT, "examples", "**", "*.py"), recursive=True):
+        declared |= set(re.findall(r'add_argument\(\s*"(--[a-zA-Z0-9_\-]+)"', open(f).read()))
+    launcher = {"--nnodes", "--nproc-per-node", "--master-addr", "--master-port", "--node-rank", "--standalone", "--local-addr"}
+    scripts = glob.glob(os.path.join(ROOT, "examples", "**", "*.sh"), recursive=True) + glob.glob(os.path.join(ROOT, "scripts", "*.sh"))
+    assert len(scripts) >= 15
+    bad = {}
+    for f in scripts:
+        for flag in set(re.findall(r"(?<![\w-])(--[a-zA-Z][a-zA-Z0-9_\-]*)", open(f).read())):
+            if flag not in known and flag not in declared and flag not in launcher:
+                bad.setdefault(os.path.relpath(f, ROOT), []).append(flag)
+    assert not bad, bad
