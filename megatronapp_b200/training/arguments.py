@@ -584,6 +584,8 @@ _UNSUPPORTED = (
     (lambda a: a.non_persistent_local_ckpt_dir is not None, "local non-persistent checkpoints are not implemented"),
     (lambda a: a.vision_backbone_type != "vit", "only the ViT vision backbone is implemented (no MiT / Swin)"),
     (lambda a: a.vision_pretraining_type != "classify", "only classification vision pre-training is implemented (no inpainting / DINO)"),
+    (lambda a: a.encoder_tensor_model_parallel_size not in (0, a.tensor_model_parallel_size),
+     "a different tensor-parallel size for the encoder (--encoder-tensor-model-parallel-size) is not implemented"),
     (lambda a: a.optimizer_cpu_offload and not (0.0 < a.optimizer_offload_fraction <= 1.0),
      "--optimizer-offload-fraction must lie in (0, 1]"),
 )
@@ -593,6 +595,9 @@ def validate_args(args, defaults=None):
     for bad, msg in _UNSUPPORTED:
         if bad(args):
             raise NotImplementedError(msg)
+    if getattr(args, "ignore_forward_tensor_parallel", False) and getattr(args, "rank", 0) == 0:
+        print("WARNING: --ignore-forward-tensor-parallel is accepted for CLI compatibility; forward ranks keep the "
+              "backward ranks' tensor-parallel degree in this implementation (see fbd/schedule.py)", flush=True)
     for k, v in (defaults or {}).items():
         if getattr(args, k, None) is None:
             setattr(args, k, v)
