@@ -142,6 +142,8 @@ def get_model(model_provider_func: Callable, model_type=None, wrap_with_ddp: boo
 
 def get_optimizer_param_scheduler(optimizer):
     args = get_args()
+    if args.lr is None:
+        raise ValueError("--lr is required to train (no learning rate was given)")
     if args.train_iters:
         if args.lr_decay_iters is None:
             args.lr_decay_iters = args.train_iters
