@@ -535,6 +535,25 @@ def attention(q, k, v, scale=None, causal=True, dropout_p=0.0, training=True, ma
                                           enable_gqa=(k.shape[1] != q.shape[1]))
 
 
+def attention_varlen(q, k, v, cu_seqlens_q, cu_seqlens_kv=None, scale=None, causal=True, dropout_p=0.0, training=True):
+    """Packed (THD) attention: ``q/k/v [t, h, d]`` hold several sequences back to back, ``cu_seqlens`` their boundaries;
+    tokens attend within their own sequence only.  Every sequence runs through ``attention`` (the tcgen05 flash
+    kernel when its length qualifies), so no ``t x t`` mask is ever materialised.  Returns ``[t, h, d]``."""
+    cu_kv = cu_seqlens_q if cu_seqlens_kv is None else cu_seqlens_kv
+    bq, bk = [int(x) for x in cu_seqlens_q.tolist()], [int(x) for x in cu_kv.tolist()]
+    outs = []
+    for (q0, q1), (k0, k1) in zip(zip(bq[:-1], bq[1:]), zip(bk[:-1], bk[1:])):
+        if q1 == q0:
+            continue
+        o = attention(q[q0:q1].transpose(0, 1).unsqueeze(0), k[k0:k1].transpose(0, 1).unsqueeze(0),
+                      v[k0:k1].transpose(0, 1).unsqueeze(0), scale, causal, dropout_p, training)
+        outs.append(o[0].transpose(0, 1))
+    tail = q.shape[0] - bq[-1]                       # padding tokens after the last sequence produce zeros
+    if tail > 0:
+        outs.append(q.new_zeros(tail, q.shape[1], v.shape[-1]))
+    return torch.cat(outs, dim=0)
+
+
 # ---------------------------------------------------------------------------
 # (vocab-parallel) cross entropy on [rows, vocab_local] logits
 # ---------------------------------------------------------------------------

@@ -43,6 +43,14 @@ class CrossAttentionSubmodules:
     linear_proj: Union[ModuleSpec, type] = None
 
 
+def _packed_positions(cu_seqlens: torch.Tensor, total: int, device) -> torch.Tensor:
+    """``[0..len_0-1, 0..len_1-1, ...]`` (padding after the last sequence keeps counting) for THD rotary embeddings."""
+    cu = cu_seqlens.to(device=device, dtype=torch.long)
+    idx = torch.arange(total, device=device)
+    seg = torch.bucketize(idx, cu[1:], right=True).clamp_max(cu.numel() - 2)
+    return idx - cu[seg]
+
+
 class DotProductAttention(MegatronModule):
     """Core attention on ``[s, b, np, hn]`` tensors -> ``[s, b, np*hn]``."""
 
@@ -84,8 +92,14 @@ class DotProductAttention(MegatronModule):
 
     def forward(self, query, key, value, attention_mask=None, attn_mask_type=None, attention_bias=None,
                 packed_seq_params=None):
-        if packed_seq_params is not None:
-            raise NotImplementedError("packed (THD) sequences are handled by ops.attention_varlen")
+        if packed_seq_params is not None:          # THD: [t, 1, np, hn] with sequence boundaries in cu_seqlens
+            if query.shape[1] != 1:
+                raise ValueError("packed sequences expect micro-batch 1 (all sequences concatenated along tokens)")
+            causal = str(attn_mask_type or self.attn_mask_type).endswith("causal")
+            o = ops.attention_varlen(query[:, 0], key[:, 0], value[:, 0], packed_seq_params.cu_seqlens_q,
+                                     packed_seq_params.cu_seqlens_kv, self.softmax_scale, causal,
+                                     self.dropout_p if self.training else 0.0, self.training)
+            return o.reshape(query.shape[0], 1, self.np * o.shape[-1])
         mask_type = attn_mask_type or self.attn_mask_type
         causal = str(mask_type).endswith("causal")
         sq, b = query.shape[0], query.shape[1]
@@ -170,7 +184,11 @@ class Attention(MegatronModule):
                 return self._dynamic_batch_attention(query, key, value, rotary_pos_emb, inference_context)
             if rotary_pos_emb is not None:
                 q_cs, k_cs = rotary_pos_emb if isinstance(rotary_pos_emb, tuple) else (rotary_pos_emb, rotary_pos_emb)
-                if inference_context is not None:
+                if packed_seq_params is not None:      # positions restart at every packed sequence
+                    q_cs = q_cs[_packed_positions(packed_seq_params.cu_seqlens_q, query.shape[0], q_cs.device)]
+                    k_cs = k_cs[_packed_positions(packed_seq_params.cu_seqlens_kv if packed_seq_params.cu_seqlens_kv is not None
+                                                  else packed_seq_params.cu_seqlens_q, key.shape[0], k_cs.device)]
+                elif inference_context is not None:
                     off = inference_context.sequence_len_offset
                     q_cs = q_cs[off:off + query.shape[0]]
                     k_cs = k_cs[off:off + key.shape[0]]

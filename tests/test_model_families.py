@@ -464,3 +464,32 @@ def test_radio_vit_resolution_agnostic_position_embeddings():
     out = m(torch.randn(2, 3, 16, 16))
     out.square().mean().backward()
     assert m.position_embeddings.grad is not None and m.class_token.grad is not None
+
+
+def test_packed_thd_sequences_match_separate_forward():
+    """Three sequences packed into one THD row (cu_seqlens) == the three sequences run on their own: attention stays
+    inside each sequence and rotary positions restart at the boundaries."""
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+    from megatronapp_b200.utils.packed_seq_params import PackedSeqParams
+
+    _init()
+    torch.manual_seed(0)
+    cfg = _cfg(kernel_backend="torch")
+    m = GPTModel(cfg, get_gpt_layer_local_spec(), 64, 64, position_embedding_type="rope").eval()
+    lens = [5, 9, 3]
+    seqs = [torch.randint(0, 64, (1, n)) for n in lens]
+    with torch.no_grad():
+        ref = torch.cat([m(s, torch.arange(s.shape[1]).unsqueeze(0), None) for s in seqs], dim=1)
+        cu = torch.tensor([0, 5, 14, 17], dtype=torch.int32)
+        psp = PackedSeqParams(qkv_format="thd", cu_seqlens_q=cu, cu_seqlens_kv=cu, max_seqlen_q=9, max_seqlen_kv=9)
+        packed = torch.cat(seqs, dim=1)
+        pos = torch.cat([torch.arange(n) for n in lens]).unsqueeze(0)
+        out = m(packed, pos, None, packed_seq_params=psp)
+        assert torch.allclose(out, ref, atol=1e-5), float((out - ref).abs().max())
+        naive = m(packed, torch.arange(17).unsqueeze(0), None)            # without the boundaries tokens see their neighbours
+        assert not torch.allclose(naive[:, 5:], ref[:, 5:], atol=1e-3)
+    # gradients flow through the per-sequence path
+    m.train()
+    loss = m(packed, pos, None, labels=packed, packed_seq_params=psp).mean()
+    loss.backward()
+    assert m.decoder.layers[0].self_attention.linear_qkv.weight.grad.abs().sum() > 0
