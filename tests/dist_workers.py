@@ -529,6 +529,50 @@ def moe_reshard(ep=1, path=None, mode="save", grouped=False):
     return {"out": out.flatten().tolist(), "keys": keys}
 
 
+def dpp_compat_transport():
+    """The reference's module-function mailbox API over 2 pipeline ranks: non-blocking gets, last->first slot shift."""
+    import sys
+    import time
+
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    import shm_tensor_new_rdma_pre_alloc as shm
+
+    rank, world = _setup()
+    pp, total = 2, 4                                        # 2 microbatches x 2 chunks
+    shm.init_shared_memory(6, rank, total, 2, pp, ["127.0.0.1"] * 2, (rank - 1) % 2, (rank + 1) % 2, rank == 1, rank == 0,
+                           1 << 20, 2, dtype=torch.float32, device="cpu")
+    shm.init_forward_rdma(6, rank, (rank + 1) % 2, (rank - 1) % 2, rank)
+    out = {}
+    if rank == 0:
+        assert shm.get_forward_tensor(2) is None           # nothing has arrived yet: poll, don't block
+        shm.put_forward_tensor(1, torch.full((2, 3), 7.0))   # stage 0 -> stage 1, same slot
+        deadline = time.time() + 30
+        t = None
+        while t is None and time.time() < deadline:          # stage 1 (last) put slot 0 -> lands in slot 0 + pp here
+            t = shm.get_forward_tensor(2)
+            time.sleep(0.01)
+        out["wrapped"] = t.tolist()
+        g = None
+        while g is None and time.time() < deadline:
+            g = shm.get_backward_tensor(1)
+            time.sleep(0.01)
+        out["grad"] = g.tolist()
+    else:
+        deadline = time.time() + 30
+        t = None
+        while t is None and time.time() < deadline:
+            t = shm.get_forward_tensor(1)
+            time.sleep(0.01)
+        out["fwd"] = t.tolist()
+        shm.put_forward_tensor(0, torch.arange(6.0))         # last stage: crosses to the next chunk's slot on stage 0
+        shm.put_backward_tensor(1, torch.full((6,), -1.0))
+    while not shm.check_send_finish(False):
+        time.sleep(0.01)
+    dist.barrier()
+    shm.join_threads()
+    return out
+
+
 WORKERS = {k: v for k, v in globals().items() if callable(v) and not k.startswith("_")}
 
 if __name__ == "__main__":

@@ -94,3 +94,11 @@ def test_reference_committed_traces_reproduce_baseline_numbers():
     assert 0.74 < r["dpp_speedup"] < 0.78                      # the reference's DPP is 1.32x slower
     rw = [r["static"]["ranks"][k]["reduce_window_ms"] for k in sorted(r["static"]["ranks"])]
     assert all(abs(x - y) < 1.0 for x, y in zip(rw, [44.4, 51.9, 61.6, 69.5])), rw
+
+
+def test_reference_transport_api_compat():
+    from dist_utils import run_distributed
+
+    r0, r1 = run_distributed("dpp_compat_transport", 2)
+    assert r1["fwd"] == [7.0] * 6
+    assert r0["wrapped"] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and r0["grad"] == [-1.0] * 6
