@@ -58,10 +58,41 @@ _ALIASES = {
     "megatron.core.models.mamba.mamba_model": "megatronapp_b200.models.mamba.mamba_model",
     "megatron.core.models.common.embeddings": "megatronapp_b200.models.common.embeddings",
     "megatron.core.ssm.mamba_mixer": "megatronapp_b200.ssm.mamba",
-    "megatron.core.inference": "megatronapp_b200.inference.core",
     "megatron.core.datasets.indexed_dataset": "megatronapp_b200.data.indexed_dataset",
     "megatron.core.datasets.gpt_dataset": "megatronapp_b200.data.gpt_dataset",
     "megatron.core.datasets.helpers": "megatronapp_b200.data._helpers",
+    "megatron.core.datasets.blended_megatron_dataset_builder": "megatronapp_b200.data.blended_builder",
+    "megatron.core.datasets.blended_megatron_dataset_config": "megatronapp_b200.data.blended_builder",
+    "megatron.core.datasets.masked_dataset": "megatronapp_b200.data.masked_dataset",
+    "megatron.core.datasets.bert_dataset": "megatronapp_b200.data.masked_dataset",
+    "megatron.core.datasets.t5_dataset": "megatronapp_b200.data.masked_dataset",
+    "megatron.core.packed_seq_params": "megatronapp_b200.utils.packed_seq_params",
+    "megatron.core.process_groups_config": "megatronapp_b200.parallel.process_groups_config",
+    "megatron.core.fp8_utils": "megatronapp_b200.ops.fp8",
+    "megatron.core.inference.engines": "megatronapp_b200.inference",
+    "megatron.core.inference.sampling_params": "megatronapp_b200.inference.core",
+    "megatron.core.inference.inference_request": "megatronapp_b200.inference.core",
+    "megatron.core.inference.scheduler": "megatronapp_b200.inference.core",
+    "megatron.core.inference.contexts": "megatronapp_b200.inference",
+    "megatron.core.inference.text_generation_controllers.text_generation_controller": "megatronapp_b200.inference.core",
+    "megatron.core.models.vision.clip_vit_model": "megatronapp_b200.models.vision.clip_vit_model",
+    "megatron.core.models.vision.radio": "megatronapp_b200.models.vision.radio",
+    "megatron.core.models.vision.multimodal_projector": "megatronapp_b200.models.vision.multimodal_projector",
+    "megatron.core.models.multimodal.llava_model": "megatronapp_b200.models.multimodal.llava_model",
+    "megatron.core.models.retro": "megatronapp_b200.models.retro",
+    "megatron.core.models.common.embeddings.relative_pos_embedding": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.common.embeddings.rotary_pos_embedding": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.common.language_module.language_module": "megatronapp_b200.models.common.language_module",
+    "megatron.core.export.trtllm": "megatronapp_b200.export.trtllm",
+    "megatron.core.post_training.modelopt": "megatronapp_b200.post_training.quantization",
+    "megatron.legacy.model": "megatronapp_b200.legacy.model",
+    "megatron.legacy.model.biencoder_model": "megatronapp_b200.legacy.model.biencoder_model",
+    "megatron.legacy.data.ict_dataset": "megatronapp_b200.data.ict_dataset",
+    "megatron.training.tokenizer.multimodal_tokenizer": "megatronapp_b200.data.tokenizer_extra",
+    "megatron.training.yaml_arguments": "megatronapp_b200.training.yaml_arguments",
+    "megatron.training.ft_integration": "megatronapp_b200.training.ft_integration",
+    "megatron.training.async_utils": "megatronapp_b200.training.async_utils",
+    "megatron.post_training.checkpointing": "megatronapp_b200.post_training.quantization",
     # megatron.training & add-ons
     "megatron.training.arguments": "megatronapp_b200.training.arguments",
     "megatron.training.initialize": "megatronapp_b200.training.initialize",
@@ -136,7 +167,12 @@ _UNIONS = {
     "megatron.core.tensor_parallel": ("megatronapp_b200.parallel.tp_layers", "megatronapp_b200.parallel.mappings",
                                       "megatronapp_b200.parallel.cross_entropy", "megatronapp_b200.parallel.random"),
     "megatron.core.pipeline_parallel": ("megatronapp_b200.parallel.schedules",),
-    "megatron.core.datasets": ("megatronapp_b200.data.gpt_dataset", "megatronapp_b200.data.indexed_dataset"),
+    "megatron.core.datasets": ("megatronapp_b200.data.gpt_dataset", "megatronapp_b200.data.indexed_dataset",
+                               "megatronapp_b200.data.blended_builder", "megatronapp_b200.data.mock"),
+    "megatron.core.datasets.gpt_dataset": (),
+    "megatron.core.dist_checkpointing": ("megatronapp_b200.ckpt.sharded",),
+    "megatron.core.inference": ("megatronapp_b200.inference", "megatronapp_b200.inference.core"),
+    "megatron.training.tokenizer": ("megatronapp_b200.data.tokenizer", "megatronapp_b200.data.tokenizer_extra"),
 }
 
 

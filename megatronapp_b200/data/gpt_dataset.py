@@ -207,3 +207,15 @@ def build_gpt_datasets(args, train_val_test_num_samples):
             ws = [w for w, d in zip(weights, per_split[i]) if d is not None]
             out.append(BlendedDataset(ds, ws, int(n)))
     return tuple(out)
+
+
+def __getattr__(name):      # names the reference exposes from ``core/datasets/gpt_dataset.py`` that live in sibling modules here
+    if name in ("GPTDatasetConfig", "BlendedMegatronDatasetConfig"):
+        from . import blended_builder
+
+        return getattr(blended_builder, name)
+    if name == "MockGPTDataset":
+        from .mock import MockGPTDataset
+
+        return MockGPTDataset
+    raise AttributeError(name)

@@ -34,3 +34,28 @@ def test_core_distributed_and_optimizer_paths():
 
     assert DistributedDataParallel and finalize_model_grads and OptimizerConfig and get_megatron_optimizer
     assert callable(get_forward_backward_func) and callable(gather_from_sequence_parallel_region)
+
+
+def test_namespace_covers_datasets_inference_checkpointing_and_legacy():
+    import subprocess
+    import sys
+
+    code = """
+from megatron.core import dist_checkpointing
+from megatron.core.datasets.gpt_dataset import GPTDatasetConfig, MockGPTDataset
+from megatron.core.datasets.blended_megatron_dataset_builder import BlendedMegatronDatasetBuilder
+from megatron.core.inference.engines import StaticInferenceEngine, DynamicInferenceEngine
+from megatron.core.inference.sampling_params import SamplingParams
+from megatron.core.packed_seq_params import PackedSeqParams
+from megatron.core.models.vision.radio import RADIOViTModel
+from megatron.core.models.multimodal.llava_model import LLaVAModel
+from megatron.legacy.model import GPTModel, BertModel
+from megatron.training.tokenizer import build_tokenizer
+import shm_tensor_new_rdma_pre_alloc as shm
+assert callable(dist_checkpointing.save) and callable(dist_checkpointing.load) and callable(shm.put_forward_tensor)
+print("ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "compat"), root]))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stderr[-2000:]
