@@ -181,7 +181,27 @@ def get_moe_layer_wise_logging_tracker():
     return _MOE_LAYER_WISE_LOGGING_TRACKER
 
 
+def reduce_aux_losses_tracker_across_ranks():
+    """Layers live on different pipeline stages: sum the per-layer vectors over the PP group so that the logging rank
+    sees every layer (reference ``moe_utils.reduce_aux_losses_tracker_across_ranks``), then average over the data-parallel
+    replicas."""
+    import torch.distributed as dist
+
+    from ..parallel import state as ps
+
+    if not (dist.is_available() and dist.is_initialized() and ps.model_parallel_is_initialized()):
+        return
+    for d in _MOE_LAYER_WISE_LOGGING_TRACKER.values():
+        v = d["values"]
+        for group, avg in ((ps.get_pipeline_model_parallel_group(), False), (ps.get_data_parallel_group(), True)):
+            if group is not None and not isinstance(group, ps._SingleGroup):
+                dist.all_reduce(v, group=group)
+                if avg:
+                    v.div_(dist.get_world_size(group))
+
+
 def track_moe_metrics(loss_scale, iteration, writer, wandb_writer=None, total_loss_dict=None, per_layer_logging=False):
+    reduce_aux_losses_tracker_across_ranks()
     for name, d in _MOE_LAYER_WISE_LOGGING_TRACKER.items():
         vals = d["values"].float() * loss_scale
         if total_loss_dict is not None:

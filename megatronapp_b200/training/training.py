@@ -295,6 +295,18 @@ def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scal
             total_loss_dict[k] = total_loss_dict.get(k, 0.0) + fv
             got_nan = got_nan or not math.isfinite(fv)
     total_loss_dict[nan] = total_loss_dict.get(nan, 0) + int(got_nan)
+    # auxiliary losses that never reach the loss function's report: MoE load balancing / z-loss (per layer, summed over
+    # micro-batches) and the multi-token-prediction heads (reference training_log: track_moe_metrics, track_mtp_metrics)
+    if args.num_experts is not None:
+        from ..moe.moe_utils import track_moe_metrics
+
+        track_moe_metrics(1.0 / get_num_microbatches(), iteration, writer, None, None if skipped_iter else total_loss_dict,
+                          getattr(args, "moe_per_layer_logging", False))
+    if getattr(args, "mtp_num_layers", None):
+        from ..transformer.multi_token_prediction import MTPLossLoggingHelper
+
+        MTPLossLoggingHelper.track_mtp_metrics(1.0 / get_num_microbatches(), iteration, writer,
+                                               None if skipped_iter else total_loss_dict)
     batch_size = args.micro_batch_size * args.effective_data_parallel_size * get_num_microbatches()
     if writer and iteration % args.tensorboard_log_interval == 0:
         writer.add_scalar("learning-rate", learning_rate, iteration)
