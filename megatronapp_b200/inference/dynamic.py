@@ -13,6 +13,8 @@ request's slots (padded over requests), so admission, retirement and preemption 
 from __future__ import annotations
 
 import itertools
+import queue
+import threading
 import time
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -185,6 +187,11 @@ class DynamicInferenceEngine:
         self.num_preemptions = 0
         self.steps = 0
         self.padded_vocab_size = None
+        # continuous serving: requests from concurrent clients join the running batch between two steps
+        self._inbox: "queue.Queue" = queue.Queue()
+        self._done: Dict[str, threading.Event] = {}
+        self._loop_thread: Optional[threading.Thread] = None
+        self._stop = False
 
     # -- API -----------------------------------------------------------------------
     def add_request(self, prompt: str, sampling_params: Optional[SamplingParams] = None,
@@ -219,8 +226,75 @@ class DynamicInferenceEngine:
     def controller(self):            # the servers reach the tokenizer through engine.controller.tokenizer
         return self
 
+    # -- continuous serving ------------------------------------------------------------------
+    def serving(self) -> bool:
+        return self._loop_thread is not None
+
+    def start_background_loop(self):
+        """Rank 0 of a server: run ``run_loop`` in a thread; ``generate`` then enqueues instead of driving the engine."""
+        self._loop_thread = threading.Thread(target=self.run_loop, daemon=True)
+        self._loop_thread.start()
+
+    def stop_loop(self):
+        self._stop = True
+        if self._loop_thread is not None and self._loop_thread is not threading.current_thread():
+            self._loop_thread.join(timeout=30)
+        self._loop_thread = None
+
+    def run_loop(self):
+        """The serving loop, executed by EVERY model-parallel rank in lockstep: rank 0 drains the inbox and broadcasts
+        the newly arrived requests, all ranks admit them in the same order (hence the same request ids) and take one
+        engine step.  Requests therefore join and leave the batch at token granularity across HTTP clients."""
+        import torch.distributed as dist
+
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        rank0 = not multi or dist.get_rank() == 0
+        while True:
+            new = []
+            if rank0:
+                try:
+                    block = not self.has_unfinished_requests()
+                    new.append(self._inbox.get(timeout=0.005) if block else self._inbox.get_nowait())
+                    while True:
+                        new.append(self._inbox.get_nowait())
+                except queue.Empty:
+                    pass
+            box = [[(p, sp, toks) for p, sp, toks, *_ in new], self._stop]
+            if multi:
+                dist.broadcast_object_list(box, src=0)
+            if box[1]:
+                return
+            for i, (prompt, sp, toks) in enumerate(box[0]):
+                rid = self.add_request(prompt, sp, toks)
+                if rank0:
+                    new[i][3].append(rid)                      # hand the id back to the submitting thread
+                    self._done[rid] = new[i][4]
+            if self.has_unfinished_requests():
+                for r in self.step():
+                    ev = self._done.pop(r.request_id, None)
+                    if ev is not None:
+                        ev.set()
+
+    def submit(self, prompts: List[str], sampling_params: Optional[SamplingParams], token_lists: List[List[int]],
+               timeout: float = 600.0) -> List[InferenceRequest]:
+        tickets = []
+        for p, toks in zip(prompts, token_lists):
+            ids, ev = [], threading.Event()
+            self._inbox.put((p, sampling_params or SamplingParams(), toks, ids, ev))
+            tickets.append((ids, ev))
+        out = []
+        for ids, ev in tickets:
+            if not ev.wait(timeout):
+                raise TimeoutError("generation did not finish in time")
+            out.append(self.completed[ids[0]])
+        return out
+
     def generate(self, prompts: List[str], sampling_params: Optional[SamplingParams] = None,
                  add_BOS: bool = False) -> List[InferenceRequest]:
+        if self.serving() and threading.current_thread() is not self._loop_thread:
+            b = getattr(self.tokenizer, "bos", None) if add_BOS else None
+            toks = [([b] if b is not None else []) + self.tokenizer.tokenize(p) for p in prompts]
+            return self.submit(prompts, sampling_params, toks)
         bos = getattr(self.tokenizer, "bos", None) if add_BOS else None
         if bos is not None:
             ids = [self.add_request(p, sampling_params, [bos] + self.tokenizer.tokenize(p)) for p in prompts]

@@ -108,10 +108,19 @@ def run_generate(engine: StaticInferenceEngine, req: dict, announce: bool = True
                             num_tokens_to_generate=int(req.get("tokens_to_generate", 64)))
     if req.get("random_seed") is not None:
         torch.manual_seed(int(req["random_seed"]))
+    if getattr(engine, "serving", lambda: False)():
+        # continuous batching: the engine's own loop (run by every rank) admits this request into the running batch;
+        # concurrent HTTP clients share steps instead of queueing behind a lock
+        results = engine.generate(req["prompts"], params, add_BOS=bool(req.get("add_BOS", False)))
+        return _format(results, params)
     with _LOCK:                                   # one generation at a time; the announcement is part of it
         if announce:
             _announce(_GENERATE, req)
         results = engine.generate(req["prompts"], params, add_BOS=bool(req.get("add_BOS", False)))
+    return _format(results, params)
+
+
+def _format(results, params):
     out = {"text": [r.prompt + r.generated_text for r in results],
            "tokens": [r.prompt_tokens + r.generated_tokens.tolist() for r in results]}
     if params.return_log_probs:

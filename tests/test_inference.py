@@ -266,3 +266,42 @@ def test_vlm_generation_with_kv_cache_matches_full_forward():
                 logits = m(images[i:i + 1], ids, torch.arange(len(toks)).unsqueeze(0), None)
             toks.append(int(logits[0, -1, :128].argmax()))
         assert toks[len(r.prompt_tokens):] == r.generated_tokens.tolist()
+
+
+def test_dynamic_engine_serves_concurrent_clients_in_shared_steps(engine):
+    """Two HTTP clients at once: their requests are admitted into ONE running batch (fewer engine steps than the sum of
+    their standalone runs) and each gets exactly its standalone greedy continuation."""
+    import threading
+
+    from megatronapp_b200.inference import DynamicInferenceEngine
+    from megatronapp_b200.inference.server import MegatronServer
+
+    eng, model = engine
+    sp = SamplingParams(top_k=1, num_tokens_to_generate=12)
+    prompts = ["5 9 23 7 8 1 2 3", "11 3 40 41"]
+    ref = [eng.generate([p], sp)[0].generated_tokens.tolist() for p in prompts]
+    dyn = DynamicInferenceEngine(model, NullTokenizer(127), max_sequence_length=64, num_blocks=32, block_size=4,
+                                 max_tokens_per_step=4, max_requests=4)
+    dyn.start_background_loop()
+    srv = MegatronServer(dyn)
+    srv.run(port=18815, block=False)
+    time.sleep(0.3)
+    outs = [None, None]
+
+    def client(i):
+        body = json.dumps({"prompts": [prompts[i]], "tokens_to_generate": 12, "top_k": 1}).encode()
+        req = urllib.request.Request("http://127.0.0.1:18815/api", data=body, method="PUT",
+                                     headers={"Content-Type": "application/json"})
+        outs[i] = json.loads(urllib.request.urlopen(req, timeout=120).read())
+
+    try:
+        ts = [threading.Thread(target=client, args=(i,)) for i in range(2)]
+        [t.start() for t in ts]
+        [t.join(timeout=120) for t in ts]
+        for i, p in enumerate(prompts):
+            assert outs[i]["tokens"][0][len(p.split()):] == ref[i]
+        standalone_steps = sum(-(-len(p.split()) // 4) + len(r) - 1 for p, r in zip(prompts, ref))
+        assert dyn.steps < standalone_steps                        # the two requests really overlapped
+    finally:
+        srv.shutdown()
+        dyn.stop_loop()

@@ -30,6 +30,11 @@ def main():
         engine = DynamicInferenceEngine.from_args(model[0], tok, args, core_transformer_config_from_args(args))
     else:
         engine = StaticInferenceEngine(TextGenerationController(wrapper, tok), args.inference_max_requests)
+    if args.inference_dynamic_batching:
+        # continuous batching: every rank runs the engine's serving loop in lockstep (rank 0 in a thread next to HTTP)
+        if args.rank != 0:
+            return engine.run_loop()
+        engine.start_background_loop()
     if args.rank != 0:                       # model-parallel peers follow rank 0's announcements
         from megatronapp_b200.inference.server import serve_worker_ranks
 
