@@ -136,7 +136,8 @@ class _Range:
 class _BufferState:
     """Optimizer state for one ParamAndGradBuffer (full, or this rank's shards under ZeRO-1)."""
 
-    def __init__(self, buf: ParamAndGradBuffer, ranges: List[_Range], sharded: bool, offload_fraction: float = 0.0):
+    def __init__(self, buf: ParamAndGradBuffer, ranges: List[_Range], sharded: bool, offload_fraction: float = 0.0,
+                 moment_dtypes=(torch.float32, torch.float32)):
         self.buf, self.sharded = buf, sharded
         dev = buf.param_data.device
         if sharded:
@@ -152,8 +153,10 @@ class _BufferState:
         self.master = torch.empty(off, dtype=torch.float32, device=dev)
         for (s, e), o in zip(self.segments, self.seg_offsets):
             self.master[o:o + e - s].copy_(buf.param_data[s:e])
-        self.exp_avg = torch.zeros_like(self.master)
-        self.exp_avg_sq = torch.zeros_like(self.master)
+        # precision-aware optimizer: the moments may be stored in 16 bit (half the optimizer-state memory); the step
+        # up-casts a slice, runs the fp32 Adam arithmetic and stores it back
+        self.exp_avg = torch.zeros_like(self.master, dtype=moment_dtypes[0])
+        self.exp_avg_sq = torch.zeros_like(self.master, dtype=moment_dtypes[1])
         # --optimizer-cpu-offload: the tail [cpu_from, local_numel) of master / moments lives in (pinned) host memory and
         # is stepped on the CPU (reference optimizer/cpu_offloading/hybrid_optimizer.py: HybridDeviceOptimizer)
         self.cpu_from = off
@@ -189,6 +192,16 @@ class _BufferState:
         dev_part.copy_(value[: dev_part.numel()])
         if cpu_part is not None:
             cpu_part.copy_(value[dev_part.numel():])
+
+
+def _adam(master, m, v, grad, p16, lr, cfg, wd, gs, step):
+    """One fused-Adam launch on a slice; 16-bit moments are up-cast around the fp32 kernel and stored back."""
+    low = m.dtype != torch.float32 or v.dtype != torch.float32
+    m32, v32 = (m.float(), v.float()) if low else (m, v)
+    ops.adam_step(master, m32, v32, grad, p16, lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, wd, gs, step)
+    if low:
+        m.copy_(m32)
+        v.copy_(v32)
 
 
 class MegatronOptimizer:
@@ -231,7 +244,9 @@ class MegatronOptimizer:
                     else:
                         merged.append(_Range(r.start, r.end, r.wd_mult, r.lr_mult))
                 self.states.append(_BufferState(buf, merged, self.sharded and _is_real_group(buf.group),
-                                                config.optimizer_offload_fraction if config.optimizer_cpu_offload else 0.0))
+                                                config.optimizer_offload_fraction if config.optimizer_cpu_offload else 0.0,
+                                                (config.exp_avg_dtype, config.exp_avg_sq_dtype)
+                                                if config.use_precision_aware_optimizer else (torch.float32, torch.float32)))
         if config.fp16:
             if config.loss_scale:
                 self.grad_scaler = ConstantGradScaler(config.loss_scale)
@@ -353,14 +368,13 @@ class MegatronOptimizer:
                     grad = grad.float()
                 if lo >= st.cpu_from:                      # offloaded slice: D2H grad, CPU Adam, H2D parameter
                     c = lo - st.cpu_from
-                    ops.adam_step(st.master_cpu[c:c + n], st.exp_avg_cpu[c:c + n], st.exp_avg_sq_cpu[c:c + n],
-                                  grad.to("cpu", non_blocking=False), None, lr, cfg.adam_beta1, cfg.adam_beta2,
-                                  cfg.adam_eps, wd, gs, self.step_count)
+                    _adam(st.master_cpu[c:c + n], st.exp_avg_cpu[c:c + n], st.exp_avg_sq_cpu[c:c + n],
+                          grad.to("cpu", non_blocking=False), None, lr, cfg, wd, gs, self.step_count)
                     buf.param_data[a:b].copy_(st.master_cpu[c:c + n], non_blocking=True)
                     continue
                 p16 = buf.param_data[a:b] if buf.param_dtype != torch.float32 else None
-                ops.adam_step(st.master[lo:lo + n], st.exp_avg[lo:lo + n], st.exp_avg_sq[lo:lo + n], grad, p16,
-                              lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, wd, gs, self.step_count)
+                _adam(st.master[lo:lo + n], st.exp_avg[lo:lo + n], st.exp_avg_sq[lo:lo + n], grad, p16, lr, cfg, wd, gs,
+                      self.step_count)
                 if p16 is None:
                     buf.param_data[a:b].copy_(st.master[lo:lo + n])
         if self.sharded:

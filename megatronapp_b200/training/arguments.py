@@ -575,9 +575,12 @@ def _vocab_size_with_padding(orig: int, args) -> int:
 
 _UNSUPPORTED = (
     # (predicate on args, message) -- flags that are parsed for CLI compatibility but would silently change nothing
-    (lambda a: a.use_precision_aware_optimizer and any(getattr(a, k) != "fp32" for k in
-                                                       ("main_grads_dtype", "main_params_dtype", "exp_avg_dtype", "exp_avg_sq_dtype")),
-     "--use-precision-aware-optimizer with non-fp32 state dtypes is not implemented (the fused Adam kernel keeps fp32 state)"),
+    (lambda a: any(getattr(a, k) != "fp32" for k in ("main_grads_dtype", "main_params_dtype")),
+     "--main-grads-dtype / --main-params-dtype other than fp32 are not implemented (gradient accumulation and master "
+     "weights stay fp32; the Adam moments may be fp16 / bf16 with --use-precision-aware-optimizer)"),
+    (lambda a: "fp8" in (a.exp_avg_dtype, a.exp_avg_sq_dtype), "fp8 Adam moments are not implemented (use fp16 / bf16)"),
+    (lambda a: not a.use_precision_aware_optimizer and (a.exp_avg_dtype != "fp32" or a.exp_avg_sq_dtype != "fp32"),
+     "--exp-avg-dtype / --exp-avg-sq-dtype need --use-precision-aware-optimizer"),
     (lambda a: a.init_model_with_meta_device, "--init-model-with-meta-device is not implemented"),
     (lambda a: a.external_cuda_graph, "--external-cuda-graph is not implemented; use --enable-cuda-graph"),
     (lambda a: a.pipeline_model_parallel_comm_backend == "ucc", "the UCC pipeline backend is not available; p2p runs on NCCL/gloo channels"),

@@ -182,6 +182,10 @@ def setup_model_and_optimizer(model_provider_func, model_type=None, no_wd_decay_
     for f in dataclasses.fields(OptimizerConfig):
         if hasattr(args, f.name):
             kw[f.name] = getattr(args, f.name)
+    names = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+    for k in ("main_grads_dtype", "main_params_dtype", "exp_avg_dtype", "exp_avg_sq_dtype"):
+        if isinstance(kw.get(k), str):
+            kw[k] = names[kw[k]]
     config = OptimizerConfig(**kw)
     config.timers = get_timers()
     optimizer = get_megatron_optimizer(config, model, no_wd_decay_cond, scale_lr_cond, lr_mult)

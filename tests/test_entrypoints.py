@@ -28,6 +28,8 @@ CASES = {
     "gpt_heterogeneous": ["pretrain_gpt.py", "--heterogeneous-layers-config-encoded-json",
                           '{"block_configs": [{"attention": {"n_heads_in_group": 2}, "ffn": {"ffn_mult": 1.5}}, '
                           '{"attention": {"no_op": true}, "ffn": {"intermediate_size": 48}}]}'],
+    "gpt_bf16_moments_offload": ["pretrain_gpt.py", "--use-precision-aware-optimizer", "--exp-avg-dtype", "bf16", "--exp-avg-sq-dtype",
+                                 "bf16", "--optimizer-cpu-offload", "--optimizer-offload-fraction", "0.5"],
     "bert": ["pretrain_bert.py"],
     "bert_legacy": ["pretrain_bert.py", "--use-legacy-models"],
     "t5": ["pretrain_t5.py", "--encoder-seq-length", "32", "--decoder-seq-length", "16"],
