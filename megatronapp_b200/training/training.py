@@ -420,12 +420,41 @@ def evaluate_and_print_results(prefix, forward_step_func, data_iterator, model, 
     print_rank_last("-" * (len(s) + 1))
 
 
+def append_to_progress_log(line: str, barrier: bool = True):
+    """``--log-progress``: one tab-separated line per event in ``<save>/progress.txt`` (reference training.py:398-440)."""
+    args = get_args()
+    if not getattr(args, "log_progress", False) or args.save is None:
+        return
+    if barrier and dist.is_initialized():
+        dist.barrier()
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        os.makedirs(args.save, exist_ok=True)
+        job = os.getenv("SLURM_JOB_ID", "") or os.getenv("TORCHELASTIC_RUN_ID", "") or str(os.getpid())
+        with open(os.path.join(args.save, "progress.txt"), "a") as f:
+            f.write(f"{time.strftime('%Y-%m-%d %H:%M:%S')}\tJob ID: {job}\t# GPUs: {args.world_size}\t{line}\n")
+
+
+def compute_throughputs_and_append_to_progress_log(iteration, num_floating_point_operations_so_far):
+    """Job throughput (since this launch) in TFLOP/s/GPU from the analytic FLOP model, logged at every checkpoint."""
+    args = get_args()
+    if not getattr(args, "log_progress", False) or args.save is None:
+        return
+    done = num_floating_point_operations_so_far - getattr(args, "_flops_at_job_start", 0)
+    tput = done / (max(time.time() - _TRAIN_START_TIME, 1e-9) * 1e12 * args.world_size)
+    tokens = args.consumed_train_samples * args.seq_length
+    append_to_progress_log(f"{'Saving async checkpoint' if args.async_save else 'Saved checkpoint'}\tIteration: {iteration}\t"
+                           f"Job throughput: {tput:.1f} TFLOP/s/GPU\t"
+                           f"Floating-point operations: {num_floating_point_operations_so_far:.2e}\t"
+                           f"Tokens (in billions): {tokens / 1e9:.2f}")
+
+
 def save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far):
     timers = get_timers()
     timers("save-checkpoint", log_level=0).start(barrier=True)
     checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far)
     timers("save-checkpoint").stop(barrier=True)
     timers.log(["save-checkpoint"])
+    compute_throughputs_and_append_to_progress_log(iteration, num_floating_point_operations_so_far)
 
 
 def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_iterator, valid_data_iterator,
@@ -723,8 +752,19 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
 
         install_fbd_schedule(args)
     timers("model-and-optimizer-setup", log_level=0).start(barrier=True)
+    append_to_progress_log("Starting job")
     model, optimizer, scheduler = setup_model_and_optimizer(model_provider, model_type)
     timers("model-and-optimizer-setup").stop()
+    args._flops_at_job_start = args.num_floating_point_operations_so_far
+    if getattr(args, "ckpt_convert_format", None):
+        # --ckpt-convert-format F --ckpt-convert-save DIR: re-save the just-loaded checkpoint in another format and stop
+        # (reference training.py: "Convert checkpoint format" block)
+        if not args.ckpt_convert_save:
+            raise ValueError("--ckpt-convert-format needs --ckpt-convert-save")
+        args.ckpt_format, args.save = args.ckpt_convert_format, args.ckpt_convert_save
+        checkpointing.save_checkpoint(args.iteration, model, optimizer, scheduler, args.num_floating_point_operations_so_far)
+        print_rank_0(f"> converted checkpoint: {args.load} -> {args.save} ({args.ckpt_format})")
+        return model, optimizer
     config = unwrap_model(model[0]).config
     timers("train/valid/test-data-iterators-setup", log_level=0).start(barrier=True)
     if args.virtual_pipeline_model_parallel_size is not None:

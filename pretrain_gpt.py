@@ -31,6 +31,23 @@ def model_provider(pre_process=True, post_process=True):
 
         return LegacyGPTModel(config, num_tokentypes=0, parallel_output=True, pre_process=pre_process,
                               post_process=post_process)
+    if args.spec:
+        # --spec module.path [function]: user-supplied layer / block spec (reference pretrain_gpt.py:96-97)
+        from megatronapp_b200.transformer.spec_utils import import_module
+
+        obj = import_module(tuple(args.spec) if len(args.spec) > 1 else tuple(args.spec[0].rsplit(".", 1)))
+        spec = obj
+        if callable(obj) and not hasattr(obj, "module"):            # a factory rather than a ModuleSpec instance
+            try:
+                spec = obj()
+            except TypeError:
+                spec = obj(config)
+        return GPTModel(config=config, transformer_layer_spec=spec, vocab_size=args.padded_vocab_size,
+                        max_sequence_length=args.max_position_embeddings, pre_process=pre_process, post_process=post_process,
+                        fp16_lm_cross_entropy=args.fp16_lm_cross_entropy, parallel_output=True,
+                        share_embeddings_and_output_weights=not args.untie_embeddings_and_output_weights,
+                        position_embedding_type=args.position_embedding_type, rotary_percent=args.rotary_percent,
+                        rotary_base=args.rotary_base)
     het = getattr(args, "heterogeneous_layers_config_path", None) or getattr(args, "heterogeneous_layers_config_encoded_json", None)
     if het:
         import json

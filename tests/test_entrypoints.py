@@ -30,6 +30,7 @@ CASES = {
                           '{"attention": {"no_op": true}, "ffn": {"intermediate_size": 48}}]}'],
     "gpt_bf16_moments_offload": ["pretrain_gpt.py", "--use-precision-aware-optimizer", "--exp-avg-dtype", "bf16", "--exp-avg-sq-dtype",
                                  "bf16", "--optimizer-cpu-offload", "--optimizer-offload-fraction", "0.5"],
+    "gpt_user_spec": ["pretrain_gpt.py", "--spec", "megatronapp_b200.models.gpt.gpt_layer_specs", "get_gpt_layer_local_spec"],
     "bert": ["pretrain_bert.py"],
     "bert_legacy": ["pretrain_bert.py", "--use-legacy-models"],
     "t5": ["pretrain_t5.py", "--encoder-seq-length", "32", "--decoder-seq-length", "16"],
@@ -283,3 +284,26 @@ def test_example_scripts_only_use_flags_that_exist():
             if flag not in known and flag not in declared and flag not in launcher:
                 bad.setdefault(os.path.relpath(f, ROOT), []).append(flag)
     assert not bad, bad
+
+
+def test_checkpoint_format_conversion_and_progress_log(tmp_path):
+    """``--ckpt-convert-format`` re-saves a per-rank checkpoint as a sharded one (and stops); ``--log-progress`` writes the
+    job start and every checkpoint with its throughput to ``<save>/progress.txt``."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="",
+               OMP_NUM_THREADS="2")
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *COMMON, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+        return p.stdout + p.stderr
+
+    run("--save", a, "--save-interval", "3", "--ckpt-format", "torch", "--log-progress")
+    lines = open(os.path.join(a, "progress.txt")).read().strip().split("\n")
+    assert "Starting job" in lines[0] and "Saved checkpoint\tIteration: 3" in lines[-1] and "TFLOP/s/GPU" in lines[-1]
+    out = run("--load", a, "--ckpt-format", "torch", "--ckpt-convert-format", "torch_dist", "--ckpt-convert-save", b)
+    assert "converted checkpoint" in out and "iteration        1/" not in out          # converts and stops, no training
+    assert os.path.exists(os.path.join(b, "iter_0000003", "metadata.json"))
+    out = run("--load", b, "--ckpt-format", "torch_dist", "--train-iters", "4", "--override-opt_param-scheduler")
+    assert "successfully loaded checkpoint" in out and re.search(r"iteration\s+4/\s+4 \|", out)
