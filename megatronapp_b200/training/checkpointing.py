@@ -130,12 +130,34 @@ def _to_cpu(obj):
     return obj
 
 
+def non_persistent_dir(args) -> str:
+    """Where ``--non-persistent-ckpt-type global`` checkpoints go: frequent, overwritten-in-place safety checkpoints next
+    to (not instead of) the persistent ones (reference checkpointing.py: ``non_persistent_ckpt``)."""
+    return args.non_persistent_global_ckpt_dir or os.path.join(args.save or args.load, "non_persistent")
+
+
 def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far=0,
-                    args=None, checkpointing_context=None):
+                    args=None, checkpointing_context=None, non_persistent_ckpt: bool = False):
     if args is None:
         from .global_vars import get_args
 
         args = get_args()
+    if non_persistent_ckpt:
+        # same writer, different root; once the new one is complete the previous non-persistent iteration is removed
+        import copy
+        import shutil
+
+        npd = non_persistent_dir(args)
+        old = None
+        tr = get_checkpoint_tracker_filename(npd)
+        if os.path.isfile(tr):
+            old = read_metadata(tr)[0]
+        a2 = copy.copy(args)
+        a2.save, a2.async_save = npd, False
+        save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far, a2)
+        if old is not None and old != iteration and (not dist.is_initialized() or dist.get_rank() == 0):
+            shutil.rmtree(get_checkpoint_name(npd, old, return_base_dir=True), ignore_errors=True)
+        return
     model = model if isinstance(model, (list, tuple)) else [model]
     rank = dist.get_rank() if dist.is_initialized() else 0
     base = get_checkpoint_name(args.save, iteration, return_base_dir=True)
@@ -210,6 +232,15 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
         args = get_args()
     load_dir = getattr(args, load_arg)
     model = model if isinstance(model, (list, tuple)) else [model]
+    if load_dir and getattr(args, "non_persistent_ckpt_type", None) == "global" and not getattr(args, "ckpt_step", None):
+        # resume from whichever is newer: the last persistent checkpoint or the non-persistent safety checkpoint
+        npd = args.non_persistent_global_ckpt_dir or os.path.join(load_dir, "non_persistent")
+        tr_np, tr_p = get_checkpoint_tracker_filename(npd), get_checkpoint_tracker_filename(load_dir)
+        if os.path.isfile(tr_np):
+            it_np = read_metadata(tr_np)[0]
+            it_p = read_metadata(tr_p)[0] if os.path.isfile(tr_p) else -1
+            if it_np > it_p:
+                load_dir = npd
     tracker = get_checkpoint_tracker_filename(load_dir) if load_dir else None
     if not load_dir or not os.path.isfile(tracker):
         if getattr(args, "exit_on_missing_checkpoint", False):

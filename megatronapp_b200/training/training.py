@@ -569,6 +569,14 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             if check_adlr_autoresume_termination(iteration, model, optimizer, opt_param_scheduler, _save):
                 exit_flag = True
                 break
+        if (args.save and getattr(args, "non_persistent_save_interval", None) and not saved
+                and iteration % args.non_persistent_save_interval == 0
+                and not (args.save_interval and iteration % args.save_interval == 0)):
+            if args.non_persistent_ckpt_type != "global":
+                raise NotImplementedError("only --non-persistent-ckpt-type global is implemented")
+            timers("interval-time").stop()
+            checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, nflops, non_persistent_ckpt=True)
+            timers("interval-time", log_level=0).start(barrier=True)
         if args.save and args.save_interval and iteration % args.save_interval == 0:
             timers("interval-time").stop()
             save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, nflops)

@@ -307,3 +307,31 @@ def test_checkpoint_format_conversion_and_progress_log(tmp_path):
     assert os.path.exists(os.path.join(b, "iter_0000003", "metadata.json"))
     out = run("--load", b, "--ckpt-format", "torch_dist", "--train-iters", "4", "--override-opt_param-scheduler")
     assert "successfully loaded checkpoint" in out and re.search(r"iteration\s+4/\s+4 \|", out)
+
+
+def test_non_persistent_checkpoints_cover_the_gap_between_persistent_ones(tmp_path):
+    """Persistent checkpoint every 4 iterations, a non-persistent ("global") one every iteration: after a crash at
+    iteration 5 the job resumes from the non-persistent iteration-5 state, not from iteration 4."""
+    import shutil
+
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="",
+               OMP_NUM_THREADS="2")
+    base = COMMON + ["--train-iters", "6", "--attention-dropout", "0", "--hidden-dropout", "0", "--lr", "1e-2",
+                     "--lr-decay-iters", "100"]
+    ck = str(tmp_path / "ck")
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *base, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-3000:]
+        return out, re.findall(r"\\] iteration\\s+(\\d+)/.*?lm loss: ([0-9.E+\\-]+)", out)
+
+    _, straight = run()
+    run("--save", ck, "--save-interval", "4", "--non-persistent-save-interval", "1", "--non-persistent-ckpt-type", "global",
+        "--exit-interval", "5")
+    assert sorted(os.listdir(os.path.join(ck, "non_persistent"))) == ["iter_0000005", "latest_checkpointed_iteration.txt"]
+    shutil.rmtree(os.path.join(ck, "iter_0000005"))                  # "crash": the exit checkpoint never made it to disk
+    open(os.path.join(ck, "latest_checkpointed_iteration.txt"), "w").write("4")
+    out, resumed = run("--load", ck, "--non-persistent-ckpt-type", "global")
+    assert "non_persistent at iteration 5" in out and resumed == straight[5:]
