@@ -87,7 +87,7 @@ def clip_grad_norm_model_parallel(params, max_norm: float) -> float:
 def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: int = 16, lr: float = 2e-5,
              weight_decay: float = 0.01, warmup_fraction: float = 0.1, clip_grad: float = 1.0,
              forward_step: Callable = classification_forward_step, end_of_epoch_callback: Optional[Callable] = None,
-             log_interval: int = 50, sampler_seed: int = 1234):
+             log_interval: int = 50, sampler_seed: int = 1234, evaluate: Optional[Callable] = None):
     """Single-replica (or DDP-sharded through the sampler) finetuning loop; returns per-epoch metrics."""
     import torch.distributed as dist
 
@@ -129,7 +129,7 @@ def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: i
                 if not dist.is_initialized() or dist.get_rank() == 0:
                     print(f" epoch {epoch} step {step}/{total_steps} | loss {running / log_interval:.4f} | lr {sched.get_last_lr()[0]:.3e}", flush=True)
                 running = 0.0
-        metrics = calculate_correct_answers(model, vloader)
+        metrics = (evaluate or calculate_correct_answers)(model, vloader)
         metrics["epoch"] = epoch
         history.append(metrics)
         if end_of_epoch_callback is not None:

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def get_tasks_args(parser):
     g = parser.add_argument_group("tasks")
     g.add_argument("--task", type=str, required=True,
-                   help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE | RETRIEVER-EVAL (MSDP-*: tasks/msdp/main.py)")
+                   help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE | RETRIEVER-EVAL | VISION-CLASSIFY (MSDP-*: tasks/msdp/main.py)")
     g.add_argument("--qa-data-test", type=str, default=None, help="NQ-open style TSV: question \\t [answers]")
     g.add_argument("--faiss-match", type=str, default="string", choices=["regex", "string"])
     g.add_argument("--faiss-topk-retrievals", type=int, default=100)
@@ -34,6 +34,8 @@ if __name__ == "__main__":
         from tasks.glue.finetune import main
     elif args.task == "RACE":
         from tasks.race.finetune import main
+    elif args.task == "VISION-CLASSIFY":
+        from tasks.vision.classification import main
     elif args.task == "RETRIEVER-EVAL":
         def main():
             from megatronapp_b200.training import checkpointing

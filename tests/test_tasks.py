@@ -250,3 +250,34 @@ def test_orqa_evaluator_retrieves_with_biencoder():
     acc = ev.evaluate(["passage number lemon about lemon", "passage number harbor about harbor"], [["lemon"], ["nowhere"]], docs,
                       report_topk=(1, 3))
     assert acc[1] == 50.0 and acc[3] == 50.0
+
+
+def test_vision_classification_finetune_learns_from_an_image_folder(tmp_path):
+    import numpy as np
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.vision.vit_classification import VitClassificationModel
+    from megatronapp_b200.parallel import state as ps
+    from tasks.finetune_utils import finetune
+    from tasks.vision.classification import ImageFolderTensors, top1, vision_forward_step
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+    rng = np.random.default_rng(0)
+    for split in ("train", "val"):
+        for c, mean in (("bright", 1.5), ("dark", -1.5)):
+            os.makedirs(tmp_path / split / c)
+            for i in range(8 if split == "train" else 4):
+                np.save(tmp_path / split / c / f"{i}.npy", (rng.standard_normal((3, 20, 20)) * 0.3 + mean).astype(np.float32))
+    train = ImageFolderTensors(str(tmp_path / "train"), 16, 16)
+    valid = ImageFolderTensors(str(tmp_path / "val"), 16, 16, train.classes)
+    assert train.classes == ["bright", "dark"] and len(train) == 16 and train[0]["image"].shape == (3, 16, 16)   # resized
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch", params_dtype=torch.float32)
+    model = VitClassificationModel(cfg, 2, img_h=16, img_w=16, patch_dim=4, finetune=True)
+    vloader = torch.utils.data.DataLoader(valid, batch_size=4)
+    hist = finetune(model, train, valid, epochs=6, batch_size=4, lr=5e-3, forward_step=vision_forward_step,
+                    evaluate=lambda m, _l: top1(m, vloader), warmup_fraction=0.0)
+    assert hist[-1]["total"] == 8 and hist[-1]["accuracy"] == 1.0
