@@ -1,4 +1,4 @@
 from .core import (GPTInferenceWrapper, InferenceParams, InferenceRequest, SamplingParams,  # noqa: F401
-                   Scheduler, StaticInferenceContext, StaticInferenceEngine, Status, TextGenerationController,
+                   Scheduler, StaticInferenceContext, StaticInferenceEngine, Status, T5InferenceWrapper, TextGenerationController,
                    VLMInferenceWrapper, sample_from_logits)
 from .dynamic import BlockAllocator, DynamicInferenceContext, DynamicInferenceEngine  # noqa: F401

@@ -286,6 +286,59 @@ class VLMInferenceWrapper(GPTInferenceWrapper):
         return logits
 
 
+class T5InferenceWrapper(GPTInferenceWrapper):
+    """Encoder-decoder generation (reference ``model_inference_wrappers/t5/t5_inference_wrapper.py``): the prompt is the
+    ENCODER input; it is encoded once per batch and cached, and the decoder -- started from ``decoder_start_token`` --
+    is re-run on the tokens generated so far at every step (cross attention to the cached encoder states, causal self
+    attention), which needs no decoder KV cache and keeps the model code untouched."""
+
+    def __init__(self, model, max_batch_size: int = 8, max_sequence_length: int = 512, padded_vocab_size=None,
+                 decoder_start_token: int = 0, pad_token: int = 0):
+        super().__init__(model, max_batch_size, max_sequence_length, padded_vocab_size)
+        self.decoder_start_token, self.pad_token = decoder_start_token, pad_token
+        self._enc = self._enc_mask = None
+
+    def prep_model_for_inference(self, prompts_tokens: torch.Tensor):
+        super().prep_model_for_inference(prompts_tokens)
+        self._enc = self._enc_mask = None
+
+    @torch.no_grad()
+    def encode(self, encoder_tokens: torch.Tensor):
+        pad = (encoder_tokens != self.pad_token).float()
+        self._enc_mask = pad
+        self._enc = self.model(encoder_tokens, None, pad.unsqueeze(1) * pad.unsqueeze(2), None, None,
+                               output_encoder_hidden_only=True)
+        return self._enc
+
+    @torch.no_grad()
+    def decode_step(self, decoder_tokens: torch.Tensor) -> torch.Tensor:
+        """``decoder_tokens [b, t]`` (starting with ``decoder_start_token``) -> next-token logits ``[b, V]``."""
+        b, t = decoder_tokens.shape
+        dm = torch.tril(torch.ones(t, t, device=decoder_tokens.device)).unsqueeze(0).expand(b, -1, -1)
+        edm = self._enc_mask.unsqueeze(1).expand(b, t, -1)
+        logits = self.model(None, decoder_tokens, None, dm, edm, encoder_hidden_states=self._enc)
+        return gather_full_vocab(logits, self.padded_vocab_size)[:, -1]
+
+    @torch.no_grad()
+    def generate(self, encoder_tokens: torch.Tensor, params: "SamplingParams", eos_token: Optional[int] = None):
+        """Greedy / sampled decoding for a batch of encoder inputs; returns ``[b, <= num_tokens_to_generate]`` token ids
+        (rows stop at ``eos_token``, the remainder is padded with it)."""
+        self.model.eval()
+        self.encode(encoder_tokens)
+        b, dev = encoder_tokens.shape[0], encoder_tokens.device
+        dec = torch.full((b, 1), self.decoder_start_token, dtype=torch.long, device=dev)
+        done = torch.zeros(b, dtype=torch.bool, device=dev)
+        for _ in range(params.num_tokens_to_generate):
+            nxt = sync_sampled_tokens(sample_from_logits(self.decode_step(dec), params), b, dev)
+            if eos_token is not None:
+                nxt = torch.where(done, torch.full_like(nxt, eos_token), nxt)
+                done |= nxt == eos_token
+            dec = torch.cat([dec, nxt.unsqueeze(1)], dim=1)
+            if eos_token is not None and bool(done.all()):
+                break
+        return dec[:, 1:]
+
+
 class TextGenerationController:
     def __init__(self, inference_wrapped_model: GPTInferenceWrapper, tokenizer):
         self.inference_wrapped_model = inference_wrapped_model

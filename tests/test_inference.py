@@ -305,3 +305,38 @@ def test_dynamic_engine_serves_concurrent_clients_in_shared_steps(engine):
     finally:
         srv.shutdown()
         dyn.stop_loop()
+
+
+def test_t5_encoder_decoder_generation():
+    """Encode once, decode step by step: equals calling the full model on the growing decoder prefix."""
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.inference import T5InferenceWrapper
+    from megatronapp_b200.models.T5 import T5Model, get_t5_decoder_block_spec, get_t5_encoder_block_spec
+    from megatronapp_b200.parallel import state as ps
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, kernel_backend="torch",
+                            use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0, params_dtype=torch.float32)
+    m = T5Model(cfg, cfg, get_t5_encoder_block_spec(2), get_t5_decoder_block_spec(2), vocab_size=64, max_sequence_length=32).eval()
+    enc = torch.randint(1, 64, (2, 10))
+    enc[1, 7:] = 0                                                   # padding in the second prompt
+    w = T5InferenceWrapper(m, decoder_start_token=1, pad_token=0, padded_vocab_size=64)
+    out = w.generate(enc, SamplingParams(top_k=1, num_tokens_to_generate=5))
+    assert out.shape == (2, 5)
+    pad = (enc != 0).float()
+    em = pad.unsqueeze(1) * pad.unsqueeze(2)
+    dec = torch.full((2, 1), 1)
+    with torch.no_grad():
+        for t in range(5):
+            n = dec.shape[1]
+            dm = torch.tril(torch.ones(n, n)).unsqueeze(0).expand(2, -1, -1)
+            logits = m(enc, dec, em, dm, pad.unsqueeze(1).expand(2, n, -1))
+            dec = torch.cat([dec, logits[:, -1].argmax(-1, keepdim=True)], 1)
+    assert torch.equal(out, dec[:, 1:])
+    eos = int(out[0, 1])
+    stopped = w.generate(enc, SamplingParams(top_k=1, num_tokens_to_generate=5), eos_token=eos)
+    first = (stopped[0] == eos).nonzero()[0, 0]
+    assert stopped.shape[1] <= 5 and torch.equal(stopped[0, :first + 1], out[0, :first + 1]) and (stopped[0, first:] == eos).all()
