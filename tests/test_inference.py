@@ -277,7 +277,7 @@ def test_dynamic_engine_serves_concurrent_clients_in_shared_steps(engine):
     from megatronapp_b200.inference.server import MegatronServer
 
     eng, model = engine
-    sp = SamplingParams(top_k=1, num_tokens_to_generate=12)
+    sp = SamplingParams(top_k=1, num_tokens_to_generate=30)
     prompts = ["5 9 23 7 8 1 2 3", "11 3 40 41"]
     ref = [eng.generate([p], sp)[0].generated_tokens.tolist() for p in prompts]
     dyn = DynamicInferenceEngine(model, NullTokenizer(127), max_sequence_length=64, num_blocks=32, block_size=4,
@@ -288,8 +288,11 @@ def test_dynamic_engine_serves_concurrent_clients_in_shared_steps(engine):
     time.sleep(0.3)
     outs = [None, None]
 
+    gate = threading.Barrier(2)
+
     def client(i):
-        body = json.dumps({"prompts": [prompts[i]], "tokens_to_generate": 12, "top_k": 1}).encode()
+        gate.wait()                                                  # both requests leave at the same moment
+        body = json.dumps({"prompts": [prompts[i]], "tokens_to_generate": 30, "top_k": 1}).encode()
         req = urllib.request.Request("http://127.0.0.1:18815/api", data=body, method="PUT",
                                      headers={"Content-Type": "application/json"})
         outs[i] = json.loads(urllib.request.urlopen(req, timeout=120).read())
