@@ -479,10 +479,13 @@ def get_megatron_optimizer(config: OptimizerConfig, model_chunks, no_weight_deca
         raise ValueError(f"optimizer {config.optimizer!r} is not supported (adam only)")
     if not isinstance(model_chunks, (list, tuple)):
         model_chunks = [model_chunks]
-    from ..parallel.fsdp import FSDPOptimizer, FullyShardedDataParallel
+    from ..parallel.fsdp import (FSDPOptimizer, FullyShardedDataParallel, TorchFSDPOptimizer,
+                                 TorchFullyShardedDataParallel)
 
     if all(isinstance(m, FullyShardedDataParallel) for m in model_chunks):
         return FSDPOptimizer(config, model_chunks)
+    if all(isinstance(m, TorchFullyShardedDataParallel) for m in model_chunks):
+        return TorchFSDPOptimizer(config, model_chunks)
     for m in model_chunks:
         if not isinstance(m, DistributedDataParallel):
             raise TypeError("get_megatron_optimizer expects DistributedDataParallel-wrapped chunks")

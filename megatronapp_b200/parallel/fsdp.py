@@ -14,6 +14,7 @@ from __future__ import annotations
 from typing import Callable, Iterable, List, Optional
 
 import contextlib
+import math
 
 import torch
 import torch.distributed as dist
@@ -341,3 +342,61 @@ class FSDPOptimizer:
         for u, m in zip(self.units, sd["main"]):
             u.main_shard.data.copy_(m)
             u.copy_main_to_model()
+
+
+class TorchFSDPOptimizer:
+    """AdamW over the DTensor parameters of torch-FSDP2-wrapped chunks, behind the interface the training loop expects
+    (``step() -> (ok, grad_norm, num_zeros)``, ``param_groups`` with lr / weight decay set by the scheduler,
+    ``scale_loss``, ``state_dict``).  torch does the sharded bookkeeping; this only adapts the surface."""
+
+    sharded = True
+
+    def __init__(self, config, model_chunks):
+        self.config, self.model_chunks = config, model_chunks
+        decay, no_decay = [], []
+        for m in model_chunks:
+            for n, p in m.named_parameters():
+                if p.requires_grad:
+                    (no_decay if (p.dim() <= 1 or n.endswith(".bias")) else decay).append(p)
+        self.opt = torch.optim.AdamW([{"params": decay, "weight_decay": config.weight_decay, "wd_mult": 1.0, "lr_mult": 1.0},
+                                      {"params": no_decay, "weight_decay": 0.0, "wd_mult": 0.0, "lr_mult": 1.0}],
+                                     lr=config.lr or 0.0, betas=(config.adam_beta1, config.adam_beta2), eps=config.adam_eps)
+        self.param_groups = self.opt.param_groups
+        self.grad_scaler = None
+
+    def zero_grad(self, set_to_none=True):
+        self.opt.zero_grad(set_to_none=set_to_none)
+
+    def get_loss_scale(self):
+        return torch.tensor([1.0])
+
+    def scale_loss(self, loss):
+        return loss
+
+    def _params(self):
+        return [p for g in self.opt.param_groups for p in g["params"] if p.grad is not None]
+
+    @torch.no_grad()
+    def step(self):
+        params = self._params()
+        norm = None
+        if self.config.clip_grad > 0.0 and params:
+            total = torch.nn.utils.clip_grad_norm_(params, self.config.clip_grad)
+            total = total.full_tensor() if hasattr(total, "full_tensor") else total
+            norm = float(total)
+            if not math.isfinite(norm):
+                return False, norm, None
+        self.opt.step()
+        return True, norm, None
+
+    def reload_model_params(self):
+        pass
+
+    def state_dict(self):
+        return self.opt.state_dict()
+
+    def load_state_dict(self, sd):
+        self.opt.load_state_dict(sd)
+
+    def sharded_state_dict(self, *a, **k):
+        return self.state_dict()

@@ -83,6 +83,8 @@ MULTI = {
     "gpt_dpp_vpp_eval": ["pretrain_gpt.py", "--num-layers", "4", "--pipeline-model-parallel-size", "2",
                          "--num-layers-per-virtual-pipeline-stage", "1", "--use-dpp", "--eval-interval", "2"],
     "gpt_fbd": ["pretrain_gpt.py", "--forward-backward-disaggregating"],
+    "gpt_torch_fsdp2": ["pretrain_gpt.py", "--use-torch-fsdp2"],
+    "gpt_custom_fsdp_bf16": ["pretrain_gpt.py", "--use-custom-fsdp", "--bf16"],
     "gpt_trace_pp2": ["pretrain_gpt.py", "--pipeline-model-parallel-size", "2", "--trace", "--trace-interval", "1",
                       "--continuous-trace-iterations", "2"],
     "vlm_pp2": ["pretrain_vlm.py", "--img-h", "14", "--img-w", "14", "--patch-dim", "7", "--pipeline-model-parallel-size", "2"],
