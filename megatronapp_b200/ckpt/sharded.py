@@ -126,10 +126,13 @@ def save(sharded_state_dict: Dict[str, object], checkpoint_dir: str, common_stat
     mine, meta = {}, {}
     for k, v in sharded_state_dict.items():
         if isinstance(v, ShardedTensor):
+            data = v.data
+            if hasattr(data, "full_tensor"):          # torch FSDP2 DTensor: assembling it is a collective -> every rank
+                data = data.full_tensor()
             if not v.is_main_replica():
                 continue
             sk = f"{v.key}@{','.join(map(str, v.global_offset))}"
-            mine[sk] = v.data.detach().to("cpu", copy=True)
+            mine[sk] = data.detach().to("cpu", copy=True)
             meta.setdefault(v.key, {"global_shape": list(v.global_shape), "dtype": _dtype_str(v.dtype), "shards": []})
             meta[v.key]["shards"].append({"file": f"shards_{rank:05d}.pt", "offset": list(v.global_offset),
                                           "shape": list(v.local_shape), "name": sk})
@@ -202,7 +205,13 @@ def load(sharded_state_dict: Dict[str, object], checkpoint_dir: str, strict: boo
             covered += n
         if covered < dst.numel() and not v.allow_shape_mismatch:
             raise ValueError(f"checkpoint shards do not cover {v.key} (covered {covered} of {dst.numel()})")
-        if v.data is not None:
+        if v.data is not None and hasattr(v.data, "full_tensor"):
+            from torch.distributed.tensor import distribute_tensor
+
+            local = distribute_tensor(dst.to(v.data.device), v.data.device_mesh, v.data.placements)
+            with torch.no_grad():
+                v.data.detach().to_local().copy_(local.to_local())
+        elif v.data is not None:
             v.data.data.copy_(dst.to(v.data.device))
         out[k] = dst
     if missing and strict:
