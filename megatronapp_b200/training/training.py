@@ -550,6 +550,9 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             timers("interval-time", log_level=0).start(barrier=True)
         if args.manual_gc and args.manual_gc_interval and iteration % args.manual_gc_interval == 0:
             gc.collect()
+        if getattr(args, "train_sync_interval", None) and iteration % args.train_sync_interval == 0 \
+                and torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()        # keep the host from running arbitrarily far ahead of the GPU
         checkpointing.maybe_finalize_async_save(blocking=False)
         saved = False
         sh = get_signal_handler()
