@@ -70,6 +70,26 @@ def forward_step(data_iterator, model):
 def train_valid_test_datasets_provider(num_samples):
     args = get_args()
     dec = args.decoder_seq_length or max(8, args.seq_length // 4)
+    if getattr(args, "data_path", None) and not args.mock_data:
+        # sentence-level .bin/.idx corpus -> span-corruption samples; the sentinels are the tokenizer's extra ids
+        # (--vocab-extra-ids 100), as in the reference's T5MaskedWordPieceDataset
+        from megatronapp_b200.data.gpt_dataset import parse_split, split_document_ranges
+        from megatronapp_b200.data.indexed_dataset import IndexedDataset
+        from megatronapp_b200.data.masked_dataset import MaskedWordPieceDatasetConfig, T5MaskedWordPieceDataset
+        from megatronapp_b200.training.global_vars import get_tokenizer
+
+        prefix = args.data_path[0] if len(args.data_path) == 1 else args.data_path[1]
+        idx = IndexedDataset(prefix)
+        tok = get_tokenizer()
+        cfg = MaskedWordPieceDatasetConfig(sequence_length=args.encoder_seq_length or args.seq_length,
+                                           sequence_length_decoder=dec, masking_probability=args.mask_prob,
+                                           short_sequence_probability=args.short_seq_prob, random_seed=args.seed,
+                                           classification_head=False)
+        n_extra = getattr(args, "vocab_extra_ids", 0) or 0
+        sentinels = list(range(tok.vocab_size - n_extra, tok.vocab_size)) if n_extra else None
+        ranges = split_document_ranges(len(idx.document_indices) - 1, parse_split(args.split or "969,30,1"))
+        return tuple(T5MaskedWordPieceDataset(idx, max(int(n), 1), cfg, tok, doc_range=r, sentinel_tokens=sentinels)
+                     if r[1] > r[0] else None for n, r in zip(num_samples, ranges))
     mk = lambda n, s: MockT5Dataset(max(int(n), 1), args.seq_length, dec, args.padded_vocab_size, s)  # noqa: E731
     return mk(num_samples[0], args.seed), mk(num_samples[1], args.seed + 1), mk(num_samples[2], args.seed + 2)
 

@@ -337,3 +337,35 @@ def test_non_persistent_checkpoints_cover_the_gap_between_persistent_ones(tmp_pa
     open(os.path.join(ck, "latest_checkpointed_iteration.txt"), "w").write("4")
     out, resumed = run("--load", ck, "--non-persistent-ckpt-type", "global")
     assert "non_persistent at iteration 5" in out and resumed == straight[5:]
+
+
+def test_t5_trains_on_a_preprocessed_sentence_corpus(tmp_path):
+    """jsonl -> ``tools/preprocess_data.py --split-sentences`` -> ``pretrain_t5.py --data-path`` (span corruption with the
+    tokenizer's extra ids as sentinels) -- the whole real-data path through the CLIs."""
+    import json
+    import random
+
+    random.seed(0)
+    words = ["the", "cat", "dog", "sat", "ran"] + list("abcdefghij")
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words + ["."]
+    (tmp_path / "vocab.txt").write_text("\n".join(vocab) + "\n")
+    with open(tmp_path / "c.jsonl", "w") as f:
+        for _ in range(60):
+            f.write(json.dumps({"text": ". ".join(" ".join(random.choice(words) for _ in range(random.randint(4, 9)))
+                                                   for _ in range(random.randint(3, 6)))}) + "\n")
+    tok = ["--tokenizer-type", "BertWordPieceLowerCase", "--vocab-file", str(tmp_path / "vocab.txt"), "--vocab-extra-ids", "10"]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "preprocess_data.py"), "--input", str(tmp_path / "c.jsonl"),
+                        "--split-sentences", "--output-prefix", str(tmp_path / "c"), "--workers", "1", *tok],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_port()), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    common = [a for a in COMMON if a not in ("--mock-data",)]
+    i = common.index("--vocab-size")
+    common = common[:i] + common[i + 2:]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_t5.py"), *common, *tok, "--encoder-seq-length", "32",
+                        "--decoder-seq-length", "16", "--data-path", str(tmp_path / "c_text_sentence"), "--split", "90,5,5"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    assert re.search(r"iteration\s+3/\s+3 \|.*lm loss: [0-9.E+\-]+", out) and "validation loss at the end of training" in out
