@@ -34,6 +34,12 @@ enum GemmComm : int {
   kCommReduceScatter = 2,  // reduce-scatter(D rows) fused behind the GEMM
 };
 
+enum GemmGroupMode : int {
+  kGroupNone = 0,
+  kGroupM = 1,   // rows of A / D belong to groups (MoE forward + dgrad); B and bias are stacked per group
+  kGroupK = 2,   // the reduction dimension is split by group (MoE wgrad); D is stacked per group
+};
+
 struct GemmArgs {
   // D[M,N] = A[M,K] * B[N,K]^T  (logical).  *_mn_major: operand stored transposed
   // (A stored [K,M] / B stored [K,N], leading dimension = lda/ldb elements).
@@ -63,6 +69,15 @@ struct GemmArgs {
   void* peer_buf[kMaxPeers] = {nullptr};       // AG: peers' gather buffers; RS: peers' staging buffers
   uint32_t* peer_flags[kMaxPeers] = {nullptr};  // per-peer flag arrays (index tp_rank = local)
   // reduce-scatter: D is the local output shard [M/tp, N]; staging in peer_buf[tp_rank]
+  // ---- grouped GEMM (cta_group::2 kernel only) -------------------------------------------
+  // group_offsets: device int32 [n_groups + 1], multiples of 256 (the padded ragged row layout written by the MoE
+  // permute kernel).  kGroupM: M = row capacity, B is the stacked weight [n_groups * group_stride, ...].
+  // kGroupK: K = row capacity, D is the stacked fp32 gradient [n_groups * group_stride, N].
+  int group_mode = kGroupNone;
+  const int32_t* group_offsets = nullptr;
+  int n_groups = 0;
+  int group_stride = 0;
+  const float* row_scale = nullptr;   // kGroupM: optional per-row multiplier (router probability)
   cudaStream_t stream = nullptr;
 };
 

@@ -68,7 +68,7 @@ class MoEAuxLossAutoScaler(torch.autograd.Function):
     def backward(ctx, grad_output):
         (aux_loss,) = ctx.saved_tensors
         scale = MoEAuxLossAutoScaler.main_loss_backward_scale
-        return grad_output, torch.ones_like(aux_loss) * scale.to(aux_loss.device)
+        return grad_output, torch.ones_like(aux_loss) * scale.to(aux_loss.device).reshape(-1)[0]
 
     @staticmethod
     def set_loss_scale(scale):

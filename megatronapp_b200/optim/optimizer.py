@@ -226,6 +226,7 @@ class MegatronOptimizer:
         for chunk in model_chunks:
             names = {p: n for n, p in chunk.module.named_parameters()}
             for buf in chunk.buffers + chunk.expert_parallel_buffers:
+                is_expert_buf = any(buf is b for b in chunk.expert_parallel_buffers)
                 raw = []
                 for p in buf.params:
                     s, e, _ = buf.param_index[p]
@@ -247,6 +248,7 @@ class MegatronOptimizer:
                                                 config.optimizer_offload_fraction if config.optimizer_cpu_offload else 0.0,
                                                 (config.exp_avg_dtype, config.exp_avg_sq_dtype)
                                                 if config.use_precision_aware_optimizer else (torch.float32, torch.float32)))
+                self.states[-1].is_expert = is_expert_buf
         if config.fp16:
             if config.loss_scale:
                 self.grad_scaler = ConstantGradScaler(config.loss_scale)
@@ -279,18 +281,22 @@ class MegatronOptimizer:
             for s, e in st.segments:
                 yield st.buf.grad_data[s:e]
 
-    def get_grad_norm(self) -> float:
+    def _norm_sq(self, states) -> torch.Tensor:
+        """Sum of squares of the grads owned by ``states`` minus the TP-duplicated / shared copies."""
         dev = self._found_inf.device
         total = torch.zeros(1, dtype=torch.float32, device=dev)
-        ops.l2norm_sq(list(self._owned_grads()), total)
-        if self._excluded_from_norm:
+        grads = [st.buf.grad_data[s:e] for st in states for s, e in st.segments]
+        if grads:
+            ops.l2norm_sq(grads, total)
+        excl_params = [p for st in states for p in st.buf.params if any(p is q for q in self._excluded_from_norm)]
+        if excl_params:
             excl = torch.zeros(1, dtype=torch.float32, device=dev)
             if self.sharded:
                 # excluded params may straddle shards: subtract only the owned part
                 parts = []
-                for st in self.states:
+                for st in states:
                     for p in st.buf.params:
-                        if any(p is q for q in self._excluded_from_norm):
+                        if any(p is q for q in excl_params):
                             s, e, _ = st.buf.param_index[p]
                             for a, b in st.segments:
                                 lo, hi = max(a, s), min(b, e)
@@ -298,16 +304,41 @@ class MegatronOptimizer:
                                     parts.append(st.buf.grad_data[lo:hi])
                 ops.l2norm_sq(parts, excl) if parts else None
             else:
-                ops.l2norm_sq([p.main_grad.reshape(-1) for p in self._excluded_from_norm], excl)
+                ops.l2norm_sq([p.main_grad.reshape(-1) for p in excl_params], excl)
             total = total - excl
         if self.sharded:
-            for st in self.states:
+            for st in states:
                 if _is_real_group(st.buf.group):
                     dist.all_reduce(total, group=st.buf.group)
                     break
-        mp = ps.get_model_parallel_group(check_initialized=False) if ps.model_parallel_is_initialized() else None
+        return total
+
+    def _model_parallel_groups(self):
+        """(dense group, expert group): dense grads are distinct across tp x pp; expert grads are distinct across
+        tp x ep x pp (every EP rank holds different experts) -- reference ``clip_grads`` / ``get_grad_stats_parallel_group``."""
+        if not ps.model_parallel_is_initialized():
+            return None, None
+        mp = ps.get_model_parallel_group(check_initialized=False)
+        try:
+            emp = ps.get_state().group("tp_ep_pp")
+        except Exception:
+            emp = mp
+        return mp, emp
+
+    def get_grad_norm(self) -> float:
+        dense = [st for st in self.states if not st.is_expert]
+        expert = [st for st in self.states if st.is_expert]
+        mp, emp = self._model_parallel_groups()
+        total = self._norm_sq(dense)
         if _is_real_group(mp):
             dist.all_reduce(total, group=mp)
+        if expert:
+            etotal = self._norm_sq(expert)
+            if _is_real_group(emp):
+                dist.all_reduce(etotal, group=emp)
+            elif _is_real_group(mp):
+                dist.all_reduce(etotal, group=mp)
+            total = total + etotal
         return float(total.clamp_min(0).sqrt().item())
 
     def count_zeros(self) -> float:
@@ -323,9 +354,12 @@ class MegatronOptimizer:
                 ops.ext().check_finite(g, self._found_inf)
             elif not torch.isfinite(g).all():
                 self._found_inf.fill_(1.0)
-        mp = ps.get_model_parallel_group(check_initialized=False) if ps.model_parallel_is_initialized() else None
+        mp, emp = self._model_parallel_groups()
         if _is_real_group(mp):
             dist.all_reduce(self._found_inf, op=dist.ReduceOp.MAX, group=mp)
+        if any(st.is_expert for st in self.states) and _is_real_group(emp) and emp is not mp:
+            # an inf that only one EP rank's experts produced must stop the step on every rank
+            dist.all_reduce(self._found_inf, op=dist.ReduceOp.MAX, group=emp)
         if self.sharded:
             for st in self.states:
                 if _is_real_group(st.buf.group):

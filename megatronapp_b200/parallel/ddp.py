@@ -91,12 +91,20 @@ class ParamAndGradBuffer:
         bstart, bparams = 0, []
         for p in reversed(self.params):
             n = p.numel()
+            own_bucket = getattr(p, "shared_embedding", False) and ddp_config.use_distributed_optimizer
+            if own_bucket and bparams:
+                # the tied embedding must sit ALONE in its bucket on every pipeline stage (flush what
+                # came before it as well as closing after it, reference param_and_grad_buffer.py:582-590):
+                # the first<->last stage embedding all-reduce runs on reduce-scattered shards, so both
+                # stages must own identical element ranges of the weight
+                off = pad(off, pad_to)
+                self.buckets.append(_Bucket(bparams, bstart, off, len(self.buckets)))
+                bstart, bparams = off, []
             start = pad(off, 64)  # 128B/256B-aligned views: TMA + vectorised kernels need 16B alignment
             end = start + n
             self.param_index[p] = (start, end, len(self.buckets))
             bparams.append(p)
             off = end
-            own_bucket = getattr(p, "shared_embedding", False) and ddp_config.use_distributed_optimizer
             if (bucket_size is not None and (off - bstart) >= bucket_size) or own_bucket:
                 off = pad(off, pad_to)
                 self.buckets.append(_Bucket(bparams, bstart, off, len(self.buckets)))

@@ -156,6 +156,25 @@ def forward_step(forward_step_func, data_iterator, model, num_microbatches, inpu
             forward_data_store.append(loss_reduced)
         else:
             forward_data_store.append(loss_func(output_tensor, non_loss_data=True))
+    # Auxiliary losses (MoE load-balancing / z-loss, MTP) enter autograd through auto-scaler functions
+    # whose backward scale must equal the main loss's: the fp16 loss scale, divided by the number
+    # of microbatches unless the loss is per-token (reference schedules.py:317-339).
+    n_experts = getattr(config, "num_moe_experts", None)
+    mtp_layers = getattr(config, "mtp_num_layers", None)
+    if n_experts is not None or mtp_layers:
+        dev = output_tensor.device if torch.is_tensor(output_tensor) else None
+        one = torch.ones(1, device=dev)
+        scale = config.grad_scale_func(one) if config.grad_scale_func is not None else one
+        if not config.calculate_per_token_loss:
+            scale = scale / num_microbatches
+        if n_experts is not None:
+            from ..moe.moe_utils import MoEAuxLossAutoScaler
+
+            MoEAuxLossAutoScaler.set_loss_scale(scale)
+        if mtp_layers:
+            from ..transformer.multi_token_prediction import MTPLossAutoScaler
+
+            MTPLossAutoScaler.set_loss_scale(scale)
     return output_tensor, num_tokens
 
 

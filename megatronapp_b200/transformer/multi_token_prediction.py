@@ -44,7 +44,7 @@ class MTPLossAutoScaler(torch.autograd.Function):
     def backward(ctx, grad_output: torch.Tensor):
         (mtp_loss,) = ctx.saved_tensors
         scale = MTPLossAutoScaler.main_loss_backward_scale
-        return grad_output, torch.ones_like(mtp_loss) * scale.to(mtp_loss.device)
+        return grad_output, torch.ones_like(mtp_loss) * scale.to(mtp_loss.device).reshape(-1)[0]
 
     @staticmethod
     def set_loss_scale(scale: torch.Tensor):
