@@ -162,39 +162,51 @@ def run_own(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    scope_ms = None
-    if args.trace_scopes:
-        # one extra (untimed) step under the MegaScan tracer: per-scope device time on this rank
-        from megatronapp_b200.scan.tracer import get_tracer
+    # ---- MegaScan metrics (BASELINE.json): the same K steps again under the tracer (CUDA-event scopes, per-iteration
+    # flush of the event list, records gathered to rank 0 and written by the background thread) -> trace overhead %;
+    # the scope records give the exposed (compute-stream-blocking) communication time per step.
+    from megatronapp_b200.scan.tracer import get_tracer
 
-        tr = get_tracer()
-        tr.configure(True, trace_dir="/tmp/b200_bench_trace", interval=1, continuous_iterations=1)
-        tr.log = lambda: None
-        tr.iteration_begin(0)
+    tr = get_tracer()
+    trace_dir = os.path.join(os.environ.get("B200_BENCH_TRACE_DIR", "/tmp"), f"b200_bench_trace_{os.getpid()}")
+    tr.configure(True, trace_dir=trace_dir, interval=args.steps, continuous_iterations=args.steps)
+    scope_stats = {}
+    orig_log = tr.log
+
+    def _log_and_digest():
+        scope_stats.update(_digest_scopes(tr._records))
+        orig_log()
+
+    tr.log = _log_and_digest
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(args.steps):
+        tr.iteration_begin(i)
         train_step(state, dev_batches, sync_loss=False)
         tr.iteration_end()
-        tot, cnt, stack = {}, {}, []
-        for r in tr._records:
-            if r["ph"] == "B":
-                stack.append(r)
-            elif r["ph"] == "E":
-                for k in range(len(stack) - 1, -1, -1):
-                    if stack[k]["name"] == r["name"]:
-                        b = stack.pop(k)
-                        tot[r["name"]] = tot.get(r["name"], 0.0) + (r["rel_ts"] - b["rel_ts"]) / 1e6
-                        cnt[r["name"]] = cnt.get(r["name"], 0) + 1
-                        break
-        scope_ms = {k: {"ms": round(v, 3), "calls": cnt[k]} for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
-        tr.configure(False)
-        barrier()
+    g1.record()
+    barrier()
+    ms_traced = g0.elapsed_time(g1)
+    tr.configure(False)
+    tr.log = orig_log
+    try:
+        tr.shutdown()
+    except Exception:
+        pass
+    exposed_ms = scope_stats.get("exposed_comm_ns", 0) / 1e6 / max(1, args.steps)
+    scope_ms = {k: {"ms": round(v["ns"] / 1e6 / args.steps, 3), "calls": v["calls"] // max(1, args.steps)}
+                for k, v in sorted(scope_stats.get("per_scope", {}).items(), key=lambda kv: -kv[1]["ns"])}
     last_loss = _finite_from_any_rank(last_loss, world)
-    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    tokens = global_batch * S * args.steps
     first_or_last = state.pre_process or state.post_process
     h2d = sum(v.numel() * v.element_size() for b in pin_batches for v in b.values()) if first_or_last else 0
+    d2h = 4 if state.post_process else 0       # the loss scalar is read back on the last pipeline stage every step
+    t = torch.tensor([ms, ms_e2e, ms_traced, exposed_ms, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_traced, exposed_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    h2d, d2h = int(t[4]), int(t[5])            # per-rank maxima: the stages that own the data / the loss
+    tokens = global_batch * S * args.steps
     if rank == 0:
         par = f"tp{tp}" + (f"pp{pp}" if pp > 1 else "") + (f"dp{dp}" if dp > 1 else "") + ("+sp" if tp > 1 else "")
         out = {
@@ -208,21 +220,60 @@ def run_own(args):
                        "optimizer": "Adam fp32 master + fp32 main grads, clip 1.0",
                        "l2_policy": "working set (>=13 GB weights + grads per step) >> 126 MB L2; no explicit flush",
                        "attention_impl": "native" if ops.native_attention_available() else "sdpa-library",
-                       "fused_tp_comm": (tp > 1 and not args.no_fused_tp_comm)},
+                       "fused_tp_comm": (tp > 1 and not args.no_fused_tp_comm),
+                       "fused_gemm_rs": (tp > 1 and not args.no_fused_tp_comm and not args.no_fused_rs)},
             "clocks": clocks,
             "e2e": {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if state.post_process else 0,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "copies": "pinned-host microbatches -> device on the first/last pipeline stage every step; the "
+                              "last stage reads the loss back (.item()) every step",
                     "final_loss": last_loss},
+            "trace_overhead_pct": 100.0 * (ms_traced - ms) / ms,
+            "traced_ms_per_step": ms_traced / args.steps,
+            "exposed_comm_ms_per_step": exposed_ms,
             "gpu_launches": launches,
             "library_fallbacks": dict(ops.fallback_counts),
             "tflops_per_gpu": 6.0 * _param_count(L, H, F, vocab) * tokens / (ms / 1e3) / 1e12 / args.gpus,
         }
-        if scope_ms is not None:
-            out["rank0_scope_ms_one_step"] = scope_ms
+        out["rank0_scope_ms_per_step"] = scope_ms
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+COMM_SCOPES = {"_reduce", "_gather_along_first_dim", "_reduce_scatter_along_first_dim", "_gather_along_last_dim",
+               "_reduce_scatter_along_last_dim", "all_to_all", "allreduce", "reduce", "grad-reduce-scatter",
+               "param-all-gather", "send-forward", "recv-forward", "send-backward", "recv-backward",
+               "send-forward-recv-backward", "send-backward-recv-forward", "fbd-send", "fbd-recv"}
+
+
+def _digest_scopes(records):
+    """Per-scope device time and the exposed communication time of this rank from MegaScan B/E records.
+    Exposed = time the compute stream spends inside (outermost) NCCL collective / p2p scopes; the fused
+    AG->GEMM / GEMM->RS kernels carry their transfers inside the GEMM and are listed under their own scope names."""
+    per, stack, comm_depth, exposed = {}, [], 0, 0
+    for r in records:
+        ph, name = r.get("ph"), r.get("name")
+        if name == "iteration":
+            continue
+        if ph == "B":
+            stack.append((name, r["rel_ts"]))
+            if name in COMM_SCOPES:
+                comm_depth += 1
+        elif ph == "E":
+            for k in range(len(stack) - 1, -1, -1):
+                if stack[k][0] == name:
+                    _, t0 = stack.pop(k)
+                    d = per.setdefault(name, {"ns": 0, "calls": 0})
+                    d["ns"] += r["rel_ts"] - t0
+                    d["calls"] += 1
+                    if name in COMM_SCOPES:
+                        comm_depth -= 1
+                        if comm_depth == 0:
+                            exposed += r["rel_ts"] - t0
+                    break
+    return {"per_scope": per, "exposed_comm_ns": exposed}
 
 
 def _finite_from_any_rank(x, world):
@@ -257,11 +308,12 @@ def main():
     ap.add_argument("--microbatches-per-gpu", type=int, default=8)
     ap.add_argument("--tp", type=int, default=None)
     ap.add_argument("--no-fused-tp-comm", action="store_true", help="NCCL collectives instead of fused AG/RS GEMMs")
-    ap.add_argument("--trace-scopes", action="store_true", help="add one untimed traced step; per-scope device ms in the JSON")
-    ap.add_argument("--fused-rs", action="store_true", help="also fuse GEMM->reduce-scatter (default: AG->GEMM only)")
+    ap.add_argument("--trace-scopes", action="store_true", help="(kept for compatibility; scopes are always reported)")
+    ap.add_argument("--no-fused-rs", action="store_true", help="GEMM + NCCL reduce-scatter instead of the fused GEMM->RS kernel")
+    ap.add_argument("--fused-rs", action="store_true", help="(default now) fuse GEMM->reduce-scatter")
     args = ap.parse_args()
-    if args.fused_rs:
-        os.environ["B200_FUSED_RS"] = "1"
+    if args.no_fused_rs:
+        os.environ["B200_FUSED_RS"] = "0"
     if args.impl == "reference":
         from baseline.reference_arm import run_reference
 

@@ -135,10 +135,12 @@ class TPFusedComm:
         # fixed (6 x 32 KB), so the count scales with the number of destinations (override: B200_AG_COMM_CTAS)
         env = os.environ.get("B200_AG_COMM_CTAS")
         self.n_comm_ctas = int(env) if env else (n_comm_ctas if arena.size <= 2 else 16)
-        # GEMM->RS fusion is numerically validated but (round 1) ~20 % slower than tcgen05 GEMM +
-        # NCCL reduce-scatter on 2 GPUs; AG->GEMM fusion wins 8-16 % -- see profiles/.  Opt in with
-        # B200_FUSED_RS=1 / bench.py --fused-rs.
-        self.use_fused_rs = os.environ.get("B200_FUSED_RS", "0") == "1"
+        # GEMM->RS: pushed partial tiles + reduction folded into the epilogue of the owner's own tiles (cta_group::2
+        # kernel, no serialised reduce tail).  On by default; B200_FUSED_RS=0 / bench.py --no-fused-rs falls back to
+        # tcgen05 GEMM + NCCL reduce-scatter (the in-tree baseline).
+        self.use_fused_rs = os.environ.get("B200_FUSED_RS", "1") == "1"
+        # 0 = auto (cta_group::2 kernel when the shape allows), 128 / 256 = force the 1-CTA kernel (A/B measurements)
+        self.block_n = int(os.environ.get("B200_FUSED_BLOCK_N", "0"))
         self.calls = {"ag": 0, "rs": 0}
         ext = ops.ext()
         nflags = max(ext.gemm_flags_needed(max_tokens, max(max_in, max_out), arena.size), 4096)
@@ -148,7 +150,8 @@ class TPFusedComm:
         self.rs_flags = [arena.region(f"tp_rs_flags{i}", nflags * 4) for i in range(2)]
 
     def ag_gemm(self, x_local: torch.Tensor, weight: torch.Tensor, bias=None, b_mn: bool = False,
-                act: int = 0, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                act: int = 0, out: Optional[torch.Tensor] = None,
+                out_pre: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """``AG(x_local) @ W^T``; returns (out, gathered_x_view).  The gathered view aliases the
         arena slot and is only valid until the slot is reused two calls later."""
         a = self.arena
@@ -162,7 +165,7 @@ class TPFusedComm:
         if out is None:
             out = torch.empty(M, N, dtype=x_local.dtype, device=x_local.device)
         ops.ext().gemm_ag(x_local, a.local_ptr + reg.offset, weight, out, b_mn, bias, act,
-                          a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, self.n_comm_ctas, 0)
+                          a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, self.n_comm_ctas, self.block_n, out_pre)
         gathered = a.local(reg, (M, K), x_local.dtype)
         return out, gathered
 
@@ -176,5 +179,5 @@ class TPFusedComm:
         M = x.shape[0]
         N = weight.shape[1] if b_mn else weight.shape[0]
         out = torch.empty(M // a.size, N, dtype=x.dtype, device=x.device)
-        ops.ext().gemm_rs(x, weight, out, b_mn, bias, a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, 0)
+        ops.ext().gemm_rs(x, weight, out, b_mn, bias, a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, self.block_n)
         return out

@@ -223,6 +223,20 @@ void wait_flags(const uint32_t* flags, int n, uint32_t target, cudaStream_t s);
 void spin_kernel(int64_t cycles, cudaStream_t s);  // MegaScan software slow-rank injector
 void write_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
 
+// ---------------------------------------------------------------- MoE (moe.cu)
+void moe_router_topk_fwd(const float* logits, float* probs, uint8_t* map, int32_t* tokens_per_expert, int n, int E, int k,
+                         bool pre_softmax, float scaling, cudaStream_t s);
+void moe_router_topk_bwd(const float* logits, const float* probs, const uint8_t* map, const float* dprobs, float* dlogits,
+                         int n, int E, bool pre_softmax, float scaling, cudaStream_t s);
+// ragged layout: counts[E_local], offsets[E_local+1] (segments padded to `pad` rows), row_slot[cap] = token*E_total+expert
+// (or -1), row_prob[cap], dest_row[n*E_local] = row (or -1); pos_scratch[n*E_local]
+void moe_build_layout(const uint8_t* map, const float* probs, int n, int E_total, int e_begin, int E_local, int pad,
+                      int32_t* pos_scratch, int32_t* counts, int32_t* offsets, int32_t* row_slot, float* row_prob,
+                      int32_t* dest_row, int cap, cudaStream_t s);
+void moe_gather_rows(const void* in, const int32_t* row_slot, int slot_div, const float* row_scale, const int32_t* offsets,
+                     int n_groups, int cap, int cols, void* out, const void* other, float* dot_out, bool is_bf16, cudaStream_t s);
+void moe_gather_sum(const void* y, const int32_t* dest_row, int n, int E_local, int cols, void* out, bool is_bf16, cudaStream_t s);
+
 // MegaDPP mailbox (mailbox.cpp)
 int mailbox_create(int n_slots, size_t slot_bytes, const char* shm_name, void* ipc_handle_out64);
 int mailbox_connect(int id, const void* peer_ipc_handle64, const char* peer_shm_name);

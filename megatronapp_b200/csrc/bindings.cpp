@@ -70,10 +70,49 @@ void gemm(const Tensor& A, const Tensor& B, Tensor& D, bool a_mn, bool b_mn, int
   count();
 }
 
+// Grouped GEMM over the 256-row-padded ragged layout written by moe_permute (MoE experts).
+//   mode 1 (GroupM): D[cap, N] = A[cap, K] . W_g^T, W stacked [G * stride, .]; b_mn selects dgrad (W stored [K-rows, N]).
+//   mode 2 (GroupK): D32[G * stride, N] += A[cap, M]^T . B[cap, N] restricted to the rows of each group.
+void gemm_grouped(const Tensor& A, const Tensor& B, Tensor& D, const Tensor& offsets, int mode, bool b_mn,
+                  const c10::optional<Tensor>& bias, int act, const c10::optional<Tensor>& D_pre,
+                  const c10::optional<Tensor>& row_scale, int n_groups, int group_stride) {
+  c10::cuda::CUDAGuard guard(A.device());
+  check_2d(A, "A"); check_2d(B, "B"); check_2d(D, "D");
+  TORCH_CHECK(offsets.is_cuda() && offsets.scalar_type() == at::kInt && offsets.numel() >= n_groups + 1, "offsets: int32 [G+1]");
+  b200::GemmArgs g;
+  g.A = A.data_ptr(); g.B = B.data_ptr(); g.D = D.data_ptr();
+  g.lda = static_cast<int>(A.stride(0)); g.ldb = static_cast<int>(B.stride(0)); g.ldd = static_cast<int>(D.stride(0));
+  g.is_bf16 = is_bf16(A);
+  g.group_offsets = offsets.data_ptr<int32_t>(); g.n_groups = n_groups; g.group_stride = group_stride;
+  g.bias = optptr(bias); g.act = act; g.D_pre = const_cast<void*>(optptr(D_pre));
+  g.row_scale = row_scale.has_value() && row_scale->defined() ? row_scale->data_ptr<float>() : nullptr;
+  if (mode == 1) {
+    g.group_mode = b200::kGroupM; g.epilogue = b200::kEpiStore16;
+    g.a_mn_major = false; g.b_mn_major = b_mn;
+    g.M = static_cast<int>(A.size(0)); g.K = static_cast<int>(A.size(1)); g.N = static_cast<int>(D.size(1));
+    TORCH_CHECK(D.size(0) == A.size(0) && A.size(0) % 256 == 0, "GroupM: row capacity must be a multiple of 256");
+    TORCH_CHECK(B.size(0) == static_cast<int64_t>(n_groups) * group_stride, "GroupM: stacked weight rows != G * stride");
+    TORCH_CHECK(b_mn ? (group_stride == g.K && B.size(1) == g.N) : (group_stride == g.N && B.size(1) == g.K),
+                "GroupM: weight shape does not match A/D");
+  } else {
+    g.group_mode = b200::kGroupK; g.epilogue = b200::kEpiAccumF32;
+    g.a_mn_major = true; g.b_mn_major = true;
+    g.M = static_cast<int>(A.size(1)); g.K = static_cast<int>(A.size(0)); g.N = static_cast<int>(B.size(1));
+    TORCH_CHECK(A.size(0) == B.size(0), "GroupK: A and B must have the same row capacity");
+    TORCH_CHECK(D.scalar_type() == at::kFloat && D.size(0) == static_cast<int64_t>(n_groups) * group_stride && D.size(1) == g.N,
+                "GroupK: D must be fp32 [G * stride, N]");
+    TORCH_CHECK(group_stride == g.M, "GroupK: stride must equal the per-group output rows");
+  }
+  g.stream = cur_stream();
+  int rc = b200::gemm_bf16(g);
+  TORCH_CHECK(rc == 0, "b200 grouped gemm failed (", rc, "): ", b200::gemm_last_error());
+  count();
+}
+
 void gemm_ag(const Tensor& A_local, int64_t gather_ptr, const Tensor& B, Tensor& D, bool b_mn,
              const c10::optional<Tensor>& bias, int act, std::vector<int64_t> peer_bufs,
              std::vector<int64_t> peer_flags, int rank, int size, int64_t epoch, int n_comm_ctas,
-             int block_n) {
+             int block_n, const c10::optional<Tensor>& D_pre) {
   c10::cuda::CUDAGuard guard(A_local.device());
   check_2d(A_local, "A_local"); check_2d(B, "B"); check_2d(D, "D");
   b200::GemmArgs g;
@@ -85,6 +124,7 @@ void gemm_ag(const Tensor& A_local, int64_t gather_ptr, const Tensor& B, Tensor&
   g.lda = g.K; g.ldb = static_cast<int>(B.stride(0)); g.ldd = static_cast<int>(D.stride(0));
   g.a_mn_major = false; g.b_mn_major = b_mn; g.is_bf16 = is_bf16(A_local);
   g.epilogue = b200::kEpiStore16; g.bias = optptr(bias); g.act = act; g.block_n = block_n;
+  g.D_pre = const_cast<void*>(optptr(D_pre));
   g.comm = b200::kCommAllGather; g.tp_rank = rank; g.tp_size = size; g.epoch = static_cast<uint32_t>(epoch);
   g.n_comm_ctas = n_comm_ctas;
   for (int i = 0; i < size; ++i) {
@@ -119,6 +159,88 @@ void gemm_rs(const Tensor& A, const Tensor& B, Tensor& D_out, bool b_mn, const c
   int rc = b200::gemm_bf16(g);
   TORCH_CHECK(rc == 0, "b200 gemm_rs failed (", rc, "): ", b200::gemm_last_error());
   count();
+}
+
+// ---------------------------------------------------------------- MoE
+std::vector<Tensor> moe_router_topk_fwd(const Tensor& logits, int k, bool pre_softmax, double scaling) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(logits.dim() == 2 && logits.scalar_type() == at::kFloat && logits.is_contiguous(), "router logits: fp32 [n, E]");
+  const int n = static_cast<int>(logits.size(0)), E = static_cast<int>(logits.size(1));
+  TORCH_CHECK(E <= 256 && k >= 1 && k <= 8 && k <= E, "router kernel: E <= 256, 1 <= topk <= 8");
+  auto probs = torch::empty_like(logits);
+  auto map = torch::empty({n, E}, logits.options().dtype(at::kBool));
+  auto tpe = torch::zeros({E}, logits.options().dtype(at::kInt));
+  b200::moe_router_topk_fwd(logits.data_ptr<float>(), probs.data_ptr<float>(), reinterpret_cast<uint8_t*>(map.data_ptr()),
+                            tpe.data_ptr<int32_t>(), n, E, k, pre_softmax, static_cast<float>(scaling), cur_stream());
+  count();
+  return {probs, map, tpe};
+}
+
+Tensor moe_router_topk_bwd(const Tensor& logits, const Tensor& probs, const Tensor& map, const Tensor& dprobs, bool pre_softmax,
+                           double scaling) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto dl = torch::empty_like(logits);
+  auto dp = dprobs.contiguous();
+  b200::moe_router_topk_bwd(logits.data_ptr<float>(), probs.data_ptr<float>(), reinterpret_cast<const uint8_t*>(map.data_ptr()),
+                            dp.data_ptr<float>(), dl.data_ptr<float>(), static_cast<int>(logits.size(0)),
+                            static_cast<int>(logits.size(1)), pre_softmax, static_cast<float>(scaling), cur_stream());
+  count();
+  return dl;
+}
+
+// -> counts [E_local], offsets [E_local+1], row_slot [cap], row_prob [cap], dest_row [n, E_local]   (all on the device)
+std::vector<Tensor> moe_build_layout(const Tensor& map, const c10::optional<Tensor>& probs, int e_begin, int E_local, int pad, int cap) {
+  c10::cuda::CUDAGuard guard(map.device());
+  TORCH_CHECK(map.dim() == 2 && map.is_contiguous() && (map.scalar_type() == at::kBool || map.scalar_type() == at::kByte),
+              "routing map: bool [n, E]");
+  const int n = static_cast<int>(map.size(0)), E = static_cast<int>(map.size(1));
+  TORCH_CHECK(e_begin >= 0 && e_begin + E_local <= E && cap % pad == 0, "bad expert range / capacity");
+  auto io = map.options().dtype(at::kInt);
+  auto pos = torch::empty({n, E_local}, io);
+  auto counts = torch::empty({E_local}, io);
+  auto offsets = torch::empty({E_local + 1}, io);
+  auto row_slot = torch::empty({cap}, io);
+  auto row_prob = torch::zeros({cap}, map.options().dtype(at::kFloat));
+  auto dest_row = torch::empty({n, E_local}, io);
+  const float* pp = nullptr;
+  if (probs.has_value() && probs->defined()) {
+    TORCH_CHECK(probs->scalar_type() == at::kFloat && probs->is_contiguous() && probs->sizes() == map.sizes(), "probs: fp32 [n, E]");
+    pp = probs->data_ptr<float>();
+  }
+  b200::moe_build_layout(reinterpret_cast<const uint8_t*>(map.data_ptr()), pp, n, E, e_begin, E_local, pad, pos.data_ptr<int32_t>(),
+                         counts.data_ptr<int32_t>(), offsets.data_ptr<int32_t>(), row_slot.data_ptr<int32_t>(),
+                         row_prob.data_ptr<float>(), dest_row.data_ptr<int32_t>(), cap, cur_stream());
+  count(3);
+  return {counts, offsets, row_slot, row_prob, dest_row};
+}
+
+// out[r] = scale[r] * in[row_slot[r] / slot_div]; optional dot_out[row_slot[r]] = <in_row, other[r]> / scale[r]
+Tensor moe_gather_rows(const Tensor& in, const Tensor& row_slot, int slot_div, const c10::optional<Tensor>& row_scale,
+                       const Tensor& offsets, int n_groups, const c10::optional<Tensor>& other, c10::optional<Tensor> dot_out) {
+  c10::cuda::CUDAGuard guard(in.device());
+  check_2d(in, "in");
+  TORCH_CHECK(in.is_contiguous() && in.size(1) % 8 == 0, "gather_rows: contiguous rows, cols % 8 == 0");
+  const int cap = static_cast<int>(row_slot.numel()), cols = static_cast<int>(in.size(1));
+  auto out = torch::empty({cap, cols}, in.options());
+  const float* sc = row_scale.has_value() && row_scale->defined() ? row_scale->data_ptr<float>() : nullptr;
+  float* dp = dot_out.has_value() && dot_out->defined() ? dot_out->data_ptr<float>() : nullptr;
+  TORCH_CHECK(dp == nullptr || (sc != nullptr && other.has_value()), "dot output needs row_scale and other");
+  b200::moe_gather_rows(in.data_ptr(), row_slot.data_ptr<int32_t>(), slot_div, sc, offsets.data_ptr<int32_t>(), n_groups, cap, cols,
+                        out.data_ptr(), optptr(other), dp, is_bf16(in), cur_stream());
+  count();
+  return out;
+}
+
+Tensor moe_gather_sum(const Tensor& y, const Tensor& dest_row) {
+  c10::cuda::CUDAGuard guard(y.device());
+  check_2d(y, "y");
+  TORCH_CHECK(y.is_contiguous() && y.size(1) % 8 == 0 && dest_row.dim() == 2, "gather_sum: contiguous y, dest_row [n, E_local]");
+  const int n = static_cast<int>(dest_row.size(0)), el = static_cast<int>(dest_row.size(1));
+  auto out = torch::empty({n, y.size(1)}, y.options());
+  b200::moe_gather_sum(y.data_ptr(), dest_row.data_ptr<int32_t>(), n, el, static_cast<int>(y.size(1)), out.data_ptr(), is_bf16(y),
+                       cur_stream());
+  count();
+  return out;
 }
 
 // ---------------------------------------------------------------- norms etc.
@@ -573,7 +695,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("fp8_quantize", &fp8_quantize);
-  m.def("gemm_ag", &gemm_ag);
+  m.def("gemm_ag", &gemm_ag, py::arg("A_local"), py::arg("gather_ptr"), py::arg("B"), py::arg("D"), py::arg("b_mn"),
+        py::arg("bias"), py::arg("act"), py::arg("peer_bufs"), py::arg("peer_flags"), py::arg("rank"), py::arg("size"),
+        py::arg("epoch"), py::arg("n_comm_ctas"), py::arg("block_n"), py::arg("D_pre") = c10::optional<Tensor>());
+  m.def("gemm_grouped", &gemm_grouped);
+  m.def("moe_router_topk_fwd", &moe_router_topk_fwd);
+  m.def("moe_router_topk_bwd", &moe_router_topk_bwd);
+  m.def("moe_build_layout", &moe_build_layout);
+  m.def("moe_gather_rows", &moe_gather_rows);
+  m.def("moe_gather_sum", &moe_gather_sum);
   m.def("gemm_rs", &gemm_rs);
   m.def("gemm_flags_needed", &b200::gemm_flags_needed);
   m.def("layernorm_fwd", &layernorm_fwd);

@@ -60,6 +60,26 @@ class SequentialMLP(MegatronModule):
         return _expert_replica(sd)
 
     def forward(self, permuted_local_hidden_states, tokens_per_expert, permuted_probs=None):
+        from .token_dispatcher import RaggedTokens
+
+        if isinstance(permuted_local_hidden_states, RaggedTokens):
+            # ragged layout of the fused dispatcher: per-expert row ranges come from the device-side offsets (this
+            # module-per-expert path reads them back; GroupedMLP is the sync-free one)
+            rt = permuted_local_hidden_states
+            offs = rt.layout.offsets.tolist()
+            out = torch.zeros(rt.data.shape[0], self.config.hidden_size, dtype=rt.data.dtype, device=rt.data.device)
+            pieces = []
+            for i, expert in enumerate(self.local_experts):
+                r0, r1 = offs[i], offs[i + 1]
+                if r1 > r0:
+                    o, b = expert(rt.data[r0:r1])
+                    pieces.append((r0, r1, o if b is None else o + b))
+            if pieces:
+                out = torch.cat([torch.zeros(0, self.config.hidden_size, dtype=out.dtype, device=out.device)] +
+                                [p[2] for p in pieces] +
+                                [torch.zeros(rt.data.shape[0] - pieces[-1][1], self.config.hidden_size, dtype=out.dtype,
+                                             device=out.device)], dim=0)
+            return RaggedTokens(out, rt.layout, rt.probs), None
         if self.num_local_experts == 1:
             out, bias = self.local_experts[0](permuted_local_hidden_states)
             return out, bias
@@ -119,7 +139,24 @@ class GroupedMLP(MegatronModule):
                            if etp > 1 else make_sharded_tensor_for_checkpoint(view, key, prepend_offsets=tuple(sharded_offsets)))
         return _expert_replica(sd)
 
+    def _activation(self, inter):
+        return ops.swiglu(inter) if (self.glu and self.config.activation_func is F.silu) else (
+            self._glu(inter) if self.glu else self._act(inter))
+
     def forward(self, permuted_local_hidden_states, tokens_per_expert, permuted_probs=None):
+        from .token_dispatcher import RaggedTokens
+
+        if isinstance(permuted_local_hidden_states, RaggedTokens):
+            # ONE grouped tcgen05 GEMM per matrix over the ragged layout; the router probability rides in the FC2
+            # epilogue and the un-permutation is a gather-sum: no host sync, no per-expert launches
+            from ..ops import moe as mops
+
+            rt = permuted_local_hidden_states
+            fuse = bool(self.config.gradient_accumulation_fusion)
+            inter = mops.grouped_linear(rt.data, self.weight1, rt.layout, self.fc1_out, fuse)
+            inter = self._activation(inter)
+            out = mops.grouped_linear_combine(inter, self.weight2, rt.probs, rt.layout, self.config.hidden_size, fuse)
+            return RaggedTokens(None, rt.layout, rt.probs, combined=out), None
         x = permuted_local_hidden_states
         sizes = tokens_per_expert.tolist()
         h = self.config.hidden_size

@@ -86,11 +86,17 @@ class TopKRouter(MegatronModule):
             act = torch.sigmoid(logits) if self.topk == 1 else torch.softmax(logits, dim=-1, dtype=torch.float32).type_as(logits)
             rmap = torch.zeros_like(logits).int().scatter(1, idx, 1).bool()
             return act * rmap, rmap
-        probs, rmap, tpe = topk_softmax_with_capacity(
-            logits, self.topk, cfg.moe_expert_capacity_factor, cfg.moe_pad_expert_input_to_capacity,
-            cfg.moe_token_drop_policy, cfg.moe_router_pre_softmax, cfg.moe_router_num_groups,
-            cfg.moe_router_group_topk, cfg.moe_router_topk_scaling_factor, cfg.deterministic_mode,
-            self.score_function, self.expert_bias)
+        fused_ok = (logits.is_cuda and self.score_function == "softmax" and cfg.moe_expert_capacity_factor is None
+                    and not cfg.moe_router_group_topk and self.expert_bias is None and self.num_experts <= 256
+                    and self.topk <= 8 and logits.dtype in (torch.float32, torch.bfloat16, torch.float16))
+        if fused_ok:
+            # one warp per token: softmax + top-k (+ renormalisation / scaling), dense probs + routing map out
+            from ..ops.moe import router_topk
+
+            probs, rmap, tpe = router_topk(logits, self.topk, bool(cfg.moe_router_pre_softmax),
+                                           cfg.moe_router_topk_scaling_factor)
+        else:
+            probs, rmap, tpe = self._routing_torch(logits, cfg)
         if self.training and cfg.moe_aux_loss_coeff > 0 and self.routing_type in ("aux_loss", "seq_aux_loss"):
             scores = torch.softmax(logits, dim=-1, dtype=torch.float32) if self.score_function == "softmax" else (
                 lambda s: s / (s.sum(-1, keepdim=True) + 1e-20))(torch.sigmoid(logits.float()))
@@ -105,6 +111,13 @@ class TopKRouter(MegatronModule):
             with torch.no_grad():
                 self.local_tokens_per_expert += rmap.sum(dim=0)
         return probs, rmap
+
+    def _routing_torch(self, logits, cfg):
+        return topk_softmax_with_capacity(
+            logits, self.topk, cfg.moe_expert_capacity_factor, cfg.moe_pad_expert_input_to_capacity,
+            cfg.moe_token_drop_policy, cfg.moe_router_pre_softmax, cfg.moe_router_num_groups,
+            cfg.moe_router_group_topk, cfg.moe_router_topk_scaling_factor, cfg.deterministic_mode,
+            self.score_function, self.expert_bias)
 
     def forward(self, x):
         x = self.apply_input_jitter(x)

@@ -181,6 +181,89 @@ class _ReduceScatterFirstDimVarAutograd(torch.autograd.Function):
         return _gather_along_first_dim(g.contiguous(), ctx.group, ctx.sizes), None, None
 
 
+class RaggedTokens:
+    """Expert-side token buffer of the fused dispatcher: ``data`` [capacity, h] in the 256-row padded per-expert layout
+    described by ``layout`` (``ops/moe.py``); ``probs`` is the router's dense probability tensor (carries the gradient).
+    ``combined`` is set by experts that already applied the probabilities and summed the copies of every token
+    (``GroupedMLP`` does both inside the FC2 kernel + gather-sum)."""
+
+    def __init__(self, data, layout, probs, combined=None):
+        self.data, self.layout, self.probs, self.combined = data, layout, probs, combined
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+
+class _Combine(torch.autograd.Function):
+    """out[t] = sum_e p[t, e] * y[row(t, e)] for experts that return un-scaled ragged rows (SequentialMLP)."""
+
+    @staticmethod
+    def forward(ctx, y, probs, lay):
+        from ..ops import moe as mops
+
+        ctx.lay = lay
+        ctx.save_for_backward(y)
+        ctx.probs_shape, ctx.probs_dtype = probs.shape, probs.dtype
+        z = (y.float() * lay.row_prob.unsqueeze(-1)).to(y.dtype)
+        return mops._gather_sum(z, lay)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ..ops import moe as mops
+
+        (y,) = ctx.saved_tensors
+        lay = ctx.lay
+        dprobs = torch.zeros(ctx.probs_shape, dtype=torch.float32, device=dout.device)
+        g = mops._gather_rows(dout.contiguous(), lay, lay.E_total)                # dOut re-permuted, un-scaled
+        valid = (lay.row_slot >= 0)
+        d = (g.float() * y.float()).sum(-1)
+        dprobs.view(-1)[lay.row_slot[valid].long()] = d[valid]
+        dy = (g.float() * lay.row_prob.unsqueeze(-1)).to(y.dtype)
+        return dy, dprobs.to(ctx.probs_dtype), None
+
+
+class MoEFusedDispatcher(MoETokenDispatcher):
+    """``--moe-token-dispatcher-type fused``: device-side routing layout + grouped tcgen05 expert GEMMs, zero host syncs.
+
+    ``token_permutation`` builds the ragged layout on the device (``moe.cu``: stable per-expert positions, 256-row padded
+    segments, row <-> (token, expert) maps) and gathers the token rows into it; the experts consume it as ONE grouped GEMM
+    per matrix; ``token_unpermutation`` is a gather-sum.  With expert tensor parallelism the tokens / routing of the
+    TP group are all-gathered in front (every TP rank holds 1/etp of every expert's FFN) and the partial outputs are
+    reduce-scattered behind, as in the reference's dispatcher (token_dispatcher.py:560-640).  Expert parallelism > 1 goes
+    through the EP symmetric arena (``MoEArenaDispatcher``)."""
+
+    def __init__(self, num_local_experts, local_expert_indices, config):
+        super().__init__(config)
+        self.num_local_experts, self.local_expert_indices = num_local_experts, local_expert_indices
+        self.num_experts = config.num_moe_experts
+        if self.ep_size > 1:
+            raise ValueError("MoEFusedDispatcher handles expert-parallel size 1; use MoEArenaDispatcher (flex) for ep > 1")
+
+    def token_permutation(self, hidden_states, probs, routing_map):
+        from ..ops import moe as mops
+
+        self.hidden_shape = hidden_states.shape
+        x = hidden_states.reshape(-1, self.hidden_shape[-1])
+        if self.etp_size > 1:
+            routing_map = _gather_along_first_dim(routing_map.to(torch.uint8), self.etp_group).bool()
+            probs = _GatherFirstDimAutograd.apply(probs.contiguous(), self.etp_group)
+            x = _GatherFirstDimAutograd.apply(x.contiguous(), self.etp_group)
+        lay = mops.build_layout(routing_map.contiguous(), probs, self.local_expert_indices[0], self.num_local_experts,
+                                self.config.moe_router_topk)
+        return RaggedTokens(mops.permute(x, lay), lay, probs), lay.counts
+
+    def token_unpermutation(self, expert_out, bias=None):
+        if isinstance(expert_out, RaggedTokens):
+            out = expert_out.combined if expert_out.combined is not None else \
+                _Combine.apply(expert_out.data, expert_out.probs, expert_out.layout)
+        else:
+            raise TypeError("MoEFusedDispatcher expects the experts to return RaggedTokens")
+        if self.etp_size > 1:
+            out = _ReduceScatterFirstDimAutograd.apply(out, self.etp_group)
+        return out.view(self.hidden_shape), None
+
+
 class _PeerScatter(torch.autograd.Function):
     """rows -> owner buffers via the fused NVLink scatter kernel; backward = the reverse scatter."""
 

@@ -136,14 +136,19 @@ class _ColumnParallelFn(torch.autograd.Function):
         ctx.fused = False
         if sequence_parallel and tp > 1:
             rows_total = x2.shape[0] * tp
+            # bias + tanh-GELU ride in the epilogue of the fused kernel too; the pre-activation is kept for backward
+            pre = torch.empty(rows_total, weight.shape[0], dtype=x2.dtype, device=x2.device) if act else None
             if _fusable(rows_total, x2, weight):
                 with _scope("ag_gemm", data=x2.numel() * x2.element_size() * (tp - 1)):
-                    out, _ = _FUSED_COMM.ag_gemm(x2.contiguous(), weight, bias)
+                    out, _ = _FUSED_COMM.ag_gemm(x2.contiguous(), weight, bias, act=act, out_pre=pre)
                 ctx.fused = True
             else:
                 total = _gather_along_first_dim(x2)
-                out = ops.gemm(total, weight, bias=bias)
+                out = ops.gemm(total, weight, bias=bias, act=act, out_pre=pre)
             out_shape = (x.shape[0] * tp,) + tuple(x.shape[1:-1]) + (weight.shape[0],)
+            if act:
+                ctx.save_for_backward(x2, weight, pre)
+                return out.view(out_shape)
         else:
             pre = None
             if act:
@@ -299,11 +304,9 @@ class ColumnParallelLinear(nn.Module):
                           self.gradient_accumulation_fusion and weight.requires_grad)
 
     def can_fuse_gelu(self, input_) -> bool:
-        """bias + tanh-GELU can ride in the GEMM epilogue (not on the fused all-gather path, whose
-        launcher has no second output for the pre-activation)."""
+        """bias + tanh-GELU can ride in the GEMM epilogue (plain and fused all-gather kernels alike)."""
         return (self.fp8_recipe is None and input_.is_cuda and input_.dtype in (torch.bfloat16, torch.float16)
-                and not self.gather_output
-                and not (self.sequence_parallel and self.tp_size > 1) and self.weight is not None
+                and not self.gather_output and self.weight is not None
                 and self.weight.shape[0] % 64 == 0 and not self.explicit_expert_comm)
 
     def forward(self, input_, weight=None, runtime_gather_output=None, fused_gelu: bool = False):

@@ -150,7 +150,8 @@ def moe_parity(ep=1, dispatcher="alltoall", grouped=False):
     x = torch.randn(8, 2, 32, generator=g, requires_grad=True)
     out, _ = layer(x)
     out.pow(2).sum().backward()
-    return {"out": out.detach().flatten().tolist(), "gx": x.grad.flatten().tolist(), "seed_rank": rank}
+    return {"out": out.detach().flatten().tolist(), "gx": x.grad.flatten().tolist(), "seed_rank": rank,
+            "grouter": layer.router.weight.grad.flatten().tolist()}
 
 
 def cp_attention_parity(comm="a2a", causal=True):

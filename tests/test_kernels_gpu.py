@@ -109,6 +109,30 @@ def test_cuda_graph_layer_matches_eager():
     assert p.returncode == 0 and "GRAPH_OK" in p.stdout, (p.stdout[-1500:], p.stderr[-3000:])
 
 
+def test_fp8_gemm_and_linear():
+    """tcgen05 kind::f8f6f4 GEMM + the fp8 linear (fwd / dgrad / wgrad) vs fp32 references."""
+    res = gc.check_fp8()
+    _assert_small({k: v for k, v in res.items() if not isinstance(v, (list, dict))}, 8e-2)
+
+
+def test_grouped_gemm_ragged_layout():
+    """MoE grouped GEMM (cta_group::2, device-side offsets): forward, row-scaled forward, dgrad, wgrad, empty experts."""
+    _assert_small(gc.check_grouped_gemm(), 2e-2)
+
+
+def test_moe_device_kernels():
+    """Fused router top-k fwd/bwd, layout builder, permute / gather-sum / combine-backward kernels."""
+    res = gc.check_moe_kernels()
+    exact = {k: v for k, v in res.items() if any(t in k for t in ("_map_mismatch", "_tpe", "_offsets", "_counts", "_dest_row",
+                                                                  "_row_slot", "_permute"))}
+    assert all(v == 0 for v in exact.values()), {k: v for k, v in exact.items() if v != 0}
+    _assert_small({k: v for k, v in res.items() if k not in exact}, 2e-2)
+
+
+def test_moe_layer_fused_matches_sequential():
+    _assert_small(gc.check_moe_layer(), 5e-2)
+
+
 def test_model_step_matches_fp32_reference():
     res = gc.check_model_parity()
     assert res["max_abs_diff"] < 0.08, res

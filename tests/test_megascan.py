@@ -92,3 +92,25 @@ def test_tracer_cpu_roundtrip(tmp_path):
     assert red["group"] == [0] and red["data"] == 4096 and "bandwidth" in red
     traces = agg.benchmark_to_chrome_trace({(0, 0, 0): recs})
     assert any(e["name"] == "forward" and e["ph"] == "X" for e in traces)
+
+
+def test_bench_scope_digest_counts_outermost_comm_only():
+    """bench.py's exposed-comm metric: nested comm scopes are counted once, compute scopes never."""
+    import bench
+
+    recs = [
+        {"name": "iteration", "ph": "B", "rel_ts": 0},
+        {"name": "forward", "ph": "B", "rel_ts": 10},
+        {"name": "_reduce_scatter_along_first_dim", "ph": "B", "rel_ts": 20},
+        {"name": "_reduce_scatter_along_first_dim", "ph": "E", "rel_ts": 50},
+        {"name": "forward", "ph": "E", "rel_ts": 100},
+        {"name": "allreduce", "ph": "B", "rel_ts": 110},
+        {"name": "grad-reduce-scatter", "ph": "B", "rel_ts": 120},
+        {"name": "grad-reduce-scatter", "ph": "E", "rel_ts": 150},
+        {"name": "allreduce", "ph": "E", "rel_ts": 160},
+        {"name": "iteration", "ph": "E", "rel_ts": 200},
+    ]
+    d = bench._digest_scopes(recs)
+    assert d["exposed_comm_ns"] == 30 + 50
+    assert d["per_scope"]["forward"] == {"ns": 90, "calls": 1}
+    assert d["per_scope"]["grad-reduce-scatter"]["ns"] == 30

@@ -30,3 +30,13 @@ def test_flex_dispatcher_single_rank_matches_alltoall():
     b = run_distributed("moe_parity", 1, ep=1, dispatcher="flex")[0]
     _close(a["out"], b["out"])
     _close(a["gx"], b["gx"])
+
+
+@pytest.mark.parametrize("grouped", [True, False])
+def test_fused_dispatcher_matches_alltoall(grouped):
+    """Ragged 256-row padded layout + grouped GEMM (reference implementation of the CUDA path) == per-expert modules."""
+    a = run_distributed("moe_parity", 1, ep=1, dispatcher="alltoall")[0]
+    b = run_distributed("moe_parity", 1, ep=1, dispatcher="fused", grouped=grouped)[0]
+    _close(a["out"], b["out"])
+    _close(a["gx"], b["gx"])
+    _close(a["grouter"], b["grouter"])

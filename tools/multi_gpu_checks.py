@@ -21,7 +21,20 @@ import torch.distributed as dist  # noqa: E402
 
 
 def rel_err(a, b):
-    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6))
+    """element-wise: max |a - b| / (|b| + rms(b))  (same criterion as tools/gpu_checks.py)"""
+    a, b = a.float(), b.float()
+    rms = b.pow(2).mean().sqrt().clamp_min(1e-12)
+    return float(((a - b).abs() / (b.abs() + rms)).max())
+
+
+def roofline_ms(flops, nvlink_bytes):
+    """B200_PROFILING.md: slower of FLOPs / measured GEMM peak and NVLink bytes / 770 GB/s per direction."""
+    peak = 1671.6e12
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] * 1e12
+    except Exception:
+        pass
+    return max(flops / peak, nvlink_bytes / 770e9) * 1e3
 
 
 def timed(fn, iters=20, warm=5):
@@ -63,13 +76,15 @@ def main():
             print(k, v, flush=True)
 
     try:
-        shapes = [(2048, 4096, 16384 // world, "fc1"), (2048, 4096, 12288 // world, "qkv"), (8192, 4096, 16384 // world, "fc1_mbs4")]
-        arena = SymmetricArena(group, 2 * (2 * 8192 * 16384 * 2) + (200 << 20))
-        fc = TPFusedComm(arena, 8192, 16384, 16384)
+        Mt = 2048 * world          # bench.py: micro-batch = TP degree, seq 2048
+        shapes = [(Mt, 4096, 16384 // world, "fc1"), (Mt, 4096, 12288 // world, "qkv")]
+        arena = SymmetricArena(group, 2 * (2 * Mt * 16384 * 2) + (200 << 20))
+        fc = TPFusedComm(arena, Mt, 16384, 16384)
         arena.barrier()
         torch.cuda.synchronize()
         log("arena_ok", True)
-        # ---------------- AG -> GEMM (column parallel forward)
+        variants = (("2cta", 0), ("1cta", 256))
+        # ---------------- AG -> GEMM (column parallel forward, bias + GELU + pre-activation in the epilogue)
         for (M, K, N, name) in shapes:
             torch.manual_seed(100 + rank)
             x_local = torch.randn(M // world, K, device="cuda", dtype=dt) * 0.5
@@ -79,11 +94,26 @@ def main():
             full = torch.empty(M, K, device="cuda", dtype=dt)
             dist.all_gather_into_tensor(full, x_local, group=group)
             ref = full.float() @ w.float().t() + bias.float()
-            out, gathered = fc.ag_gemm(x_local, w, bias)
-            torch.cuda.synchronize()
-            log(f"ag_gemm_{name}_err", rel_err(out, ref))
-            log(f"ag_gemm_{name}_gather_err", rel_err(gathered, full))
             outb = torch.empty(M, N, device="cuda", dtype=dt)
+            preb = torch.empty(M, N, device="cuda", dtype=dt)
+            times = {}
+            for vname, bn in variants:
+                fc.block_n = bn
+                out, gathered = fc.ag_gemm(x_local, w, bias)
+                torch.cuda.synchronize()
+                log(f"ag_gemm_{name}_{vname}_err", rel_err(out, ref))
+                log(f"ag_gemm_{name}_{vname}_gather_err", rel_err(gathered, full))
+                out, _ = fc.ag_gemm(x_local, w, bias, act=1, out_pre=preb)
+                torch.cuda.synchronize()
+                log(f"ag_gemm_{name}_{vname}_gelu_err", max(rel_err(preb, ref), rel_err(out, torch.nn.functional.gelu(ref, approximate="tanh"))))
+                sweep = {}
+                for ncc in ((8, 16) if world > 2 else (4, 8)):
+                    fc.n_comm_ctas = ncc
+                    sweep[ncc] = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb), 10, 3)
+                best = min(sweep, key=sweep.get)
+                fc.n_comm_ctas = best
+                times[f"fused_{vname}"] = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb))
+                times[f"fused_{vname}_comm_ctas"] = sweep
 
             def unfused():
                 dist.all_gather_into_tensor(full, x_local, group=group)
@@ -93,33 +123,38 @@ def main():
                 dist.all_gather_into_tensor(full, x_local, group=group)
                 torch.addmm(bias, full, w.t(), out=outb)
 
-            sweep = {}
-            for ncc in (4, 8, 16):
-                fc.n_comm_ctas = ncc
-                sweep[ncc] = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb), 10, 3)
-            best = min(sweep, key=sweep.get)
-            fc.n_comm_ctas = best
-            log(f"ag_gemm_{name}_comm_cta_sweep_ms", sweep)
-            t_f = timed(lambda: fc.ag_gemm(x_local, w, bias, out=outb))
-            t_u = timed(unfused)
-            t_c = timed(cublas_unfused)
-            t_g = timed(lambda: ops.gemm(full, w, out=outb, bias=bias))
-            log(f"ag_gemm_{name}_ms", {"fused": t_f, "nccl+b200gemm": t_u, "nccl+cublas": t_c, "gemm_only": t_g,
-                                         "tflops_fused": 2.0 * M * N * K / t_f / 1e9})
+            times["nccl+b200gemm"] = timed(unfused)
+            times["nccl+cublas"] = timed(cublas_unfused)
+            times["gemm_only"] = timed(lambda: ops.gemm(full, w, out=outb, bias=bias))
+            best_f = min(times["fused_2cta"], times["fused_1cta"])
+            roof = roofline_ms(2.0 * M * N * K, (M // world) * K * 2 * (world - 1))
+            times.update(roofline_ms=roof, frac_of_roofline=roof / best_f, fused_over_cublas_nccl=best_f / times["nccl+cublas"],
+                         tflops_fused=2.0 * M * N * K / best_f / 1e9)
+            log(f"ag_gemm_{name}_ms", times)
         # ---------------- GEMM -> RS (row parallel forward)
-        for (M, N, K, name) in [(2048, 4096, 16384 // world, "fc2"), (2048, 4096, 4096 // world, "proj"),
-                                (8192, 4096, 16384 // world, "fc2_mbs4")]:
+        for (M, N, K, name) in [(Mt, 4096, 16384 // world, "fc2"), (Mt, 4096, 4096 // world, "proj")]:
             torch.manual_seed(200 + rank)
             x = torch.randn(M, K, device="cuda", dtype=dt) * 0.5
             w = torch.randn(N, K, device="cuda", dtype=dt) * 0.05
+            bias = torch.randn(N, device="cuda", dtype=dt)
             part = (x.float() @ w.float().t())
             ref = torch.empty(M // world, N, device="cuda", dtype=torch.float32)
             dist.reduce_scatter_tensor(ref, part, group=group)
-            out = fc.gemm_rs(x, w)
-            torch.cuda.synchronize()
-            log(f"gemm_rs_{name}_err", rel_err(out, ref))
             pb = torch.empty(M, N, device="cuda", dtype=dt)
             ob = torch.empty(M // world, N, device="cuda", dtype=dt)
+            times = {}
+            for vname, bn in variants:
+                fc.block_n = bn
+                out = fc.gemm_rs(x, w)
+                torch.cuda.synchronize()
+                log(f"gemm_rs_{name}_{vname}_err", rel_err(out, ref))
+                out = fc.gemm_rs(x, w, bias=bias)
+                torch.cuda.synchronize()
+                log(f"gemm_rs_{name}_{vname}_bias_err", rel_err(out, ref + bias.float()))
+                o1 = fc.gemm_rs(x, w).clone()
+                o2 = fc.gemm_rs(x, w)
+                log(f"gemm_rs_{name}_{vname}_deterministic", bool(torch.equal(o1, o2)))
+                times[f"fused_{vname}"] = timed(lambda: fc.gemm_rs(x, w))
 
             def unfused():
                 ops.gemm(x, w, out=pb)
@@ -129,29 +164,43 @@ def main():
                 torch.matmul(x, w.t(), out=pb)
                 dist.reduce_scatter_tensor(ob, pb, group=group)
 
-            t_f = timed(lambda: fc.gemm_rs(x, w))
-            t_u = timed(unfused)
-            t_c = timed(cublas_unfused)
-            t_g = timed(lambda: ops.gemm(x, w, out=pb))
-            log(f"gemm_rs_{name}_ms", {"fused": t_f, "b200gemm+nccl": t_u, "cublas+nccl": t_c, "gemm_only": t_g,
-                                         "tflops_fused": 2.0 * M * N * K / t_f / 1e9})
+            times["b200gemm+nccl"] = timed(unfused)
+            times["cublas+nccl"] = timed(cublas_unfused)
+            times["gemm_only"] = timed(lambda: ops.gemm(x, w, out=pb))
+            best_f = min(times["fused_2cta"], times["fused_1cta"])
+            roof = roofline_ms(2.0 * M * N * K, (M // world) * N * 2 * (world - 1))
+            times.update(roofline_ms=roof, frac_of_roofline=roof / best_f, fused_over_cublas_nccl=best_f / times["cublas+nccl"],
+                         tflops_fused=2.0 * M * N * K / best_f / 1e9)
+            log(f"gemm_rs_{name}_ms", times)
         # dgrad duals (B MN-major)
-        M, K, N = 2048, 4096, 16384 // world
+        M, K, N = Mt, 4096, 16384 // world
         torch.manual_seed(300 + rank)
         dy = torch.randn(M, N, device="cuda", dtype=dt) * 0.5
         w = torch.randn(N, K, device="cuda", dtype=dt) * 0.05
         part = dy.float() @ w.float()
         ref = torch.empty(M // world, K, device="cuda", dtype=torch.float32)
         dist.reduce_scatter_tensor(ref, part, group=group)
-        out = fc.gemm_rs(dy, w, b_mn=True)
-        log("gemm_rs_dgrad_err", rel_err(out, ref))
         dyl = torch.randn(M // world, K, device="cuda", dtype=dt) * 0.5   # row-parallel dgrad: AG(dy) @ W[K_out, N_in]
         w2 = torch.randn(K, N, device="cuda", dtype=dt) * 0.05
         fulldy = torch.empty(M, K, device="cuda", dtype=dt)
         dist.all_gather_into_tensor(fulldy, dyl, group=group)
         ref2 = fulldy.float() @ w2.float()
-        out2, _ = fc.ag_gemm(dyl, w2, None, b_mn=True)
-        log("ag_gemm_dgrad_err", rel_err(out2, ref2))
+        pbd = torch.empty(M, K, device="cuda", dtype=dt)
+        obd = torch.empty(M // world, K, device="cuda", dtype=dt)
+        for vname, bn in variants:
+            fc.block_n = bn
+            out = fc.gemm_rs(dy, w, b_mn=True)
+            log(f"gemm_rs_dgrad_{vname}_err", rel_err(out, ref))
+            out2, _ = fc.ag_gemm(dyl, w2, None, b_mn=True)
+            log(f"ag_gemm_dgrad_{vname}_err", rel_err(out2, ref2))
+            log(f"gemm_rs_dgrad_{vname}_ms", timed(lambda: fc.gemm_rs(dy, w, b_mn=True)))
+
+        def dgrad_unfused():
+            torch.matmul(dy, w, out=pbd)
+            dist.reduce_scatter_tensor(obd, pbd, group=group)
+
+        log("gemm_rs_dgrad_cublas+nccl_ms", timed(dgrad_unfused))
+        fc.block_n = 0
         # ---------------- fused bucket reduce-scatter (scale + cast + RS)
         n = 8 * 1024 * 1024
         torch.manual_seed(400 + rank)
