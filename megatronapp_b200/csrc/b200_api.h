@@ -237,6 +237,19 @@ void moe_gather_rows(const void* in, const int32_t* row_slot, int slot_div, cons
                      int n_groups, int cap, int cols, void* out, const void* other, float* dot_out, bool is_bf16, cudaStream_t s);
 void moe_gather_sum(const void* y, const int32_t* dest_row, int n, int E_local, int cols, void* out, bool is_bf16, cudaStream_t s);
 
+// expert parallelism over the EP symmetric arena (pointer tables are indexed by EP rank)
+void moe_ep_dispatch(const void* x, const int32_t* send_offsets, const int32_t* send_row, const int32_t* counts_send, const float* probs,
+                     void* const* stage_x, int32_t* const* stage_idx, float* const* stage_prob, int32_t* const* recv_counts,
+                     uint32_t* const* flags, int n, int E_total, int E_local, int me, int ep, int Rs, int cols, uint32_t epoch,
+                     int32_t* done_counter, cudaStream_t s);
+void moe_ep_recv_layout(const uint32_t* flags, const int32_t* recv_counts, int ep, int E_local, int Rs, int pad, int cap,
+                        uint32_t epoch, int32_t* offsets, int32_t* counts, int32_t* row_stage, int32_t* overflow, cudaStream_t s);
+void moe_ep_combine_push(const void* z, const int32_t* row_stage, const int32_t* row_idx, const float* side, const int32_t* offsets,
+                         int n_groups, int cap, int Rs, int cols, void* const* ret_x, float* const* ret_f, uint32_t* const* flags,
+                         int me, int ep, uint32_t epoch, int32_t* done_counter, cudaStream_t s);
+void moe_ep_wait(const uint32_t* flags, int ep, uint32_t epoch, cudaStream_t s);
+void moe_scatter_dprobs(const float* ret_f, const int32_t* send_row, float* dprobs, int64_t pairs, cudaStream_t s);
+
 // MegaDPP mailbox (mailbox.cpp)
 int mailbox_create(int n_slots, size_t slot_bytes, const char* shm_name, void* ipc_handle_out64);
 int mailbox_connect(int id, const void* peer_ipc_handle64, const char* peer_shm_name);

@@ -243,6 +243,81 @@ Tensor moe_gather_sum(const Tensor& y, const Tensor& dest_row) {
   return out;
 }
 
+// ---- expert parallel over the EP arena: pointer tables arrive as lists of device addresses (one per EP rank)
+template <typename T>
+std::vector<T*> ptrs_of(const std::vector<int64_t>& v) {
+  std::vector<T*> o(b200::kMaxPeers, nullptr);
+  TORCH_CHECK(v.size() <= static_cast<size_t>(b200::kMaxPeers), "at most 8 expert-parallel peers");
+  for (size_t i = 0; i < v.size(); ++i) o[i] = reinterpret_cast<T*>(v[i]);
+  return o;
+}
+
+void moe_ep_dispatch(const Tensor& x, const Tensor& send_offsets, const Tensor& send_row, const Tensor& counts_send,
+                     const c10::optional<Tensor>& probs, std::vector<int64_t> stage_x, std::vector<int64_t> stage_idx,
+                     std::vector<int64_t> stage_prob, std::vector<int64_t> recv_counts, std::vector<int64_t> flags, int E_local,
+                     int me, int Rs, int64_t epoch, Tensor& done_counter) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check_2d(x, "x");
+  TORCH_CHECK(x.is_contiguous() && x.size(1) % 8 == 0 && send_row.dim() == 2 && send_row.size(0) == x.size(0), "ep_dispatch shapes");
+  const int ep = static_cast<int>(stage_x.size());
+  const int E_total = static_cast<int>(send_row.size(1));
+  TORCH_CHECK(E_total == ep * E_local && E_local <= 64, "E_total == ep * E_local, E_local <= 64");
+  is_bf16(x);
+  const float* pp = probs.has_value() && probs->defined() ? probs->data_ptr<float>() : nullptr;
+  auto sx = ptrs_of<void>(stage_x); auto si = ptrs_of<int32_t>(stage_idx); auto sp = ptrs_of<float>(stage_prob);
+  auto rc = ptrs_of<int32_t>(recv_counts); auto fl = ptrs_of<uint32_t>(flags);
+  b200::moe_ep_dispatch(x.data_ptr(), send_offsets.data_ptr<int32_t>(), send_row.data_ptr<int32_t>(), counts_send.data_ptr<int32_t>(),
+                        pp, sx.data(), si.data(), sp.data(), rc.data(), fl.data(), static_cast<int>(x.size(0)), E_total, E_local, me,
+                        ep, Rs, static_cast<int>(x.size(1)), static_cast<uint32_t>(epoch), done_counter.data_ptr<int32_t>(), cur_stream());
+  count();
+}
+
+// -> offsets [E_local+1], counts [E_local], row_stage [cap]; *overflow is set when the compact capacity was exceeded
+std::vector<Tensor> moe_ep_recv_layout(int64_t flags_ptr, int64_t recv_counts_ptr, int ep, int E_local, int Rs, int pad, int cap,
+                                       int64_t epoch, Tensor& overflow) {
+  c10::cuda::CUDAGuard guard(overflow.device());
+  TORCH_CHECK(E_local <= 64 && ep <= b200::kMaxPeers && cap % pad == 0, "ep_recv_layout limits");
+  auto io = overflow.options().dtype(at::kInt);
+  auto offsets = torch::empty({E_local + 1}, io);
+  auto counts = torch::empty({E_local}, io);
+  auto row_stage = torch::empty({cap}, io);
+  b200::moe_ep_recv_layout(reinterpret_cast<const uint32_t*>(flags_ptr), reinterpret_cast<const int32_t*>(recv_counts_ptr), ep, E_local, Rs,
+                           pad, cap, static_cast<uint32_t>(epoch), offsets.data_ptr<int32_t>(), counts.data_ptr<int32_t>(),
+                           row_stage.data_ptr<int32_t>(), overflow.data_ptr<int32_t>(), cur_stream());
+  count();
+  return {offsets, counts, row_stage};
+}
+
+void moe_ep_combine_push(const Tensor& z, const Tensor& row_stage, const Tensor& row_idx, const c10::optional<Tensor>& side,
+                         const Tensor& offsets, int n_groups, int Rs, std::vector<int64_t> ret_x, std::vector<int64_t> ret_f,
+                         std::vector<int64_t> flags, int me, int64_t epoch, Tensor& done_counter) {
+  c10::cuda::CUDAGuard guard(z.device());
+  check_2d(z, "z");
+  TORCH_CHECK(z.is_contiguous() && z.size(1) % 8 == 0 && z.size(0) == row_stage.numel(), "ep_combine_push shapes");
+  is_bf16(z);
+  const int ep = static_cast<int>(ret_x.size());
+  auto rx = ptrs_of<void>(ret_x); auto rf = ptrs_of<float>(ret_f); auto fl = ptrs_of<uint32_t>(flags);
+  const float* sd = side.has_value() && side->defined() ? side->data_ptr<float>() : nullptr;
+  b200::moe_ep_combine_push(z.data_ptr(), row_stage.data_ptr<int32_t>(), row_idx.data_ptr<int32_t>(), sd,
+                            offsets.data_ptr<int32_t>(), n_groups, static_cast<int>(z.size(0)), Rs, static_cast<int>(z.size(1)),
+                            rx.data(), rf.data(), fl.data(), me, ep, static_cast<uint32_t>(epoch), done_counter.data_ptr<int32_t>(),
+                            cur_stream());
+  count();
+}
+
+void moe_ep_wait(int64_t flags_ptr, int ep, int64_t epoch) {
+  b200::moe_ep_wait(reinterpret_cast<const uint32_t*>(flags_ptr), ep, static_cast<uint32_t>(epoch), cur_stream());
+  count();
+}
+
+Tensor moe_scatter_dprobs(const Tensor& ret_f, const Tensor& send_row) {
+  c10::cuda::CUDAGuard guard(ret_f.device());
+  auto out = torch::empty(send_row.sizes(), ret_f.options());
+  b200::moe_scatter_dprobs(ret_f.data_ptr<float>(), send_row.data_ptr<int32_t>(), out.data_ptr<float>(), send_row.numel(), cur_stream());
+  count();
+  return out;
+}
+
 // ---------------------------------------------------------------- norms etc.
 std::vector<Tensor> layernorm_fwd(const Tensor& x, const Tensor& gamma, const c10::optional<Tensor>& beta,
                                   double eps, bool rms, bool zero_centered) {
@@ -704,6 +779,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("moe_build_layout", &moe_build_layout);
   m.def("moe_gather_rows", &moe_gather_rows);
   m.def("moe_gather_sum", &moe_gather_sum);
+  m.def("moe_ep_dispatch", &moe_ep_dispatch);
+  m.def("moe_ep_recv_layout", &moe_ep_recv_layout);
+  m.def("moe_ep_combine_push", &moe_ep_combine_push);
+  m.def("moe_ep_wait", &moe_ep_wait);
+  m.def("moe_scatter_dprobs", &moe_scatter_dprobs);
   m.def("gemm_rs", &gemm_rs);
   m.def("gemm_flags_needed", &b200::gemm_flags_needed);
   m.def("layernorm_fwd", &layernorm_fwd);

@@ -186,10 +186,11 @@ __device__ __forceinline__ Tile2 tile_info(const P2& p, int tile) {
   const int m_local = r / n_in_group;
   t.n_blk = g * kGroupN2 + (r - m_local * n_in_group);
   t.m_blk = chunk * p.m_blocks_per_chunk + m_local;
+  t.valid = t.m_blk < p.num_m_blocks;          // the last L2 band may be partial
   if constexpr (kMode == kModeGroupM) {
     const int row0 = t.m_blk * 256;
     const int total = __ldg(p.group_offsets + p.n_groups);
-    t.valid = row0 < total;
+    t.valid = t.valid && row0 < total;
     int e = 0;
     if (t.valid) {
       while (e + 1 < p.n_groups && __ldg(p.group_offsets + e + 1) <= row0) ++e;
@@ -333,7 +334,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int cluster_id = static_cast<int>(blockIdx.x >> 1) - comm_clusters;
   const int n_clusters = static_cast<int>(gridDim.x >> 1) - comm_clusters;
   const int num_tiles = (kMode == kModeGroupK) ? p.n_groups * p.num_m_blocks * p.num_n_blocks
-                                               : p.num_m_blocks * p.num_n_blocks;
+                                               : p.n_chunks * p.m_blocks_per_chunk * p.num_n_blocks;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -781,7 +782,26 @@ int gemm2_bf16(const GemmArgs& a) {
       p.chunk_base = (a.tp_rank + 1) % a.tp_size; p.chunk_dir = 1;  // own rows last
     }
   }
-  const long tiles = (mode == kModeGroupK ? static_cast<long>(a.n_groups) : 1L) * p.num_m_blocks * p.num_n_blocks;
+  if (mode == kModePlain || mode == kModeGroupM) {
+    // L2 banding: tiles walk n-groups (8 x 256 columns) inside a band of m-blocks.  Without bands the whole A operand is
+    // re-streamed from HBM once per n-group as soon as it no longer fits L2; with bands B is re-read once per band.
+    // Pick whichever moves fewer bytes (l2_eff: what one operand can hold on to while the other streams through).
+    const double l2_eff = 48.0 * (1 << 20);
+    const double a_blk = 256.0 * a.K * 2, a_total = a_blk * p.num_m_blocks;
+    const double b_one = static_cast<double>(a.N) * a.K * 2;
+    const int n_ngroups = (p.num_n_blocks + kGroupN2 - 1) / kGroupN2;
+    const int groups = mode == kModeGroupM ? a.n_groups : 1;
+    int band = static_cast<int>(l2_eff / a_blk);
+    if (band < 2) band = 2;
+    if (a_total > l2_eff && band < p.num_m_blocks) {
+      const int n_bands = (p.num_m_blocks + band - 1) / band;
+      const double cost_plain = groups * b_one + a_total * n_ngroups;
+      const double cost_band = (groups - 1 + n_bands) * b_one + a_total;
+      if (cost_band < cost_plain) { p.n_chunks = n_bands; p.m_blocks_per_chunk = band; }
+    }
+  }
+  const long tiles = mode == kModeGroupK ? static_cast<long>(a.n_groups) * p.num_m_blocks * p.num_n_blocks
+                                         : static_cast<long>(p.n_chunks) * p.m_blocks_per_chunk * p.num_n_blocks;
   const int comm_clusters = p.n_comm_ctas / 2;
   if (tiles < clusters - comm_clusters) clusters = static_cast<int>(tiles) + comm_clusters;
   const int dt = a.is_bf16 ? 0 : 1;

@@ -20,6 +20,8 @@
 #include "b200_api.h"
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace b200 {
 
 namespace {
@@ -291,7 +293,225 @@ __global__ void __launch_bounds__(128) gather_sum_kernel(const uint16_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ expert parallel (arena)
+// Sources push routed rows straight into the expert owner's staging buffer over NVLink; per-(source, local expert)
+// counts, the sender's compact slot index and the router probability travel with the rows.  One epoch flag per
+// (owner, source) pair, raised by the last CTA of the sender ("last block" pattern), tells the owner that everything
+// from that source has landed.  Staging layout on an owner: [source s][rows of local expert 0 | 1 | ...] (capacity Rs
+// rows per source).
+struct EpPeers {
+  void* stage_x[kMaxPeers];
+  int32_t* stage_idx[kMaxPeers];
+  float* stage_prob[kMaxPeers];
+  int32_t* recv_counts[kMaxPeers];   // [ep][E_local] on each owner
+  uint32_t* flags[kMaxPeers];        // [ep] on each owner
+};
+
+__global__ void __launch_bounds__(256) ep_dispatch_kernel(const uint16_t* __restrict__ x, const int32_t* __restrict__ send_offsets,
+                                                          const int32_t* __restrict__ send_row, const int32_t* __restrict__ counts_send,
+                                                          const float* __restrict__ probs, EpPeers peers, int n, int E_total,
+                                                          int E_local, int me, int ep, int Rs, int cols, uint32_t epoch,
+                                                          int32_t* __restrict__ done_counter) {
+  extern __shared__ int pre_s[];      // per global expert: rows of my region on its owner that precede this expert
+  for (int ge = threadIdx.x; ge < E_total; ge += blockDim.x) {
+    const int d = ge / E_local, le = ge - d * E_local;
+    int o = 0;
+    for (int j = 0; j < le; ++j) o += counts_send[d * E_local + j];
+    pre_s[ge] = o;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    // my per-expert counts -> every owner (including myself)
+    for (int ge = threadIdx.x; ge < E_total; ge += blockDim.x) {
+      const int d = ge / E_local, le = ge - d * E_local;
+      peers.recv_counts[d][me * E_local + le] = counts_send[ge];
+    }
+  }
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vecs = cols / 8;
+  const int64_t pairs = static_cast<int64_t>(n) * E_total;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * warps + warp; i < pairs; i += static_cast<int64_t>(gridDim.x) * warps) {
+    const int sr = __ldg(send_row + i);
+    if (sr < 0) continue;
+    const int t = static_cast<int>(i / E_total), ge = static_cast<int>(i - static_cast<int64_t>(t) * E_total);
+    const int d = ge / E_local;
+    const int row = me * Rs + pre_s[ge] + (sr - __ldg(send_offsets + ge));   // position among my rows for this expert
+    const int4* src = reinterpret_cast<const int4*>(x + static_cast<size_t>(t) * cols);
+    int4* dst = reinterpret_cast<int4*>(reinterpret_cast<uint16_t*>(peers.stage_x[d]) + static_cast<size_t>(row) * cols);
+    for (int v = lane; v < vecs; v += 32) st_na_v4(dst + v, ld_nc_v4(src + v));
+    if (lane == 0) {
+      peers.stage_idx[d][row] = sr;
+      peers.stage_prob[d][row] = probs != nullptr ? __ldg(probs + i) : 1.f;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(done_counter, 1);
+    if (old == static_cast<int>(gridDim.x) - 1) {
+      __threadfence_system();
+      for (int d = 0; d < ep; ++d) st_release_sys(peers.flags[d] + me, epoch);
+      *done_counter = 0;
+    }
+  }
+}
+
+// owner: one block.  Waits for every source, then turns the per-(source, expert) counts into the ragged layout:
+// offsets[] (256-row padded segments, expert-major, sources in rank order inside a segment) and, for every compact
+// row, the staging row it comes from (-1 = padding).  Rows that do not fit the compact capacity are dropped and
+// *overflow is raised (the caller re-runs with more slack).
+__global__ void __launch_bounds__(1024) ep_recv_layout_kernel(const uint32_t* __restrict__ flags, const int32_t* __restrict__ recv_counts,
+                                                              int ep, int E_local, int Rs, int pad, int cap, uint32_t epoch,
+                                                              int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
+                                                              int32_t* __restrict__ row_stage, int32_t* __restrict__ overflow) {
+  __shared__ int cnt[kMaxPeers * 64];
+  __shared__ int offs[65];
+  if (threadIdx.x < ep) {
+    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(64);
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ep * E_local; i += blockDim.x)
+    cnt[i] = static_cast<int>(ld_relaxed_sys(reinterpret_cast<const uint32_t*>(recv_counts + i)));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int o = 0;
+    bool ovf = false;
+    for (int le = 0; le < E_local; ++le) {
+      offs[le] = o;
+      int c = 0;
+      for (int s2 = 0; s2 < ep; ++s2) c += cnt[s2 * E_local + le];
+      int padded = (c + pad - 1) / pad * pad;
+      if (o + padded > cap) {
+        ovf = true;
+        padded = (cap - o) / pad * pad;
+        c = min(c, padded);
+      }
+      counts[le] = c;
+      o += padded;
+    }
+    offs[E_local] = o;
+    if (ovf) *overflow = 1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e <= E_local; e += blockDim.x) offsets[e] = offs[e];
+  for (int r = threadIdx.x; r < cap; r += blockDim.x) row_stage[r] = -1;
+  __syncthreads();
+  for (int le = 0; le < E_local; ++le) {
+    const int seg_rows = offs[le + 1] - offs[le];
+    int base = offs[le];
+    for (int s2 = 0; s2 < ep; ++s2) {
+      int sbase = s2 * Rs;
+      for (int j = 0; j < le; ++j) sbase += cnt[s2 * E_local + j];
+      const int c = cnt[s2 * E_local + le];
+      for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const int r = base + i;
+        if (r - offs[le] < seg_rows) row_stage[r] = sbase + i;
+      }
+      base += c;
+    }
+  }
+}
+
+struct EpRet {
+  void* ret_x[kMaxPeers];       // [n * k, cols] on each source
+  float* ret_f[kMaxPeers];      // optional fp32 side payload (d prob), same indexing
+  uint32_t* flags[kMaxPeers];   // [ep] on each source
+};
+
+// owner -> sources: compact row r returns to source (row_stage[r] / Rs) at the slot the source named (row_idx[r])
+__global__ void __launch_bounds__(256) ep_combine_push_kernel(const uint16_t* __restrict__ z, const int32_t* __restrict__ row_stage,
+                                                              const int32_t* __restrict__ row_idx, const float* __restrict__ side,
+                                                              const int32_t* __restrict__ offsets, int n_groups, int cap, int Rs,
+                                                              int cols, EpRet ret, int me, int ep, uint32_t epoch,
+                                                              int32_t* __restrict__ done_counter) {
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = min(cap, __ldg(offsets + n_groups));
+  const int vecs = cols / 8;
+  for (int r = blockIdx.x * warps + warp; r < total; r += gridDim.x * warps) {
+    const int sr = __ldg(row_stage + r);
+    if (sr < 0) continue;
+    const int s2 = sr / Rs;
+    const int idx = __ldg(row_idx + r);
+    const int4* src = reinterpret_cast<const int4*>(z + static_cast<size_t>(r) * cols);
+    int4* dst = reinterpret_cast<int4*>(reinterpret_cast<uint16_t*>(ret.ret_x[s2]) + static_cast<size_t>(idx) * cols);
+    for (int v = lane; v < vecs; v += 32) st_na_v4(dst + v, ld_nc_v4(src + v));
+    if (side != nullptr && lane == 0) ret.ret_f[s2][idx] = __ldg(side + r);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(done_counter, 1);
+    if (old == static_cast<int>(gridDim.x) - 1) {
+      __threadfence_system();
+      for (int s2 = 0; s2 < ep; ++s2) st_release_sys(ret.flags[s2] + me, epoch);
+      *done_counter = 0;
+    }
+  }
+}
+
+__global__ void ep_wait_kernel(const uint32_t* __restrict__ flags, int ep, uint32_t epoch) {
+  if (threadIdx.x < ep) {
+    while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(64);
+    __threadfence_system();
+  }
+}
+
+// dense d(probs)[t, e] = ret_f[send_row[t, e]] for routed pairs (0 elsewhere)
+__global__ void scatter_dprobs_kernel(const float* __restrict__ ret_f, const int32_t* __restrict__ send_row, float* __restrict__ dprobs,
+                                      int64_t pairs) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pairs) return;
+  const int r = send_row[i];
+  dprobs[i] = r >= 0 ? ret_f[r] : 0.f;
+}
+
 }  // namespace
+
+void moe_ep_dispatch(const void* x, const int32_t* send_offsets, const int32_t* send_row, const int32_t* counts_send, const float* probs,
+                     void* const* stage_x, int32_t* const* stage_idx, float* const* stage_prob, int32_t* const* recv_counts,
+                     uint32_t* const* flags, int n, int E_total, int E_local, int me, int ep, int Rs, int cols, uint32_t epoch,
+                     int32_t* done_counter, cudaStream_t s) {
+  EpPeers p{};
+  for (int i = 0; i < ep; ++i) {
+    p.stage_x[i] = stage_x[i]; p.stage_idx[i] = stage_idx[i]; p.stage_prob[i] = stage_prob[i];
+    p.recv_counts[i] = recv_counts[i]; p.flags[i] = flags[i];
+  }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t pairs = static_cast<int64_t>(n) * E_total;
+  int blocks = static_cast<int>(std::min<int64_t>((pairs + 7) / 8, sms * 4));
+  if (blocks < 1) blocks = 1;
+  ep_dispatch_kernel<<<blocks, 256, E_total * sizeof(int), s>>>(reinterpret_cast<const uint16_t*>(x), send_offsets, send_row, counts_send, probs, p,
+                                                               n, E_total, E_local, me, ep, Rs, cols, epoch, done_counter);
+}
+
+void moe_ep_recv_layout(const uint32_t* flags, const int32_t* recv_counts, int ep, int E_local, int Rs, int pad, int cap,
+                        uint32_t epoch, int32_t* offsets, int32_t* counts, int32_t* row_stage, int32_t* overflow, cudaStream_t s) {
+  ep_recv_layout_kernel<<<1, 1024, 0, s>>>(flags, recv_counts, ep, E_local, Rs, pad, cap, epoch, offsets, counts, row_stage, overflow);
+}
+
+void moe_ep_combine_push(const void* z, const int32_t* row_stage, const int32_t* row_idx, const float* side, const int32_t* offsets,
+                         int n_groups, int cap, int Rs, int cols, void* const* ret_x, float* const* ret_f, uint32_t* const* flags,
+                         int me, int ep, uint32_t epoch, int32_t* done_counter, cudaStream_t s) {
+  EpRet r{};
+  for (int i = 0; i < ep; ++i) { r.ret_x[i] = ret_x[i]; r.ret_f[i] = ret_f[i]; r.flags[i] = flags[i]; }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = std::min((cap + 7) / 8, sms * 4);
+  if (blocks < 1) blocks = 1;
+  ep_combine_push_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(z), row_stage, row_idx, side, offsets, n_groups, cap,
+                                                Rs, cols, r, me, ep, epoch, done_counter);
+}
+
+void moe_ep_wait(const uint32_t* flags, int ep, uint32_t epoch, cudaStream_t s) { ep_wait_kernel<<<1, 32, 0, s>>>(flags, ep, epoch); }
+
+void moe_scatter_dprobs(const float* ret_f, const int32_t* send_row, float* dprobs, int64_t pairs, cudaStream_t s) {
+  if (pairs <= 0) return;
+  scatter_dprobs_kernel<<<static_cast<int>((pairs + 255) / 256), 256, 0, s>>>(ret_f, send_row, dprobs, pairs);
+}
 
 void moe_router_topk_fwd(const float* logits, float* probs, uint8_t* map, int32_t* tokens_per_expert, int n, int E, int k,
                          bool pre_softmax, float scaling, cudaStream_t s) {

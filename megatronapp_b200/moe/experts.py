@@ -155,6 +155,12 @@ class GroupedMLP(MegatronModule):
             fuse = bool(self.config.gradient_accumulation_fusion)
             inter = mops.grouped_linear(rt.data, self.weight1, rt.layout, self.fc1_out, fuse)
             inter = self._activation(inter)
+            call = getattr(rt, "ep_call", None)
+            if call is not None:      # expert parallel: outputs go home over the EP arena
+                from .token_dispatcher import _GroupedLinearCombineEP
+
+                out = _GroupedLinearCombineEP.apply(inter, self.weight2, call, self.config.hidden_size, fuse)
+                return RaggedTokens(None, rt.layout, rt.probs, combined=out), None
             out = mops.grouped_linear_combine(inter, self.weight2, rt.probs, rt.layout, self.config.hidden_size, fuse)
             return RaggedTokens(None, rt.layout, rt.probs, combined=out), None
         x = permuted_local_hidden_states

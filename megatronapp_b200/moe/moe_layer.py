@@ -15,7 +15,7 @@ from ..transformer.mlp import MLP
 from ..transformer.module import MegatronModule
 from ..transformer.spec_utils import ModuleSpec, build_module
 from .router import TopKRouter
-from .token_dispatcher import (MoEAllGatherTokenDispatcher, MoEAlltoAllTokenDispatcher, MoEFusedDispatcher,
+from .token_dispatcher import (MoEAllGatherTokenDispatcher, MoEAlltoAllTokenDispatcher, MoEArenaDispatcher, MoEFusedDispatcher,
                                MoEPeerScatterDispatcher)
 
 
@@ -41,8 +41,10 @@ class MoELayer(MegatronModule):
             self.token_dispatcher = MoEAllGatherTokenDispatcher(self.num_local_experts, self.local_expert_indices, config)
         elif kind in ("alltoall", "alltoall_seq"):
             self.token_dispatcher = MoEAlltoAllTokenDispatcher(self.num_local_experts, self.local_expert_indices, config)
-        elif kind == "fused" or (kind == "flex" and ep == 1):
+        elif kind in ("flex", "fused") and ep == 1:
             self.token_dispatcher = MoEFusedDispatcher(self.num_local_experts, self.local_expert_indices, config)
+        elif kind in ("flex", "fused") and torch.cuda.is_available() and not config.use_cpu_initialization:
+            self.token_dispatcher = MoEArenaDispatcher(self.num_local_experts, self.local_expert_indices, config)
         elif kind == "flex":
             self.token_dispatcher = MoEPeerScatterDispatcher(self.num_local_experts, self.local_expert_indices, config)
         else:

@@ -264,6 +264,206 @@ class MoEFusedDispatcher(MoETokenDispatcher):
         return out.view(self.hidden_shape), None
 
 
+class _EPCall:
+    """State of one dispatch -> experts -> combine round trip over the EP arena (one MoE layer call)."""
+
+    def __init__(self, disp, send_lay, lay, row_idx, n_tokens, hidden):
+        self.disp, self.send_lay, self.lay, self.row_idx = disp, send_lay, lay, row_idx
+        self.n_tokens, self.hidden = n_tokens, hidden
+        self.dprob_row = None        # filled by the FC2 backward, shipped home by the dispatch backward
+
+
+class _EPDispatch(torch.autograd.Function):
+    """tokens [n, h] -> rows of my local experts [cap, h] (256-row padded ragged layout) over NVLink.
+    backward: d(rows) travel home the same way they will in the combine (push + gather-sum), d(probs) ride along."""
+
+    @staticmethod
+    def forward(ctx, x, probs, disp, send_lay):
+        call = disp._dispatch_forward(x, probs, send_lay)
+        ctx.call = call
+        ctx.probs_dtype = probs.dtype
+        disp._last_call = call
+        return call.xp
+
+    @staticmethod
+    def backward(ctx, dxp):
+        call = ctx.call
+        disp = call.disp
+        ret_x, ret_f = disp._push_home(dxp.contiguous(), call, call.dprob_row)
+        from ..ops import ext
+
+        dx = ext().moe_gather_sum(ret_x, call.send_lay.dest_row)
+        dprobs = ext().moe_scatter_dprobs(ret_f, call.send_lay.dest_row) if call.dprob_row is not None else None
+        return dx, (dprobs.to(ctx.probs_dtype) if dprobs is not None else None), None, None
+
+
+class _GroupedLinearCombineEP(torch.autograd.Function):
+    """Expert FC2 on the owner (router probability in the GEMM epilogue) + combine over NVLink + gather-sum at home."""
+
+    @staticmethod
+    def forward(ctx, h, weight, call, stride, fuse_wgrad):
+        from ..ops import ext
+        from ..ops import moe as mops
+
+        ctx.call, ctx.stride, ctx.fuse = call, stride, fuse_wgrad
+        z = mops.grouped_gemm(h, weight, call.lay, stride, row_scale=call.lay.row_prob)
+        ret_x, _ = call.disp._push_home(z, call, None)
+        out = ext().moe_gather_sum(ret_x, call.send_lay.dest_row)
+        ctx.save_for_backward(h, weight, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ..ops import ext
+        from ..ops import moe as mops
+
+        h, weight, z = ctx.saved_tensors
+        call = ctx.call
+        disp = call.disp
+        stage = disp._dispatch_rows_only(dout.contiguous(), call)          # dOut rows land in my staging again
+        dprob_stage = torch.zeros(disp.ep_size * disp.Rs, dtype=torch.float32, device=dout.device)
+        dy = ext().moe_gather_rows(stage, call.lay.row_slot, 1, call.lay.row_prob, call.lay.offsets, call.lay.E_local, z,
+                                   dprob_stage)
+        call.dprob_row = dprob_stage[call.lay.row_slot.clamp(min=0).long()]
+        dh = mops.grouped_gemm(dy, weight, call.lay, ctx.stride, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = mops.grouped_wgrad(dy, h, weight, call.lay, ctx.stride, ctx.fuse) if ctx.needs_input_grad[1] else None
+        return dh, dw, None, None, None
+
+
+class MoEArenaDispatcher(MoETokenDispatcher):
+    """``--moe-token-dispatcher-type flex`` with expert parallelism: sync-free dispatch / combine over the EP symmetric arena.
+
+    Every source rank writes its routed rows straight into the expert owner's staging buffer with NVLink stores
+    (``moe.cu: ep_dispatch_kernel``), together with its per-expert counts, the slot each row returns to and the router
+    probability; the owner turns the counts into the ragged 256-row padded layout on the device (``ep_recv_layout``),
+    runs the grouped tcgen05 GEMMs over it and pushes the (probability-scaled) outputs back to the slots the sources
+    named (``ep_combine_push``); the source finishes with a gather-sum.  No host synchronisation, no NCCL, no padding to a
+    capacity factor: the only static bound is the compact buffer size (``B200_MOE_SLACK`` x the balanced load; an overflow
+    raises a device flag that ``check_overflow()`` reports).  Parity: reference token_dispatcher.py:248-706 (alltoall) and
+    the DeepEP ``flex`` dispatcher fused_a2a.py:66-202."""
+
+    def __init__(self, num_local_experts, local_expert_indices, config):
+        import os
+
+        super().__init__(config)
+        self.num_local_experts, self.local_expert_indices = num_local_experts, local_expert_indices
+        self.num_experts = config.num_moe_experts
+        self.slack = float(os.environ.get("B200_MOE_SLACK", "2.0"))
+        self._ready = False
+        self._last_call = None
+
+    # ---- arena ------------------------------------------------------------------------------------------------
+    def _setup(self, n, hidden, dtype, device):
+        from ..comm.arena import get_arena
+
+        ep, El, k = self.ep_size, self.num_local_experts, self.config.moe_router_topk
+        self.n, self.hidden = n, hidden
+        self.Rs = (n * min(k, El) + 7) // 8 * 8                              # staging rows per source
+        self.cap_send = n * min(k, self.num_experts)
+        bal = n * k                                                          # balanced load: what I send == what I receive
+        self.cap = (int(self.slack * bal) + 255) // 256 * 256 + 256 * El
+        sizes = {"ep_stage_x": ep * self.Rs * hidden * 2, "ep_stage_idx": ep * self.Rs * 4, "ep_stage_prob": ep * self.Rs * 4,
+                 "ep_recv_counts": ep * El * 4 + 64, "ep_flags_d": 256, "ep_flags_c": 256,
+                 "ep_ret_x": self.cap_send * hidden * 2, "ep_ret_f": self.cap_send * 4}
+        total = sum((v + 1023) // 1024 * 1024 for v in sizes.values()) + (1 << 20)
+        self.arena = get_arena("ep", self.ep_group, total)
+        self.reg = {name: self.arena.region(name, nbytes) for name, nbytes in sizes.items()}
+        a = self.arena
+        self.stage_x = a.local(self.reg["ep_stage_x"], (ep * self.Rs, hidden), dtype)
+        self.stage_idx = a.local(self.reg["ep_stage_idx"], (ep * self.Rs,), torch.int32)
+        self.stage_prob = a.local(self.reg["ep_stage_prob"], (ep * self.Rs,), torch.float32)
+        self.ret_x = a.local(self.reg["ep_ret_x"], (self.cap_send, hidden), dtype)
+        self.ret_f = a.local(self.reg["ep_ret_f"], (self.cap_send,), torch.float32)
+        self.done = torch.zeros(2, dtype=torch.int32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self._ready = True
+
+    def check_overflow(self) -> bool:
+        """True when some call received more rows than the compact buffer holds (host sync; call it at log intervals)."""
+        return self._ready and bool(self.overflow.item())
+
+    # ---- wire protocol ------------------------------------------------------------------------------------------
+    def _send(self, x, send_lay, probs_f32):
+        from ..ops import ext
+
+        a, r = self.arena, self.reg
+        epoch = a.next_epoch(r["ep_flags_d"])
+        ext().moe_ep_dispatch(x, send_lay.offsets, send_lay.dest_row, send_lay.counts, probs_f32, a.ptrs(r["ep_stage_x"]),
+                              a.ptrs(r["ep_stage_idx"]), a.ptrs(r["ep_stage_prob"]), a.ptrs(r["ep_recv_counts"]),
+                              a.ptrs(r["ep_flags_d"]), self.num_local_experts, a.rank, self.Rs, epoch, self.done[0:1])
+        return epoch
+
+    def _dispatch_forward(self, x, probs, send_lay):
+        from ..ops import ext
+        from ..ops.moe import RaggedLayout
+
+        if not self._ready:
+            self._setup(x.shape[0], x.shape[1], x.dtype, x.device)
+        if x.shape[0] != self.n or x.shape[1] != self.hidden:
+            raise RuntimeError("MoEArenaDispatcher: token count / hidden size changed after the arena was sized")
+        a, r = self.arena, self.reg
+        epoch = self._send(x.contiguous(), send_lay, probs.detach().float().contiguous())
+        El = self.num_local_experts
+        offsets, counts, row_stage = ext().moe_ep_recv_layout(a.local_ptr + r["ep_flags_d"].offset,
+                                                              a.local_ptr + r["ep_recv_counts"].offset, self.ep_size, El, self.Rs,
+                                                              256, self.cap, epoch, self.overflow)
+        safe = row_stage.clamp(min=0).long()
+        valid = row_stage >= 0
+        row_prob = self.stage_prob[safe] * valid
+        row_idx = self.stage_idx[safe]
+        lay = RaggedLayout(x.shape[0], 1, 0, El, self.cap, counts, offsets, row_stage, row_prob, None)
+        call = _EPCall(self, send_lay, lay, row_idx, x.shape[0], x.shape[1])
+        call.xp = ext().moe_gather_rows(self.stage_x, row_stage, 1, None, offsets, El, None, None)
+        return call
+
+    def _dispatch_rows_only(self, x, call):
+        """Backward of the combine: the same routing again, payload = dOut rows; returns my staging buffer."""
+        from ..ops import ext
+
+        a, r = self.arena, self.reg
+        epoch = self._send(x, call.send_lay, None)
+        ext().moe_ep_wait(a.local_ptr + r["ep_flags_d"].offset, self.ep_size, epoch)
+        return self.stage_x
+
+    def _push_home(self, z, call, side):
+        from ..ops import ext
+
+        a, r = self.arena, self.reg
+        epoch = a.next_epoch(r["ep_flags_c"])
+        ext().moe_ep_combine_push(z, call.lay.row_slot, call.row_idx, side, call.lay.offsets, call.lay.E_local, self.Rs,
+                                  a.ptrs(r["ep_ret_x"]), a.ptrs(r["ep_ret_f"]), a.ptrs(r["ep_flags_c"]), a.rank, epoch,
+                                  self.done[1:2])
+        ext().moe_ep_wait(a.local_ptr + r["ep_flags_c"].offset, self.ep_size, epoch)
+        return self.ret_x, self.ret_f
+
+    # ---- dispatcher API -------------------------------------------------------------------------------------------
+    def token_permutation(self, hidden_states, probs, routing_map):
+        from ..ops import moe as mops
+
+        if not hidden_states.is_cuda:
+            raise NotImplementedError("the arena (flex) dispatcher needs CUDA peers; use --moe-token-dispatcher-type alltoall on CPU")
+        self.hidden_shape = hidden_states.shape
+        x = hidden_states.reshape(-1, self.hidden_shape[-1])
+        if self.etp_size > 1:
+            routing_map = _gather_along_first_dim(routing_map.to(torch.uint8), self.etp_group).bool()
+            probs = _GatherFirstDimAutograd.apply(probs.contiguous(), self.etp_group)
+            x = _GatherFirstDimAutograd.apply(x.contiguous(), self.etp_group)
+        send_lay = mops.build_layout(routing_map.contiguous(), probs, 0, self.num_experts, self.config.moe_router_topk, pad=1)
+        xp = _EPDispatch.apply(x, probs, self, send_lay)
+        call = self._last_call
+        rt = RaggedTokens(xp, call.lay, probs)
+        rt.ep_call = call
+        return rt, call.lay.counts
+
+    def token_unpermutation(self, expert_out, bias=None):
+        if not (isinstance(expert_out, RaggedTokens) and expert_out.combined is not None):
+            raise TypeError("MoEArenaDispatcher needs GroupedMLP experts (--moe-grouped-gemm)")
+        out = expert_out.combined
+        if self.etp_size > 1:
+            out = _ReduceScatterFirstDimAutograd.apply(out, self.etp_group)
+        return out.view(self.hidden_shape), None
+
+
 class _PeerScatter(torch.autograd.Function):
     """rows -> owner buffers via the fused NVLink scatter kernel; backward = the reverse scatter."""
 

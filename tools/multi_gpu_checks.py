@@ -57,6 +57,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "multi.json"))
     ap.add_argument("--skip-model", action="store_true")
+    ap.add_argument("--skip-moe", action="store_true")
+    ap.add_argument("--skip-kernels", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -76,6 +78,8 @@ def main():
             print(k, v, flush=True)
 
     try:
+        if a.skip_kernels:
+            raise KeyboardInterrupt
         Mt = 2048 * world          # bench.py: micro-batch = TP degree, seq 2048
         shapes = [(Mt, 4096, 16384 // world, "fc1"), (Mt, 4096, 12288 // world, "qkv")]
         arena = SymmetricArena(group, 2 * (2 * Mt * 16384 * 2) + (200 << 20))
@@ -228,6 +232,8 @@ def main():
             log(f"bucket_rs_{wname}_ms", {"fused": tf_, "mul+nccl": tn_, "GBs_per_rank_fused": n * 4 * (world - 1) / world / tf_ / 1e6})
         arena.barrier()
         torch.cuda.synchronize()
+    except KeyboardInterrupt:
+        pass
     except Exception as e:  # noqa: BLE001
         import traceback
 
@@ -256,6 +262,89 @@ def main():
             import traceback
 
             log("EXCEPTION_model", traceback.format_exc()[-1500:])
+    # ---------------- expert parallel MoE layer: arena dispatcher + grouped GEMMs vs NCCL all-to-all + per-expert modules
+    if not a.skip_moe:
+        try:
+            import torch.nn.functional as F
+            from megatronapp_b200.comm.arena import destroy_arenas
+            from megatronapp_b200.config.transformer_config import TransformerConfig
+            from megatronapp_b200.models.gpt.gpt_layer_specs import get_mlp_module_spec
+            from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+            from megatronapp_b200.transformer.spec_utils import build_module
+
+            ps.destroy_model_parallel()
+            ps.initialize_model_parallel(1, 1, expert_model_parallel_size=world)
+            model_parallel_cuda_manual_seed(123)
+            E = 8 if 8 % world == 0 else 2 * world
+
+            def build(kind, grouped, H, FF):
+                cfg = TransformerConfig(num_layers=1, hidden_size=H, num_attention_heads=8, ffn_hidden_size=FF, num_moe_experts=E,
+                                        moe_router_topk=2, expert_model_parallel_size=world, moe_token_dispatcher_type=kind,
+                                        add_bias_linear=False, activation_func=F.silu, gated_linear_unit=True,
+                                        moe_grouped_gemm=grouped, bf16=True, params_dtype=torch.bfloat16, moe_aux_loss_coeff=0.0)
+                layer = build_module(get_mlp_module_spec(False, E, grouped), config=cfg).cuda()
+                with torch.no_grad():
+                    torch.manual_seed(11)
+                    layer.router.weight.copy_(torch.randn_like(layer.router.weight.float()) * 0.3)
+                    for i, e in enumerate(layer.local_expert_indices):
+                        g = torch.Generator().manual_seed(1000 + e)
+                        w1 = (torch.randn(2 * FF, H, generator=g) * 0.03).bfloat16().cuda()
+                        w2 = (torch.randn(H, FF, generator=g) * 0.03).bfloat16().cuda()
+                        if grouped:
+                            layer.experts.weight1[i * 2 * FF:(i + 1) * 2 * FF].copy_(w1)
+                            layer.experts.weight2[i * H:(i + 1) * H].copy_(w2)
+                        else:
+                            layer.experts.local_experts[i].linear_fc1.weight.copy_(w1)
+                            layer.experts.local_experts[i].linear_fc2.weight.copy_(w2)
+                return layer
+
+            def run(layer, x, go):
+                x = x.clone().requires_grad_(True)
+                for p_ in layer.parameters():
+                    p_.grad = None
+                out, _ = layer(x)
+                (out.float() * go).sum().backward()
+                return out.detach(), x.grad.detach()
+
+            H, FF, T = 1024, 2048, 1024
+            gx = torch.Generator().manual_seed(77 + rank)
+            x = (torch.randn(T, 2, H, generator=gx) * 0.5).bfloat16().cuda()
+            go = torch.randn(T, 2, H, generator=torch.Generator().manual_seed(5 + rank)).cuda()
+            ref_layer = build("alltoall", False, H, FF)
+            o_ref, dx_ref = run(ref_layer, x, go)
+            w1_ref = torch.cat([ex.linear_fc1.weight.grad.float() for ex in ref_layer.experts.local_experts])
+            w2_ref = torch.cat([ex.linear_fc2.weight.grad.float() for ex in ref_layer.experts.local_experts])
+            dr_ref = ref_layer.router.weight.grad.float().clone()
+            fl = build("flex", True, H, FF)
+            o_f, dx_f = run(fl, x, go)
+            log("moe_ep_dispatcher", type(fl.token_dispatcher).__name__)
+            log("moe_ep_err", {"out": rel_err(o_f, o_ref), "dx": rel_err(dx_f, dx_ref),
+                               "drouter": rel_err(fl.router.weight.grad.float(), dr_ref),
+                               "dw1": rel_err(fl.experts.weight1.grad.float(), w1_ref),
+                               "dw2": rel_err(fl.experts.weight2.grad.float(), w2_ref),
+                               "overflow": bool(fl.token_dispatcher.check_overflow())})
+            o_f2, dx_f2 = run(fl, x, go)
+            log("moe_ep_deterministic", bool(torch.equal(o_f, o_f2) and torch.equal(dx_f, dx_f2)))
+            del ref_layer, fl
+            destroy_arenas()
+            # timing at Mixtral-8x7B layer dimensions (h 4096, ffn 14336, 8 experts, top-2), 4096 tokens per rank
+            H, FF, T = 4096, 14336, 2048
+            x = (torch.randn(T, 2, H, generator=gx) * 0.5).bfloat16().cuda()
+            go = torch.randn(T, 2, H, generator=torch.Generator().manual_seed(5 + rank)).cuda()
+            tm = {}
+            for name, kind, grouped in (("arena+grouped", "flex", True), ("nccl_a2a+grouped_loop", "alltoall", True),
+                                        ("nccl_a2a+sequential", "alltoall", False)):
+                layer = build(kind, grouped, H, FF)
+                tm[name] = timed(lambda: run(layer, x, go), 8, 3)
+                del layer
+                torch.cuda.empty_cache()
+            flops = 3 * 2.0 * (T * 2 * 2) * H * (3 * FF)          # fwd + bwd, top-2, gate/up/down
+            tm["tflops_per_gpu_arena"] = flops / tm["arena+grouped"] / 1e9
+            log("moe_ep_layer_fwd_bwd_ms", tm)
+        except Exception:  # noqa: BLE001
+            import traceback
+
+            log("EXCEPTION_moe", traceback.format_exc()[-2500:])
     if rank == 0:
         os.makedirs(os.path.dirname(a.out), exist_ok=True)
         json.dump(res, open(a.out, "w"), indent=1)

@@ -105,6 +105,14 @@ def main():
     extra = [k for k in ref_sd if k not in own_sd]
     shape_bad = [k for k in own_sd if k in ref_sd and tuple(own_sd[k].shape) != tuple(ref_sd[k].shape)]
     assert not missing and not shape_bad, (missing[:5], extra[:5], shape_bad[:5])
+    # both arms of bench.py start from their OWN random init: compare the init distributions parameter by parameter
+    init_stats = {}
+    for k, v in own_sd.items():
+        if v.dim() >= 2 or k.endswith("position_embeddings.weight"):
+            so, sr = float(v.float().std()), float(ref_sd[k].float().std())
+            kk = ".".join(p for p in k.split(".") if not p.isdigit())
+            init_stats.setdefault(kk, []).append(round(so / max(sr, 1e-12), 4))
+    init_stats = {k: (min(v), max(v)) for k, v in init_stats.items()}
     with torch.no_grad():
         for k, v in own_sd.items():
             v.copy_(ref_sd[k].to(v.dtype))
@@ -133,6 +141,7 @@ def main():
     diffs = [abs(x - y) for x, y in zip(ref_losses, own_losses)]
     res = {"tp": tp, "steps": a.steps, "reference": ref_losses, "own": own_losses, "abs_diff": diffs,
            "max_abs_diff": max(diffs), "max_abs_diff_first10": max(diffs[:10]),
+           "own_init_std_over_reference_init_std": init_stats,
            "config": {"layers": a.layers, "hidden": a.hidden, "heads": a.heads, "ffn": a.ffn, "seq": a.seq, "vocab": a.vocab,
                       "micro_batch": a.micro_batch, "n_mb": a.n_mb}}
     if rank == 0:
