@@ -42,6 +42,7 @@ class ShardedTensor:
     prepend_axis_num: int = 0
     allow_shape_mismatch: bool = False
     flattened_range: Optional[slice] = None
+    replica_count: Optional[int] = None   # size of the group the last replica_id component indexes (fully-parallel save)
 
     @classmethod
     def from_rank_offsets(cls, key, data, *rank_offsets, replica_id=(0,), prepend_axis_num=0,
@@ -67,6 +68,35 @@ class ShardedObject:
     key: str
     data: object
     replica_id: Tuple[int, ...] = (0,)
+    global_shape: Tuple[int, ...] = (1,)
+    global_offset: Tuple[int, ...] = (0,)
+
+
+def _dp_world() -> int:
+    try:
+        return ps.get_data_parallel_world_size(with_context_parallel=True) if ps.model_parallel_is_initialized() else 1
+    except Exception:  # noqa: BLE001
+        return 1
+
+
+def _from_offsets_with_prepend(key, data, prepend_offsets, data_offsets, replica_id, allow_shape_mismatch=False,
+                               prepend_axis_num=None, **_kw):
+    """``prepend_offsets`` (axis, rank, fragments) describe axes that exist only in the GLOBAL tensor (stacked layers /
+    experts, reference ``ShardedTensor.from_rank_offsets(..., prepend_axis_num=)``); ``data_offsets`` index axes of ``data``."""
+    prepend_offsets = tuple(prepend_offsets)
+    pre = len(prepend_offsets)
+    gshape = [1] * pre + list(data.shape)
+    goff = [0] * (pre + data.dim())
+    frag = [1] * (pre + data.dim())
+    for i, (axis, r, n) in enumerate(prepend_offsets):
+        gshape[i], goff[i], frag[i] = n, r, n
+    for axis, r, n in data_offsets:
+        a = axis + pre
+        gshape[a] = data.shape[axis] * n
+        goff[a] = data.shape[axis] * r
+        frag[a] = n
+    return ShardedTensor(key, data, data.dtype, tuple(data.shape), tuple(gshape), tuple(goff), tuple(frag), replica_id,
+                         pre, allow_shape_mismatch)
 
 
 def make_tp_sharded_tensor_for_checkpoint(tensor, key, tp_axis=0, replica_id=None, prepend_offsets=(), **kw):
@@ -74,8 +104,9 @@ def make_tp_sharded_tensor_for_checkpoint(tensor, key, tp_axis=0, replica_id=Non
     dp_rank = ps.get_data_parallel_rank(with_context_parallel=True) if ps.model_parallel_is_initialized() else 0
     if replica_id is None:
         replica_id = (0, 0, dp_rank)
-    return ShardedTensor.from_rank_offsets(key, tensor, *prepend_offsets, (tp_axis, tp_rank, tp_size),
-                                           replica_id=replica_id, **kw)
+    st = _from_offsets_with_prepend(key, tensor, prepend_offsets, [(tp_axis, tp_rank, tp_size)], replica_id, **kw)
+    st.replica_count = _dp_world()
+    return st
 
 
 def make_sharded_tensor_for_checkpoint(tensor, key, prepend_offsets=(), replica_id=None, **kw):
@@ -83,7 +114,9 @@ def make_sharded_tensor_for_checkpoint(tensor, key, prepend_offsets=(), replica_
     dp_rank = ps.get_data_parallel_rank(with_context_parallel=True) if ps.model_parallel_is_initialized() else 0
     if replica_id is None:
         replica_id = (0, tp_rank, dp_rank)
-    return ShardedTensor.from_rank_offsets(key, tensor, *prepend_offsets, replica_id=replica_id, **kw)
+    st = _from_offsets_with_prepend(key, tensor, prepend_offsets, [], replica_id, **kw)
+    st.replica_count = _dp_world()
+    return st
 
 
 def make_sharded_tensors_for_checkpoint(state_dict: Dict[str, torch.Tensor], prefix: str,

@@ -29,7 +29,8 @@ def _expert_replica(sd: dict) -> dict:
     out = {}
     for k, t in sd.items():
         rid = tuple(t.replica_id) if isinstance(t.replica_id, (tuple, list)) else (t.replica_id,)
-        out[k] = dataclasses.replace(t, replica_id=rid[:-1] + (edp,)) if len(rid) >= 1 else t
+        out[k] = dataclasses.replace(t, replica_id=rid[:-1] + (edp,), replica_count=ps.get_state().world("edp")) \
+            if (len(rid) >= 1 and hasattr(t, "replica_count")) else t
     return out
 
 

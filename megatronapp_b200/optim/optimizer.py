@@ -454,7 +454,69 @@ class MegatronOptimizer:
             self.grad_scaler.load_state_dict(sd["grad_scaler"])
 
     def sharded_state_dict(self, model_sharded_state_dict=None, is_loading=False, **kw):
-        return self.state_dict()
+        """Optimizer state in MODEL SPACE, the reference's layout (``dist_checkpointing/optimizer.py:75-140``,
+        ``distrib_optimizer.sharded_param_state_fs_model_space``): for every model ShardedTensor ``K`` the fp32 main
+        parameter and both Adam moments are ShardedTensors ``optimizer.state.{param|fp32_param,exp_avg,exp_avg_sq}.K`` with
+        the parameter's own sharding; under the distributed optimizer each rank contributes the run of the flattened
+        local parameter it owns (``flattened_range``).  Such a checkpoint loads under any TP / PP / DP layout."""
+        from dataclasses import replace
+
+        from ..ckpt.sharded import ShardedTensor
+
+        if model_sharded_state_dict is None:
+            return self.state_dict()
+        if any(st.master_cpu is not None for st in self.states):
+            raise NotImplementedError("sharded optimizer state with --optimizer-cpu-offload: use --ckpt-format torch")
+        owners = []                      # (ptr_lo, ptr_hi, state, param, buffer start)
+        for st in self.states:
+            for p in st.buf.params:
+                s, e, _ = st.buf.param_index[p]
+                owners.append((p.data_ptr(), p.data_ptr() + p.numel() * p.element_size(), st, p, s))
+        owners.sort(key=lambda o: o[0])
+        import bisect
+
+        los = [o[0] for o in owners]
+        out = {}
+        main_name = "param" if self.sharded else "fp32_param"
+        for mkey, mst in model_sharded_state_dict.items():
+            if not isinstance(mst, ShardedTensor) or mst.data is None or not torch.is_tensor(mst.data):
+                continue
+            ptr = mst.data.data_ptr()
+            i = bisect.bisect_right(los, ptr) - 1
+            if i < 0 or ptr >= owners[i][1] or not mst.data.is_contiguous():
+                continue                  # buffers / frozen tensors: no optimizer state
+            _, _, st, p, s = owners[i]
+            off = (ptr - p.data_ptr()) // p.element_size()
+            a, b = s + off, s + off + mst.data.numel()
+            for name, attr in ((main_name, "master"), ("exp_avg", "exp_avg"), ("exp_avg_sq", "exp_avg_sq")):
+                flat = getattr(st, attr)
+                key = f"optimizer.state.{name}.{mst.key}"
+                if not st.sharded:
+                    out[f"optimizer.state.{name}.{mkey}"] = replace(mst, key=key, data=flat[a:b].view(mst.data.shape),
+                                                                     dtype=flat.dtype)
+                    continue
+                for (ss, se), o in zip(st.segments, st.seg_offsets):
+                    lo, hi = max(a, ss), min(b, se)
+                    if lo < hi:
+                        rid = tuple(mst.replica_id) if isinstance(mst.replica_id, (tuple, list)) else (mst.replica_id,)
+                        out[f"optimizer.state.{name}.{mkey}"] = replace(
+                            mst, key=key, data=flat[o + lo - ss:o + hi - ss], dtype=flat.dtype,
+                            flattened_range=slice(lo - a, hi - a), replica_id=rid[:-1] + (0,), replica_count=1)
+        return out
+
+    def sharded_common_state(self) -> dict:
+        """The non-tensor part of the optimizer state (goes to ``common.pt``)."""
+        sd = {"step": self.step_count, "param_groups": [{k: v for k, v in g.items()} for g in self.param_groups]}
+        if self.grad_scaler is not None:
+            sd["grad_scaler"] = self.grad_scaler.state_dict()
+        return sd
+
+    def load_sharded_common_state(self, sd: dict) -> None:
+        self.step_count = sd.get("step", 0)
+        for g, sg in zip(self.param_groups, sd.get("param_groups", [])):
+            g.update({k: v for k, v in sg.items() if k in ("lr", "weight_decay")})
+        if self.grad_scaler is not None and "grad_scaler" in sd:
+            self.grad_scaler.load_state_dict(sd["grad_scaler"])
 
 
 Float16OptimizerWithFloat16Params = MegatronOptimizer
@@ -505,6 +567,21 @@ class ChainedOptimizer:
     def load_state_dict(self, sd):
         for o, s in zip(self.chained_optimizers, sd):
             o.load_state_dict(s)
+
+    def sharded_state_dict(self, model_sharded_state_dict=None, is_loading=False, **kw):
+        if model_sharded_state_dict is None:
+            return self.state_dict()
+        out = {}
+        for o in self.chained_optimizers:
+            out.update(o.sharded_state_dict(model_sharded_state_dict, is_loading, **kw))
+        return out
+
+    def sharded_common_state(self):
+        return [o.sharded_common_state() for o in self.chained_optimizers]
+
+    def load_sharded_common_state(self, sd):
+        for o, s in zip(self.chained_optimizers, sd):
+            o.load_sharded_common_state(s)
 
 
 def get_megatron_optimizer(config: OptimizerConfig, model_chunks, no_weight_decay_cond=None,

@@ -20,12 +20,13 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ..ckpt import sharded
+from ..ckpt import sharded, torch_dist
 from ..parallel import state as ps
 from ..parallel.random import get_cuda_rng_tracker
 
 _CHECKPOINT_VERSION = 3.0
 _ASYNC_THREADS: List[threading.Thread] = []
+_PENDING: List[dict] = []          # async saves whose tracker update is deferred to maybe_finalize_async_save
 
 
 def get_checkpoint_tracker_filename(checkpoints_path):
@@ -163,6 +164,7 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
     base = get_checkpoint_name(args.save, iteration, return_base_dir=True)
     fmt = args.ckpt_format
     rng_state = get_rng_state()
+    pending = []
     if fmt == "torch":
         dp_rank = ps.get_data_parallel_rank(with_context_parallel=True)
         name = get_checkpoint_name(args.save, iteration)
@@ -186,43 +188,116 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
             oname = os.path.join(os.path.dirname(name), f"distrib_optim.pt" if dp_rank == 0 else f"distrib_optim_dp{dp_rank:03d}.pt")
             _write(_to_cpu(optimizer.state_dict()), oname, args.async_save)
     else:
-        ssd = {}
         common = {"args": args, "checkpoint_version": _CHECKPOINT_VERSION, "iteration": iteration,
                   "num_floating_point_operations_so_far": num_floating_point_operations_so_far,
                   "opt_param_scheduler": opt_param_scheduler.state_dict() if opt_param_scheduler else None,
-                  "rng_state": rng_state}
+                  "rng_state": rng_state, "parallel_layout": _layout_tag()}
+        dl = getattr(args, "_dataloader_state_fn", None)
+        if dl is not None:
+            common["dataloader_state"] = dl()        # reference checkpointing.py:681 (train_data_iterator.save_state)
         with _full_params(model, writeback=False):
-            for i, m in enumerate(model):
-                prefix = "" if len(model) == 1 else f"model{i}."
-                ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
-            sharded.save(ssd, base, common)
-        if optimizer is not None and not args.no_save_optim:
-            torch.save(_to_cpu(optimizer.state_dict()), os.path.join(base, f"optim_{rank:05d}.pt"))
+            ssd = _model_sharded_state_dict(model, args)
+            if fmt == "b200_sharded":
+                sharded.save(ssd, base, common)
+                if optimizer is not None and not args.no_save_optim:
+                    torch.save(_to_cpu(optimizer.state_dict()), os.path.join(base, f"optim_{rank:05d}.pt"))
+            else:
+                if optimizer is not None and not args.no_save_optim and hasattr(optimizer, "sharded_common_state"):
+                    ssd.update(optimizer.sharded_state_dict(ssd))
+                    common["optimizer"] = optimizer.sharded_common_state()
+                elif optimizer is not None and not args.no_save_optim:
+                    # optimizers without a model-space view (ZeRO-3 wrappers): per-rank state, same-layout restore only
+                    os.makedirs(base, exist_ok=True)
+                    _write(_to_cpu(optimizer.state_dict()), os.path.join(base, f"optim_{rank:05d}.pt"), args.async_save)
+                pending.append(torch_dist.save(ssd, base, common, async_save=bool(args.async_save)))
+    _finish_save(args, iteration, pending, defer=bool(args.async_save))
+
+
+def _layout_tag() -> dict:
+    if not ps.model_parallel_is_initialized():
+        return {}
+    return {"tp": ps.get_tensor_model_parallel_world_size(), "pp": ps.get_pipeline_model_parallel_world_size(),
+            "dp": ps.get_data_parallel_world_size(with_context_parallel=True), "ep": ps.get_expert_model_parallel_world_size()}
+
+
+def _model_sharded_state_dict(model, args) -> dict:
+    """Model keys in the reference's layout: homogeneous decoder layers stacked under one key (transformer_block.py:600)
+    unless the model is MoE / heterogeneous or ``--ckpt-... non-homogeneous`` was asked for."""
+    ssd = {}
+    for i, m in enumerate(model):
+        prefix = "" if len(model) == 1 else f"model{i}."
+        ssd.update(_unwrap(m).sharded_state_dict(prefix=prefix))
+    cfg = getattr(_unwrap(model[0]), "config", None)
+    homogeneous = (cfg is not None and getattr(cfg, "num_moe_experts", None) is None
+                   and not getattr(cfg, "heterogeneous_block_specs", False)
+                   and not getattr(args, "hetereogenous_dist_checkpoint", False)
+                   and not getattr(args, "ckpt_non_homogeneous_layers", False)
+                   and getattr(args, "ckpt_format", "torch_dist") != "b200_sharded")
+    if homogeneous:
+        ssd = torch_dist.stack_homogeneous_layers(ssd, cfg.num_layers)
+    return ssd
+
+
+def _finish_save(args, iteration, pending, defer: bool):
+    """A checkpoint becomes visible only when every rank's data is on disk: write the tracker after the (cross-rank)
+    finalize.  With ``--async-save`` this runs from ``maybe_finalize_async_save`` (reference async_utils.py:90-230)."""
+    rec = {"args_save": args.save, "iteration": iteration, "pending": pending, "threads": list(_ASYNC_THREADS)}
+    if defer:
+        _PENDING.append(rec)
+        return
+    _complete(rec)
+
+
+def _complete(rec):
+    for t in rec["threads"]:
+        t.join()
+        if t in _ASYNC_THREADS:
+            _ASYNC_THREADS.remove(t)
+    for p in rec["pending"]:
+        p.finalize()
+    rank = dist.get_rank() if dist.is_initialized() else 0
     if dist.is_initialized():
         dist.barrier()
     if rank == 0:
-        with open(get_checkpoint_tracker_filename(args.save), "w") as f:
-            f.write(str(iteration))
-        print(f"  successfully saved checkpoint from iteration {iteration:7d} to {args.save}", flush=True)
+        tr = get_checkpoint_tracker_filename(rec["args_save"])
+        with open(tr + ".tmp", "w") as f:
+            f.write(str(rec["iteration"]))
+        os.replace(tr + ".tmp", tr)
+        print(f"  successfully saved checkpoint from iteration {rec['iteration']:7d} to {rec['args_save']}", flush=True)
     if dist.is_initialized():
         dist.barrier()
+
+
+def _atomic_torch_save(obj, path):
+    torch.save(obj, path + ".tmp")
+    os.replace(path + ".tmp", path)
 
 
 def _write(obj, path, async_save):
     if async_save:
-        t = threading.Thread(target=torch.save, args=(obj, path), daemon=False)
+        t = threading.Thread(target=_atomic_torch_save, args=(obj, path), daemon=False)
         t.start()
         _ASYNC_THREADS.append(t)
     else:
-        torch.save(obj, path)
+        _atomic_torch_save(obj, path)
 
 
 def maybe_finalize_async_save(blocking: bool = False):
-    for t in list(_ASYNC_THREADS):
-        if blocking:
-            t.join()
-        if not t.is_alive():
-            _ASYNC_THREADS.remove(t)
+    """Complete the oldest outstanding async save once EVERY rank's writer has finished (an all-reduce of the local
+    "done" flags keeps the ranks in lock step); only then is the tracker file updated."""
+    while _PENDING:
+        rec = _PENDING[0]
+        done = all(not t.is_alive() for t in rec["threads"]) and all(p.ready() for p in rec["pending"])
+        if not blocking:
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                flag = torch.tensor([1 if done else 0], dtype=torch.int32,
+                                    device="cuda" if (torch.cuda.is_available() and dist.get_backend() == "nccl") else "cpu")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                done = bool(flag.item())
+            if not done:
+                return
+        _PENDING.pop(0)
+        _complete(rec)
 
 
 def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", strict=True, args=None):
@@ -251,7 +326,43 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
         iteration = args.ckpt_step
     base = get_checkpoint_name(load_dir, iteration, release, return_base_dir=True)
     is_sharded = os.path.exists(os.path.join(base, "metadata.json"))
-    if is_sharded:
+    if is_sharded and torch_dist.is_torch_dist_checkpoint(base):
+        # reference layout (.metadata + __*.distcp): model AND optimizer state reshard to the current layout
+        sd = torch_dist.load_common_state_dict(base)
+        want_opt = optimizer is not None and not args.finetune and not args.no_load_optim and "optimizer" in sd \
+            and hasattr(optimizer, "load_sharded_common_state")
+        with _full_params(model, writeback=True):
+            ssd = _model_sharded_state_dict(model, args)
+            md = torch_dist.read_metadata(base)
+            if not any(k.startswith("decoder.layers.") and not k[len("decoder.layers."):].split(".")[0].isdigit()
+                       for k in md.state_dict_metadata) and any(".layers." in k for k in md.state_dict_metadata):
+                # checkpoint written with per-layer keys (non-homogeneous / MoE / older runs): ask for the same layout
+                ssd = {}
+                for i, m in enumerate(model):
+                    ssd.update(_unwrap(m).sharded_state_dict(prefix="" if len(model) == 1 else f"model{i}."))
+            model_keys = set(ssd)
+            if want_opt:
+                ssd.update(optimizer.sharded_state_dict(ssd, is_loading=True))
+            try:
+                torch_dist.load(ssd, base, strict=strict)
+            except KeyError:
+                if not want_opt:
+                    raise
+                # optimizer tensors absent (saved with --no-save-optim or by another optimizer): weights only
+                torch_dist.load({k: v for k, v in ssd.items() if k in model_keys}, base, strict=strict)
+                want_opt = False
+        if optimizer is not None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+            op = os.path.join(base, f"optim_{rank:05d}.pt")
+            if want_opt:
+                optimizer.load_sharded_common_state(sd["optimizer"])
+            elif (not args.finetune and not args.no_load_optim and os.path.exists(op)
+                  and sd.get("parallel_layout") in (None, _layout_tag())):
+                optimizer.load_state_dict(torch.load(op, map_location="cpu", weights_only=False))
+            else:
+                optimizer.reload_model_params()
+        _fix_qkv_ordering_if_needed(model, sd)
+    elif is_sharded:
         ssd = {}
         with _full_params(model, writeback=True):
             for i, m in enumerate(model):
@@ -261,9 +372,13 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
         sd = sharded.load_common_state_dict(base)
         rank = dist.get_rank() if dist.is_initialized() else 0
         op = os.path.join(base, f"optim_{rank:05d}.pt")
-        if optimizer is not None and not args.finetune and not args.no_load_optim and os.path.exists(op):
+        same_layout = sd.get("parallel_layout") in (None, _layout_tag())
+        if optimizer is not None and not args.finetune and not args.no_load_optim and os.path.exists(op) and same_layout:
             optimizer.load_state_dict(torch.load(op, map_location="cpu", weights_only=False))
         elif optimizer is not None:
+            if not same_layout and not args.finetune and not args.no_load_optim:
+                print(f"WARNING: per-rank optimizer files were written under layout {sd.get('parallel_layout')}, current "
+                      f"layout is {_layout_tag()}: optimizer state is re-initialised from the loaded weights", flush=True)
             optimizer.reload_model_params()
     else:
         name = get_checkpoint_name(load_dir, iteration, release)
@@ -310,6 +425,31 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
     return iteration, sd.get("num_floating_point_operations_so_far", 0)
 
 
+def _fix_qkv_ordering_if_needed(model, sd) -> None:
+    """Checkpoints older than version 2.0 store the fused QKV projection as [q_all; k_all; v_all] (version 0) or
+    [heads, 3, hn] (version 1); current layout is per-group [q..., k, v] (reference checkpointing.py:822
+    ``fix_query_key_value_ordering``)."""
+    version = sd.get("checkpoint_version", _CHECKPOINT_VERSION)
+    if version is None or version >= 2.0:
+        return
+    for m in model:
+        core = _unwrap(m)
+        for name, p in core.named_parameters():
+            if not name.endswith(("linear_qkv.weight", "linear_qkv.bias", "query_key_value.weight", "query_key_value.bias")):
+                continue
+            cfg = core.config
+            tp = ps.get_tensor_model_parallel_world_size()
+            heads = cfg.num_attention_heads // tp
+            hn = cfg.kv_channels or cfg.hidden_size // cfg.num_attention_heads
+            rest = tuple(p.shape[1:])
+            with torch.no_grad():
+                if version == 0:
+                    t = p.data.view(3, heads, hn, *rest).transpose(0, 1).contiguous()
+                else:
+                    t = p.data.view(heads, hn, 3, *rest).transpose(1, 2).contiguous()
+                p.data.copy_(t.view(p.shape))
+
+
 def load_args_from_checkpoint(args, load_arg="load"):
     load_dir = getattr(args, load_arg)
     tracker = get_checkpoint_tracker_filename(load_dir)
@@ -318,7 +458,7 @@ def load_args_from_checkpoint(args, load_arg="load"):
     iteration, release = read_metadata(tracker)
     base = get_checkpoint_name(load_dir, iteration, release, return_base_dir=True)
     if os.path.exists(os.path.join(base, "common.pt")):
-        sd = sharded.load_common_state_dict(base)
+        sd = sharded.load_common_state_dict(base)     # same file name / format in both sharded layouts
     else:
         name = get_checkpoint_name(load_dir, iteration, release, tensor_rank=0, pipeline_rank=0,
                                    pipeline_parallel=os.path.isdir(os.path.join(base, "mp_rank_00_000")),

@@ -47,6 +47,40 @@ class MLP(MegatronModule):
             input_is_parallel=True, skip_bias_add=True, is_expert=is_expert, tp_comm_buffer_name="fc2")
         self.layer_number = None
 
+    def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
+        """Gated MLPs keep ``[gate_r; up_r]`` in each TP rank's fc1 shard, so the rank-major concatenation is NOT the
+        global tensor: gate and up are exposed as two shards of the same key, gate rows first (global layout
+        ``[gate_0..gate_{tp-1}; up_0..up_{tp-1}]``), as the reference's ``apply_swiglu_sharded_factory`` (mlp.py:300-371)."""
+        from dataclasses import replace
+
+        from .module import sharded_state_dict_of
+
+        sd = {}
+        for name, child in self.named_children():
+            sub = sharded_state_dict_of(child, f"{prefix}{name}.", sharded_offsets, metadata)
+            if name == "linear_fc1" and self.config.gated_linear_unit:
+                split = {}
+                for k, st in sub.items():
+                    if not (hasattr(st, "local_shape") and st.data is not None and st.data.dim() >= 1
+                            and k.endswith(("weight", "bias"))):
+                        split[k] = st
+                        continue
+                    pre = st.prepend_axis_num
+                    half = st.local_shape[0] // 2
+                    frag = list(st.axis_fragmentations or (1,) * len(st.global_shape))
+                    tp_frag, tp_idx = frag[pre], st.global_offset[pre] // st.local_shape[0] if st.local_shape[0] else 0
+                    g_rows = half * tp_frag                      # rows of the global gate block
+                    frag[pre] = 2 * tp_frag
+                    for j, (nm, base) in enumerate((("gate", 0), ("up", g_rows))):
+                        goff = list(st.global_offset)
+                        goff[pre] = base + tp_idx * half
+                        split[f"{k}#{nm}"] = replace(st, data=st.data.narrow(0, j * half, half),
+                                                     local_shape=(half,) + tuple(st.local_shape[1:]),
+                                                     global_offset=tuple(goff), axis_fragmentations=tuple(frag))
+                sub = split
+            sd.update(sub)
+        return sd
+
     def _activation(self, x, bias):
         cfg = self.config
         if cfg.gated_linear_unit:

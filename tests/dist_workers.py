@@ -60,8 +60,42 @@ def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=F
             l = train_step(st, mine)
         losses.append(l)
     w = next(st.model[0].parameters()).detach().double().sum().item()
-    return {"losses": losses, "dp": dp, "w": w, "last": st.post_process,
+    inner = st.model[0]
+    while hasattr(inner, "module"):
+        inner = inner.module
+    emb = None
+    if (st.pre_process or st.post_process) and getattr(inner, "share_embeddings_and_output_weights", False):
+        emb = inner.shared_embedding_or_output_weight().detach().double().pow(2).sum().item()
+    return {"losses": losses, "dp": dp, "w": w, "last": st.post_process, "emb": emb,
             "is_backward": ps.is_backward_stage()}
+
+
+def ep_clip_consistency(steps=3):
+    """EP=2 without the distributed optimizer: the clip coefficient must be identical on both ranks (expert grads are
+    reduced over tp x ep x pp), otherwise the dense weights of the two data-parallel replicas drift apart."""
+    from megatronapp_b200.bench_model import train_step
+    from megatronapp_b200.parallel import state as ps
+
+    rank, world = _setup()
+    st, batches = _model_losses(steps, 4, num_experts=4, ep=2)
+    st.optimizer.config.clip_grad = 0.05            # always active
+    norms = []
+    orig = st.optimizer.get_grad_norm
+
+    def spy():
+        n = orig()
+        norms.append(n)
+        return n
+
+    st.optimizer.get_grad_norm = spy
+    dpr = ps.get_data_parallel_rank()
+    for _ in range(steps):
+        train_step(st, batches[dpr::2])
+    dense = 0.0
+    for n, p in st.model[0].named_parameters():
+        if getattr(p, "allreduce", True):
+            dense += p.detach().double().pow(2).sum().item()
+    return {"norms": norms, "dense": dense}
 
 
 def collectives_roundtrip():
@@ -452,7 +486,7 @@ def generation_parity(tp=1, pp=1):
             "logprobs": [r.generated_log_probs for r in res], "dynamic": [r.generated_tokens.tolist() for r in dres]}
 
 
-def reshard_logits(tp=1, pp=1, path=None, mode="save", tied=True):
+def reshard_logits(tp=1, pp=1, path=None, mode="save", tied=True, fmt="b200_sharded", swiglu=False):
     """Save a sharded checkpoint under one (tp, pp) layout / load it under another; returns the eval logits of a fixed
     batch (from the last pipeline stage, gathered over TP) so that layouts can be compared."""
     from megatronapp_b200.ckpt import sharded
@@ -461,11 +495,18 @@ def reshard_logits(tp=1, pp=1, path=None, mode="save", tied=True):
 
     rank, world = _setup()
     torch.manual_seed(1234 if mode == "save" else 99)          # the loader starts from DIFFERENT weights
-    st, _ = _model_losses(tp=tp, pp=pp, num_layers=4)
+    st, _ = _model_losses(tp=tp, pp=pp, num_layers=4, swiglu=swiglu, bias=not swiglu)
     m = st.model[0]
     inner = m
     while hasattr(inner, "module"):
         inner = inner.module
+
+    def ssd():
+        from megatronapp_b200.ckpt import torch_dist
+
+        sd = inner.sharded_state_dict()
+        return torch_dist.stack_homogeneous_layers(sd, 4) if fmt == "torch_dist" else sd
+
     if mode == "save":
         with torch.no_grad():
             for p_ in m.parameters():                             # break every symmetry the init may have
@@ -473,7 +514,16 @@ def reshard_logits(tp=1, pp=1, path=None, mode="save", tied=True):
         if pp > 1 and tied and ps.is_rank_in_embedding_group():   # keep the tied copies identical after the noise
             w = inner.shared_embedding_or_output_weight()
             dist.broadcast(w.data, ps.get_pipeline_model_parallel_first_rank(), group=ps.get_embedding_group())
-        sharded.save(inner.sharded_state_dict(), path, {"iteration": 1})
+        if fmt == "torch_dist":
+            from megatronapp_b200.ckpt import torch_dist
+
+            torch_dist.save(ssd(), path, {"iteration": 1}).finalize()
+        else:
+            sharded.save(inner.sharded_state_dict(), path, {"iteration": 1})
+    elif fmt == "torch_dist":
+        from megatronapp_b200.ckpt import torch_dist
+
+        torch_dist.load(ssd(), path)
     else:
         sharded.load(inner.sharded_state_dict(), path)
     dist.barrier()

@@ -63,6 +63,17 @@ def test_pipeline_1f1b(ref):
     assert all(math.isfinite(x) for x in a) and a[-1] < a[0]
 
 
+def test_pp2_dp2_distributed_optimizer_keeps_tied_embeddings_in_sync():
+    """PP2 x DP2 + ZeRO-1 with tied embeddings: the embedding weight sits ALONE in its bucket on the first and the last stage
+    (identical shard ranges), so the first<->last embedding all-reduce on reduce-scattered shards is exact: same losses as
+    PP2 x DP2 with the replicated optimizer, and the two copies of the embedding stay bit-identical."""
+    base = run_distributed("train_parity", 4, pp=2)
+    zero = run_distributed("train_parity", 4, pp=2, dist_opt=True)
+    _close(_last_stage_losses(zero), _last_stage_losses(base), 1e-5)
+    embs = [r["emb"] for r in zero if r.get("emb") is not None]
+    assert len(embs) == 4 and max(embs) - min(embs) < 1e-9, embs
+
+
 def test_pipeline_interleaved_and_dpp_agree():
     base = _last_stage_losses(run_distributed("train_parity", 2, pp=2, vpp=2))
     for pol in ("static", "bfc", "dfc", "auto"):
@@ -159,6 +170,26 @@ def test_sharded_checkpoint_reshards_across_tp_and_pp(tmp_path):
     ref2 = np.asarray([r["logits"] for r in saved if r["logits"] is not None][0])
     one = run_distributed("reshard_logits", 1, path=path2, mode="load")[0]
     assert np.allclose(np.asarray(one["logits"]), ref2, atol=1e-5)
+
+
+@pytest.mark.parametrize("swiglu", [False, True])
+def test_torch_dist_checkpoint_reshards_across_tp_and_pp(tmp_path, swiglu):
+    """Reference-layout (DCP) checkpoints: stacked layer keys, gate/up-split gated fc1 -- written at tp=2, read at tp=1 and
+    pp=2 and the other way round; every layout reproduces the saver's logits (the swiglu case is the one a rank-major
+    concatenation of [gate_r; up_r] shards gets wrong)."""
+    import numpy as np
+
+    path = str(tmp_path / "ck")
+    saved = run_distributed("reshard_logits", 2, tp=2, path=path, mode="save", fmt="torch_dist", swiglu=swiglu)
+    ref = np.asarray(saved[0]["logits"])
+    for world, kw in ((1, {}), (2, {"pp": 2})):
+        res = run_distributed("reshard_logits", world, path=path, mode="load", fmt="torch_dist", swiglu=swiglu, **kw)
+        got = [np.asarray(r["logits"]) for r in res if r["logits"] is not None]
+        assert got and all(np.allclose(g, ref, atol=1e-5) for g in got), kw
+    path1 = str(tmp_path / "ck1")
+    one = run_distributed("reshard_logits", 1, path=path1, mode="save", fmt="torch_dist", swiglu=swiglu)[0]
+    two = run_distributed("reshard_logits", 2, tp=2, path=path1, mode="load", fmt="torch_dist", swiglu=swiglu)
+    assert np.allclose(np.asarray(two[0]["logits"]), np.asarray(one["logits"]), atol=1e-5)
 
 
 def test_moe_checkpoint_reshards_over_expert_parallel_and_grouped(tmp_path):

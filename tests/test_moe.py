@@ -40,3 +40,9 @@ def test_fused_dispatcher_matches_alltoall(grouped):
     _close(a["out"], b["out"])
     _close(a["gx"], b["gx"])
     _close(a["grouter"], b["grouter"])
+
+
+def test_expert_parallel_grad_norm_and_clipping_agree_across_ranks():
+    res = run_distributed("ep_clip_consistency", 2)
+    assert res[0]["norms"] and res[0]["norms"] == pytest.approx(res[1]["norms"], rel=1e-6), res
+    assert res[0]["dense"] == pytest.approx(res[1]["dense"], rel=1e-9), res      # dense replicas stay identical
