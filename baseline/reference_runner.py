@@ -26,13 +26,18 @@ def main(args, MODELS, layout_for, pad_vocab):
     tp, pp = layout_for(args.gpus)
     if args.tp:
         tp, pp = args.tp, args.gpus // args.tp
+    if getattr(args, "layout", None):
+        import re
+
+        lay = dict(re.findall(r"(tp|pp)(\d+)", args.layout))
+        tp, pp = int(lay.get("tp", 1)), int(lay.get("pp", 1))
     L, H, A, F, S, V = MODELS[args.model]
     if args.layers:
         L = args.layers
     dp = args.gpus // (tp * pp)
     if not args.micro_batch:
         args.micro_batch = tp          # same rule as the framework's own arm (bench.py)
-    gbs = args.microbatches_per_gpu * args.gpus      # weak scaling: 8 sequences per GPU
+    gbs = getattr(args, "global_batch", None) or args.microbatches_per_gpu * args.gpus      # weak scaling: 8 sequences per GPU
     n_mb = gbs // (args.micro_batch * dp)
     vocab = pad_vocab(V, tp)
     argv = ["reference", "--transformer-impl", "local", "--use-mcore-models",
@@ -47,6 +52,13 @@ def main(args, MODELS, layout_for, pad_vocab):
             "--mock-data", "--no-create-attention-mask-in-dataloader", "--no-gradient-accumulation-fusion",
             "--no-masked-softmax-fusion", "--no-persist-layer-norm", "--distributed-backend", "nccl", "--log-interval", "1000000",
             "--eval-iters", "0", "--no-save-optim", "--no-save-rng", "--ckpt-format", "torch"]
+    if args.model == "llama3_8b":
+        argv += ["--swiglu", "--position-embedding-type", "rope", "--normalization", "RMSNorm", "--group-query-attention",
+                 "--num-query-groups", "8", "--disable-bias-linear", "--no-position-embedding"]
+    if getattr(args, "seq_len", None):
+        i = argv.index("--seq-length")
+        argv[i + 1] = str(args.seq_len)
+        argv[argv.index("--max-position-embeddings") + 1] = str(args.seq_len)
     import importlib.util
 
     # the stock local spec falls back to torch LayerNorm without Apex/TE, and that norm refuses

@@ -30,12 +30,31 @@ MODELS = {
     "gpt3_6.7b": (32, 4096, 32, 16384, 2048, 50257),
     "gpt3_1.3b": (24, 2048, 16, 8192, 2048, 50257),
     "gpt2_125m": (12, 768, 12, 3072, 1024, 50257),
+    "mixtral_8x7b": (32, 4096, 32, 14336, 4096, 32000),
+    "llama3_8b": (32, 4096, 32, 14336, 8192, 128256),
     "tiny": (2, 512, 8, 2048, 256, 4000),
+    "tiny_moe": (2, 512, 8, 1024, 256, 4000),
+}
+# architecture switches beyond the GPT-3 defaults (gelu MLP, LayerNorm, learned positions, biases)
+ARCH = {
+    "mixtral_8x7b": dict(swiglu=True, rope=True, rmsnorm=True, kv_groups=8, bias=False, num_experts=8, moe_topk=2),
+    "llama3_8b": dict(swiglu=True, rope=True, rmsnorm=True, kv_groups=8, bias=False),
+    "tiny_moe": dict(swiglu=True, rope=True, rmsnorm=True, kv_groups=2, bias=False, num_experts=4, moe_topk=2),
 }
 
 
 def layout_for(n_gpus: int):
     return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}.get(n_gpus, (min(n_gpus, 4), max(1, n_gpus // 4)))
+
+
+def parse_layout(spec: str):
+    """'tp2ep4', 'tp1pp4dp2', 'tp8' ... -> dict(tp, pp, ep, dp?)"""
+    import re
+
+    out = {"tp": 1, "pp": 1, "ep": 1}
+    for k, v in re.findall(r"(tp|pp|ep|dp|etp|vpp)(\d+)", spec):
+        out[k] = int(v)
+    return out
 
 
 def pad_vocab(v: int, tp: int) -> int:
@@ -113,20 +132,60 @@ def run_own(args):
     tp, pp = layout_for(args.gpus)
     if args.tp:
         tp, pp = args.tp, args.gpus // args.tp
+    ep, etp, vpp = 1, None, args.vpp
+    if args.layout:
+        lay = parse_layout(args.layout)
+        tp, pp, ep = lay["tp"], lay["pp"], lay["ep"]
+        etp, vpp = lay.get("etp"), lay.get("vpp", vpp)
     L, H, A, F, S, V = MODELS[args.model]
+    arch = dict(ARCH.get(args.model, {}))
     if args.layers:
         L = args.layers
+    if args.seq_len:
+        S = args.seq_len
     vocab = pad_vocab(V, tp)
     # micro-batch = TP degree keeps the per-GPU GEMM shapes of the 1-GPU run (a TP4 rank with
     # mbs 1 would run 35 us GEMMs and be launch-bound); the reference arm uses the same rule
     mbs = args.micro_batch or tp
-    dp = args.gpus // (tp * pp)
-    global_batch = args.microbatches_per_gpu * args.gpus   # weak scaling: 8 sequences per GPU
+    fb = 2 if args.fbd else 1                               # MegaFBD: every data-parallel slot is a (forward, backward) pair
+    dp = args.gpus // (tp * pp * fb)
+    global_batch = args.global_batch or args.microbatches_per_gpu * args.gpus   # weak scaling: 8 sequences per GPU
     n_mb = global_batch // (mbs * dp)                       # microbatches per data-parallel replica
     ops.ext()
+    moe = arch.get("num_experts") is not None
+    if moe:
+        arch.update(ep=ep, etp=etp, moe_grouped=not args.moe_baseline, moe_ffn=F,
+                    moe_dispatcher="alltoall" if args.moe_baseline else "flex", moe_aux_loss_coeff=1e-2)
     state = build_gpt_for_bench(L, H, A, S, vocab, mbs, ffn=F, tp=tp, pp=pp, sequence_parallel=tp > 1,
                                 device=f"cuda:{local_rank}", lr=1e-4, fused_tp_comm=not args.no_fused_tp_comm,
-                                use_distributed_optimizer=dp > 1, dropout=0.0)
+                                use_distributed_optimizer=dp > 1, dropout=0.0, vpp=vpp, fbd=args.fbd,
+                                fp8="hybrid" if args.fp8 else None, fp8_recipe=args.fp8_recipe, **arch)
+    if args.fbd:
+        from megatronapp_b200.fbd.schedule import install_fbd_schedule
+
+        install_fbd_schedule()
+    if args.dpp:
+        from megatronapp_b200.dpp.scheduler import install_dpp_schedule
+
+        install_dpp_schedule(policy=args.dpp)
+    slow = None
+    if args.slow_rank_inject:
+        r_, cyc = args.slow_rank_inject.split(":")
+        slow = (int(r_), int(cyc))
+    _train_step = train_step
+
+    def train_step(st, batches, sync_loss=True):            # noqa: F811 - add-on aware wrapper around the public API
+        if slow is not None and rank == slow[0]:
+            ops.ext().spin(slow[1])                         # MegaScan software slow-rank injector (comm.cu spin_kernel)
+        if args.fbd:
+            from megatronapp_b200.fbd.schedule import sync_forward_weights
+            from megatronapp_b200.parallel import state as ps_
+
+            out = _train_step(st, batches, sync_loss=sync_loss, do_optimizer=ps_.is_backward_stage())
+            sync_forward_weights(st.model)
+            return out
+        return _train_step(st, batches, sync_loss=sync_loss)
+
     dev_batches = [synthetic_batch(state, f"cuda:{local_rank}", seed=i) for i in range(n_mb)]
     pin_batches = [synthetic_batch(state, f"cuda:{local_rank}", seed=i, pinned=True) for i in range(n_mb)]
 
@@ -174,6 +233,7 @@ def run_own(args):
     orig_log = tr.log
 
     def _log_and_digest():
+        tr._drain()
         scope_stats.update(_digest_scopes(tr._records))
         orig_log()
 
@@ -185,6 +245,8 @@ def run_own(args):
         tr.iteration_begin(i)
         train_step(state, dev_batches, sync_loss=False)
         tr.iteration_end()
+    tr._ship_at = None
+    tr.log()          # drain + gather to rank 0 + hand to the writer thread: all of it inside the timed region
     g1.record()
     barrier()
     ms_traced = g0.elapsed_time(g1)
@@ -208,7 +270,9 @@ def run_own(args):
     h2d, d2h = int(t[4]), int(t[5])            # per-rank maxima: the stages that own the data / the loss
     tokens = global_batch * S * args.steps
     if rank == 0:
-        par = f"tp{tp}" + (f"pp{pp}" if pp > 1 else "") + (f"dp{dp}" if dp > 1 else "") + ("+sp" if tp > 1 else "")
+        par = (f"tp{tp}" + (f"pp{pp}" if pp > 1 else "") + (f"vpp{vpp}" if vpp else "") + (f"ep{ep}" if ep > 1 else "")
+               + (f"dp{dp}" if dp > 1 else "") + ("+sp" if tp > 1 else "") + ("+fbd" if args.fbd else "")
+               + (f"+dpp:{args.dpp}" if args.dpp else ""))
         out = {
             "metric": "GPT training tokens/sec (whole job, device-timed, max over ranks)",
             "value": tokens / (ms / 1e3), "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -233,7 +297,7 @@ def run_own(args):
             "exposed_comm_ms_per_step": exposed_ms,
             "gpu_launches": launches,
             "library_fallbacks": dict(ops.fallback_counts),
-            "tflops_per_gpu": 6.0 * _param_count(L, H, F, vocab) * tokens / (ms / 1e3) / 1e12 / args.gpus,
+            "tflops_per_gpu": 6.0 * _param_count(L, H, F, vocab, arch, A) * tokens / (ms / 1e3) / 1e12 / args.gpus,
         }
         out["rank0_scope_ms_per_step"] = scope_ms
         print(json.dumps(out), flush=True)
@@ -292,8 +356,14 @@ def _finite_from_any_rank(x, world):
     return x
 
 
-def _param_count(L, H, F, V):
-    return L * (4 * H * H + 2 * H * F) + V * H
+def _param_count(L, H, F, V, arch=None, heads=None):
+    """ACTIVE matmul parameters per token (MoE: top-k experts), for the model-FLOPs estimate 6 * N * tokens."""
+    arch = arch or {}
+    kv = arch.get("kv_groups") or heads
+    hd = H // heads if heads else H
+    attn = H * H + 2 * H * (kv * hd if heads else H) + H * H
+    mlp = (3 if arch.get("swiglu") else 2) * H * F * (arch.get("moe_topk", 1) if arch.get("num_experts") else 1)
+    return L * (attn + mlp) + V * H
 
 
 def main():
@@ -307,6 +377,17 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=None, help="default: TP degree")
     ap.add_argument("--microbatches-per-gpu", type=int, default=8)
     ap.add_argument("--tp", type=int, default=None)
+    ap.add_argument("--layout", default=None, help="e.g. tp2ep4, tp1pp4dp2vpp2, tp8 (overrides the per-N default)")
+    ap.add_argument("--vpp", type=int, default=None, help="virtual pipeline stages per rank (interleaved 1F1B)")
+    ap.add_argument("--global-batch", type=int, default=None, help="sequences per step (default 8 per GPU)")
+    ap.add_argument("--seq-len", type=int, default=None)
+    ap.add_argument("--fbd", action="store_true", help="MegaFBD: forward and backward of a stage on separate GPUs")
+    ap.add_argument("--dpp", default=None, choices=["static", "bfc", "dfc", "auto"], help="MegaDPP dynamic pipeline schedule")
+    ap.add_argument("--fp8", action="store_true", help="fp8 (hybrid e4m3/e5m2) linears")
+    ap.add_argument("--fp8-recipe", default="delayed", choices=["delayed", "tensorwise", "mxfp8"])
+    ap.add_argument("--slow-rank-inject", default=None, help="RANK:CYCLES software slow-rank injector (MegaScan demo)")
+    ap.add_argument("--moe-baseline", action="store_true",
+                    help="MoE in-tree baseline: NCCL all-to-all dispatcher + one module per expert (reference algorithm)")
     ap.add_argument("--no-fused-tp-comm", action="store_true", help="NCCL collectives instead of fused AG/RS GEMMs")
     ap.add_argument("--trace-scopes", action="store_true", help="(kept for compatibility; scopes are always reported)")
     ap.add_argument("--no-fused-rs", action="store_true", help="GEMM + NCCL reduce-scatter instead of the fused GEMM->RS kernel")

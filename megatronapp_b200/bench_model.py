@@ -41,12 +41,18 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
                         sequence_parallel=False, device="cuda", dtype=torch.bfloat16, swiglu=False,
                         rope=False, rmsnorm=False, kv_groups=None, bias=True, lr=1e-4, fused_tp_comm=True,
                         use_distributed_optimizer=False, dropout=0.0, vpp=None, overlap_grad_reduce=False,
-                        seed=1234, num_experts=None, ep=1, moe_topk=2, fused_grad_rs=False) -> BenchState:
+                        seed=1234, num_experts=None, ep=1, moe_topk=2, fused_grad_rs=False, fp8=None, fp8_recipe="delayed",
+                        moe_grouped=False, moe_dispatcher=None, moe_ffn=None, fbd=False, etp=None,
+                        moe_aux_loss_coeff=0.0) -> BenchState:
     if torch.cuda.is_available() and str(device).startswith("cuda"):
         torch.cuda.set_device(torch.device(device) if ":" in str(device) else torch.cuda.current_device())
     if not ps.model_parallel_is_initialized():
-        ps.initialize_model_parallel(tp, pp, virtual_pipeline_model_parallel_size=vpp,
-                                     expert_model_parallel_size=ep)
+        kw_ps = dict(virtual_pipeline_model_parallel_size=vpp, expert_model_parallel_size=ep)
+        if etp is not None:
+            kw_ps["expert_tensor_parallel_size"] = etp
+        if fbd:
+            kw_ps["forward_backward_disaggregating"] = True
+        ps.initialize_model_parallel(tp, pp, **kw_ps)
         if dist.is_initialized():
             p2p.build_channels()
     model_parallel_cuda_manual_seed(seed)
@@ -57,13 +63,16 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
               hidden_dropout=dropout, attention_dropout=dropout, add_bias_linear=bias,
               normalization="RMSNorm" if rmsnorm else "LayerNorm", gradient_accumulation_fusion=True,
               pipeline_dtype=dtype, deallocate_pipeline_outputs=True, expert_model_parallel_size=ep,
-              num_moe_experts=num_experts, moe_router_topk=moe_topk,
-              moe_token_dispatcher_type="alltoall" if num_experts else "allgather",
+              num_moe_experts=num_experts, moe_router_topk=moe_topk, moe_grouped_gemm=bool(moe_grouped),
+              moe_token_dispatcher_type=(moe_dispatcher or "alltoall") if num_experts else "allgather",
+              moe_ffn_hidden_size=moe_ffn, moe_aux_loss_coeff=moe_aux_loss_coeff, fp8=fp8, fp8_recipe=fp8_recipe,
               use_cpu_initialization=not str(device).startswith("cuda"))
     if swiglu:
         kw.update(activation_func=F.silu, gated_linear_unit=True)
     config = TransformerConfig(**kw)
-    spec = get_gpt_layer_local_spec(num_experts, False)
+    if etp is not None:
+        kw["expert_tensor_parallel_size"] = etp
+    spec = get_gpt_layer_local_spec(num_experts, bool(moe_grouped))
     chunks = []
     n_chunks = vpp or 1
     for c in range(n_chunks):

@@ -2,9 +2,11 @@
 
 ``scope(name, **attrs)`` records a begin/end pair per call site.  On CUDA the pair is two
 ``torch.cuda.Event(enable_timing=True)`` records on the current stream (no host sync on the hot
-path); on CPU (gloo plumbing runs) it is ``time.perf_counter_ns``.  ``iteration_end`` does the
-only synchronisation of a traced iteration and converts events to nanosecond offsets from the
-iteration-begin event.  Records are tagged with dp/pp/tp rank, device and global rank, gathered
+path); on CPU (gloo plumbing runs) it is ``time.perf_counter_ns``.  ``iteration_end`` does NOT
+synchronise the device: it records the end event and hands the iteration's scope tree to a resolver
+thread, which waits on that event (a host-side wait, the GPU keeps running the next step), converts
+event pairs to nanosecond offsets from the iteration-begin event and recycles the events through a pool
+(no ``cudaEventCreate`` on the hot path after the first traced iteration).  Records are tagged with dp/pp/tp rank, device and global rank, gathered
 to rank 0 with ``gather_object`` and streamed to disk by a background thread as JSON-lines
 (finalised to one JSON array per rank-tuple file on shutdown).
 
@@ -86,6 +88,12 @@ class Tracer:
         self._q: Optional[queue.Queue] = None
         self._thread: Optional[threading.Thread] = None
         self._files: Dict[str, str] = {}
+        # sync-free resolution: finished iterations wait here for their end event
+        self._rq: Optional[queue.Queue] = None
+        self._rthread: Optional[threading.Thread] = None
+        self._free: List[Any] = []            # recycled CUDA events (list.append / list.pop are atomic)
+        self._ship_at: Optional[int] = None
+        self._device = None
 
     # -- configuration -----------------------------------------------------------
     def configure(self, enabled: bool, trace_dir: str = "trace", interval: int = 1,
@@ -113,7 +121,10 @@ class Tracer:
     # -- hot path ----------------------------------------------------------------
     def _tick(self):
         if self._use_cuda:
-            ev = torch.cuda.Event(enable_timing=True)
+            try:
+                ev = self._free.pop()
+            except IndexError:
+                ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             return ev
         return time.perf_counter_ns()
@@ -162,33 +173,65 @@ class Tracer:
         if self._ended:
             return
         self._ended = True
+        if self._ship_at is not None and self.iteration >= self._ship_at:
+            # the window that closed one iteration ago has certainly left the GPU by now: shipping it does not stall
+            self._ship_at = None
+            self.log()
         if not self.active:
             return
         end = self._tick()
-        if self._use_cuda:
-            torch.cuda.synchronize()
-        wall_end = time.time_ns()
-        info = self._ranks()
-        recs = [{"name": "iteration", "ph": "B", "rel_ts": 0, "iteration": self.iteration,
-                 "pad_before": self._pad_before, "unix_ns": self._iter_begin_wall, **info}]
-        for s in self._pending:
-            self._emit(s, recs, info)
-        recs.append({"name": "iteration", "ph": "E", "rel_ts": self._rel(end), "iteration": self.iteration,
-                     "duration_wall": wall_end - self._iter_begin_wall,
-                     "duration_cuda": self._rel(end), **info})
-        self._records.extend(recs)
+        job = {"iteration": self.iteration, "begin": self._iter_begin, "end": end, "pending": self._pending,
+               "pad_before": self._pad_before, "wall_begin": self._iter_begin_wall, "info": self._ranks()}
         self._pending = []
-        self._prev_end_wall = wall_end
+        self._prev_end_wall = time.time_ns()
         self.active = False
-        if (self.iteration % self.interval) == self.continuous - 1:
-            self.log()
-
-    def _rel(self, t) -> int:
         if self._use_cuda:
-            return int(self._iter_begin.elapsed_time(t) * 1e6)
-        return int(t - self._iter_begin)
+            if self._rthread is None:
+                self._device = torch.cuda.current_device()
+                self._rq = queue.Queue()
+                self._rthread = threading.Thread(target=self._resolver, name="megascan-resolver", daemon=True)
+                self._rthread.start()
+            self._rq.put(job)
+        else:
+            self._resolve(job)
+        if (self.iteration % self.interval) == self.continuous - 1:
+            self._ship_at = self.iteration + 1      # ship one iteration later (see iteration_end); shutdown() flushes
 
-    def _emit(self, s: _Scope, out: List[dict], info: Dict[str, int]) -> None:
+    def _resolver(self) -> None:
+        torch.cuda.set_device(self._device)
+        while True:
+            job = self._rq.get()
+            try:
+                if job is not None:
+                    job["end"].synchronize()          # host-side wait; the training stream is not stalled
+                    self._resolve(job)
+            finally:
+                self._rq.task_done()
+            if job is None:
+                return
+
+    def _drain(self) -> None:
+        """Wait until every finished iteration has been converted to records (called before shipping them)."""
+        if self._rq is not None:
+            self._rq.join()
+
+    def _resolve(self, job) -> None:
+        begin, end, info = job["begin"], job["end"], job["info"]
+        wall_end = time.time_ns()
+        rel = (lambda t: int(begin.elapsed_time(t) * 1e6)) if self._use_cuda else (lambda t: int(t - begin))
+        recs = [{"name": "iteration", "ph": "B", "rel_ts": 0, "iteration": job["iteration"],
+                 "pad_before": job["pad_before"], "unix_ns": job["wall_begin"], **info}]
+        used: List[Any] = [begin, end]
+        for s in job["pending"]:
+            self._emit(s, recs, info, rel, used)
+        dur = rel(end)
+        recs.append({"name": "iteration", "ph": "E", "rel_ts": dur, "iteration": job["iteration"],
+                     "duration_wall": wall_end - job["wall_begin"], "duration_cuda": dur, **info})
+        self._records.extend(recs)
+        if self._use_cuda:
+            self._free.extend(used)
+
+    def _emit(self, s: _Scope, out: List[dict], info: Dict[str, int], rel, used: List[Any]) -> None:
         if s.e is None:
             return
         attrs = {}
@@ -202,15 +245,19 @@ class Tracer:
                     v = None
             if v is not None:
                 attrs[k] = v
-        tb, te = self._rel(s.b), self._rel(s.e)
+        tb = rel(s.b)
         if s.slots.get("__instant__"):
+            used.append(s.b)
             out.append({"name": s.name, "ph": "i", "rel_ts": tb, **attrs, **info})
             return
+        te = rel(s.e)
+        used.append(s.b)
+        used.append(s.e)
         if "data" in attrs and te > tb:
             attrs["bandwidth"] = attrs["data"] * 8 / (te - tb)  # Gbit/s (bytes*8 / ns)
         out.append({"name": s.name, "ph": "B", "rel_ts": tb, **attrs, **info})
         for c in s.children:
-            self._emit(c, out, info)
+            self._emit(c, out, info, rel, used)
         out.append({"name": s.name, "ph": "E", "rel_ts": te, **info})
 
     # -- output --------------------------------------------------------------------
@@ -219,6 +266,7 @@ class Tracer:
 
     def log(self) -> None:
         """Ship this window's records to rank 0 and hand them to the writer thread."""
+        self._drain()
         recs, self._records = self._records, []
         if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             gathered = [None] * torch.distributed.get_world_size() if torch.distributed.get_rank() == 0 else None
@@ -254,8 +302,14 @@ class Tracer:
                 os.fsync(f.fileno())
 
     def shutdown(self) -> None:
+        self._drain()
+        self._ship_at = None
         if self._records:
             self.log()
+        if self._rthread is not None:
+            self._rq.put(None)
+            self._rthread.join()
+            self._rthread = self._rq = None
         if self._thread is not None:
             self._q.put(None)
             self._thread.join()
