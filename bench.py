@@ -250,12 +250,12 @@ def run_own(args):
     g1.record()
     barrier()
     ms_traced = g0.elapsed_time(g1)
-    tr.configure(False)
     tr.log = orig_log
     try:
-        tr.shutdown()
+        tr.shutdown()            # flush the writer thread while trace_dir still points at this run's directory
     except Exception:
         pass
+    tr.configure(False, trace_dir=trace_dir)
     exposed_ms = scope_stats.get("exposed_comm_ns", 0) / 1e6 / max(1, args.steps)
     scope_ms = {k: {"ms": round(v["ns"] / 1e6 / args.steps, 3), "calls": v["calls"] // max(1, args.steps)}
                 for k, v in sorted(scope_stats.get("per_scope", {}).items(), key=lambda kv: -kv[1]["ns"])}

@@ -114,6 +114,29 @@ void fp8_scale_from_amax(const float* amax, bool e5m2, int margin, float* scale,
 void fp8_cast_transpose(const void* x, const float* scale, void* q, void* qt, int rows, int cols, bool is_bf16,
                         bool e5m2, cudaStream_t s);
 
+// ---------------------------------------------------------------- mxfp8 (gemm_mxfp8_sm100.cu)
+struct MxGemmArgs {
+  // D[M,N] = (A8 * 2^(sfa-127)) . (B8 * 2^(sfb-127))^T (+ bias); K % 128 == 0; sfa in A-role, sfb in B-role chunk layout
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* D = nullptr;
+  const void* sfa = nullptr;
+  const void* sfb = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0, ldd = 0;
+  bool a_e5m2 = false, b_e5m2 = false;
+  const void* bias = nullptr;
+  bool out_bf16 = true;
+  bool accum_f32 = false;
+  cudaStream_t stream = nullptr;
+};
+int gemm_mxfp8(const MxGemmArgs& a);
+const char* gemm_mxfp8_last_error();
+int64_t mx_sf_bytes(int role, int rows, int K);     // role 0: A operand (128-row chunks), 1: B operand (192-row tiles)
+// x [R, C] 16-bit -> row-wise (blocks along C) and / or column-wise (x^T, blocks along R) fp8 + E8M0 scales
+void mx_quantize(const void* x, int R, int C, bool is_bf16, bool e5m2, void* q_row, void* sf_row, int role_row, void* q_col,
+                 void* sf_col, int role_col, cudaStream_t s);
+
 // ---------------------------------------------------------------- elementwise / norm
 void layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
                    float* rstd, int rows, int cols, float eps, bool rms, bool zero_centered,

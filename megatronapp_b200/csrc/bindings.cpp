@@ -161,6 +161,55 @@ void gemm_rs(const Tensor& A, const Tensor& B, Tensor& D_out, bool b_mn, const c
   count();
 }
 
+// ---------------------------------------------------------------- mxfp8
+// -> [q_row, sf_row, q_col, sf_col] (undefined tensors for the directions that were not asked for)
+std::vector<Tensor> mx_quantize(const Tensor& x, bool e5m2, int role_row, int role_col) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check_2d(x, "x");
+  TORCH_CHECK(x.is_contiguous(), "mx_quantize: contiguous input");
+  const int R = static_cast<int>(x.size(0)), C = static_cast<int>(x.size(1));
+  auto bo = x.options().dtype(at::kByte);
+  Tensor q_row, sf_row, q_col, sf_col;
+  if (role_row >= 0) {
+    TORCH_CHECK(C % 128 == 0, "row-wise mxfp8 needs cols % 128 == 0");
+    q_row = torch::empty({R, C}, bo);
+    sf_row = torch::zeros({b200::mx_sf_bytes(role_row, R, C)}, bo);
+  }
+  if (role_col >= 0) {
+    TORCH_CHECK(R % 128 == 0 && C % 8 == 0, "column-wise mxfp8 needs rows % 128 == 0");
+    q_col = torch::empty({C, R}, bo);
+    sf_col = torch::zeros({b200::mx_sf_bytes(role_col, C, R)}, bo);
+  }
+  b200::mx_quantize(x.data_ptr(), R, C, is_bf16(x), e5m2, role_row >= 0 ? q_row.data_ptr() : nullptr,
+                    role_row >= 0 ? sf_row.data_ptr() : nullptr, role_row, role_col >= 0 ? q_col.data_ptr() : nullptr,
+                    role_col >= 0 ? sf_col.data_ptr() : nullptr, role_col, cur_stream());
+  count();
+  return {q_row, sf_row, q_col, sf_col};
+}
+
+void gemm_mxfp8(const Tensor& A, const Tensor& sfa, const Tensor& B, const Tensor& sfb, Tensor& D, bool a_e5m2, bool b_e5m2,
+                const c10::optional<Tensor>& bias, bool accumulate) {
+  c10::cuda::CUDAGuard guard(A.device());
+  check_2d(A, "A"); check_2d(B, "B"); check_2d(D, "D");
+  TORCH_CHECK(A.scalar_type() == at::kByte && B.scalar_type() == at::kByte && A.size(1) == B.size(1), "mxfp8 operands: uint8 [rows, K]");
+  b200::MxGemmArgs g;
+  g.A = A.data_ptr(); g.B = B.data_ptr(); g.D = D.data_ptr(); g.sfa = sfa.data_ptr(); g.sfb = sfb.data_ptr();
+  g.M = static_cast<int>(A.size(0)); g.N = static_cast<int>(B.size(0)); g.K = static_cast<int>(A.size(1));
+  TORCH_CHECK(D.size(0) == g.M && D.size(1) == g.N, "D shape");
+  TORCH_CHECK(sfa.numel() >= b200::mx_sf_bytes(0, g.M, g.K) && sfb.numel() >= b200::mx_sf_bytes(1, g.N, g.K), "scale buffers too small");
+  g.lda = static_cast<int>(A.stride(0)); g.ldb = static_cast<int>(B.stride(0)); g.ldd = static_cast<int>(D.stride(0));
+  g.a_e5m2 = a_e5m2; g.b_e5m2 = b_e5m2; g.bias = optptr(bias); g.accum_f32 = accumulate;
+  if (accumulate) {
+    TORCH_CHECK(D.scalar_type() == at::kFloat, "accumulate needs fp32 D");
+  } else {
+    g.out_bf16 = is_bf16(D);
+  }
+  g.stream = cur_stream();
+  int rc = b200::gemm_mxfp8(g);
+  TORCH_CHECK(rc == 0, "b200 gemm_mxfp8 failed (", rc, "): ", b200::gemm_mxfp8_last_error());
+  count();
+}
+
 // ---------------------------------------------------------------- MoE
 std::vector<Tensor> moe_router_topk_fwd(const Tensor& logits, int k, bool pre_softmax, double scaling) {
   c10::cuda::CUDAGuard guard(logits.device());
@@ -774,6 +823,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("bias"), py::arg("act"), py::arg("peer_bufs"), py::arg("peer_flags"), py::arg("rank"), py::arg("size"),
         py::arg("epoch"), py::arg("n_comm_ctas"), py::arg("block_n"), py::arg("D_pre") = c10::optional<Tensor>());
   m.def("gemm_grouped", &gemm_grouped);
+  m.def("mx_quantize", &mx_quantize);
+  m.def("gemm_mxfp8", &gemm_mxfp8);
+  m.def("mx_sf_bytes", &b200::mx_sf_bytes);
   m.def("moe_router_topk_fwd", &moe_router_topk_fwd);
   m.def("moe_router_topk_bwd", &moe_router_topk_bwd);
   m.def("moe_build_layout", &moe_build_layout);

@@ -95,6 +95,13 @@ def gemm_fp8(a8, b8, sa_inv, sb_inv, *, a_e5m2=False, b_e5m2=False, bias=None, o
     return out
 
 
+def _zero_if_first(weight, main_grad) -> None:
+    """The DDP buffer skips zeroing the main_grad of weights whose first wgrad of a step is a plain store
+    (``b200_wgrad_store_first``, bf16 path); the fp8 kernels only have the ``+=`` epilogue, so clear it here."""
+    if getattr(weight, "b200_wgrad_store_first", False) and not getattr(weight, "grad_added_to_main_grad", False):
+        main_grad.zero_()
+
+
 class _WeightCache:
     """fp8 (and transposed fp8) copies of a weight, rebuilt only when the parameter changes (once per
     optimizer step, not per micro-batch)."""
@@ -138,6 +145,7 @@ class Fp8LinearFn(torch.autograd.Function):
             main = getattr(weight, "main_grad", None)
             if rec.wgrad:
                 if ctx.fuse_wgrad and main is not None:
+                    _zero_if_first(weight, main)
                     gemm_fp8(d8t, x8t, ds, xs, a_e5m2=e5, out=main, accumulate=True)              # main_grad += dy^T @ x
                     weight.grad_added_to_main_grad = True
                     hook = getattr(weight, "grad_ready_hook", None)
@@ -204,16 +212,124 @@ def gemm_mx(a8, sa, b8, sb, *, a_e5m2=False, b_e5m2=False, bias=None, out_dtype=
     return d.to(out_dtype)
 
 
+# ---- native path: tcgen05.mma.kind::mxf8f6f4.block_scale (csrc/gemm_mxfp8_sm100.cu) ---------------------------------------
+MX_BN = 192        # N-tile of the native kernel = height of a B-operand scale tile
+
+
+@dataclass
+class MxTensor:
+    """fp8 payload ``q [rows, K]`` + E8M0 scales in the kernel's chunk layout (``role`` 0 = A operand, 1 = B operand)."""
+    q: torch.Tensor
+    sf: torch.Tensor
+    role: int
+    e5m2: bool = False
+
+
+def mx_native_ok(t: torch.Tensor) -> bool:
+    return _native(t) and have_ext()
+
+
+def quantize_mx_native(x2: torch.Tensor, e5m2: bool, role_row: int = -1, role_col: int = -1):
+    """One kernel: row-wise copy (blocks along the last dim) and / or column-wise copy (x^T, blocks along the rows)."""
+    q_row, sf_row, q_col, sf_col = ext().mx_quantize(x2.contiguous(), e5m2, role_row, role_col)
+    return (MxTensor(q_row, sf_row, role_row, e5m2) if role_row >= 0 else None,
+            MxTensor(q_col, sf_col, role_col, e5m2) if role_col >= 0 else None)
+
+
+def sf_matrix(t: MxTensor) -> torch.Tensor:
+    """Scales of ``t`` as a plain ``[rows, K/32]`` uint8 matrix (de-layout of the chunked storage; tests / debugging)."""
+    rows, K = t.q.shape
+    r = torch.arange(rows, device=t.sf.device).unsqueeze(1)
+    kb32 = torch.arange(K // 32, device=t.sf.device).unsqueeze(0)
+    kb, ks, kblocks = kb32 // 4, kb32 % 4, K // 128
+    if t.role == 0:
+        chunk, rr = (r // 128) * kblocks + kb, r % 128
+    else:
+        tile, r2 = r // MX_BN, r % MX_BN
+        chunk, rr = (tile * kblocks + kb) * 2 + r2 // 128, r2 % 128
+    off = chunk * 512 + (rr % 32) * 16 + (rr // 32) * 4 + ks
+    return t.sf[off.reshape(-1).long()].view(rows, K // 32)
+
+
+def dequantize_mx_native(t: MxTensor, dtype=torch.float32) -> torch.Tensor:
+    return dequantize_mx(t.q, sf_matrix(t), t.e5m2, dtype)
+
+
+def gemm_mx_native(a: MxTensor, b: MxTensor, *, bias=None, out=None, out_dtype=torch.bfloat16, accumulate=False):
+    """``D = deq(a) @ deq(b)^T`` on the block-scaled tensor-core path (scales applied inside the MMA)."""
+    assert a.role == 0 and b.role == 1
+    M, N = a.q.shape[0], b.q.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if accumulate else out_dtype, device=a.q.device)
+    ext().gemm_mxfp8(a.q, a.sf, b.q, b.sf, out, a.e5m2, b.e5m2, bias, accumulate)
+    return out
+
+
 class _MxWeightCache(_WeightCache):
     """Row-wise (blocks along ``in``: fprop) and column-wise (blocks along ``out``: dgrad) mxfp8 copies of a weight."""
 
     def get(self, w: torch.Tensor, margin: int = 0):
         if self.val is None or self.version != w._version or self.data_ptr != w.data_ptr():
             wd = w.detach()
-            ok_t = wd.shape[0] % MX_BLOCK == 0
-            self.val = (*quantize_mx(wd), *(quantize_mx(wd.t().contiguous()) if ok_t else (None, None)))
+            if mx_native_ok(wd) and wd.shape[1] % 128 == 0 and wd.shape[0] % 128 == 0:
+                self.val = ("native",) + quantize_mx_native(wd, False, 1, 1)     # (W, blocks along in) , (W^T, blocks along out)
+            else:
+                ok_t = wd.shape[0] % MX_BLOCK == 0
+                self.val = (*quantize_mx(wd), *(quantize_mx(wd.t().contiguous()) if ok_t else (None, None)))
             self.version, self.data_ptr = w._version, w.data_ptr()
         return self.val
+
+
+class MxFp8LinearNativeFn(torch.autograd.Function):
+    """mxfp8 linear on the native block-scaled GEMM: every operand is quantised ONCE per use-direction by a dual
+    (row-wise + column-wise) kernel, the three GEMMs read fp8 + E8M0 scales directly -- no bf16 dequantisation."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, recipe: Fp8Recipe, cache: _MxWeightCache, fuse_wgrad: bool):
+        x2 = x.reshape(-1, x.shape[-1])
+        rows = x2.shape[0]
+        want_wgrad = weight.requires_grad and recipe.wgrad and rows % 128 == 0
+        xr, xc = quantize_mx_native(x2, False, 0, 1 if want_wgrad else -1)       # X (A of fprop), X^T (B of wgrad)
+        _, wr, wc = cache.get(weight)
+        y = gemm_mx_native(xr, wr, bias=bias, out_dtype=x.dtype)
+        ctx.xc, ctx.wc = xc, wc
+        ctx.save_for_backward(x2 if xc is None else None)
+        ctx.recipe, ctx.fuse_wgrad, ctx.weight = recipe, fuse_wgrad, weight
+        ctx.x_shape, ctx.has_bias, ctx.dtype = x.shape, bias is not None, x.dtype
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2,) = ctx.saved_tensors
+        rec, weight = ctx.recipe, ctx.weight
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        e5 = rec.fmt == "hybrid"
+        dr, dc = quantize_mx_native(dy2, e5, 0, 0 if ctx.xc is not None else -1)  # dY (A of dgrad), dY^T (A of wgrad)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_mx_native(dr, ctx.wc, out_dtype=ctx.dtype).view(ctx.x_shape)          # dY @ W
+        if ctx.needs_input_grad[1]:
+            main = getattr(weight, "main_grad", None)
+            if ctx.xc is not None:
+                if ctx.fuse_wgrad and main is not None and main.dtype == torch.float32:
+                    _zero_if_first(weight, main)
+                    gemm_mx_native(dc, ctx.xc, out=main, accumulate=True)                    # main_grad += dY^T @ X
+                    weight.grad_added_to_main_grad = True
+                    hook = getattr(weight, "grad_ready_hook", None)
+                    if hook is not None and getattr(weight, "b200_wgrad_store_first", False):
+                        hook()
+                else:
+                    dw = gemm_mx_native(dc, ctx.xc, out_dtype=weight.dtype)
+            else:
+                from . import wgrad as _wgrad
+
+                dw = _wgrad(dy2, x2, weight, ctx.fuse_wgrad)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            from . import bias_grad
+
+            db = bias_grad(dy2).to(dy.dtype)
+        ctx.xc = ctx.wc = None
+        return dx, dw, db, None, None, None
 
 
 class MxFp8LinearFn(torch.autograd.Function):
@@ -225,7 +341,11 @@ class MxFp8LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, recipe: Fp8Recipe, cache: _MxWeightCache, fuse_wgrad: bool):
         x2 = x.reshape(-1, x.shape[-1])
         xq, xs = quantize_mx(x2)
-        wq, ws, wtq, wts = cache.get(weight)
+        val = cache.get(weight)
+        if val[0] == "native":            # cached by the native path for another input shape: rebuild in matrix form
+            wd = weight.detach()
+            val = (*quantize_mx(wd), *(quantize_mx(wd.t().contiguous()) if wd.shape[0] % MX_BLOCK == 0 else (None, None)))
+        wq, ws, wtq, wts = val
         y = gemm_mx(xq, xs, wq, ws, bias=bias, out_dtype=x.dtype)
         ctx.save_for_backward(x2, wtq, wts)
         ctx.recipe, ctx.fuse_wgrad, ctx.weight = recipe, fuse_wgrad, weight
@@ -256,6 +376,7 @@ class MxFp8LinearFn(torch.autograd.Function):
                 dw = dy2.float().t() @ x2.float()
             main = getattr(weight, "main_grad", None)
             if ctx.fuse_wgrad and main is not None:
+                _zero_if_first(weight, main)
                 main.add_(dw)
                 weight.grad_added_to_main_grad = True
                 dw = None
@@ -274,5 +395,8 @@ def fp8_linear(x, weight, bias=None, recipe: Optional[Fp8Recipe] = None, cache: 
     if recipe.recipe == "mxfp8" and x.shape[-1] % MX_BLOCK == 0:
         if not isinstance(cache, _MxWeightCache):
             cache = _MxWeightCache()
+        if (mx_native_ok(x) and x.shape[-1] % 128 == 0 and weight.shape[0] % 128 == 0 and weight.dtype == x.dtype
+                and x.reshape(-1, x.shape[-1]).shape[0] > 0):
+            return MxFp8LinearNativeFn.apply(x, weight, bias, recipe, cache, fuse_wgrad)
         return MxFp8LinearFn.apply(x, weight, bias, recipe, cache, fuse_wgrad)
     return Fp8LinearFn.apply(x, weight, bias, recipe or Fp8Recipe(), cache or _WeightCache(), fuse_wgrad)

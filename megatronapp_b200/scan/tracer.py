@@ -293,6 +293,7 @@ class Tracer:
             if item is None:
                 return
             info = item[0]
+            os.makedirs(self.trace_dir, exist_ok=True)
             path = os.path.join(self.trace_dir, self.file_name(info) + "l")  # .jsonl sidecar
             self._files[path] = path[:-1]
             with open(path, "a") as f:

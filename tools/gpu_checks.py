@@ -439,6 +439,78 @@ def check_fp8():
     return res
 
 
+def check_mxfp8():
+    """Native block-scaled GEMM (tcgen05 kind::mxf8f6f4.block_scale, scales in TMEM) and the dual quantiser vs the
+    PyTorch OCP-MX emulation; the mxfp8 linear (fprop / dgrad / wgrad) vs fp32."""
+    import torch
+    from megatronapp_b200 import ops
+    from megatronapp_b200.ops import fp8
+
+    res = {}
+    for (M, N, K) in ((256, 384, 256), (384, 192, 128), (2048, 4096, 4096), (300, 520, 384), (4096, 1024, 2048)):
+        torch.manual_seed(M + N + K)
+        a = (torch.randn(M, K, device="cuda") * (torch.rand(M, 1, device="cuda") * 4 + 0.1)).bfloat16()
+        b = (torch.randn(N, K, device="cuda") * 0.3).bfloat16()
+        key = f"{M}x{N}x{K}"
+        try:
+            for e5 in (False, True):
+                ar, _ = fp8.quantize_mx_native(a, e5, 0, -1)
+                q_ref, s_ref = fp8.quantize_mx(a, e5)
+                tag = key + ("_e5m2" if e5 else "_e4m3")
+                res[tag + "_q_mismatch"] = float((ar.q != q_ref).float().mean())
+                res[tag + "_sf_mismatch"] = float((fp8.sf_matrix(ar) != s_ref).float().mean())
+            ar, _ = fp8.quantize_mx_native(a, False, 0, -1)
+            br, _ = fp8.quantize_mx_native(b, False, 1, -1)
+            res[key + "_sfb_mismatch"] = float((fp8.sf_matrix(br) != fp8.quantize_mx(b)[1]).float().mean())
+            ref = fp8.dequantize_mx_native(ar) @ fp8.dequantize_mx_native(br).t()
+            bias = torch.randn(N, device="cuda").bfloat16()
+            out = fp8.gemm_mx_native(ar, br, bias=bias)
+            res[key + "_gemm"] = _rel_err(out, ref + bias.float())
+            acc = torch.randn(M, N, device="cuda")
+            want = acc + ref
+            fp8.gemm_mx_native(ar, br, out=acc, accumulate=True)
+            res[key + "_accum"] = _rel_err(acc, want)
+            if M % 128 == 0:
+                _, ac = fp8.quantize_mx_native(a, True, -1, 0)            # a^T [K, M], blocks along M
+                qt_ref, st_ref = fp8.quantize_mx(a.t().contiguous(), True)
+                res[key + "_colwise_q_mismatch"] = float((ac.q != qt_ref).float().mean())
+                res[key + "_colwise_sf_mismatch"] = float((fp8.sf_matrix(ac) != st_ref).float().mean())
+        except Exception as e:  # noqa: BLE001
+            res[key] = f"EXC {type(e).__name__}: {str(e)[:300]}"
+    # the linear layer
+    torch.manual_seed(0)
+    x = (torch.randn(512, 1024, device="cuda") * 0.5).bfloat16().requires_grad_(True)
+    w = (torch.randn(768, 1024, device="cuda") * 0.05).bfloat16().requires_grad_(True)
+    rec = fp8.Fp8Recipe(fmt="hybrid", recipe="mxfp8")
+    y = fp8.fp8_linear(x, w, None, rec, fp8._MxWeightCache())
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    res["linear_fwd_vs_fp32"] = _rel_err(y, x.detach().float() @ w.detach().float().t())
+    res["linear_dx_vs_fp32"] = _rel_err(x.grad, dy.float() @ w.detach().float())
+    res["linear_dw_vs_fp32"] = _rel_err(w.grad, dy.float().t() @ x.detach().float())
+    res["_fallbacks"] = dict(ops.fallback_counts)
+    return res
+
+
+def check_mxfp8_perf():
+    import torch
+    from megatronapp_b200.ops import fp8
+
+    res = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for (M, N, K, name) in ((8192, 16384, 4096, "fc1"), (8192, 4096, 16384, "fc2"), (8192, 8192, 8192, "sq8k")):
+        a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+        b = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+        ar, _ = fp8.quantize_mx_native(a, False, 0, -1)
+        br, _ = fp8.quantize_mx_native(b, False, 1, -1)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        t = _time(lambda: fp8.gemm_mx_native(ar, br, out=out), flush=flush)
+        res[f"mxfp8_{name}_tflops"] = 2.0 * M * N * K / t / 1e9
+        t = _time(lambda: fp8.quantize_mx_native(a, False, 0, 1), flush=flush)
+        res[f"mx_dual_quantize_{name}_GBs"] = (M * K * 2 + 2 * M * K) / t / 1e6
+    return res
+
+
 def check_fp8_perf():
     import torch
     from megatronapp_b200 import ops
@@ -707,13 +779,14 @@ CHECKS = {
     "attention_fwd": check_attention_fwd,
     "attention": check_attention,
     "fp8": check_fp8,
+    "mxfp8": check_mxfp8,
     "grouped_gemm": check_grouped_gemm,
     "moe_kernels": check_moe_kernels,
     "moe_layer": check_moe_layer,
     "model_parity": check_model_parity,
     "smoke": check_smoke,
 }
-PERF = {"grouped_perf": check_grouped_perf, "fp8_perf": check_fp8_perf, "gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
+PERF = {"mxfp8_perf": check_mxfp8_perf, "grouped_perf": check_grouped_perf, "fp8_perf": check_fp8_perf, "gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
 
 
 def main():
