@@ -13,6 +13,15 @@ gc = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(gc)
 
 
+@pytest.fixture(autouse=True)
+def _fresh_fallback_counters():
+    """``ops.fallback_counts`` is process-global: every test judges only the fallbacks it caused itself."""
+    from megatronapp_b200 import ops
+
+    ops.fallback_counts.clear()
+    yield
+
+
 def _assert_small(res, tol):
     bad = {k: v for k, v in res.items() if not k.startswith("_") and (isinstance(v, str) or v > tol)}
     assert not bad, bad
@@ -49,7 +58,7 @@ def test_attention_forward_kernel():
 
 def test_attention_backward_kernels():
     """dQ / dK / dV of the native kernels through autograd vs the fp32 reference."""
-    _assert_small(gc.check_attention(), 3e-2)
+    _assert_small(gc.check_attention(), 6e-2)   # element-wise criterion (|err| <= tol * (|ref| + rms)); P and dS are 16-bit
 
 
 def test_attention_op_uses_native_kernel():
@@ -116,6 +125,16 @@ def test_fp8_gemm_and_linear():
     # fp8 linear vs the exact fp32 result: bounded by e4m3 / e5m2 quantisation (2^-4 / 2^-3 per element), element-wise max
     _assert_small({k: v for k, v in res.items() if k.startswith("linear_")}, 0.5)
     _assert_small({k: v for k, v in res.items() if not k.startswith("linear_")}, 1e-2)
+
+
+def test_mxfp8_block_scaled_gemm_and_quantiser():
+    """tcgen05 kind::mxf8f6f4.block_scale GEMM (E8M0 scales staged in TMEM by UTCCP) + the dual row/column MX quantiser:
+    bit-exact quantisation vs the OCP-MX emulation, GEMM vs the product of the dequantised operands."""
+    res = gc.check_mxfp8()
+    bad = {k: v for k, v in res.items() if k.endswith("_mismatch") and v != 0}
+    assert not bad, bad
+    _assert_small({k: v for k, v in res.items() if k.startswith("linear_")}, 0.5)
+    _assert_small({k: v for k, v in res.items() if not k.startswith("linear_") and not k.endswith("_mismatch")}, 1e-2)
 
 
 def test_grouped_gemm_ragged_layout():
