@@ -43,7 +43,8 @@ constexpr int BM = 128;         // rows per CTA (256 per pair)
 constexpr int BN = 256;         // tile N (128 rows of B per CTA)
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int kStages = 6;
+constexpr int kStagesDefault = 6;
+enum : int { kModePlain = 0, kModeAG = 1, kModeRS = 2, kModeGroupM = 3, kModeGroupK = 4 };
 constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int kGroupN2 = 8;
@@ -51,7 +52,6 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a sh
 constexpr int kBulkChunk2 = 32768;            // comm-CTA TMA bulk copy granule
 constexpr int kBulkStages2 = 6;
 
-enum : int { kModePlain = 0, kModeAG = 1, kModeRS = 2, kModeGroupM = 3, kModeGroupK = 4 };
 
 struct P2 {
   int M, N, K, ldd;
@@ -82,14 +82,21 @@ struct PeerMaps2 {
   CUtensorMap m[kMaxPeers];
 };
 
-struct Smem2 {
+// Shared-memory plan.  Default: six 32 KB operand stages + two 16 KB epilogue staging buffers.  The reduce-scatter mode
+// trades two operand stages for four more staging buffers: a TMA store to PEER memory keeps its source buffer busy for a
+// full NVLink round trip (measured: ~2.6 GB/s per SM with two buffers, the kernel ran at compute + transfer instead of
+// max(compute, transfer)), so the bytes in flight per SM -- not the issue rate -- bound the push bandwidth.
+template <int kMode>
+struct Smem2T {
+  static constexpr int kStages = (kMode == kModeRS) ? 4 : kStagesDefault;
+  static constexpr int kCBufs = (kMode == kModeRS) ? 6 : 2;
   static constexpr int kA = BM * BK * 2;          // 16 KB
   static constexpr int kB = (BN / 2) * BK * 2;    // 16 KB (this CTA's half of the B tile)
   static constexpr int kC = BM * 64 * 2;          // 16 KB
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kAOff + kStages * kA;
   static constexpr int kCOff = kBOff + kStages * kB;
-  static constexpr int kBarOff = kCOff + 2 * kC;
+  static constexpr int kBarOff = kCOff + kCBufs * kC;
   static constexpr int kTotal = kBarOff + 256 + 1024;
 };
 
@@ -205,7 +212,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_local,
              const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_d,
              const __grid_constant__ CUtensorMap tmap_d_pre, const __grid_constant__ PeerMaps2 peer_maps, const P2 p) {
-  using L = Smem2;
+  using L = Smem2T<kMode>;
+  constexpr int kStages = L::kStages;
+  constexpr int kCBufs = L::kCBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem + L::kAOff;
@@ -565,7 +574,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const int n_out = (kMode != kModeRS && p.D_pre != nullptr) ? 2 : 1;
           for (int o = 0; o < n_out; ++o) {
             const bool pre = (n_out == 2 && o == 0);
-            if (epi_tid == 0) tma_store_wait_read<1>();
+            if (epi_tid == 0) tma_store_wait_read<kCBufs - 1>();
             named_bar_sync(1, kEpiThreads);
             uint8_t* sc = smem_c + cbuf * L::kC + row_in_tile * 128;
 #pragma unroll
@@ -595,14 +604,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               }
               tma_store_commit();
             }
-            cbuf ^= 1;
+            if (++cbuf == kCBufs) cbuf = 0;
           }
         } else {
           const int drow0 = (kMode == kModeGroupK) ? t.group * p.group_stride + m0 : m0;
 #pragma unroll
           for (int hseg = 0; hseg < 2; ++hseg) {
             const uint32_t* v = hseg == 0 ? v0 : v1;
-            if (epi_tid == 0) tma_store_wait_read<1>();
+            if (epi_tid == 0) tma_store_wait_read<kCBufs - 1>();
             named_bar_sync(1, kEpiThreads);
             uint8_t* sc = smem_c + cbuf * L::kC + row_in_tile * 128;
 #pragma unroll
@@ -616,7 +625,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               else tma_store_2d(&tmap_d, smem_c + cbuf * L::kC, gcol0 + hseg * 32, drow0);
               tma_store_commit();
             }
-            cbuf ^= 1;
+            if (++cbuf == kCBufs) cbuf = 0;
           }
         }
       }
@@ -702,12 +711,12 @@ int launch2(const GemmArgs& a, const P2& p, const CUtensorMap& ta, const CUtenso
   auto kern = gemm2_kernel<AM, BMj, EPI, MODE>;
   static bool set = false;
   if (!set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kTotal) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<MODE>::kTotal) != cudaSuccess) {
       g_err2 = "cudaFuncSetAttribute failed"; return -10;
     }
     set = true;
   }
-  kern<<<grid, kThreads, Smem2::kTotal, a.stream>>>(ta, tal, tb, td, tdp, pm, p);
+  kern<<<grid, kThreads, Smem2T<MODE>::kTotal, a.stream>>>(ta, tal, tb, td, tdp, pm, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err2 = std::string("launch: ") + cudaGetErrorString(e); return -11; }
   return 0;

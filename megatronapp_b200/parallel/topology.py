@@ -125,12 +125,28 @@ class Topology:
     vpp: int | None = None
     order: str = "tp-cp-ep-dp-pp"
     fbd: bool = False
+    # MegaFBD with the forward tensor parallelism COLLAPSED (reference ``--ignore-forward-tensor-parallel``,
+    # parallel_state.py:896-964): every (pipeline stage, replica) is a block of 1 + tp ranks -- ONE forward rank that
+    # holds the un-sharded stage and runs true TP=1 math, followed by the tp backward ranks of that stage.
+    fbd_collapse: bool = False
     num_distributed_optimizer_instances: int = 1
     split_rank: int | None = None   # first pipeline stage of the decoder (encoder-decoder models)
 
     def __post_init__(self):
         if self.split_rank is not None and not (0 < self.split_rank < self.pp):
             raise ValueError(f"pipeline split rank {self.split_rank} must lie strictly inside [1, pp={self.pp})")
+        if self.fbd_collapse:
+            if not self.fbd:
+                raise ValueError("fbd_collapse needs fbd=True")
+            if self.cp != 1 or self.ep != 1 or (self.etp not in (None, self.tp)):
+                raise ValueError("collapsed MegaFBD does not support cp / ep > 1 or a separate expert TP size")
+            blk = (self.tp + 1) * self.pp
+            if self.world_size % blk != 0:
+                raise ValueError(f"world_size ({self.world_size}) must be a multiple of (tp + 1) * pp = {blk}")
+            object.__setattr__(self, "dp", self.world_size // blk)      # replicas; every replica has its own forward rank
+            object.__setattr__(self, "etp", self.tp)
+            object.__setattr__(self, "edp", self.world_size // blk)
+            return
         mp = self.tp * self.pp * self.cp
         if self.world_size % mp != 0:
             raise ValueError(
@@ -171,8 +187,54 @@ class Topology:
         sz = {"tp": self.etp, "ep": self.ep, "dp": self.edp, "pp": self.pp}
         return AxisLayout(tuple((n, sz[n]) for n in names))
 
+    # ---- collapsed MegaFBD: explicit rank arithmetic (blocks are not a regular grid) -----------
+    def _cblock(self, p: int, r: int) -> int:
+        return (p * self.dp + r) * (self.tp + 1)
+
+    def _cfwd(self, p: int, r: int) -> int:
+        return self._cblock(p, r)
+
+    def _cbwd(self, p: int, r: int, t: int) -> int:
+        return self._cblock(p, r) + 1 + t
+
+    def _collapsed_coords(self, rank: int) -> Dict[str, int]:
+        b, o = divmod(rank, self.tp + 1)
+        p, r = divmod(b, self.dp)
+        t = max(0, o - 1)
+        return {"tp": t, "pp": p, "dp": r, "cp": 0, "ep": 0, "etp": t, "edp": r, "fb": 0 if o == 0 else 1, "hdp": r}
+
+    def _collapsed_groups(self, kind: str) -> List[List[int]]:
+        P, R, T = self.pp, self.dp, self.tp
+        fw = lambda p, r: [self._cfwd(p, r)]                                    # noqa: E731
+        bw = lambda p, r: [self._cbwd(p, r, t) for t in range(T)]               # noqa: E731
+        if kind in ("tp", "etp", "tp_cp", "ep_tp"):
+            return [g for p in range(P) for r in range(R) for g in (fw(p, r), bw(p, r))]
+        if kind == "pp":
+            return ([[self._cfwd(p, r) for p in range(P)] for r in range(R)]
+                    + [[self._cbwd(p, r, t) for p in range(P)] for r in range(R) for t in range(T)])
+        if kind in ("dp", "dp_cp", "edp", "half_dp", "intra_dp_cp"):
+            return ([[self._cfwd(p, r) for r in range(R)] for p in range(P)]
+                    + [[self._cbwd(p, r, t) for r in range(R)] for p in range(P) for t in range(T)])
+        if kind in ("cp", "ep", "inter_dp_cp"):
+            return [[k] for k in range(self.world_size)]
+        if kind in ("mp", "tp_ep_pp"):
+            return ([[self._cfwd(p, r) for p in range(P)] for r in range(R)]
+                    + [[self._cbwd(p, r, t) for p in range(P) for t in range(T)] for r in range(R)])
+        if kind in ("tp_dp_cp", "tp_dp"):
+            return ([[self._cfwd(p, r) for r in range(R)] for p in range(P)]
+                    + [[self._cbwd(p, r, t) for r in range(R) for t in range(T)] for p in range(P)])
+        if kind == "embd":
+            return [self.embedding_ranks(g) for g in self._collapsed_groups("pp")]
+        if kind == "pos_embd":
+            return [self.position_embedding_ranks(g) for g in self._collapsed_groups("pp")]
+        if kind == "fb":          # [forward rank, backward tp rank 0, ..., tp - 1]
+            return [fw(p, r) + bw(p, r) for p in range(P) for r in range(R)]
+        raise KeyError(kind)
+
     # ---- coordinates ---------------------------------------------------
     def coords(self, rank: int) -> Dict[str, int]:
+        if self.fbd_collapse:
+            return self._collapsed_coords(rank)
         c = self.dense.coords(rank)
         e = self.expert.coords(rank)
         c["ep"] = e["ep"]
@@ -185,6 +247,8 @@ class Topology:
 
     # ---- group families ------------------------------------------------
     def groups(self, kind: str) -> List[List[int]]:
+        if self.fbd_collapse:
+            return self._collapsed_groups(kind)
         d, e = self.dense, self.expert
         if kind == "tp":
             return d.groups("tp")
@@ -269,15 +333,23 @@ class Topology:
     # ---- convenience ---------------------------------------------------
     @property
     def effective_dp(self) -> int:
+        if self.fbd_collapse:
+            return self.dp
         return self.dp // 2 if self.fbd else self.dp
 
     def is_forward_rank(self, rank: int) -> bool:
+        if self.fbd_collapse:
+            return rank % (self.tp + 1) == 0
         return self.fbd and self.coords(rank)["dp"] % 2 == 0
 
     def is_backward_rank(self, rank: int) -> bool:
+        if self.fbd_collapse:
+            return rank % (self.tp + 1) != 0
         return (not self.fbd) or self.coords(rank)["dp"] % 2 == 1
 
     def twin_of(self, rank: int) -> int:
+        """The partner across the forward/backward split; under the collapsed layout a backward rank's twin is its
+        block's forward rank and a forward rank's "twin" is backward TP rank 0 (use ``group_of('fb')`` for all)."""
         if not self.fbd:
             raise ValueError("no twin without fbd")
         g = self.group_of("fb", rank)
