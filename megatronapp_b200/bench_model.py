@@ -43,7 +43,7 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
                         use_distributed_optimizer=False, dropout=0.0, vpp=None, overlap_grad_reduce=False,
                         seed=1234, num_experts=None, ep=1, moe_topk=2, fused_grad_rs=False, fp8=None, fp8_recipe="delayed",
                         moe_grouped=False, moe_dispatcher=None, moe_ffn=None, fbd=False, etp=None,
-                        moe_aux_loss_coeff=0.0) -> BenchState:
+                        moe_aux_loss_coeff=0.0, fbd_collapse=False) -> BenchState:
     if torch.cuda.is_available() and str(device).startswith("cuda"):
         torch.cuda.set_device(torch.device(device) if ":" in str(device) else torch.cuda.current_device())
     if not ps.model_parallel_is_initialized():
@@ -52,11 +52,18 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
             kw_ps["expert_tensor_parallel_size"] = etp
         if fbd:
             kw_ps["forward_backward_disaggregating"] = True
+            kw_ps["ignore_forward_tensor_parallel"] = bool(fbd_collapse)
         ps.initialize_model_parallel(tp, pp, **kw_ps)
         if dist.is_initialized():
             p2p.build_channels()
     model_parallel_cuda_manual_seed(seed)
-    kw = dict(num_layers=num_layers, hidden_size=hidden, num_attention_heads=heads, ffn_hidden_size=ffn,
+    fbd_bwd = None
+    if ps.fbd_forward_tp_collapsed() and ps.is_forward_stage():
+        import types
+
+        fbd_bwd = types.SimpleNamespace(sequence_parallel=bool(sequence_parallel and tp > 1), tensor_model_parallel_size=tp)
+        tp, sequence_parallel = 1, False          # the un-sharded forward rank runs true TP=1 math
+    kw = dict(fbd_backward_config=fbd_bwd, num_layers=num_layers, hidden_size=hidden, num_attention_heads=heads, ffn_hidden_size=ffn,
               num_query_groups=kv_groups, tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp,
               virtual_pipeline_model_parallel_size=vpp, sequence_parallel=sequence_parallel and tp > 1,
               params_dtype=dtype, bf16=dtype == torch.bfloat16, fp16=dtype == torch.float16,

@@ -20,8 +20,13 @@ pairing inside DP) and ``p2p_communication.py:723-756`` (stage-input hand-off), 
   ``virtual_tensor_parallel_communication.py``): the channel transport of ``parallel/p2p.py``
   is deadlock-free for this data flow by construction.
 
-``--ignore-forward-tensor-parallel`` is accepted; in this revision forward ranks keep the
-backward ranks' TP degree (the collapse needs an extra weight re-shard after every step).
+``--ignore-forward-tensor-parallel`` (reference ``parallel_state.py:896-964``): every (stage, replica) becomes a
+block of ``1 + tp`` ranks -- ONE forward rank that holds the un-sharded stage and runs true TP=1 math (the reference
+emulates the tp virtual ranks with threads on that GPU and a gloo "virtual TP" shim; here it is simply a TP=1 model),
+plus the ``tp`` backward ranks.  The forward rank feeds each backward rank its (sequence-parallel slice of the) stage
+input and, after every optimizer step, re-assembles its weights from the ``tp`` updated shards
+(``sync_forward_weights``: column-parallel shards concatenate along dim 0, row-parallel along dim 1, gated fc1
+re-interleaves ``[gate_r; up_r]`` into ``[gate; up]``, replicated parameters come from TP rank 0).
 """
 from __future__ import annotations
 
@@ -46,6 +51,10 @@ def fbd_forward_backward(*, forward_step_func, data_iterator, model, num_microba
     config = schedules._get_config(m0)
     pp, rank = ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_rank()
     shape = get_tensor_shapes(seq_length, micro_batch_size, config)
+    bwd_config = config
+    if ps.fbd_forward_tp_collapsed() and ps.is_forward_stage():
+        # this rank runs TP=1 / no SP; what it ships must have the layout its BACKWARD twins expect
+        bwd_config = getattr(config, "fbd_backward_config", config)
     dtype = config.pipeline_dtype or config.params_dtype
     first, last = rank == 0, rank == pp - 1
     it = data_iterator[0] if isinstance(data_iterator, (list, tuple)) else data_iterator
@@ -57,7 +66,7 @@ def fbd_forward_backward(*, forward_step_func, data_iterator, model, num_microba
             inp = None
             if not first:
                 inp = p2p.recv(shape, dtype, ps.get_pipeline_model_parallel_prev_rank(), "fwd", "recv-forward")
-                p2p.send_corresponding_forward(inp)
+                p2p.send_corresponding_forward(inp, bwd_config)
             if last:
                 if it is not None and pp > 1:
                     pass  # labels are read by the backward twin from its own (identical) iterator
@@ -100,10 +109,64 @@ def fbd_forward_backward(*, forward_step_func, data_iterator, model, num_microba
     return store
 
 
+def _is_gated_fc1(name: str, config) -> bool:
+    return bool(getattr(config, "gated_linear_unit", False)) and name.endswith(("mlp.linear_fc1.weight", "mlp.linear_fc1.bias"))
+
+
+def _sync_forward_weights_collapsed(model) -> None:
+    """tp backward shards -> one un-sharded forward copy.  Both sides walk ``named_parameters()`` in the same order;
+    every backward rank ships ONE flat buffer (all its parameters back to back) over its ``fbw`` channel."""
+    st = ps.get_state()
+    block = st.ranks("fb")
+    fwd, twins = block[0], block[1:]
+    tp = len(twins)
+    chunks = model if isinstance(model, (list, tuple)) else [model]
+    for ch in chunks:
+        inner = ch
+        while hasattr(inner, "module"):
+            inner = inner.module
+        params = list(inner.named_parameters())
+        if ps.is_backward_stage():
+            flat = torch.cat([p.detach().reshape(-1) for _, p in params])
+            p2p.send(flat, fwd, "fbw", "fbd-weights-send")
+            continue
+        config = inner.config
+        dtype = params[0][1].dtype
+        # shard sizes as the backward ranks see them
+        sizes = []
+        for name, p in params:
+            sharded = getattr(p, "tensor_model_parallel", False)
+            sizes.append(p.numel() // tp if sharded else p.numel())
+        total = sum(sizes)
+        dev = params[0][1].device
+        shards = [p2p.recv((total,), dtype, src, "fbw", "fbd-weights-recv", device=dev) for src in twins]
+        off = 0
+        with torch.no_grad():
+            for (name, p), n in zip(params, sizes):
+                if not getattr(p, "tensor_model_parallel", False):
+                    p.copy_(shards[0][off:off + n].view_as(p))
+                else:
+                    dim = getattr(p, "partition_dim", 0)
+                    shp = list(p.shape)
+                    shp[dim] //= tp
+                    parts = [s_[off:off + n].view(shp) for s_ in shards]
+                    if _is_gated_fc1(name, config):
+                        half = shp[0] // 2       # every shard is [gate_r; up_r]: the full tensor is [gate_0..; up_0..]
+                        full = torch.cat([x[:half] for x in parts] + [x[half:] for x in parts], dim=0)
+                    else:
+                        full = torch.cat(parts, dim=dim)
+                    p.copy_(full)
+                off += n
+    p2p.flush()
+
+
 def sync_forward_weights(model) -> None:
     """Backward rank -> forward twin broadcast of the (updated) contiguous parameter buffers."""
     st = ps.get_state()
     if not st.topo.fbd:
+        return
+    if st.topo.fbd_collapse:
+        _sync_forward_weights_collapsed(model)
         return
     g = st.group("fb")
     pair = st.ranks("fb")

@@ -41,8 +41,11 @@ def build_channels() -> None:
             edges.append((a, b, "fwd"))   # activations a -> b
             edges.append((b, a, "bwd"))   # gradients  b -> a
     if topo.fbd:
-        for a, b in topo.groups("fb"):
-            edges.append((a, b, "fbd"))   # forward rank -> backward twin (stage inputs)
+        for g in topo.groups("fb"):
+            for b in g[1:]:
+                edges.append((g[0], b, "fbd"))    # forward rank -> backward twin(s): stage inputs
+                if topo.fbd_collapse:
+                    edges.append((b, g[0], "fbw"))  # backward TP rank -> un-sharded forward rank: updated weight shards
     seen = set()
     for a, b, kind in edges:
         if (a, b, kind) in seen:
@@ -144,12 +147,22 @@ def send_backward_recv_forward(input_tensor_grad, tensor_shape, config):
 
 
 def send_corresponding_forward(tensor, config=None):
-    """MegaFBD: forward rank ships a stage input to its backward twin."""
-    send(tensor, ps.get_twin_rank(), "fbd", "fbd-send")
+    """MegaFBD: forward rank ships a stage input to its backward twin.  With the forward TP collapsed the one forward
+    rank feeds all tp backward ranks of its block: each gets the full activation, or -- under sequence parallelism --
+    its own ``s / tp`` slice of the sequence dimension."""
+    if not ps.fbd_forward_tp_collapsed():
+        send(tensor, ps.get_twin_rank(), "fbd", "fbd-send")
+        return
+    twins = ps.get_fbd_block_ranks()[1:]
+    sp = bool(config is not None and getattr(config, "sequence_parallel", False))
+    n = tensor.shape[0] // len(twins) if sp else 0
+    for t, dst in enumerate(twins):
+        send(tensor[t * n:(t + 1) * n] if sp else tensor, dst, "fbd", "fbd-send")
 
 
 def recv_corresponding_forward(tensor_shape, dtype):
-    return recv(tensor_shape, dtype, ps.get_twin_rank(), "fbd", "fbd-recv", requires_grad=True)
+    src = ps.get_fbd_block_ranks()[0] if ps.fbd_forward_tp_collapsed() else ps.get_twin_rank()
+    return recv(tensor_shape, dtype, src, "fbd", "fbd-recv", requires_grad=True)
 
 
 def communicate_shapes(tensor: Optional[torch.Tensor], src_or_dst: int, kind: str, sending: bool):

@@ -141,6 +141,7 @@ def initialize_model_parallel(
     get_position_embedding_ranks=None,
     create_gloo_process_groups: bool = False,
     forward_backward_disaggregating: bool = False,
+    ignore_forward_tensor_parallel: bool = False,
     world_size: Optional[int] = None,
     rank: Optional[int] = None,
 ) -> ParallelState:
@@ -167,6 +168,7 @@ def initialize_model_parallel(
         vpp=virtual_pipeline_model_parallel_size,
         order=order,
         fbd=forward_backward_disaggregating,
+        fbd_collapse=bool(forward_backward_disaggregating and ignore_forward_tensor_parallel),
         num_distributed_optimizer_instances=num_distributed_optimizer_instances,
         split_rank=(encoder_pipeline_model_parallel_size or pipeline_model_parallel_split_rank or None)
         if pipeline_model_parallel_size > 1 else None,
@@ -409,11 +411,21 @@ def is_rank_in_position_embedding_group() -> bool:
 
 def is_forward_stage() -> bool:
     """True on a MegaFBD forward-only rank."""
-    return _STATE is not None and _STATE.topo.fbd and _STATE.coords["dp"] % 2 == 0
+    return _STATE is not None and _STATE.topo.fbd and _STATE.topo.is_forward_rank(_STATE.rank)
 
 
 def is_backward_stage() -> bool:
-    return _STATE is None or (not _STATE.topo.fbd) or _STATE.coords["dp"] % 2 == 1
+    return _STATE is None or (not _STATE.topo.fbd) or _STATE.topo.is_backward_rank(_STATE.rank)
+
+
+def fbd_forward_tp_collapsed() -> bool:
+    """``--ignore-forward-tensor-parallel``: one un-sharded forward rank serves the tp backward ranks of its stage."""
+    return _STATE is not None and _STATE.topo.fbd_collapse
+
+
+def get_fbd_block_ranks() -> List[int]:
+    """[forward rank, backward tp rank 0, ..., tp - 1] of this rank's (stage, replica) block."""
+    return get_state().ranks("fb")
 
 
 def get_twin_rank() -> int:

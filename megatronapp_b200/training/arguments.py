@@ -598,9 +598,8 @@ def validate_args(args, defaults=None):
     for bad, msg in _UNSUPPORTED:
         if bad(args):
             raise NotImplementedError(msg)
-    if getattr(args, "ignore_forward_tensor_parallel", False) and getattr(args, "rank", 0) == 0:
-        print("WARNING: --ignore-forward-tensor-parallel is accepted for CLI compatibility; forward ranks keep the "
-              "backward ranks' tensor-parallel degree in this implementation (see fbd/schedule.py)", flush=True)
+    if getattr(args, "ignore_forward_tensor_parallel", False) and not getattr(args, "forward_backward_disaggregating", False):
+        raise ValueError("--ignore-forward-tensor-parallel needs --forward-backward-disaggregating")
     for k, v in (defaults or {}).items():
         if getattr(args, k, None) is None:
             setattr(args, k, v)
@@ -615,10 +614,23 @@ def validate_args(args, defaults=None):
     if args.batch_size is not None and args.micro_batch_size is None:
         args.micro_batch_size = args.batch_size
     mp = args.tensor_model_parallel_size * args.pipeline_model_parallel_size * args.context_parallel_size
-    if args.world_size % mp != 0:
+    collapse = bool(getattr(args, "ignore_forward_tensor_parallel", False) and args.forward_backward_disaggregating)
+    if collapse:
+        # every (stage, replica) is a block of ONE un-sharded forward rank + tp backward ranks
+        blk = (args.tensor_model_parallel_size + 1) * args.pipeline_model_parallel_size
+        if args.world_size % blk != 0:
+            raise ValueError(f"world size ({args.world_size}) must be a multiple of (tp + 1) * pp = {blk} with "
+                             "--ignore-forward-tensor-parallel")
+        if args.context_parallel_size > 1 or args.expert_model_parallel_size > 1:
+            raise ValueError("MegaFBD does not support context / expert parallelism")
+        args.data_parallel_size = args.effective_data_parallel_size = args.world_size // blk
+    elif args.world_size % mp != 0:
         raise ValueError(f"world size ({args.world_size}) is not divisible by tp*pp*cp ({mp})")
-    args.data_parallel_size = args.world_size // mp
-    if args.forward_backward_disaggregating:
+    else:
+        args.data_parallel_size = args.world_size // mp
+    if collapse:
+        pass
+    elif args.forward_backward_disaggregating:
         if args.data_parallel_size % 2 != 0:
             raise ValueError("--forward-backward-disaggregating needs an even data-parallel size")
         if args.context_parallel_size > 1 or args.expert_model_parallel_size > 1:
@@ -745,6 +757,17 @@ def core_transformer_config_from_args(args, config_class=None) -> TransformerCon
     for f in dataclasses.fields(config_class):
         if hasattr(args, f.name):
             kw[f.name] = getattr(args, f.name)
+    from ..parallel import state as _ps
+
+    if _ps.fbd_forward_tp_collapsed() and _ps.is_forward_stage():
+        # un-sharded forward rank: true TP=1 execution; remember what its backward twins run so that the stage inputs it
+        # hands over have their layout (sequence-parallel slices)
+        import types
+
+        kw["fbd_backward_config"] = types.SimpleNamespace(sequence_parallel=bool(kw.get("sequence_parallel")),
+                                                          tensor_model_parallel_size=kw.get("tensor_model_parallel_size", 1))
+        kw["tensor_model_parallel_size"] = 1
+        kw["sequence_parallel"] = False
     kw["persist_layer_norm"] = not args.no_persist_layer_norm
     kw["layernorm_zero_centered_gamma"] = args.apply_layernorm_1p
     kw["layernorm_epsilon"] = args.norm_epsilon

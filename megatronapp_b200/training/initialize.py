@@ -98,6 +98,7 @@ def _initialize_distributed(args):
         nccl_communicator_config_path=args.nccl_communicator_config_path,
         order="tp-cp-ep-dp-pp" if not args.use_tp_pp_dp_mapping else "tp-cp-ep-pp-dp",
         forward_backward_disaggregating=args.forward_backward_disaggregating,
+        ignore_forward_tensor_parallel=bool(getattr(args, "ignore_forward_tensor_parallel", False)),
         world_size=args.world_size, rank=args.rank)
     if dist.is_initialized():
         p2p.build_channels()

@@ -765,6 +765,12 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     timers("model-and-optimizer-setup", log_level=0).start(barrier=True)
     append_to_progress_log("Starting job")
     model, optimizer, scheduler = setup_model_and_optimizer(model_provider, model_type)
+    if args.forward_backward_disaggregating:
+        # forward ranks start from their backward twins' weights (mandatory with --ignore-forward-tensor-parallel, where
+        # the un-sharded forward rank cannot reproduce the TP-sharded initialisation from the seed)
+        from ..fbd.schedule import sync_forward_weights
+
+        sync_forward_weights(model)
     timers("model-and-optimizer-setup").stop()
     args._flops_at_job_start = args.num_floating_point_operations_so_far
     if getattr(args, "ckpt_convert_format", None):

@@ -28,13 +28,13 @@ def _model_losses(steps=3, n_mb=4, **build_kw):
 
 
 def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=False, steps=3, n_mb=4,
-                 overlap=False):
+                 overlap=False, collapse=False, swiglu=False):
     from megatronapp_b200.bench_model import train_step
     from megatronapp_b200.parallel import state as ps
 
     rank, world = _setup()
     if fbd:
-        ps.initialize_model_parallel(tp, pp, forward_backward_disaggregating=True)
+        ps.initialize_model_parallel(tp, pp, forward_backward_disaggregating=True, ignore_forward_tensor_parallel=collapse)
         from megatronapp_b200.parallel import p2p
 
         p2p.build_channels()
@@ -42,7 +42,10 @@ def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=F
 
         install_fbd_schedule()
     st, batches = _model_losses(steps, n_mb, tp=tp, pp=pp, vpp=vpp, sequence_parallel=sp,
-                                use_distributed_optimizer=dist_opt, overlap_grad_reduce=overlap)
+                                use_distributed_optimizer=dist_opt, overlap_grad_reduce=overlap,
+                                **(dict(swiglu=True, bias=False) if swiglu else {}))
+    if fbd:
+        sync_forward_weights(st.model)          # forward ranks start from their twins' weights
     if dpp:
         from megatronapp_b200.dpp.scheduler import install_dpp_schedule
 
@@ -52,7 +55,7 @@ def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=F
     losses = []
     for s in range(steps):
         # every DP replica gets its own slice of the global batch
-        mine = batches[dpr::dp] if not fbd else batches[(ps.get_state().coords["dp"] // 2)::dp]
+        mine = batches[dpr::dp] if not fbd else batches[ps.get_state().coords["hdp"]::dp]
         if fbd:
             l = train_step(st, mine, do_optimizer=ps.is_backward_stage())
             sync_forward_weights(st.model)

@@ -95,6 +95,17 @@ def test_fbd_matches_plain_pipeline():
     _close(_last_stage_losses(res), base, 1e-5)
 
 
+@pytest.mark.parametrize("swiglu", [False, True])
+def test_fbd_forward_tp_collapse_matches_plain_tp_pipeline(swiglu):
+    """--ignore-forward-tensor-parallel: 6 ranks = pp 2 x (1 un-sharded forward rank + 2 backward TP ranks, sequence
+    parallel) reproduce the losses of the 4-rank tp2 x pp2 pipeline: the forward rank runs true TP=1 math on weights
+    re-assembled from its twins' shards every step (gated fc1 included) and hands each twin its s/tp slice."""
+    base = _last_stage_losses(run_distributed("train_parity", 4, tp=2, pp=2, sp=True, swiglu=swiglu))
+    res = run_distributed("train_parity", 6, tp=2, pp=2, sp=True, fbd=True, collapse=True, swiglu=swiglu)
+    _close(_last_stage_losses(res), base, 1e-4)
+    assert sum(1 for r in res if not r["is_backward"]) == 2
+
+
 @pytest.mark.parametrize("comm", ["a2a", "all_gather", "p2p"])
 def test_context_parallel_attention(comm):
     for r in run_distributed("cp_attention_parity", 2, comm=comm):
