@@ -82,14 +82,14 @@ struct PeerMaps2 {
   CUtensorMap m[kMaxPeers];
 };
 
-// Shared-memory plan.  Default: six 32 KB operand stages + two 16 KB epilogue staging buffers.  The reduce-scatter mode
-// trades two operand stages for four more staging buffers: a TMA store to PEER memory keeps its source buffer busy for a
-// full NVLink round trip (measured: ~2.6 GB/s per SM with two buffers, the kernel ran at compute + transfer instead of
-// max(compute, transfer)), so the bytes in flight per SM -- not the issue rate -- bound the push bandwidth.
+// Shared-memory plan: six 32 KB operand stages + two 16 KB epilogue staging buffers.  (Measured at TP4: giving the
+// reduce-scatter mode 6 staging buffers / 4 stages does NOT speed up the peer pushes -- 50 MB of 128-byte row segments
+// leave a GPU at ~400 GB/s whatever the bytes in flight per SM, NCCL's ring moves the same bytes at ~470 GB/s -- so the
+// link-bound attention-projection case stays transfer-bound and the plan is the same for every mode.)
 template <int kMode>
 struct Smem2T {
-  static constexpr int kStages = (kMode == kModeRS) ? 4 : kStagesDefault;
-  static constexpr int kCBufs = (kMode == kModeRS) ? 6 : 2;
+  static constexpr int kStages = kStagesDefault;
+  static constexpr int kCBufs = 2;
   static constexpr int kA = BM * BK * 2;          // 16 KB
   static constexpr int kB = (BN / 2) * BK * 2;    // 16 KB (this CTA's half of the B tile)
   static constexpr int kC = BM * 64 * 2;          // 16 KB
