@@ -139,6 +139,9 @@ class TPFusedComm:
         # kernel, no serialised reduce tail).  On by default; B200_FUSED_RS=0 / bench.py --no-fused-rs falls back to
         # tcgen05 GEMM + NCCL reduce-scatter (the in-tree baseline).
         self.use_fused_rs = os.environ.get("B200_FUSED_RS", "1") == "1"
+        # column-parallel wgrad with the activation re-gather fused along its reduction axis (B200_FUSED_AG_WGRAD=0: NCCL
+        # all-gather overlapped with the dgrad kernel + plain wgrad GEMM)
+        self.use_fused_ag_wgrad = os.environ.get("B200_FUSED_AG_WGRAD", "1") == "1"
         # 0 = auto (cta_group::2 kernel when the shape allows), 128 / 256 = force the 1-CTA kernel (A/B measurements)
         self.block_n = int(os.environ.get("B200_FUSED_BLOCK_N", "0"))
         self.calls = {"ag": 0, "rs": 0}
@@ -168,6 +171,17 @@ class TPFusedComm:
                           a.ptrs(reg), a.ptrs(freg), a.rank, a.size, epoch, self.n_comm_ctas, self.block_n, out_pre)
         gathered = a.local(reg, (M, K), x_local.dtype)
         return out, gathered
+
+    def ag_wgrad(self, dy: torch.Tensor, x_local: torch.Tensor, out32: torch.Tensor, accumulate: bool) -> None:
+        """``out32 (+)= dy^T @ all_gather(x_local)``: the column-parallel weight gradient with the re-gather of the
+        sequence-parallel activation fused into the GEMM's reduction loop (no NCCL all-gather next to the dgrad kernel)."""
+        a = self.arena
+        slot = self.calls["ag"] & 1
+        self.calls["ag"] += 1
+        reg, freg = self.ag[slot], self.ag_flags[slot]
+        epoch = a.next_epoch(freg)
+        ops.ext().gemm_ag_wgrad(dy, x_local, a.local_ptr + reg.offset, out32, accumulate, a.ptrs(reg), a.ptrs(freg), a.rank,
+                                a.size, epoch, self.n_comm_ctas)
 
     def gemm_rs(self, x: torch.Tensor, weight: torch.Tensor, bias=None, b_mn: bool = False) -> torch.Tensor:
         """``reduce_scatter(x @ W^T)`` along rows."""

@@ -32,6 +32,7 @@ enum GemmComm : int {
   kCommNone = 0,
   kCommAllGather = 1,      // all-gather(A rows) fused in front of the GEMM (column-parallel linear)
   kCommReduceScatter = 2,  // reduce-scatter(D rows) fused behind the GEMM
+  kCommAllGatherK = 3,     // all-gather along the reduction (token) axis of B fused into the wgrad GEMM (2-CTA kernel only)
 };
 
 enum GemmGroupMode : int {

@@ -137,6 +137,33 @@ void gemm_ag(const Tensor& A_local, int64_t gather_ptr, const Tensor& B, Tensor&
   count();
 }
 
+// column-parallel wgrad under sequence parallelism: D32[N_out, K_in] (+)= dY[tokens, N_out]^T . all_gather(X_local)[tokens, K_in]
+void gemm_ag_wgrad(const Tensor& dY, const Tensor& X_local, int64_t gather_ptr, Tensor& D, bool accumulate,
+                   std::vector<int64_t> peer_bufs, std::vector<int64_t> peer_flags, int rank, int size, int64_t epoch,
+                   int n_comm_ctas) {
+  c10::cuda::CUDAGuard guard(dY.device());
+  check_2d(dY, "dY"); check_2d(X_local, "X_local"); check_2d(D, "D");
+  TORCH_CHECK(D.scalar_type() == at::kFloat, "AG-wgrad accumulates into an fp32 gradient");
+  b200::GemmArgs g;
+  g.A = dY.data_ptr(); g.B = reinterpret_cast<const void*>(gather_ptr); g.D = D.data_ptr();
+  g.A_local = X_local.data_ptr(); g.lda_local = static_cast<int>(X_local.stride(0));
+  g.M = static_cast<int>(dY.size(1)); g.N = static_cast<int>(X_local.size(1)); g.K = static_cast<int>(dY.size(0));
+  TORCH_CHECK(X_local.size(0) * size == g.K && D.size(0) == g.M && D.size(1) == g.N, "AG-wgrad shapes");
+  g.lda = static_cast<int>(dY.stride(0)); g.ldb = g.N; g.ldd = static_cast<int>(D.stride(0));
+  g.a_mn_major = true; g.b_mn_major = true; g.is_bf16 = is_bf16(dY);
+  g.epilogue = accumulate ? b200::kEpiAccumF32 : b200::kEpiStoreF32;
+  g.comm = b200::kCommAllGatherK; g.tp_rank = rank; g.tp_size = size; g.epoch = static_cast<uint32_t>(epoch);
+  g.n_comm_ctas = n_comm_ctas;
+  for (int i = 0; i < size; ++i) {
+    g.peer_buf[i] = reinterpret_cast<void*>(peer_bufs[i]);
+    g.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  }
+  g.stream = cur_stream();
+  int rc = b200::gemm_bf16(g);
+  TORCH_CHECK(rc == 0, "b200 gemm_ag_wgrad failed (", rc, "): ", b200::gemm_last_error());
+  count();
+}
+
 void gemm_rs(const Tensor& A, const Tensor& B, Tensor& D_out, bool b_mn, const c10::optional<Tensor>& bias,
              std::vector<int64_t> peer_stage, std::vector<int64_t> peer_flags, int rank, int size,
              int64_t epoch, int block_n) {
@@ -837,6 +864,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("moe_ep_wait", &moe_ep_wait);
   m.def("moe_scatter_dprobs", &moe_scatter_dprobs);
   m.def("gemm_rs", &gemm_rs);
+  m.def("gemm_ag_wgrad", &gemm_ag_wgrad);
   m.def("gemm_flags_needed", &b200::gemm_flags_needed);
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);

@@ -24,6 +24,11 @@
 //                 them in fp32 to the accumulator it just read from TMEM, adds the bias and stores the final bf16
 //                 output.  No separate reduce phase, no serialised tail, fixed summation order (deterministic).
 //                 (reference layers.py:1200-1217; dgrad dual :496-507 with B MN-major)
+//   kModeAGK      all-gather along the REDUCTION dimension -> GEMM: the column-parallel wgrad dW = dY^T . AG(X) under sequence
+//                 parallelism.  Comm clusters push the local X shard to the peers exactly as in kModeAG; the producers walk
+//                 the token (K) axis own shard first, then in arrival order, and wait on the 128-token block flag before
+//                 loading B from the gather buffer.  Replaces the NCCL re-gather of X that used to run next to the dgrad
+//                 kernel and fight it for NVLink and SMs (reference layers.py:461-471, 509-541).
 //   kModeGroupM   grouped GEMM over a 256-row-padded ragged row layout (MoE experts, forward + dgrad): m-block ->
 //                 group through a device-side offsets array (no host sync), B/bias selected per group, optional
 //                 per-row scale (router probability) in the epilogue.  (reference moe/experts.py:90-265 gmm)
@@ -44,7 +49,7 @@ constexpr int BN = 256;         // tile N (128 rows of B per CTA)
 constexpr int BK = 64;
 constexpr int UK = 16;
 constexpr int kStagesDefault = 6;
-enum : int { kModePlain = 0, kModeAG = 1, kModeRS = 2, kModeGroupM = 3, kModeGroupK = 4 };
+enum : int { kModePlain = 0, kModeAG = 1, kModeRS = 2, kModeGroupM = 3, kModeGroupK = 4, kModeAGK = 5 };
 constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int kGroupN2 = 8;
@@ -69,6 +74,7 @@ struct P2 {
   int col_splits;
   const void* A_local;
   int lda_local;
+  int ag_cols;                    // columns of the gathered matrix (kModeAG: K, kModeAGK: N)
   void* peer_buf[kMaxPeers];
   uint32_t* peer_flags[kMaxPeers];
   // grouped
@@ -230,16 +236,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int lane = threadIdx.x & 31;
 
   // ------------------------------------------------------------------ comm CTAs (all-gather push over NVLink)
-  if constexpr (kMode == kModeAG) {
+  if constexpr (kMode == kModeAG || kMode == kModeAGK) {
     if (static_cast<int>(blockIdx.x) < p.n_comm_ctas) {
       // work item = (row block of 128 rows, destination, column split); all remote destinations first (they gate
       // the peers' GEMM tiles), the local copy (d == 0: complete gathered view for the caller's wgrad) last
       const int rb_per_rank = p.rows_per_rank / BM;
       const int per_dst = rb_per_rank * p.col_splits;
-      const int n_items = per_dst * p.tp_size;
-      const int row_bytes = p.K * 2;
+      const int n_items = per_dst * (kMode == kModeAGK ? p.tp_size - 1 : p.tp_size);   // AG-K reads its own shard in place
+      const int row_bytes = p.ag_cols * 2;
       const int split_bytes = row_bytes / p.col_splits;  // multiple of 16 (checked on host)
-      const bool contiguous = (p.lda_local == p.K) && (p.col_splits == 1) && ((BM * row_bytes) % kBulkChunk2 == 0);
+      const bool contiguous = (p.lda_local == p.ag_cols) && (p.col_splits == 1) && ((BM * row_bytes) % kBulkChunk2 == 0);
       if (contiguous) {
         // TMA bulk pipeline: thread 0 streams gmem -> smem stages, thread 32 streams smem -> peer gmem
         uint64_t* c_full = reinterpret_cast<uint64_t*>(smem + kBulkStages2 * kBulkChunk2);
@@ -339,7 +345,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
-  const int comm_clusters = (kMode == kModeAG) ? (p.n_comm_ctas >> 1) : 0;
+  const int comm_clusters = (kMode == kModeAG || kMode == kModeAGK) ? (p.n_comm_ctas >> 1) : 0;
   const int cluster_id = static_cast<int>(blockIdx.x >> 1) - comm_clusters;
   const int n_clusters = static_cast<int>(gridDim.x >> 1) - comm_clusters;
   const int num_tiles = (kMode == kModeGroupK) ? p.n_groups * p.num_m_blocks * p.num_n_blocks
@@ -349,7 +355,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_d);
-    if constexpr (kMode == kModeAG) tma_prefetch_desc(&tmap_a_local);
+    if constexpr (kMode == kModeAG || kMode == kModeAGK) tma_prefetch_desc(&tmap_a_local);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -401,7 +407,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             fence_proxy_async_all();
           }
         }
-        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        for (int kbi = t.kb0; kbi < t.kb1; ++kbi) {
+          int kb = kbi;
+          const CUtensorMap* tb = &tmap_b;
+          int kb_b = kbi;                      // k-block coordinate inside the B tensor map
+          if constexpr (kMode == kModeAGK) {
+            // token axis: own shard first, then rank-1, rank-2, ... (the order the peers' pushes arrive in)
+            const int kb_per_rank = p.rows_per_rank / BK;
+            const int hop = kbi / kb_per_rank, kin = kbi - hop * kb_per_rank;
+            int src = (p.tp_rank - hop) % p.tp_size;
+            if (src < 0) src += p.tp_size;
+            kb = src * kb_per_rank + kin;
+            kb_b = kb;
+            if (src == p.tp_rank) {
+              tb = &tmap_a_local;
+              kb_b = kin;
+            } else if ((kin & 1) == 0) {       // a flag covers 128 token rows = two k-blocks
+              const uint32_t* flag = p.peer_flags[p.tp_rank] +
+                                     (static_cast<size_t>(src) * (p.rows_per_rank / BM) + (kin >> 1)) * p.col_splits;
+              for (int cs = 0; cs < p.col_splits; ++cs) {
+                while (static_cast<int32_t>(ld_acquire_sys(flag + cs) - p.epoch) < 0) __nanosleep(64);
+              }
+              fence_proxy_async_all();
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], kPairStageBytes);
           else mbar_arrive_remote(&full_bar[stage], 0);
@@ -415,11 +444,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               tma_load_2d_2sm(ta, &full_bar[stage], sa + j * (BK * 128), m0 + j * 64, kb * BK);
           }
           if constexpr (!kBMn) {
-            tma_load_2d_2sm(&tmap_b, &full_bar[stage], sb, kb * BK, n0 + b_row_off);
+            tma_load_2d_2sm(tb, &full_bar[stage], sb, kb_b * BK, n0 + b_row_off);
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / 2) / 64; ++j)
-              tma_load_2d_2sm(&tmap_b, &full_bar[stage], sb + j * (BK * 128), n0 + j * 64, kb * BK + b_k_off);
+              tma_load_2d_2sm(tb, &full_bar[stage], sb + j * (BK * 128), n0 + j * 64, kb_b * BK + b_k_off);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -731,6 +760,10 @@ bool gemm2_supported(const GemmArgs& a) {
   if (a.comm == kCommAllGather) {
     return a.epilogue == kEpiStore16 && !a.a_mn_major && a.tp_size >= 2 && a.M % (a.tp_size * 256) == 0 && a.N >= 128;
   }
+  if (a.comm == kCommAllGatherK) {
+    return (a.epilogue == kEpiAccumF32 || a.epilogue == kEpiStoreF32) && a.a_mn_major && a.b_mn_major && a.tp_size >= 2 &&
+           a.K % (a.tp_size * 128) == 0 && a.M >= 256 && a.N >= 128 && a.N % 8 == 0;
+  }
   if (a.comm == kCommReduceScatter) {
     return a.epilogue == kEpiReduceScatter && !a.a_mn_major && a.tp_size >= 2 && a.M % (a.tp_size * 256) == 0 &&
            a.N >= 128 && a.N % 8 == 0;
@@ -766,6 +799,20 @@ int gemm2_bf16(const GemmArgs& a) {
       g_err2 = "GroupK: MN-major A and B, fp32 accumulate epilogue"; return -4;
     }
     if (a.M % 256 != 0) { g_err2 = "GroupK: M (output features) must be a multiple of 256"; return -4; }
+  } else if (a.comm == kCommAllGatherK) {
+    mode = kModeAGK;
+    if (a.tp_size < 2 || a.tp_size > kMaxPeers) { g_err2 = "fused collective needs 2 <= tp <= 8"; return -4; }
+    if (a.K % (a.tp_size * 128) != 0) { g_err2 = "AG-K fusion needs tokens % (tp*128) == 0"; return -4; }
+    p.rows_per_rank = a.K / a.tp_size;
+    for (int i = 0; i < a.tp_size; ++i) { p.peer_buf[i] = a.peer_buf[i]; p.peer_flags[i] = a.peer_flags[i]; }
+    p.A_local = a.A_local; p.lda_local = a.lda_local; p.ag_cols = a.N;
+    p.n_comm_ctas = a.n_comm_ctas > 0 ? (a.n_comm_ctas + 1) / 2 * 2 : 12;
+    const int base_items = (p.rows_per_rank / BM) * a.tp_size;
+    int cs = 1;
+    const bool bulk_ok = (a.lda_local == a.N) && ((BM * a.N * 2) % kBulkChunk2 == 0);
+    while (!bulk_ok && base_items * cs < p.n_comm_ctas && (a.N * 2) % (32 * cs) == 0 && cs < 8) cs *= 2;
+    p.col_splits = cs;
+    if (p.n_comm_ctas / 2 >= clusters) { g_err2 = "too many comm CTAs"; return -4; }
   } else if (a.comm != kCommNone) {
     if (a.tp_size < 2 || a.tp_size > kMaxPeers) { g_err2 = "fused collective needs 2 <= tp <= 8"; return -4; }
     if (a.M % (a.tp_size * 256) != 0) { g_err2 = "2-CTA fused collective needs M % (tp*256) == 0"; return -4; }
@@ -777,7 +824,7 @@ int gemm2_bf16(const GemmArgs& a) {
       mode = kModeAG;
       if ((a.K * 2) % 16 != 0) { g_err2 = "AG fusion needs K % 8 == 0"; return -4; }
       p.chunk_base = a.tp_rank; p.chunk_dir = -1;        // own shard first, then arrival order
-      p.A_local = a.A_local; p.lda_local = a.lda_local;
+      p.A_local = a.A_local; p.lda_local = a.lda_local; p.ag_cols = a.K;
       p.n_comm_ctas = a.n_comm_ctas > 0 ? (a.n_comm_ctas + 1) / 2 * 2 : 12;
       const int base_items = (p.rows_per_rank / BM) * a.tp_size;
       int cs = 1;
@@ -819,6 +866,7 @@ int gemm2_bf16(const GemmArgs& a) {
   if (!a.a_mn_major) ok = ok && tmap2(&ta, a.A, dt, a.K, a.M, a.lda, BK, BM);
   else ok = ok && tmap2(&ta, a.A, dt, a.M, a.K, a.lda, 64, BK);
   if (mode == kModeAG) ok = ok && tmap2(&tal, a.A_local, dt, a.K, p.rows_per_rank, a.lda_local, BK, BM);
+  else if (mode == kModeAGK) ok = ok && tmap2(&tal, a.A_local, dt, a.N, p.rows_per_rank, a.lda_local, 64, BK);
   else tal = ta;
   const uint64_t b_groups = (mode == kModeGroupM) ? static_cast<uint64_t>(a.n_groups) : 1;
   if (!a.b_mn_major) ok = ok && tmap2(&tb, a.B, dt, a.K, static_cast<uint64_t>(a.N) * b_groups, a.ldb, BK, BN / 2);
@@ -860,6 +908,8 @@ int gemm2_bf16(const GemmArgs& a) {
   G2_CASE(false, true, kEpiStore16, kModeAG)
   G2_CASE(false, false, kEpiReduceScatter, kModeRS)
   G2_CASE(false, true, kEpiReduceScatter, kModeRS)
+  G2_CASE(true, true, kEpiAccumF32, kModeAGK)
+  G2_CASE(true, true, kEpiStoreF32, kModeAGK)
   // grouped (MoE)
   G2_CASE(false, false, kEpiStore16, kModeGroupM)
   G2_CASE(false, true, kEpiStore16, kModeGroupM)

@@ -730,7 +730,8 @@ int gemm_bf16(const GemmArgs& a) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { g_last_error = "empty problem"; return -1; }
   // block_n: 2 = force the cta_group::2 kernel, 128 / 256 = force the 1-CTA kernel, 0 = auto
   if (a.group_mode != kGroupNone && a.block_n != 2 && a.block_n != 0) { g_last_error = "grouped GEMM runs on the 2-CTA kernel only"; return -3; }
-  if ((a.group_mode != kGroupNone || a.block_n == 2 || (a.block_n == 0 && prefer_2cta())) && gemm2_supported(a)) {
+  if (a.comm == kCommAllGatherK && !gemm2_supported(a)) { g_last_error = "AG-K wgrad: unsupported shape for the 2-CTA kernel"; return -3; }
+  if ((a.group_mode != kGroupNone || a.comm == kCommAllGatherK || a.block_n == 2 || (a.block_n == 0 && prefer_2cta())) && gemm2_supported(a)) {
     if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15) ||
         (reinterpret_cast<uintptr_t>(a.D) & 15) || (a.lda % 8) || (a.ldb % 8) ||
         ((a.epilogue == kEpiStore16 || a.epilogue == kEpiReduceScatter) ? (a.ldd % 8) : ((a.ldd % 4) || (a.N % 4)))) {

@@ -177,7 +177,14 @@ class _ColumnParallelFn(torch.autograd.Function):
         handle = None
         total = x2
         group = ps.get_tensor_model_parallel_group()
-        if ctx.sp and tp > 1 and ctx.needs_input_grad[1]:
+        # fused AG-wgrad: the activation re-gather rides inside the wgrad GEMM (its reduction axis is the token axis), so no
+        # NCCL all-gather competes with the dgrad->reduce-scatter kernel for NVLink and SMs
+        main_grad = getattr(weight, "main_grad", None)
+        fused_wgrad = (ctx.sp and tp > 1 and ctx.needs_input_grad[1] and ctx.fused and ctx.fuse_wgrad
+                       and main_grad is not None and main_grad.dtype == torch.float32 and _FUSED_COMM is not None
+                       and _FUSED_COMM.use_fused_ag_wgrad and _fusable(dy2.shape[0], dy2, x2)
+                       and weight.shape[0] >= 256 and x2.is_contiguous())
+        if ctx.sp and tp > 1 and ctx.needs_input_grad[1] and not fused_wgrad:
             # re-gather the activation for wgrad, overlapped with the dgrad GEMM (reference :461-471)
             total = torch.empty((x2.shape[0] * tp, x2.shape[1]), dtype=x2.dtype, device=x2.device)
             handle = dist.all_gather_into_tensor(total, x2, group=group, async_op=True)
@@ -203,7 +210,16 @@ class _ColumnParallelFn(torch.autograd.Function):
                     ar_handle = dist.all_reduce(dx, group=group, async_op=True)
             dx = dx.view(ctx.x_shape)
         dw = db = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and fused_wgrad:
+            first = (not getattr(weight, "grad_added_to_main_grad", False)) and getattr(weight, "b200_wgrad_store_first", False)
+            with _scope("ag_wgrad", data=x2.numel() * x2.element_size() * (tp - 1)):
+                _FUSED_COMM.ag_wgrad(dy2, x2, main_grad, accumulate=not first)
+            weight.grad_added_to_main_grad = True
+            if getattr(weight, "b200_wgrad_store_first", False):
+                hook = getattr(weight, "grad_ready_hook", None)
+                if hook is not None:
+                    hook()
+        elif ctx.needs_input_grad[1]:
             if handle is not None:
                 handle.wait()
             dw = ops.wgrad(dy2, total, weight, ctx.fuse_wgrad)

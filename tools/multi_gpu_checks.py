@@ -205,6 +205,32 @@ def main():
 
         log("gemm_rs_dgrad_cublas+nccl_ms", timed(dgrad_unfused))
         fc.block_n = 0
+        # ---------------- AG -> wgrad (column-parallel weight gradient: all-gather fused along the reduction axis)
+        for (tok, n_out, k_in, name) in [(Mt, 16384 // world, 4096, "fc1"), (Mt, 12288 // world, 4096, "qkv")]:
+            torch.manual_seed(500 + rank)
+            x_l = torch.randn(tok // world, k_in, device="cuda", dtype=dt) * 0.5
+            dyw = torch.randn(tok, n_out, device="cuda", dtype=dt) * 0.1
+            xf = torch.empty(tok, k_in, device="cuda", dtype=dt)
+            dist.all_gather_into_tensor(xf, x_l, group=group)
+            refw = dyw.float().t() @ xf.float()
+            g32 = torch.zeros(n_out, k_in, device="cuda")
+            fc.ag_wgrad(dyw, x_l, g32, accumulate=False)
+            torch.cuda.synchronize()
+            log(f"ag_wgrad_{name}_err", rel_err(g32, refw))
+            fc.ag_wgrad(dyw, x_l, g32, accumulate=True)
+            torch.cuda.synchronize()
+            log(f"ag_wgrad_{name}_accum_err", rel_err(g32, 2 * refw))
+
+            def wg_unfused():
+                dist.all_gather_into_tensor(xf, x_l, group=group)
+                ops.gemm(dyw, xf, out=g32, a_mn=True, b_mn=True, epilogue=1)
+
+            tw = {"fused": timed(lambda: fc.ag_wgrad(dyw, x_l, g32, accumulate=True)), "nccl+b200gemm": timed(wg_unfused),
+                  "gemm_only": timed(lambda: ops.gemm(dyw, xf, out=g32, a_mn=True, b_mn=True, epilogue=1))}
+            roof = roofline_ms(2.0 * tok * n_out * k_in, (tok // world) * k_in * 2 * (world - 1))
+            tw.update(roofline_ms=roof, frac_of_roofline=roof / tw["fused"], tflops_fused=2.0 * tok * n_out * k_in / tw["fused"] / 1e9)
+            log(f"ag_wgrad_{name}_ms", tw)
+
         # ---------------- fused bucket reduce-scatter (scale + cast + RS)
         n = 8 * 1024 * 1024
         torch.manual_seed(400 + rank)
