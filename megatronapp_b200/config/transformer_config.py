@@ -161,6 +161,7 @@ class TransformerConfig(ModelParallelConfig):
     distribute_saved_activations: Optional[bool] = None
     recompute_modules: Optional[List[str]] = None
 
+    mrope_section: Optional[list] = None           # M-RoPE: rotary channel pairs driven by (temporal, height, width) positions
     fbd_backward_config: Optional[object] = None   # collapsed MegaFBD: the (tp, SP) layout of this forward rank's backward twins
     fp8: Optional[str] = None
     fp8_recipe: Optional[str] = "delayed"

@@ -138,6 +138,37 @@ class RotaryEmbedding(nn.Module):
         return t
 
 
+class MultimodalRotaryEmbedding(nn.Module):
+    """M-RoPE (Qwen2-VL): three position streams -- temporal, height, width -- each drive their own section of the rotary
+    channels.  ``forward(position_ids [3, b, s], mrope_section)`` -> ``[s, b, 2 * dim/2]`` table of (cos | sin) with
+    channel ``c`` taken from stream ``section_of(c) % 3``.  Parity: reference ``rotary_pos_embedding.py:224-310``."""
+
+    def __init__(self, kv_channels: int, rotary_percent: float = 1.0, rotary_interleaved: bool = False,
+                 seq_len_interpolation_factor: Optional[float] = None, rotary_base: float = 10000.0):
+        super().__init__()
+        dim = kv_channels if rotary_percent >= 1.0 else int(kv_channels * rotary_percent)
+        self.dim, self.rotary_interleaved = dim, rotary_interleaved
+        self.seq_len_interpolation_factor = seq_len_interpolation_factor
+        self.register_buffer("inv_freq", 1.0 / (rotary_base ** (torch.arange(0, dim, 2, dtype=torch.float32) / dim)),
+                             persistent=False)
+
+    def forward(self, position_ids: torch.Tensor, mrope_section) -> torch.Tensor:
+        if position_ids.dim() != 3 or position_ids.shape[0] != 3:
+            raise ValueError("M-RoPE position ids must be [3, batch, seq] (temporal, height, width)")
+        if sum(mrope_section) != self.dim // 2:
+            raise ValueError(f"mrope_section {list(mrope_section)} must sum to rotary_dim / 2 = {self.dim // 2}")
+        pos = position_ids.float()
+        if self.seq_len_interpolation_factor is not None:
+            pos = pos / self.seq_len_interpolation_factor
+        ang = pos.unsqueeze(-1) * self.inv_freq.to(pos.device)                      # [3, b, s, dim/2]
+        parts, c0 = [], 0
+        for i, n in enumerate(mrope_section):
+            parts.append(ang[i % 3, :, :, c0:c0 + n])
+            c0 += n
+        ang = torch.cat(parts, dim=-1).transpose(0, 1)                               # [s, b, dim/2]
+        return torch.cat([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+
 class YarnRotaryEmbedding(RotaryEmbedding):
     """YaRN: NTK-by-parts interpolation of the rotary frequencies + attention temperature."""
 

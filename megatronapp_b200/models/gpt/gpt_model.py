@@ -17,7 +17,7 @@ from ...parallel.tp_layers import ColumnParallelLinear
 from ...scan.tracer import scope as _scope
 from ...transformer.spec_utils import ModuleSpec
 from ...transformer.transformer_block import TransformerBlock
-from ..common.embeddings import LanguageModelEmbedding, RotaryEmbedding
+from ..common.embeddings import LanguageModelEmbedding, MultimodalRotaryEmbedding, RotaryEmbedding
 from ..common.language_module import LanguageModule
 
 
@@ -48,6 +48,12 @@ class GPTModel(LanguageModule):
             self.rotary_pos_emb = RotaryEmbedding(config.kv_channels, rotary_percent, config.rotary_interleaved,
                                                   seq_len_interpolation_factor, rotary_base, rope_scaling,
                                                   rope_scaling_factor)
+        if position_embedding_type == "mrope":
+            self.rotary_pos_emb = MultimodalRotaryEmbedding(config.kv_channels, rotary_percent, config.rotary_interleaved,
+                                                            seq_len_interpolation_factor, rotary_base)
+            self.mrope_section = list(getattr(config, "mrope_section", None) or [])
+            if not self.mrope_section:
+                raise ValueError("position_embedding_type 'mrope' needs config.mrope_section (--mrope-section t h w)")
         self.decoder = TransformerBlock(config, transformer_layer_spec, pre_process=pre_process,
                                         post_process=post_process)
         if post_process:
@@ -87,6 +93,9 @@ class GPTModel(LanguageModule):
                 from ...parallel.context_parallel import get_pos_emb_on_this_cp_rank
 
                 rotary = get_pos_emb_on_this_cp_rank(rotary, 0)
+        if self.position_embedding_type == "mrope":
+            pid = position_ids if position_ids.dim() == 3 else position_ids.unsqueeze(0).expand(3, -1, -1)
+            rotary = self.rotary_pos_emb(pid, self.mrope_section)                     # [s, b, rot] per-sample table
         with _scope("decoder"):
             hidden = self.decoder(hidden_states=decoder_input, attention_mask=attention_mask,
                                   inference_context=inference_context, rotary_pos_emb=rotary,

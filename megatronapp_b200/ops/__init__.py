@@ -364,11 +364,16 @@ def rope_cos_sin(seq_len: int, rot_dim: int, base: float = 10000.0, device=None,
 
 
 def rope_ref(x, cos_sin, interleaved=False, inverse=False):
+    """``cos_sin``: [s, rot] (one table for the batch) or [s, b, rot] (per-sample positions: M-RoPE)."""
     s = x.shape[0]
     rot = cos_sin.shape[-1]
     half = rot // 2
-    cos = cos_sin[:s, :half].float()[:, None, None, :]
-    sin = cos_sin[:s, half:].float()[:, None, None, :]
+    if cos_sin.dim() == 3:
+        cos = cos_sin[:s, :, :half].float()[:, :, None, :]
+        sin = cos_sin[:s, :, half:].float()[:, :, None, :]
+    else:
+        cos = cos_sin[:s, :half].float()[:, None, None, :]
+        sin = cos_sin[:s, half:].float()[:, None, None, :]
     if inverse:
         sin = -sin
     xf = x.float()
@@ -396,7 +401,7 @@ class _RopeFn(torch.autograd.Function):
 
 
 def rope(x, cos_sin, interleaved=False):
-    if _native(x) and x.dim() == 4 and cos_sin.dtype == torch.float32 and cos_sin.is_contiguous():
+    if _native(x) and x.dim() == 4 and cos_sin.dim() == 2 and cos_sin.dtype == torch.float32 and cos_sin.is_contiguous():
         return _RopeFn.apply(x, cos_sin, interleaved)
     return rope_ref(x, cos_sin, interleaved)
 

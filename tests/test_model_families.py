@@ -493,3 +493,30 @@ def test_packed_thd_sequences_match_separate_forward():
     loss = m(packed, pos, None, labels=packed, packed_seq_params=psp).mean()
     loss.backward()
     assert m.decoder.layers[0].self_attention.linear_qkv.weight.grad.abs().sum() > 0
+
+
+def test_mrope_reduces_to_rope_for_text_and_separates_streams():
+    """M-RoPE (reference rotary_pos_embedding.py:224): with identical temporal/height/width ids it IS ordinary RoPE; with
+    distinct ids every channel section follows its own position stream."""
+    import torch
+
+    from megatronapp_b200 import ops
+    from megatronapp_b200.models.common.embeddings import MultimodalRotaryEmbedding, RotaryEmbedding
+
+    torch.manual_seed(0)
+    s, b, h, d = 12, 2, 3, 16
+    x = torch.randn(s, b, h, d)
+    pid = torch.arange(s).view(1, 1, s).expand(3, b, s)
+    m = MultimodalRotaryEmbedding(d)
+    table = m(pid, [2, 3, 3])
+    assert table.shape == (s, b, d)
+    ref = ops.rope_ref(x, RotaryEmbedding(d)(s, device="cpu"))
+    assert torch.allclose(ops.rope(x, table), ref, atol=1e-6)
+    pid2 = torch.stack([pid[0], pid[1] * 2, pid[2] * 3])
+    t2 = m(pid2, [2, 3, 3])
+    half = d // 2
+    assert torch.allclose(t2[..., :2], table[..., :2])                      # temporal section unchanged
+    assert not torch.allclose(t2[..., 2:5], table[..., 2:5])                # height section follows the doubled ids
+    ang = torch.atan2(t2[..., half + 2:half + 5], t2[..., 2:5])
+    ang_ref = torch.atan2(table[..., half + 2:half + 5], table[..., 2:5])
+    assert torch.allclose(torch.remainder(ang[1], 6.283185307), torch.remainder(2 * ang_ref[1], 6.283185307), atol=1e-4)

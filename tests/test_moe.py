@@ -46,3 +46,34 @@ def test_expert_parallel_grad_norm_and_clipping_agree_across_ranks():
     res = run_distributed("ep_clip_consistency", 2)
     assert res[0]["norms"] and res[0]["norms"] == pytest.approx(res[1]["norms"], rel=1e-6), res
     assert res[0]["dense"] == pytest.approx(res[1]["dense"], rel=1e-9), res      # dense replicas stay identical
+
+
+@pytest.mark.parametrize("grouped", [False, True])
+def test_upcycled_moe_reproduces_the_dense_model(grouped):
+    """Sparse upcycling: every expert starts as the dense MLP, so (top-k probabilities sum to 1) the MoE model's logits
+    equal the dense model's on day 0."""
+    import torch
+    import torch.nn.functional as F
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+    from megatronapp_b200.moe.upcycling_utils import upcycle_state_dict
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(7)
+    kw = dict(num_layers=2, hidden_size=32, num_attention_heads=4, ffn_hidden_size=64, add_bias_linear=False,
+              activation_func=F.silu, gated_linear_unit=True, use_cpu_initialization=True, hidden_dropout=0.0,
+              attention_dropout=0.0)
+    dense = GPTModel(TransformerConfig(**kw), get_gpt_layer_local_spec(), 64, 16)
+    cfg_m = TransformerConfig(num_moe_experts=4, moe_router_topk=2, moe_grouped_gemm=grouped,
+                              moe_token_dispatcher_type="fused" if grouped else "alltoall", **kw)
+    moe = GPTModel(cfg_m, get_gpt_layer_local_spec(4, grouped), 64, 16)
+    sd = upcycle_state_dict([moe], [dense])["model"]
+    moe.load_state_dict(sd, strict=True)
+    ids = torch.randint(0, 64, (2, 16))
+    pos = torch.arange(16).unsqueeze(0).expand(2, -1)
+    dense.eval(), moe.eval()
+    with torch.no_grad():
+        assert torch.allclose(moe(ids, pos, None), dense(ids, pos, None), atol=1e-5)
