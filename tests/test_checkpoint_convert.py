@@ -295,3 +295,68 @@ def test_hf_mixtral_to_core_logit_parity_and_expert_parallel_layout(tmp_path):
     again = conv.load_hf_mixtral(out)
     assert all(torch.equal(again["weights"][k], v) for k, v in ck["weights"].items())
     assert json.load(open(os.path.join(out, "config.json")))["num_local_experts"] == 4
+
+
+def test_hf_llava_roundtrip_and_loads_into_the_core_model(tmp_path):
+    """HF LLaVA layout (CLIP tower + MLP projector + Llama) -> core keys -> HF layout is the identity, and the core-side
+    keys / shapes are exactly the ones ``LLaVAModel`` declares (reference loader_llava / saver_hf_llava)."""
+    import importlib.util
+    import json
+    import os
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("conv", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                       "tools", "checkpoint", "convert.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    torch.manual_seed(0)
+    vh, vl, vnh, vff, th, tl, tnh, tng, tff, V = 32, 2, 4, 64, 48, 2, 4, 2, 96, 128
+    sd = {}
+    vt = "model.vision_tower.vision_model."
+    sd[vt + "embeddings.patch_embedding.weight"] = torch.randn(vh, 3, 14, 14)
+    sd[vt + "embeddings.class_embedding"] = torch.randn(vh)
+    sd[vt + "embeddings.position_embedding.weight"] = torch.randn(5, vh)
+    for nm, shp in (("weight", (vh,)), ("bias", (vh,))):
+        sd[vt + f"pre_layrnorm.{nm}"] = torch.randn(*shp)
+    for i in range(vl):
+        a = f"{vt}encoder.layers.{i}."
+        for p in ("q", "k", "v", "out"):
+            sd[a + f"self_attn.{p}_proj.weight"], sd[a + f"self_attn.{p}_proj.bias"] = torch.randn(vh, vh), torch.randn(vh)
+        for ln in ("layer_norm1", "layer_norm2"):
+            sd[a + ln + ".weight"], sd[a + ln + ".bias"] = torch.randn(vh), torch.randn(vh)
+        sd[a + "mlp.fc1.weight"], sd[a + "mlp.fc1.bias"] = torch.randn(vff, vh), torch.randn(vff)
+        sd[a + "mlp.fc2.weight"], sd[a + "mlp.fc2.bias"] = torch.randn(vh, vff), torch.randn(vh)
+    sd["model.multi_modal_projector.linear_1.weight"], sd["model.multi_modal_projector.linear_1.bias"] = torch.randn(th, vh), torch.randn(th)
+    sd["model.multi_modal_projector.linear_2.weight"], sd["model.multi_modal_projector.linear_2.bias"] = torch.randn(th, th), torch.randn(th)
+    lm = "model.language_model."
+    hn = th // tnh
+    sd[lm + "embed_tokens.weight"], sd[lm + "norm.weight"], sd["lm_head.weight"] = torch.randn(V, th), torch.randn(th), torch.randn(V, th)
+    for i in range(tl):
+        a = f"{lm}layers.{i}."
+        sd[a + "self_attn.q_proj.weight"], sd[a + "self_attn.o_proj.weight"] = torch.randn(tnh * hn, th), torch.randn(th, tnh * hn)
+        sd[a + "self_attn.k_proj.weight"], sd[a + "self_attn.v_proj.weight"] = torch.randn(tng * hn, th), torch.randn(tng * hn, th)
+        sd[a + "input_layernorm.weight"], sd[a + "post_attention_layernorm.weight"] = torch.randn(th), torch.randn(th)
+        sd[a + "mlp.gate_proj.weight"], sd[a + "mlp.up_proj.weight"] = torch.randn(tff, th), torch.randn(tff, th)
+        sd[a + "mlp.down_proj.weight"] = torch.randn(th, tff)
+    src = tmp_path / "hf"
+    src.mkdir()
+    torch.save(sd, src / "pytorch_model.bin")
+    json.dump({"model_type": "llava", "image_token_index": 32000,
+               "vision_config": {"hidden_size": vh, "num_hidden_layers": vl, "num_attention_heads": vnh, "intermediate_size": vff,
+                                 "patch_size": 14, "image_size": 28},
+               "text_config": {"hidden_size": th, "num_hidden_layers": tl, "num_attention_heads": tnh, "num_key_value_heads": tng,
+                               "intermediate_size": tff, "vocab_size": V, "max_position_embeddings": 64, "rope_theta": 10000.0,
+                               "rms_norm_eps": 1e-5}}, open(src / "config.json", "w"))
+    ck = conv.load_hf_llava(str(src))
+    w = ck["weights"]
+    assert w["vision_model.decoder.layers.0.self_attention.linear_qkv.weight"].shape == (3 * vh, vh)
+    assert w["vision_model.decoder.layers.1.self_attention.linear_qkv.bias"].shape == (3 * vh,)
+    assert w["language_model.decoder.layers.0.self_attention.linear_qkv.weight"].shape == ((tnh + 2 * tng) * hn, th)
+    assert w["language_model.decoder.layers.0.mlp.linear_fc1.weight"].shape == (2 * tff, th)
+    assert w["vision_projection.encoder.linear_fc2.weight"].shape == (th, th) and ck["config"]["image_token_index"] == 32000
+    dst = tmp_path / "back"
+    conv.save_hf_llava(ck, str(dst))
+    back = torch.load(dst / "pytorch_model.bin")
+    assert set(back) == set(sd)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)

@@ -362,6 +362,118 @@ def save_hf_mixtral(ckpt: Dict, save_dir: str):
     _write_hf(sd, hc, save_dir)
 
 
+# ------------------------------------------------------------------------------------ HF: LLaVA
+# reference tools/checkpoint/{loader_llava,saver_llava,saver_hf_llava}.py: CLIP vision tower + 2-layer MLP projector +
+# Llama language model.  Core-side keys: ``vision_model.*`` (CLIPViTModel), ``vision_projection.encoder.*``,
+# ``language_model.*`` (GPTModel).  Both HF prefix generations are accepted (``model.vision_tower...`` and the older
+# ``vision_tower...`` / ``language_model.model...``).
+_LLAVA_VIT = (("input_layernorm", "layer_norm1"), ("pre_mlp_layernorm", "layer_norm2"), ("self_attention.linear_proj", "self_attn.out_proj"),
+              ("mlp.linear_fc1", "mlp.fc1"), ("mlp.linear_fc2", "mlp.fc2"))
+
+
+def _strip_llava_prefixes(sd: Dict) -> Dict:
+    out = {}
+    for k, v in sd.items():
+        k2 = k[len("model."):] if k.startswith("model.") and not k.startswith("model.layers") else k
+        k2 = k2.replace("language_model.model.", "language_model.").replace("language_model.lm_head.", "lm_head.")
+        out[k2] = v
+    return out
+
+
+def load_hf_llava(load_dir: str) -> Dict:
+    hc = json.load(open(os.path.join(load_dir, "config.json")))
+    vc, tc = hc["vision_config"], hc["text_config"]
+    sd = _strip_llava_prefixes(_hf_state(load_dir))
+    w = {}
+    # ---- vision tower (CLIP ViT: MHA with biases, learned positions, class token, pre LayerNorm)
+    nh, h = vc["num_attention_heads"], vc["hidden_size"]
+    hn = h // nh
+    vt = "vision_tower.vision_model."
+    w["vision_model.conv1.weight"] = sd[vt + "embeddings.patch_embedding.weight"]
+    w["vision_model.class_token"] = sd[vt + "embeddings.class_embedding"].reshape(1, 1, h)
+    w["vision_model.position_embeddings.weight"] = sd[vt + "embeddings.position_embedding.weight"]
+    for nm in ("weight", "bias"):
+        w[f"vision_model.ln_pre.{nm}"] = sd[vt + f"pre_layrnorm.{nm}"]
+    for i in range(vc["num_hidden_layers"]):
+        a, b = f"{vt}encoder.layers.{i}.", f"vision_model.decoder.layers.{i}."
+        for nm in ("weight", "bias"):
+            q, k, v = (sd[a + f"self_attn.{p}_proj.{nm}"] for p in "qkv")
+            if nm == "bias":
+                q, k, v = (t.unsqueeze(-1) for t in (q, k, v))
+            fused = qkv_from_separate(q, k, v, nh, nh, hn)
+            w[b + f"self_attention.linear_qkv.{nm}"] = fused.squeeze(-1) if nm == "bias" else fused
+            for core, hf in _LLAVA_VIT:
+                w[b + f"{core}.{nm}"] = sd[a + f"{hf}.{nm}"]
+    # ---- projector
+    for j, name in ((1, "linear_fc1"), (2, "linear_fc2")):
+        for nm in ("weight", "bias"):
+            w[f"vision_projection.encoder.{name}.{nm}"] = sd[f"multi_modal_projector.linear_{j}.{nm}"]
+    # ---- language model: reuse the Llama mapping on the language sub-dict
+    lsd = {("model." + k[len("language_model."):]): v for k, v in sd.items() if k.startswith("language_model.")}
+    if "lm_head.weight" in sd:
+        lsd["lm_head.weight"] = sd["lm_head.weight"]
+    tmp = os.path.join(load_dir, "._llava_text_tmp")
+    os.makedirs(tmp, exist_ok=True)
+    try:
+        torch.save(lsd, os.path.join(tmp, "pytorch_model.bin"))
+        json.dump(tc, open(os.path.join(tmp, "config.json"), "w"))
+        text = load_hf_llama(tmp)
+    finally:
+        import shutil
+
+        shutil.rmtree(tmp, ignore_errors=True)
+    for k, v in text["weights"].items():
+        w["language_model." + k] = v
+    cfg = dict(text["config"])
+    cfg.update(model_kind="llava", vision=dict(num_layers=vc["num_hidden_layers"], hidden_size=h, num_attention_heads=nh,
+                                                ffn_hidden_size=vc["intermediate_size"], patch_dim=vc.get("patch_size", 14),
+                                                img_h=vc.get("image_size", 336), img_w=vc.get("image_size", 336)),
+               image_token_index=hc.get("image_token_index", hc.get("image_token_id", -200)))
+    return {"config": cfg, "weights": w, "iteration": 0}
+
+
+def save_hf_llava(ckpt: Dict, save_dir: str):
+    cfg, w = ckpt["config"], ckpt["weights"]
+    vis = cfg["vision"]
+    nh, h = vis["num_attention_heads"], vis["hidden_size"]
+    hn = h // nh
+    text = {"config": {k: v for k, v in cfg.items() if k not in ("vision", "model_kind", "image_token_index")},
+            "weights": {k[len("language_model."):]: v for k, v in w.items() if k.startswith("language_model.")}}
+    lsd, tc = _hf_llama_trunk_out(text)
+    for i in range(text["config"]["num_layers"]):
+        a, b = f"model.layers.{i}.", f"decoder.layers.{i}."
+        g, u = torch.chunk(text["weights"][b + "mlp.linear_fc1.weight"], 2, dim=0)
+        lsd[a + "mlp.gate_proj.weight"], lsd[a + "mlp.up_proj.weight"] = g, u
+        lsd[a + "mlp.down_proj.weight"] = text["weights"][b + "mlp.linear_fc2.weight"]
+    sd = {}
+    for k, v in lsd.items():
+        sd["lm_head.weight" if k == "lm_head.weight" else "model.language_model." + k[len("model."):]] = v
+    vt = "model.vision_tower.vision_model."
+    sd[vt + "embeddings.patch_embedding.weight"] = w["vision_model.conv1.weight"]
+    sd[vt + "embeddings.class_embedding"] = w["vision_model.class_token"].reshape(h)
+    sd[vt + "embeddings.position_embedding.weight"] = w["vision_model.position_embeddings.weight"]
+    for nm in ("weight", "bias"):
+        sd[vt + f"pre_layrnorm.{nm}"] = w[f"vision_model.ln_pre.{nm}"]
+    for i in range(vis["num_layers"]):
+        a, b = f"{vt}encoder.layers.{i}.", f"vision_model.decoder.layers.{i}."
+        for nm in ("weight", "bias"):
+            fused = w[b + f"self_attention.linear_qkv.{nm}"]
+            q, k, v = qkv_to_separate(fused.unsqueeze(-1) if nm == "bias" else fused, nh, nh, hn)
+            for p, t in zip("qkv", (q, k, v)):
+                sd[a + f"self_attn.{p}_proj.{nm}"] = t.squeeze(-1) if nm == "bias" else t
+            for core, hf in _LLAVA_VIT:
+                sd[a + f"{hf}.{nm}"] = w[b + f"{core}.{nm}"]
+    for j, name in ((1, "linear_fc1"), (2, "linear_fc2")):
+        for nm in ("weight", "bias"):
+            sd[f"model.multi_modal_projector.linear_{j}.{nm}"] = w[f"vision_projection.encoder.{name}.{nm}"]
+    hc = {"architectures": ["LlavaForConditionalGeneration"], "model_type": "llava", "text_config": tc,
+          "vision_config": {"model_type": "clip_vision_model", "hidden_size": h, "num_hidden_layers": vis["num_layers"],
+                            "num_attention_heads": nh, "intermediate_size": vis["ffn_hidden_size"], "patch_size": vis["patch_dim"],
+                            "image_size": vis["img_h"]},
+          "image_token_index": cfg.get("image_token_index", -200), "projector_hidden_act": "gelu"}
+    _write_hf(sd, hc, save_dir)
+
+
 # ------------------------------------------------------------------------------------ HF: GPT-2
 def load_hf_gpt2(load_dir: str) -> Dict:
     """HF GPT-2 (Conv1D weights are [in, out]; fused c_attn is [q | k | v] by columns)."""
@@ -405,14 +517,15 @@ def pad_vocab(ckpt: Dict, multiple: int):
                 ckpt["config"]["padded_vocab_size"] = v
 
 
-LOADERS = {"core": load_core, "legacy": load_core, "hf_mixtral": load_hf_mixtral, "hf_llama": load_hf_llama, "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2}
+LOADERS = {"core": load_core, "legacy": load_core, "hf_mixtral": load_hf_mixtral, "hf_llama": load_hf_llama,
+           "hf_mistral": load_hf_llama, "hf_gpt2": load_hf_gpt2, "hf_llava": load_hf_llava}
 
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description="checkpoint converter")
     ap.add_argument("--model-type", default="GPT", choices=["GPT"])
     ap.add_argument("--loader", default="core", choices=list(LOADERS))
-    ap.add_argument("--saver", default="core", choices=["core", "legacy", "hf_llama", "hf_mixtral"])
+    ap.add_argument("--saver", default="core", choices=["core", "legacy", "hf_llama", "hf_mixtral", "hf_llava"])
     ap.add_argument("--load-dir", required=True)
     ap.add_argument("--save-dir", required=True)
     ap.add_argument("--target-tensor-parallel-size", type=int, default=1)
@@ -431,6 +544,8 @@ def main(argv=None):
                   legacy=a.saver == "legacy", ep=a.target_expert_parallel_size)
     elif a.saver == "hf_mixtral":
         save_hf_mixtral(ckpt, a.save_dir)
+    elif a.saver == "hf_llava":
+        save_hf_llava(ckpt, a.save_dir)
     else:
         save_hf_llama(ckpt, a.save_dir)
     print(f"converted {a.loader} -> {a.saver}: {len(ckpt['weights'])} tensors, "
