@@ -585,8 +585,6 @@ _UNSUPPORTED = (
     (lambda a: a.external_cuda_graph, "--external-cuda-graph is not implemented; use --enable-cuda-graph"),
     (lambda a: a.pipeline_model_parallel_comm_backend == "ucc", "the UCC pipeline backend is not available; p2p runs on NCCL/gloo channels"),
     (lambda a: a.non_persistent_local_ckpt_dir is not None, "local non-persistent checkpoints are not implemented"),
-    (lambda a: a.vision_backbone_type != "vit", "only the ViT vision backbone is implemented (no MiT / Swin)"),
-    (lambda a: a.vision_pretraining_type != "classify", "only classification vision pre-training is implemented (no inpainting / DINO)"),
     (lambda a: a.encoder_tensor_model_parallel_size not in (0, a.tensor_model_parallel_size),
      "a different tensor-parallel size for the encoder (--encoder-tensor-model-parallel-size) is not implemented"),
     (lambda a: a.optimizer_cpu_offload and not (0.0 < a.optimizer_offload_fraction <= 1.0),

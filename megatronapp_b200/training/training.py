@@ -260,6 +260,10 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
     timers("optimizer").stop()
     update_successful = logical_and_across_model_parallel_group(update_successful)
     grad_norm = reduce_max_stat_across_model_parallel_group(grad_norm)
+    if update_successful and getattr(args, "vision_pretraining", False) and args.vision_pretraining_type == "dino":
+        from .utils import unwrap_model
+
+        unwrap_model(model[0]).update_momentum(args.curr_iteration)     # EMA teacher (reference training.py train_step)
     if update_successful:
         increment = get_num_microbatches() * args.micro_batch_size * args.effective_data_parallel_size
         opt_param_scheduler.step(increment=increment)
@@ -508,6 +512,7 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             args.consumed_train_samples += get_current_global_batch_size()
             tracer.iteration_end()
             continue
+        args.curr_iteration = iteration
         _maybe_simulate_fault(args, iteration)
         if getattr(args, '_fault_deadline', None) and time.time() > args._fault_deadline:
             while True:

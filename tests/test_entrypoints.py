@@ -42,6 +42,16 @@ CASES = {
                   "--max-img-h", "28", "--max-img-w", "28"],
     "retro": ["pretrain_retro.py", "--retro-chunk-length", "8", "--retro-retrieved-length", "12"],
     "vision_classify": ["pretrain_vision_classify.py", "--img-h", "16", "--img-w", "16", "--patch-dim", "4", "--num-classes", "5"],
+    "vision_dino": ["pretrain_vision_dino.py", "--img-h", "16", "--img-w", "16", "--patch-dim", "4", "--num-classes", "5",
+                    "--dino-local-img-size", "8", "--dino-local-crops-number", "2", "--dino-out-dim", "64",
+                    "--dino-head-hidden-size", "32", "--dino-bottleneck-size", "16", "--iter-per-epoch", "2"],
+    "vision_dino_swin": ["pretrain_vision_dino.py", "--img-h", "224", "--img-w", "224", "--num-classes", "5",
+                         "--vision-backbone-type", "swin", "--dino-local-img-size", "224", "--dino-local-crops-number", "0",
+                         "--dino-out-dim", "64", "--dino-head-hidden-size", "32", "--dino-bottleneck-size", "16",
+                         "--micro-batch-size", "1", "--global-batch-size", "1"],
+    "vision_inpaint": ["pretrain_vision_inpaint.py", "--img-h", "16", "--img-w", "16", "--patch-dim", "4"],
+    "vision_inpaint_mit": ["pretrain_vision_inpaint.py", "--img-h", "32", "--img-w", "32", "--patch-dim", "4",
+                           "--vision-backbone-type", "mit", "--mask-type", "row"],
     "ict": ["pretrain_ict.py", "--retriever-report-topk-accuracies", "1", "2", "--retriever-score-scaling",
             "--biencoder-projection-dim", "16"],
 }
