@@ -379,3 +379,38 @@ def test_t5_trains_on_a_preprocessed_sentence_corpus(tmp_path):
     out = p.stdout + p.stderr
     assert p.returncode == 0, out[-3000:]
     assert re.search(r"iteration\s+3/\s+3 \|.*lm loss: [0-9.E+\-]+", out) and "validation loss at the end of training" in out
+
+
+@pytest.mark.parametrize("family", ["gpt", "bert"])
+def test_shipped_sample_corpus_preprocesses_and_trains(tmp_path, family):
+    """The in-tree sample corpora (``datasets_gpt/``: jsonl + byte-level BPE vocab / merges; ``datasets_bert/``: pre-split
+    sentences + WordPiece vocab -- generated by ``tools/make_sample_corpus.py``) go through ``tools/preprocess_data.py`` and
+    then train, like the reference README's quick-start on its own ``datasets_*`` folders."""
+    import json
+
+    if family == "gpt":
+        tok = ["--tokenizer-type", "GPT2BPETokenizer", "--vocab-file", os.path.join(ROOT, "datasets_gpt", "vocab.json"),
+               "--merge-file", os.path.join(ROOT, "datasets_gpt", "merges.txt")]
+        src, extra, prefix, script = os.path.join(ROOT, "datasets_gpt", "dataset.json"), ["--append-eod"], "c_text_document", "pretrain_gpt.py"
+    else:
+        tok = ["--tokenizer-type", "BertWordPieceLowerCase", "--vocab-file", os.path.join(ROOT, "datasets_bert", "vocab.txt")]
+        src, extra, prefix, script = os.path.join(ROOT, "datasets_bert", "dataset_ss.json"), ["--split-sentences"], "c_text_sentence", "pretrain_bert.py"
+    small = tmp_path / "c.jsonl"
+    with open(src) as f, open(small, "w") as g:                     # the first 150 documents keep the CPU test short
+        for _, line in zip(range(150), f):
+            d = json.loads(line)
+            g.write(json.dumps({"text": " ".join(d["text"]) if isinstance(d["text"], list) else d["text"]}) + "\n")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "preprocess_data.py"), "--input", str(small),
+                        "--output-prefix", str(tmp_path / "c"), "--workers", "1", *extra, *tok],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_port()), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    common = [a for a in COMMON if a != "--mock-data"]
+    i = common.index("--vocab-size")
+    common = common[:i] + common[i + 2:]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, script), *common, *tok, "--data-path", str(tmp_path / prefix),
+                        "--split", "90,5,5"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    assert re.search(r"iteration\s+3/\s+3 \|.*lm loss: [0-9.E+\-]+", out) and "validation loss at the end of training" in out
