@@ -139,9 +139,10 @@ class TPFusedComm:
         # kernel, no serialised reduce tail).  On by default; B200_FUSED_RS=0 / bench.py --no-fused-rs falls back to
         # tcgen05 GEMM + NCCL reduce-scatter (the in-tree baseline).
         self.use_fused_rs = os.environ.get("B200_FUSED_RS", "1") == "1"
-        # column-parallel wgrad with the activation re-gather fused along its reduction axis (B200_FUSED_AG_WGRAD=0: NCCL
-        # all-gather overlapped with the dgrad kernel + plain wgrad GEMM)
-        self.use_fused_ag_wgrad = os.environ.get("B200_FUSED_AG_WGRAD", "1") == "1"
+        # column-parallel wgrad with the activation re-gather fused along its reduction axis.  Opt-in (B200_FUSED_AG_WGRAD=1):
+        # measured at TP4 (profiles/r2_fused_comm_4gpu_agwgrad.json) it is exact but 0.42 ms vs 0.31 ms for the NCCL
+        # all-gather overlapped with the dgrad kernel + plain wgrad GEMM, and the 6.7B step is 4 % slower with it.
+        self.use_fused_ag_wgrad = os.environ.get("B200_FUSED_AG_WGRAD", "0") == "1"
         # 0 = auto (cta_group::2 kernel when the shape allows), 128 / 256 = force the 1-CTA kernel (A/B measurements)
         self.block_n = int(os.environ.get("B200_FUSED_BLOCK_N", "0"))
         self.calls = {"ag": 0, "rs": 0}

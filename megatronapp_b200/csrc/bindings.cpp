@@ -1,5 +1,7 @@
 // PyTorch bindings for the sm_100a kernels (pybind11 module megatronapp_b200._C).
 #include <torch/extension.h>
+#include <mutex>
+#include <vector>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
@@ -842,6 +844,84 @@ void reset_launch_count() { g_launches.store(0); }
 
 }  // namespace
 
+// ---- MegaScan native event pool ------------------------------------------------------------------------------------------
+// The tracer's hot path is two event records per scope.  Events live in a process-wide pool addressed by index, so Python
+// holds plain ints; resolving a whole iteration (thousands of cudaEventElapsedTime calls) runs with the GIL released.
+namespace {
+struct TraceEventPool {
+  std::vector<cudaEvent_t> evs;
+  std::vector<int64_t> free_;
+  std::mutex mu;
+};
+TraceEventPool& trace_pool() {
+  static TraceEventPool p;
+  return p;
+}
+}  // namespace
+
+static int64_t trace_tick() {
+  auto& p = trace_pool();
+  int64_t idx;
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> g(p.mu);
+    if (p.free_.empty()) {
+      cudaEvent_t e;
+      C10_CUDA_CHECK(cudaEventCreate(&e));
+      p.evs.push_back(e);
+      idx = (int64_t)p.evs.size() - 1;
+    } else {
+      idx = p.free_.back();
+      p.free_.pop_back();
+    }
+    ev = p.evs[idx];
+  }
+  C10_CUDA_CHECK(cudaEventRecord(ev, at::cuda::getCurrentCUDAStream()));
+  return idx;
+}
+
+static void trace_wait(int64_t idx) {
+  cudaEvent_t ev;
+  {
+    auto& p = trace_pool();
+    std::lock_guard<std::mutex> g(p.mu);
+    ev = p.evs.at(idx);
+  }
+  py::gil_scoped_release nogil;
+  C10_CUDA_CHECK(cudaEventSynchronize(ev));
+}
+
+// ns offsets of `idx[i]` from `base`; every event in `idx` (and `base` when `recycle_base`) returns to the pool
+static std::vector<int64_t> trace_resolve(int64_t base, const std::vector<int64_t>& idx, bool recycle_base) {
+  auto& p = trace_pool();
+  std::vector<cudaEvent_t> evs(idx.size());
+  cudaEvent_t b;
+  {
+    std::lock_guard<std::mutex> g(p.mu);
+    b = p.evs.at(base);
+    for (size_t i = 0; i < idx.size(); ++i) evs[i] = p.evs.at(idx[i]);
+  }
+  std::vector<int64_t> out(idx.size());
+  {
+    py::gil_scoped_release nogil;
+    for (size_t i = 0; i < idx.size(); ++i) {
+      float ms = 0.f;
+      C10_CUDA_CHECK(cudaEventElapsedTime(&ms, b, evs[i]));
+      out[i] = (int64_t)((double)ms * 1e6);
+    }
+    std::lock_guard<std::mutex> g(p.mu);
+    for (auto i : idx) p.free_.push_back(i);
+    if (recycle_base) p.free_.push_back(base);
+  }
+  return out;
+}
+
+static int64_t trace_pool_size() {
+  auto& p = trace_pool();
+  std::lock_guard<std::mutex> g(p.mu);
+  return (int64_t)p.evs.size();
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm);
   m.def("gemm_fp8", &gemm_fp8);
@@ -909,6 +989,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mailbox_slot_tensor", &mailbox_slot_tensor);
   m.def("mailbox_sent", &mailbox_sent);
   m.def("mailbox_destroy", &mailbox_destroy);
+  m.def("trace_tick", &trace_tick);
+  m.def("trace_wait", &trace_wait);
+  m.def("trace_resolve", &trace_resolve);
+  m.def("trace_pool_size", &trace_pool_size);
   m.def("launch_count", &launch_count);
   m.def("reset_launch_count", &reset_launch_count);
 }

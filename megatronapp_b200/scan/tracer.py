@@ -6,9 +6,12 @@ path); on CPU (gloo plumbing runs) it is ``time.perf_counter_ns``.  ``iteration_
 synchronise the device: it records the end event and hands the iteration's scope tree to a resolver
 thread, which waits on that event (a host-side wait, the GPU keeps running the next step), converts
 event pairs to nanosecond offsets from the iteration-begin event and recycles the events through a pool
-(no ``cudaEventCreate`` on the hot path after the first traced iteration).  Records are tagged with dp/pp/tp rank, device and global rank, gathered
-to rank 0 with ``gather_object`` and streamed to disk by a background thread as JSON-lines
-(finalised to one JSON array per rank-tuple file on shutdown).
+(no ``cudaEventCreate`` on the hot path after the first traced iteration).  With the in-tree extension the events live in a
+native pool (``_C.trace_tick`` -> an int; one ``_C.trace_resolve`` call per iteration converts them all with the GIL
+released).  Records are tagged with dp/pp/tp rank, device and global rank and streamed to disk *by the rank that produced
+them* (background thread, JSON-lines, finalised to one JSON array per rank-tuple file on shutdown): on one NVSwitch node
+every rank sees the same trace directory, so nothing is gathered on the training path; ranks on other nodes hand their
+files to rank 0 once, at shutdown.
 
 Capability parity: reference ``megatron/training/trace.py`` (``Tracer`` :242, ``_TracerScope``
 :196, windows :594-614, granularity :75-100, file name :544, bandwidth :371-380).
@@ -94,6 +97,8 @@ class Tracer:
         self._free: List[Any] = []            # recycled CUDA events (list.append / list.pop are atomic)
         self._ship_at: Optional[int] = None
         self._device = None
+        self._native = None                   # _C module when its event pool is usable
+        self._switch_interval: Optional[float] = None
 
     # -- configuration -----------------------------------------------------------
     def configure(self, enabled: bool, trace_dir: str = "trace", interval: int = 1,
@@ -104,6 +109,26 @@ class Tracer:
         self.continuous = max(1, continuous_iterations)
         self.granularity = granularity
         self._use_cuda = torch.cuda.is_available()
+        self._native = None
+        if self._use_cuda and enabled:
+            try:
+                from .. import _C
+
+                self._native = _C if hasattr(_C, "trace_tick") else None
+            except ImportError:
+                self._native = None
+        if enabled and self._switch_interval is None:
+            # the resolver / writer threads are pure Python: a short GIL switch interval keeps the launching thread from
+            # waiting the default 5 ms behind them
+            import sys
+
+            self._switch_interval = sys.getswitchinterval()
+            sys.setswitchinterval(min(self._switch_interval, 2e-4))
+        elif not enabled and self._switch_interval is not None:
+            import sys
+
+            sys.setswitchinterval(self._switch_interval)
+            self._switch_interval = None
 
     def _ranks(self) -> Dict[str, int]:
         if not self._rank_info:
@@ -120,6 +145,8 @@ class Tracer:
 
     # -- hot path ----------------------------------------------------------------
     def _tick(self):
+        if self._native is not None:
+            return self._native.trace_tick()
         if self._use_cuda:
             try:
                 ev = self._free.pop()
@@ -203,7 +230,8 @@ class Tracer:
             job = self._rq.get()
             try:
                 if job is not None:
-                    job["end"].synchronize()          # host-side wait; the training stream is not stalled
+                    # host-side wait; the training stream is not stalled
+                    self._native.trace_wait(job["end"]) if self._native is not None else job["end"].synchronize()
                     self._resolve(job)
             finally:
                 self._rq.task_done()
@@ -218,7 +246,24 @@ class Tracer:
     def _resolve(self, job) -> None:
         begin, end, info = job["begin"], job["end"], job["info"]
         wall_end = time.time_ns()
-        rel = (lambda t: int(begin.elapsed_time(t) * 1e6)) if self._use_cuda else (lambda t: int(t - begin))
+        if self._native is not None:
+            # one GIL-free call turns every event of the iteration into a nanosecond offset (and recycles the events)
+            idx: List[int] = [end]
+            stack = list(job["pending"])
+            while stack:
+                sc = stack.pop()
+                if sc.e is None:
+                    continue
+                idx.append(sc.b)
+                if sc.e != sc.b:
+                    idx.append(sc.e)
+                stack.extend(sc.children)
+            table = dict(zip(idx, self._native.trace_resolve(begin, idx, True)))
+            rel = table.__getitem__
+        elif self._use_cuda:
+            rel = lambda t: int(begin.elapsed_time(t) * 1e6)  # noqa: E731
+        else:
+            rel = lambda t: int(t - begin)  # noqa: E731
         recs = [{"name": "iteration", "ph": "B", "rel_ts": 0, "iteration": job["iteration"],
                  "pad_before": job["pad_before"], "unix_ns": job["wall_begin"], **info}]
         used: List[Any] = [begin, end]
@@ -228,7 +273,7 @@ class Tracer:
         recs.append({"name": "iteration", "ph": "E", "rel_ts": dur, "iteration": job["iteration"],
                      "duration_wall": wall_end - job["wall_begin"], "duration_cuda": dur, **info})
         self._records.extend(recs)
-        if self._use_cuda:
+        if self._use_cuda and self._native is None:
             self._free.extend(used)
 
     def _emit(self, s: _Scope, out: List[dict], info: Dict[str, int], rel, used: List[Any]) -> None:
@@ -265,20 +310,12 @@ class Tracer:
         return f"benchmark-data-{info['dp_rk']}-pipeline-{info['pp_rk']}-tensor-{info['tp_rk']}.json"
 
     def log(self) -> None:
-        """Ship this window's records to rank 0 and hand them to the writer thread."""
+        """Hand this window's records to the local writer thread (no collective: see the module docstring)."""
         self._drain()
         recs, self._records = self._records, []
-        if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            gathered = [None] * torch.distributed.get_world_size() if torch.distributed.get_rank() == 0 else None
-            torch.distributed.gather_object(recs, gathered, dst=0)
-            if torch.distributed.get_rank() != 0:
-                return
-        else:
-            gathered = [recs]
-        self._ensure_writer()
-        for r in gathered:
-            if r:
-                self._q.put(r)
+        if recs:
+            self._ensure_writer()
+            self._q.put(recs)
 
     def _ensure_writer(self) -> None:
         if self._thread is None:
@@ -327,7 +364,39 @@ class Tracer:
                 with open(final, "w") as f:
                     json.dump(prev + recs, f)
                 os.remove(jl)
-            self._files = {}
+        self._collect_remote_nodes(list(self._files.values()))
+        self._files = {}
+
+    def _collect_remote_nodes(self, mine: List[str]) -> None:
+        """Multi-node jobs: ranks that do not share rank 0's trace directory send their finished files to rank 0.  Runs once,
+        in ``shutdown`` (collective over WORLD when tracing was enabled on every rank), never on the training path."""
+        if not (self.enabled and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+            return
+        import socket
+
+        world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if int(os.environ.get("LOCAL_WORLD_SIZE", world)) >= world:
+            return                                       # one node: every rank already wrote into the shared directory
+        hosts = [None] * world
+        try:
+            torch.distributed.all_gather_object(hosts, socket.gethostname())
+        except Exception:
+            return
+        if len(set(hosts)) == 1:
+            return
+        payload = None
+        if hosts[rank] != hosts[0]:
+            payload = {os.path.basename(f): open(f).read() for f in mine if os.path.exists(f)}
+        got = [None] * world if rank == 0 else None
+        torch.distributed.gather_object(payload, got, dst=0)
+        if rank == 0:
+            os.makedirs(self.trace_dir, exist_ok=True)
+            for files in got:
+                for name, text in (files or {}).items():
+                    path = os.path.join(self.trace_dir, name)
+                    prev = json.load(open(path)) if os.path.exists(path) else []
+                    with open(path, "w") as f:
+                        json.dump(prev + json.loads(text), f)
 
 
 _TRACER = Tracer()
