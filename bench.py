@@ -172,11 +172,13 @@ def run_own(args):
     if args.slow_rank_inject:
         r_, cyc = args.slow_rank_inject.split(":")
         slow = (int(r_), int(cyc))
+        if rank == slow[0]:
+            # MegaScan software slow-rank injector: burns CYCLES SM clocks at two points of every transformer layer, forward
+            # and backward, on this rank only -- what a clock-capped GPU looks like to its tensor-parallel peers
+            ops.set_slow_rank_spin(slow[1])
     _train_step = train_step
 
     def train_step(st, batches, sync_loss=True):            # noqa: F811 - add-on aware wrapper around the public API
-        if slow is not None and rank == slow[0]:
-            ops.ext().spin(slow[1])                         # MegaScan software slow-rank injector (comm.cu spin_kernel)
         if args.fbd:
             from megatronapp_b200.fbd.schedule import sync_forward_weights
             from megatronapp_b200.parallel import state as ps_
@@ -222,22 +224,25 @@ def run_own(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     # ---- MegaScan metrics (BASELINE.json): the same K steps again under the tracer (CUDA-event scopes, per-iteration
-    # flush of the event list, records gathered to rank 0 and written by the background thread) -> trace overhead %;
+    # hand-off to the resolver thread, records written by each rank's background writer) -> trace overhead %;
     # the scope records give the exposed (compute-stream-blocking) communication time per step.
     from megatronapp_b200.scan.tracer import get_tracer
 
     tr = get_tracer()
-    trace_dir = os.path.join(os.environ.get("B200_BENCH_TRACE_DIR", "/tmp"), f"b200_bench_trace_{os.getpid()}")
+    # one directory for the whole job (every rank writes its own file into it): the launcher's pid is common to all ranks
+    trace_dir = os.path.join(os.environ.get("B200_BENCH_TRACE_DIR", "/tmp"),
+                             f"b200_bench_trace_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}")
     tr.configure(True, trace_dir=trace_dir, interval=args.steps, continuous_iterations=args.steps)
     scope_stats = {}
+    kept = []
     orig_log = tr.log
 
-    def _log_and_digest():
+    def _log_and_keep():
         tr._drain()
-        scope_stats.update(_digest_scopes(tr._records))
+        kept.extend(tr._records)       # the bench's own analysis (below, outside the timed region) reads the same records
         orig_log()
 
-    tr.log = _log_and_digest
+    tr.log = _log_and_keep
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
@@ -246,16 +251,33 @@ def run_own(args):
         train_step(state, dev_batches, sync_loss=False)
         tr.iteration_end()
     tr._ship_at = None
-    tr.log()          # drain + gather to rank 0 + hand to the writer thread: all of it inside the timed region
+    tr.log()          # drain the resolver + hand the window to the writer thread: inside the timed region
     g1.record()
     barrier()
     ms_traced = g0.elapsed_time(g1)
+    scope_stats.update(_digest_scopes(kept))
     tr.log = orig_log
     try:
         tr.shutdown()            # flush the writer thread while trace_dir still points at this run's directory
     except Exception:
         pass
     tr.configure(False, trace_dir=trace_dir)
+    detector = None
+    if args.detect:
+        barrier()                  # every rank's file is final
+        if rank == 0:
+            from megatronapp_b200.scan import aggregate as _agg
+
+            ab = os.path.join(trace_dir, "abnormal.txt")
+            _, findings = _agg.aggregate(trace_dir, os.path.join(trace_dir, "aggregated.json"), detect=True, abnormal_file=ab)
+            detector = {"abnormal_txt": open(ab).read().strip() if os.path.exists(ab) else None,
+                        "injected_rank": slow[0] if slow else None, "findings": findings[:4]}
+    if not os.environ.get("B200_BENCH_TRACE_DIR"):
+        barrier()
+        if rank == 0:
+            import shutil
+
+            shutil.rmtree(trace_dir, ignore_errors=True)
     exposed_ms = scope_stats.get("exposed_comm_ns", 0) / 1e6 / max(1, args.steps)
     scope_ms = {k: {"ms": round(v["ns"] / 1e6 / args.steps, 3), "calls": v["calls"] // max(1, args.steps)}
                 for k, v in sorted(scope_stats.get("per_scope", {}).items(), key=lambda kv: -kv[1]["ns"])}
@@ -300,6 +322,10 @@ def run_own(args):
             "tflops_per_gpu": 6.0 * _param_count(L, H, F, vocab, arch, A) * tokens / (ms / 1e3) / 1e12 / args.gpus,
         }
         out["rank0_scope_ms_per_step"] = scope_ms
+        if detector is not None:
+            out["detector"] = detector
+        if slow is not None:
+            out["slow_rank_inject"] = {"rank": slow[0], "cycles_per_injection": slow[1], "injections_per_layer": 4}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -386,6 +412,7 @@ def main():
     ap.add_argument("--fp8", action="store_true", help="fp8 (hybrid e4m3/e5m2) linears")
     ap.add_argument("--fp8-recipe", default="delayed", choices=["delayed", "tensorwise", "mxfp8"])
     ap.add_argument("--slow-rank-inject", default=None, help="RANK:CYCLES software slow-rank injector (MegaScan demo)")
+    ap.add_argument("--detect", action="store_true", help="run the MegaScan detector on the traced steps (rank 0) and report it")
     ap.add_argument("--moe-baseline", action="store_true",
                     help="MoE in-tree baseline: NCCL all-to-all dispatcher + one module per expert (reference algorithm)")
     ap.add_argument("--no-fused-tp-comm", action="store_true", help="NCCL collectives instead of fused AG/RS GEMMs")

@@ -20,7 +20,7 @@ def _tp():
 
 def _group_ranks():
     try:
-        return ps.get_tensor_and_data_parallel_ranks()
+        return ps.get_group_ranks("tp")
     except Exception:
         return None
 

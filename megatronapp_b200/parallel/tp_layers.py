@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from . import state as ps
 from .mappings import (
+    _group_ranks,
     gather_from_sequence_parallel_region,
     _gather_along_first_dim,
     _reduce_scatter_along_first_dim,
@@ -139,7 +140,7 @@ class _ColumnParallelFn(torch.autograd.Function):
             # bias + tanh-GELU ride in the epilogue of the fused kernel too; the pre-activation is kept for backward
             pre = torch.empty(rows_total, weight.shape[0], dtype=x2.dtype, device=x2.device) if act else None
             if _fusable(rows_total, x2, weight):
-                with _scope("ag_gemm", data=x2.numel() * x2.element_size() * (tp - 1)):
+                with _scope("ag_gemm", group=_group_ranks, expect="ag_gemm", data=x2.numel() * x2.element_size() * (tp - 1)):
                     out, _ = _FUSED_COMM.ag_gemm(x2.contiguous(), weight, bias, act=act, out_pre=pre)
                 ctx.fused = True
             else:
@@ -193,7 +194,7 @@ class _ColumnParallelFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if ctx.sp and tp > 1:
                 if ctx.fused and _FUSED_COMM.use_fused_rs and _fusable(dy2.shape[0], dy2, weight):
-                    with _scope("gemm_rs_dgrad", data=dy2.shape[0] * weight.shape[1] * 2):
+                    with _scope("gemm_rs_dgrad", group=_group_ranks, expect="gemm_rs_dgrad", data=dy2.shape[0] * weight.shape[1] * 2):
                         dx = _FUSED_COMM.gemm_rs(dy2, weight, b_mn=True)
                 else:
                     # dgrad reduce-scatter runs on the NCCL stream underneath the wgrad GEMM
@@ -212,7 +213,7 @@ class _ColumnParallelFn(torch.autograd.Function):
         dw = db = None
         if ctx.needs_input_grad[1] and fused_wgrad:
             first = (not getattr(weight, "grad_added_to_main_grad", False)) and getattr(weight, "b200_wgrad_store_first", False)
-            with _scope("ag_wgrad", data=x2.numel() * x2.element_size() * (tp - 1)):
+            with _scope("ag_wgrad", group=_group_ranks, expect="ag_wgrad", data=x2.numel() * x2.element_size() * (tp - 1)):
                 _FUSED_COMM.ag_wgrad(dy2, x2, main_grad, accumulate=not first)
             weight.grad_added_to_main_grad = True
             if getattr(weight, "b200_wgrad_store_first", False):
@@ -384,7 +385,7 @@ class _RowParallelFn(torch.autograd.Function):
         ctx.fused = False
         if sequence_parallel and tp > 1 and do_reduce:
             if _fusable(x2.shape[0], x2, weight) and _FUSED_COMM.use_fused_rs:
-                with _scope("gemm_rs", data=x2.shape[0] * weight.shape[0] * 2):
+                with _scope("gemm_rs", group=_group_ranks, expect="gemm_rs", data=x2.shape[0] * weight.shape[0] * 2):
                     out = _FUSED_COMM.gemm_rs(x2, weight)
                 ctx.fused = True
             elif _fusable(x2.shape[0], x2, weight):
@@ -396,7 +397,7 @@ class _RowParallelFn(torch.autograd.Function):
         else:
             out = ops.gemm(x2, weight)
             if tp > 1 and do_reduce:
-                with _scope("_reduce", data=out.numel() * out.element_size()):
+                with _scope("_reduce", group=_group_ranks, expect="_reduce", data=out.numel() * out.element_size()):
                     dist.all_reduce(out, group=ps.get_tensor_model_parallel_group())
             out_shape = tuple(x.shape[:-1]) + (weight.shape[0],)
         ctx.do_reduce = do_reduce
@@ -413,7 +414,7 @@ class _RowParallelFn(torch.autograd.Function):
         dx = None
         if ctx.sp and tp > 1 and ctx.do_reduce:
             if ctx.fused and _fusable(dy2.shape[0] * tp, dy2, weight):
-                with _scope("ag_gemm_dgrad", data=dy2.numel() * 2 * (tp - 1)):
+                with _scope("ag_gemm_dgrad", group=_group_ranks, expect="ag_gemm_dgrad", data=dy2.numel() * 2 * (tp - 1)):
                     dx, dy_full = _FUSED_COMM.ag_gemm(dy2, weight, None, b_mn=True)
             else:
                 dy_full = _gather_along_first_dim(dy2)

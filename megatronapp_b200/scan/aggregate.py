@@ -169,6 +169,10 @@ def amend_p2p(traces: List[dict]) -> None:
 # slow-rank detection
 # ---------------------------------------------------------------------------
 
+_SYNC_NAMES = {"_reduce", "_gather_along_first_dim", "_reduce_scatter_along_first_dim", "_gather_along_last_dim",
+               "_reduce_scatter_along_last_dim", "ag_gemm", "gemm_rs", "gemm_rs_dgrad", "ag_gemm_dgrad", "ag_wgrad", "all_to_all"}
+
+
 def _per_rank_durations(traces: List[dict], names) -> Dict[int, Dict[str, List[float]]]:
     out: Dict[int, Dict[str, List[float]]] = collections.defaultdict(lambda: collections.defaultdict(list))
     for e in traces:
@@ -187,7 +191,10 @@ def try_detect(traces: List[dict], out_file: Optional[str] = "abnormal.txt", com
              (``loss`` / ``allreduce``) take < 0.9x, collects a vote per event;
     stage 2  a rank with enough votes is confirmed if, in the collectives it took part in
              (``related_sync_op`` sets of ``_reduce`` & friends), it is the *fast* one
-             (< 0.9x the peers' mean: it arrived last so it waited least) in > 40% of cases.
+             (< 0.9x the peers' mean: it arrived last so it waited least) in > 40% of cases -- or, time-weighted, if
+             its *total* time inside those collectives is < 0.9x the mean total of its peers (a rank that is late only
+             at a few synchronisation points per step still makes every peer wait there: counting events misses it,
+             summing the waits does not).
     """
     meta: Dict[int, Tuple[int, int, int]] = {}
     for e in traces:
@@ -230,14 +237,42 @@ def try_detect(traces: List[dict], out_file: Optional[str] = "abnormal.txt", com
         compare(sorted(g))
     for g in by_dp.values():
         compare(sorted(g))
+    # stage 1b: tensor-parallel peers run in lock step -- their collectives equalise every scope's duration, so a slow GPU
+    # shows up only in *where* the time goes: its scopes hold more compute and less waiting.  Exclusive compute of the k-th
+    # ``forward`` / ``backward`` / ``iteration`` scope = duration - time inside the collectives it contains.
+    sync_ev: Dict[int, List[Tuple[float, float]]] = collections.defaultdict(list)
+    for e in traces:
+        if e.get("ph") == "X" and e["name"] in _SYNC_NAMES and "group" in e.get("args", {}):
+            sync_ev[e["pid"]].append((e["ts"], e["dur"]))
+    excl: Dict[int, Dict[str, List[float]]] = collections.defaultdict(lambda: collections.defaultdict(list))
+    for r, evs in sync_ev.items():
+        evs.sort()
+        starts = np.array([t for t, _ in evs])
+        csum = np.concatenate([[0.0], np.cumsum([d for _, d in evs])])
+        for e in traces:
+            if e.get("ph") == "X" and e["pid"] == r and e["name"] in ("forward", "backward", "iteration"):
+                lo, hi = np.searchsorted(starts, e["ts"]), np.searchsorted(starts, e["ts"] + e["dur"])
+                excl[r][e["name"]].append(e["dur"] - float(csum[hi] - csum[lo]))
+    for g in by_dp.values():
+        g = [r for r in sorted(g) if r in excl]
+        for name in ("forward", "backward", "iteration"):
+            series = {r: excl[r][name] for r in g if excl[r][name]}
+            if len(series) < 2:
+                continue
+            for i in range(min(len(v) for v in series.values())):
+                vals = sorted((v[i], r) for r, v in series.items())
+                rest = float(np.mean([x[0] for x in vals[:-1]]))
+                if rest > 0 and vals[-1][0] > compute_thresh * rest:
+                    votes[vals[-1][1]] += 1
     findings = []
     by_id = {e["args"]["id"]: e for e in traces if "args" in e and "id" in e["args"]}
-    sync_names = {"_reduce", "_gather_along_first_dim", "_reduce_scatter_along_first_dim", "ag_gemm", "gemm_rs"}
+    sync_names = _SYNC_NAMES
     for r, v in votes.most_common():
         logging.info("Suspect: rank %s (%s) %d votes", r, meta.get(r), v)
         if v < min_votes:
             continue
         all_cnt = fast_cnt = 0
+        own_total = peer_total = 0.0
         for e in traces:
             if e.get("ph") != "X" or e["pid"] != r or e["name"] not in sync_names:
                 continue
@@ -248,10 +283,14 @@ def try_detect(traces: List[dict], out_file: Optional[str] = "abnormal.txt", com
             if not peers:
                 continue
             all_cnt += 1
-            if e["dur"] < wait_thresh * np.mean([p["dur"] for p in peers]):
+            peer_mean = float(np.mean([p["dur"] for p in peers]))
+            own_total += e["dur"]
+            peer_total += peer_mean
+            if e["dur"] < wait_thresh * peer_mean:
                 fast_cnt += 1
-        confirmed = all_cnt == 0 or fast_cnt > sync_frac * all_cnt
+        confirmed = all_cnt == 0 or fast_cnt > sync_frac * all_cnt or own_total < wait_thresh * peer_total
         findings.append({"g_rk": r, "rank": meta.get(r), "votes": v, "sync_all": all_cnt, "sync_fast": fast_cnt,
+                         "sync_time_ratio": round(own_total / peer_total, 4) if peer_total else None,
                          "confirmed": bool(confirmed)})
     confirmed = [f for f in findings if f["confirmed"]]
     if confirmed and out_file:

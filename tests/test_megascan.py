@@ -65,6 +65,45 @@ def test_healthy_run_reports_nothing(tmp_path):
     assert not ab.exists() and not [f for f in findings if f["confirmed"]]
 
 
+def _lockstep_tp_rank(tp, slow_rank, n_tp=4, iters=3, layers=6):
+    """A TP group in lock step: every layer = compute + one collective; the slow rank computes 30 % longer and the others
+    spend exactly that extra time waiting inside the collective -> identical ``forward`` durations on every rank."""
+    info = {"dp_rk": 0, "pp_rk": 0, "tp_rk": tp, "g_rk": tp, "dev": tp}
+    recs = []
+    for it in range(iters):
+        t = 0
+        recs.append({"name": "iteration", "ph": "B", "rel_ts": 0, "iteration": it, "pad_before": 0, **info})
+        for name in ("forward", "backward"):
+            recs.append({"name": name, "ph": "B", "rel_ts": t, **info})
+            for _ in range(layers):
+                comp = 1_300_000 if tp == slow_rank else 1_000_000
+                t += comp
+                recs.append({"name": "gemm_rs", "ph": "B", "rel_ts": t, "group": list(range(n_tp)), "expect": "gemm_rs", **info})
+                t += 200_000 + (1_300_000 - comp)              # transfer + waiting for the slow peer
+                recs.append({"name": "gemm_rs", "ph": "E", "rel_ts": t, **info})
+            recs.append({"name": name, "ph": "E", "rel_ts": t, **info})
+        recs.append({"name": "iteration", "ph": "E", "rel_ts": t, "iteration": it, "duration_wall": t, "duration_cuda": t, **info})
+    return recs
+
+
+def test_detects_slow_rank_inside_a_lockstep_tensor_parallel_group(tmp_path):
+    d = tmp_path / "bench"
+    d.mkdir()
+    for tp in range(4):
+        (d / f"benchmark-data-0-pipeline-0-tensor-{tp}.json").write_text(json.dumps(_lockstep_tp_rank(tp, slow_rank=1)))
+    ab = tmp_path / "abnormal.txt"
+    _, findings = agg.aggregate(str(d), str(tmp_path / "o.json"), detect=True, abnormal_file=str(ab))
+    assert ab.read_text().strip() == "1 0-0-1"
+    f = findings[0]
+    assert f["g_rk"] == 1 and f["confirmed"] and f["sync_all"] > 0 and f["sync_time_ratio"] < 0.5
+    # and a healthy lock-step group reports nothing
+    for tp in range(4):
+        (d / f"benchmark-data-0-pipeline-0-tensor-{tp}.json").write_text(json.dumps(_lockstep_tp_rank(tp, slow_rank=-1)))
+    ab.unlink()
+    _, findings = agg.aggregate(str(d), str(tmp_path / "o.json"), detect=True, abnormal_file=str(ab))
+    assert not ab.exists() and not [x for x in findings if x["confirmed"]]
+
+
 def test_amend_p2p():
     tr = [{"name": "send-forward", "ph": "X", "ts": 0.0, "dur": 100.0, "pid": 0, "args": {"peer": 1, "data": 1000, "id": 0}},
           {"name": "recv-forward", "ph": "X", "ts": 60.0, "dur": 45.0, "pid": 1, "args": {"peer": 0, "data": 1000, "id": 1}}]
