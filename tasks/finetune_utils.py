@@ -87,7 +87,8 @@ def clip_grad_norm_model_parallel(params, max_norm: float) -> float:
 def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: int = 16, lr: float = 2e-5,
              weight_decay: float = 0.01, warmup_fraction: float = 0.1, clip_grad: float = 1.0,
              forward_step: Callable = classification_forward_step, end_of_epoch_callback: Optional[Callable] = None,
-             log_interval: int = 50, sampler_seed: int = 1234, evaluate: Optional[Callable] = None):
+             log_interval: int = 50, sampler_seed: int = 1234, evaluate: Optional[Callable] = None,
+             collate_fn: Optional[Callable] = None, eval_batch_size: Optional[int] = None):
     """Single-replica (or DDP-sharded through the sampler) finetuning loop; returns per-epoch metrics."""
     import torch.distributed as dist
 
@@ -96,8 +97,8 @@ def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: i
     dp_rank = ps.get_data_parallel_rank() if ps.model_parallel_is_initialized() else 0
     dp_size = ps.get_data_parallel_world_size() if ps.model_parallel_is_initialized() else 1
     sampler = torch.utils.data.distributed.DistributedSampler(train_dataset, dp_size, dp_rank, shuffle=True, seed=sampler_seed)
-    loader = torch.utils.data.DataLoader(train_dataset, batch_size=batch_size, sampler=sampler, drop_last=True)
-    vloader = torch.utils.data.DataLoader(valid_dataset, batch_size=batch_size, shuffle=False)
+    loader = torch.utils.data.DataLoader(train_dataset, batch_size=batch_size, sampler=sampler, drop_last=True, collate_fn=collate_fn)
+    vloader = torch.utils.data.DataLoader(valid_dataset, batch_size=eval_batch_size or batch_size, shuffle=False, collate_fn=collate_fn)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay)
     total_steps = max(1, epochs * len(loader))

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def get_tasks_args(parser):
     g = parser.add_argument_group("tasks")
     g.add_argument("--task", type=str, required=True,
-                   help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE | RETRIEVER-EVAL | VISION-CLASSIFY (MSDP-*: tasks/msdp/main.py)")
+                   help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE | RETRIEVER-EVAL | RET-FINETUNE-NQ | VISION-CLASSIFY (MSDP-*: tasks/msdp/main.py)")
     g.add_argument("--qa-data-test", type=str, default=None, help="NQ-open style TSV: question \\t [answers]")
     g.add_argument("--faiss-match", type=str, default="string", choices=["regex", "string"])
     g.add_argument("--faiss-topk-retrievals", type=int, default=100)
@@ -19,6 +19,12 @@ def get_tasks_args(parser):
     g.add_argument("--overlapping-eval", type=int, default=32, help="sliding window stride for perplexity")
     g.add_argument("--strict-lambada", action="store_true", help="whole-word LAMBADA (all word pieces must match)")
     g.add_argument("--eval-micro-batch-size", type=int, default=None)
+    # supervised retriever fine-tuning (RET-FINETUNE-NQ)
+    g.add_argument("--train-with-neg", action="store_true", help="add hard negatives to the in-batch negatives")
+    g.add_argument("--train-hard-neg", type=int, default=0, help="hard negatives per question")
+    g.add_argument("--val-av-rank-hard-neg", type=int, default=30)
+    g.add_argument("--val-av-rank-other-neg", type=int, default=30)
+    g.add_argument("--sample-rate", type=float, default=1.0)
     return parser
 
 
@@ -36,6 +42,8 @@ if __name__ == "__main__":
         from tasks.race.finetune import main
     elif args.task == "VISION-CLASSIFY":
         from tasks.vision.classification import main
+    elif args.task == "RET-FINETUNE-NQ":
+        from tasks.orqa.supervised import main
     elif args.task == "RETRIEVER-EVAL":
         def main():
             from megatronapp_b200.training import checkpointing

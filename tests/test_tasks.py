@@ -252,6 +252,60 @@ def test_orqa_evaluator_retrieves_with_biencoder():
     assert acc[1] == 50.0 and acc[3] == 50.0
 
 
+def test_supervised_retriever_finetune_on_dpr_json_learns_and_ranks(tmp_path):
+    """RET-FINETUNE-NQ: DPR-format json -> bi-encoder training with hard negatives -> average-rank / top-k validation."""
+    import random
+
+    from functools import partial
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.legacy.model.biencoder_model import BiEncoderModel
+    from megatronapp_b200.parallel import state as ps
+    from tasks.finetune_utils import finetune
+    from tasks.orqa.supervised import NQSupervisedDataset, retrieval_forward_step, retrieval_metrics, task_collate_fn
+
+    if not ps.model_parallel_is_initialized():
+        ps.init_distributed("gloo")
+        ps.initialize_model_parallel(1, 1)
+
+    class Tok:
+        cls, sep, pad = 1, 2, 0
+
+        def __init__(self):
+            self.v = {}
+
+        def tokenize(self, t):
+            return [self.v.setdefault(w, 3 + len(self.v)) for w in t.lower().split()]
+
+    random.seed(0)
+    topics = ["zebra", "quartz", "lemon", "violin", "harbor", "comet", "saddle", "walnut", "ember", "glacier", "orchid", "anvil"]
+    rows = []
+    for i, w in enumerate(topics):
+        others = [t for t in topics if t != w]
+        rows.append({"question": f"what is known about {w} ?", "answers": [w],
+                     "positive_ctxs": [{"title": w, "text": f"the {w} entry describes {w} in detail"}],
+                     "hard_negative_ctxs": [{"title": o, "text": f"the {o} entry describes {o} in detail"} for o in others[:3]],
+                     "negative_ctxs": [{"title": o, "text": f"unrelated note on {o}"} for o in others[3:6]]})
+    path = tmp_path / "nq.json"
+    path.write_text(json.dumps(rows))
+    tok = Tok()
+    train = NQSupervisedDataset("training", [str(path)], tok, 16, train_with_neg=True, train_hard_neg=2)
+    valid = NQSupervisedDataset("validation", [str(path)], tok, 16, evaluate=True, val_av_rank_hard_neg=3, val_av_rank_other_neg=3)
+    s0 = train[0]
+    assert s0["query"][0] == 1 and len(s0["neg"]) == 2 and len(valid[0]["neg"]) == 6
+    assert "?" not in tok.v                                              # the trailing question mark is stripped
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, kernel_backend="torch", params_dtype=torch.float32)
+    m = BiEncoderModel(cfg, 128, 16, biencoder_shared_query_context_model=True)
+    loader = torch.utils.data.DataLoader(valid, batch_size=4, collate_fn=task_collate_fn)
+    before = retrieval_metrics(m, loader, topk=(1, 3))
+    hist = finetune(m, train, valid, epochs=40, batch_size=4, lr=3e-3, log_interval=0, clip_grad=0.0, collate_fn=task_collate_fn,
+                    forward_step=partial(retrieval_forward_step, train_with_neg=True), evaluate=partial(retrieval_metrics, topk=(1, 3)))
+    after = hist[-1]
+    assert after["total"] == 12 and after["rank"] < before["rank"] and after["top3_acc"] >= 90.0 > before["top3_acc"], (before, after)
+
+
 def test_vision_classification_finetune_learns_from_an_image_folder(tmp_path):
     import numpy as np
 
