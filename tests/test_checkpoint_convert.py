@@ -360,3 +360,129 @@ def test_hf_llava_roundtrip_and_loads_into_the_core_model(tmp_path):
     back = torch.load(dst / "pytorch_model.bin")
     assert set(back) == set(sd)
     assert all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def _trt_cfg(c, **kw):
+    from types import SimpleNamespace
+
+    base = dict(num_layers=c["num_layers"], hidden_size=c["hidden_size"], num_attention_heads=c["num_attention_heads"],
+                num_query_groups=c["num_query_groups"], kv_channels=c["kv_channels"], ffn_hidden_size=c["ffn_hidden_size"],
+                gated_linear_unit=True, layernorm_epsilon=1e-5, add_bias_linear=False, num_moe_experts=None, moe_router_topk=2,
+                layernorm_zero_centered_gamma=False, normalization="RMSNorm")
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def _megatron_tp_shard(sd, tp, r):
+    """this framework's tensor-parallel layout of a canonical state dict (what a training rank holds)"""
+    out = {}
+    for k, w in sd.items():
+        if k.endswith("linear_qkv.weight") or k.endswith("word_embeddings.weight") or k.endswith("output_layer.weight"):
+            out[k] = torch.chunk(w, tp, 0)[r].clone()
+        elif k.endswith("linear_fc1.weight"):
+            gate, up = torch.chunk(w, 2, 0)
+            out[k] = torch.cat([torch.chunk(gate, tp, 0)[r], torch.chunk(up, tp, 0)[r]], 0)
+        elif k.endswith(("linear_proj.weight", "linear_fc2.weight")):
+            out[k] = torch.chunk(w, tp, 1)[r].clone()
+        else:
+            out[k] = w
+    return out
+
+
+def test_trtllm_on_device_distributed_conversion_matches_single_device_export(tmp_path):
+    """Every (tp, pp) training rank converts only its own shard; the result equals the slice the single-device exporter
+    produces for that rank (global layer numbering, vocabulary padding removed, head re-split)."""
+    from megatronapp_b200.export import DistributedTRTLLMConverter, ExportConfig, TRTLLMHelper
+
+    _, d = _tiny_hf_llama(str(tmp_path))
+    ck = conv.load_hf_llama(d)
+    sd = {k: v.float() for k, v in ck["weights"].items()}
+    h = TRTLLMHelper(_trt_cfg(ck["config"]), model_type="llama", activation="silu")
+    tok_vocab = 250                                                 # the table is padded to 256
+    ref_w, ref_c = h.get_trtllm_pretrained_config_and_model_weights(sd, "float32", ExportConfig(2, 2), vocab_size=tok_vocab)
+    assert len(ref_w) == 4 and [c["mapping"]["rank"] for c in ref_c] == [0, 1, 2, 3]
+    assert "transformer.vocab_embedding.weight" in ref_w[0] and "lm_head.weight" not in ref_w[0] and "lm_head.weight" in ref_w[3]
+    assert ref_w[0]["transformer.vocab_embedding.weight"].shape[0] == tok_vocab
+    L = ck["config"]["num_layers"]
+    for pr in range(2):
+        for tr in range(2):
+            local = _megatron_tp_shard(sd, 2, tr)
+            lo, hi = pr * L // 2, (pr + 1) * L // 2
+            stage = {}
+            for k, v in local.items():
+                if k.startswith("decoder.layers."):
+                    if lo <= int(k.split(".")[2]) < hi:
+                        stage[k] = v
+                elif k.startswith("embedding.") and pr == 0:
+                    stage[k] = v
+                elif (k.startswith("decoder.final_layernorm") or k.startswith("output_layer")) and pr == 1:
+                    stage[k] = v
+
+            def fake_all_reduce(t, tr=tr):                         # the peer's half of the vocabulary-parallel table
+                other = _megatron_tp_shard(sd, 2, 1 - tr)
+                src = other["embedding.word_embeddings.weight"] if t.shape[0] == sd["embedding.word_embeddings.weight"].shape[0] and pr == 0 \
+                    else other["output_layer.weight"]
+                n = src.shape[0]
+                t[(1 - tr) * n:(2 - tr) * n] += src
+
+            dc = DistributedTRTLLMConverter(h, tp_rank=tr, tp_size=2, pp_rank=pr, pp_size=2, tp_all_reduce=fake_all_reduce)
+            got = dc.convert(stage, torch.float32, tokenizer_vocab_size=tok_vocab)
+            want = ref_w[pr * 2 + tr]
+            assert set(got) == set(want), (pr, tr, set(got) ^ set(want))
+            for k in want:
+                assert torch.equal(got[k], want[k]), (pr, tr, k)
+
+
+def test_trtllm_moe_fp8_and_engine_plan(tmp_path):
+    from megatronapp_b200.export import TRTLLMEngineBuilder, TRTLLMHelper
+
+    torch.manual_seed(0)
+    H, F, E, L = 16, 24, 4, 1
+    cfg = _trt_cfg(dict(num_layers=L, hidden_size=H, num_attention_heads=2, num_query_groups=2, kv_channels=8, ffn_hidden_size=F),
+                   num_moe_experts=E, layernorm_zero_centered_gamma=True, normalization="LayerNorm")
+    sd = {"embedding.word_embeddings.weight": torch.randn(32, H), "decoder.final_layernorm.weight": torch.zeros(H),
+          "decoder.layers.0.input_layernorm.weight": torch.zeros(H), "decoder.layers.0.pre_mlp_layernorm.weight": torch.zeros(H),
+          "decoder.layers.0.self_attention.linear_qkv.weight": torch.randn(3 * H, H),
+          "decoder.layers.0.self_attention.linear_proj.weight": torch.randn(H, H),
+          "decoder.layers.0.mlp.router.weight": torch.randn(E, H)}
+    for e in range(E):
+        sd[f"decoder.layers.0.mlp.experts.local_experts.{e}.linear_fc1.weight"] = torch.randn(2 * F, H)
+        sd[f"decoder.layers.0.mlp.experts.local_experts.{e}.linear_fc2.weight"] = torch.randn(H, F)
+    h = TRTLLMHelper(cfg, model_type="mixtral", activation="silu")
+    w = h.convert(sd, torch.float32)
+    assert torch.equal(w["transformer.layers.0.input_layernorm.weight"], torch.ones(H))           # zero-centred gamma + 1
+    fc, proj = w["transformer.layers.0.mlp.fc.weight"], w["transformer.layers.0.mlp.proj.weight"]
+    assert fc.shape == (E, 2 * F, H) and proj.shape == (E, H, F) and w["transformer.layers.0.mlp.router.weight"].dtype == torch.float32
+    gate, up = torch.chunk(sd["decoder.layers.0.mlp.experts.local_experts.2.linear_fc1.weight"], 2, 0)
+    assert torch.equal(fc[2, :F], up) and torch.equal(fc[2, F:], gate)                             # MoE plugin order: [up ; gate]
+    s1 = h.shard(w, 2, 1)
+    assert torch.equal(s1["transformer.layers.0.mlp.fc.weight"][2, :F // 2], up[F // 2:]) and s1["transformer.layers.0.mlp.proj.weight"].shape == (E, H, F // 2)
+    # the grouped-GEMM parameter layout converts to the same tensors
+    g = {k: v for k, v in sd.items() if "local_experts" not in k}
+    g["decoder.layers.0.mlp.experts.weight1"] = torch.stack([sd[f"decoder.layers.0.mlp.experts.local_experts.{e}.linear_fc1.weight"].t() for e in range(E)])
+    g["decoder.layers.0.mlp.experts.weight2"] = torch.stack([sd[f"decoder.layers.0.mlp.experts.local_experts.{e}.linear_fc2.weight"].t() for e in range(E)])
+    wg = h.convert(g, torch.float32)
+    assert torch.equal(wg["transformer.layers.0.mlp.fc.weight"], fc) and torch.equal(wg["transformer.layers.0.mlp.proj.weight"], proj)
+    # fp8: weights quantised with per-tensor scales that reproduce them; config advertises the quant mode
+    ws, cs = h.get_trtllm_pretrained_config_and_model_weights(sd, "bfloat16", fp8_quantized=True, fp8_kvcache=True)
+    q = ws[0]["transformer.layers.0.attention.qkv.weight"]
+    assert q.dtype == torch.float8_e4m3fn and cs[0]["quantization"] == {"quant_algo": "FP8", "kv_cache_quant_algo": "FP8"}
+    deq = q.float() * ws[0]["transformer.layers.0.attention.qkv.weights_scaling_factor"]
+    assert (deq - w["transformer.layers.0.attention.qkv.weight"]).abs().max() < 0.07 * w["transformer.layers.0.attention.qkv.weight"].abs().max()
+    assert ws[0]["transformer.layers.0.attention.kv_cache_scaling_factor"].item() == 1.0
+    # engine plan: token limits follow TRT-LLM's defaulting; the plan is written even though tensorrt_llm is absent
+    conf = cs[0]
+    plan = TRTLLMEngineBuilder.plan(conf, max_input_len=512, max_output_len=256, max_batch_size=8, paged_context_fmha=True, tokens_per_block=64)
+    assert plan.max_seq_len == 768 and plan.max_num_tokens == 8 * 768 and plan.opt_num_tokens == 8 and plan.plugin["tokens_per_block"] == 64
+    assert TRTLLMEngineBuilder.plan(conf, remove_input_padding=False).max_num_tokens is None
+    try:
+        import tensorrt_llm  # noqa: F401
+    except ImportError:
+        import json
+
+        import pytest
+
+        with pytest.raises(RuntimeError, match="build_config.json"):
+            h.build_and_save_engine(str(tmp_path / "engine"), ws[0], conf, max_batch_size=2)
+        saved = json.load(open(tmp_path / "engine" / "build_config.json"))
+        assert saved["build"]["max_batch_size"] == 2 and saved["plugin_config"]["paged_kv_cache"] is True
