@@ -158,7 +158,8 @@ def run_own(args):
                     moe_dispatcher="alltoall" if args.moe_baseline else "flex", moe_aux_loss_coeff=1e-2)
     state = build_gpt_for_bench(L, H, A, S, vocab, mbs, ffn=F, tp=tp, pp=pp, sequence_parallel=tp > 1,
                                 device=f"cuda:{local_rank}", lr=1e-4, fused_tp_comm=not args.no_fused_tp_comm,
-                                use_distributed_optimizer=dp > 1, dropout=0.0, vpp=vpp, fbd=args.fbd,
+                                use_distributed_optimizer=dp > 1, overlap_grad_reduce=(dp > 1 and not args.no_dp_overlap),
+                                fused_grad_rs=(args.fused_grad_rs and dp > 1 and not moe), dropout=0.0, vpp=vpp, fbd=args.fbd,
                                 fp8="hybrid" if args.fp8 else None, fp8_recipe=args.fp8_recipe, **arch)
     if args.fbd:
         from megatronapp_b200.fbd.schedule import install_fbd_schedule
@@ -307,7 +308,9 @@ def run_own(args):
                        "l2_policy": "working set (>=13 GB weights + grads per step) >> 126 MB L2; no explicit flush",
                        "attention_impl": "native" if ops.native_attention_available() else "sdpa-library",
                        "fused_tp_comm": (tp > 1 and not args.no_fused_tp_comm),
-                       "fused_gemm_rs": (tp > 1 and not args.no_fused_tp_comm and not args.no_fused_rs)},
+                       "fused_gemm_rs": (tp > 1 and not args.no_fused_tp_comm and not args.no_fused_rs),
+                       "dp_grad_sync": (None if dp == 1 else ("fused-kernel" if (args.fused_grad_rs and not moe) else "nccl")
+                                        + ("" if args.no_dp_overlap else "+overlap"))},
             "clocks": clocks,
             "e2e": {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -412,6 +415,9 @@ def main():
     ap.add_argument("--fp8", action="store_true", help="fp8 (hybrid e4m3/e5m2) linears")
     ap.add_argument("--fp8-recipe", default="delayed", choices=["delayed", "tensorwise", "mxfp8"])
     ap.add_argument("--slow-rank-inject", default=None, help="RANK:CYCLES software slow-rank injector (MegaScan demo)")
+    ap.add_argument("--no-dp-overlap", action="store_true", help="dp>1: reduce-scatter the gradients after backward instead of per bucket")
+    ap.add_argument("--fused-grad-rs", action="store_true",
+                    help="dp>1: sm_100a bucket reduce-scatter (scale + cast + RS over NVLink peer stores) instead of NCCL")
     ap.add_argument("--detect", action="store_true", help="run the MegaScan detector on the traced steps (rank 0) and report it")
     ap.add_argument("--moe-baseline", action="store_true",
                     help="MoE in-tree baseline: NCCL all-to-all dispatcher + one module per expert (reference algorithm)")

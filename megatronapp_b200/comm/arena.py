@@ -145,13 +145,42 @@ class TPFusedComm:
         self.use_fused_ag_wgrad = os.environ.get("B200_FUSED_AG_WGRAD", "0") == "1"
         # 0 = auto (cta_group::2 kernel when the shape allows), 128 / 256 = force the 1-CTA kernel (A/B measurements)
         self.block_n = int(os.environ.get("B200_FUSED_BLOCK_N", "0"))
-        self.calls = {"ag": 0, "rs": 0}
+        self.calls = {"ag": 0, "rs": 0, "embed": 0}
+        # K14: vocab-parallel embedding lookup fused with the sequence-parallel scatter (B200_FUSED_EMBED=0: F.embedding +
+        # mask + NCCL reduce-scatter)
+        self.use_fused_embed = os.environ.get("B200_FUSED_EMBED", "1") == "1"
+        self.embed_ctas = 32
+        self._embed = None
         ext = ops.ext()
         nflags = max(ext.gemm_flags_needed(max_tokens, max(max_in, max_out), arena.size), 4096)
         self.ag = [arena.region(f"tp_ag{i}", max_tokens * max_in * 2) for i in range(2)]
         self.ag_flags = [arena.region(f"tp_ag_flags{i}", nflags * 4) for i in range(2)]
         self.rs = [arena.region(f"tp_rs{i}", max_tokens * max_out * 2) for i in range(2)]
         self.rs_flags = [arena.region(f"tp_rs_flags{i}", nflags * 4) for i in range(2)]
+
+    def embed_fits(self, n_tokens: int, hidden: int) -> bool:
+        need = n_tokens * hidden * 2 // self.arena.size
+        if self._embed is None:
+            try:
+                self._embed = ([self.arena.region(f"tp_embed{i}", need) for i in range(2)],
+                               [self.arena.region(f"tp_embed_flags{i}", self.arena.size * self.embed_ctas * 4) for i in range(2)])
+            except RuntimeError:
+                self.use_fused_embed = False
+                return False
+        return self._embed[0][0].nbytes >= need
+
+    def embed(self, tokens: torch.Tensor, weight: torch.Tensor, vocab_start: int) -> torch.Tensor:
+        """tokens [b, s] int64, weight [V / tp, h] -> [s / tp, b, h]; rows arrive from their owners over NVLink."""
+        a = self.arena
+        slot = self.calls["embed"] % 2
+        self.calls["embed"] += 1
+        out_reg, flag_reg = self._embed[0][slot], self._embed[1][slot]
+        ep = a.next_epoch(flag_reg)
+        ops.ext().embed_scatter(tokens, weight, a.ptrs(out_reg), a.ptrs(flag_reg), int(vocab_start), a.rank, a.size, ep,
+                                self.embed_ctas)
+        b, s = tokens.shape
+        # the slot is rewritten two calls later: hand autograd its own copy
+        return a.local(out_reg, (s // a.size, b, weight.shape[1]), weight.dtype).clone()
 
     def ag_gemm(self, x_local: torch.Tensor, weight: torch.Tensor, bias=None, b_mn: bool = False,
                 act: int = 0, out: Optional[torch.Tensor] = None,

@@ -243,6 +243,11 @@ struct A2aArgs {  // MoE dispatch: scatter routed rows into expert-owner buffers
   bool is_bf16; int n_ctas;
 };
 void a2a_scatter_rows(const A2aArgs& a, cudaStream_t s);
+struct EmbedArgs {  // K14: vocab-parallel embedding + sequence-parallel scatter
+  const int64_t* tokens; const void* weight; void* peer_out[kMaxPeers]; uint32_t* peer_flags[kMaxPeers];
+  int b; int s; int h; int64_t vocab_start; int64_t vocab_end; int rank; int size; uint32_t epoch; int n_ctas;
+};
+void embed_scatter(const EmbedArgs& a, cudaStream_t s);
 void wait_flags(const uint32_t* flags, int n, uint32_t target, cudaStream_t s);
 void spin_kernel(int64_t cycles, cudaStream_t s);  // MegaScan software slow-rank injector
 void write_flag(uint32_t* flag, uint32_t value, cudaStream_t s);

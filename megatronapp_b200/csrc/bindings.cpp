@@ -795,6 +795,21 @@ void a2a_scatter_rows(const Tensor& src, const Tensor& dst_rank, const Tensor& d
   b200::a2a_scatter_rows(a, cur_stream());
   count();
 }
+void embed_scatter(const Tensor& tokens, const Tensor& weight, std::vector<int64_t> peer_out, std::vector<int64_t> peer_flags,
+                   int64_t vocab_start, int rank, int size, int64_t epoch, int n_ctas) {
+  c10::cuda::CUDAGuard guard(weight.device());
+  TORCH_CHECK(tokens.dim() == 2 && tokens.is_contiguous() && tokens.scalar_type() == at::kLong, "tokens must be [b, s] int64");
+  TORCH_CHECK(weight.dim() == 2 && weight.is_contiguous() && weight.element_size() == 2 && weight.size(1) % 8 == 0);
+  TORCH_CHECK(tokens.size(1) % size == 0, "sequence length must divide over the group");
+  b200::EmbedArgs a{};
+  a.tokens = tokens.data_ptr<int64_t>(); a.weight = weight.data_ptr();
+  a.b = static_cast<int>(tokens.size(0)); a.s = static_cast<int>(tokens.size(1)); a.h = static_cast<int>(weight.size(1));
+  a.vocab_start = vocab_start; a.vocab_end = vocab_start + weight.size(0); a.rank = rank; a.size = size;
+  a.epoch = static_cast<uint32_t>(epoch); a.n_ctas = n_ctas;
+  for (int i = 0; i < size; ++i) { a.peer_out[i] = reinterpret_cast<void*>(peer_out[i]); a.peer_flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
+  b200::embed_scatter(a, cur_stream());
+  count();
+}
 void spin(int64_t cycles) { b200::spin_kernel(cycles, cur_stream()); count(); }
 void write_flag(int64_t flag_ptr, int64_t value) { b200::write_flag(reinterpret_cast<uint32_t*>(flag_ptr), static_cast<uint32_t>(value), cur_stream()); count(); }
 void peer_copy(int64_t dst_ptr, const Tensor& src) {
@@ -977,6 +992,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bucket_reduce_scatter", &bucket_reduce_scatter);
   m.def("shard_all_gather_cast", &shard_all_gather_cast);
   m.def("a2a_scatter_rows", &a2a_scatter_rows);
+  m.def("embed_scatter", &embed_scatter);
   m.def("spin", &spin);
   m.def("write_flag", &write_flag);
   m.def("peer_copy", &peer_copy);

@@ -10,6 +10,7 @@
 //   bucket_reduce_scatter  - DP gradient reduce-scatter fused with the 1/dp scale and the
 //                            fp32->wire cast  (reference param_and_grad_buffer.py:301-355)
 //   shard_all_gather_cast  - ZeRO-1 param all-gather fused with the fp32->bf16 cast (:194-240)
+//   embed_scatter          - vocab-parallel embedding lookup fused with the sequence-parallel scatter (K14)
 //   a2a_scatter_rows       - MoE dispatch/combine: routed rows go straight into the expert
 //                            owner's buffer (token_dispatcher.py:512-520), no host-synced splits
 #include "b200_api.h"
@@ -71,20 +72,42 @@ template <> struct Wire<__nv_bfloat16> {
 
 // grid = n_ctas; CTA c owns slice c of every rank's shard, so rank q / CTA c only ever waits for
 // CTA c of the other ranks (tile-granular overlap, no grid-wide sync).
-template <typename W>
+//
+// Bandwidth: a thread that loads, scales and stores one float4 per iteration keeps ONE 16-byte request in flight, and
+// 32 CTAs x 512 threads x 16 B per ~1 us HBM round trip is ~0.25 TB/s -- what round 1 measured (219 GB/s).  Each thread
+// therefore issues kU independent loads before the first dependent store (phase 1) and the loads of all sources of kR
+// elements before the first add (phase 2): the NVLink stores are posted, so with 4-8 requests per thread in flight the
+// kernel is bound by the link, not by latency.
+constexpr int kRsUnroll = 8;   // phase 1: independent 16-byte loads per thread
+constexpr int kRsRedUnroll = 2;  // phase 2: elements x sources (<= 8) loads per thread
+
+template <typename W, int kSize>   // kSize: group size known at compile time (2 / 4 / 8) or 0 = runtime
 __global__ void __launch_bounds__(512) bucket_rs_kernel(RsArgs a) {
   const int64_t shard = a.n / a.size;
   const int64_t per_cta = ((shard + gridDim.x - 1) / gridDim.x + 3) / 4 * 4;
   const int64_t lo = min(shard, static_cast<int64_t>(blockIdx.x) * per_cta);
   const int64_t hi = min(shard, lo + per_cta);
+  const int64_t step = static_cast<int64_t>(blockDim.x) * 4;
+  const float scale = a.scale;
   // phase 1: push my (scaled, cast) contribution for every peer's shard slice
   for (int d = 1; d < a.size; ++d) {
     const int peer = (a.rank + d) % a.size;
     const float* src = a.src + peer * shard;
     W* dst = reinterpret_cast<W*>(a.peer_stage[peer]) + static_cast<int64_t>(a.rank) * shard;
-    for (int64_t i = lo + threadIdx.x * 4; i < hi; i += blockDim.x * 4) {
-      float4 g = *reinterpret_cast<const float4*>(src + i);
-      float v[4] = {g.x * a.scale, g.y * a.scale, g.z * a.scale, g.w * a.scale};
+    int64_t i = lo + threadIdx.x * 4;
+    for (; i + (kRsUnroll - 1) * step < hi; i += kRsUnroll * step) {
+      float4 g[kRsUnroll];
+#pragma unroll
+      for (int u = 0; u < kRsUnroll; ++u) g[u] = __ldcs(reinterpret_cast<const float4*>(src + i + u * step));
+#pragma unroll
+      for (int u = 0; u < kRsUnroll; ++u) {
+        float v[4] = {g[u].x * scale, g[u].y * scale, g[u].z * scale, g[u].w * scale};
+        Wire<W>::store4(dst + i + u * step, v);
+      }
+    }
+    for (; i < hi; i += step) {
+      float4 g = __ldcs(reinterpret_cast<const float4*>(src + i));
+      float v[4] = {g.x * scale, g.y * scale, g.z * scale, g.w * scale};
       Wire<W>::store4(dst + i, v);
     }
     __threadfence_system();
@@ -101,20 +124,53 @@ __global__ void __launch_bounds__(512) bucket_rs_kernel(RsArgs a) {
   __syncthreads();
   const W* stage = reinterpret_cast<const W*>(a.peer_stage[a.rank]);
   const float* mine = a.src + a.rank * shard;
-  for (int64_t i = lo + threadIdx.x * 4; i < hi; i += blockDim.x * 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < a.size; ++s) {
-      float v[4];
-      if (s == a.rank) {
-        float4 g = *reinterpret_cast<const float4*>(mine + i);
-        v[0] = g.x * a.scale; v[1] = g.y * a.scale; v[2] = g.z * a.scale; v[3] = g.w * a.scale;
-      } else {
-        Wire<W>::load4(stage + static_cast<int64_t>(s) * shard + i, v);
-      }
+  auto reduce_at = [&](int64_t i, float (&acc)[4]) {
+    if constexpr (kSize > 0) {
+      // every source's load is issued before the first add: kSize requests in flight per element group
+      float v[kSize][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] += v[j];
+      for (int s_ = 0; s_ < kSize; ++s_) {
+        if (s_ == a.rank) {
+          float4 g = __ldcs(reinterpret_cast<const float4*>(mine + i));
+          v[s_][0] = g.x * scale; v[s_][1] = g.y * scale; v[s_][2] = g.z * scale; v[s_][3] = g.w * scale;
+        } else {
+          Wire<W>::load4(stage + static_cast<int64_t>(s_) * shard + i, v[s_]);
+        }
+      }
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
+      for (int s_ = 0; s_ < kSize; ++s_) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += v[s_][j];
+      }
+    } else {
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      for (int s_ = 0; s_ < a.size; ++s_) {
+        float v[4];
+        if (s_ == a.rank) {
+          float4 g = __ldcs(reinterpret_cast<const float4*>(mine + i));
+          v[0] = g.x * scale; v[1] = g.y * scale; v[2] = g.z * scale; v[3] = g.w * scale;
+        } else {
+          Wire<W>::load4(stage + static_cast<int64_t>(s_) * shard + i, v);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += v[j];
+      }
     }
-    *reinterpret_cast<float4*>(a.dst + i) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  };
+  int64_t i = lo + threadIdx.x * 4;
+  for (; i + (kRsRedUnroll - 1) * step < hi; i += kRsRedUnroll * step) {
+    float acc[kRsRedUnroll][4];
+#pragma unroll
+    for (int u = 0; u < kRsRedUnroll; ++u) reduce_at(i + u * step, acc[u]);
+#pragma unroll
+    for (int u = 0; u < kRsRedUnroll; ++u)
+      __stcs(reinterpret_cast<float4*>(a.dst + i + u * step), make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]));
+  }
+  for (; i < hi; i += step) {
+    float acc[4];
+    reduce_at(i, acc);
+    __stcs(reinterpret_cast<float4*>(a.dst + i), make_float4(acc[0], acc[1], acc[2], acc[3]));
   }
 }
 
@@ -171,6 +227,39 @@ __global__ void __launch_bounds__(256) a2a_scatter_kernel(A2aArgs a) {
   __syncthreads();
 }
 
+// K14: vocabulary-parallel embedding fused with the sequence-parallel scatter.  Every token's row lives on exactly one rank
+// of the group, so "masked lookup -> reduce-scatter" (reference layers.py:242-273) needs no reduction at all: the owner
+// writes the row straight into the [s/tp, b, h] output of the rank that owns that sequence position (plain st over NVLink,
+// one warp per token).  CTA c signals CTA c of every peer when its rows are out and waits for theirs: when the kernel
+// retires on a rank, every (peer, CTA) pair has delivered, i.e. the output is complete.
+__global__ void __launch_bounds__(256) embed_scatter_kernel(EmbedArgs a) {
+  const int warps_per_cta = blockDim.x / 32;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x & 31;
+  const int row_vec = a.h * 2 / 16;
+  const int s_local = a.s / a.size;
+  const int64_t n = static_cast<int64_t>(a.b) * a.s;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_cta + warp; t < n;
+       t += static_cast<int64_t>(gridDim.x) * warps_per_cta) {
+    const int64_t id = a.tokens[t];
+    if (id < a.vocab_start || id >= a.vocab_end) continue;
+    const int bi = static_cast<int>(t / a.s), si = static_cast<int>(t % a.s);
+    const int dest = si / s_local;
+    const int64_t row = static_cast<int64_t>(si % s_local) * a.b + bi;
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const uint16_t*>(a.weight) + (id - a.vocab_start) * a.h);
+    int4* dst = reinterpret_cast<int4*>(reinterpret_cast<uint16_t*>(a.peer_out[dest]) + row * a.h);
+    for (int v = lane; v < row_vec; v += 32) st_na_v4(dst + v, ld_nc_v4(src + v));
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.size && threadIdx.x != a.rank)
+    st_release_sys(a.peer_flags[threadIdx.x] + static_cast<int64_t>(a.rank) * gridDim.x + blockIdx.x, a.epoch);
+  if (threadIdx.x < a.size && threadIdx.x != a.rank) {
+    const uint32_t* f = a.peer_flags[a.rank] + static_cast<int64_t>(threadIdx.x) * gridDim.x + blockIdx.x;
+    while (static_cast<int32_t>(ld_acquire_sys(f) - a.epoch) < 0) __nanosleep(64);
+  }
+  __syncthreads();
+}
+
 __global__ void wait_flags_kernel(const uint32_t* flags, int n, uint32_t target) {
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     while (static_cast<int32_t>(ld_acquire_sys(flags + i) - target) < 0) __nanosleep(64);
@@ -198,8 +287,15 @@ void push_flags_barrier(uint32_t* const* peer_flags, int rank, int size, int slo
 
 void bucket_reduce_scatter(const RsArgs& a, cudaStream_t s) {
   const int ctas = a.n_ctas > 0 ? a.n_ctas : 32;
-  if (a.wire_dtype == 2) bucket_rs_kernel<float><<<ctas, 512, 0, s>>>(a);
-  else bucket_rs_kernel<__nv_bfloat16><<<ctas, 512, 0, s>>>(a);
+#define B200_RS_LAUNCH(W)                                                              \
+  switch (a.size) {                                                                   \
+    case 2: bucket_rs_kernel<W, 2><<<ctas, 512, 0, s>>>(a); break;                    \
+    case 4: bucket_rs_kernel<W, 4><<<ctas, 512, 0, s>>>(a); break;                    \
+    case 8: bucket_rs_kernel<W, 8><<<ctas, 512, 0, s>>>(a); break;                    \
+    default: bucket_rs_kernel<W, 0><<<ctas, 512, 0, s>>>(a);                          \
+  }
+  if (a.wire_dtype == 2) { B200_RS_LAUNCH(float) } else { B200_RS_LAUNCH(__nv_bfloat16) }
+#undef B200_RS_LAUNCH
 }
 
 void shard_all_gather_cast(const AgArgs& a, cudaStream_t s) {
@@ -211,6 +307,11 @@ void shard_all_gather_cast(const AgArgs& a, cudaStream_t s) {
 void a2a_scatter_rows(const A2aArgs& a, cudaStream_t s) {
   const int ctas = a.n_ctas > 0 ? a.n_ctas : 32;
   a2a_scatter_kernel<<<ctas, 256, 0, s>>>(a);
+}
+
+void embed_scatter(const EmbedArgs& a, cudaStream_t s) {
+  const int ctas = a.n_ctas > 0 ? a.n_ctas : 32;
+  embed_scatter_kernel<<<ctas, 256, 0, s>>>(a);
 }
 
 void wait_flags(const uint32_t* flags, int n, uint32_t target, cudaStream_t s) {

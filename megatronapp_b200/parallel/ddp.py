@@ -18,6 +18,7 @@ scale and the wire cast over NVLink peer stores (``bucket_reduce_scatter``) inst
 """
 from __future__ import annotations
 
+import os
 import math
 from contextlib import contextmanager
 from dataclasses import dataclass
@@ -50,6 +51,7 @@ class DistributedDataParallelConfig:
     keep_fp8_transpose_cache_when_using_custom_fsdp: bool = False
     # B200: fused scale/cast + reduce-scatter kernel over the DP symmetric arena
     fused_grad_reduce_scatter: bool = False
+    fused_rs_ctas: int = int(os.environ.get("B200_DP_RS_CTAS", "48"))   # SM carve-out of the fused bucket reduce-scatter
     grad_wire_dtype: str = "fp32"  # fp32 | bf16
 
 
@@ -200,13 +202,25 @@ class ParamAndGradBuffer:
         wire_bytes = 4 if wire == 2 else 2
         slot = self._rs_epoch & 1
         stage = arena.region(f"dp_rs_stage{slot}", self.max_bucket_numel() * wire_bytes)
-        flags = arena.region(f"dp_rs_flags{slot}", 64 * 8 * 4)
+        flags = arena.region(f"dp_rs_flags{slot}", 128 * 8 * 4)
         epoch = arena.next_epoch(flags)
         self._rs_epoch += 1
         s, e = self.shard_range(bucket, arena.rank)
         scale = self.gradient_scaling_factor if not self.ddp_config.average_in_collective else 1.0 / self.group_size
-        ops.ext().bucket_reduce_scatter(g, self.grad_data[s:e], arena.ptrs(stage), arena.ptrs(flags), arena.rank,
-                                        arena.size, scale, epoch, wire, 32)
+        # side stream: the 32-64 CTA reduce-scatter runs next to the backward GEMMs instead of in front of them; the
+        # optimizer joins it in finish_grad_sync
+        cur = torch.cuda.current_stream()
+        if self.ddp_config.overlap_grad_reduce:
+            if getattr(self, "_rs_stream", None) is None:
+                self._rs_stream = torch.cuda.Stream()
+            self._rs_stream.wait_stream(cur)
+            with torch.cuda.stream(self._rs_stream):
+                ops.ext().bucket_reduce_scatter(g, self.grad_data[s:e], arena.ptrs(stage), arena.ptrs(flags), arena.rank,
+                                                arena.size, scale, epoch, wire, self.ddp_config.fused_rs_ctas)
+            self._rs_pending = True
+        else:
+            ops.ext().bucket_reduce_scatter(g, self.grad_data[s:e], arena.ptrs(stage), arena.ptrs(flags), arena.rank,
+                                            arena.size, scale, epoch, wire, self.ddp_config.fused_rs_ctas)
         return True
 
     def max_bucket_numel(self) -> int:
@@ -230,6 +244,9 @@ class ParamAndGradBuffer:
             if b.handle is not None:
                 b.handle.wait()
                 b.handle = None
+        if getattr(self, "_rs_pending", False):
+            torch.cuda.current_stream().wait_stream(self._rs_stream)
+            self._rs_pending = False
 
 
 class DistributedDataParallel(nn.Module):

@@ -57,6 +57,7 @@ def setup_tp_fused_comm(max_tokens: int, hidden: int, max_out: int, n_comm_ctas:
         return None
     max_dim = max(hidden, max_out)
     nbytes = 2 * (max_tokens * max_dim * 2) * 2 + 4 * 1024 * 1024
+    nbytes += 2 * (max_tokens * hidden * 2 // tp + 4096)        # K14: two embedding-output slots
     arena = SymmetricArena(ps.get_tensor_model_parallel_group(), nbytes)
     _FUSED_COMM = TPFusedComm(arena, max_tokens, max_dim, max_dim, n_comm_ctas)
     return _FUSED_COMM
@@ -521,6 +522,29 @@ class VocabUtility:
         return VocabUtility.vocab_range_from_per_partition_vocab_size(global_vocab_size // world_size, rank, world_size)
 
 
+class _FusedEmbedSP(torch.autograd.Function):
+    """tokens [b, s] -> embeddings [s / tp, b, h] (sequence parallel).  Backward is the adjoint of "lookup then
+    reduce-scatter": all-gather dy along s, then the dense embedding gradient of the locally owned rows."""
+
+    @staticmethod
+    def forward(ctx, tokens, weight, vocab_start, deterministic):
+        ctx.save_for_backward(tokens)
+        ctx.vocab_start, ctx.v_local, ctx.deterministic = vocab_start, weight.shape[0], deterministic
+        with _scope("embed_scatter", group=_group_ranks, expect="embed_scatter",
+                    data=tokens.numel() * weight.shape[1] * 2 // ps.get_tensor_model_parallel_world_size()):
+            return _FUSED_COMM.embed(tokens, weight.detach(), vocab_start)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (tokens,) = ctx.saved_tensors
+        dy_full = _gather_along_first_dim(dy.contiguous())                      # [s, b, h]
+        local = tokens - ctx.vocab_start
+        mask = (local < 0) | (local >= ctx.v_local)
+        g = dy_full.transpose(0, 1).masked_fill(mask.unsqueeze(-1), 0.0)        # [b, s, h], rows of foreign tokens zeroed
+        dw = torch.ops.aten.embedding_dense_backward(g, local.masked_fill(mask, 0), ctx.v_local, -1, False)
+        return None, dw, None, None
+
+
 class VocabParallelEmbedding(nn.Module):
     def __init__(self, num_embeddings, embedding_dim, *, init_method: Callable,
                  reduce_scatter_embeddings: bool = False, config, tp_group=None):
@@ -541,6 +565,13 @@ class VocabParallelEmbedding(nn.Module):
             set_tensor_model_parallel_attributes(self.weight, True, 0, 1)
 
     def forward(self, input_):
+        fc = _FUSED_COMM
+        if (self.reduce_scatter_embeddings and fc is not None and fc.use_fused_embed and input_.is_cuda and input_.dim() == 2
+                and self.weight.element_size() == 2 and input_.shape[1] % self.tp_size == 0
+                and fc.embed_fits(input_.numel(), self.embedding_dim)):
+            # K14: the owner of a token's row writes it straight into the sequence-parallel output of the rank that
+            # owns the position (no masked lookup, no reduce-scatter)
+            return _FusedEmbedSP.apply(input_.contiguous(), self.weight, self.vocab_start_index, self.deterministic_mode)
         if self.tp_size > 1:
             mask = (input_ < self.vocab_start_index) | (input_ >= self.vocab_end_index)
             local = (input_ - self.vocab_start_index).masked_fill(mask, 0)
