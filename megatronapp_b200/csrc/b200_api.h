@@ -252,6 +252,24 @@ void wait_flags(const uint32_t* flags, int n, uint32_t target, cudaStream_t s);
 void spin_kernel(int64_t cycles, cudaStream_t s);  // MegaScan software slow-rank injector
 void write_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
 
+// ---------------------------------------------------------------- paged-KV attention (paged_attn.cu)
+struct PagedAttnArgs {
+  const void* q;            // [T, ng * group, d]
+  const void* k_cache;      // [n_slots, ng, d]   slot = block * block_size + offset
+  const void* v_cache;
+  void* out;                // [T, ng * group, d]
+  const int32_t* block_table;  // [R, max_blocks]
+  const int32_t* tok_req;   // [T] row of block_table
+  const int32_t* tok_len;   // [T] keys visible to the token (its position + 1)
+  float* ws_o;              // [T * heads * splits, d]   (splits > 1)
+  float* ws_ml;             // [T * heads * splits, 2]
+  int n_tokens, ng, group, head_dim, block_size, max_blocks;
+  float scale_log2;
+  bool is_bf16;
+};
+bool paged_attention_supported(int head_dim, int group);
+void paged_attention(const PagedAttnArgs& a, int splits, cudaStream_t s);
+
 // ---------------------------------------------------------------- MoE (moe.cu)
 void moe_router_topk_fwd(const float* logits, float* probs, uint8_t* map, int32_t* tokens_per_expert, int n, int E, int k,
                          bool pre_softmax, float scaling, cudaStream_t s);

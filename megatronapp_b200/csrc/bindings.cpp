@@ -810,6 +810,34 @@ void embed_scatter(const Tensor& tokens, const Tensor& weight, std::vector<int64
   b200::embed_scatter(a, cur_stream());
   count();
 }
+Tensor paged_attention(const Tensor& q, const Tensor& k_cache, const Tensor& v_cache, const Tensor& block_table,
+                       const Tensor& tok_req, const Tensor& tok_len, int64_t block_size, double scale, int64_t splits) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 3 && q.is_contiguous() && k_cache.dim() == 3 && k_cache.is_contiguous() && v_cache.is_contiguous());
+  TORCH_CHECK(q.scalar_type() == k_cache.scalar_type() && (is_bf16(q) || q.scalar_type() == at::kHalf));
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && tok_req.scalar_type() == at::kInt && tok_len.scalar_type() == at::kInt);
+  TORCH_CHECK(block_table.dim() == 2 && block_table.is_contiguous() && v_cache.sizes() == k_cache.sizes());
+  const int T = static_cast<int>(q.size(0)), np = static_cast<int>(q.size(1)), d = static_cast<int>(q.size(2));
+  const int ng = static_cast<int>(k_cache.size(1));
+  TORCH_CHECK(np % ng == 0 && k_cache.size(2) == d && b200::paged_attention_supported(d, np / ng), "unsupported paged attention shape");
+  auto out = at::empty_like(q);
+  b200::PagedAttnArgs a{};
+  a.q = q.data_ptr(); a.k_cache = k_cache.data_ptr(); a.v_cache = v_cache.data_ptr(); a.out = out.data_ptr();
+  a.block_table = block_table.data_ptr<int32_t>(); a.tok_req = tok_req.data_ptr<int32_t>(); a.tok_len = tok_len.data_ptr<int32_t>();
+  a.n_tokens = T; a.ng = ng; a.group = np / ng; a.head_dim = d; a.block_size = static_cast<int>(block_size);
+  a.max_blocks = static_cast<int>(block_table.size(1)); a.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
+  a.is_bf16 = is_bf16(q);
+  Tensor ws_o, ws_ml;
+  if (splits > 1) {
+    ws_o = at::empty({static_cast<int64_t>(T) * np * splits, d}, q.options().dtype(at::kFloat));
+    ws_ml = at::empty({static_cast<int64_t>(T) * np * splits, 2}, q.options().dtype(at::kFloat));
+    a.ws_o = ws_o.data_ptr<float>(); a.ws_ml = ws_ml.data_ptr<float>();
+  }
+  if (T > 0) b200::paged_attention(a, static_cast<int>(splits), cur_stream());
+  count();
+  return out;
+}
+bool paged_attention_supported(int64_t head_dim, int64_t group) { return b200::paged_attention_supported(static_cast<int>(head_dim), static_cast<int>(group)); }
 void spin(int64_t cycles) { b200::spin_kernel(cycles, cur_stream()); count(); }
 void write_flag(int64_t flag_ptr, int64_t value) { b200::write_flag(reinterpret_cast<uint32_t*>(flag_ptr), static_cast<uint32_t>(value), cur_stream()); count(); }
 void peer_copy(int64_t dst_ptr, const Tensor& src) {
@@ -993,6 +1021,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("shard_all_gather_cast", &shard_all_gather_cast);
   m.def("a2a_scatter_rows", &a2a_scatter_rows);
   m.def("embed_scatter", &embed_scatter);
+  m.def("paged_attention", &paged_attention);
+  m.def("paged_attention_supported", &paged_attention_supported);
   m.def("spin", &spin);
   m.def("write_flag", &write_flag);
   m.def("peer_copy", &peer_copy);

@@ -12,6 +12,7 @@ request's slots (padded over requests), so admission, retirement and preemption 
 """
 from __future__ import annotations
 
+import os
 import itertools
 import queue
 import threading
@@ -59,6 +60,8 @@ class DynamicInferenceContext:
         self.allocator = BlockAllocator(num_blocks)
         self.seqs: Dict[str, _Seq] = {}
         self.kv: Dict[int, tuple] = {}                 # layer -> (K, V) [num_blocks*bs, ng, hn]
+        self.use_paged_kernel = os.environ.get("B200_PAGED_ATTN", "1") == "1"     # 0: gather + einsum reference path
+        self.kernel_calls = 0
         # per-step plan (set by begin_step)
         self.positions: Optional[torch.Tensor] = None
         self._plan: List[tuple] = []                   # (rid, q_start, n_new, kv_before)
@@ -122,6 +125,20 @@ class DynamicInferenceContext:
             mask[i, :n, :L] = torch.arange(L).unsqueeze(0) <= qpos
             mask[i, n:, 0] = True                                      # padded query rows: keep softmax finite
         self._plan = plan
+        # paged-attention kernel inputs: the request row and the number of visible keys of every packed query token, and
+        # the block tables of this step's requests
+        max_blocks = max(len(self.seqs[p[0]].blocks) for p in plan)
+        table = torch.zeros(R, max_blocks, dtype=torch.int32)
+        tok_req, tok_len = [], []
+        for i, (rid, qs, n, before) in enumerate(plan):
+            blocks = self.seqs[rid].blocks
+            table[i, :len(blocks)] = torch.tensor(blocks, dtype=torch.int32)
+            tok_req += [i] * n
+            tok_len += list(range(before + 1, before + n + 1))
+        self._block_table = table.to(device)
+        self._tok_req = torch.tensor(tok_req, dtype=torch.int32).to(device)
+        self._tok_len = torch.tensor(tok_len, dtype=torch.int32).to(device)
+        self._max_len = l_max
         self.positions = torch.cat(pos_all).to(device)
         self._write_slots = torch.cat(slots_all).to(device)
         self._q_index, self._q_valid = q_index.to(device), q_valid.to(device)
@@ -147,6 +164,17 @@ class DynamicInferenceContext:
         kc[self._write_slots] = k
         vc[self._write_slots] = v
         np_, ng = q.shape[1], k.shape[1]
+        if q.is_cuda and self.use_paged_kernel and k.shape[-1] == v.shape[-1] == q.shape[-1] and q.dtype in (torch.bfloat16, torch.float16):
+            from .. import ops
+
+            ext = ops.ext()
+            if ext.paged_attention_supported(q.shape[-1], np_ // ng):
+                # flash-decoding split of long contexts when the (token, KV head) grid alone cannot fill the GPU
+                ctas = q.shape[0] * ng
+                splits = 1 if ctas >= 296 else max(1, min(16, self._max_len // 512, 296 // max(1, ctas)))
+                self.kernel_calls += 1
+                return ext.paged_attention(q.contiguous(), kc, vc, self._block_table, self._tok_req, self._tok_len,
+                                           self.block_size, float(scale), splits)
         qp = q[self._q_index]                                        # [R, n, np, hn]
         kp, vp = kc[self._kv_slots], vc[self._kv_slots]               # [R, L, ng, hn]
         if np_ != ng:

@@ -151,6 +151,15 @@ def test_moe_device_kernels():
     _assert_small({k: v for k, v in res.items() if k not in exact}, 2e-2)
 
 
+def test_paged_kv_attention_kernel_and_dynamic_engine():
+    """Paged-KV attention (decode + chunked prefill, GQA, split-KV) vs fp32 reference; the dynamic engine generates the
+    same tokens through the kernel as through the gather + einsum path, and really uses the kernel."""
+    res = gc.check_paged_attention()
+    flags = {k: v for k, v in res.items() if k.startswith("paged_engine_")}
+    assert all(v == 0 for v in flags.values()), flags
+    _assert_small({k: v for k, v in res.items() if k not in flags}, 2e-2)
+
+
 def test_moe_layer_fused_matches_sequential():
     _assert_small(gc.check_moe_layer(), 5e-2)
 

@@ -767,6 +767,139 @@ def check_model_parity():
             "max_abs_diff": max(abs(a - c) for a, c in zip(l_native, l_ref))}
 
 
+def _paged_case(lens_new, lens_before, np_, ng, d, bs, dtype, seed=0):
+    """A ragged step: request i already holds ``lens_before[i]`` keys and feeds ``lens_new[i]`` tokens.  Returns the
+    kernel inputs and the fp32 reference output."""
+    import torch
+
+    torch.manual_seed(seed)
+    dev = "cuda"
+    R = len(lens_new)
+    total = [b + n for b, n in zip(lens_before, lens_new)]
+    nblk = [-(-t // bs) for t in total]
+    n_blocks = sum(nblk) + 3
+    perm = torch.randperm(n_blocks)[: sum(nblk)].tolist()              # pages scattered over the pool
+    tables, o = [], 0
+    for nb in nblk:
+        tables.append(perm[o:o + nb])
+        o += nb
+    table = torch.zeros(R, max(nblk), dtype=torch.int32)
+    for i, t in enumerate(tables):
+        table[i, :len(t)] = torch.tensor(t, dtype=torch.int32)
+    kc = torch.zeros(n_blocks * bs, ng, d, device=dev, dtype=dtype)
+    vc = torch.zeros_like(kc)
+    ks = [torch.randn(t, ng, d, device=dev, dtype=dtype) for t in total]
+    vs = [torch.randn(t, ng, d, device=dev, dtype=dtype) for t in total]
+    for i in range(R):
+        pos = torch.arange(total[i])
+        slot = torch.tensor(tables[i])[pos // bs] * bs + pos % bs
+        kc[slot.to(dev)] = ks[i]
+        vc[slot.to(dev)] = vs[i]
+    T = sum(lens_new)
+    q = torch.randn(T, np_, d, device=dev, dtype=dtype)
+    tok_req, tok_len, ref = [], [], []
+    scale = d ** -0.5
+    qo = 0
+    for i in range(R):
+        for j in range(lens_new[i]):
+            L = lens_before[i] + j + 1
+            tok_req.append(i)
+            tok_len.append(L)
+            kk = ks[i][:L].float().repeat_interleave(np_ // ng, 1)       # [L, np, d]
+            vv = vs[i][:L].float().repeat_interleave(np_ // ng, 1)
+            sc = torch.einsum("hd,lhd->hl", q[qo].float(), kk) * scale
+            ref.append(torch.einsum("hl,lhd->hd", torch.softmax(sc, -1), vv))
+            qo += 1
+    return (q, kc, vc, table.to(dev), torch.tensor(tok_req, dtype=torch.int32, device=dev),
+            torch.tensor(tok_len, dtype=torch.int32, device=dev), bs, scale), torch.stack(ref)
+
+
+def check_paged_attention():
+    """paged-KV attention kernel vs an fp32 reference: decode + chunked-prefill mix, GQA groups 1/4/8, d 64/128, fp16/bf16,
+    the flash-decoding split path, and the dynamic engine producing the same tokens with and without the kernel."""
+    import torch
+
+    from megatronapp_b200 import ops
+
+    ext = ops.ext()
+    out = {}
+    for name, (new, before, np_, ng, d, bs, dt) in {
+        "decode_g4_d128": ([1, 1, 1, 1, 1], [37, 512, 1, 200, 1023], 8, 2, 128, 16, torch.bfloat16),
+        "mixed_g8_d128": ([1, 7, 1, 33], [300, 0, 45, 64], 16, 2, 128, 16, torch.bfloat16),
+        "mha_d64_fp16": ([1, 5, 1], [129, 3, 77], 4, 4, 64, 32, torch.float16),
+        "g2_d64": ([2, 1], [50, 260], 4, 2, 64, 16, torch.bfloat16),
+    }.items():
+        args, ref = _paged_case(new, before, np_, ng, d, bs, dt)
+        for splits in (1, 4):
+            got = ext.paged_attention(*args, splits)
+            out[f"paged_{name}_s{splits}"] = _rel_err(got, ref)
+    # engine parity: same greedy continuation through the kernel and through the gather + einsum path
+    import os
+
+    from megatronapp_b200.inference.dynamic import DynamicInferenceEngine
+    from megatronapp_b200.inference.core import SamplingParams
+    from megatronapp_b200.bench_model import build_gpt_for_bench
+
+    from megatronapp_b200.data.tokenizer import NullTokenizer
+
+    st = build_gpt_for_bench(2, 256, 4, 256, 512, 1, ffn=512, tp=1, device="cuda", kv_groups=2, rope=True, bias=False)
+    model = st.model[0]
+    model.eval()
+    res = {}
+    prompts = ["5 9 23 7 100 3 4 8 15 16 23 42", "11 3", " ".join(str(7 + 3 * i) for i in range(40))]
+    for flag in ("1", "0"):
+        os.environ["B200_PAGED_ATTN"] = flag
+        eng = DynamicInferenceEngine(model, NullTokenizer(511), max_sequence_length=256, num_blocks=64, block_size=16,
+                                     max_tokens_per_step=32, max_requests=3)
+        eng.padded_vocab_size = 512
+        with torch.no_grad():
+            rs = eng.generate(prompts, SamplingParams(num_tokens_to_generate=12, top_k=1))
+        res[flag] = ([[int(x) for x in r.generated_tokens] for r in rs], eng.context.kernel_calls)
+    os.environ["B200_PAGED_ATTN"] = "1"
+    out["paged_engine_token_mismatch"] = float(res["1"][0] != res["0"][0])
+    out["paged_engine_kernel_unused"] = float(res["1"][1] == 0 or res["0"][1] != 0)
+    return out
+
+
+def check_paged_attention_perf():
+    """decode step: 64 requests x 4096 keys, 32 q heads / 8 kv heads, d 128 -> achieved HBM bandwidth over the K/V bytes"""
+    import torch
+
+    from megatronapp_b200 import ops
+
+    ext = ops.ext()
+    out = {}
+    for name, R, L, np_, ng in (("r64_l4096", 64, 4096, 32, 8), ("r8_l16384", 8, 16384, 32, 8), ("r256_l1024", 256, 1024, 32, 8)):
+        args, _ = None, None
+        torch.manual_seed(0)
+        bs, d = 16, 128
+        nblk = -(-L // bs)
+        table = torch.randperm(R * nblk, dtype=torch.int32).view(R, nblk).cuda()
+        kc = torch.randn(R * nblk * bs, ng, d, device="cuda", dtype=torch.bfloat16)
+        vc = torch.randn_like(kc)
+        q = torch.randn(R, np_, d, device="cuda", dtype=torch.bfloat16)
+        tok_req = torch.arange(R, dtype=torch.int32, device="cuda")
+        tok_len = torch.full((R,), L, dtype=torch.int32, device="cuda")
+        ctas = R * ng
+        best = None
+        for splits in (1, 2, 4, 8, 16):
+            ms = _time(lambda: ext.paged_attention(q, kc, vc, table, tok_req, tok_len, bs, d ** -0.5, splits))
+            gbs = 2 * R * L * ng * d * 2 / ms / 1e6
+            out[f"paged_{name}_s{splits}"] = {"ms": round(ms, 4), "GBs": round(gbs, 1)}
+            best = max(best or 0, gbs)
+        out[f"paged_{name}_best_frac_of_hbm"] = round(best / 7700.0, 3)
+
+        def gather_ref():
+            slots = (table.long().unsqueeze(-1) * bs + torch.arange(bs, device="cuda")).view(R, -1)[:, :L]
+            kp, vp = kc[slots].repeat_interleave(np_ // ng, 2), vc[slots].repeat_interleave(np_ // ng, 2)
+            s_ = torch.einsum("rhd,rlhd->rhl", q.float(), kp.float()) * d ** -0.5
+            return torch.einsum("rhl,rlhd->rhd", torch.softmax(s_, -1), vp.float())
+
+        if R * L <= 64 * 4096:
+            out[f"paged_{name}_gather_einsum_ms"] = round(_time(gather_ref, iters=5, warmup=2), 3)
+    return out
+
+
 CHECKS = {
     "gemm_nt": lambda: check_gemm("nt"),
     "gemm_nt_bias_gelu": lambda: check_gemm("nt_bias_gelu", [(256, 256, 128), (2048, 4096, 4096), (300, 520, 264)]),
@@ -783,10 +916,11 @@ CHECKS = {
     "grouped_gemm": check_grouped_gemm,
     "moe_kernels": check_moe_kernels,
     "moe_layer": check_moe_layer,
+    "paged_attention": check_paged_attention,
     "model_parity": check_model_parity,
     "smoke": check_smoke,
 }
-PERF = {"mxfp8_perf": check_mxfp8_perf, "grouped_perf": check_grouped_perf, "fp8_perf": check_fp8_perf, "gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
+PERF = {"paged_attention_perf": check_paged_attention_perf, "mxfp8_perf": check_mxfp8_perf, "grouped_perf": check_grouped_perf, "fp8_perf": check_fp8_perf, "gemm_perf": check_gemm_perf, "elementwise_perf": check_elementwise_perf, "attention_perf": check_attention_perf}
 
 
 def main():
