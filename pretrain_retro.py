@@ -62,6 +62,23 @@ class MockRetroDataset(torch.utils.data.Dataset):
 
 def train_valid_test_datasets_provider(num_samples):
     a = get_args()
+    if a.retro_project_dir and a.data_path:
+        # real data: the GPT blend + the neighbour table tools/retro/preprocess_data.py wrote for exactly this blend / split /
+        # seed / sequence length; validation and test fall back to mock neighbours (only the train split is queried)
+        from megatronapp_b200.data.gpt_dataset import build_gpt_datasets
+        from megatronapp_b200.data.retro import ChunkDB, RetroDataset, RetroPreprocessingConfig
+
+        cfg = RetroPreprocessingConfig.load(a.retro_project_dir)
+        for mine, theirs, what in ((a.seq_length, cfg.retro_gpt_seq_length, "sequence length"),
+                                   (a.retro_chunk_length, cfg.retro_gpt_chunk_length, "chunk length"),
+                                   (a.retro_retrieved_length, cfg.retro_retrieved_length, "retrieved length"),
+                                   (a.retro_num_neighbors, cfg.retro_query_num_neighbors_save, "neighbour count")):
+            if mine != theirs:
+                raise ValueError(f"retro project was preprocessed with {what} {theirs}, training asks for {mine}")
+        train, valid, test = build_gpt_datasets(a, [cfg.retro_gpt_train_samples or num_samples[0], num_samples[1], num_samples[2]])
+        mock = lambda n, s: MockRetroDataset(max(int(n), 1), a.seq_length, a.padded_vocab_size, a.retro_chunk_length,  # noqa: E731
+                                             a.retro_num_neighbors, a.retro_retrieved_length, s)
+        return RetroDataset(cfg, train, ChunkDB(cfg), "train"), mock(num_samples[1], 2), mock(num_samples[2], 3)
     mk = lambda n, s: MockRetroDataset(max(int(n), 1), a.seq_length, a.padded_vocab_size, a.retro_chunk_length,  # noqa: E731
                                        a.retro_num_neighbors, a.retro_retrieved_length, s)
     return mk(num_samples[0], 1), mk(num_samples[1], 2), mk(num_samples[2], 3)
