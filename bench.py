@@ -160,7 +160,8 @@ def run_own(args):
                                 device=f"cuda:{local_rank}", lr=1e-4, fused_tp_comm=not args.no_fused_tp_comm,
                                 use_distributed_optimizer=dp > 1, overlap_grad_reduce=(dp > 1 and not args.no_dp_overlap),
                                 fused_grad_rs=(args.fused_grad_rs and dp > 1 and not moe), dropout=0.0, vpp=vpp, fbd=args.fbd,
-                                fp8="hybrid" if args.fp8 else None, fp8_recipe=args.fp8_recipe, **arch)
+                                fp8="hybrid" if args.fp8 else None, fp8_recipe=args.fp8_recipe,
+                                recompute_layers=args.recompute_layers, **arch)
     if args.fbd:
         from megatronapp_b200.fbd.schedule import install_fbd_schedule
 
@@ -309,6 +310,7 @@ def run_own(args):
                        "attention_impl": "native" if ops.native_attention_available() else "sdpa-library",
                        "fused_tp_comm": (tp > 1 and not args.no_fused_tp_comm),
                        "fused_gemm_rs": (tp > 1 and not args.no_fused_tp_comm and not args.no_fused_rs),
+                       "recompute_layers": args.recompute_layers,
                        "dp_grad_sync": (None if dp == 1 else ("fused-kernel" if (args.fused_grad_rs and not moe) else "nccl")
                                         + ("" if args.no_dp_overlap else "+overlap"))},
             "clocks": clocks,
@@ -418,6 +420,8 @@ def main():
     ap.add_argument("--no-dp-overlap", action="store_true", help="dp>1: reduce-scatter the gradients after backward instead of per bucket")
     ap.add_argument("--fused-grad-rs", action="store_true",
                     help="dp>1: sm_100a bucket reduce-scatter (scale + cast + RS over NVLink peer stores) instead of NCCL")
+    ap.add_argument("--recompute-layers", type=int, default=0,
+                    help="full activation recompute of the first N layers per stage (memory-bound configs, e.g. Mixtral 8x7B on 8 GPUs)")
     ap.add_argument("--detect", action="store_true", help="run the MegaScan detector on the traced steps (rank 0) and report it")
     ap.add_argument("--moe-baseline", action="store_true",
                     help="MoE in-tree baseline: NCCL all-to-all dispatcher + one module per expert (reference algorithm)")

@@ -43,7 +43,7 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
                         use_distributed_optimizer=False, dropout=0.0, vpp=None, overlap_grad_reduce=False,
                         seed=1234, num_experts=None, ep=1, moe_topk=2, fused_grad_rs=False, fp8=None, fp8_recipe="delayed",
                         moe_grouped=False, moe_dispatcher=None, moe_ffn=None, fbd=False, etp=None,
-                        moe_aux_loss_coeff=0.0, fbd_collapse=False) -> BenchState:
+                        moe_aux_loss_coeff=0.0, fbd_collapse=False, recompute_layers=0) -> BenchState:
     if torch.cuda.is_available() and str(device).startswith("cuda"):
         torch.cuda.set_device(torch.device(device) if ":" in str(device) else torch.cuda.current_device())
     if not ps.model_parallel_is_initialized():
@@ -76,6 +76,9 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
               use_cpu_initialization=not str(device).startswith("cuda"))
     if swiglu:
         kw.update(activation_func=F.silu, gated_linear_unit=True)
+    if recompute_layers:
+        # full activation recompute of the first N layers of every stage ("block"): trades N/L x one extra forward for memory
+        kw.update(recompute_granularity="full", recompute_method="block", recompute_num_layers=int(recompute_layers))
     config = TransformerConfig(**kw)
     if etp is not None:
         kw["expert_tensor_parallel_size"] = etp

@@ -52,6 +52,13 @@ static int g_next = 1;
 static std::string g_err;
 const char* mailbox_last_error() { return g_err.c_str(); }
 
+// the id -> mailbox table is read from the scheduler thread while setup / teardown may run on another one
+static Mailbox* find_box(int id) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_boxes.find(id);
+  return it == g_boxes.end() ? nullptr : it->second;
+}
+
 int mailbox_create(int n_slots, size_t slot_bytes, const char* shm_name, void* ipc_handle_out64) {
   auto* mb = new Mailbox();
   mb->n_slots = n_slots;
@@ -75,7 +82,8 @@ int mailbox_create(int n_slots, size_t slot_bytes, const char* shm_name, void* i
 }
 
 int mailbox_connect(int id, const void* peer_ipc_handle64, const char* peer_shm_name) {
-  Mailbox* mb = g_boxes.at(id);
+  Mailbox* mb = find_box(id);
+  if (!mb) { g_err = "unknown mailbox"; return -1; }
   cudaIpcMemHandle_t h;
   memcpy(&h, peer_ipc_handle64, sizeof(h));
   if (cudaIpcOpenMemHandle(&mb->peer_buf, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { g_err = "cudaIpcOpenMemHandle failed"; return -1; }
@@ -91,7 +99,8 @@ int mailbox_connect(int id, const void* peer_ipc_handle64, const char* peer_shm_
 }
 
 int mailbox_put(int id, int slot, const void* src, size_t nbytes, uint32_t epoch, cudaStream_t s) {
-  Mailbox* mb = g_boxes.at(id);
+  Mailbox* mb = find_box(id);
+  if (!mb) { g_err = "unknown mailbox"; return -1; }
   if (slot < 0 || slot >= mb->n_slots || nbytes > mb->slot_bytes || !mb->peer_buf) { g_err = "bad slot / size / not connected"; return -1; }
   char* dst = (char*)mb->peer_buf + (size_t)slot * mb->slot_bytes;
   if (cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { g_err = "peer memcpy failed"; return -1; }
@@ -101,19 +110,23 @@ int mailbox_put(int id, int slot, const void* src, size_t nbytes, uint32_t epoch
 }
 
 bool mailbox_try_get(int id, int slot, uint32_t epoch) {
-  Mailbox* mb = g_boxes.at(id);
-  volatile uint32_t* f = mb->recv_flags_host + slot;
-  uint32_t v = *f;
-  std::atomic_thread_fence(std::memory_order_acquire);
+  Mailbox* mb = find_box(id);
+  if (!mb || slot < 0 || slot >= mb->n_slots) return false;
+  // acquire load of the doorbell word the sender's stream wrote (st.release.sys) after the payload
+  const uint32_t v = __atomic_load_n(mb->recv_flags_host + slot, __ATOMIC_ACQUIRE);
   return (int32_t)(v - epoch) >= 0 && v != 0;
 }
 
 void* mailbox_slot_ptr(int id, int slot) {
-  Mailbox* mb = g_boxes.at(id);
+  Mailbox* mb = find_box(id);
+  if (!mb) return nullptr;
   return (char*)mb->recv_buf + (size_t)slot * mb->slot_bytes;
 }
 
-long mailbox_sent(int id) { return g_boxes.at(id)->sent.load(); }
+long mailbox_sent(int id) {
+  Mailbox* mb = find_box(id);
+  return mb ? mb->sent.load() : -1;
+}
 
 void mailbox_destroy(int id) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -1,0 +1,26 @@
+"""ThreadSanitizer run of the MegaDPP mailbox's host-side protocol (table lookups under create / destroy churn, shm
+doorbells, payload-before-flag ordering) against a host-only CUDA shim -- CPU only, real threads."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_mailbox_is_clean_under_thread_sanitizer(tmp_path):
+    exe = str(tmp_path / "mailbox_tsan")
+    nat = os.path.join(ROOT, "tests", "native")
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I", os.path.join(nat, "fake_cuda"),
+                            "-I", os.path.join(ROOT, "megatronapp_b200", "csrc"), os.path.join(nat, "mailbox_tsan.cpp"),
+                            os.path.join(ROOT, "megatronapp_b200", "csrc", "mailbox.cpp"), "-o", exe, "-lpthread", "-lrt"],
+                           capture_output=True, text=True, timeout=300)
+    if build.returncode != 0 and "tsan" in build.stderr.lower():
+        pytest.skip("libtsan is not installed")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0"))
+    out = run.stdout + run.stderr
+    assert run.returncode == 0 and "errors=0" in out, out[-3000:]
+    assert "ThreadSanitizer" not in out, out[-3000:]
