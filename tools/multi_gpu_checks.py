@@ -53,12 +53,74 @@ def timed(fn, iters=20, warm=5):
     return float(t.item())
 
 
+def dp_and_embed_checks(arena, fc, group, rank, world, dt, log, ops):
+    # ---------------- fused bucket reduce-scatter (scale + cast + RS): a default-sized DP bucket (40 M fp32 elements)
+    n = 40 * 1024 * 1024
+    torch.manual_seed(400 + rank)
+    g = torch.randn(n, device="cuda")
+    ref = torch.empty(n // world, device="cuda")
+    dist.reduce_scatter_tensor(ref, g / world, group=group)
+    stage = arena.region("rs_stage", n * 4)
+    flags = arena.region("rs_flags", 128 * 8 * 4)
+    outs = torch.empty(n // world, device="cuda")
+
+    def nccl():
+        g2 = g * (1.0 / world)
+        dist.reduce_scatter_tensor(ref, g2, group=group)
+
+    tn_ = timed(nccl, 10, 3)
+    for wire, wname in ((2, "fp32"), (0, "bf16")):
+        ep = arena.next_epoch(flags)
+        ops.ext().bucket_reduce_scatter(g, outs, arena.ptrs(stage), arena.ptrs(flags), rank, world, 1.0 / world, ep, wire, 32)
+        torch.cuda.synchronize()
+        log(f"bucket_rs_{wname}_err", rel_err(outs, ref))
+        row = {"mul+nccl": tn_}
+        for ctas in (16, 32, 64, 128):
+            def fused(ctas=ctas):
+                e = arena.next_epoch(flags)
+                ops.ext().bucket_reduce_scatter(g, outs, arena.ptrs(stage), arena.ptrs(flags), rank, world, 1.0 / world, e, wire, ctas)
+
+            t = timed(fused, 10, 3)
+            # bytes this rank puts on the wire / time, and the fp32-equivalent ("algorithm") rate NCCL is quoted in
+            row[f"fused_{ctas}cta"] = t
+            row[f"wire_GBs_{ctas}cta"] = n * (4 if wire == 2 else 2) * (world - 1) / world / t / 1e6
+            row[f"fp32_equiv_GBs_{ctas}cta"] = n * 4 * (world - 1) / world / t / 1e6
+        row["nccl_fp32_GBs"] = n * 4 * (world - 1) / world / tn_ / 1e6
+        log(f"bucket_rs_{wname}_ms", row)
+
+    # ---------------- K14: vocab-parallel embedding fused with the sequence-parallel scatter
+    import torch.nn.functional as F_
+
+    bb, ss, hh, Vv = world, 2048, 4096, 50432 // world * world
+    torch.manual_seed(11)
+    toks = torch.randint(0, Vv, (bb, ss), device="cuda")
+    torch.manual_seed(500 + rank)
+    wemb = torch.randn(Vv // world, hh, device="cuda", dtype=dt)
+    v0 = rank * (Vv // world)
+
+    def emb_ref():
+        m = (toks < v0) | (toks >= v0 + Vv // world)
+        o = F_.embedding((toks - v0).masked_fill(m, 0), wemb).masked_fill(m.unsqueeze(-1), 0.0).transpose(0, 1).contiguous()
+        r = torch.empty(ss // world, bb, hh, device="cuda", dtype=dt)
+        dist.reduce_scatter_tensor(r, o, group=group)
+        return r
+
+    if fc.embed_fits(bb * ss, hh):
+        got, want = fc.embed(toks, wemb, v0), emb_ref()
+        torch.cuda.synchronize()
+        log("embed_scatter_exact", bool(torch.equal(got, want)))
+        log("embed_scatter_ms", {"fused": timed(lambda: fc.embed(toks, wemb, v0)), "embedding+mask+nccl_rs": timed(emb_ref)})
+    else:
+        log("embed_scatter_exact", "arena too small")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "multi.json"))
     ap.add_argument("--skip-model", action="store_true")
     ap.add_argument("--skip-moe", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
+    ap.add_argument("--dp-only", action="store_true", help="only the bucket reduce-scatter sweep and the K14 embedding scatter")
     a = ap.parse_args()
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -79,6 +141,15 @@ def main():
 
     try:
         if a.skip_kernels:
+            raise KeyboardInterrupt
+        if a.dp_only:
+            Mt = 2048 * world
+            arena = SymmetricArena(group, (520 << 20))
+            fc = TPFusedComm(arena, Mt, 4096, 4096)
+            arena.barrier()
+            dp_and_embed_checks(arena, fc, group, rank, world, dt, log, ops)
+            arena.barrier()
+            torch.cuda.synchronize()
             raise KeyboardInterrupt
         Mt = 2048 * world          # bench.py: micro-batch = TP degree, seq 2048
         shapes = [(Mt, 4096, 16384 // world, "fc1"), (Mt, 4096, 12288 // world, "qkv")]
@@ -231,64 +302,7 @@ def main():
             tw.update(roofline_ms=roof, frac_of_roofline=roof / tw["fused"], tflops_fused=2.0 * tok * n_out * k_in / tw["fused"] / 1e9)
             log(f"ag_wgrad_{name}_ms", tw)
 
-        # ---------------- fused bucket reduce-scatter (scale + cast + RS): a default-sized DP bucket (40 M fp32 elements)
-        n = 40 * 1024 * 1024
-        torch.manual_seed(400 + rank)
-        g = torch.randn(n, device="cuda")
-        ref = torch.empty(n // world, device="cuda")
-        dist.reduce_scatter_tensor(ref, g / world, group=group)
-        stage = arena.region("rs_stage", n * 4)
-        flags = arena.region("rs_flags", 128 * 8 * 4)
-        outs = torch.empty(n // world, device="cuda")
-
-        def nccl():
-            g2 = g * (1.0 / world)
-            dist.reduce_scatter_tensor(ref, g2, group=group)
-
-        tn_ = timed(nccl, 10, 3)
-        for wire, wname in ((2, "fp32"), (0, "bf16")):
-            ep = arena.next_epoch(flags)
-            ops.ext().bucket_reduce_scatter(g, outs, arena.ptrs(stage), arena.ptrs(flags), rank, world, 1.0 / world, ep, wire, 32)
-            torch.cuda.synchronize()
-            log(f"bucket_rs_{wname}_err", rel_err(outs, ref))
-            row = {"mul+nccl": tn_}
-            for ctas in (16, 32, 64, 128):
-                def fused(ctas=ctas):
-                    e = arena.next_epoch(flags)
-                    ops.ext().bucket_reduce_scatter(g, outs, arena.ptrs(stage), arena.ptrs(flags), rank, world, 1.0 / world, e, wire, ctas)
-
-                t = timed(fused, 10, 3)
-                # bytes this rank puts on the wire / time, and the fp32-equivalent ("algorithm") rate NCCL is quoted in
-                row[f"fused_{ctas}cta"] = t
-                row[f"wire_GBs_{ctas}cta"] = n * (4 if wire == 2 else 2) * (world - 1) / world / t / 1e6
-                row[f"fp32_equiv_GBs_{ctas}cta"] = n * 4 * (world - 1) / world / t / 1e6
-            row["nccl_fp32_GBs"] = n * 4 * (world - 1) / world / tn_ / 1e6
-            log(f"bucket_rs_{wname}_ms", row)
-
-        # ---------------- K14: vocab-parallel embedding fused with the sequence-parallel scatter
-        import torch.nn.functional as F_
-
-        bb, ss, hh, Vv = world, 2048, 4096, 50432 // world * world
-        torch.manual_seed(11)
-        toks = torch.randint(0, Vv, (bb, ss), device="cuda")
-        torch.manual_seed(500 + rank)
-        wemb = torch.randn(Vv // world, hh, device="cuda", dtype=dt)
-        v0 = rank * (Vv // world)
-
-        def emb_ref():
-            m = (toks < v0) | (toks >= v0 + Vv // world)
-            o = F_.embedding((toks - v0).masked_fill(m, 0), wemb).masked_fill(m.unsqueeze(-1), 0.0).transpose(0, 1).contiguous()
-            r = torch.empty(ss // world, bb, hh, device="cuda", dtype=dt)
-            dist.reduce_scatter_tensor(r, o, group=group)
-            return r
-
-        if fc.embed_fits(bb * ss, hh):
-            got, want = fc.embed(toks, wemb, v0), emb_ref()
-            torch.cuda.synchronize()
-            log("embed_scatter_exact", bool(torch.equal(got, want)))
-            log("embed_scatter_ms", {"fused": timed(lambda: fc.embed(toks, wemb, v0)), "embedding+mask+nccl_rs": timed(emb_ref)})
-        else:
-            log("embed_scatter_exact", "arena too small")
+        dp_and_embed_checks(arena, fc, group, rank, world, dt, log, ops)
         arena.barrier()
         torch.cuda.synchronize()
     except KeyboardInterrupt:
