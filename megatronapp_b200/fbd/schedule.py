@@ -46,7 +46,8 @@ def fbd_forward_backward(*, forward_step_func, data_iterator, model, num_microba
                          collect_non_loss_data=False, first_val_step=None):
     chunks = model if isinstance(model, (list, tuple)) else [model]
     if len(chunks) != 1:
-        raise RuntimeError("MegaFBD does not support interleaved (virtual pipeline) schedules")
+        return _fbd_interleaved(forward_step_func, data_iterator, chunks, num_microbatches, seq_length, micro_batch_size,
+                                forward_only, collect_non_loss_data)
     m0 = chunks[0]
     config = schedules._get_config(m0)
     pp, rank = ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_rank()
@@ -104,6 +105,93 @@ def fbd_forward_backward(*, forward_step_func, data_iterator, model, num_microba
     p2p.flush()
     if hasattr(m0, "is_last_microbatch"):
         m0.is_last_microbatch = True
+    if not forward_only and config.finalize_model_grads_func is not None:
+        config.finalize_model_grads_func(chunks, total_tokens if config.calculate_per_token_loss else None)
+    return store
+
+
+def _fbd_interleaved(forward_step_func, data_iterator, chunks, num_microbatches, seq_length, micro_batch_size,
+                     forward_only, collect_non_loss_data):
+    """MegaFBD on the interleaved (virtual pipeline) layout: rank r holds chunks c = 0..V-1, i.e. virtual stages
+    ``c * pp + r``.  Microbatches travel in groups of ``pp`` (the interleaved unit):
+
+    * forward ranks run group g through chunk 0, then chunk 1, ... (the order of the interleaved warm-up, so the ring
+      stays busy) and hand every virtual stage's input to their twin in that order;
+    * a backward rank first collects the group's ``V x pp`` stage inputs from its twin (same FIFO order; ~one activation
+      tensor each), then walks the virtual stages of the group *backwards* -- chunk V-1 ... 0 -- recomputing one
+      microbatch at a time, so it still holds a single microbatch of activations.
+
+    Every directed edge carries its messages in one agreed order ((group, chunk ascending, microbatch) for activations,
+    (group, chunk descending, microbatch) for gradients, the wrap edge last->first included), so the unidirectional
+    channels cannot dead-lock."""
+    V = len(chunks)
+    pp, rank = ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_rank()
+    if num_microbatches % pp:
+        raise RuntimeError(f"interleaved MegaFBD needs num_microbatches ({num_microbatches}) divisible by pp ({pp})")
+    config = schedules._get_config(chunks[0])
+    shape = get_tensor_shapes(seq_length, micro_batch_size, config)
+    bwd_config = config
+    if ps.fbd_forward_tp_collapsed() and ps.is_forward_stage():
+        bwd_config = getattr(config, "fbd_backward_config", config)
+    dtype = config.pipeline_dtype or config.params_dtype
+    its = list(data_iterator) if isinstance(data_iterator, (list, tuple)) else [data_iterator] * V
+    nxt, prv = ps.get_pipeline_model_parallel_next_rank(), ps.get_pipeline_model_parallel_prev_rank()
+    is_first = lambda c: rank == 0 and c == 0                       # noqa: E731  first / last VIRTUAL stage
+    is_last = lambda c: rank == pp - 1 and c == V - 1               # noqa: E731
+    groups = [list(range(g, g + pp)) for g in range(0, num_microbatches, pp)]
+    store: List = []
+    total_tokens = torch.zeros((), dtype=torch.int, device=next(chunks[0].parameters()).device)
+    if ps.is_forward_stage():
+        for grp in groups:
+            for c in range(V):
+                ps.set_virtual_pipeline_model_parallel_rank(c)
+                for mb in grp:
+                    inp = None
+                    if not is_first(c):
+                        inp = p2p.recv(shape, dtype, prv, "fwd", "recv-forward")
+                        p2p.send_corresponding_forward(inp, bwd_config)
+                    if is_last(c):
+                        continue
+                    with torch.no_grad():
+                        out, _ = forward_step(forward_step_func, its[c], chunks[c], num_microbatches, inp, store, config,
+                                              collect_non_loss_data, is_first_microbatch=(mb == 0), current_microbatch=mb,
+                                              is_last_stage=False)
+                    p2p.send(out, nxt, "fwd", "send-forward")
+        p2p.flush()
+        ps.set_virtual_pipeline_model_parallel_rank(0)
+        return []
+    for ch in chunks:
+        if hasattr(ch, "is_last_microbatch"):
+            ch.is_last_microbatch = False
+    for grp in groups:
+        stash = {}
+        for c in range(V):
+            for mb in grp:
+                if not is_first(c):
+                    stash[(c, mb)] = p2p.recv_corresponding_forward(shape, dtype)
+        for c in reversed(range(V)):
+            ps.set_virtual_pipeline_model_parallel_rank(c)
+            for mb in grp:
+                inp = stash.pop((c, mb), None)
+                ctx = torch.no_grad() if forward_only else contextlib.nullcontext()
+                with ctx:
+                    out, ntok = forward_step(forward_step_func, its[c], chunks[c], num_microbatches, inp, store, config,
+                                             collect_non_loss_data, is_first_microbatch=(mb == 0), current_microbatch=mb,
+                                             is_last_stage=is_last(c))
+                total_tokens += ntok.to(total_tokens.device) if torch.is_tensor(ntok) else int(ntok)
+                if forward_only:
+                    continue
+                grad = None if is_last(c) else p2p.recv(shape, dtype, nxt, "bwd", "recv-backward")
+                if hasattr(chunks[c], "is_last_microbatch"):
+                    chunks[c].is_last_microbatch = (mb == num_microbatches - 1)
+                in_grad = backward_step(inp, out, grad, None, config, microbatch=mb)
+                if not is_first(c):
+                    p2p.send(in_grad, prv, "bwd", "send-backward")
+    p2p.flush()
+    ps.set_virtual_pipeline_model_parallel_rank(0)
+    for ch in chunks:
+        if hasattr(ch, "is_last_microbatch"):
+            ch.is_last_microbatch = True
     if not forward_only and config.finalize_model_grads_func is not None:
         config.finalize_model_grads_func(chunks, total_tokens if config.calculate_per_token_loss else None)
     return store

@@ -34,7 +34,8 @@ def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=F
 
     rank, world = _setup()
     if fbd:
-        ps.initialize_model_parallel(tp, pp, forward_backward_disaggregating=True, ignore_forward_tensor_parallel=collapse)
+        ps.initialize_model_parallel(tp, pp, virtual_pipeline_model_parallel_size=vpp, forward_backward_disaggregating=True,
+                                     ignore_forward_tensor_parallel=collapse)
         from megatronapp_b200.parallel import p2p
 
         p2p.build_channels()
@@ -63,12 +64,16 @@ def train_parity(tp=1, pp=1, vpp=None, sp=False, dist_opt=False, dpp=None, fbd=F
             l = train_step(st, mine)
         losses.append(l)
     w = next(st.model[0].parameters()).detach().double().sum().item()
-    inner = st.model[0]
-    while hasattr(inner, "module"):
-        inner = inner.module
     emb = None
-    if (st.pre_process or st.post_process) and getattr(inner, "share_embeddings_and_output_weights", False):
-        emb = inner.shared_embedding_or_output_weight().detach().double().pow(2).sum().item()
+    for chunk in st.model:                       # interleaved schedules: the chunk that holds the (tied) embedding copy
+        inner = chunk
+        while hasattr(inner, "module"):
+            inner = inner.module
+        if (st.pre_process or st.post_process) and getattr(inner, "share_embeddings_and_output_weights", False):
+            wt = inner.shared_embedding_or_output_weight()
+            if wt is not None:
+                emb = wt.detach().double().pow(2).sum().item()
+                break
     return {"losses": losses, "dp": dp, "w": w, "last": st.post_process, "emb": emb,
             "is_backward": ps.is_backward_stage()}
 

@@ -95,6 +95,16 @@ def test_fbd_matches_plain_pipeline():
     _close(_last_stage_losses(res), base, 1e-5)
 
 
+def test_fbd_interleaved_matches_plain_interleaved_pipeline():
+    """MegaFBD on the virtual-pipeline layout: 4 ranks = pp 2 x (forward, backward) twins with 2 chunks per rank reproduce
+    the 2-rank interleaved pipeline (same data, same seeds) -- activations of a group of pp microbatches are handed over in
+    forward order and consumed by the backward twin walking the virtual stages in reverse."""
+    base = _last_stage_losses(run_distributed("train_parity", 2, pp=2, vpp=2))
+    res = run_distributed("train_parity", 4, pp=2, vpp=2, fbd=True)
+    _close(_last_stage_losses(res), base, 1e-5)
+    assert sum(1 for r in res if not r["is_backward"]) == 2
+
+
 @pytest.mark.parametrize("swiglu", [False, True])
 def test_fbd_forward_tp_collapse_matches_plain_tp_pipeline(swiglu):
     """--ignore-forward-tensor-parallel: 6 ranks = pp 2 x (1 un-sharded forward rank + 2 backward TP ranks, sequence
