@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(128) paged_attn_kernel(PagedAttnArgs a) {
   const int k0 = split * per, k1 = min(len, k0 + per);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lk = lane % kLPK, grp = warp * kKPW + lane / kLPK;
+  // the key groups of a warp run different trip counts at the tail of a context: shuffles name only the group's lanes
+  const unsigned gmask = (kLPK == 32) ? 0xffffffffu : (((1u << kLPK) - 1u) << (lane / kLPK * kLPK));
   const int np = a.ng * G;
 
   __shared__ float s_m[kGroups][G], s_l[kGroups][G];
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(128) paged_attn_kernel(PagedAttnArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) s = fmaf(q[g][j], kf[j], s);
 #pragma unroll
-      for (int o = kLPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, kLPK);
+      for (int o = kLPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, kLPK);
       const float mn = fmaxf(m[g], s);
       const float corr = exp2f(m[g] - mn), p = exp2f(s - mn);
       l[g] = l[g] * corr + p;
