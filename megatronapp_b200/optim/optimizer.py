@@ -504,6 +504,11 @@ class MegatronOptimizer:
                             flattened_range=slice(lo - a, hi - a), replica_id=rid[:-1] + (0,), replica_count=1)
         return out
 
+    def supports_model_space_state(self) -> bool:
+        """False when part of the state lives in pinned host memory (--optimizer-cpu-offload): such runs checkpoint the
+        optimizer per rank (same-layout restore), like the ZeRO-3 wrappers."""
+        return not any(st.master_cpu is not None for st in self.states)
+
     def sharded_common_state(self) -> dict:
         """The non-tensor part of the optimizer state (goes to ``common.pt``)."""
         sd = {"step": self.step_count, "param_groups": [{k: v for k, v in g.items()} for g in self.param_groups]}
@@ -575,6 +580,9 @@ class ChainedOptimizer:
         for o in self.chained_optimizers:
             out.update(o.sharded_state_dict(model_sharded_state_dict, is_loading, **kw))
         return out
+
+    def supports_model_space_state(self) -> bool:
+        return all(getattr(o, "supports_model_space_state", lambda: True)() for o in self.chained_optimizers)
 
     def sharded_common_state(self):
         return [o.sharded_common_state() for o in self.chained_optimizers]

@@ -202,7 +202,8 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
                 if optimizer is not None and not args.no_save_optim:
                     torch.save(_to_cpu(optimizer.state_dict()), os.path.join(base, f"optim_{rank:05d}.pt"))
             else:
-                if optimizer is not None and not args.no_save_optim and hasattr(optimizer, "sharded_common_state"):
+                if (optimizer is not None and not args.no_save_optim and hasattr(optimizer, "sharded_common_state")
+                        and getattr(optimizer, "supports_model_space_state", lambda: True)()):
                     ssd.update(optimizer.sharded_state_dict(ssd))
                     common["optimizer"] = optimizer.sharded_common_state()
                 elif optimizer is not None and not args.no_save_optim:
