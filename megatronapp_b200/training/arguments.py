@@ -584,7 +584,11 @@ _UNSUPPORTED = (
     (lambda a: a.init_model_with_meta_device, "--init-model-with-meta-device is not implemented"),
     (lambda a: a.external_cuda_graph, "--external-cuda-graph is not implemented; use --enable-cuda-graph"),
     (lambda a: a.pipeline_model_parallel_comm_backend == "ucc", "the UCC pipeline backend is not available; p2p runs on NCCL/gloo channels"),
-    (lambda a: a.non_persistent_local_ckpt_dir is not None, "local non-persistent checkpoints are not implemented"),
+    (lambda a: a.non_persistent_ckpt_type == "local" and not a.non_persistent_local_ckpt_dir,
+     "--non-persistent-ckpt-type local needs --non-persistent-local-ckpt-dir"),
+    (lambda a: a.replication and (a.non_persistent_ckpt_type != "local" or not a.replication_jump),
+     "--replication requires --non-persistent-ckpt-type local and --replication-jump"),
+    (lambda a: a.non_persistent_ckpt_type == "in_memory", "in-memory non-persistent checkpoints are not implemented (use local / global)"),
     (lambda a: a.encoder_tensor_model_parallel_size not in (0, a.tensor_model_parallel_size),
      "a different tensor-parallel size for the encoder (--encoder-tensor-model-parallel-size) is not implemented"),
     (lambda a: a.optimizer_cpu_offload and not (0.0 < a.optimizer_offload_fraction <= 1.0),

@@ -131,6 +131,20 @@ def _to_cpu(obj):
     return obj
 
 
+_LOCAL_MGR = None
+
+
+def local_checkpoint_manager(args):
+    """``--non-persistent-ckpt-type local``: the per-rank, node-local checkpoint manager (one per process)."""
+    global _LOCAL_MGR
+    if _LOCAL_MGR is None or _LOCAL_MGR.dir != args.non_persistent_local_ckpt_dir:
+        from .local_checkpoint import LocalCheckpointManager
+
+        _LOCAL_MGR = LocalCheckpointManager(args.non_persistent_local_ckpt_dir, bool(getattr(args, "replication", False)),
+                                            getattr(args, "replication_jump", None), getattr(args, "replication_factor", 2))
+    return _LOCAL_MGR
+
+
 def non_persistent_dir(args) -> str:
     """Where ``--non-persistent-ckpt-type global`` checkpoints go: frequent, overwritten-in-place safety checkpoints next
     to (not instead of) the persistent ones (reference checkpointing.py: ``non_persistent_ckpt``)."""
@@ -143,6 +157,18 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floati
         from .global_vars import get_args
 
         args = get_args()
+    if non_persistent_ckpt and getattr(args, "non_persistent_ckpt_type", None) == "local":
+        # every rank keeps its own complete state on node-local storage (no shared file system, no gather)
+        chunks = model if isinstance(model, (list, tuple)) else [model]
+        if any(_fsdp_wrapper(m) is not None for m in chunks):
+            raise NotImplementedError("local non-persistent checkpoints with ZeRO-3 wrappers: use --non-persistent-ckpt-type global")
+        sd = generate_state_dict(args, chunks, optimizer, opt_param_scheduler, get_rng_state(), iteration,
+                                 num_floating_point_operations_so_far)
+        sd["parallel_layout"] = _layout_tag()
+        local_checkpoint_manager(args).save(_to_cpu(sd), iteration)
+        if not dist.is_initialized() or dist.get_rank() == 0:
+            print(f"  successfully saved local checkpoint from iteration {iteration:7d} to {args.non_persistent_local_ckpt_dir}", flush=True)
+        return
     if non_persistent_ckpt:
         # same writer, different root; once the new one is complete the previous non-persistent iteration is removed
         import copy
@@ -318,16 +344,43 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
             if it_np > it_p:
                 load_dir = npd
     tracker = get_checkpoint_tracker_filename(load_dir) if load_dir else None
-    if not load_dir or not os.path.isfile(tracker):
+    local_sd = None
+    if (load_arg == "load" and getattr(args, "non_persistent_ckpt_type", None) == "local" and args.non_persistent_local_ckpt_dir
+            and not getattr(args, "ckpt_step", None) and not args.finetune):
+        # node-local safety checkpoint: used when it is newer than the last persistent one and every rank's state is
+        # retrievable (own file or a replica); same parallel layout only
+        mgr = local_checkpoint_manager(args)
+        it_local = mgr.find_latest()
+        it_p = read_metadata(tracker)[0] if (tracker and os.path.isfile(tracker)) else -1
+        if it_local > it_p:
+            cand = mgr.load(it_local)
+            if cand.get("parallel_layout") in (None, _layout_tag()):
+                local_sd = cand
+            elif not dist.is_initialized() or dist.get_rank() == 0:
+                print(f"WARNING: local checkpoint of iteration {it_local} was written under layout {cand.get('parallel_layout')}; "
+                      f"current layout {_layout_tag()}: ignoring it", flush=True)
+    if local_sd is None and (not load_dir or not os.path.isfile(tracker)):
         if getattr(args, "exit_on_missing_checkpoint", False):
             raise SystemExit(f">> no checkpoint found in {load_dir}; exiting")
         return 0, 0
-    iteration, release = read_metadata(tracker)
-    if getattr(args, "ckpt_step", None):
-        iteration = args.ckpt_step
-    base = get_checkpoint_name(load_dir, iteration, release, return_base_dir=True)
-    is_sharded = os.path.exists(os.path.join(base, "metadata.json"))
-    if is_sharded and torch_dist.is_torch_dist_checkpoint(base):
+    if local_sd is not None:
+        iteration, release, sd, is_sharded, base = int(local_sd["iteration"]), False, local_sd, False, None
+        load_dir = f"{args.non_persistent_local_ckpt_dir} (local)"
+        for i, m in enumerate(model):
+            _unwrap(m).load_state_dict(sd["model" if len(model) == 1 else f"model{i}"], strict=strict)
+        if optimizer is not None and not args.no_load_optim and "optimizer" in sd:
+            optimizer.load_state_dict(sd["optimizer"])
+        elif optimizer is not None:
+            optimizer.reload_model_params()
+    else:
+        iteration, release = read_metadata(tracker)
+        if getattr(args, "ckpt_step", None):
+            iteration = args.ckpt_step
+        base = get_checkpoint_name(load_dir, iteration, release, return_base_dir=True)
+        is_sharded = os.path.exists(os.path.join(base, "metadata.json"))
+    if local_sd is not None:
+        pass
+    elif is_sharded and torch_dist.is_torch_dist_checkpoint(base):
         # reference layout (.metadata + __*.distcp): model AND optimizer state reshard to the current layout
         sd = torch_dist.load_common_state_dict(base)
         want_opt = optimizer is not None and not args.finetune and not args.no_load_optim and "optimizer" in sd \

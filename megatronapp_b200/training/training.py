@@ -580,8 +580,8 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if (args.save and getattr(args, "non_persistent_save_interval", None) and not saved
                 and iteration % args.non_persistent_save_interval == 0
                 and not (args.save_interval and iteration % args.save_interval == 0)):
-            if args.non_persistent_ckpt_type != "global":
-                raise NotImplementedError("only --non-persistent-ckpt-type global is implemented")
+            if args.non_persistent_ckpt_type not in ("global", "local"):
+                raise NotImplementedError("--non-persistent-ckpt-type must be global or local")
             timers("interval-time").stop()
             checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, nflops, non_persistent_ckpt=True)
             timers("interval-time", log_level=0).start(barrier=True)

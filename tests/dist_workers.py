@@ -588,6 +588,40 @@ def moe_reshard(ep=1, path=None, mode="save", grouped=False):
     return {"out": out.flatten().tolist(), "keys": keys}
 
 
+def local_ckpt_replication(path=None):
+    """3 ranks, replication jump 1 factor 2: every rank's state is also held by its right neighbour.  Rank 1 "loses its
+    node" (its directory is wiped): the latest iteration stays retrievable and rank 1 gets its state back from rank 2;
+    after wiping rank 2 as well the state of rank 1 is gone everywhere -> find_latest falls back to -1."""
+    import shutil
+
+    from megatronapp_b200.training.local_checkpoint import LocalCheckpointManager
+
+    rank, world = _setup()
+    mine = os.path.join(path, f"node{rank}")                      # separate "local disks"
+    mgr = LocalCheckpointManager(mine, replication=True, replication_jump=1, replication_factor=2)
+    out = {"holders": mgr.holders, "sources": mgr.sources}
+    for it in (3, 4):
+        mgr.save({"iteration": it, "w": torch.full((4,), float(10 * rank + it))}, it)
+    out["kept"] = sorted(os.listdir(mine))
+    out["latest"] = mgr.find_latest()
+    dist.barrier()
+    if rank == 1:
+        shutil.rmtree(mine)
+        os.makedirs(mine)
+    dist.barrier()
+    out["latest_after_loss"] = mgr.find_latest()
+    st = mgr.load(out["latest_after_loss"])
+    out["restored"] = [int(st["iteration"]), float(st["w"][0])]
+    out["own_file_back"] = os.path.exists(os.path.join(mine, "iter_0000004", f"rank_{rank:05d}.pt"))
+    dist.barrier()
+    if rank in (1, 2):
+        shutil.rmtree(mine)
+        os.makedirs(mine)
+    dist.barrier()
+    out["latest_after_two_losses"] = mgr.find_latest()
+    return out
+
+
 def dpp_compat_transport():
     """The reference's module-function mailbox API over 2 pipeline ranks: non-blocking gets, last->first slot shift."""
     import sys

@@ -225,3 +225,13 @@ def test_moe_checkpoint_reshards_over_expert_parallel_and_grouped(tmp_path):
         res = run_distributed("moe_reshard", world, path=path, mode="load", **kw)
         for r in res:
             assert np.allclose(np.asarray(r["out"]), ref, atol=1e-5), kw
+
+
+def test_local_checkpoint_manager_replication_survives_a_lost_node(tmp_path):
+    res = run_distributed("local_ckpt_replication", 3, path=str(tmp_path))
+    for r, o in enumerate(res):
+        assert o["holders"] == [(r + 1) % 3] and o["sources"] == [(r - 1) % 3]
+        assert o["kept"] == ["iter_0000004"]                                   # older iterations are cleaned up
+        assert o["latest"] == 4 and o["latest_after_loss"] == 4
+        assert o["restored"] == [4, float(10 * r + 4)] and o["own_file_back"]
+        assert o["latest_after_two_losses"] == -1                              # rank 1's state had one holder (rank 2): both gone

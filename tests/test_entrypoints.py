@@ -337,7 +337,7 @@ def test_non_persistent_checkpoints_cover_the_gap_between_persistent_ones(tmp_pa
                            env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
         out = p.stdout + p.stderr
         assert p.returncode == 0, out[-3000:]
-        return out, re.findall(r"\\] iteration\\s+(\\d+)/.*?lm loss: ([0-9.E+\\-]+)", out)
+        return out, re.findall(r"\] iteration\s+(\d+)/.*?lm loss: ([0-9.E+\-]+)", out)
 
     _, straight = run()
     run("--save", ck, "--save-interval", "4", "--non-persistent-save-interval", "1", "--non-persistent-ckpt-type", "global",
@@ -346,7 +346,36 @@ def test_non_persistent_checkpoints_cover_the_gap_between_persistent_ones(tmp_pa
     shutil.rmtree(os.path.join(ck, "iter_0000005"))                  # "crash": the exit checkpoint never made it to disk
     open(os.path.join(ck, "latest_checkpointed_iteration.txt"), "w").write("4")
     out, resumed = run("--load", ck, "--non-persistent-ckpt-type", "global")
-    assert "non_persistent at iteration 5" in out and resumed == straight[5:]
+    assert len(straight) == 6 and "non_persistent at iteration 5" in out and resumed == straight[5:]
+
+
+def test_local_non_persistent_checkpoint_resumes_exactly(tmp_path):
+    """``--non-persistent-ckpt-type local``: per-rank state on node-local storage every iteration; after a crash at
+    iteration 5 (last persistent checkpoint: 4) the run resumes from the local iteration-5 state and reproduces the
+    uninterrupted losses."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="",
+               OMP_NUM_THREADS="2")
+    base = COMMON + ["--train-iters", "6", "--attention-dropout", "0", "--hidden-dropout", "0", "--lr", "1e-2",
+                     "--lr-decay-iters", "100"]
+    ck, loc = str(tmp_path / "ck"), str(tmp_path / "local_ssd")
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *base, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-3000:]
+        return out, re.findall(r"\] iteration\s+(\d+)/.*?lm loss: ([0-9.E+\-]+)", out)
+
+    _, straight = run()
+    np_args = ["--non-persistent-save-interval", "1", "--non-persistent-ckpt-type", "local", "--non-persistent-local-ckpt-dir", loc]
+    run("--save", ck, "--save-interval", "4", *np_args, "--exit-interval", "5")
+    assert os.listdir(loc) == ["iter_0000005"]
+    import shutil
+
+    shutil.rmtree(os.path.join(ck, "iter_0000005"), ignore_errors=True)   # "crash": the exit checkpoint never made it to disk
+    open(os.path.join(ck, "latest_checkpointed_iteration.txt"), "w").write("4")
+    out, resumed = run("--load", ck, *np_args)
+    assert len(straight) == 6 and "(local) at iteration 5" in out and resumed == straight[5:]
 
 
 def test_t5_trains_on_a_preprocessed_sentence_corpus(tmp_path):
