@@ -544,8 +544,12 @@ def attention_varlen(q, k, v, cu_seqlens_q, cu_seqlens_kv=None, scale=None, caus
     """Packed (THD) attention: ``q/k/v [t, h, d]`` hold several sequences back to back, ``cu_seqlens`` their boundaries;
     tokens attend within their own sequence only.  Every sequence runs through ``attention`` (the tcgen05 flash
     kernel when its length qualifies), so no ``t x t`` mask is ever materialised.  Returns ``[t, h, d]``."""
-    cu_kv = cu_seqlens_q if cu_seqlens_kv is None else cu_seqlens_kv
-    bq, bk = [int(x) for x in cu_seqlens_q.tolist()], [int(x) for x in cu_kv.tolist()]
+    if isinstance(cu_seqlens_q, tuple) and len(cu_seqlens_q) == 2 and isinstance(cu_seqlens_q[0], list):
+        bq, bk = cu_seqlens_q                        # host boundaries cached on PackedSeqParams: no device sync
+    else:
+        cu_kv = cu_seqlens_q if cu_seqlens_kv is None else cu_seqlens_kv
+        to_list = lambda t: [int(x) for x in (t.tolist() if torch.is_tensor(t) else t)]  # noqa: E731
+        bq, bk = to_list(cu_seqlens_q), to_list(cu_kv)
     outs = []
     for (q0, q1), (k0, k1) in zip(zip(bq[:-1], bq[1:]), zip(bk[:-1], bk[1:])):
         if q1 == q0:

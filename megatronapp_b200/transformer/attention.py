@@ -96,8 +96,9 @@ class DotProductAttention(MegatronModule):
             if query.shape[1] != 1:
                 raise ValueError("packed sequences expect micro-batch 1 (all sequences concatenated along tokens)")
             causal = str(attn_mask_type or self.attn_mask_type).endswith("causal")
-            o = ops.attention_varlen(query[:, 0], key[:, 0], value[:, 0], packed_seq_params.cu_seqlens_q,
-                                     packed_seq_params.cu_seqlens_kv, self.softmax_scale, causal,
+            host = packed_seq_params.boundaries() if hasattr(packed_seq_params, "boundaries") else None
+            o = ops.attention_varlen(query[:, 0], key[:, 0], value[:, 0], host or packed_seq_params.cu_seqlens_q,
+                                     None if host else packed_seq_params.cu_seqlens_kv, self.softmax_scale, causal,
                                      self.dropout_p if self.training else 0.0, self.training)
             return o.reshape(query.shape[0], 1, self.np * o.shape[-1])
         mask_type = attn_mask_type or self.attn_mask_type
