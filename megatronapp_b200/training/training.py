@@ -489,6 +489,10 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             from .. import ops
 
             ops.set_slow_rank_spin(slow)      # spins in front of every layer, forward and backward
+    if args.async_save and getattr(args, "use_persistent_ckpt_worker", False) and args.ckpt_format == "torch_dist":
+        from .async_utils import init_persistent_async_worker
+
+        init_persistent_async_worker()        # spawn the writer process now, not inside the first save
     exit_flag = False
     start_time = time.time()
     stimer = get_straggler_detector()
