@@ -443,3 +443,46 @@ def test_shipped_sample_corpus_preprocesses_and_trains(tmp_path, family):
     out = p.stdout + p.stderr
     assert p.returncode == 0, out[-3000:]
     assert re.search(r"iteration\s+3/\s+3 \|.*lm loss: [0-9.E+\-]+", out) and "validation loss at the end of training" in out
+
+
+@pytest.mark.parametrize("script", ["gpt_static_inference.py", "gpt_dynamic_inference.py"])
+def test_inference_examples_generate(script, tmp_path):
+    """examples/inference/gpt: static batch and continuous batching (Poisson arrivals) through the CLI, random weights."""
+    import json
+
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_port()), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    out_path = str(tmp_path / "gen.json")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "inference", "gpt", script), "--num-layers", "2", "--hidden-size", "32",
+                        "--num-attention-heads", "4", "--seq-length", "64", "--max-position-embeddings", "64", "--micro-batch-size", "1",
+                        "--tokenizer-type", "NullTokenizer", "--vocab-size", "127", "--distributed-backend", "gloo", "--prompts", "5 9 23 7",
+                        "11 3", "--num-synthetic-prompts", "3", "--synthetic-prompt-length", "6", "--num-tokens-to-generate", "5",
+                        "--incoming-requests-per-sec", "50", "--inference-dynamic-batching-buffer-size-gb", "0.001", "--output-path", out_path],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    rows = json.load(open(out_path))
+    assert len(rows) == 5 and all(len(r["tokens"]) == 5 for r in rows)
+
+
+def test_trtllm_export_examples(tmp_path):
+    """single-device export to an inference layout (tp 2) and the on-device distributed export on 2 gloo ranks"""
+    import json
+
+    single, distd = str(tmp_path / "single"), str(tmp_path / "dist")
+    ex = os.path.join(ROOT, "examples", "export", "trtllm_export")
+    p = subprocess.run([sys.executable, os.path.join(ex, "single_device_export", "gpt_single_device_cpu_export.py"), "--out", single,
+                        "--export-tp", "2"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    conf = json.load(open(os.path.join(single, "config.json")))
+    assert conf["mapping"]["tp_size"] == 2 and sorted(f for f in os.listdir(single) if f.startswith("rank")) == ["rank0.safetensors", "rank1.safetensors"]
+    assert json.load(open(os.path.join(single, "build_config.json")))["plugin_config"]["paged_kv_cache"] is True
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        str(_port()), os.path.join(ex, "distributed_export", "gpt_distributed_gpu_export.py"), "--tensor-model-parallel-size", "2",
+                        "--out", distd], cwd=str(tmp_path), env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    import torch
+
+    from safetensors.torch import load_file
+
+    a, b = load_file(os.path.join(single, "rank1.safetensors")), torch.load(os.path.join(distd, "rank1.pt"))
+    assert sorted(a) == sorted(b) and all(a[k].shape == b[k].shape for k in a)
