@@ -14,6 +14,42 @@
 
 #include "b200_api.h"
 
+#undef mmap
+#undef munmap
+#include <sys/stat.h>
+
+#include <map>
+#include <mutex>
+
+// one mapping per shm object per process (see fake_cuda/shm_alias.h)
+namespace {
+struct Alias { void* addr; size_t len; int refs; };
+std::map<ino_t, Alias> g_alias;
+std::mutex g_alias_mu;
+}  // namespace
+
+void* harness_mmap(void* addr, size_t len, int prot, int flags, int fd, off_t off) {
+  struct stat st;
+  if (fd < 0 || fstat(fd, &st) != 0) return mmap(addr, len, prot, flags, fd, off);
+  std::lock_guard<std::mutex> g(g_alias_mu);
+  auto it = g_alias.find(st.st_ino);
+  if (it != g_alias.end()) { it->second.refs++; return it->second.addr; }
+  void* p = mmap(addr, len, prot, flags, fd, off);
+  if (p != MAP_FAILED) g_alias[st.st_ino] = {p, len, 1};
+  return p;
+}
+
+int harness_munmap(void* addr, size_t len) {
+  std::lock_guard<std::mutex> g(g_alias_mu);
+  for (auto it = g_alias.begin(); it != g_alias.end(); ++it)
+    if (it->second.addr == addr) {
+      if (--it->second.refs > 0) return 0;
+      g_alias.erase(it);
+      break;
+    }
+  return munmap(addr, len);
+}
+
 namespace b200 {
 // the doorbell kernel of comm.cu: release-store of the epoch after the payload, on the same "stream"
 void write_flag(uint32_t* flag, uint32_t value, cudaStream_t) { __atomic_store_n(flag, value, __ATOMIC_RELEASE); }

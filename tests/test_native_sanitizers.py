@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_mailbox_is_clean_under_thread_sanitizer(tmp_path):
     exe = str(tmp_path / "mailbox_tsan")
     nat = os.path.join(ROOT, "tests", "native")
-    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I", os.path.join(nat, "fake_cuda"),
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I", os.path.join(nat, "fake_cuda"), "-include", os.path.join(nat, "fake_cuda", "shm_alias.h"),
                             "-I", os.path.join(ROOT, "megatronapp_b200", "csrc"), os.path.join(nat, "mailbox_tsan.cpp"),
                             os.path.join(ROOT, "megatronapp_b200", "csrc", "mailbox.cpp"), "-o", exe, "-lpthread", "-lrt"],
                            capture_output=True, text=True, timeout=300)
