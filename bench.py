@@ -156,12 +156,19 @@ def run_own(args):
     if moe:
         arch.update(ep=ep, etp=etp, moe_grouped=not args.moe_baseline, moe_ffn=F,
                     moe_dispatcher="alltoall" if args.moe_baseline else "flex", moe_aux_loss_coeff=1e-2)
+    recompute_layers, bf16_moments = args.recompute_layers, args.bf16_adam_moments
+    if args.model == "mixtral_8x7b" and args.gpus <= 8 and not args.layers:
+        # 46.7 B parameters on <= 8 x 180 GB: fp32 main grads + fp32 master weights stay, but the Adam moments are kept in
+        # bf16 (precision-aware optimizer) and every layer is recomputed in backward -- the round-2 runs with fp32 moments
+        # went out of memory at 169 GB even with half of the layers recomputed (profiles/README.md)
+        recompute_layers = recompute_layers or L // pp
+        bf16_moments = True
     state = build_gpt_for_bench(L, H, A, S, vocab, mbs, ffn=F, tp=tp, pp=pp, sequence_parallel=tp > 1,
                                 device=f"cuda:{local_rank}", lr=1e-4, fused_tp_comm=not args.no_fused_tp_comm,
                                 use_distributed_optimizer=dp > 1, overlap_grad_reduce=(dp > 1 and not args.no_dp_overlap),
                                 fused_grad_rs=(args.fused_grad_rs and dp > 1 and not moe), dropout=0.0, vpp=vpp, fbd=args.fbd,
                                 fp8="hybrid" if args.fp8 else None, fp8_recipe=args.fp8_recipe,
-                                recompute_layers=args.recompute_layers, **arch)
+                                recompute_layers=recompute_layers, bf16_adam_moments=bf16_moments, **arch)
     if args.fbd:
         from megatronapp_b200.fbd.schedule import install_fbd_schedule
 
@@ -305,12 +312,12 @@ def run_own(args):
             "impl": "megatronapp_b200",
             "config": {"model": args.model, "layers": L, "hidden": H, "heads": A, "ffn": F, "vocab_padded": vocab,
                        "global_batch": global_batch, "micro_batch": mbs, "seq_len": S, "parallelism": par,
-                       "optimizer": "Adam fp32 master + fp32 main grads, clip 1.0",
+                       "optimizer": "Adam fp32 master + fp32 main grads, clip 1.0" + (", bf16 moments" if bf16_moments else ""),
                        "l2_policy": "working set (>=13 GB weights + grads per step) >> 126 MB L2; no explicit flush",
                        "attention_impl": "native" if ops.native_attention_available() else "sdpa-library",
                        "fused_tp_comm": (tp > 1 and not args.no_fused_tp_comm),
                        "fused_gemm_rs": (tp > 1 and not args.no_fused_tp_comm and not args.no_fused_rs),
-                       "recompute_layers": args.recompute_layers,
+                       "recompute_layers": recompute_layers, "adam_moments": "bf16" if bf16_moments else "fp32",
                        "dp_grad_sync": (None if dp == 1 else ("fused-kernel" if (args.fused_grad_rs and not moe) else "nccl")
                                         + ("" if args.no_dp_overlap else "+overlap"))},
             "clocks": clocks,
@@ -420,6 +427,7 @@ def main():
     ap.add_argument("--no-dp-overlap", action="store_true", help="dp>1: reduce-scatter the gradients after backward instead of per bucket")
     ap.add_argument("--fused-grad-rs", action="store_true",
                     help="dp>1: sm_100a bucket reduce-scatter (scale + cast + RS over NVLink peer stores) instead of NCCL")
+    ap.add_argument("--bf16-adam-moments", action="store_true", help="precision-aware optimizer: exp_avg / exp_avg_sq in bf16")
     ap.add_argument("--recompute-layers", type=int, default=0,
                     help="full activation recompute of the first N layers per stage (memory-bound configs, e.g. Mixtral 8x7B on 8 GPUs)")
     ap.add_argument("--detect", action="store_true", help="run the MegaScan detector on the traced steps (rank 0) and report it")

@@ -43,7 +43,7 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
                         use_distributed_optimizer=False, dropout=0.0, vpp=None, overlap_grad_reduce=False,
                         seed=1234, num_experts=None, ep=1, moe_topk=2, fused_grad_rs=False, fp8=None, fp8_recipe="delayed",
                         moe_grouped=False, moe_dispatcher=None, moe_ffn=None, fbd=False, etp=None,
-                        moe_aux_loss_coeff=0.0, fbd_collapse=False, recompute_layers=0) -> BenchState:
+                        moe_aux_loss_coeff=0.0, fbd_collapse=False, recompute_layers=0, bf16_adam_moments=False) -> BenchState:
     if torch.cuda.is_available() and str(device).startswith("cuda"):
         torch.cuda.set_device(torch.device(device) if ":" in str(device) else torch.cuda.current_device())
     if not ps.model_parallel_is_initialized():
@@ -108,7 +108,9 @@ def build_gpt_for_bench(num_layers, hidden, heads, seq, vocab, micro_batch, ffn=
     model = [DistributedDataParallel(config, ddp_cfg, m, disable_bucketing=(i > 0)) for i, m in enumerate(chunks)]
     opt_cfg = OptimizerConfig(lr=lr, weight_decay=0.01, bf16=dtype == torch.bfloat16, fp16=dtype == torch.float16,
                               params_dtype=dtype, use_distributed_optimizer=use_distributed_optimizer,
-                              clip_grad=1.0, adam_beta2=0.95)
+                              clip_grad=1.0, adam_beta2=0.95,
+                              **(dict(use_precision_aware_optimizer=True, exp_avg_dtype=torch.bfloat16,
+                                      exp_avg_sq_dtype=torch.bfloat16) if bf16_adam_moments else {}))
     optimizer = get_megatron_optimizer(opt_cfg, model)
     config.grad_scale_func = optimizer.scale_loss
     config.finalize_model_grads_func = finalize_model_grads
