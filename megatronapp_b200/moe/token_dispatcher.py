@@ -450,7 +450,7 @@ class MoEArenaDispatcher(MoETokenDispatcher):
             x = _GatherFirstDimAutograd.apply(x.contiguous(), self.etp_group)
         send_lay = mops.build_layout(routing_map.contiguous(), probs, 0, self.num_experts, self.config.moe_router_topk, pad=1)
         xp = _EPDispatch.apply(x, probs, self, send_lay)
-        call = self._last_call
+        call, self._last_call = self._last_call, None     # do not keep the call (received tokens, layouts) alive across steps
         rt = RaggedTokens(xp, call.lay, probs)
         rt.ep_call = call
         return rt, call.lay.counts
