@@ -11,7 +11,9 @@ Parity: reference ``core/utils.py get_batch_on_this_cp_rank :1704-1734``, rotary
                  local queries attend with a position mask.
 * ``p2p``        K/V blocks travel around the CP ring (send to next / receive from previous,
                  ``cp - 1`` hops); attention runs on the assembled keys with the same mask.
-* ``a2a+p2p``    hierarchical: treated as ``a2a`` inside a node (one NVSwitch domain).
+* ``a2a+p2p``    hierarchical (``--hierarchical-context-parallel-sizes a p``, ``cp = a * p``): an all-to-all inside groups
+                 of ``a`` consecutive CP ranks trades sequence for heads, then the K/V of the ``p`` outer groups travel around
+                 a ring; without the sizes it degenerates to ``a2a`` over the whole CP group.
 """
 from __future__ import annotations
 
@@ -174,6 +176,9 @@ def cp_attention(q, k, v, scale, causal: bool, comm_type: str = "p2p", dropout_p
     s_full = s_local * cp
     comm_type = (comm_type or "p2p").lower()
     heads_ok = q.shape[1] % cp == 0 and k.shape[1] % cp == 0
+    hcp = ps.get_hierarchical_context_parallel_groups() if comm_type == "a2a+p2p" else None
+    if hcp is not None:
+        return _hierarchical_attention(q, k, v, scale, causal, dropout_p, training, attn_fn, hcp, cp, rank)
     if comm_type in ("a2a", "a2a+p2p") and heads_ok:
         order = gathered_order(s_full, cp, q.device)        # position of each gathered row
         to_nat = torch.argsort(order)                        # gathered row index for each natural position
@@ -190,3 +195,35 @@ def cp_attention(q, k, v, scale, causal: bool, comm_type: str = "p2p", dropout_p
     kpos = gathered_order(s_full, cp, q.device)
     mask = (kpos.unsqueeze(0) > qpos.unsqueeze(1)).view(1, 1, s_local, s_full)   # True = masked out
     return attn_fn(q, kf, vf, scale, False, dropout_p, training, mask)
+
+
+def _hierarchical_attention(q, k, v, scale, causal, dropout_p, training, attn_fn, hcp, cp, rank):
+    """``a2a+p2p``: level 0 (inner, ``a`` ranks) exchanges sequence for heads -- every rank then holds ``h / a`` heads of the
+    ``a * s_local`` tokens owned by its inner group --, level 1 (outer, ``p`` ranks) circulates those K/V blocks around a ring
+    so each rank sees all keys for its heads; a position mask (from the zig-zag chunk ids) keeps causality; the inverse
+    all-to-all restores ``[b, h, s_local, d]``."""
+    inner, outer = hcp
+    a = dist.get_world_size(inner) if not isinstance(inner, ps._SingleGroup) else 1
+    p_ = dist.get_world_size(outer) if not isinstance(outer, ps._SingleGroup) else 1
+    if q.shape[1] % a or k.shape[1] % a:
+        raise ValueError(f"a2a+p2p context parallelism needs the head counts ({q.shape[1]}, {k.shape[1]}) divisible by the inner size {a}")
+    s_local = q.shape[2]
+    s_full = s_local * cp
+    if a > 1:
+        q, k, v = (_SeqToHeads.apply(t.contiguous(), inner, False) for t in (q, k, v))            # [b, h/a, a*s_local, d]
+    if p_ > 1:
+        kf = _RingGatherSeq.apply(k.contiguous(), 2, outer)
+        vf = _RingGatherSeq.apply(v.contiguous(), 2, outer)
+    else:
+        kf, vf = k, v
+    if causal:
+        inner_idx, outer_idx = rank % a, rank // a                                                   # cp rank = outer * a + inner
+        def group_pos(o):                                                                            # rows of inner group o, rank-major
+            return torch.cat([local_positions(s_full, cp, o * a + i, q.device) for i in range(a)])
+        qpos = group_pos(outer_idx)
+        kpos = torch.cat([group_pos(o) for o in range(p_)])
+        mask = (kpos.unsqueeze(0) > qpos.unsqueeze(1)).view(1, 1, qpos.numel(), kpos.numel())
+        o = attn_fn(q, kf, vf, scale, False, dropout_p, training, mask)
+    else:
+        o = attn_fn(q, kf, vf, scale, False, dropout_p, training, None)
+    return _SeqToHeads.apply(o.contiguous(), inner, True) if a > 1 else o

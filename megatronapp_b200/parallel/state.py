@@ -58,6 +58,8 @@ class ParallelState:
             kinds += ["intra_dp_cp", "inter_dp_cp"]
         if topo.fbd:
             kinds += ["fb", "half_dp"]
+        if topo.hcp_sizes:
+            kinds += ["hcp_inner", "hcp_outer"]
         for kind in kinds:
             all_groups = topo.groups(kind)
             mine = None
@@ -172,6 +174,7 @@ def initialize_model_parallel(
         num_distributed_optimizer_instances=num_distributed_optimizer_instances,
         split_rank=(encoder_pipeline_model_parallel_size or pipeline_model_parallel_split_rank or None)
         if pipeline_model_parallel_size > 1 else None,
+        hcp_sizes=tuple(int(x) for x in hierarchical_context_parallel_sizes) if hierarchical_context_parallel_sizes else None,
     )
     backend = dist.get_backend() if (dist.is_available() and dist.is_initialized()) else None
     _STATE = ParallelState(topo, rk, backend=backend,
@@ -246,6 +249,15 @@ get_embedding_group, _embd_world, _embd_rank = _acc("embd")
 get_position_embedding_group, _pe_world, _pe_rank = _acc("pos_embd")
 get_forward_backward_parallel_group, get_forward_backward_parallel_world_size, get_forward_backward_parallel_rank = _acc("fb")
 get_tensor_and_context_parallel_group, get_tensor_and_context_parallel_world_size, get_tensor_and_context_parallel_rank = _acc("tp_cp")
+
+
+def get_hierarchical_context_parallel_groups(check_initialized: bool = True):
+    """``[inner (all-to-all) group, outer (ring) group]`` of this rank (reference ``parallel_state.py`` ``_HIERARCHICAL_CONTEXT_PARALLEL_GROUPS``);
+    ``None`` when ``--hierarchical-context-parallel-sizes`` was not given."""
+    st = get_state()
+    if not st.topo.hcp_sizes:
+        return None
+    return [st.group("hcp_inner"), st.group("hcp_outer")]
 
 
 def _dp_kind(with_context_parallel: bool = False) -> str:

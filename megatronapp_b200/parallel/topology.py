@@ -131,6 +131,9 @@ class Topology:
     fbd_collapse: bool = False
     num_distributed_optimizer_instances: int = 1
     split_rank: int | None = None   # first pipeline stage of the decoder (encoder-decoder models)
+    # hierarchical context parallelism (``--hierarchical-context-parallel-sizes a p``, cp = a * p): level 0 = inner groups of
+    # ``a`` consecutive cp ranks (all-to-all), level 1 = outer groups of ``p`` ranks with the same inner index (p2p ring)
+    hcp_sizes: tuple | None = None
 
     def __post_init__(self):
         if self.split_rank is not None and not (0 < self.split_rank < self.pp):
@@ -166,6 +169,12 @@ class Topology:
             raise ValueError("ep*etp must divide dp*cp*tp")
         if self.vpp is not None and self.vpp > 1 and self.pp < 2:
             raise ValueError("virtual pipeline needs pp >= 2")
+        if self.hcp_sizes:
+            prod = 1
+            for x in self.hcp_sizes:
+                prod *= int(x)
+            if prod != self.cp or len(self.hcp_sizes) != 2:
+                raise ValueError(f"hierarchical context parallel sizes {self.hcp_sizes} must be two levels whose product is cp={self.cp}")
         if self.fbd:
             if dp % 2 != 0:
                 raise ValueError("MegaFBD needs an even data-parallel size")
@@ -291,6 +300,17 @@ class Topology:
             out = []
             for g in d.groups("dp"):
                 out += [g[0::2], g[1::2]]
+            return out
+        if kind in ("hcp_inner", "hcp_outer"):
+            if not self.hcp_sizes:
+                return [[r] for r in range(self.world_size)]
+            a = int(self.hcp_sizes[0])
+            out = []
+            for g in d.groups("cp"):
+                if kind == "hcp_inner":
+                    out += [g[i:i + a] for i in range(0, len(g), a)]
+                else:
+                    out += [g[i::a] for i in range(a)]
             return out
         if kind == "intra_dp_cp":
             n = self.num_distributed_optimizer_instances

@@ -196,14 +196,14 @@ def moe_parity(ep=1, dispatcher="alltoall", grouped=False):
             "grouter": layer.router.weight.grad.flatten().tolist()}
 
 
-def cp_attention_parity(comm="a2a", causal=True):
+def cp_attention_parity(comm="a2a", causal=True, hcp=None):
     """Context-parallel attention (cp = world) vs. full-sequence attention on one rank."""
     from megatronapp_b200 import ops
     from megatronapp_b200.parallel import state as ps
     from megatronapp_b200.parallel.context_parallel import cp_attention, slice_for_cp_rank
 
     rank, world = _setup()
-    ps.initialize_model_parallel(1, 1, context_parallel_size=world)
+    ps.initialize_model_parallel(1, 1, context_parallel_size=world, hierarchical_context_parallel_sizes=hcp)
     torch.manual_seed(0)
     b, h, s, d = 2, 4, 32, 16
     q, k, v = (torch.randn(b, h, s, d, dtype=torch.float64) for _ in range(3))

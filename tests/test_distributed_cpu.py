@@ -122,6 +122,13 @@ def test_context_parallel_attention(comm):
         assert max(r["fwd"], r["dq"], r["dk"], r["dv"]) < 1e-5, r   # reference attention runs in fp32
 
 
+@pytest.mark.parametrize("causal", [True, False])
+def test_hierarchical_context_parallel_attention(causal):
+    """cp 4 = 2 (all-to-all inside) x 2 (K/V ring outside): forward and all three gradients match single-rank attention"""
+    for r in run_distributed("cp_attention_parity", 4, comm="a2a+p2p", hcp=[2, 2], causal=causal):
+        assert max(r["fwd"], r["dq"], r["dk"], r["dv"]) < 1e-5, r
+
+
 def test_fsdp_zero3_matches_unsharded_training():
     for r in run_distributed("fsdp_parity", 2):
         _close(r["losses"], r["ref"], 2e-4)
