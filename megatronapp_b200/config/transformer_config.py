@@ -180,6 +180,7 @@ class TransformerConfig(ModelParallelConfig):
 
     moe_shared_expert_intermediate_size: Optional[int] = None
     moe_shared_expert_overlap: bool = False
+    moe_shared_expert_gate: bool = False
     moe_layer_freq: Union[int, List[int]] = 1
     moe_ffn_hidden_size: Optional[int] = None
     moe_router_load_balancing_type: str = "aux_loss"

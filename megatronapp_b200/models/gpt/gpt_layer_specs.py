@@ -27,8 +27,10 @@ def get_mlp_module_spec(use_te: bool = False, num_experts: Optional[int] = None,
 
     experts = ModuleSpec(module=GroupedMLP if moe_grouped_gemm else SequentialMLP,
                          submodules=MLPSubmodules(linear_fc1=ColumnParallelLinear, linear_fc2=RowParallelLinear))
-    shared = ModuleSpec(module=MLP, submodules=MLPSubmodules(linear_fc1=ColumnParallelLinear,
-                                                             linear_fc2=RowParallelLinear))
+    from ...moe.shared_experts import SharedExpertMLP
+
+    shared = ModuleSpec(module=SharedExpertMLP, params={"gate": False},
+                        submodules=MLPSubmodules(linear_fc1=ColumnParallelLinear, linear_fc2=RowParallelLinear))
     return ModuleSpec(module=MoELayer, submodules=MoESubmodules(experts=experts, shared_experts=shared))
 
 

@@ -52,8 +52,11 @@ class MoELayer(MegatronModule):
         self.experts = build_module(submodules.experts, self.num_local_experts, config)
         self.shared_experts = None
         if config.moe_shared_expert_intermediate_size:
-            self.shared_experts = build_module(submodules.shared_experts, config=config,
-                                               input_size=None) if False else _SharedExpertMLP(config, submodules.shared_experts)
+            from .shared_experts import SharedExpertMLP
+
+            spec = submodules.shared_experts
+            gate = bool(getattr(spec, "params", None) and spec.params.get("gate")) or bool(getattr(config, "moe_shared_expert_gate", False))
+            self.shared_experts = SharedExpertMLP(config, spec.submodules if hasattr(spec, "submodules") else spec, gate=gate)
 
     def set_layer_number(self, n):
         self.layer_number = n
@@ -62,25 +65,12 @@ class MoELayer(MegatronModule):
     def forward(self, hidden_states):
         if self.training and ps.get_tensor_model_parallel_world_size() > 1 and not self.config.sequence_parallel:
             raise ValueError("training MoE with tensor parallelism requires sequence parallelism")
+        if self.shared_experts is not None:
+            self.shared_experts.start(hidden_states)          # side stream under --moe-shared-expert-overlap
         probs, routing_map = self.router(hidden_states)
         dispatched, tokens_per_expert = self.token_dispatcher.token_permutation(hidden_states, probs, routing_map)
         expert_out, mlp_bias = self.experts(dispatched, tokens_per_expert)
         out, mlp_bias = self.token_dispatcher.token_unpermutation(expert_out, mlp_bias)
         if self.shared_experts is not None:
-            out = out + self.shared_experts(hidden_states)
+            out = out + self.shared_experts.finish()
         return out, mlp_bias
-
-
-class _SharedExpertMLP(MegatronModule):
-    def __init__(self, config, spec):
-        super().__init__(config)
-        import copy
-
-        cfg = copy.copy(config)
-        cfg.ffn_hidden_size = config.moe_shared_expert_intermediate_size
-        sub = spec.submodules if hasattr(spec, "submodules") else spec
-        self.mlp = MLP(cfg, sub)
-
-    def forward(self, x):
-        out, bias = self.mlp(x)
-        return out if bias is None else out + bias

@@ -90,6 +90,7 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--moe-ffn-hidden-size", type=int, default=None)
     _add(g, "--moe-shared-expert-intermediate-size", type=int, default=None)
     _add(g, "--moe-shared-expert-overlap", action="store_true")
+    _add(g, "--moe-shared-expert-gate", action="store_true", help="scale the shared expert by a learned sigmoid gate (Qwen2-MoE)")
     _add(g, "--moe-grouped-gemm", action="store_true")
     _add(g, "--moe-use-legacy-grouped-gemm", action="store_true")
     _add(g, "--moe-router-load-balancing-type", type=str, default="aux_loss",

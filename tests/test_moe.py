@@ -77,3 +77,51 @@ def test_upcycled_moe_reproduces_the_dense_model(grouped):
     dense.eval(), moe.eval()
     with torch.no_grad():
         assert torch.allclose(moe(ids, pos, None), dense(ids, pos, None), atol=1e-5)
+
+
+def test_shared_expert_gate_overlap_and_checkpoint_keys():
+    """Shared expert: added to the routed output; with the sigmoid gate it is scaled per token; ``start`` / ``finish`` (the
+    overlap API) give the same result as a direct call; parameters live under the reference's key names."""
+    import torch.nn.functional as F
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.gpt.gpt_layer_specs import get_mlp_module_spec
+    from megatronapp_b200.moe.shared_experts import SharedExpertMLP
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+    from megatronapp_b200.transformer.spec_utils import build_module
+
+    if not ps.model_parallel_is_initialized():
+        ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(3)
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, num_moe_experts=4, moe_router_topk=2,
+                            moe_shared_expert_intermediate_size=48, moe_shared_expert_gate=True, moe_shared_expert_overlap=True,
+                            gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, use_cpu_initialization=True,
+                            params_dtype=torch.float32, kernel_backend="torch")
+    layer = build_module(get_mlp_module_spec(num_experts=4), config=cfg)
+    se = layer.shared_experts
+    assert isinstance(se, SharedExpertMLP) and se.gate_weight.shape == (1, 32)
+    keys = set(layer.state_dict())
+    assert {"shared_experts.linear_fc1.weight", "shared_experts.linear_fc2.weight", "shared_experts.gate_weight"} <= keys
+    x = torch.randn(6, 2, 32)
+    y, _ = layer(x)
+    direct = se(x)
+    se.start(x)
+    assert torch.equal(se.finish(), direct)
+    raw, _ = MLP_forward(se, x)
+    gate = torch.sigmoid(x @ se.gate_weight.t())
+    assert torch.allclose(direct, raw * gate, atol=1e-6)
+    se_off = layer.shared_experts
+    layer.shared_experts = None
+    y_routed, _ = layer(x)
+    layer.shared_experts = se_off
+    assert torch.allclose(y, y_routed + direct, atol=1e-5)
+    y.sum().backward()
+    assert se.gate_weight.grad is not None and se.gate_weight.grad.abs().sum() > 0
+
+
+def MLP_forward(se, x):
+    from megatronapp_b200.transformer.mlp import MLP
+
+    return MLP.forward(se, x)
