@@ -35,6 +35,8 @@ _ALIASES = {
     "megatron.core.transformer.moe.experts": "megatronapp_b200.moe.experts",
     "megatron.core.transformer.moe.moe_utils": "megatronapp_b200.moe.moe_utils",
     "megatron.core.transformer.moe.token_dispatcher": "megatronapp_b200.moe.token_dispatcher",
+    "megatron.core.transformer.moe.shared_experts": "megatronapp_b200.moe.shared_experts",
+    "megatron.core.transformer.moe.upcycling_utils": "megatronapp_b200.moe.upcycling_utils",
     "megatron.core.fusions.fused_layer_norm": "megatronapp_b200.transformer.norms",
     "megatron.core.tensor_parallel.layers": "megatronapp_b200.parallel.tp_layers",
     "megatron.core.tensor_parallel.mappings": "megatronapp_b200.parallel.mappings",
@@ -84,6 +86,20 @@ _ALIASES = {
     "megatron.core.models.common.embeddings.rotary_pos_embedding": "megatronapp_b200.models.common.embeddings",
     "megatron.core.models.common.language_module.language_module": "megatronapp_b200.models.common.language_module",
     "megatron.core.export.trtllm": "megatronapp_b200.export.trtllm",
+    "megatron.core.export.trtllm.trtllm_helper": "megatronapp_b200.export.trtllm.trtllm_helper",
+    "megatron.core.export.trtllm.engine_builder": "megatronapp_b200.export.trtllm.engine_builder",
+    "megatron.core.export.trtllm.engine_builder.trtllm_engine_builder": "megatronapp_b200.export.trtllm.engine_builder.trtllm_engine_builder",
+    "megatron.core.export.trtllm.trtllm_weights_converter": "megatronapp_b200.export.trtllm.trtllm_weights_converter",
+    "megatron.core.export.data_type": "megatronapp_b200.export.data_type",
+    "megatron.core.export.export_config": "megatronapp_b200.export.export_config",
+    "megatron.core.export.model_type": "megatronapp_b200.export.model_type",
+    "megatron.core.datasets.retro": "megatronapp_b200.data.retro",
+    "megatron.core.datasets.retro.config": "megatronapp_b200.data.retro.config",
+    "megatron.core.datasets.retro.db": "megatronapp_b200.data.retro.db",
+    "megatron.core.datasets.retro.index": "megatronapp_b200.data.retro.index",
+    "megatron.core.datasets.retro.query": "megatronapp_b200.data.retro.query",
+    "megatron.legacy.model.vision": "megatronapp_b200.legacy.model.vision",
+    "megatron.training.local_checkpoint": "megatronapp_b200.training.local_checkpoint",
     "megatron.core.post_training.modelopt": "megatronapp_b200.post_training.quantization",
     "megatron.legacy.model": "megatronapp_b200.legacy.model",
     "megatron.legacy.model.biencoder_model": "megatronapp_b200.legacy.model.biencoder_model",

@@ -207,8 +207,8 @@ class TRTLLMHelper:
 
         * default: ``model_state_dict`` is the full canonical model; one entry per ``tp x pp`` export rank;
         * ``on_device_distributed_conversion``: ``model_state_dict`` is THIS training rank's shard; one entry (this rank)."""
-        from .data_type import DataType
-        from .export_config import ExportConfig
+        from ..data_type import DataType
+        from ..export_config import ExportConfig
 
         dt = DataType.of(dtype)
         if on_device_distributed_conversion:
@@ -248,7 +248,7 @@ class TRTLLMHelper:
         cfg["quantization"] = {"quant_algo": "FP8" if fp8 else None, "kv_cache_quant_algo": "FP8" if fp8_kv else None}
 
     def build_and_save_engine(self, engine_dir: str, trtllm_model_weights: Dict, trtllm_model_config: Dict, **kw):
-        from .trtllm_engine_builder import TRTLLMEngineBuilder
+        from ..trtllm_engine_builder import TRTLLMEngineBuilder
 
         return TRTLLMEngineBuilder.build_and_save_engine(engine_dir, trtllm_model_weights, trtllm_model_config, **kw)
 
@@ -262,7 +262,7 @@ class DistributedTRTLLMConverter:
 
     def __init__(self, helper: TRTLLMHelper, tp_rank: Optional[int] = None, tp_size: Optional[int] = None, pp_rank: Optional[int] = None,
                  pp_size: Optional[int] = None, tp_all_reduce=None):
-        from ..parallel import state as ps
+        from ...parallel import state as ps
 
         init = ps.model_parallel_is_initialized()
         self.h = helper
