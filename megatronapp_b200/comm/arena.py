@@ -146,9 +146,11 @@ class TPFusedComm:
         # 0 = auto (cta_group::2 kernel when the shape allows), 128 / 256 = force the 1-CTA kernel (A/B measurements)
         self.block_n = int(os.environ.get("B200_FUSED_BLOCK_N", "0"))
         self.calls = {"ag": 0, "rs": 0, "embed": 0}
-        # K14: vocab-parallel embedding lookup fused with the sequence-parallel scatter (B200_FUSED_EMBED=0: F.embedding +
-        # mask + NCCL reduce-scatter)
-        self.use_fused_embed = os.environ.get("B200_FUSED_EMBED", "1") == "1"
+        # K14: vocab-parallel embedding lookup fused with the sequence-parallel scatter.  Kernel-level it is bit-exact and
+        # 2.6x faster than F.embedding + mask + NCCL reduce-scatter (profiles/r2_bucket_rs_embed_2gpu.json), but the in-model
+        # path (autograd backward through the tied embedding) has not run a training step on hardware yet, and it saves
+        # ~0.1 ms per step: opt-in (B200_FUSED_EMBED=1) until it has.
+        self.use_fused_embed = os.environ.get("B200_FUSED_EMBED", "0") == "1"
         self.embed_ctas = 32
         self._embed = None
         ext = ops.ext()
