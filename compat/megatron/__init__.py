@@ -81,6 +81,14 @@ _ALIASES = {
     "megatron.core.models.vision.radio": "megatronapp_b200.models.vision.radio",
     "megatron.core.models.vision.multimodal_projector": "megatronapp_b200.models.vision.multimodal_projector",
     "megatron.core.models.multimodal.llava_model": "megatronapp_b200.models.multimodal.llava_model",
+    "megatron.core.models.multimodal.llava_spec": "megatronapp_b200.models.multimodal.llava_spec",
+    "megatron.core.models.multimodal.context_parallel": "megatronapp_b200.models.multimodal.context_parallel",
+    "megatron.core.models.vision.vit_layer_specs": "megatronapp_b200.models.vision.vit_layer_specs",
+    "megatron.core.models.huggingface": "megatronapp_b200.models.huggingface",
+    "megatron.core.models.huggingface.module": "megatronapp_b200.models.huggingface.module",
+    "megatron.core.models.huggingface.clip_model": "megatronapp_b200.models.huggingface.clip_model",
+    "megatron.core.models.huggingface.qwen_model": "megatronapp_b200.models.huggingface.qwen_model",
+    "megatron.core.models.common.vision_module.vision_module": "megatronapp_b200.models.common.vision_module.vision_module",
     "megatron.core.models.retro": "megatronapp_b200.models.retro",
     "megatron.core.models.common.embeddings.relative_pos_embedding": "megatronapp_b200.models.common.embeddings",
     "megatron.core.models.common.embeddings.rotary_pos_embedding": "megatronapp_b200.models.common.embeddings",

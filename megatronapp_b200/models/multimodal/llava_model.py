@@ -54,7 +54,14 @@ class LLaVAModel(MegatronModule):
                 scatter_embedding_sequence_parallel=False)
             self.share_embeddings_and_output_weights = self.language_model.share_embeddings_and_output_weights
         if add_encoder:
-            if vision_model_type == "radio":
+            if str(vision_model_type).startswith("hf://"):
+                # a transformers vision tower used as is (reference core/models/huggingface): CLIP / SigLIP
+                from ..huggingface import build_hf_model
+
+                self.vision_model = build_hf_model(vision_transformer_config, vision_model_type)
+                if self.vision_model.hidden_size:
+                    vision_transformer_config.hidden_size = self.vision_model.hidden_size
+            elif vision_model_type == "radio":
                 from ..vision.radio import RADIOViTModel
 
                 self.vision_model = RADIOViTModel(vision_transformer_config, vision_transformer_layer_spec, img_h=img_h,
@@ -70,6 +77,10 @@ class LLaVAModel(MegatronModule):
             self.vision_projection = MultimodalProjector(vision_projection_config, vision_projection_layer_spec,
                                                          vision_projection_type, vision_transformer_config.hidden_size)
         self.vision_model_type = vision_model_type
+        if str(vision_model_type).startswith("hf://"):
+            from ..huggingface import get_hf_model_type
+
+            vision_model_type = get_hf_model_type(vision_model_type)                 # "clip" / "siglip": class-token accounting
         self.img_seq_len = get_num_image_embeddings(img_h, img_w, patch_dim, vision_model_type, drop_vision_class_token,
                                                     class_token_len or (8 if vision_model_type == "radio" else 1),
                                                     pixel_shuffle)

@@ -520,3 +520,76 @@ def test_mrope_reduces_to_rope_for_text_and_separates_streams():
     ang = torch.atan2(t2[..., half + 2:half + 5], t2[..., 2:5])
     ang_ref = torch.atan2(table[..., half + 2:half + 5], table[..., 2:5])
     assert torch.allclose(torch.remainder(ang[1], 6.283185307), torch.remainder(2 * ang_ref[1], 6.283185307), atol=1e-4)
+
+
+def test_huggingface_towers_and_llava_with_an_hf_vision_encoder(tmp_path):
+    """``core/models/huggingface``: a transformers CLIP vision tower (config-only directory -> random weights, no download) is
+    used as LLaVA's image encoder through ``hf://``; a Qwen2 causal LM wraps as a language model; the multimodal
+    sequence-parallel / context-parallel padding helpers give the reference's values."""
+    import json
+
+    import torch
+    from transformers import CLIPVisionConfig, Qwen2Config
+
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatronapp_b200.models.huggingface import build_hf_model, get_hf_model_type
+    from megatronapp_b200.models.multimodal.context_parallel import get_packed_seq_params, get_padding
+    from megatronapp_b200.models.multimodal.llava_model import LLaVAModel
+    from megatronapp_b200.models.multimodal.llava_spec import decoder_model_with_local_default_spec
+    from megatronapp_b200.models.vision.vit_layer_specs import get_vit_layer_with_local_spec
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.parallel.random import model_parallel_cuda_manual_seed
+
+    if not ps.model_parallel_is_initialized():
+        ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(11)
+    torch.manual_seed(0)
+    vdir = tmp_path / "clip"
+    vdir.mkdir()
+    vc = CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4, image_size=28, patch_size=14)
+    d = vc.to_dict()
+    d["architectures"] = ["CLIPVisionModel"]
+    (vdir / "config.json").write_text(json.dumps(d))
+    assert get_hf_model_type(f"hf://{vdir}") == "clip"
+    kw = dict(use_cpu_initialization=True, params_dtype=torch.float32, kernel_backend="torch", hidden_dropout=0.0, attention_dropout=0.0)
+    lcfg = TransformerConfig(num_layers=2, hidden_size=48, num_attention_heads=4, **kw)
+    vcfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, **kw)
+    pcfg = TransformerConfig(num_layers=1, hidden_size=48, num_attention_heads=4, ffn_hidden_size=64, **kw)
+    tower = build_hf_model(vcfg, f"hf://{vdir}")
+    img = torch.randn(2, 3, 28, 28)
+    feats = tower(img)
+    assert feats.shape == (2, 4 + 1, 32)                                       # 2x2 patches + class token
+    from megatronapp_b200.models.vision.multimodal_projector import MultimodalProjector  # noqa: F401
+    from megatronapp_b200.transformer.mlp import MLPSubmodules
+    from megatronapp_b200.parallel.tp_layers import ColumnParallelLinear, RowParallelLinear
+
+    m = LLaVAModel(lcfg, decoder_model_with_local_default_spec(), 128, 64, vcfg, get_vit_layer_with_local_spec(), True, pcfg,
+                   MLPSubmodules(linear_fc1=ColumnParallelLinear, linear_fc2=RowParallelLinear), vision_projection_type="mlp",
+                   img_h=28, img_w=28, patch_dim=14, vision_model_type=f"hf://{vdir}", image_token_index=5)
+    assert m.img_seq_len == 4                                                   # class token dropped
+    ids = torch.randint(6, 128, (2, 12))
+    ids[:, 3] = 5
+    labels = torch.randint(6, 128, (2, 12))
+    out = m(img, ids, torch.arange(12).unsqueeze(0).expand(2, -1), labels=labels, loss_mask=torch.ones(2, 12),
+            num_image_tiles=torch.ones(2, dtype=torch.int))
+    loss = out[0] if isinstance(out, tuple) else out
+    assert loss.shape[0] == 2 and loss.shape[1] == 12 + 4 - 1 and torch.isfinite(loss).all()
+    loss.float().mean().backward()
+    assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in m.vision_model.parameters())
+    # Qwen2 as a wrapped language model
+    qdir = tmp_path / "qwen"
+    qdir.mkdir()
+    qd = Qwen2Config(vocab_size=128, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                     num_key_value_heads=2, max_position_embeddings=64).to_dict()
+    qd["architectures"] = ["Qwen2ForCausalLM"]
+    (qdir / "config.json").write_text(json.dumps(qd))
+    q = build_hf_model(lcfg, f"hf://{qdir}")
+    emb = q.embedding(ids)
+    assert emb.shape == (12, 2, 32) and q(decoder_input=emb).shape == (2, 12, 128) and q(input_ids=ids, labels=labels).shape == (2, 12)
+    # padding rules
+    assert get_padding(1001, 1, 4, True) == 3 and get_padding(1001, 2, 1, False) == 3 and get_padding(1001, 2, 4, True) == 7
+    assert get_padding(1000, 1, 4, True, decoder_tp_comm_overlap=True, decoder_seq_len=1024) == 24 and get_padding(7, 1, 1, False) == 0
+    ps_ = get_packed_seq_params(torch.zeros(2, 10, dtype=torch.long), img_seq_len=6, padding_needed=4, cp_size=2)
+    assert ps_.qkv_format == "thd" and ps_.cu_seqlens_q.tolist() == [0, 12, 24] and ps_.cu_seqlens_q_padded.tolist() == [0, 16, 32]
+    assert get_packed_seq_params(torch.zeros(2, 10, dtype=torch.long), 6, 0, 1).qkv_format == "sbhd"
