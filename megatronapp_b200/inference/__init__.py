@@ -2,3 +2,4 @@ from .core import (GPTInferenceWrapper, InferenceParams, InferenceRequest, Sampl
                    Scheduler, StaticInferenceContext, StaticInferenceEngine, Status, T5InferenceWrapper, TextGenerationController,
                    VLMInferenceWrapper, sample_from_logits)
 from .dynamic import BlockAllocator, DynamicInferenceContext, DynamicInferenceEngine  # noqa: F401
+from .async_stream import AsyncStream, TokenStream  # noqa: F401,E402

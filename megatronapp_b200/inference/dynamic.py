@@ -195,6 +195,8 @@ class _Running:
     n_prompt: int
     fed: int = 0                      # tokens already forwarded (== kv_len)
     logprobs: List[float] = field(default_factory=list)
+    stream: Optional[object] = None   # TokenStream: every sampled token is published as it is produced
+    cancelled: bool = False
 
 
 class DynamicInferenceEngine:
@@ -223,12 +225,41 @@ class DynamicInferenceEngine:
 
     # -- API -----------------------------------------------------------------------
     def add_request(self, prompt: str, sampling_params: Optional[SamplingParams] = None,
-                    prompt_tokens: Optional[List[int]] = None) -> str:
+                    prompt_tokens: Optional[List[int]] = None, stream=None) -> str:
         rid = str(next(self._ids))
         toks = list(prompt_tokens) if prompt_tokens is not None else self.tokenizer.tokenize(prompt)
         req = InferenceRequest(rid, prompt, sampling_params or SamplingParams(), toks, time.time())
-        self.waiting[rid] = _Running(req, list(toks), len(toks))
+        self.waiting[rid] = _Running(req, list(toks), len(toks), stream=stream)
+        if stream is not None:
+            stream.request_id, stream._cancel = rid, self.cancel_request
         return rid
+
+    def cancel_request(self, rid: str) -> None:
+        """Drop a request (a streaming client went away): it leaves the batch at the next step boundary."""
+        r = self.running.get(rid) or self.waiting.get(rid)
+        if r is not None:
+            r.cancelled = True
+
+    def generate_stream(self, prompt: str, sampling_params: Optional[SamplingParams] = None,
+                        prompt_tokens: Optional[List[int]] = None):
+        """Synchronous token streaming: yields ``{"token", "text", "logprob"}`` as soon as a token is sampled, stepping the
+        engine itself (stand-alone use) or reading from the serving loop's stream (``serving()``); other requests keep
+        sharing the steps."""
+        from .async_stream import TokenStream
+
+        st = TokenStream()
+        if self.serving() and threading.current_thread() is not self._loop_thread:
+            toks = list(prompt_tokens) if prompt_tokens is not None else self.tokenizer.tokenize(prompt)
+            self._inbox.put((prompt, sampling_params or SamplingParams(), toks, [], threading.Event(), st))
+            yield from st
+            return
+        self.add_request(prompt, sampling_params, prompt_tokens, stream=st)
+        while not st.finished:
+            self.step()
+            while not st._q.empty():
+                item = st._q.get_nowait()
+                if isinstance(item, dict):
+                    yield item
 
     def has_unfinished_requests(self) -> bool:
         return bool(self.waiting) or bool(self.running)
@@ -288,12 +319,13 @@ class DynamicInferenceEngine:
                 except queue.Empty:
                     pass
             box = [[(p, sp, toks) for p, sp, toks, *_ in new], self._stop]
+            streams = [(n[5] if len(n) > 5 else None) for n in new]
             if multi:
                 dist.broadcast_object_list(box, src=0)
             if box[1]:
                 return
             for i, (prompt, sp, toks) in enumerate(box[0]):
-                rid = self.add_request(prompt, sp, toks)
+                rid = self.add_request(prompt, sp, toks, stream=streams[i] if (rank0 and i < len(streams)) else None)
                 if rank0:
                     new[i][3].append(rid)                      # hand the id back to the submitting thread
                     self._done[rid] = new[i][4]
@@ -420,7 +452,10 @@ class DynamicInferenceEngine:
             r.tokens.append(new)
             r.req.status = Status.ACTIVE_AND_GENERATING_TOKENS
             n_gen = len(r.tokens) - r.n_prompt
-            if new == eod or n_gen >= p.num_tokens_to_generate or len(r.tokens) >= ctx.max_sequence_length:
+            if r.stream is not None and new != eod:
+                r.stream.put({"token": new, "text": self.tokenizer.detokenize([new]),
+                              "logprob": r.logprobs[-1] if (p.return_log_probs and r.logprobs) else None})
+            if new == eod or n_gen >= p.num_tokens_to_generate or len(r.tokens) >= ctx.max_sequence_length or r.cancelled:
                 gen = r.tokens[r.n_prompt:]
                 r.req.generated_tokens = torch.tensor(gen, dtype=torch.long)
                 r.req.generated_length = len(gen)
@@ -431,4 +466,6 @@ class DynamicInferenceEngine:
                 self.running.pop(rid)
                 self.completed[rid] = r.req
                 finished.append(r.req)
+                if r.stream is not None:
+                    r.stream.finish(r.req)
         return finished

@@ -184,6 +184,8 @@ class MegatronServer:
                 err = _validate(inner)
                 if err:
                     return self._send(400, {"error": err})
+                if req.get("stream"):
+                    return self._stream_completion(req, inner, prompts)
                 out = run_generate(engine, inner)
                 echo = bool(req.get("echo", False))
                 choices = []
@@ -194,6 +196,42 @@ class MegatronServer:
                     choices.append(c)
                 self._send(200, {"object": "text_completion", "model": req.get("model", "megatronapp_b200"),
                                  "choices": choices})
+
+            def _stream_completion(self, req, inner, prompts):
+                """``"stream": true``: server-sent events, one ``data: {choices: [{text}]}`` line per generated token, then
+                ``data: [DONE]`` (OpenAI wire format).  The dynamic engine publishes tokens as they are sampled while other
+                clients keep sharing its steps; the static engine generates first and then replays the tokens."""
+                if len(prompts) != 1:
+                    return self._send(400, {"error": "streaming takes exactly one prompt"})
+                params = SamplingParams(temperature=inner["temperature"], top_k=inner["top_k"], top_p=inner["top_p"],
+                                        return_log_probs=inner["logprobs"], num_tokens_to_generate=inner["tokens_to_generate"])
+                self.send_response(200)
+                self.send_header("Content-Type", "text/event-stream")
+                self.send_header("Cache-Control", "no-cache")
+                self.end_headers()
+
+                def emit(obj):
+                    self.wfile.write(("data: " + (obj if isinstance(obj, str) else json.dumps(obj)) + "\n\n").encode())
+                    self.wfile.flush()
+
+                model = req.get("model", "megatronapp_b200")
+                try:
+                    if hasattr(engine, "generate_stream"):
+                        chunks = engine.generate_stream(prompts[0], params)
+                    else:
+                        res = run_generate(engine, inner)
+                        tok = engine.controller.tokenizer
+                        n_prompt = len(tok.tokenize(prompts[0]))
+                        chunks = ({"token": t, "text": tok.detokenize([t]), "logprob": None} for t in res["tokens"][0][n_prompt:])
+                    for ch in chunks:
+                        c = {"index": 0, "text": ch["text"], "finish_reason": None}
+                        if ch.get("logprob") is not None:
+                            c["logprobs"] = {"token_logprobs": [float(ch["logprob"])]}
+                        emit({"object": "text_completion", "model": model, "choices": [c]})
+                    emit({"object": "text_completion", "model": model, "choices": [{"index": 0, "text": "", "finish_reason": "length"}]})
+                    emit("[DONE]")
+                except (BrokenPipeError, ConnectionResetError):
+                    pass                                  # client went away: the generator's close() cancels the request
 
             do_POST = do_PUT
 

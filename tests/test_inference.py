@@ -1,5 +1,6 @@
 """Inference: KV-cache decode == full recompute, sampling rules, scheduler, REST + WS servers."""
 import json
+import threading
 import time
 import urllib.request
 
@@ -193,6 +194,67 @@ def test_dynamic_engine_behind_rest_server(engine):
         out = json.loads(urllib.request.urlopen(req, timeout=30).read())
         ref = eng.generate(["1 2 3"], SamplingParams(top_k=1, num_tokens_to_generate=4))[0]
         assert out["tokens"][0][3:] == ref.generated_tokens.tolist()
+    finally:
+        srv.shutdown()
+
+
+def test_token_streaming_engine_asyncio_and_sse(engine):
+    """Streaming: tokens are published as they are sampled -- (a) synchronous generator on a stand-alone dynamic engine,
+    (b) asyncio consumer of a TokenStream fed by the serving loop, (c) server-sent events from ``/v1/completions`` with
+    ``"stream": true`` (dynamic engine) and from the static engine; every path yields the greedy continuation."""
+    import asyncio
+
+    from megatronapp_b200.inference import DynamicInferenceEngine, TokenStream
+    from megatronapp_b200.inference.server import MegatronServer
+
+    eng, model = engine
+    sp = SamplingParams(top_k=1, num_tokens_to_generate=5, return_log_probs=True)
+    ref = eng.generate(["5 9 23 7"], SamplingParams(top_k=1, num_tokens_to_generate=5))[0].generated_tokens.tolist()
+    dyn = DynamicInferenceEngine(model, NullTokenizer(127), max_sequence_length=64, num_blocks=32, block_size=4,
+                                 max_tokens_per_step=6, max_requests=3)
+    other = dyn.add_request("11 3", SamplingParams(top_k=1, num_tokens_to_generate=3))          # shares the steps
+    chunks = list(dyn.generate_stream("5 9 23 7", sp))
+    assert [c["token"] for c in chunks] == ref and all(c["logprob"] is not None and c["text"] == str(c["token"]) for c in chunks)
+    while dyn.has_unfinished_requests():
+        dyn.step()
+    assert other in dyn.completed
+    # (b) asyncio consumer while a background thread steps the engine
+    dyn.start_background_loop()
+    try:
+        async def consume():
+            st = TokenStream().bind_loop()
+            dyn._inbox.put(("5 9 23 7", sp, [5, 9, 23, 7], [], threading.Event(), st))
+            return [c["token"] async for c in st.generator()], st
+
+        toks, st = asyncio.run(consume())
+        assert toks == ref and st.finished and st.result.generated_tokens.tolist() == ref
+        # (c) SSE from the HTTP server on the same (serving) engine
+        srv = MegatronServer(dyn)
+        srv.run(port=18815, block=False)
+        time.sleep(0.3)
+        try:
+            body = json.dumps({"prompt": "5 9 23 7", "max_tokens": 5, "temperature": 0, "stream": True}).encode()
+            req = urllib.request.Request("http://127.0.0.1:18815/v1/completions", data=body, method="POST",
+                                         headers={"Content-Type": "application/json"})
+            with urllib.request.urlopen(req, timeout=30) as r:
+                assert r.headers["Content-Type"] == "text/event-stream"
+                lines = [ln.decode().strip() for ln in r if ln.strip()]
+            assert lines[-1] == "data: [DONE]"
+            texts = [json.loads(ln[6:])["choices"][0]["text"] for ln in lines[:-1]]
+            assert [int(t) for t in texts if t] == ref
+        finally:
+            srv.shutdown()
+    finally:
+        dyn.stop_loop()
+    srv = MegatronServer(eng)                                       # static engine: generate, then replay as events
+    srv.run(port=18816, block=False)
+    time.sleep(0.3)
+    try:
+        body = json.dumps({"prompt": "5 9 23 7", "max_tokens": 5, "temperature": 0, "stream": True}).encode()
+        req = urllib.request.Request("http://127.0.0.1:18816/v1/completions", data=body, method="POST", headers={"Content-Type": "application/json"})
+        with urllib.request.urlopen(req, timeout=30) as r:
+            lines = [ln.decode().strip() for ln in r if ln.strip()]
+        assert [int(json.loads(ln[6:])["choices"][0]["text"]) for ln in lines[:-2]] == ref and lines[-1] == "data: [DONE]"
     finally:
         srv.shutdown()
 
