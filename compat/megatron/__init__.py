@@ -75,6 +75,12 @@ _ALIASES = {
     "megatron.core.inference.sampling_params": "megatronapp_b200.inference.core",
     "megatron.core.inference.inference_request": "megatronapp_b200.inference.core",
     "megatron.core.inference.scheduler": "megatronapp_b200.inference.core",
+    "megatron.core.inference.async_stream": "megatronapp_b200.inference.async_stream",
+    "megatron.core.inference.common_inference_params": "megatronapp_b200.inference.core",
+    "megatron.core.inference.engines.dynamic_engine": "megatronapp_b200.inference.dynamic",
+    "megatron.core.inference.engines.static_engine": "megatronapp_b200.inference.core",
+    "megatron.core.inference.contexts.dynamic_context": "megatronapp_b200.inference.dynamic",
+    "megatron.core.inference.contexts.static_context": "megatronapp_b200.inference.core",
     "megatron.core.inference.contexts": "megatronapp_b200.inference",
     "megatron.core.inference.text_generation_controllers.text_generation_controller": "megatronapp_b200.inference.core",
     "megatron.core.models.vision.clip_vit_model": "megatronapp_b200.models.vision.clip_vit_model",
