@@ -52,7 +52,10 @@ _ALIASES = {
     "megatron.core.num_microbatches_calculator": "megatronapp_b200.utils.microbatches",
     "megatron.core.timers": "megatronapp_b200.utils.timers",
     "megatron.core.rerun_state_machine": "megatronapp_b200.training.rerun_state_machine",
-    "megatron.core.dist_checkpointing.serialization": "megatronapp_b200.ckpt.sharded",
+    "megatron.core.dist_checkpointing.serialization": "megatronapp_b200.ckpt.serialization",
+    "megatron.core.dist_checkpointing.validation": "megatronapp_b200.ckpt.serialization",
+    "megatron.core.dist_checkpointing.core": "megatronapp_b200.ckpt.serialization",
+    "megatron.core.dist_checkpointing.mapping": "megatronapp_b200.ckpt",
     "megatron.core.models.gpt.gpt_model": "megatronapp_b200.models.gpt.gpt_model",
     "megatron.core.models.gpt.gpt_layer_specs": "megatronapp_b200.models.gpt.gpt_layer_specs",
     "megatron.core.models.bert.bert_model": "megatronapp_b200.models.bert.bert_model",
@@ -200,7 +203,7 @@ _UNIONS = {
     "megatron.core.datasets": ("megatronapp_b200.data.gpt_dataset", "megatronapp_b200.data.indexed_dataset",
                                "megatronapp_b200.data.blended_builder", "megatronapp_b200.data.mock"),
     "megatron.core.datasets.gpt_dataset": (),
-    "megatron.core.dist_checkpointing": ("megatronapp_b200.ckpt.sharded",),
+    "megatron.core.dist_checkpointing": ("megatronapp_b200.ckpt", "megatronapp_b200.ckpt.sharded"),
     "megatron.core.inference": ("megatronapp_b200.inference", "megatronapp_b200.inference.core"),
     "megatron.training.tokenizer": ("megatronapp_b200.data.tokenizer", "megatronapp_b200.data.tokenizer_extra"),
 }

@@ -150,3 +150,50 @@ def test_async_writer_process_defers_visibility(tmp_path):
     td.load({"w": back}, str(tmp_path))
     assert torch.equal(back.data, ssd["w"].data)
     td.shutdown_async_writer()
+
+
+def test_dist_checkpointing_entry_points_strictness_metadata_removal_and_validation(tmp_path):
+    """The reference's ``dist_checkpointing`` surface: strict modes of ``load``, metadata-only and whole-tensor loads, dropping a
+    key family (optimizer state) from an existing checkpoint, non-persistent local objects, sharding validation."""
+    import megatronapp_b200.ckpt as dc
+    from megatronapp_b200.ckpt import CheckpointingException, LocalNonpersistentObject, StrictHandling
+
+    w = torch.arange(48, dtype=torch.float32).view(8, 6)
+    ssd = {"w#0": _st("blk.weight", w[:4], offsets=[(0, 0, 2)]), "w#1": _st("blk.weight", w[4:], offsets=[(0, 1, 2)]),
+           "m": _st("optimizer.state.exp_avg.blk.weight", torch.ones(8, 6)), "obj": ShardedObject("blk._extra_state", {"a": 1}),
+           "rng": LocalNonpersistentObject({"seed": 7})}
+    dc.save(ssd, str(tmp_path), {"iteration": 3}).finalize()
+    assert dc.check_is_distributed_checkpoint(str(tmp_path)) and dc.load_common_state_dict(str(tmp_path))["iteration"] == 3
+    meta = dc.load_tensors_metadata(str(tmp_path))
+    assert set(meta) == {"blk.weight", "optimizer.state.exp_avg.blk.weight"} and meta["blk.weight"].global_shape == (8, 6) and meta["blk.weight"].data is None
+    assert "blk._extra_state/shard_0_1" in dc.load_sharded_metadata(str(tmp_path)) or any("_extra_state" in k for k in dc.load_sharded_metadata(str(tmp_path)))
+    plain = dc.load_plain_tensors(str(tmp_path))
+    assert torch.equal(plain["blk.weight"], w)
+    # strictness
+    want = {"w": _st("blk.weight", torch.zeros(8, 6)), "gone": _st("blk.bias", torch.zeros(6)), "rng": LocalNonpersistentObject({"seed": 9})}
+    out, missing, unexpected = dc.load(want, str(tmp_path), StrictHandling.RETURN_ALL)
+    assert torch.equal(out["w"], w) and out["rng"] == {"seed": 9} and missing == ["blk.bias"] and "optimizer.state.exp_avg.blk.weight" in unexpected
+    with pytest.raises(CheckpointingException, match="missing"):
+        dc.load(want, str(tmp_path), StrictHandling.RAISE_ALL)
+    with pytest.raises(CheckpointingException, match="unexpected"):
+        dc.load({"w": _st("blk.weight", torch.zeros(8, 6))}, str(tmp_path), StrictHandling.RAISE_UNEXPECTED)
+    with pytest.raises(KeyError):
+        dc.load(want, str(tmp_path), StrictHandling.ASSUME_OK_UNEXPECTED)
+    # release checkpoint: optimizer state dropped from the metadata, the model still loads
+    gone = dc.remove_sharded_tensors(str(tmp_path), "optimizer.")
+    assert gone == ["optimizer.state.exp_avg.blk.weight"] and set(dc.load_tensors_metadata(str(tmp_path))) == {"blk.weight"}
+    full = dc.load({"w": _st("blk.weight", torch.zeros(8, 6)), "obj": ShardedObject("blk._extra_state", None)}, str(tmp_path),
+                   StrictHandling.RAISE_ALL)
+    assert torch.equal(full["w"], w) and full["obj"] == {"a": 1}
+    # validation: gap, overlap, out-of-bounds, flattened ranges
+    dc.validate_sharding_integrity(ssd)
+    with pytest.raises(CheckpointingException, match="cover 24 of 48"):
+        dc.validate_sharding_integrity({"w#0": ssd["w#0"]})
+    with pytest.raises(CheckpointingException, match="overlap"):
+        dc.validate_sharding_integrity({"a": ssd["w#0"], "b": _st("blk.weight", w[:4], offsets=[(0, 0, 2)])})
+    flat = {"a": _st("p", torch.zeros(10), flat=(0, 6)), "b": _st("p", torch.zeros(10), flat=(6, 10))}
+    dc.validate_sharding_integrity(flat)
+    with pytest.raises(CheckpointingException, match="cover 9 of 10"):
+        dc.validate_sharding_integrity({"a": flat["a"], "b": _st("p", torch.zeros(10), flat=(7, 10))})
+    with pytest.raises(CheckpointingException):
+        dc.save({"w#0": ssd["w#0"]}, str(tmp_path / "bad"))
