@@ -50,8 +50,29 @@ class MockImageDataset(torch.utils.data.Dataset):
         return {"image": img, "label": torch.tensor(label)}
 
 
+class _DictView(torch.utils.data.Dataset):
+    """(image, label) folder samples as the dict the forward step reads"""
+
+    def __init__(self, ds, n):
+        self.ds, self.n = ds, max(int(n), len(ds))
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        img, label = self.ds[i % len(self.ds)]
+        return {"image": img, "label": torch.tensor(label)}
+
+
 def train_valid_test_datasets_provider(num_samples):
     a = get_args()
+    if a.data_path:
+        # <data-path>/train/<class>/*.jpg and <data-path>/val/... (reference legacy/data/vit_dataset.py)
+        from megatronapp_b200.legacy.data.vit_dataset import build_train_valid_datasets
+
+        tr, va = build_train_valid_datasets(a.data_path if len(a.data_path) > 1 else a.data_path[0], (a.img_h, a.img_w), "classify",
+                                            classes_fraction=a.classes_fraction, data_per_class_fraction=a.data_per_class_fraction)
+        return _DictView(tr, num_samples[0]), _DictView(va, num_samples[1]), _DictView(va, num_samples[2])
     mk = lambda n, s: MockImageDataset(max(int(n), 1), a.img_h, a.img_w, a.num_classes, s)  # noqa: E731
     return mk(num_samples[0], 1), mk(num_samples[1], 2), mk(num_samples[2], 3)
 

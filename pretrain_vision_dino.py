@@ -70,8 +70,31 @@ class MockMultiCropDataset(torch.utils.data.Dataset):
                 "label": torch.tensor(label)}
 
 
+class _MultiCropView(torch.utils.data.Dataset):
+    def __init__(self, ds, n, n_local, local_size):
+        self.ds, self.n, self.n_local, self.local = ds, max(int(n), len(ds)), n_local, local_size
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        crops, label = self.ds[i % len(self.ds)]
+        if not isinstance(crops, list):                             # evaluation transform: one centre crop, used twice
+            crops = [crops, crops]
+        return {"global": torch.stack(crops[:2]), "local": torch.stack(crops[2:]) if len(crops) > 2 else torch.zeros(0),
+                "label": torch.tensor(label)}
+
+
 def train_valid_test_datasets_provider(num_samples):
     a = get_args()
+    if a.data_path:
+        from megatronapp_b200.legacy.data.vit_dataset import build_train_valid_datasets
+
+        tr, _ = build_train_valid_datasets(a.data_path if len(a.data_path) > 1 else a.data_path[0], a.img_h, "dino",
+                                           dino_local_img_size=a.dino_local_img_size, dino_local_crops_number=a.dino_local_crops_number,
+                                           classes_fraction=a.classes_fraction, data_per_class_fraction=a.data_per_class_fraction)
+        mk = lambda n: _MultiCropView(tr, n, a.dino_local_crops_number, a.dino_local_img_size)  # noqa: E731
+        return mk(num_samples[0]), mk(num_samples[1]), mk(num_samples[2])
     mk = lambda n, s: MockMultiCropDataset(max(int(n), 1), a.img_h, a.dino_local_img_size, a.dino_local_crops_number,  # noqa: E731
                                            a.num_classes, s)
     return mk(num_samples[0], 1), mk(num_samples[1], 2), mk(num_samples[2], 3)

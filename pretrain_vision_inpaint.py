@@ -57,8 +57,27 @@ class MockInpaintDataset(torch.utils.data.Dataset):
         return {"image": img, "mask": mask}
 
 
+class _MaskedView(torch.utils.data.Dataset):
+    def __init__(self, ds, n):
+        self.ds, self.n = ds, max(int(n), len(ds))
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        (img, mask), _ = self.ds[i % len(self.ds)]
+        return {"image": img, "mask": mask}
+
+
 def train_valid_test_datasets_provider(num_samples):
     a = get_args()
+    if a.data_path:
+        from megatronapp_b200.legacy.data.vit_dataset import build_train_valid_datasets
+
+        tr, va = build_train_valid_datasets(a.data_path if len(a.data_path) > 1 else a.data_path[0], (a.img_h, a.img_w), "inpaint",
+                                            patch_dim=a.patch_dim, mask_factor=a.mask_factor, mask_type=a.mask_type,
+                                            classes_fraction=a.classes_fraction, data_per_class_fraction=a.data_per_class_fraction)
+        return _MaskedView(tr, num_samples[0]), _MaskedView(va, num_samples[1]), _MaskedView(va, num_samples[2])
     mk = lambda n, s: MockInpaintDataset(max(int(n), 1), a.img_h, a.img_w, a.patch_dim, a.mask_type, a.mask_factor, s)  # noqa: E731
     return mk(num_samples[0], 1), mk(num_samples[1], 2), mk(num_samples[2], 3)
 

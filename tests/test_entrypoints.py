@@ -486,3 +486,31 @@ def test_trtllm_export_examples(tmp_path):
 
     a, b = load_file(os.path.join(single, "rank1.safetensors")), torch.load(os.path.join(distd, "rank1.pt"))
     assert sorted(a) == sorted(b) and all(a[k].shape == b[k].shape for k in a)
+
+
+@pytest.mark.parametrize("script,extra", [("pretrain_vision_classify.py", ["--num-classes", "3"]),
+                                          ("pretrain_vision_inpaint.py", ["--mask-type", "row"]),
+                                          ("pretrain_vision_dino.py", ["--dino-local-img-size", "8", "--dino-local-crops-number", "2", "--dino-out-dim", "32",
+                                                                       "--dino-head-hidden-size", "32", "--dino-bottleneck-size", "16", "--iter-per-epoch", "2"])])
+def test_vision_entrypoints_train_from_an_image_folder(tmp_path, script, extra):
+    """``--data-path <dir>`` with ``train/<class>/*.png`` and ``val/...``: torchvision transforms (AutoAugment, multi-crop,
+    patch masks) from ``legacy/data/vit_dataset.py`` feed the three vision pre-training entry points."""
+    import numpy as np
+    from PIL import Image
+
+    rng = np.random.RandomState(0)
+    for split in ("train", "val"):
+        for ci, c in enumerate(("cat", "dog", "eel")):
+            os.makedirs(tmp_path / split / c)
+            for i in range(6):
+                a = (rng.rand(24, 24, 3) * 60).astype(np.uint8)
+                a[..., ci] += 150
+                Image.fromarray(a).save(tmp_path / split / c / f"{i}.png")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_port()), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    common = [a for a in COMMON if a != "--mock-data"]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, script), *common, "--img-h", "16", "--img-w", "16", "--patch-dim", "4",
+                        "--data-path", str(tmp_path), *extra], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    assert re.search(r"iteration\s+3/\s+3 \|.*loss: [0-9.E+\-]+", out) and "validation loss at the end of training" in out
