@@ -140,6 +140,9 @@ _ALIASES = {
     "megatron.core.tensor_tracer": "megatronapp_b200.scope.capture",
     "megatron.core.tensor_disturbance": "megatronapp_b200.scope.disturbance",
     "megatron.inference.text_generation_server": "megatronapp_b200.inference.server",
+    "megatron.inference.text_generation": "megatronapp_b200.inference.text_generation",
+    "megatron.inference.text_generation.api": "megatronapp_b200.inference.text_generation.api",
+    "megatron.inference.text_generation.beam_utils": "megatronapp_b200.inference.beam_search",
     "megatron.legacy.data.data_samplers": "megatronapp_b200.data.samplers",
 }
 

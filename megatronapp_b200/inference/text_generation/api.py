@@ -1,0 +1,110 @@
+"""Function-style text generation (reference ``megatron/inference/text_generation/{api,generation,tokenization}.py``).
+
+The reference threads an ``inference_context`` and a ``forward_step`` class through these calls; here the model is wrapped in
+``GPTInferenceWrapper`` + ``StaticInferenceEngine`` (KV cache, pipeline / tensor-parallel token synchronisation) on first use
+and the wrapper is cached on the model, so callers keep the one-line API:
+
+    texts, segments, logprobs, tokens = generate_and_post_process(model, prompts=["Hello"], tokens_to_generate=32, top_k_sampling=1)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from ..beam_search import beam_search as _beam_search
+from ..core import GPTInferenceWrapper, SamplingParams, StaticInferenceEngine, TextGenerationController
+
+
+def _tokenizer(tokenizer=None):
+    if tokenizer is not None:
+        return tokenizer
+    from ...training.global_vars import get_tokenizer
+
+    return get_tokenizer()
+
+
+def _engine(model, tokenizer, max_batch: int, max_seq: Optional[int]) -> StaticInferenceEngine:
+    inner = model
+    while hasattr(inner, "module"):
+        inner = inner.module
+    cache = getattr(inner, "_b200_generation_engine", None)
+    if cache is not None and cache[1] >= max_batch and cache[2] is tokenizer:
+        return cache[0]
+    if max_seq is None:
+        max_seq = getattr(inner, "max_sequence_length", None) or getattr(getattr(inner, "config", None), "seq_length", None) or 4096
+    pv = getattr(inner, "vocab_size", None)
+    eng = StaticInferenceEngine(TextGenerationController(GPTInferenceWrapper(model, max_batch, max_seq, pv), tokenizer), max_batch)
+    inner._b200_generation_engine = (eng, max_batch, tokenizer)
+    return eng
+
+
+def generate(model, inference_context=None, forward_step=None, prompts: Optional[Sequence[str]] = None, tokens_to_generate: int = 0,
+             return_output_log_probs: bool = False, top_k_sampling: int = 0, top_p_sampling: float = 0.0, top_p_decay: float = 0.0,
+             top_p_bound: float = 0.0, temperature: float = 1.0, add_BOS: bool = False, use_eod_token_for_early_termination: bool = True,
+             stop_on_double_eol: bool = False, stop_on_eol: bool = False, prevent_newline_after_colon: bool = False,
+             random_seed: int = -1, data_parallel: bool = False, return_topk_logprobs: int = 0, tokenizer=None,
+             max_sequence_length: Optional[int] = None):
+    """Returns ``(tokens [b, max_len] padded with eod, lengths [b], output_log_probs | None, None)``."""
+    if top_p_decay or top_p_bound or stop_on_double_eol or stop_on_eol or prevent_newline_after_colon:
+        raise NotImplementedError("top-p decay and the end-of-line stopping rules of the legacy API are not implemented")
+    if not prompts:
+        raise ValueError("prompts is empty")
+    tok = _tokenizer(tokenizer)
+    if random_seed is not None and random_seed >= 0:
+        torch.manual_seed(random_seed)
+    eng = _engine(model, tok, max(len(prompts), 1), max_sequence_length)
+    sp = SamplingParams(temperature=temperature, top_k=top_k_sampling, top_p=top_p_sampling, return_log_probs=return_output_log_probs,
+                        num_tokens_to_generate=tokens_to_generate, add_BOS=add_BOS)
+    res = eng.generate(list(prompts), sp, add_BOS=add_BOS)
+    rows = [list(r.prompt_tokens) + [int(t) for t in r.generated_tokens] for r in res]
+    lengths = torch.tensor([len(r) for r in rows])
+    tokens = torch.full((len(rows), int(lengths.max())), tok.eod, dtype=torch.long)
+    for i, r in enumerate(rows):
+        tokens[i, :len(r)] = torch.tensor(r)
+    logp = [list(r.generated_log_probs or []) for r in res] if return_output_log_probs else None
+    return tokens, lengths, logp, None
+
+
+def generate_and_post_process(model, inference_context=None, forward_step=None, prompts=None, tokens_to_generate=0,
+                              return_output_log_probs=False, top_k_sampling=0, top_p_sampling=0.0, top_p_decay=0.0, top_p_bound=0.0,
+                              temperature=1.0, add_BOS=False, use_eod_token_for_early_termination=True, stop_on_double_eol=False,
+                              stop_on_eol=False, prevent_newline_after_colon=False, random_seed=-1, detokenize_segments=True,
+                              data_parallel=False, return_topk_logprobs=0, tokenizer=None, max_sequence_length=None):
+    """Returns ``(texts, segments, output_log_probs, tokens)`` as python lists: ``texts`` = prompt + continuation,
+    ``segments`` = the per-token strings of each row (``detokenize_segments``), ``tokens`` = token id lists."""
+    tok = _tokenizer(tokenizer)
+    tokens, lengths, logp, _ = generate(model, inference_context, forward_step, prompts, tokens_to_generate, return_output_log_probs,
+                                        top_k_sampling, top_p_sampling, top_p_decay, top_p_bound, temperature, add_BOS,
+                                        use_eod_token_for_early_termination, stop_on_double_eol, stop_on_eol, prevent_newline_after_colon,
+                                        random_seed, data_parallel, return_topk_logprobs, tok, max_sequence_length)
+    rows = [tokens[i, : int(lengths[i])].tolist() for i in range(tokens.shape[0])]
+    texts = [tok.detokenize([t for t in r if t != tok.eod]) for r in rows]
+    segments = [[tok.detokenize([t]) for t in r] for r in rows] if detokenize_segments else None
+    return texts, segments, logp, rows
+
+
+def beam_search(model, forward_step=None, prompts=None, tokens_to_generate: int = 0, beam_size: int = 0, add_BOS: bool = False,
+                stop_token: Optional[int] = None, num_return_gen: int = 1, length_penalty: float = 1.0,
+                prevent_newline_after_colon: bool = False, tokenizer=None, max_sequence_length: Optional[int] = None):
+    """Single prompt (as in the reference).  Returns ``(tokens [num_return_gen, len], scores [num_return_gen])``."""
+    if not prompts or len(prompts) != 1:
+        raise ValueError("beam search takes exactly one prompt")
+    tok = _tokenizer(tokenizer)
+    eng = _engine(model, tok, max(beam_size, 1), max_sequence_length)
+    ids = eng.controller.tokenize_prompt(prompts[0], add_BOS)
+    return _beam_search(eng.controller.inference_wrapped_model, ids, beam_size, tokens_to_generate,
+                        tok.eod if stop_token is None else stop_token, length_penalty, num_return_gen)
+
+
+def beam_search_and_post_process(model, forward_step=None, prompts=None, tokens_to_generate=0, beam_size=0, add_BOS=False,
+                                 stop_token=None, num_return_gen=1, length_penalty=1.0, prevent_newline_after_colon=False,
+                                 detokenize_segments=True, tokenizer=None, max_sequence_length=None):
+    """Returns ``(texts, segments, scores)``."""
+    tok = _tokenizer(tokenizer)
+    hyps, scores = beam_search(model, forward_step, prompts, tokens_to_generate, beam_size, add_BOS, stop_token, num_return_gen,
+                               length_penalty, prevent_newline_after_colon, tok, max_sequence_length)
+    rows = [[int(t) for t in h] for h in hyps]
+    texts = [tok.detokenize([t for t in r if t != tok.eod]) for r in rows]
+    segments = [[tok.detokenize([t]) for t in r] for r in rows] if detokenize_segments else None
+    return texts, segments, [float(s) for s in scores]

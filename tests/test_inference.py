@@ -198,6 +198,28 @@ def test_dynamic_engine_behind_rest_server(engine):
         srv.shutdown()
 
 
+def test_function_style_generation_api_matches_the_engine(engine):
+    """``generate_and_post_process`` / ``beam_search_and_post_process`` (the reference's megatron.inference.text_generation
+    API) over a bare model give the engine's greedy continuation and the beam search module's best hypothesis."""
+    from megatronapp_b200.inference.beam_search import beam_search as bs
+    from megatronapp_b200.inference.text_generation import beam_search_and_post_process, generate_and_post_process
+
+    eng, model = engine
+    tok = NullTokenizer(127)
+    prompts = ["5 9 23 7", "11 3"]
+    ref = eng.generate(prompts, SamplingParams(top_k=1, num_tokens_to_generate=5))
+    texts, segments, logp, tokens = generate_and_post_process(model, prompts=prompts, tokens_to_generate=5, top_k_sampling=1,
+                                                              return_output_log_probs=True, tokenizer=tok, max_sequence_length=32)
+    for i, r in enumerate(ref):
+        assert tokens[i] == r.prompt_tokens + r.generated_tokens.tolist()
+        assert texts[i] == tok.detokenize(tokens[i]) and segments[i] == [str(t) for t in tokens[i]] and len(logp[i]) == 5
+    w = GPTInferenceWrapper(model, 4, 32, None)
+    hyps, scores = bs(w, [3, 7, 11], beam_size=3, tokens_to_generate=4, stop_token=10 ** 6, num_return_gen=2)
+    t2, seg2, sc2 = beam_search_and_post_process(model, prompts=["3 7 11"], tokens_to_generate=4, beam_size=3, stop_token=10 ** 6,
+                                                 num_return_gen=2, tokenizer=tok, max_sequence_length=32)
+    assert t2[0] == tok.detokenize(hyps[0].tolist()) and abs(sc2[0] - float(scores[0])) < 1e-5 and len(seg2[0]) == 7
+
+
 def test_token_streaming_engine_asyncio_and_sse(engine):
     """Streaming: tokens are published as they are sampled -- (a) synchronous generator on a stand-alone dynamic engine,
     (b) asyncio consumer of a TokenStream fed by the serving loop, (c) server-sent events from ``/v1/completions`` with
