@@ -622,6 +622,52 @@ def local_ckpt_replication(path=None):
     return out
 
 
+def evidence_indexer(path=None):
+    """2 ranks embed an evidence TSV with the bi-encoder's context tower, rank 0 merges the shards; the MIPS index built
+    from the merged store returns every passage as its own nearest neighbour (shared towers)."""
+    from megatronapp_b200.config.transformer_config import TransformerConfig
+    from megatronapp_b200.legacy.data.realm_index import FaissMIPSIndex, OpenRetreivalDataStore
+    from megatronapp_b200.legacy.indexer import IndexBuilder
+    from megatronapp_b200.legacy.model.biencoder_model import BiEncoderModel
+    from megatronapp_b200.parallel import state as ps
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(1, 1)
+
+    class Tok:
+        cls, sep, pad = 1, 2, 0
+
+        def tokenize(self, t):
+            return [3 + (sum(map(ord, w)) % 100) for w in t.lower().split()]
+
+    tsv = os.path.join(path, "evidence.tsv")
+    if rank == 0:
+        with open(tsv, "w") as f:
+            f.write("id\ttext\ttitle\n")
+            for i, w in enumerate(["zebra", "quartz", "lemon", "violin", "harbor", "comet", "saddle"]):
+                f.write(f"{i + 10}\tpassage about {w} and more {w}\t{w}\n")
+    dist.barrier()
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0,
+                            attention_dropout=0.0, kernel_backend="torch", params_dtype=torch.float32)
+    model = BiEncoderModel(cfg, 128, 16, biencoder_shared_query_context_model=True)
+    emb_path = os.path.join(path, "emb.pkl")
+    IndexBuilder(model, Tok(), tsv, emb_path, seq_length=16, batch_size=2).build_and_save_index()
+    out = {"rank": rank}
+    if rank == 0:
+        store = OpenRetreivalDataStore(emb_path, load_from_path=True)
+        out["ids"] = sorted(store.embed_data)
+        n = len(store.embed_data)
+        vecs = {k: torch.tensor(store.embed_data[k], dtype=torch.float32) for k in store.embed_data}
+        index = FaissMIPSIndex(32, store)
+        index.add_embed_data(store)
+        q = torch.stack([vecs[k] for k in sorted(vecs)])
+        _, hits = index.search_mips_index(q, top_k=2, reconstruct=False)
+        out["self_hits"] = [int(h[0]) for h in hits]
+        out["n"], out["tmp_gone"] = n, not os.path.exists(os.path.join(path, "emb_tmp"))
+    return out
+
+
 def dpp_compat_transport():
     """The reference's module-function mailbox API over 2 pipeline ranks: non-blocking gets, last->first slot shift."""
     import sys

@@ -242,3 +242,10 @@ def test_local_checkpoint_manager_replication_survives_a_lost_node(tmp_path):
         assert o["latest"] == 4 and o["latest_after_loss"] == 4
         assert o["restored"] == [4, float(10 * r + 4)] and o["own_file_back"]
         assert o["latest_after_two_losses"] == -1                              # rank 1's state had one holder (rank 2): both gone
+
+
+def test_evidence_indexer_shards_over_ranks_and_feeds_the_mips_index(tmp_path):
+    res = run_distributed("evidence_indexer", 2, path=str(tmp_path))
+    r0 = [r for r in res if r["rank"] == 0][0]
+    assert r0["ids"] == list(range(10, 17)) and r0["n"] == 7 and r0["tmp_gone"]
+    assert r0["self_hits"] == r0["ids"]                     # every passage retrieves itself first
