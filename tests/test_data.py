@@ -310,3 +310,34 @@ def test_preprocess_mmdata_roundtrip(tmp_path):
     assert ds.index.sequence_modes.tolist() == [0, 1, 0, 1]
     assert ds[0].tolist() == [5, 6, 7, 50] and ds[2].tolist() == [8, 9, 10, 11]     # padded with eod / truncated
     assert mm.words_to_image_bytes(ds[1]) == blobs[0] and mm.words_to_image_bytes(ds[3]) == blobs[1]
+
+
+def test_multimodal_dataset_reads_preprocessed_caption_image_pairs(tmp_path):
+    """tools/preprocess_mmdata.py output -> legacy MultiModalDataset: captions come back as token ids, images are decoded
+    from the stored file bytes and transformed to ``[3, h, w]`` CLIP-normalised tensors."""
+    import importlib.util
+    import json
+
+    import numpy as np
+    from PIL import Image
+
+    from megatronapp_b200.legacy.data.multimodal_dataset import MultiModalDataset
+
+    spec = importlib.util.spec_from_file_location("preprocess_mmdata", os.path.join(ROOT, "tools", "preprocess_mmdata.py"))
+    mm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mm)
+    (tmp_path / "img").mkdir()
+    rng = np.random.RandomState(0)
+    for i in range(3):
+        a = np.zeros((20, 30, 3), dtype=np.uint8)
+        a[..., i] = 255                                               # pure red / green / blue images
+        Image.fromarray(a).save(tmp_path / "img" / f"{i:03d}.png")
+    (tmp_path / "cap.jsonl").write_text("\n".join(json.dumps({"text": f"{i + 3} {i + 4}"}) for i in range(3)) + "\n")
+    mm.main(["--input", str(tmp_path / "cap.jsonl"), "--input-image", str(tmp_path / "img"), "--pad-length", "4",
+             "--tokenizer-type", "NullTokenizer", "--vocab-size", "50", "--output-prefix", str(tmp_path / "mm")])
+    ds = MultiModalDataset("train", str(tmp_path / "mm"), img_h=8, img_w=8)
+    assert len(ds) == 3
+    for i in range(3):
+        s = ds[i]
+        assert s["text"].tolist() == [i + 3, i + 4, 50, 50] and s["img"].shape == (3, 8, 8)
+        assert int(np.argmax(s["img"].mean(axis=(1, 2)))) == i      # the dominant channel survives decode + normalise
