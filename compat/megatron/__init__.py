@@ -126,6 +126,7 @@ _ALIASES = {
     "megatron.training.ft_integration": "megatronapp_b200.training.ft_integration",
     "megatron.training.async_utils": "megatronapp_b200.training.async_utils",
     "megatron.post_training.checkpointing": "megatronapp_b200.post_training.quantization",
+    "megatron.post_training.algos.distillation": "megatronapp_b200.post_training.distillation",
     # megatron.training & add-ons
     "megatron.training.arguments": "megatronapp_b200.training.arguments",
     "megatron.training.initialize": "megatronapp_b200.training.initialize",

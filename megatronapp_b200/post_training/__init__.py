@@ -1,1 +1,3 @@
-from .distillation import LogitsKLLoss, HiddenStateCosineLoss, DistillationLossBalancer, distillation_forward  # noqa: F401
+from .distillation import (DistillationLossBalancer, DistillationState, HiddenStateCosineLoss, LogitsAndIntermediatesLossBalancer,  # noqa: F401
+                           LogitsKLLoss, MSELoss, ProjectionLayer, attach_teacher, distillation_forward,
+                           load_distillation_config, teacher_args_from_checkpoint)

@@ -518,6 +518,20 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--inference-dynamic-batching-chunk-size", type=int, default=256,
          help="tokens per KV block of the paged cache")
     _add(g, "--inference-max-batch-size", type=int, default=8, dest="inference_max_requests")
+    g = p.add_argument_group("post-training")     # reference megatron/post_training/arguments.py (add_modelopt_args)
+    _add(g, "--export-kd-cfg", type=str, default=None, help="distillation yaml: logit_layers, intermediate_layer_pairs, "
+         "skip_lm_loss, kd_loss_scale")
+    _add(g, "--export-kd-teacher-load", type=str, default=None, help="checkpoint of the (frozen) distillation teacher")
+    _add(g, "--export-kd-finalize", action="store_true", help="load a distillation run and save the plain student")
+    _add(g, "--export-model-type", type=str, default="GPTModel", choices=["GPTModel", "MambaModel"])
+    _add(g, "--export-legacy-megatron", action="store_true")
+    _add(g, "--export-te-mcore-model", action="store_true")
+    _add(g, "--export-force-local-attention", action="store_true")
+    _add(g, "--export-kv-cache-quant", action="store_true")
+    _add(g, "--export-real-quant-cfg", type=str, default="None", choices=["fp8_real_quant", "fp8_blockwise_real_quant", "None"])
+    _add(g, "--export-num-medusa-heads", type=int, default=0)
+    _add(g, "--export-num-eagle-layers", type=int, default=0)
+    _add(g, "--finetune-hf-dataset", type=str, default=None)
     g = p.add_argument_group("MegaScan")
     _add(g, "--trace", action="store_true")
     _add(g, "--trace-dir", type=str, default="trace")
@@ -668,8 +682,9 @@ def validate_args(args, defaults=None):
         args.params_dtype = torch.half
     if args.bf16:
         args.params_dtype = torch.bfloat16
-        if not args.accumulate_allreduce_grads_in_fp32:
-            args.accumulate_allreduce_grads_in_fp32 = True
+        # --grad-reduce-in-bf16 (reference arguments.py: bf16 reduction instead of fp32).  With the fused reduce-scatter kernel
+        # the main grads stay fp32 and only the NVLink wire format is bf16; with NCCL the grad buffers themselves are bf16.
+        args.accumulate_allreduce_grads_in_fp32 = not (args.grad_reduce_in_bf16 and not args.fused_grad_reduce_scatter)
     if args.dataloader_type is None:
         args.dataloader_type = "single"
     args.consumed_train_samples = 0

@@ -439,7 +439,10 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
         sd = torch.load(name, map_location="cpu", weights_only=False)
         for i, m in enumerate(model):
             target = _fsdp_wrapper(m) or _unwrap(m)          # ZeRO-3: load through the wrapper (gathers, loads, re-shards)
-            target.load_state_dict(sd["model" if len(model) == 1 else f"model{i}"], strict=strict)
+            msd = sd["model" if len(model) == 1 else f"model{i}"]
+            if not hasattr(_unwrap(m), "kd_projections"):    # a distillation run's trainable projections are not model state
+                msd = {k: v for k, v in msd.items() if not k.startswith("kd_projections.")}
+            target.load_state_dict(msd, strict=strict)
         if optimizer is not None and not args.finetune and not args.no_load_optim:
             dp_rank = ps.get_data_parallel_rank(with_context_parallel=True)
             dop = os.path.join(os.path.dirname(name), "distrib_optim.pt" if dp_rank == 0 else f"distrib_optim_dp{dp_rank:03d}.pt")

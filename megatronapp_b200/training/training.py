@@ -125,7 +125,8 @@ def get_model(model_provider_func: Callable, model_type=None, wrap_with_ddp: boo
             check_for_nan_in_grad=False,
             bucket_size=args.ddp_bucket_size,
             average_in_collective=args.ddp_average_in_collective,
-            fused_grad_reduce_scatter=args.fused_grad_reduce_scatter)
+            fused_grad_reduce_scatter=args.fused_grad_reduce_scatter,
+            grad_wire_dtype="bf16" if args.grad_reduce_in_bf16 else "fp32")
         if args.use_custom_fsdp or args.use_torch_fsdp2:
             from ..parallel.fsdp import FullyShardedDataParallel, TorchFullyShardedDataParallel
 

@@ -24,6 +24,42 @@ from megatronapp_b200.training.utils import get_batch_on_this_tp_rank, print_ran
 
 def model_provider(pre_process=True, post_process=True):
     args = get_args()
+    student = _build_model(args, pre_process, post_process)
+    if getattr(args, "export_kd_teacher_load", None) and not args.export_kd_finalize:
+        _attach_distillation_teacher(args, student)
+    return student
+
+
+def _attach_distillation_teacher(args, student):
+    """--export-kd-teacher-load: knowledge distillation from a frozen teacher checkpoint (reference
+    ``megatron/post_training/model_provider.py:222-247``).  The teacher shares the student's tensor-parallel layout and its
+    tokenizer; its architecture comes from ``model_config.yaml`` in the checkpoint folder or from the checkpoint's own args."""
+    from megatronapp_b200.post_training import attach_teacher, load_distillation_config, teacher_args_from_checkpoint
+    from megatronapp_b200.training.checkpointing import load_checkpoint
+
+    if args.pipeline_model_parallel_size > 1:
+        raise ValueError("distillation does not support pipeline parallelism")
+    if args.use_legacy_models:
+        raise ValueError("distillation needs the core GPT model (not --use-legacy-models)")
+    targs = teacher_args_from_checkpoint(args, args.export_kd_teacher_load)
+    targs.export_kd_teacher_load, targs.export_kd_finalize = None, False
+    print_rank_0(f"building the distillation teacher ({targs.num_layers} layers, hidden size {targs.hidden_size}) ...")
+    teacher = _build_model(targs, True, True)
+    finetune, no_load_rng = args.finetune, args.no_load_rng
+    args.finetune = args.no_load_rng = True          # weights only: no iteration / rng / consumed-samples side effects
+    try:
+        load_checkpoint([teacher], None, None, load_arg="export_kd_teacher_load", strict=True)
+    finally:
+        args.finetune, args.no_load_rng = finetune, no_load_rng
+    if args.bf16 or args.fp16:
+        teacher = teacher.to(torch.bfloat16 if args.bf16 else torch.float16)
+    if torch.cuda.is_available():
+        teacher = teacher.cuda(torch.cuda.current_device())
+    cfg = load_distillation_config(args.export_kd_cfg, student.config, teacher.config, args.sequence_parallel)
+    attach_teacher(student, teacher, cfg, args.sequence_parallel)
+
+
+def _build_model(args, pre_process=True, post_process=True):
     print_rank_0("building GPT model ...")
     config = core_transformer_config_from_args(args)
     if args.use_legacy_models:
@@ -105,12 +141,34 @@ def loss_func(loss_mask, output_tensor):
     return loss[0] * args.context_parallel_size, local_num_tokens, {"lm loss": (reporting[0], reporting[1])}
 
 
+def kd_loss_func(loss_mask, kd, output_tensor):
+    """Loss with the distillation terms (reference ``post_training/loss_func.py``): the LM loss is still reported, the
+    optimised quantity is the balancer's mix of LM, logit-KL and intermediate-layer losses."""
+    lm_sum, num_tokens, report = loss_func(loss_mask, output_tensor)
+    mask = loss_mask.float()
+    count = mask.sum().clamp(min=1)
+    total, kd_logits = kd.compute_kd_loss(student_loss=lm_sum / count, loss_reduction_fn=lambda x: (x * mask).sum() / count)
+    rep = torch.stack([kd_logits * count, count]).detach()
+    g = mpu.get_data_parallel_group()
+    if g is not None and not isinstance(g, mpu._SingleGroup) and torch.distributed.get_world_size(g) > 1:
+        torch.distributed.all_reduce(rep, group=g)
+    report["kd loss"] = (rep[0], rep[1])
+    return total * count, num_tokens, report
+
+
 def forward_step(data_iterator, model):
     timers = get_timers()
     timers("batch-generator", log_level=2).start()
     tokens, labels, loss_mask, attention_mask, position_ids = get_batch(data_iterator)
     timers("batch-generator").stop()
     output_tensor = model(tokens, position_ids, attention_mask, labels=labels)
+    core = model
+    while hasattr(core, "module"):
+        core = core.module
+    kd = core.__dict__.get("_kd")
+    if kd is not None and core.training:
+        kd.teacher_forward(tokens, position_ids, attention_mask)
+        return output_tensor, partial(kd_loss_func, loss_mask, kd)
     return output_tensor, partial(loss_func, loss_mask)
 
 

@@ -140,6 +140,37 @@ def vocab_parallel_ce():
             "bwd": float((local.grad - full.grad[..., rank * 16:(rank + 1) * 16]).abs().max())}
 
 
+def vocab_parallel_kd_loss():
+    """LogitsKLLoss over vocabulary shards: value and gradient against the unsharded KL."""
+    from megatronapp_b200.parallel import state as ps
+    from megatronapp_b200.post_training import LogitsKLLoss
+
+    rank, world = _setup()
+    ps.initialize_model_parallel(world)
+    torch.manual_seed(0)
+    V = 16 * world
+    student = torch.randn(6, 3, V, requires_grad=True)
+    teacher = torch.randn(6, 3, V)
+    w = torch.rand(6, 3)                          # a non-uniform cotangent (the loss mask of a real run)
+    out = {}
+    for reverse in (False, True):
+        if reverse:
+            ref = torch.nn.functional.kl_div(torch.log_softmax(teacher / 2, -1), torch.log_softmax(student / 2, -1), reduction="none",
+                                             log_target=True).sum(-1) * 4
+        else:
+            ref = torch.nn.functional.kl_div(torch.log_softmax(student / 2, -1), torch.softmax(teacher / 2, -1),
+                                             reduction="none").sum(-1) * 4
+        student.grad = None
+        (ref * w).sum().backward()
+        sl = slice(rank * 16, (rank + 1) * 16)
+        local = student.detach()[..., sl].clone().requires_grad_(True)
+        kl = LogitsKLLoss(temperature=2.0, reverse=reverse)(local, teacher[..., sl].clone())
+        (kl * w).sum().backward()
+        out[f"fwd{int(reverse)}"] = float((kl - ref).abs().max())
+        out[f"bwd{int(reverse)}"] = float((local.grad - student.grad[..., sl]).abs().max())
+    return out
+
+
 def sharded_ckpt(tp_save=2, tp_load=1, path=None):
     """Save at one TP degree, load at another (resharding is a format feature)."""
     from megatronapp_b200.ckpt import sharded

@@ -40,6 +40,11 @@ def test_vocab_parallel_cross_entropy():
         assert r["fwd"] < 1e-5 and r["bwd"] < 1e-6
 
 
+def test_vocab_parallel_distillation_kl():
+    for r in run_distributed("vocab_parallel_kd_loss", 2):
+        assert max(r["fwd0"], r["fwd1"]) < 1e-5 and max(r["bwd0"], r["bwd1"]) < 1e-6, r
+
+
 def test_data_parallel_matches_single(ref):
     res = run_distributed("train_parity", 2)
     _close(_last_stage_losses(res), ref, 2e-4)

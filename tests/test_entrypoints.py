@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -514,3 +515,48 @@ def test_vision_entrypoints_train_from_an_image_folder(tmp_path, script, extra):
     out = p.stdout + p.stderr
     assert p.returncode == 0, out[-3000:]
     assert re.search(r"iteration\s+3/\s+3 \|.*loss: [0-9.E+\-]+", out) and "validation loss at the end of training" in out
+
+
+def test_knowledge_distillation_from_a_teacher_checkpoint(tmp_path):
+    """--export-kd-teacher-load / --export-kd-cfg (reference post_training/model_provider.py + loss_func.py): a TP2 + SP student
+    of another width learns from a frozen teacher checkpoint through the logit KL and one intermediate pair (with a trained
+    projection); the teacher's architecture is read from model_config.yaml; --export-kd-finalize then resumes the plain student."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    common = [("8" if a == "4" and COMMON[i - 1] == "--global-batch-size" else a) for i, a in enumerate(COMMON)]
+    common = [a for i, a in enumerate(common) if a not in ("--num-layers", "--hidden-size", "--num-attention-heads")
+              and common[i - 1] not in ("--num-layers", "--hidden-size", "--num-attention-heads")]
+    tp = ["--tensor-model-parallel-size", "2", "--sequence-parallel"]
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                            "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "pretrain_gpt.py"), *common, *tp, *extra],
+                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-3000:]
+        return out
+
+    teacher, student, final = (str(tmp_path / d) for d in ("teacher", "student", "final"))
+    run("--num-layers", "2", "--hidden-size", "32", "--num-attention-heads", "4", "--save", teacher, "--save-interval", "3")
+    with open(os.path.join(teacher, "model_config.yaml"), "w") as f:
+        f.write("num_layers: 2\nhidden_size: 32\nnum_attention_heads: 4\nencoder_seq_length: 32\nbias: true\n")
+    cfg = str(tmp_path / "kd.yaml")
+    with open(cfg, "w") as f:
+        f.write('logit_layers: ["output_layer", "output_layer"]\n'
+                'intermediate_layer_pairs:\n  - ["decoder.final_layernorm", "decoder.layers.1.input_layernorm"]\n'
+                "skip_lm_loss: false\nkd_loss_scale: 2.0\n")
+    small = ["--num-layers", "1", "--hidden-size", "16", "--num-attention-heads", "2"]
+    out = run(*small, "--export-kd-teacher-load", teacher, "--export-kd-cfg", cfg, "--save", student, "--save-interval", "3",
+              "--ckpt-format", "torch")
+    assert "building the distillation teacher (2 layers, hidden size 32)" in out
+    kd = [float(x) for x in re.findall(r"kd loss: ([0-9.E+\-]+)", out)]
+    assert len(kd) == 3 and all(0 < v < 1 for v in kd) and kd[-1] < kd[0], kd
+    assert "kd loss" not in out.split("validation loss at the end of training")[1]        # evaluation reports the LM loss only
+    sd = torch.load(os.path.join(student, "iter_0000003", "mp_rank_00", "model_optim_rng.pt"), weights_only=False)["model"]
+    assert sd["kd_projections.0.fit.weight"].shape == (32, 16)
+    out = run(*small, "--export-kd-teacher-load", teacher, "--export-kd-finalize", "--load", student, "--save", final,
+              "--save-interval", "4", "--train-iters", "4", "--override-opt_param-scheduler", "--ckpt-format", "torch")
+    assert re.search(r"iteration\s+4/\s+4 \|", out) and "kd loss" not in out
+    sd = torch.load(os.path.join(final, "iter_0000004", "mp_rank_00", "model_optim_rng.pt"), weights_only=False)["model"]
+    assert not [k for k in sd if k.startswith("kd_")]
