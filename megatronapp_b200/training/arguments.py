@@ -243,7 +243,8 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--use-dist-ckpt", action="store_true", dest="use_dist_ckpt_deprecated")
     _add(g, "--auto-detect-ckpt-format", action="store_true")
     _add(g, "--dist-ckpt-format", dest="dist_ckpt_format_deprecated", default=None)
-    _add(g, "--ckpt-format", default="torch_dist", choices=["torch", "torch_dist", "zarr", "torch_dcp"])
+    _add(g, "--ckpt-format", default="torch_dist", choices=["torch", "torch_dist", "zarr", "torch_dcp", "b200_sharded"],
+         help="zarr / torch_dcp are accepted for compatibility and written in the torch_dist layout")
     _add(g, "--ckpt-convert-format", default=None, choices=["torch", "torch_dist", "zarr"])
     _add(g, "--ckpt-convert-save", default=None)
     _add(g, "--ckpt-fully-parallel-save", action="store_true", dest="ckpt_fully_parallel_save_deprecated")

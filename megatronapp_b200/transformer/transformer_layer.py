@@ -7,6 +7,7 @@ pre_mlp_layernorm -> mlp -> bias-dropout-add; ``get_transformer_layer_offset``).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
+import dataclasses
 from typing import Dict, Optional, Union
 
 import torch
@@ -55,11 +56,23 @@ class TransformerLayerSubmodules:
     sharded_state_dict_keys_map: Dict[str, str] = field(default_factory=dict)
 
 
+def layer_precision_config(config, layer_number: int):
+    """--first-last-layers-bf16 (reference ``fp8_utils.is_first_last_bf16_layer``): the first
+    ``num_layers_at_start_in_bf16`` and the last ``num_layers_at_end_in_bf16`` layers of an fp8 model keep bf16 GEMMs."""
+    if not (getattr(config, "fp8", None) and getattr(config, "first_last_layers_bf16", False)):
+        return config
+    n = config.num_layers
+    if layer_number <= config.num_layers_at_start_in_bf16 or layer_number > n - config.num_layers_at_end_in_bf16:
+        return dataclasses.replace(config, fp8=None)
+    return config
+
+
 class TransformerLayer(MegatronModule):
     def __init__(self, config, submodules: TransformerLayerSubmodules, layer_number: int = 1,
                  hidden_dropout: Optional[float] = None):
-        super().__init__(config)
         self.layer_number = layer_number + get_transformer_layer_offset(config)
+        config = layer_precision_config(config, self.layer_number)
+        super().__init__(config)
         self.hidden_dropout = config.hidden_dropout if hidden_dropout is None else hidden_dropout
         eps = config.layernorm_epsilon
         self.input_layernorm = build_module(submodules.input_layernorm, config=config,

@@ -5,6 +5,7 @@ import os
 if not os.path.exists("/dev/nvidia0"):
     os.environ.setdefault("OMP_NUM_THREADS", "2")
 
+import argparse
 import copy
 from functools import partial
 
@@ -27,7 +28,13 @@ def add_vlm_extra_args(parser):
     g.add_argument("--img-h", type=int, default=336)
     g.add_argument("--img-w", type=int, default=336)
     g.add_argument("--patch-dim", type=int, default=14)
-    g.add_argument("--vision-model-type", default="clip", choices=["clip", "siglip", "radio"])
+
+    def _vision_type(v):
+        if v in ("clip", "siglip", "radio") or v.startswith("hf://"):
+            return v
+        raise argparse.ArgumentTypeError("clip | siglip | radio | hf://<transformers checkpoint>")
+
+    g.add_argument("--vision-model-type", default="clip", type=_vision_type)
     g.add_argument("--max-img-h", type=int, default=2048)
     g.add_argument("--max-img-w", type=int, default=2048)
     g.add_argument("--vision-num-layers", type=int, default=None)

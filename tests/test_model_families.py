@@ -593,3 +593,21 @@ def test_huggingface_towers_and_llava_with_an_hf_vision_encoder(tmp_path):
     ps_ = get_packed_seq_params(torch.zeros(2, 10, dtype=torch.long), img_seq_len=6, padding_needed=4, cp_size=2)
     assert ps_.qkv_format == "thd" and ps_.cu_seqlens_q.tolist() == [0, 12, 24] and ps_.cu_seqlens_q_padded.tolist() == [0, 16, 32]
     assert get_packed_seq_params(torch.zeros(2, 10, dtype=torch.long), 6, 0, 1).qkv_format == "sbhd"
+
+
+def test_first_and_last_layers_stay_bf16_in_an_fp8_model():
+    """--first-last-layers-bf16 (reference fp8_utils.is_first_last_bf16_layer): only the inner layers get an fp8 recipe."""
+    from megatronapp_b200.models.gpt import GPTModel, get_gpt_layer_local_spec
+
+    _init()
+    cfg = _cfg(num_layers=5, fp8="hybrid", first_last_layers_bf16=True, num_layers_at_start_in_bf16=1, num_layers_at_end_in_bf16=2)
+    m = GPTModel(config=cfg, transformer_layer_spec=get_gpt_layer_local_spec(), vocab_size=64, max_sequence_length=16)
+    assert [l.mlp.linear_fc1.fp8_recipe is not None for l in m.decoder.layers] == [False, True, True, False, False]
+    assert [l.self_attention.linear_proj.fp8_recipe is not None for l in m.decoder.layers] == [False, True, True, False, False]
+    ids = torch.randint(0, 64, (2, 16))
+    loss = m(ids, torch.arange(16)[None].expand(2, -1), None, labels=ids).mean()
+    loss.backward()
+    assert torch.isfinite(loss)
+    plain = GPTModel(config=_cfg(num_layers=5, fp8="hybrid"), transformer_layer_spec=get_gpt_layer_local_spec(), vocab_size=64,
+                     max_sequence_length=16)
+    assert all(l.mlp.linear_fc1.fp8_recipe is not None for l in plain.decoder.layers)
