@@ -173,6 +173,39 @@ def get_optimizer_param_scheduler(optimizer):
         wsd_decay_steps=wsd_decay_steps, lr_wsd_decay_style=args.lr_wsd_decay_style)
 
 
+def _upcycle_dense_checkpoint(args, model_provider_func, model_type, model, optimizer):
+    """--moe-use-upcycling (reference training.py:1284-1311): build the dense twin of this MoE model, load the dense checkpoint
+    from --load into it, seed every expert from the dense MLP, save the result as iteration 1 under --save and start from
+    iteration 0.  Only for the first run of a conversion: a --save directory that already holds a checkpoint is an error."""
+    from ..moe import upcycling_utils
+
+    if dist.is_initialized():
+        dist.barrier()
+    if args.save and os.path.isfile(checkpointing.get_checkpoint_tracker_filename(args.save)):
+        raise RuntimeError("the upcycling destination already holds a checkpoint: --moe-use-upcycling is only for the first "
+                           "run that converts the dense model; remove the flag to resume")
+    if not args.load:
+        raise ValueError("--moe-use-upcycling needs --load <dense checkpoint>")
+    keep = (args.num_experts, args.expert_model_parallel_size, args.finetune, args.no_load_rng)
+    args.num_experts, args.expert_model_parallel_size, args.finetune, args.no_load_rng = None, 1, True, True
+    try:
+        dense = get_model(model_provider_func, model_type, wrap_with_ddp=False)
+        _, flops = upcycling_utils.load_and_upcycle_model(
+            checkpointing.load_checkpoint, unwrap_model(model), dense,
+            load_kwargs={"model": dense, "optimizer": None, "opt_param_scheduler": None, "load_arg": "load"})
+    finally:
+        args.num_experts, args.expert_model_parallel_size, args.finetune, args.no_load_rng = keep
+    del dense
+    if optimizer is not None and hasattr(optimizer, "reload_model_params"):
+        optimizer.reload_model_params()
+    args.num_floating_point_operations_so_far = flops
+    if args.save:
+        checkpointing.save_checkpoint(1, model, None, None, flops)
+        checkpointing.maybe_finalize_async_save(blocking=True)
+        print_rank_0(f"upcycled checkpoint saved to {args.save}")
+    args.iteration = 0
+
+
 def setup_model_and_optimizer(model_provider_func, model_type=None, no_wd_decay_cond=None, scale_lr_cond=None,
                               lr_mult=1.0):
     args = get_args()
@@ -191,7 +224,9 @@ def setup_model_and_optimizer(model_provider_func, model_type=None, no_wd_decay_
     config.timers = get_timers()
     optimizer = get_megatron_optimizer(config, model, no_wd_decay_cond, scale_lr_cond, lr_mult)
     scheduler = get_optimizer_param_scheduler(optimizer)
-    if args.load is not None or args.pretrained_checkpoint is not None:
+    if args.moe_use_upcycling:
+        _upcycle_dense_checkpoint(args, model_provider_func, model_type, model, optimizer)
+    elif args.load is not None or args.pretrained_checkpoint is not None:
         load_arg = "load" if (args.load and os.path.isfile(checkpointing.get_checkpoint_tracker_filename(args.load))) \
             else ("pretrained_checkpoint" if args.pretrained_checkpoint else "load")
         args.iteration, args.num_floating_point_operations_so_far = checkpointing.load_checkpoint(

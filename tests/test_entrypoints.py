@@ -560,3 +560,34 @@ def test_knowledge_distillation_from_a_teacher_checkpoint(tmp_path):
     assert re.search(r"iteration\s+4/\s+4 \|", out) and "kd loss" not in out
     sd = torch.load(os.path.join(final, "iter_0000004", "mp_rank_00", "model_optim_rng.pt"), weights_only=False)["model"]
     assert not [k for k in sd if k.startswith("kd_")]
+
+
+def test_moe_upcycling_from_a_dense_checkpoint(tmp_path):
+    """--moe-use-upcycling (reference training.py:1284-1311): a 4-expert EP2 model seeded from a trained dense checkpoint evaluates
+    to the dense model's loss, the upcycled weights are saved as iteration 1, and repeating the flag on that directory is refused."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    common = [("8" if a == "4" and COMMON[i - 1] == "--global-batch-size" else a) for i, a in enumerate(COMMON)]
+    common += ["--attention-dropout", "0", "--hidden-dropout", "0"]
+    moe = ["--num-experts", "4", "--expert-model-parallel-size", "2", "--moe-router-topk", "2", "--moe-token-dispatcher-type", "alltoall"]
+
+    def run(*extra, ok=True):
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                            "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "pretrain_gpt.py"), *common, *extra],
+                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        out = p.stdout + p.stderr
+        assert (p.returncode == 0) == ok, out[-3000:]
+        return out
+
+    def val(out):
+        return re.findall(r"validation loss at the end of training for val data \| lm loss value: ([0-9.E+\-]+)", out)
+
+    dense, up = str(tmp_path / "dense"), str(tmp_path / "moe")
+    ref = val(run("--save", dense, "--save-interval", "3"))
+    out = run(*moe, "--moe-use-upcycling", "--load", dense, "--save", up, "--skip-train")
+    assert "upcycled checkpoint saved" in out and val(out) == ref and len(ref) == 1
+    assert os.path.isdir(os.path.join(up, "iter_0000001"))
+    out = run(*moe, "--load", up, "--skip-train", "--finetune")                  # the saved MoE checkpoint reproduces it too
+    assert val(out) == ref
+    assert "only for the first" in run(*moe, "--moe-use-upcycling", "--load", dense, "--save", up, ok=False)
