@@ -42,6 +42,7 @@ class DistributedDataParallelConfig:
     use_distributed_optimizer: bool = False
     num_distributed_optimizer_instances: int = 1
     check_for_nan_in_grad: bool = False
+    check_for_large_grads: bool = False
     bucket_size: Optional[int] = None
     average_in_collective: bool = False
     fp8_param_gather: bool = False
@@ -170,6 +171,16 @@ class ParamAndGradBuffer:
         if self.ddp_config.check_for_nan_in_grad:
             if not torch.isfinite(g.float().sum()):
                 raise RuntimeError(f"NaN/Inf in gradients of bucket {bucket.bucket_id} before reduction")
+        if self.ddp_config.check_for_large_grads:
+            # reference param_and_grad_buffer.py:180-190: a bucket norm 10x the largest seen so far is reported / re-run
+            from functools import partial
+
+            from ..training.rerun_state_machine import get_rerun_state_machine
+
+            rsm = get_rerun_state_machine()
+            rsm.validate_result(g.float().norm(), partial(rsm.is_unexpectedly_large, threshold=10, context="grads"),
+                                "found unexpected large grads in bucket before data-parallel communication collective",
+                                tolerance=0.001, fatal=False)
         if not _is_real_group(self.group):
             if self.gradient_scaling_factor != 1.0:
                 ops.scale_(g, self.gradient_scaling_factor)

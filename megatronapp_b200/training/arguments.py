@@ -252,7 +252,9 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--async-save", action="store_true", default=None)
     _add(g, "--ckpt-fully-parallel-load", action="store_true")
     _add(g, "--ckpt-assume-constant-structure", action="store_true")
-    _add(g, "--dist-ckpt-strictness", type=str, default="assume_ok_unexpected")
+    _add(g, "--dist-ckpt-strictness", type=str, default="assume_ok_unexpected",
+         choices=["assume_ok_unexpected", "log_unexpected", "log_all", "raise_unexpected", "raise_all", "return_unexpected",
+                  "return_all", "ignore_all"])
     g = p.add_argument_group("mixed precision")
     _add(g, "--fp16", action="store_true")
     _add(g, "--bf16", action="store_true")
@@ -806,8 +808,10 @@ def core_transformer_config_from_args(args, config_class=None) -> TransformerCon
         from ..transformer.mlp import squared_relu
 
         kw["activation_func"] = squared_relu
-    else:
-        kw["bias_activation_fusion"] = False
+    elif args.onnx_safe and not args.openai_gelu:
+        from ..transformer.mlp import erf_gelu
+
+        kw["activation_func"] = erf_gelu        # --openai-gelu (tanh form) is what the default fused bias-GELU computes
     if args.init_method_xavier_uniform:
         kw["init_method"] = torch.nn.init.xavier_uniform_
     if args.group_query_attention:

@@ -397,13 +397,26 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
             model_keys = set(ssd)
             if want_opt:
                 ssd.update(optimizer.sharded_state_dict(ssd, is_loading=True))
+            mode = getattr(args, "dist_ckpt_strictness", None) or "assume_ok_unexpected"
+
+            def _load(req):
+                if mode == "assume_ok_unexpected":
+                    return torch_dist.load(req, base, strict=strict)
+                # --dist-ckpt-strictness: key mismatches are logged / raised / tolerated as StrictHandling says
+                from ..ckpt import serialization
+
+                res = serialization.load(req, base, strict=mode)
+                if isinstance(res, tuple) and (res[1] or res[2]) and (not dist.is_initialized() or dist.get_rank() == 0):
+                    print(f"checkpoint key mismatches: missing {res[1][:8]} unexpected {res[2][:8]}", flush=True)
+                return res
+
             try:
-                torch_dist.load(ssd, base, strict=strict)
+                _load(ssd)
             except KeyError:
                 if not want_opt:
                     raise
                 # optimizer tensors absent (saved with --no-save-optim or by another optimizer): weights only
-                torch_dist.load({k: v for k, v in ssd.items() if k in model_keys}, base, strict=strict)
+                _load({k: v for k, v in ssd.items() if k in model_keys})
                 want_opt = False
         if optimizer is not None:
             rank = dist.get_rank() if dist.is_initialized() else 0

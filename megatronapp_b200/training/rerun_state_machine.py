@@ -118,6 +118,8 @@ class RerunStateMachine:
         self.exit_code = 0
         self.data_iterators: List[RerunDataIterator] = []
         self.stats = {"validations": 0, "rejections": 0, "max_rel_diff": 0.0}
+        self.max_values: dict = {}
+        self.large_value_counts: dict = {}
 
     # -- loop protocol ------------------------------------------------------------------
     def should_run_forward_backward(self, data_iterator) -> bool:
@@ -149,9 +151,30 @@ class RerunStateMachine:
         self.current_iteration += 1
 
     # -- validation -----------------------------------------------------------------------
+    def is_unexpectedly_large(self, result, threshold: float, context: str, num_samples: int = 100, resample: bool = False) -> bool:
+        """Rejection function for spiky losses / gradients (reference rerun_state_machine.py:655): the first ``num_samples``
+        values of a ``context`` establish the largest magnitude seen, later values are flagged at ``threshold`` times that."""
+        value = abs(float(result.item() if torch.is_tensor(result) else result))
+        if math.isnan(value) or math.isinf(value):
+            return False                                  # checked separately
+        if resample or context not in self.large_value_counts:
+            self.large_value_counts[context] = 0
+        if self.large_value_counts[context] < num_samples:
+            self.large_value_counts[context] += 1
+            self.max_values[context] = max(self.max_values.get(context, 0.0), value)
+            return False
+        return value >= self.max_values[context] * threshold
+
     def validate_result(self, result, rejection_func: Callable[[Any], bool], message: str = "unexpected result",
                         tolerance: float = 0.0, fatal: bool = True) -> None:
         if self.mode == RerunMode.DISABLED:
+            # reruns off: still validate, a rejected fatal result stops the job (reference rerun_state_machine.py:491-508)
+            if rejection_func(float(result.item() if torch.is_tensor(result) else result)):
+                self.stats["rejections"] += 1
+                text = f"iteration {self.current_iteration}: unexpected result {float(result)} ({message})"
+                if fatal:
+                    raise RuntimeError(text)
+                print(f"WARNING: {text}", flush=True)
             return
         value = float(result.item() if torch.is_tensor(result) else result)
         if self.injector.maybe_inject(self.current_iteration, self.state):

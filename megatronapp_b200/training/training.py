@@ -123,6 +123,7 @@ def get_model(model_provider_func: Callable, model_type=None, wrap_with_ddp: boo
             use_distributed_optimizer=args.use_distributed_optimizer,
             num_distributed_optimizer_instances=args.num_distributed_optimizer_instances,
             check_for_nan_in_grad=False,
+            check_for_large_grads=args.check_for_large_grads,
             bucket_size=args.ddp_bucket_size,
             average_in_collective=args.ddp_average_in_collective,
             fused_grad_reduce_scatter=args.fused_grad_reduce_scatter,

@@ -29,6 +29,12 @@ def squared_relu(x):
     return torch.pow(F.relu(x), 2)
 
 
+def erf_gelu(x):
+    """Exact GELU (``--onnx-safe``; reference legacy/model/utils.py:erf_gelu).  The default activation is the tanh form
+    (``--openai-gelu`` and the reference's fused bias-GELU), computed in the GEMM epilogue."""
+    return F.gelu(x, approximate="none")
+
+
 class MLP(MegatronModule):
     def __init__(self, config, submodules: MLPSubmodules, is_expert: bool = False,
                  input_size: Optional[int] = None):

@@ -22,6 +22,9 @@ from megatronapp_b200.training.training import pretrain
 from megatronapp_b200.training.utils import get_batch_on_this_tp_rank, print_rank_0
 
 
+SPIKY_LOSS_FACTOR = 10          # a loss 10x the largest seen so far is re-examined (reference pretrain_gpt.py)
+
+
 def model_provider(pre_process=True, post_process=True):
     args = get_args()
     student = _build_model(args, pre_process, post_process)
@@ -106,7 +109,8 @@ def _build_model(args, pre_process=True, post_process=True):
                     share_embeddings_and_output_weights=not args.untie_embeddings_and_output_weights,
                     position_embedding_type=args.position_embedding_type, rotary_percent=args.rotary_percent,
                     rotary_base=args.rotary_base, rope_scaling=args.use_rope_scaling,
-                    rope_scaling_factor=args.rope_scaling_factor)
+                    rope_scaling_factor=args.rope_scaling_factor,
+                    seq_len_interpolation_factor=args.rotary_seq_len_interpolation_factor)
 
 
 def get_batch(data_iterator):
@@ -131,8 +135,14 @@ def loss_func(loss_mask, output_tensor):
         torch.distributed.all_reduce(loss, group=mpu.get_context_parallel_group())
     rsm = get_rerun_state_machine()
     if rsm.mode != "disabled":
-        # NaN / Inf / spiky-loss checks with re-execution (reference pretrain_gpt.py loss_func)
+        # NaN / Inf checks with re-execution (reference pretrain_gpt.py loss_func).  With reruns disabled the reference
+        # still synchronises on every microbatch loss here; this framework leaves that to the per-iteration NaN
+        # accounting of the training loop.
         rsm.validate_result(loss[0] / loss[1].clamp(min=1), lambda v: not math.isfinite(v), "found NaN/Inf in local loss")
+    if args.check_for_spiky_loss:
+        rsm.validate_result(loss[0] / loss[1].clamp(min=1),
+                            partial(rsm.is_unexpectedly_large, threshold=SPIKY_LOSS_FACTOR, context="loss"), "Spiky loss",
+                            tolerance=0.0, fatal=False)
     reporting = loss.clone().detach()
     g = mpu.get_data_parallel_group()
     if g is not None and not isinstance(g, mpu._SingleGroup) and torch.distributed.get_world_size(g) > 1:

@@ -591,3 +591,25 @@ def test_moe_upcycling_from_a_dense_checkpoint(tmp_path):
     out = run(*moe, "--load", up, "--skip-train", "--finetune")                  # the saved MoE checkpoint reproduces it too
     assert val(out) == ref
     assert "only for the first" in run(*moe, "--moe-use-upcycling", "--load", dense, "--save", up, ok=False)
+
+
+def test_dist_ckpt_strictness_modes(tmp_path):
+    """--dist-ckpt-strictness: loading a tied-embedding checkpoint into an untied model misses output_layer.weight -- raise_all
+    refuses, log_all reports and trains on, ignore_all trains on silently."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="",
+               OMP_NUM_THREADS="2")
+
+    def run(*extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *COMMON, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        return p.returncode, p.stdout + p.stderr
+
+    ck = str(tmp_path / "ck")
+    assert run("--save", ck, "--save-interval", "3")[0] == 0
+    untied = ["--untie-embeddings-and-output-weights", "--load", ck, "--finetune", "--no-load-optim", "--dist-ckpt-strictness"]
+    rc, out = run(*untied, "raise_all")
+    assert rc != 0 and "missing keys: ['output_layer.weight']" in out
+    rc, out = run(*untied, "log_all")
+    assert rc == 0 and "1 requested keys are not in the checkpoint" in out and re.search(r"iteration\s+3/\s+3 \|", out)
+    rc, out = run(*untied, "ignore_all")
+    assert rc == 0 and "requested keys are not" not in out and re.search(r"iteration\s+3/\s+3 \|", out)

@@ -19,7 +19,12 @@ def _run_step(rsm, it, compute):
 def test_disabled_mode_runs_once():
     rsm = RerunStateMachine(RerunMode.DISABLED)
     it = RerunDataIterator(iter(range(10)))
-    assert _run_step(rsm, it, lambda b, r: float("nan")) == 1 and next(it) == 1
+    assert _run_step(rsm, it, lambda b, r: 1.0) == 1 and next(it) == 1
+    try:                                   # reruns off: a rejected result still stops the job (reference behaviour)
+        _run_step(RerunStateMachine(RerunMode.DISABLED), RerunDataIterator(iter(range(10))), lambda b, r: float("nan"))
+        raise AssertionError("a NaN must be fatal")
+    except RuntimeError as e:
+        assert "loss check" in str(e)
 
 
 def test_transient_error_is_rerun_on_same_data_and_classified():
@@ -109,3 +114,21 @@ def test_file_autoresume_protocol(tmp_path):
         assert ar.FileAutoResume(None, deadline=1.0).termination_requested()
     finally:
         ar.set_adlr_autoresume(None)
+
+
+def test_spiky_value_detection_and_disabled_mode_validation():
+    """is_unexpectedly_large (reference rerun_state_machine.py:655): 10x the largest of the first samples is rejected; with reruns
+    disabled a rejected fatal result raises, a non-fatal one only warns."""
+    import pytest
+    from functools import partial
+
+    m = RerunStateMachine(mode="disabled")
+    big = partial(m.is_unexpectedly_large, threshold=10, context="loss", num_samples=5)
+    assert not any(big(v) for v in (2.0, 3.0, 2.5, 1.0, 2.0))          # sampling phase
+    assert not big(29.0) and big(31.0) and not big(float("nan"))
+    assert not m.is_unexpectedly_large(1e9, threshold=10, context="grads", num_samples=5)      # contexts are independent
+    m.validate_result(31.0, big, "Spiky loss", fatal=False)
+    assert m.stats["rejections"] == 1
+    with pytest.raises(RuntimeError, match="Spiky loss"):
+        m.validate_result(31.0, big, "Spiky loss", fatal=True)
+    m.validate_result(2.0, big, "Spiky loss", fatal=True)
