@@ -325,6 +325,9 @@ def maybe_finalize_async_save(blocking: bool = False):
                 return
         _PENDING.pop(0)
         _complete(rec)
+        from . import ft_integration
+
+        ft_integration.on_checkpointing_end(is_async_finalization=True)
 
 
 def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", strict=True, args=None):
@@ -490,6 +493,10 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
             args.consumed_valid_samples = getattr(ca, "consumed_valid_samples", 0)
     if dist.is_initialized():
         dist.barrier()
+    if load_arg == "load":
+        from . import ft_integration
+
+        ft_integration.on_checkpoint_loaded(is_local_chkpt=local_sd is not None)
     print(f"  successfully loaded checkpoint from {load_dir} at iteration {iteration}", flush=True) \
         if (not dist.is_initialized() or dist.get_rank() == 0) else None
     return iteration, sd.get("num_floating_point_operations_so_far", 0)

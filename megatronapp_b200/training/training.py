@@ -28,7 +28,7 @@ from ..scan.tracer import get_tracer
 from ..transformer.module import Float16Module
 from ..utils.microbatches import get_current_global_batch_size, get_num_microbatches, update_num_microbatches
 from ..utils.straggler import get_straggler_detector
-from . import checkpointing
+from . import checkpointing, ft_integration
 from .rerun_state_machine import (RerunDataIterator, RerunErrorInjector, get_rerun_state_machine,
                                   initialize_rerun_state_machine)
 from .arguments import core_transformer_config_from_args
@@ -422,9 +422,11 @@ def evaluate(forward_step_func, data_iterator, model, config, verbose=False):
     n = 0
     with torch.no_grad():
         for it in range(args.eval_iters):
+            ft_integration.on_eval_step_start()
             out = fb(forward_step_func=forward_step_func, data_iterator=data_iterator, model=model,
                      num_microbatches=get_num_microbatches(), seq_length=args.seq_length,
                      micro_batch_size=args.micro_batch_size, forward_only=True)
+            ft_integration.on_eval_step_end()
             if ps.is_pipeline_last_stage(ignore_virtual=True):
                 for d in out:
                     for k, v in d.items():
@@ -492,7 +494,9 @@ def compute_throughputs_and_append_to_progress_log(iteration, num_floating_point
 def save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far):
     timers = get_timers()
     timers("save-checkpoint", log_level=0).start(barrier=True)
+    ft_integration.on_checkpointing_start()
     checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, num_floating_point_operations_so_far)
+    ft_integration.on_checkpointing_end(is_async_finalization=False)
     timers("save-checkpoint").stop(barrier=True)
     timers.log(["save-checkpoint"])
     compute_throughputs_and_append_to_progress_log(iteration, num_floating_point_operations_so_far)
@@ -558,9 +562,11 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if getattr(args, '_fault_deadline', None) and time.time() > args._fault_deadline:
             while True:
                 time.sleep(3600)
+        ft_integration.on_training_step_start()
         with stimer:
             loss_dict, skipped_iter, should_ckpt, should_exit, exit_code, grad_norm, num_zeros = train_step(
                 forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler, config)
+        ft_integration.on_training_step_end()
         if should_exit:
             if should_ckpt and args.save:
                 save_checkpoint_and_time(iteration, model, optimizer, opt_param_scheduler, nflops)
@@ -800,6 +806,9 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     args = get_args()
     timers = get_timers()
     print_rank_0(f"time to initialize megatron (seconds): {time.time() - _TRAIN_START_TIME:.3f}")
+    if args.enable_ft_package:
+        ft_integration.setup(args)
+        ft_integration.maybe_setup_simulated_fault()
     if args.use_dpp:
         from ..dpp.scheduler import install_dpp_schedule
 
@@ -872,4 +881,5 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
 
         shutdown_dpp()
     p2p.flush()
+    ft_integration.shutdown()
     return model, optimizer

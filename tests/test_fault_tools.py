@@ -132,3 +132,62 @@ def test_spiky_value_detection_and_disabled_mode_validation():
     with pytest.raises(RuntimeError, match="Spiky loss"):
         m.validate_result(31.0, big, "Spiky loss", fatal=True)
     m.validate_result(2.0, big, "Spiky loss", fatal=True)
+
+
+def test_rank_monitor_sections_and_learned_timeouts(tmp_path):
+    """ft_integration (reference training/ft_integration.py): sections are timed, --calc-ft-timeouts turns the observed maxima
+    into timeouts (x SAFETY_FACTOR), persists them next to the checkpoints and the next setup() loads them."""
+    import json
+    import time
+    from types import SimpleNamespace
+
+    from megatronapp_b200.training import ft_integration as ft
+
+    args = SimpleNamespace(save=str(tmp_path), calc_ft_timeouts=True, async_save=False)
+    ft.setup(args)
+    cli = ft.get_rank_monitor_client()
+    assert cli.section == "setup" and cli.section_timeouts["step"] == 600.0
+    ft.on_checkpoint_loaded(is_local_chkpt=False)
+    for _ in range(ft.NUM_WARMUP_ITERS + ft.MIN_ITERS_FOR_STEP_TIMEOUT_UPDATE):
+        ft.on_training_step_start()
+        time.sleep(0.01)
+        ft.on_training_step_end()
+    assert cli.section is None and 0.005 < cli.observed["step"] < 1.0
+    ft.on_checkpointing_start()
+    time.sleep(0.02)
+    ft.on_checkpointing_end()
+    state = json.load(open(tmp_path / "ft_state.json"))["section_timeouts"]
+    assert state["step"] < 10 and state["checkpointing"] < 10 and state["setup"] < 100 and state["out_of_section"] == 3600.0
+    ft.shutdown()                                                     # a complete run also learns the out-of-section timeout
+    assert json.load(open(tmp_path / "ft_state.json"))["section_timeouts"]["out_of_section"] < 100
+    assert ft.get_rank_monitor_client() is None
+    ft.setup(SimpleNamespace(save=str(tmp_path), calc_ft_timeouts=False, async_save=True))
+    assert ft.get_rank_monitor_client().section_timeouts["step"] == state["step"]
+    ft.shutdown()
+
+
+def test_hung_rank_is_terminated_by_the_watchdog(tmp_path):
+    """--enable-ft-package: a rank that stops making progress (--simulated-fault rank_hung) overstays its section, the watchdog
+    dumps the stacks and exits with the restart code instead of idling forever."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    save = tmp_path / "ck"
+    save.mkdir()
+    json.dump({"section_timeouts": {"setup": 120.0, "step": 60.0, "checkpointing": 60.0, "out_of_section": 3.0}},
+              open(save / "ft_state.json", "w"))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29877", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, os.path.join(root, "pretrain_gpt.py"), "--num-layers", "1", "--hidden-size", "16", "--num-attention-heads", "2",
+           "--seq-length", "16", "--max-position-embeddings", "16", "--micro-batch-size", "1", "--global-batch-size", "1",
+           "--train-iters", "100000", "--lr", "1e-3", "--vocab-size", "64", "--mock-data", "--log-interval", "1000", "--eval-interval",
+           "100000", "--eval-iters", "0", "--distributed-backend", "gloo", "--no-gradient-accumulation-fusion", "--save", str(save),
+           "--save-interval", "100000", "--enable-ft-package", "--simulated-fault", "rank_hung:0:1"]
+    p = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    out = p.stdout + p.stderr
+    assert p.returncode == 18, out[-2000:]
+    assert "FT: loaded timeouts" in out and "'out_of_section' exceeded its timeout of 3.0 s" in out
+    assert "Thread 0x" in out or "Current thread" in out            # faulthandler stack dump
