@@ -170,9 +170,30 @@ def parse_blend(data_path: List[str]):
     return [data_path[i + 1] for i in range(0, len(data_path), 2)], [float(data_path[i]) for i in range(0, len(data_path), 2)]
 
 
+def blend_and_blend_per_split(args):
+    """(blend, per-split blends) from the data flags, as the reference's ``get_blend_and_blend_per_split``: ``--data-path`` or a
+    file holding it (``--data-args-path``) give ONE blend cut by ``--split``; ``--train-data-path / --valid-data-path /
+    --test-data-path`` or a JSON ``{"train": [...], "valid": [...], "test": [...]}`` (``--per-split-data-args-path``) give each
+    split its own blend, used whole."""
+    import json
+
+    blend = getattr(args, "data_path", None)
+    if getattr(args, "data_args_path", None):
+        with open(args.data_args_path) as f:
+            blend = f.read().split()
+    per_split = [getattr(args, f"{n}_data_path", None) for n in ("train", "valid", "test")]
+    if getattr(args, "per_split_data_args_path", None):
+        with open(args.per_split_data_args_path) as f:
+            cfg = json.load(f)
+        per_split = [cfg.get(n) for n in ("train", "valid", "test")]
+    if any(per_split):
+        if blend:
+            raise ValueError("give either --data-path (one blend, cut by --split) or the per-split data paths, not both")
+        return None, per_split
+    return blend, None
+
+
 def build_gpt_datasets(args, train_val_test_num_samples):
-    prefixes, weights = parse_blend(args.data_path)
-    split = parse_split(args.split or "969,30,1")
     eod = 0
     tok = None
     try:
@@ -182,31 +203,48 @@ def build_gpt_datasets(args, train_val_test_num_samples):
         eod = tok.eod if tok is not None else 0
     except Exception:
         pass
+
+    def dataset(ds, doc_range, n, name):
+        return GPTDataset(ds, doc_range, n, args.seq_length, args.seed, name, args.data_cache_path, eod, args.reset_position_ids,
+                          args.reset_attention_mask, args.eod_mask_loss, args.create_attention_mask_in_dataloader)
+
+    def blended(parts, weights, n):
+        parts_w = [(d, w) for d, w in zip(parts, weights) if d is not None]
+        if not parts_w:
+            return None
+        if len(parts_w) == 1:
+            return parts_w[0][0]
+        return BlendedDataset([d for d, _ in parts_w], [w for _, w in parts_w], int(n))
+
+    blend, blend_per_split = blend_and_blend_per_split(args)
+    names = ("train", "valid", "test")
+    if blend_per_split is not None:
+        out = []
+        for name, paths, n in zip(names, blend_per_split, train_val_test_num_samples):
+            if not paths or n <= 0:
+                out.append(None)
+                continue
+            prefixes, weights = parse_blend(paths)
+            parts = []
+            for prefix, w in zip(prefixes, weights):
+                ds = IndexedDataset(prefix, mmap=args.mmap_bin_files)
+                ndoc = len(ds.document_indices) - 1
+                parts.append(dataset(ds, (0, ndoc), max(1, int(np.ceil(n * w / sum(weights) * 1.005))), name) if ndoc > 0 else None)
+            out.append(blended(parts, weights, n))
+        return tuple(out)
+    prefixes, weights = parse_blend(blend)
+    split = parse_split(args.split or "969,30,1")
     per_split: List[List[GPTDataset]] = [[], [], []]
-    for prefix in prefixes:
+    for prefix, w in zip(prefixes, weights):
         ds = IndexedDataset(prefix, mmap=args.mmap_bin_files)
         ranges = split_document_ranges(len(ds.document_indices) - 1, split)
-        for i, (name, n) in enumerate(zip(("train", "valid", "test"), train_val_test_num_samples)):
+        for i, (name, n) in enumerate(zip(names, train_val_test_num_samples)):
             lo, hi = ranges[i]
             if hi - lo <= 0 or n <= 0:
                 per_split[i].append(None)
                 continue
-            share = weights[prefixes.index(prefix)] / sum(weights)
-            per_split[i].append(GPTDataset(ds, (lo, hi), max(1, int(np.ceil(n * share * 1.005))), args.seq_length,
-                                           args.seed, name, args.data_cache_path, eod, args.reset_position_ids,
-                                           args.reset_attention_mask, args.eod_mask_loss,
-                                           args.create_attention_mask_in_dataloader))
-    out = []
-    for i, n in enumerate(train_val_test_num_samples):
-        ds = [d for d in per_split[i] if d is not None]
-        if not ds:
-            out.append(None)
-        elif len(ds) == 1:
-            out.append(ds[0])
-        else:
-            ws = [w for w, d in zip(weights, per_split[i]) if d is not None]
-            out.append(BlendedDataset(ds, ws, int(n)))
-    return tuple(out)
+            per_split[i].append(dataset(ds, (lo, hi), max(1, int(np.ceil(n * w / sum(weights) * 1.005))), name))
+    return tuple(blended(per_split[i], weights, n) for i, n in enumerate(train_val_test_num_samples))
 
 
 def __getattr__(name):      # names the reference exposes from ``core/datasets/gpt_dataset.py`` that live in sibling modules here

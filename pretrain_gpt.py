@@ -185,7 +185,9 @@ def forward_step(data_iterator, model):
 def train_valid_test_datasets_provider(train_val_test_num_samples):
     args = get_args()
     print_rank_0("> building train, validation, and test datasets for GPT ...")
-    if args.mock_data or not args.data_path:
+    real_data = (args.data_path or args.data_args_path or args.per_split_data_args_path or args.train_data_path
+                 or args.valid_data_path or args.test_data_path)
+    if args.mock_data or not real_data:
         vs = args.padded_vocab_size
         mk = lambda n, seed: MockGPTDataset(max(int(n), 1), args.seq_length, vs, seed,  # noqa: E731
                                             create_attention_mask=args.create_attention_mask_in_dataloader)

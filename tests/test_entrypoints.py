@@ -613,3 +613,47 @@ def test_dist_ckpt_strictness_modes(tmp_path):
     assert rc == 0 and "1 requested keys are not in the checkpoint" in out and re.search(r"iteration\s+3/\s+3 \|", out)
     rc, out = run(*untied, "ignore_all")
     assert rc == 0 and "requested keys are not" not in out and re.search(r"iteration\s+3/\s+3 \|", out)
+
+
+def test_per_split_data_paths(tmp_path):
+    """--train-data-path / --valid-data-path (each split from its own blend, used whole) and the file forms --data-args-path /
+    --per-split-data-args-path (reference get_blend_and_blend_per_split)."""
+    import json
+
+    tok = ["--tokenizer-type", "GPT2BPETokenizer", "--vocab-file", os.path.join(ROOT, "datasets_gpt", "vocab.json"),
+           "--merge-file", os.path.join(ROOT, "datasets_gpt", "merges.txt")]
+    with open(os.path.join(ROOT, "datasets_gpt", "dataset.json")) as f:
+        lines = [next(f) for _ in range(160)]
+    for name, part in (("a", lines[:100]), ("b", lines[100:130]), ("c", lines[130:])):
+        with open(tmp_path / f"{name}.jsonl", "w") as g:
+            g.writelines(part)
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "preprocess_data.py"), "--input", str(tmp_path / f"{name}.jsonl"),
+                            "--output-prefix", str(tmp_path / name), "--workers", "1", "--append-eod", *tok],
+                           cwd=ROOT, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+    a, b, c = (str(tmp_path / f"{n}_text_document") for n in "abc")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    common = [x for x in COMMON if x != "--mock-data"]
+    i = common.index("--vocab-size")
+    common = common[:i] + common[i + 2:]
+
+    def run(*extra, ok=True):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *common, *tok, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        out = p.stdout + p.stderr
+        assert (p.returncode == 0) == ok, out[-3000:]
+        return out
+
+    def losses(out):
+        return re.findall(r"lm loss: ([0-9.E+\-]+)", out), re.findall(r"for (val|test) data \| lm loss value: ([0-9.E+\-]+)", out)
+
+    ref = losses(run("--train-data-path", "0.7", a, "0.3", c, "--valid-data-path", b))
+    assert len(ref[0]) == 3 and [k for k, _ in ref[1]] == ["val"]                       # no test split given: no test evaluation
+    cfg = tmp_path / "splits.json"
+    json.dump({"train": ["0.7", a, "0.3", c], "valid": [b]}, open(cfg, "w"))
+    assert losses(run("--per-split-data-args-path", str(cfg))) == ref
+    blend = tmp_path / "blend.txt"
+    blend.write_text(f"0.7 {a} 0.3 {c}\n")
+    one = losses(run("--data-args-path", str(blend), "--split", "90,5,5"))
+    assert len(one[0]) == 3 and one != ref
+    assert "not both" in run("--data-path", a, "--valid-data-path", b, ok=False)
