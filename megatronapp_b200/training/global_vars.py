@@ -35,8 +35,31 @@ def get_tokenizer():
     return _TOKENIZER
 
 
+class _ScalarFanOut:
+    """What ``training_log`` writes scalars to: TensorBoard and / or Weights & Biases behind one ``add_scalar``."""
+
+    def __init__(self, tb, wandb_run):
+        self.tb, self.wandb = tb, wandb_run
+
+    def add_scalar(self, name, value, step):
+        if self.tb is not None:
+            self.tb.add_scalar(name, value, step)
+        if self.wandb is not None:
+            self.wandb.log({name: value}, step=int(step))
+
+    def add_text(self, *a, **k):
+        if self.tb is not None:
+            self.tb.add_text(*a, **k)
+
+    def flush(self):
+        if self.tb is not None:
+            self.tb.flush()
+
+
 def get_tensorboard_writer():
-    return _TB_WRITER
+    if _TB_WRITER is None and _WANDB_WRITER is None:
+        return None
+    return _ScalarFanOut(_TB_WRITER, _WANDB_WRITER)
 
 
 def get_wandb_writer():
@@ -58,8 +81,12 @@ def get_signal_handler():
 
 
 def set_global_variables(args, build_tokenizer: bool = True):
-    global _ARGS, _TOKENIZER, _TIMERS, _TB_WRITER, _SIGNAL_HANDLER
+    global _ARGS, _TOKENIZER, _TIMERS, _TB_WRITER, _SIGNAL_HANDLER, _WANDB_WRITER
     _ARGS = args
+    if getattr(args, "logging_level", None) is not None:
+        import logging
+
+        logging.getLogger().setLevel(int(args.logging_level))
     from ..utils.microbatches import init_num_microbatches_calculator
 
     init_num_microbatches_calculator(args.rank, args.rampup_batch_size, args.global_batch_size,
@@ -77,6 +104,23 @@ def set_global_variables(args, build_tokenizer: bool = True):
             _TB_WRITER = SummaryWriter(log_dir=args.tensorboard_dir, max_queue=args.tensorboard_queue_size)
         except Exception:
             print("WARNING: TensorBoard writing requested but is not available", flush=True)
+    if getattr(args, "wandb_project", None) and args.rank == args.world_size - 1:
+        # reference global_vars._set_wandb_writer: last rank, run directory under --wandb-save-dir (or <save>/wandb);
+        # WANDB_MODE=offline keeps it local (no network on the training nodes)
+        if not getattr(args, "wandb_exp_name", None):
+            raise ValueError("please specify the wandb experiment name (--wandb-exp-name)")
+        try:
+            import os
+
+            import wandb
+
+            save_dir = args.wandb_save_dir or os.path.join(args.save or ".", "wandb")
+            os.makedirs(save_dir, exist_ok=True)
+            wandb.init(dir=save_dir, name=args.wandb_exp_name, project=args.wandb_project,
+                       config={k: (v if isinstance(v, (int, float, str, bool, type(None))) else str(v)) for k, v in vars(args).items()})
+            _WANDB_WRITER = wandb
+        except ImportError:
+            print("WARNING: --wandb-project given but the wandb package is not available", flush=True)
     tracer = _get_tracer()
     tracer.configure(args.trace, args.trace_dir, args.trace_interval, args.continuous_trace_iterations,
                      args.trace_granularity)
@@ -91,8 +135,10 @@ def set_global_variables(args, build_tokenizer: bool = True):
 
 
 def unset_global_variables():
-    global _ARGS, _TOKENIZER, _TIMERS, _TB_WRITER, _SIGNAL_HANDLER
-    _ARGS = _TOKENIZER = _TIMERS = _TB_WRITER = _SIGNAL_HANDLER = None
+    global _ARGS, _TOKENIZER, _TIMERS, _TB_WRITER, _SIGNAL_HANDLER, _WANDB_WRITER
+    if _WANDB_WRITER is not None:
+        _WANDB_WRITER.finish()
+    _ARGS = _TOKENIZER = _TIMERS = _TB_WRITER = _SIGNAL_HANDLER = _WANDB_WRITER = None
     from ..utils.microbatches import destroy_num_microbatches_calculator
 
     destroy_num_microbatches_calculator()

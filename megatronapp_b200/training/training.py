@@ -379,6 +379,11 @@ def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scal
         if writer:
             writer.add_scalar("iteration-time", per_iter, iteration)
             writer.add_scalar("throughput", throughput, iteration)
+            if args.log_world_size_to_tensorboard:
+                writer.add_scalar("world-size", args.world_size, iteration)
+            if args.log_timers_to_tensorboard:
+                timers.write([n for n in timers._timers if n != "interval-time"], writer, iteration,
+                             normalizer=args.log_interval, reset=False)
         s = f" [{time.strftime('%Y-%m-%d %H:%M:%S')}]"
         s += f" iteration {iteration:8d}/{args.train_iters:8d} |"
         s += f" consumed samples: {args.consumed_train_samples:12d} |"

@@ -657,3 +657,32 @@ def test_per_split_data_paths(tmp_path):
     one = losses(run("--data-args-path", str(blend), "--split", "90,5,5"))
     assert len(one[0]) == 3 and one != ref
     assert "not both" in run("--data-path", a, "--valid-data-path", b, ok=False)
+
+
+def test_tensorboard_and_wandb_logging(tmp_path):
+    """--tensorboard-dir with --log-timers-to-tensorboard / --log-world-size-to-tensorboard, and --wandb-project (offline mode)."""
+    pytest.importorskip("tensorboard")
+    wandb_ok = True
+    try:
+        import wandb  # noqa: F401
+    except ImportError:
+        wandb_ok = False
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_port()), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", WANDB_MODE="offline", WANDB_SILENT="true")
+    extra = ["--tensorboard-dir", str(tmp_path / "tb"), "--tensorboard-log-interval", "1", "--log-timers-to-tensorboard",
+             "--log-world-size-to-tensorboard", "--timing-log-level", "1"]
+    if wandb_ok:
+        extra += ["--wandb-project", "proj", "--wandb-exp-name", "run", "--wandb-save-dir", str(tmp_path / "wb")]
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py"), *COMMON, *extra], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+
+    acc = EventAccumulator(str(tmp_path / "tb"))
+    acc.Reload()
+    tags = set(acc.Tags()["scalars"])
+    assert {"learning-rate", "lm loss", "world-size", "iteration-time", "optimizer-time"} <= tags, sorted(tags)
+    assert [e.step for e in acc.Scalars("lm loss")] == [1, 2, 3]
+    if wandb_ok:
+        runs = [d for d in os.listdir(tmp_path / "wb" / "wandb") if d.startswith("offline-run")]
+        assert len(runs) == 1 and any(f.endswith(".wandb") for f in os.listdir(tmp_path / "wb" / "wandb" / runs[0]))
