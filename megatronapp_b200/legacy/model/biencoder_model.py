@@ -94,6 +94,45 @@ class BiEncoderModel(MegatronModule):
         c = self.embed_text(context_tokens, context_attention_mask, context_types, False) if self.use_context_model else None
         return q, c
 
+    def init_state_dict_from_bert(self, bert_load=None):
+        """Start both towers from a pre-trained BERT checkpoint (``--bert-load``) on iteration 0 of ICT / retriever training
+        (reference biencoder_model.py:180-245).  Embedding and encoder are taken over, the LM / NSP heads are dropped; the
+        context tower also starts from the query tower's projection so both embed into the same space."""
+        from ...models.bert.bert_model import BertModel, bert_layer_local_spec
+        from ...training.checkpointing import load_checkpoint
+        from ...training.global_vars import get_args
+
+        args = get_args()
+        bert_load = bert_load or getattr(args, "bert_load", None)
+        if bert_load is None:
+            return []
+        # a BERT of the towers' architecture on this rank's tensor-parallel slice: whatever format / layout the checkpoint has,
+        # the regular loader reshards it; only embedding + encoder are kept
+        any_tower = self._tower(True) or self._tower(False)
+        emb = any_tower.embedding
+        bert = BertModel(config=self.config, num_tokentypes=2 if getattr(args, "bert_binary_head", True) else 0,
+                         transformer_layer_spec=bert_layer_local_spec(), vocab_size=args.padded_vocab_size,
+                         max_sequence_length=emb.position_embeddings.weight.shape[0], add_binary_head=getattr(args, "bert_binary_head", True),
+                         parallel_output=True)
+        keep = (args.finetune, args.no_load_rng, args.bert_load)
+        args.finetune, args.no_load_rng, args.bert_load = True, True, bert_load
+        try:
+            load_checkpoint([bert], None, None, load_arg="bert_load", strict=False)
+        finally:
+            args.finetune, args.no_load_rng, args.bert_load = keep
+        dev = next(any_tower.parameters())
+        bert_sd = {k: v.to(device=dev.device, dtype=dev.dtype) if torch.is_tensor(v) and v.is_floating_point() else v
+                   for k, v in bert.state_dict().items()}
+        taken = []
+        for tower in {self._tower(True), self._tower(False)} - {None}:
+            taken = tower.init_from_bert(bert_sd)
+            if not taken:
+                raise RuntimeError(f"no tensor of the BERT checkpoint in {bert_load} matches the bi-encoder towers")
+        if not self.shared and self.query_model is not None and self.context_model is not None \
+                and self.query_model.projection_enc is not None:
+            self.context_model.projection_enc.load_state_dict(self.query_model.projection_enc.state_dict())
+        return taken
+
     def state_dict_for_save_checkpoint(self, prefix="", keep_vars=False):
         names = ("model",) if self.shared else ("query_model", "context_model")
         return {n: getattr(self, n).state_dict(keep_vars=keep_vars) for n in names if getattr(self, n) is not None}

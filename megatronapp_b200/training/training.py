@@ -234,6 +234,13 @@ def setup_model_and_optimizer(model_provider_func, model_type=None, no_wd_decay_
             model, optimizer, scheduler, load_arg=load_arg)
     else:
         args.iteration, args.num_floating_point_operations_so_far = 0, 0
+    core = unwrap_model(model)
+    if args.iteration == 0 and len(core) == 1 and hasattr(core[0], "init_state_dict_from_bert") and getattr(args, "bert_load", None):
+        # ICT / retriever pre-training starts from a pre-trained BERT (reference training.py:1333-1338)
+        print_rank_0("initializing the bi-encoder from the pretrained BERT model")
+        core[0].init_state_dict_from_bert()
+        if hasattr(optimizer, "reload_model_params"):
+            optimizer.reload_model_params()
     # TP fused-comm arena (fused AG->GEMM / GEMM->RS kernels)
     if (args.sequence_parallel and args.fused_tp_comm and torch.cuda.is_available()
             and ps.get_tensor_model_parallel_world_size() > 1 and args.kernel_backend != "torch"):

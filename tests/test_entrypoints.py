@@ -686,3 +686,34 @@ def test_tensorboard_and_wandb_logging(tmp_path):
     if wandb_ok:
         runs = [d for d in os.listdir(tmp_path / "wb" / "wandb") if d.startswith("offline-run")]
         assert len(runs) == 1 and any(f.endswith(".wandb") for f in os.listdir(tmp_path / "wb" / "wandb" / runs[0]))
+
+
+def test_ict_starts_from_a_pretrained_bert(tmp_path):
+    """--bert-load (reference biencoder_model.py:init_state_dict_from_bert): on iteration 0 both towers take embedding + encoder from
+    a BERT checkpoint (any checkpoint format), and the context tower copies the query tower's projection."""
+    import glob
+
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+
+    def run(script, *extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, script), *COMMON, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-3000:]
+        return out
+
+    bert, ict = str(tmp_path / "bert"), str(tmp_path / "ict")
+    run("pretrain_bert.py", "--save", bert, "--save-interval", "3")
+    out = run("pretrain_ict.py", "--train-iters", "1", "--lr", "0", "--biencoder-projection-dim", "16", "--bert-load", bert, "--save", ict,
+              "--save-interval", "1", "--ckpt-format", "torch")
+    assert "initializing the bi-encoder from the pretrained BERT model" in out
+    from megatronapp_b200.ckpt import serialization
+
+    ref = serialization.load_plain_tensors(glob.glob(os.path.join(bert, "iter_*"))[0])
+    sd = torch.load(os.path.join(ict, "iter_0000001", "mp_rank_00", "model_optim_rng.pt"), weights_only=False)["model"]
+    q, c = sd["query_model"], sd["context_model"]
+    for k in ("embedding.word_embeddings.weight", "embedding.position_embeddings.weight"):
+        assert torch.equal(q[k].float(), ref[k].float()) and torch.equal(c[k].float(), ref[k].float())
+    layer0 = [k for k in q if k.startswith("encoder.layers.0.") and k.endswith("linear_fc1.weight")]
+    assert layer0 and torch.equal(q[layer0[0]], c[layer0[0]])
+    assert torch.equal(q["projection_enc.weight"], c["projection_enc.weight"])
