@@ -11,6 +11,7 @@ from __future__ import annotations
 import itertools
 import time
 from collections import OrderedDict
+import dataclasses
 from dataclasses import dataclass, field
 from enum import Enum
 from typing import Dict, List, Optional
@@ -37,6 +38,13 @@ class SamplingParams:
     num_tokens_to_generate: int = 30
     top_n_logprobs: int = 0
     add_BOS: bool = False
+    # legacy REST API knobs (reference text_generation/generation.py:236-300)
+    top_p_decay: float = 0.0                 # top_p is multiplied by this after every generated token ...
+    top_p_bound: float = 0.0                 # ... but not below this
+    stop_on_eol: bool = False                # stop a row at the first "\n" (or "\n\n") token
+    stop_on_double_eol: bool = False         # stop at "\n\n" or two consecutive "\n"
+    prevent_newline_after_colon: bool = False
+    use_eod_token_for_early_termination: bool = True
 
     def add_attributes(self, d: dict):
         for k, v in d.items():
@@ -376,12 +384,29 @@ class TextGenerationController:
         logprobs: List[List[float]] = [[] for _ in reqs]
         vocab = getattr(self.tokenizer, "vocab_size", None)
         start = 0
+        top_p = params.top_p
+        eol = eol2 = colon = None
+        if params.stop_on_eol or params.stop_on_double_eol or params.prevent_newline_after_colon:
+            # tokenizer dependent, as in the reference (which hard-codes GPT-2's 198 / 628): the ids of "\n", "\n\n" and ":"
+            def one(text):
+                ids = self.tokenizer.tokenize(text)
+                return int(ids[0]) if len(ids) == 1 else None
+
+            eol, eol2, colon = one("\n"), one("\n\n"), one(":")
         for pos in range(min_len, total):
             logits = self.inference_wrapped_model.run_one_forward_step(tokens, start, pos)
             last = new = None
             if logits is not None:                      # last pipeline stage
                 last = logits[:, -1, :]
-                new = self.sample_from_logits(last, params, vocab)
+                if params.prevent_newline_after_colon and colon is not None and eol is not None:
+                    last = last.clone()
+                    last[tokens[:, pos - 1] == colon, eol] = -1e10
+                step = params if top_p == params.top_p else dataclasses.replace(params, top_p=top_p)
+                new = self.sample_from_logits(last, step, vocab)
+                if top_p > 0.0 and params.top_p_decay > 0.0:
+                    top_p = top_p * params.top_p_decay
+                    if params.top_p_bound > 0.0:
+                        top_p = max(top_p, params.top_p_bound)
                 scope_hooks.tik_result(last, new)
             new = sync_sampled_tokens(new, len(reqs), dev)
             started = lens_t <= pos                     # rows still consuming their prompt keep it
@@ -391,7 +416,18 @@ class TextGenerationController:
                 for i in range(len(reqs)):
                     if started[i] and not done[i]:
                         logprobs[i].append(float(lp[i, tokens[i, pos]]))
-            hit = started & (new == eod) & ~done
+            never = torch.zeros_like(started)
+            is_eol2 = (new == eol2) if eol2 is not None else never
+            is_eol = (new == eol) if eol is not None else never
+            if params.stop_on_double_eol:
+                hit = is_eol2 | (is_eol & (tokens[:, pos - 1] == eol))
+            elif params.stop_on_eol:
+                hit = is_eol2 | is_eol
+            elif params.use_eod_token_for_early_termination:
+                hit = new == eod
+            else:
+                hit = never
+            hit = started & hit & ~done
             gen_len += (started & ~done).long()
             done |= hit | (gen_len >= n_gen)            # a short prompt in a ragged batch still stops after n_gen tokens
             start = pos

@@ -47,6 +47,19 @@ def _validate(req: dict):
         return "top_p must be less than or equal to 1 and greater than or equal to 0"
     if k > 0 and p > 0.0:
         return "cannot set both top-k and top-p samplings."
+    d = req.get("top_p_decay", 0.0)
+    if not isinstance(d, (int, float)) or not (0.0 <= d <= 1.0):
+        return "top_p_decay must be less than or equal to 1.0 and greater than or equal to 0.0"
+    if d > 0.0 and p == 0.0:
+        return "top_p_decay cannot be set without top_p"
+    b = req.get("top_p_bound", 0.0)
+    if not isinstance(b, (int, float)) or not (0.0 <= b <= 1.0) or (p > 0.0 and b > p):
+        return "top_p_bound must be greater than or equal to 0 and less than or equal to top_p"
+    for flag in ("add_BOS", "stop_on_double_eol", "stop_on_eol", "prevent_newline_after_colon", "logprobs"):
+        if flag in req and not isinstance(req[flag], bool):
+            return f"{flag} must be a boolean value"
+    if req.get("random_seed") is not None and (not isinstance(req["random_seed"], int) or req["random_seed"] < 0):
+        return "random_seed must be a non-negative integer"
     return None
 
 
@@ -105,7 +118,10 @@ def serve_worker_ranks(engine) -> None:
 def run_generate(engine: StaticInferenceEngine, req: dict, announce: bool = True):
     params = SamplingParams(temperature=float(req.get("temperature", 1.0)), top_k=int(req.get("top_k", 0)),
                             top_p=float(req.get("top_p", 0.0)), return_log_probs=bool(req.get("logprobs", False)),
-                            num_tokens_to_generate=int(req.get("tokens_to_generate", 64)))
+                            num_tokens_to_generate=int(req.get("tokens_to_generate", 64)),
+                            top_p_decay=float(req.get("top_p_decay", 0.0)), top_p_bound=float(req.get("top_p_bound", 0.0)),
+                            stop_on_eol=bool(req.get("stop_on_eol", False)), stop_on_double_eol=bool(req.get("stop_on_double_eol", False)),
+                            prevent_newline_after_colon=bool(req.get("prevent_newline_after_colon", False)))
     if req.get("random_seed") is not None:
         torch.manual_seed(int(req["random_seed"]))
     if getattr(engine, "serving", lambda: False)():

@@ -39,6 +39,21 @@ def _engine(model, tokenizer, max_batch: int, max_seq: Optional[int]) -> StaticI
     return eng
 
 
+def _check_token_budget(tok, prompts, tokens_to_generate: int, add_BOS: bool) -> None:
+    """``--max-tokens-to-oom`` (reference generation.py:170): refuse a batch whose padded size would not fit."""
+    try:
+        from ...training.global_vars import get_args
+
+        limit = getattr(get_args(), "max_tokens_to_oom", None)
+    except Exception:  # noqa: BLE001  (library use without the global args)
+        limit = None
+    if not limit:
+        return
+    longest = max(len(tok.tokenize(p)) + int(bool(add_BOS)) for p in prompts) + int(tokens_to_generate)
+    if longest * len(prompts) > limit:
+        raise ValueError(f"Too many tokens.  {longest * len(prompts)} is greater than {limit}")
+
+
 def generate(model, inference_context=None, forward_step=None, prompts: Optional[Sequence[str]] = None, tokens_to_generate: int = 0,
              return_output_log_probs: bool = False, top_k_sampling: int = 0, top_p_sampling: float = 0.0, top_p_decay: float = 0.0,
              top_p_bound: float = 0.0, temperature: float = 1.0, add_BOS: bool = False, use_eod_token_for_early_termination: bool = True,
@@ -46,16 +61,18 @@ def generate(model, inference_context=None, forward_step=None, prompts: Optional
              random_seed: int = -1, data_parallel: bool = False, return_topk_logprobs: int = 0, tokenizer=None,
              max_sequence_length: Optional[int] = None):
     """Returns ``(tokens [b, max_len] padded with eod, lengths [b], output_log_probs | None, None)``."""
-    if top_p_decay or top_p_bound or stop_on_double_eol or stop_on_eol or prevent_newline_after_colon:
-        raise NotImplementedError("top-p decay and the end-of-line stopping rules of the legacy API are not implemented")
     if not prompts:
         raise ValueError("prompts is empty")
     tok = _tokenizer(tokenizer)
+    _check_token_budget(tok, prompts, tokens_to_generate, add_BOS)
     if random_seed is not None and random_seed >= 0:
         torch.manual_seed(random_seed)
     eng = _engine(model, tok, max(len(prompts), 1), max_sequence_length)
     sp = SamplingParams(temperature=temperature, top_k=top_k_sampling, top_p=top_p_sampling, return_log_probs=return_output_log_probs,
-                        num_tokens_to_generate=tokens_to_generate, add_BOS=add_BOS)
+                        num_tokens_to_generate=tokens_to_generate, add_BOS=add_BOS, top_p_decay=top_p_decay, top_p_bound=top_p_bound,
+                        stop_on_eol=stop_on_eol, stop_on_double_eol=stop_on_double_eol,
+                        prevent_newline_after_colon=prevent_newline_after_colon,
+                        use_eod_token_for_early_termination=use_eod_token_for_early_termination)
     res = eng.generate(list(prompts), sp, add_BOS=add_BOS)
     rows = [list(r.prompt_tokens) + [int(t) for t in r.generated_tokens] for r in res]
     lengths = torch.tensor([len(r) for r in rows])

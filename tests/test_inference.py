@@ -427,3 +427,58 @@ def test_t5_encoder_decoder_generation():
     stopped = w.generate(enc, SamplingParams(top_k=1, num_tokens_to_generate=5), eos_token=eos)
     first = (stopped[0] == eos).nonzero()[0, 0]
     assert stopped.shape[1] <= 5 and torch.equal(stopped[0, :first + 1], out[0, :first + 1]) and (stopped[0, first:] == eos).all()
+
+
+def test_legacy_generation_rules(engine):
+    """The legacy REST API's generation rules (reference text_generation/generation.py:236-300): stop at an end of line / a double
+    end of line, no newline right after a colon, decaying top-p, and the --max-tokens-to-oom guard."""
+    from types import SimpleNamespace
+
+    from megatronapp_b200.inference.text_generation import generate
+    from megatronapp_b200.training import global_vars
+
+    eng, model = engine
+    torch.manual_seed(2)                   # the freshly initialised (tied) model just echoes its input: scramble the matrices
+    for p in model.parameters():
+        if p.dim() > 1:
+            p.data.normal_(0, 0.3)
+    prompt = "5 9 23 7"
+    g = eng.generate([prompt], SamplingParams(top_k=1, num_tokens_to_generate=6))[0].generated_tokens.tolist()
+    assert len(set(g[:4])) == 4 and not set(g) & {5, 9, 23, 7}, g
+
+    class Tok(NullTokenizer):
+        def __init__(self, special):
+            super().__init__(127)
+            self.special = special
+
+        def tokenize(self, text):
+            return [self.special[text]] if text in self.special else super().tokenize(text)
+
+    def gen(special, **kw):
+        toks, lens, _, _ = generate(model, prompts=[prompt], tokens_to_generate=6, top_k_sampling=1, tokenizer=Tok(special),
+                                    max_sequence_length=32, **kw)
+        return toks[0, 4:int(lens[0])].tolist()
+
+    unused = next(t for t in range(100) if t not in g and t not in (5, 9, 23, 7))
+    assert gen({"\n": g[1], "\n\n": unused, ":": unused}, stop_on_eol=True) == g[:2]
+    assert gen({"\n": unused, "\n\n": g[2], ":": unused}, stop_on_eol=True) == g[:3]
+    assert gen({"\n": g[1], "\n\n": unused, ":": unused}, stop_on_double_eol=True) == g                 # a single eol does not stop
+    assert gen({"\n": unused, "\n\n": g[2], ":": unused}, stop_on_double_eol=True) == g[:3]
+    out = gen({"\n": g[0], "\n\n": unused, ":": 7}, prevent_newline_after_colon=True)                  # the prompt ends with ":"
+    assert out[0] != g[0] and len(out) == 6
+    assert gen({"\n": g[0], "\n\n": unused, ":": unused}, prevent_newline_after_colon=True) == g
+    # top-p decays to a nucleus of one: after the first (sampled) token the continuation is the greedy one
+    toks, lens, _, _ = generate(model, prompts=[prompt], tokens_to_generate=5, top_p_sampling=0.9, top_p_decay=1e-9, random_seed=3,
+                                tokenizer=NullTokenizer(127), max_sequence_length=32)
+    row = toks[0, :int(lens[0])].tolist()
+    cont = eng.generate([" ".join(map(str, row[:5]))], SamplingParams(top_k=1, num_tokens_to_generate=4))[0].generated_tokens.tolist()
+    assert row[5:] == cont[:len(row) - 5]
+    old = global_vars._ARGS
+    try:
+        global_vars.set_args(SimpleNamespace(max_tokens_to_oom=9))
+        with pytest.raises(ValueError, match="Too many tokens"):
+            generate(model, prompts=[prompt], tokens_to_generate=6, tokenizer=NullTokenizer(127), max_sequence_length=32)
+        global_vars.set_args(SimpleNamespace(max_tokens_to_oom=10))
+        generate(model, prompts=[prompt], tokens_to_generate=6, top_k_sampling=1, tokenizer=NullTokenizer(127), max_sequence_length=32)
+    finally:
+        global_vars.set_args(old)
