@@ -337,6 +337,8 @@ def load_checkpoint(model, optimizer, opt_param_scheduler, load_arg="load", stri
         args = get_args()
     load_dir = getattr(args, load_arg)
     model = model if isinstance(model, (list, tuple)) else [model]
+    if getattr(args, "retro_add_retriever", False):
+        strict = False        # a GPT checkpoint may initialise a Retro model: the retriever's weights are simply absent (reference :1455)
     if load_dir and getattr(args, "non_persistent_ckpt_type", None) == "global" and not getattr(args, "ckpt_step", None):
         # resume from whichever is newer: the last persistent checkpoint or the non-persistent safety checkpoint
         npd = args.non_persistent_global_ckpt_dir or os.path.join(load_dir, "non_persistent")

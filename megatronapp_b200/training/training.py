@@ -871,6 +871,12 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     if args.rerun_mode != "disabled":
         wrap = lambda it: RerunDataIterator(it) if it is not None else None
         train_it = [wrap(i) for i in train_it] if isinstance(train_it, list) else wrap(train_it)
+    if not args.skip_train and args.dataloader_type == "cyclic" and getattr(args, "retro_project_dir", None):
+        # reference training.py:806-809: cyclic Retro training runs for --retro-cyclic-train-iters
+        if args.retro_cyclic_train_iters is None:
+            raise ValueError("--dataloader-type cyclic with a retro project needs --retro-cyclic-train-iters")
+        args.train_iters = args.retro_cyclic_train_iters
+        print_rank_0(f"retro cyclic train iters : {args.train_iters}")
     if not args.skip_train and args.train_iters and args.train_iters > 0:
         print_rank_0("training ...")
         iteration, nflops, exited = train(forward_step_func, model, optimizer, scheduler, train_it, valid_it,

@@ -35,6 +35,8 @@ def _check_parallelism(args):
 def model_provider(pre_process=True, post_process=True):
     args = get_args()
     _check_parallelism(args)
+    # --retro-add-retriever is implied: this entry point always builds the retriever (the reference falls back to a plain GPT
+    # without the flag; that baseline is pretrain_gpt.py here).  With the flag a GPT checkpoint loads non-strictly.
     print_rank_0("building Retro model ...")
     config = core_transformer_config_from_args(args, RetroConfig)
     config.retro_chunk_length, config.retro_num_neighbors = args.retro_chunk_length, args.retro_num_neighbors

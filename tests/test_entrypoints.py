@@ -717,3 +717,23 @@ def test_ict_starts_from_a_pretrained_bert(tmp_path):
     layer0 = [k for k in q if k.startswith("encoder.layers.0.") and k.endswith("linear_fc1.weight")]
     assert layer0 and torch.equal(q[layer0[0]], c[layer0[0]])
     assert torch.equal(q["projection_enc.weight"], c["projection_enc.weight"])
+
+
+@pytest.mark.parametrize("fmt", ["torch", "torch_dist"])
+def test_retro_model_initialises_from_a_gpt_checkpoint(tmp_path, fmt):
+    """--retro-add-retriever makes checkpoint loading non-strict (reference checkpointing.py:1455): the decoder of a Retro model
+    starts from a GPT checkpoint, the retriever keeps its initialisation; without the flag the missing keys are an error."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+
+    def run(script, *extra):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, script), *COMMON, "--ckpt-format", fmt, *extra], cwd=ROOT,
+                           env=dict(env, MASTER_PORT=str(_port())), capture_output=True, text=True, timeout=600)
+        return p.returncode, p.stdout + p.stderr
+
+    gpt = str(tmp_path / "gpt")
+    assert run("pretrain_gpt.py", "--save", gpt, "--save-interval", "3")[0] == 0
+    retro = ["--retro-chunk-length", "8", "--retro-retrieved-length", "12", "--load", gpt, "--finetune", "--no-load-optim"]
+    rc, out = run("pretrain_retro.py", *retro, "--retro-add-retriever")
+    assert rc == 0 and "successfully loaded checkpoint" in out and re.search(r"iteration\s+3/\s+3 \|", out), out[-2000:]
+    rc, out = run("pretrain_retro.py", *retro)
+    assert rc != 0 and ("Missing key" in out or "missing" in out.lower()), out[-2000:]
