@@ -75,7 +75,7 @@ def cosine_scheduler(base, final, epochs, niter_per_ep):
 class _Backbone(nn.Module):
     """image batch -> pooled feature, for any of the supported trunks"""
 
-    def __init__(self, kind, config, img_size, patch_dim):
+    def __init__(self, kind, config, img_size, patch_dim, swin_type="tiny", is_teacher=False):
         super().__init__()
         self.kind = kind
         if kind == "vit":
@@ -88,7 +88,7 @@ class _Backbone(nn.Module):
         elif kind == "swin":
             from .swin_backbone import get_swin
 
-            self.net = get_swin(img_size=img_size, output_avg=True)
+            self.net = get_swin(img_size=img_size, output_avg=True, kind=swin_type, is_teacher=is_teacher)
             self.dim = self.net.num_features
         else:
             from .mit_backbone import mit_b0
@@ -106,11 +106,12 @@ class DINOPretrainModel(nn.Module):
     crops); ``update_momentum(it)`` is the EMA teacher update after the optimizer step."""
 
     def __init__(self, config, out_dim=65536, img_size=224, local_img_size=96, patch_dim=16, backbone="vit",
-                 norm_last_layer=True, momentum_teacher=0.996, epochs=100, iters_per_epoch=1000, head_hidden=2048, bottleneck=256):
+                 norm_last_layer=True, momentum_teacher=0.996, epochs=100, iters_per_epoch=1000, head_hidden=2048, bottleneck=256,
+                 swin_type="tiny"):
         super().__init__()
         self.config = config
-        self.student = _Backbone(backbone, config, img_size, patch_dim)
-        self.teacher = _Backbone(backbone, config, img_size, patch_dim)
+        self.student = _Backbone(backbone, config, img_size, patch_dim, swin_type)
+        self.teacher = _Backbone(backbone, config, img_size, patch_dim, swin_type, is_teacher=True)
         self.student_head = DINOHead(self.student.dim, out_dim, head_hidden, bottleneck, norm_last_layer=norm_last_layer)
         self.teacher_head = DINOHead(self.teacher.dim, out_dim, head_hidden, bottleneck)
         self.teacher.load_state_dict(self.student.state_dict())

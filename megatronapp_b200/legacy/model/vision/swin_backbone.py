@@ -139,7 +139,18 @@ class SwinTransformer(nn.Module):
         return feats[-1].flatten(2).mean(-1) if self.output_avg else feats
 
 
-def get_swin(img_size=224, drop_path_rate=0.1, output_avg=False, tiny=True):
-    kw = dict(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24)) if tiny else \
-        dict(embed_dim=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32))
-    return SwinTransformer(img_size=img_size, window_size=7, drop_path_rate=drop_path_rate, output_avg=output_avg, **kw)
+_SWIN_TYPES = {   # reference esvit_swin_backbone.get_swin (--swin-backbone-type): embed dim, depths, heads, student drop-path
+    "tiny": (96, (2, 2, 6, 2), (3, 6, 12, 24), 0.1),
+    "base": (128, (2, 2, 18, 2), (4, 8, 16, 32), 0.2),
+    "h3": (384, (2, 2, 18, 2), (6, 12, 24, 48), 0.2),
+}
+
+
+def get_swin(img_size=224, drop_path_rate=None, output_avg=False, tiny=True, kind=None, is_teacher=False, in_chans=3):
+    """``kind`` in tiny | base | h3 (``tiny=`` kept for older callers); the teacher of a self-distillation pair runs without
+    stochastic depth."""
+    dim, depths, heads, dpr = _SWIN_TYPES[kind or ("tiny" if tiny else "base")]
+    if drop_path_rate is None:
+        drop_path_rate = dpr
+    return SwinTransformer(img_size=img_size, window_size=7, drop_path_rate=0.0 if is_teacher else drop_path_rate,
+                           output_avg=output_avg, embed_dim=dim, depths=depths, num_heads=heads, in_chans=in_chans)

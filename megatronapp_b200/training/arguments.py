@@ -800,6 +800,8 @@ def core_transformer_config_from_args(args, config_class=None) -> TransformerCon
     kw["num_layers_in_first_pipeline_stage"] = args.decoder_first_pipeline_num_layers
     kw["num_layers_in_last_pipeline_stage"] = args.decoder_last_pipeline_num_layers
     kw["tp_comm_overlap"] = bool(args.tp_comm_overlap)
+    if getattr(args, "microbatch_group_size_per_virtual_pipeline_stage", None):
+        kw["microbatch_group_size_per_vp_stage"] = args.microbatch_group_size_per_virtual_pipeline_stage
     kw["bias_activation_fusion"] = False
     if args.swiglu:
         kw["activation_func"] = F.silu

@@ -36,7 +36,8 @@ def model_provider(pre_process=True, post_process=True):
     return DINOPretrainModel(cfg, out_dim=a.dino_out_dim, img_size=a.img_h, local_img_size=a.dino_local_img_size,
                              patch_dim=a.patch_dim, backbone=a.vision_backbone_type, norm_last_layer=a.dino_norm_last_layer,
                              momentum_teacher=a.dino_momentum_teacher, epochs=a.dino_epochs, iters_per_epoch=a.iter_per_epoch,
-                             head_hidden=a.dino_head_hidden_size, bottleneck=a.dino_bottleneck_size)
+                             head_hidden=a.dino_head_hidden_size, bottleneck=a.dino_bottleneck_size,
+                             swin_type=a.swin_backbone_type)
 
 
 class MockMultiCropDataset(torch.utils.data.Dataset):
