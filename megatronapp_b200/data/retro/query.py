@@ -103,10 +103,12 @@ def query_neighbors(cfg: RetroPreprocessingConfig, db: ChunkDB, index, dataset, 
 class RetroDataset(torch.utils.data.Dataset):
     """GPT sample + ``neighbor_tokens [chunks, neighbours, retrieved_length]`` (missing neighbours are all-pad)."""
 
-    def __init__(self, cfg: RetroPreprocessingConfig, dataset, db: ChunkDB, name: str = "train", pad: int = 0):
+    def __init__(self, cfg: RetroPreprocessingConfig, dataset, db: ChunkDB, name: str = "train", pad: int = 0,
+                 verify_neighbor_count: bool = True):
         self.cfg, self.ds, self.db, self.pad = cfg, dataset, db, pad
         self.neighbors = np.load(cfg.path("query", f"{name}_neighbors.npy"), mmap_mode="r")
-        if self.neighbors.shape[0] != len(dataset):
+        # reference retro_dataset.py:216 (--retro-no-verify-neighbor-count skips it: index with idx % table size instead)
+        if verify_neighbor_count and self.neighbors.shape[0] != len(dataset):
             raise ValueError(f"neighbour table covers {self.neighbors.shape[0]} samples, dataset has {len(dataset)}: "
                              "query with the same data / split / seed / sequence length as training")
 
@@ -115,7 +117,7 @@ class RetroDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, idx):
         s = dict(self.ds[idx])
-        nb = self.neighbors[idx % len(self.ds)]
+        nb = self.neighbors[(idx % len(self.ds)) % self.neighbors.shape[0]]
         R = self.cfg.retro_retrieved_length
         toks = np.full((*nb.shape, R), self.pad, dtype=np.int64)
         for c in range(nb.shape[0]):

@@ -40,6 +40,7 @@ class RetroConfig(TransformerConfig):
     retro_encoder_attention_dropout: float = 0.1
     retro_num_retrieved_chunks: int = 2
     retro_verify_neighbor_count: bool = True
+    retro_attention_gate: float = 1.0      # scales the chunked cross-attention output before the residual add (reference --retro-attention-gate)
 
     def retro_layer_numbers(self) -> List[int]:
         """1-based decoder layers with chunked cross attention (paper: from 6 (<=15 layers) or 9, every 3rd)."""
@@ -123,7 +124,8 @@ class RetroDecoderLayer(TransformerLayer):
         if self.has_cross and context is not None and context.get("neighbor_emb") is not None:
             residual = hidden_states
             x = self.pre_cross_attn_layernorm(hidden_states)
-            hidden_states = residual + F.dropout(self._chunked_cross_attention(x, context), self.hidden_dropout, self.training)
+            gate = getattr(self.config, "retro_attention_gate", 1.0)
+            hidden_states = residual + gate * F.dropout(self._chunked_cross_attention(x, context), self.hidden_dropout, self.training)
         residual = hidden_states
         m_out, mb = self.mlp(self.pre_mlp_layernorm(hidden_states))
         return self._bda(m_out, mb, residual), context

@@ -196,6 +196,7 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     _add(g, "--use-pytorch-profiler", action="store_true")
     _add(g, "--record-memory-history", action="store_true")
     _add(g, "--memory-snapshot-path", type=str, default="snapshot.pickle")
+    _add(g, "--cuda-graph-warmup-steps", type=int, default=3)
     _add(g, "--enable-cuda-graph", action="store_true")
     _add(g, "--kernel-backend", type=str, default="auto", choices=["auto", "b200", "torch"])
     _add(g, "--no-fused-tp-comm", action="store_false", dest="fused_tp_comm",

@@ -24,6 +24,10 @@ def add_retro_args(parser):
     g.add_argument("--retro-num-neighbors", type=int, default=2)
     g.add_argument("--retro-retrieved-length", type=int, default=128)
     g.add_argument("--retro-encoder-layers", type=int, default=2)
+    g.add_argument("--retro-num-retrieved-chunks", type=int, default=None,
+                   help="retrieved length in chunks (neighbour + continuation = 2); overrides --retro-retrieved-length")
+    g.add_argument("--retro-attention-gate", type=float, default=1.0)
+    g.add_argument("--retro-no-verify-neighbor-count", action="store_false", dest="retro_verify_neighbor_count")
     return parser
 
 
@@ -38,7 +42,10 @@ def model_provider(pre_process=True, post_process=True):
     # --retro-add-retriever is implied: this entry point always builds the retriever (the reference falls back to a plain GPT
     # without the flag; that baseline is pretrain_gpt.py here).  With the flag a GPT checkpoint loads non-strictly.
     print_rank_0("building Retro model ...")
+    if args.retro_num_retrieved_chunks:
+        args.retro_retrieved_length = args.retro_num_retrieved_chunks * args.retro_chunk_length
     config = core_transformer_config_from_args(args, RetroConfig)
+    config.retro_attention_gate, config.retro_verify_neighbor_count = args.retro_attention_gate, args.retro_verify_neighbor_count
     config.retro_chunk_length, config.retro_num_neighbors = args.retro_chunk_length, args.retro_num_neighbors
     config.retro_retrieved_length, config.retro_encoder_num_layers = args.retro_retrieved_length, args.retro_encoder_layers
     return RetroModel(config, vocab_size=args.padded_vocab_size, max_sequence_length=args.max_position_embeddings,
@@ -80,7 +87,7 @@ def train_valid_test_datasets_provider(num_samples):
         train, valid, test = build_gpt_datasets(a, [cfg.retro_gpt_train_samples or num_samples[0], num_samples[1], num_samples[2]])
         mock = lambda n, s: MockRetroDataset(max(int(n), 1), a.seq_length, a.padded_vocab_size, a.retro_chunk_length,  # noqa: E731
                                              a.retro_num_neighbors, a.retro_retrieved_length, s)
-        return RetroDataset(cfg, train, ChunkDB(cfg), "train"), mock(num_samples[1], 2), mock(num_samples[2], 3)
+        return RetroDataset(cfg, train, ChunkDB(cfg), "train", verify_neighbor_count=a.retro_verify_neighbor_count), mock(num_samples[1], 2), mock(num_samples[2], 3)
     mk = lambda n, s: MockRetroDataset(max(int(n), 1), a.seq_length, a.padded_vocab_size, a.retro_chunk_length,  # noqa: E731
                                        a.retro_num_neighbors, a.retro_retrieved_length, s)
     return mk(num_samples[0], 1), mk(num_samples[1], 2), mk(num_samples[2], 3)

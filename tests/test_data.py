@@ -341,3 +341,44 @@ def test_multimodal_dataset_reads_preprocessed_caption_image_pairs(tmp_path):
         s = ds[i]
         assert s["text"].tolist() == [i + 3, i + 4, 50, 50] and s["img"].shape == (3, 8, 8)
         assert int(np.argmax(s["img"].mean(axis=(1, 2)))) == i      # the dominant channel survives decode + normalise
+
+
+def test_preprocess_data_partitions_and_sentence_splitter(tmp_path):
+    """tools/preprocess_data.py: --partitions with --keep-sequential-samples reproduces the single-pass files byte for byte,
+    round-robin partitions hold the same documents, and the rule-based sentence splitter respects abbreviations / initials."""
+    import filecmp
+    import importlib.util
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "preprocess_data.py")
+    spec = importlib.util.spec_from_file_location("preprocess_data_tool", tool)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = 'Dr. Smith went to Washington. He said "Hello there." Then he left! Was it 5 p.m. already? Yes.\nJ. R. Tolkien wrote it.'
+    assert mod.rule_based_sentences(text) == ["Dr. Smith went to Washington.", 'He said "Hello there."', "Then he left!",
+                                              "Was it 5 p.m. already?", "Yes.", "J. R. Tolkien wrote it."]
+    assert mod.rule_based_sentences(text, keep_newlines=True)[4] == "Yes.\n"
+    src = tmp_path / "in.jsonl"
+    with open(os.path.join(root, "datasets_gpt", "dataset.json")) as f, open(src, "w") as g:
+        g.writelines(next(f) for _ in range(60))
+    tok = ["--tokenizer-type", "GPT2BPETokenizer", "--vocab-file", os.path.join(root, "datasets_gpt", "vocab.json"), "--merge-file",
+           os.path.join(root, "datasets_gpt", "merges.txt"), "--append-eod"]
+
+    def run(prefix, *extra):
+        p = subprocess.run([sys.executable, tool, "--input", str(src), "--output-prefix", str(tmp_path / prefix), *tok, *extra],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+
+    run("one")
+    run("seq", "--partitions", "4", "--keep-sequential-samples", "--workers", "2")
+    run("rr", "--partitions", "3")
+    for ext in (".bin", ".idx"):
+        assert filecmp.cmp(tmp_path / f"one_text_document{ext}", tmp_path / f"seq_text_document{ext}", shallow=False)
+    from megatronapp_b200.data.indexed_dataset import IndexedDataset
+
+    a, b = IndexedDataset(str(tmp_path / "one_text_document")), IndexedDataset(str(tmp_path / "rr_text_document"))
+    assert len(a) == len(b) == 60 and sorted(len(a[i]) for i in range(60)) == sorted(len(b[i]) for i in range(60))
+    assert not [f for f in os.listdir(tmp_path) if "_part" in f]
