@@ -482,3 +482,28 @@ def test_legacy_generation_rules(engine):
         generate(model, prompts=[prompt], tokens_to_generate=6, top_k_sampling=1, tokenizer=NullTokenizer(127), max_sequence_length=32)
     finally:
         global_vars.set_args(old)
+
+
+@pytest.mark.parametrize("mode", [[], ["--stream"]])
+def test_inference_performance_tool(mode):
+    """tools/run_inference_performance_test.py on the regular argument system: static engine and streamed dynamic engine."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "run_inference_performance_test.py"), "--num-layers", "2",
+                        "--hidden-size", "64", "--num-attention-heads", "4", "--max-batch-size", "3", "--num-input-tokens", "12",
+                        "--num-tokens-to-generate", "6", "--distributed-backend", "gloo", *mode],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    line = json.loads([x for x in p.stdout.splitlines() if x.startswith("{")][-1])
+    assert line["batch"] == 3 and line["generated_tokens"] == 18 and line["tokens_per_s"] > 0
+    assert line["engine"] == ("dynamic" if mode else "static") and (("time_to_first_token_s" in line) == bool(mode))

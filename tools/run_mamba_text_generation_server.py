@@ -14,10 +14,16 @@ from megatronapp_b200.training.initialize import initialize_megatron  # noqa: E4
 from megatronapp_b200.training.training import get_model  # noqa: E402
 from pretrain_mamba import model_provider  # noqa: E402
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from run_text_generation_server import add_text_generate_args  # noqa: E402
+
 
 def main():
-    initialize_megatron(args_defaults={"tokenizer_type": "NullTokenizer", "micro_batch_size": 1})
+    initialize_megatron(extra_args_provider=add_text_generate_args,
+                        args_defaults={"tokenizer_type": "NullTokenizer", "micro_batch_size": 1})
     args = get_args()
+    if args.max_batch_size_override:
+        args.inference_max_requests = args.max_batch_size_override
     model = get_model(model_provider, wrap_with_ddp=False)
     if args.load:
         checkpointing.load_checkpoint(model, None, None)
