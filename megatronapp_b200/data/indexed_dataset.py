@@ -166,6 +166,8 @@ class IndexedDatasetBuilder:
         off = len(self.sequence_lengths)
         self.sequence_lengths.extend(other.sequence_lengths.tolist())
         self.document_indices.extend((off + other.document_indices)[1:].tolist())
+        if self.multimodal:
+            self.sequence_modes.extend(other.sequence_modes.tolist())
         with open(get_bin_path(path_prefix), "rb") as f:
             while True:
                 chunk = f.read(1 << 24)

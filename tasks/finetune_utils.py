@@ -88,7 +88,7 @@ def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: i
              weight_decay: float = 0.01, warmup_fraction: float = 0.1, clip_grad: float = 1.0,
              forward_step: Callable = classification_forward_step, end_of_epoch_callback: Optional[Callable] = None,
              log_interval: int = 50, sampler_seed: int = 1234, evaluate: Optional[Callable] = None,
-             collate_fn: Optional[Callable] = None, eval_batch_size: Optional[int] = None):
+             collate_fn: Optional[Callable] = None, eval_batch_size: Optional[int] = None, keep_last: bool = False):
     """Single-replica (or DDP-sharded through the sampler) finetuning loop; returns per-epoch metrics."""
     import torch.distributed as dist
 
@@ -97,7 +97,7 @@ def finetune(model, train_dataset, valid_dataset, epochs: int = 3, batch_size: i
     dp_rank = ps.get_data_parallel_rank() if ps.model_parallel_is_initialized() else 0
     dp_size = ps.get_data_parallel_world_size() if ps.model_parallel_is_initialized() else 1
     sampler = torch.utils.data.distributed.DistributedSampler(train_dataset, dp_size, dp_rank, shuffle=True, seed=sampler_seed)
-    loader = torch.utils.data.DataLoader(train_dataset, batch_size=batch_size, sampler=sampler, drop_last=True, collate_fn=collate_fn)
+    loader = torch.utils.data.DataLoader(train_dataset, batch_size=batch_size, sampler=sampler, drop_last=not keep_last, collate_fn=collate_fn)
     vloader = torch.utils.data.DataLoader(valid_dataset, batch_size=eval_batch_size or batch_size, shuffle=False, collate_fn=collate_fn)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay)

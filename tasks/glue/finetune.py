@@ -16,7 +16,8 @@ def main():
                            num_classes=len(LABELS[args.task]))
     train = GLUEDataset(args.task, "training", args.train_data, tok, args.seq_length)
     valid = GLUEDataset(args.task, "validation", args.valid_data, tok, args.seq_length)
-    hist = finetune(model, train, valid, epochs=args.epochs, batch_size=args.micro_batch_size, lr=args.lr)
+    hist = finetune(model, train, valid, epochs=args.epochs, batch_size=args.micro_batch_size, lr=args.lr,
+                    keep_last=getattr(args, "keep_last", False))
     for h in hist:
         print_rank_0(f" >> |epoch: {h['epoch']}| correct / total: {h['correct']} / {h['total']} = {100 * h['accuracy']:.4f} %")
     return hist

@@ -11,6 +11,10 @@ def get_tasks_args(parser):
     g.add_argument("--task", type=str, required=True,
                    help="WIKITEXT103 | LAMBADA | MNLI | QQP | RACE | RETRIEVER-EVAL | RET-FINETUNE-NQ | VISION-CLASSIFY (MSDP-*: tasks/msdp/main.py)")
     g.add_argument("--qa-data-test", type=str, default=None, help="NQ-open style TSV: question \\t [answers]")
+    g.add_argument("--qa-data-dev", type=str, default=None, help="the development split, evaluated before the test split")
+    g.add_argument("--faiss-use-gpu", action="store_true",
+                   help="score on the GPU (the evidence embeddings already live on the model's device; kept for CLI parity)")
+    g.add_argument("--keep-last", action="store_true", help="keep the last incomplete batch of a finetuning epoch")
     g.add_argument("--faiss-match", type=str, default="string", choices=["regex", "string"])
     g.add_argument("--faiss-topk-retrievals", type=int, default=100)
     g.add_argument("--train-data", nargs="*", default=None)
@@ -58,8 +62,11 @@ if __name__ == "__main__":
             ev = ORQAEvaluator(model[0], get_tokenizer(), args.retriever_seq_length, args.indexer_batch_size)
             docs = read_evidence(args.evidence_data_path)
             ev.index_evidence(docs)
-            qs, ans = read_nq_questions(args.qa_data_test)
-            ev.evaluate(qs, ans, docs, args.retriever_report_topk_accuracies or (1, 5, 20), args.faiss_match)
+            for split, path in (("DEV", args.qa_data_dev), ("TEST", args.qa_data_test)):
+                if path:
+                    print(f"evaluating the {split} split: {path}", flush=True)
+                    qs, ans = read_nq_questions(path)
+                    ev.evaluate(qs, ans, docs, args.retriever_report_topk_accuracies or (1, 5, 20), args.faiss_match)
     else:
         raise NotImplementedError(f"Task {args.task} is not implemented.")
     main()

@@ -15,7 +15,8 @@ def main():
     model = MultipleChoice(cfg, bert_layer_local_spec(), args.padded_vocab_size, args.max_position_embeddings)
     train = RaceDataset("training", args.train_data, tok, args.seq_length)
     valid = RaceDataset("validation", args.valid_data, tok, args.seq_length)
-    hist = finetune(model, train, valid, epochs=args.epochs, batch_size=args.micro_batch_size, lr=args.lr)
+    hist = finetune(model, train, valid, epochs=args.epochs, batch_size=args.micro_batch_size, lr=args.lr,
+                    keep_last=getattr(args, "keep_last", False))
     for h in hist:
         print_rank_0(f" >> |epoch: {h['epoch']}| correct / total: {h['correct']} / {h['total']} = {100 * h['accuracy']:.4f} %")
     return hist

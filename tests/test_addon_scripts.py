@@ -41,3 +41,38 @@ def _small_corpus(tmp_path):
             for _, line in zip(range(200), f):
                 g.write(line)
     return str(path)
+
+
+def test_vlm_generation_tool_directory_form(tmp_path):
+    """tools/run_vlm_text_generation.py --input-path DIR --output-path F --gt-path G (the reference CLI): every image of the
+    directory is captioned, question ids come from the COCO-style file names, ground-truth captions are attached."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    imgs = tmp_path / "imgs"
+    imgs.mkdir()
+    for i in (17, 42, 99, 120):
+        torch.save(torch.rand(3, 20, 20), imgs / f"COCO_val_{i:06d}.pt")
+    json.dump({"annotations": [{"image_id": 42, "caption": "a cat"}]}, open(tmp_path / "gt.json", "w"))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    out = tmp_path / "out.jsonl"
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "run_vlm_text_generation.py"), "--num-layers", "2", "--hidden-size", "32",
+                        "--num-attention-heads", "4", "--seq-length", "64", "--max-position-embeddings", "64", "--vocab-size", "200",
+                        "--img-h", "14", "--img-w", "14", "--patch-dim", "7", "--distributed-backend", "gloo", "--input-path", str(imgs),
+                        "--output-path", str(out), "--gt-path", str(tmp_path / "gt.json"), "--out-seq-length", "3", "--num-partitions", "2",
+                        "--partition-id", "0", "--prompt", "<image> 5 9", "--top_k", "1"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    rows = [json.loads(x) for x in open(out)]
+    assert [r["question_id"] for r in rows] == [17, 42] and rows[1]["ground_truth"] == ["a cat"] and rows[0]["ground_truth"] == []
+    assert all(len(r["caption"].split()) == 3 for r in rows)

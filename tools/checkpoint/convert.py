@@ -533,6 +533,10 @@ def main(argv=None):
     ap.add_argument("--target-expert-parallel-size", type=int, default=1)
     ap.add_argument("--make-vocab-size-divisible-by", type=int, default=128)
     ap.add_argument("--dtype", default=None, choices=[None, "bf16", "fp16", "fp32"])
+    # the reference converter streams tensors through a multiprocessing queue between a loader and a saver process and compares
+    # the two sides' arguments; here both halves run in one process on whole state dicts, so these are accepted and unused
+    ap.add_argument("--max-queue-size", type=int, default=50, help="accepted for CLI parity (no loader / saver queue here)")
+    ap.add_argument("--no-checking", action="store_false", dest="checking", help="accepted for CLI parity")
     a = ap.parse_args(argv)
     ckpt = LOADERS[a.loader](a.load_dir)
     if a.dtype:

@@ -6,6 +6,11 @@
 
 ``samples.jsonl``: ``{"image": "<path to .pt/.npy [3,H,W] tensor or an image file>", "prompt": "... <image> ..."}``.
 Images are resized to ``--img-h x --img-w`` (bilinear) and normalised with the CLIP statistics.
+
+The reference tool's directory form is also accepted: ``--input-path DIR --output-path out.jsonl [--num-partitions N
+--partition-id I] [--gt-path coco_annotations.json] [--drop-vision-class-token]`` captions every image of ``DIR`` (sorted;
+partition ``I`` of ``N`` equal parts) with the fixed COCO prompt and writes ``{"question_id", "prompt", "caption",
+"ground_truth"?}`` lines; the question id is the number at the end of the file name (COCO naming) or the file's index.
 """
 import json
 import os
@@ -45,8 +50,15 @@ def load_image(path: str, h: int, w: int) -> torch.Tensor:
 def _extra(parser):
     parser = add_vlm_args(parser)
     g = parser.add_argument_group("vlm generation")
-    g.add_argument("--input-file", required=True)
-    g.add_argument("--output-file", required=True)
+    g.add_argument("--input-file", default=None)
+    g.add_argument("--output-file", default=None)
+    g.add_argument("--input-path", default=None, help="directory of images (reference CLI)")
+    g.add_argument("--output-path", default=None)
+    g.add_argument("--num-partitions", type=int, default=0)
+    g.add_argument("--partition-id", type=int, default=0)
+    g.add_argument("--gt-path", default=None, help="COCO-style annotations json: captions are copied into the output")
+    g.add_argument("--prompt", default=None, help="prompt of the directory form (default: the reference's COCO captioning prompt)")
+    g.add_argument("--drop-vision-class-token", action="store_true", dest="disable_vision_class_token")
     g.add_argument("--out-seq-length", type=int, default=64)
     g.add_argument("--temperature", type=float, default=1.0)
     g.add_argument("--top_k", type=int, default=1)
@@ -66,6 +78,10 @@ def main():
     engine = StaticInferenceEngine(TextGenerationController(wrapper, get_tokenizer()), 1)
     sp = SamplingParams(temperature=args.temperature, top_k=args.top_k, top_p=args.top_p,
                         num_tokens_to_generate=args.out_seq_length)
+    if args.input_path:
+        return _caption_directory(args, wrapper, engine, sp, dev)
+    if not (args.input_file and args.output_file):
+        raise SystemExit("give --input-file / --output-file, or --input-path / --output-path")
     with open(args.input_file) as f, open(args.output_file, "w") as out:
         for line in f:
             if not line.strip():
@@ -75,6 +91,40 @@ def main():
             r = engine.generate([s["prompt"]], sp)[0]
             out.write(json.dumps({"prompt": s["prompt"], "image": s["image"], "text": r.generated_text}) + "\n")
             out.flush()
+
+
+COCO_PROMPT = "<image>Give a short and clear explanation of the subsequent image.\n"
+
+
+def _caption_directory(args, wrapper, engine, sp, dev):
+    import glob
+    import re
+    from collections import defaultdict
+
+    files = sorted(glob.glob(os.path.join(args.input_path, "*")))
+    if args.num_partitions > 0:
+        per = len(files) // args.num_partitions
+        files = files[per * args.partition_id: per * (args.partition_id + 1)]
+    gt = defaultdict(list)
+    if args.gt_path:
+        with open(args.gt_path) as f:
+            for a in json.load(f)["annotations"]:
+                gt[int(a["image_id"])].append(a["caption"])
+    if not args.output_path:
+        raise SystemExit("--input-path needs --output-path")
+    with open(args.output_path, "w") as out:
+        for idx, path in enumerate(files):
+            m = re.search(r"(\d+)\.[A-Za-z0-9]+$", os.path.basename(path))
+            qid = int(m.group(1)) if m else idx
+            wrapper.set_images(load_image(path, args.img_h, args.img_w).unsqueeze(0).to(dev))
+            prompt = args.prompt or COCO_PROMPT
+            r = engine.generate([prompt], sp)[0]
+            rec = {"question_id": qid, "prompt": prompt, "caption": r.generated_text}
+            if args.gt_path:
+                rec["ground_truth"] = gt.get(qid, [])
+            if args.rank == 0:
+                out.write(json.dumps(rec) + "\n")
+                out.flush()
 
 
 if __name__ == "__main__":
