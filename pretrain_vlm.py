@@ -44,12 +44,18 @@ def add_vlm_extra_args(parser):
     g.add_argument("--freeze-ViT", action="store_true")
     g.add_argument("--disable-vision-class-token", action="store_true")
     g.add_argument("--dataloader-seq-length", type=int, default=None)
+    g.add_argument("--decoder-tp-comm-overlap", action="store_true",
+                   help="accepted for CLI parity: the language model's TP collectives are fused into its GEMMs by default")
+    g.add_argument("--use-packed-sequence", action="store_true")
     return parser
 
 
 def model_provider(pre_process=True, post_process=True, add_encoder=True, add_decoder=True):
     args = get_args()
     print_rank_0("building a multimodal (LLaVA) model ...")
+    if getattr(args, "use_packed_sequence", False):
+        raise NotImplementedError("--use-packed-sequence (THD packing of image + text samples) is not implemented for the VLM entry "
+                                  "point; packed sequences are available for text models (PackedSeqParams / ops.attention_varlen)")
     if args.pipeline_model_parallel_size > 1:
         # the vision tower and projector live with the text embedding on the first pipeline stage (reference
         # pretrain_vlm.py: add_encoder = is_pipeline_first_stage() when no separate encoder pipeline is configured)
