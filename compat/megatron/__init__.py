@@ -127,6 +127,93 @@ _ALIASES = {
     "megatron.training.async_utils": "megatronapp_b200.training.async_utils",
     "megatron.post_training.checkpointing": "megatronapp_b200.post_training.quantization",
     "megatron.post_training.algos.distillation": "megatronapp_b200.post_training.distillation",
+    # function-level API (megatronapp_b200.core_api) and further module paths of the reference
+    "megatron.core.enums": "megatronapp_b200.core_api.enums",
+    "megatron.core.transformer.enums": "megatronapp_b200.core_api.enums",
+    "megatron.legacy.model.enums": "megatronapp_b200.core_api.enums",
+    "megatron.core.optimizer.clip_grads": "megatronapp_b200.core_api.clip_grads",
+    "megatron.core.tensor_parallel.utils": "megatronapp_b200.core_api.tp_utils",
+    "megatron.core.tensor_parallel.data": "megatronapp_b200.parallel.data",
+    "megatron.core.fusions.fused_bias_gelu": "megatronapp_b200.core_api.fusions",
+    "megatron.core.fusions.fused_bias_swiglu": "megatronapp_b200.core_api.fusions",
+    "megatron.core.fusions.fused_bias_geglu": "megatronapp_b200.core_api.fusions",
+    "megatron.core.fusions.fused_bias_dropout": "megatronapp_b200.core_api.fusions",
+    "megatron.core.fusions.fused_softmax": "megatronapp_b200.core_api.fusions",
+    "megatron.core.fusions.fused_cross_entropy": "megatronapp_b200.core_api.fusions",
+    "megatron.legacy.model.fused_bias_gelu": "megatronapp_b200.core_api.fusions",
+    "megatron.legacy.model.fused_softmax": "megatronapp_b200.core_api.fusions",
+    "megatron.core.extensions.transformer_engine": "megatronapp_b200.core_api.te",
+    "megatron.core.transformer.custom_layers.transformer_engine": "megatronapp_b200.core_api.te",
+    "megatron.core.inference_params": "megatronapp_b200.inference.core",
+    "megatron.core.inference.model_inference_wrappers.gpt.gpt_inference_wrapper": "megatronapp_b200.inference.core",
+    "megatron.core.inference.model_inference_wrappers.t5.t5_inference_wrapper": "megatronapp_b200.inference.core",
+    "megatron.core.inference.model_inference_wrappers.multimodal.vlm_inference_wrapper": "megatronapp_b200.inference.core",
+    "megatron.core.inference.model_inference_wrappers.abstract_model_inference_wrapper": "megatronapp_b200.inference.core",
+    "megatron.core.inference.engines.mcore_engine": "megatronapp_b200.inference.core",
+    "megatron.core.inference.engines.abstract_engine": "megatronapp_b200.inference.core",
+    "megatron.core.inference.text_generation_controllers.simple_text_generation_controller": "megatronapp_b200.inference.core",
+    "megatron.core.inference.text_generation_controllers.encoder_decoder_text_generation_controller": "megatronapp_b200.inference.core",
+    "megatron.core.inference.text_generation_controllers.vlm_text_generation_controller": "megatronapp_b200.inference.core",
+    "megatron.core.inference.communication_utils": "megatronapp_b200.core_api.text_generation",
+    "megatron.inference.text_generation.sampling": "megatronapp_b200.core_api.text_generation",
+    "megatron.inference.text_generation.tokenization": "megatronapp_b200.core_api.text_generation",
+    "megatron.inference.text_generation.communication": "megatronapp_b200.core_api.text_generation",
+    "megatron.inference.text_generation.generation": "megatronapp_b200.inference.text_generation.api",
+    "megatron.inference.endpoints.completions": "megatronapp_b200.inference.server",
+    "megatron.inference.endpoints.common": "megatronapp_b200.inference.server",
+    "megatron.core.optimizer.optimizer_config": "megatronapp_b200.optim.optimizer",
+    "megatron.core.optimizer.distrib_optimizer": "megatronapp_b200.optim.optimizer",
+    "megatron.core.optimizer.grad_scaler": "megatronapp_b200.optim.optimizer",
+    "megatron.core.distributed.distributed_data_parallel_config": "megatronapp_b200.parallel.ddp",
+    "megatron.core.distributed.finalize_model_grads": "megatronapp_b200.parallel.ddp",
+    "megatron.core.distributed.param_and_grad_buffer": "megatronapp_b200.parallel.ddp",
+    "megatron.core.distributed.data_parallel_base": "megatronapp_b200.parallel.ddp",
+    "megatron.core.distributed.custom_fsdp.fully_sharded_data_parallel": "megatronapp_b200.parallel.fsdp",
+    "megatron.core.models.retro.config": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.retro.model": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.retro.decoder_spec": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.retro.encoder_spec": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.bert.bert_layer_specs": "megatronapp_b200.models.bert.bert_model",
+    "megatron.core.models.bert.bert_lm_head": "megatronapp_b200.models.bert.bert_model",
+    "megatron.core.models.bert.pooler": "megatronapp_b200.models.bert.bert_model",
+    "megatron.core.models.common.embeddings.language_model_embedding": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.common.embeddings.rotary_pos_embedding": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.common.embeddings.relative_pos_embedding": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.common.embeddings.yarn_rotary_pos_embedding": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.gpt.heterogeneous.heterogeneous_layer_specs": "megatronapp_b200.models.gpt.heterogeneous.heterogeneous_layer_specs",
+    "megatron.core.ssm.mamba_block": "megatronapp_b200.ssm.mamba",
+    "megatron.core.ssm.mamba_layer": "megatronapp_b200.ssm.mamba",
+    "megatron.core.ssm.mamba_hybrid_layer_allocation": "megatronapp_b200.ssm.mamba",
+    "megatron.core.transformer.identity_op": "megatronapp_b200.transformer.norms",
+    "megatron.core.transformer.torch_layer_norm": "megatronapp_b200.transformer.norms",
+    "megatron.core.config_logger": "megatronapp_b200.utils.config_logger",
+    "megatron.core.trace": "megatronapp_b200.scan.tracer",
+    "megatron.core.datasets.megatron_tokenizer": "megatronapp_b200.data.tokenizer",
+    "megatron.core.datasets.blended_dataset": "megatronapp_b200.data.gpt_dataset",
+    "megatron.core.datasets.retro.config.config": "megatronapp_b200.data.retro.config",
+    "megatron.core.datasets.retro.query.retro_dataset": "megatronapp_b200.data.retro.query",
+    "megatron.core.datasets.retro.query.query": "megatronapp_b200.data.retro.query",
+    "megatron.core.datasets.retro.db.build": "megatronapp_b200.data.retro.db",
+    "megatron.core.datasets.retro.index.index": "megatronapp_b200.data.retro.index",
+    "megatron.core.export.trtllm.trt_model_type": "megatronapp_b200.export.model_type",
+    "megatron.legacy.data.autoaugment": "megatronapp_b200.legacy.data.autoaugment",
+    "megatron.legacy.data.image_folder": "megatronapp_b200.legacy.data.image_folder",
+    "megatron.legacy.data.vit_dataset": "megatronapp_b200.legacy.data.vit_dataset",
+    "megatron.legacy.data.realm_index": "megatronapp_b200.legacy.data.realm_index",
+    "megatron.legacy.data.orqa_wiki_dataset": "megatronapp_b200.legacy.data.orqa_wiki_dataset",
+    "megatron.legacy.data.multimodal_dataset": "megatronapp_b200.legacy.data.multimodal_dataset",
+    "megatron.legacy.indexer": "megatronapp_b200.legacy.indexer",
+    "megatron.legacy.model.bert_model": "megatronapp_b200.models.bert.bert_model",
+    "megatron.legacy.model.classification": "megatronapp_b200.models.bert.classification",
+    "megatron.legacy.model.multiple_choice": "megatronapp_b200.models.bert.classification",
+    "megatron.legacy.model.module": "megatronapp_b200.transformer.module",
+    "megatron.legacy.model.vision.esvit_swin_backbone": "megatronapp_b200.legacy.model.vision.swin_backbone",
+    "megatron.legacy.model.vision.classification": "megatronapp_b200.models.vision.vit_classification",
+    "megatron.training.dist_signal_handler": "megatronapp_b200.training.signals",
+    "megatron.training.one_logger_utils": "megatronapp_b200.training.one_logger_utils",
+    "megatron.training.wandb_utils": "megatronapp_b200.training.wandb_utils",
+    "megatron.training.activations": "megatronapp_b200.transformer.mlp",
+    "megatron.post_training.arguments": "megatronapp_b200.training.arguments",
     # megatron.training & add-ons
     "megatron.training.arguments": "megatronapp_b200.training.arguments",
     "megatron.training.initialize": "megatronapp_b200.training.initialize",
@@ -210,6 +297,12 @@ _UNIONS = {
     "megatron.core.dist_checkpointing": ("megatronapp_b200.ckpt", "megatronapp_b200.ckpt.sharded"),
     "megatron.core.inference": ("megatronapp_b200.inference", "megatronapp_b200.inference.core"),
     "megatron.training.tokenizer": ("megatronapp_b200.data.tokenizer", "megatronapp_b200.data.tokenizer_extra"),
+    "megatron.core.utils": ("megatronapp_b200.core_api.utils",),
+    "megatron.core.transformer.utils": ("megatronapp_b200.core_api.transformer_utils", "megatronapp_b200.ckpt.sharded"),
+    "megatron.legacy.model.utils": ("megatronapp_b200.core_api.transformer_utils", "megatronapp_b200.config.transformer_config",
+                                    "megatronapp_b200.core_api.utils"),
+    "megatron.core.dist_checkpointing.utils": ("megatronapp_b200.ckpt.serialization", "megatronapp_b200.ckpt.sharded"),
+    "megatron.core.dist_checkpointing.dict_utils": ("megatronapp_b200.ckpt.serialization", "megatronapp_b200.ckpt.sharded"),
 }
 
 
@@ -254,7 +347,8 @@ class _Finder:
             return None
         from importlib.machinery import ModuleSpec
 
-        if name in _ALIASES or any(k.startswith(name + ".") for k in _ALIASES) or name in _EXTRA_ATTRS:
+        if (name in _ALIASES or any(k.startswith(name + ".") for k in _ALIASES) or name in _EXTRA_ATTRS or name in _UNIONS
+                or any(k.startswith(name + ".") for k in _UNIONS)):
             return ModuleSpec(name, _Finder, is_package=name not in _ALIASES)
         return None
 

@@ -212,3 +212,37 @@ def track_moe_metrics(loss_scale, iteration, writer, wandb_writer=None, total_lo
                 for i, v in enumerate(vals.tolist()):
                     writer.add_scalar(f"moe/{name}_layer_{i}", v, iteration)
     clear_aux_losses_tracker()
+
+
+def sinkhorn(cost, tol: float = 1e-4):
+    from .router import sinkhorn as impl
+
+    return impl(cost, tol)
+
+
+def get_updated_expert_bias(tokens_per_expert, expert_bias, expert_bias_update_rate):
+    """Auxiliary-loss-free load balancing (DeepSeek-V3): experts that received fewer tokens than the average get their routing
+    bias raised by ``update_rate``, over-loaded ones lowered; token counts are summed over the whole data-parallel domain first."""
+    import torch.distributed as dist
+
+    from ..parallel import state as ps
+
+    with torch.no_grad():
+        counts = tokens_per_expert.float().clone()
+        if ps.model_parallel_is_initialized() and dist.is_available() and dist.is_initialized():
+            g = ps.get_tensor_and_data_parallel_group(with_context_parallel=True)
+            if not type(g).__name__.startswith("_Single") and dist.get_world_size(g) > 1:
+                dist.all_reduce(counts, group=g)
+        offset = counts.mean(dim=-1, keepdim=True) - counts
+        return expert_bias + torch.sign(offset) * expert_bias_update_rate
+
+
+def maybe_move_tensor_to_cpu(tensor, as_numpy: bool = False, record_stream: bool = False):
+    """Asynchronous device -> pinned host copy of a (small) routing tensor; the caller synchronises before reading it."""
+    if torch.is_tensor(tensor) and tensor.is_cuda:
+        out = torch.empty(tensor.size(), dtype=tensor.dtype, device="cpu", pin_memory=True)
+        out.copy_(tensor, non_blocking=True)
+        if record_stream:
+            tensor.record_stream(torch.cuda.current_stream())
+        tensor = out
+    return tensor.numpy() if (as_numpy and torch.is_tensor(tensor)) else tensor

@@ -174,3 +174,31 @@ def communicate_shapes(tensor: Optional[torch.Tensor], src_or_dst: int, kind: st
         return tuple(tensor.shape)
     s = recv((3,), torch.int64, src_or_dst, kind, "recv-shape", device=dev)
     return tuple(int(v) for v in s.tolist() if v > 0)
+
+
+# -- combined calls of the reference's p2p_communication.py (interleaved schedule steady state) ------------------------------
+def send_forward_recv_forward(output_tensor, recv_prev: bool, tensor_shape, config, overlap_p2p_comm: bool = False):
+    """Send this stage's output downstream and (optionally) receive the next input from upstream."""
+    if output_tensor is not None and not ps.is_pipeline_last_stage(ignore_virtual=True):
+        send_forward(output_tensor, config)
+    got = recv_forward(tensor_shape, config) if (recv_prev and not ps.is_pipeline_first_stage(ignore_virtual=True)) else None
+    return (got, []) if overlap_p2p_comm else got
+
+
+def send_backward_recv_backward(input_tensor_grad, recv_next: bool, tensor_shape, config, overlap_p2p_comm: bool = False):
+    if input_tensor_grad is not None and not ps.is_pipeline_first_stage(ignore_virtual=True):
+        send_backward(input_tensor_grad, config)
+    got = recv_backward(tensor_shape, config) if (recv_next and not ps.is_pipeline_last_stage(ignore_virtual=True)) else None
+    return (got, []) if overlap_p2p_comm else got
+
+
+def send_forward_backward_recv_forward_backward(output_tensor, input_tensor_grad, recv_prev: bool, recv_next: bool, tensor_shape, config):
+    """Both directions at once -> ``(input_tensor, output_tensor_grad)``.  Sends are posted before the receives on the
+    unidirectional channels, so two neighbouring stages calling this at the same time cannot deadlock."""
+    if output_tensor is not None and not ps.is_pipeline_last_stage(ignore_virtual=True):
+        send_forward(output_tensor, config)
+    if input_tensor_grad is not None and not ps.is_pipeline_first_stage(ignore_virtual=True):
+        send_backward(input_tensor_grad, config)
+    inp = recv_forward(tensor_shape, config) if (recv_prev and not ps.is_pipeline_first_stage(ignore_virtual=True)) else None
+    grad = recv_backward(tensor_shape, config) if (recv_next and not ps.is_pipeline_last_stage(ignore_virtual=True)) else None
+    return inp, grad

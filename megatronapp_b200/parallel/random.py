@@ -217,3 +217,21 @@ class CheckpointWithoutOutput:
         for orig, d in zip(self.inputs, det):
             if torch.is_tensor(orig) and orig.requires_grad and d.grad is not None:
                 orig.backward(d.grad)
+
+
+def initialize_rng_tracker(use_te_rng_tracker: bool = False, inference_rng_tracker: bool = False, use_cudagraphable_rng: bool = False,
+                           force_reset: bool = False):
+    """Create (or with ``force_reset`` re-create) the global RNG-state tracker.  There is one tracker implementation here: its
+    states are plain generator states, which is what CUDA-graph capture and inference need as well."""
+    global _TRACKER
+    if force_reset or globals().get("_TRACKER") is None:
+        _TRACKER = CudaRNGStatesTracker()
+    return _TRACKER
+
+
+def get_all_rng_states() -> dict:
+    """``{name: state}`` of the tracker (empty before ``model_parallel_cuda_manual_seed``)."""
+    return get_cuda_rng_tracker().get_states()
+
+
+CheckpointWithoutOutputFunction = CheckpointFunction

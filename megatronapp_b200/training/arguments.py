@@ -566,6 +566,27 @@ def build_parser(extra_args_provider: Optional[Callable] = None) -> argparse.Arg
     return p
 
 
+def add_megatron_arguments(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
+    """Add every framework argument to an existing parser (reference ``add_megatron_arguments``: embedding the training CLI in
+    another program's parser)."""
+    for action in build_parser()._actions:
+        if action.dest == "help" or any(o in parser._option_string_actions for o in action.option_strings):
+            continue
+        parser._add_action(action)
+    return parser
+
+
+def moe_freq_type(x):
+    """argparse type of ``--moe-layer-freq``: an int N (every N-th layer is MoE) or a python list expression like
+    ``([1]*3+[0]*1)*3``; returned as int or list."""
+    return _parse_moe_layer_freq(x) if isinstance(x, str) else x
+
+
+def add_modelopt_args(parser):
+    """The post-training (ModelOpt) flag group is part of the main parser here; kept for ``extra_args_provider=add_modelopt_args``."""
+    return parser
+
+
 def parse_args(extra_args_provider=None, ignore_unknown_args=False, args_list=None):
     parser = build_parser(extra_args_provider)
     if ignore_unknown_args:

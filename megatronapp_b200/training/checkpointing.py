@@ -555,3 +555,75 @@ def load_args_from_checkpoint(args, load_arg="load"):
         if hasattr(ca, k):
             setattr(args, k, getattr(ca, k))
     return args
+
+
+# -- further names of the reference's ``megatron/training/checkpointing.py`` --------------------------------------------------
+from enum import Enum, auto as _auto  # noqa: E402
+
+_LOADED_CHECKPOINT_VERSION = None
+
+
+class CheckpointType(Enum):
+    LEGACY = _auto()
+    LOCAL = _auto()
+    GLOBAL = _auto()
+    TORCH_DCP = _auto()
+
+
+def set_checkpoint_version(value):
+    global _LOADED_CHECKPOINT_VERSION
+    if _LOADED_CHECKPOINT_VERSION is not None and _LOADED_CHECKPOINT_VERSION != value:
+        raise AssertionError("checkpoint versions do not match")
+    _LOADED_CHECKPOINT_VERSION = value
+
+
+def get_checkpoint_version():
+    return _LOADED_CHECKPOINT_VERSION
+
+
+def ensure_directory_exists(filename, check_parent: bool = True):
+    os.makedirs(os.path.dirname(filename) if check_parent else filename, exist_ok=True)
+
+
+def checkpoint_exists(checkpoints_path) -> bool:
+    """A tracker file (``latest_checkpointed_iteration.txt``) marks a directory that holds at least one finished checkpoint."""
+    if checkpoints_path is None:
+        return False
+    return os.path.isfile(get_checkpoint_tracker_filename(checkpoints_path)) or \
+        os.path.isfile(os.path.join(checkpoints_path, "latest"))
+
+
+def get_distributed_optimizer_checkpoint_name(model_checkpoint_name):
+    return os.path.join(os.path.dirname(model_checkpoint_name), "distrib_optim.pt")
+
+
+def find_checkpoint_rank_0(checkpoints_path, iteration, release=False):
+    """File (legacy layouts, with / without pipeline / expert parallel directory names) or directory (distributed formats) of
+    rank 0's part of a checkpoint; ``None`` when there is none."""
+    for pp in (False, True):
+        for ep in (False, True):
+            name = get_checkpoint_name(checkpoints_path, iteration, release, pipeline_parallel=pp, tensor_rank=0, pipeline_rank=0,
+                                       expert_parallel=ep, expert_rank=0)
+            if os.path.isfile(name):
+                return name
+    base = get_checkpoint_name(checkpoints_path, iteration, release, return_base_dir=True)
+    if os.path.exists(os.path.join(base, "metadata.json")) or os.path.exists(os.path.join(base, ".metadata")):
+        return base
+    return None
+
+
+def fix_query_key_value_ordering(model, checkpoint_version):
+    """Checkpoints older than version 2.0 store the fused QKV weight in another head order; current ones need no change."""
+    if checkpoint_version is not None and checkpoint_version < 2.0:
+        _fix_qkv_ordering_if_needed(model if isinstance(model, (list, tuple)) else [model], {"checkpoint_version": checkpoint_version})
+
+
+def cleanup_old_non_persistent_checkpoint(save_dir, leave_ckpt_num: int = 1, do_async: bool = False):
+    """Keep the newest ``leave_ckpt_num`` ``iter_*`` directories of a non-persistent checkpoint folder."""
+    import shutil
+
+    if (dist.is_initialized() and dist.get_rank() != 0) or not os.path.isdir(save_dir):
+        return
+    dirs = sorted(d for d in os.listdir(save_dir) if d.startswith("iter_"))
+    for d in dirs[:-leave_ckpt_num] if leave_ckpt_num > 0 else dirs:
+        shutil.rmtree(os.path.join(save_dir, d), ignore_errors=True)

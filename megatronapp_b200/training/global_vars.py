@@ -142,3 +142,27 @@ def unset_global_variables():
     from ..utils.microbatches import destroy_num_microbatches_calculator
 
     destroy_num_microbatches_calculator()
+
+
+# -- further accessors of the reference's ``global_vars.py`` --------------------------------------------------------------------
+def get_one_logger():
+    """The reference's optional NVIDIA-internal telemetry client: never configured here."""
+    return None
+
+
+def get_adlr_autoresume():
+    from .autoresume import get_adlr_autoresume as impl
+
+    return impl()
+
+
+def rebuild_tokenizer(args):
+    global _TOKENIZER
+    from ..data.tokenizer import build_tokenizer as _bt
+
+    _TOKENIZER = _bt(args)
+    return _TOKENIZER
+
+
+def destroy_global_vars():
+    unset_global_variables()

@@ -123,3 +123,34 @@ def _print_args(args):
     for k in sorted(vars(args)):
         print(f"  {k} {'.' * max(1, 48 - len(k))} {getattr(args, k)}", flush=True)
     print("-------------------- end of arguments ---------------------", flush=True)
+
+
+# -- further entry points of the reference's ``initialize.py`` -----------------------------------------------------------------
+def write_args_to_tensorboard():
+    """Every argument as a text entry of the TensorBoard run (reference ``write_args_to_tensorboard``)."""
+    from .global_vars import get_args, get_tensorboard_writer
+
+    args, writer = get_args(), get_tensorboard_writer()
+    if writer is not None:
+        for name in sorted(vars(args)):
+            writer.add_text(name, str(getattr(args, name)), global_step=args.iteration if hasattr(args, "iteration") else 0)
+
+
+def set_jit_fusion_options():
+    """The reference configures the TorchScript / nvFuser fusers for its jit-compiled bias-GELU / bias-dropout-add here.  Those
+    ops are hand-written kernels in this framework and nothing is traced, so there is nothing to configure."""
+    return None
+
+
+def setup_logging() -> None:
+    """Logging level of the root logger: ``--logging-level``, else the ``MEGATRON_LOGGING_LEVEL`` environment variable."""
+    import logging
+    import os
+
+    from .global_vars import get_args
+
+    level = getattr(get_args(), "logging_level", None)
+    if level is None and os.environ.get("MEGATRON_LOGGING_LEVEL"):
+        level = int(os.environ["MEGATRON_LOGGING_LEVEL"])
+    if level is not None:
+        logging.getLogger().setLevel(int(level))

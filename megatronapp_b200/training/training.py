@@ -901,3 +901,65 @@ def pretrain(train_valid_test_dataset_provider, model_provider, model_type, forw
     p2p.flush()
     ft_integration.shutdown()
     return model, optimizer
+
+
+# -- further names of the reference's ``training.py`` ------------------------------------------------------------------------
+def print_datetime(string: str):
+    if dist.is_initialized():
+        dist.barrier()
+    print_rank_0(f"[{string}] datetime: {time.strftime('%Y-%m-%d %H:%M:%S')} ")
+
+
+def destroy_global_state():
+    """Tear everything down so that ``pretrain`` can be called again in the same process (tests, notebooks)."""
+    from .global_vars import unset_global_variables
+
+    unset_global_variables()
+    p2p.destroy_channels()
+    ps.destroy_model_parallel()
+
+
+def update_train_iters(args):
+    """``--train-samples`` -> ``args.train_iters`` (constant batch size, or with the batch-size ramp-up accounted for)."""
+    if args.train_iters:
+        return
+    if args.rampup_batch_size is None:
+        args.train_iters = args.train_samples // args.global_batch_size
+    else:
+        start, inc, ramp = (int(x) for x in args.rampup_batch_size)
+        iters, consumed, bs = 0, 0, start
+        while consumed <= ramp and consumed < args.train_samples:
+            bs = min(args.global_batch_size, start + (consumed * (args.global_batch_size - start) // max(ramp, 1)) // inc * inc)
+            consumed += bs
+            iters += 1
+        iters += max(0, args.train_samples - consumed) // args.global_batch_size
+        args.train_iters = iters
+    print_rank_0(f"setting training iterations to {args.train_iters}")
+
+
+def get_start_time_from_progress_log():
+    """(start time, floating-point operations so far) of the last job in ``<save>/progress.txt`` that shares this job's world
+    size -- what the throughput summary after a restart is computed against."""
+    from datetime import datetime
+
+    args = get_args()
+    path = os.path.join(args.save, "progress.txt")
+    start_time = start_flops = None
+    latest_flops = 0.0
+    with open(path) as f:
+        for line in f:
+            parts = line.strip().split("\t")
+            ws = [p for p in parts if p.startswith("# GPUs: ")]
+            if ws and int(ws[0].split(": ")[1]) != args.world_size:
+                start_time = start_flops = None                       # another world size: the series restarts
+                continue
+            if "Saved checkpoint" in line:
+                fl = [p for p in parts if p.startswith("Floating-point operations: ")]
+                if fl:
+                    latest_flops = float(fl[0].split(": ")[1])
+            if "Starting job" in line and start_time is None:
+                start_time = datetime.strptime(parts[0], "%Y-%m-%d %H:%M:%S")
+                start_flops = latest_flops
+    if start_time is None:
+        raise RuntimeError(f"no job start found in {path}")
+    return start_time, start_flops

@@ -146,3 +146,58 @@ def broadcast_batch(data_iterator, int_keys, float_keys=()):
     if float_keys:
         out.update(broadcast_data(list(float_keys), data, torch.float32))
     return out
+
+
+# -- further helpers of the reference's ``megatron/training/utils.py`` ------------------------------------------------------
+def is_rank0() -> bool:
+    return (not dist.is_initialized()) or dist.get_rank() == 0
+
+
+def get_ltor_masks_and_position_ids(data, eod_token, reset_position_ids=False, reset_attention_mask=False, eod_mask_loss=False, **kw):
+    """Left-to-right attention mask, loss mask and position ids of a ``[b, s]`` token batch (document boundaries at ``eod_token``)."""
+    from ..data.mock import get_ltor_masks_and_position_ids as impl
+
+    return impl(data, eod_token, reset_position_ids, reset_attention_mask, eod_mask_loss, **kw)
+
+
+def append_to_progress_log(string: str, barrier: bool = True):
+    from .training import append_to_progress_log as impl
+
+    return impl(string, barrier)
+
+
+def get_blend_and_blend_per_split(args):
+    """``(blend, blend_per_split)`` in the reference's shape: ``(prefixes, weights)`` tuples or ``None``."""
+    from ..data.gpt_dataset import blend_and_blend_per_split, parse_blend
+
+    blend, per_split = blend_and_blend_per_split(args)
+    as_tuple = lambda b: None if not b else parse_blend(b)   # noqa: E731
+    return as_tuple(blend), (None if per_split is None else [as_tuple(b) for b in per_split])
+
+
+def print_params_min_max_norm(optimizer, iteration):
+    """One line per parameter: iteration, rank, index, model-parallel flag, min, max, L2 norm."""
+    lines, index = "iteration, rank, index, tensor-model-parallel, min, max, norm\n", 0
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            index += 1
+            lines += (f"{iteration:7d}, {rank:4d}, {index:4d}, {int(getattr(p, 'tensor_model_parallel', False)):2d}, "
+                      f"{float(p.data.min()):.6E}, {float(p.data.max()):.6E}, {float(p.data.float().norm()):.6E}\n")
+    print(lines, flush=True)
+
+
+def check_adlr_autoresume_termination(iteration, model, optimizer, opt_param_scheduler):
+    """Checkpoint and exit when the cluster's auto-resume hook asks for termination."""
+    from .autoresume import check_adlr_autoresume_termination as impl
+
+    return impl(iteration, model, optimizer, opt_param_scheduler)
+
+
+def get_device_arch_version() -> int:
+    """Major compute capability of the current GPU (10 on B200)."""
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).major if torch.cuda.is_available() else 0
+
+
+def update_use_dist_ckpt(args):
+    args.use_dist_ckpt = args.ckpt_format != "torch"

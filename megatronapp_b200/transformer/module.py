@@ -124,3 +124,16 @@ class Float16Module(MegatronModule):
 
     def load_state_dict(self, state_dict, strict=True):
         return self.module.load_state_dict(state_dict, strict=strict)
+
+
+def conversion_helper(val, conversion):
+    """Apply ``conversion`` to every element of a (nested) tuple / list."""
+    return _convert(val, conversion)
+
+
+def fp32_to_float16(val, float16_convertor):
+    return _convert(val, lambda v: float16_convertor(v) if (torch.is_tensor(v) and v.dtype == torch.float32) else v)
+
+
+def float16_to_fp32(val):
+    return _convert(val, lambda v: v.float() if (torch.is_tensor(v) and v.dtype in (torch.bfloat16, torch.float16)) else v)

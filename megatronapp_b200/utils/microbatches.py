@@ -113,3 +113,17 @@ def get_current_running_global_batch_size():
 
 def update_num_microbatches(consumed_samples, consistency_check=True, verbose=False):
     _CALC.update(consumed_samples, consistency_check, verbose)
+
+
+NumMicroBatchesCalculator = ConstantNumMicroBatchesCalculator       # base type name of the reference
+
+
+def unset_num_microbatches_calculator():
+    destroy_num_microbatches_calculator()
+
+
+def reconfigure_num_microbatches_calculator(rank, rampup_batch_size, global_batch_size, micro_batch_size, data_parallel_size,
+                                            decrease_batch_size_if_needed=False):
+    """Replace the calculator (e.g. evaluation with another batch size) without tripping the "already initialised" guard."""
+    return init_num_microbatches_calculator(rank, rampup_batch_size, global_batch_size, micro_batch_size, data_parallel_size,
+                                            decrease_batch_size_if_needed)

@@ -59,3 +59,79 @@ print("ok")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "compat"), root]))
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0 and p.stdout.strip().endswith("ok"), p.stderr[-2000:]
+
+
+def test_function_level_api_of_the_reference_resolves():
+    """Names that user scripts import from the reference (``megatron.core.utils``, enums, clip_grads, fusions, TE layer names,
+    text-generation helpers, training utilities) resolve through ``compat/`` and behave."""
+    import subprocess
+    import sys
+
+    code = r'''
+import sys
+sys.path[:0] = [sys.argv[1] + "/compat", sys.argv[1]]
+import argparse
+import torch
+import megatron
+from megatron.core.utils import get_model_config, divide, make_viewless_tensor, StragglerDetector, init_method_normal, get_attr_wrapped_model
+from megatron.core.enums import ModelType
+from megatron.core.transformer.enums import AttnMaskType, AttnType, AttnBackend
+from megatron.core.transformer.utils import attention_mask_func, make_sharded_tensors_for_checkpoint, get_linear_layer
+from megatron.core.optimizer.clip_grads import get_grad_norm_fp32, clip_grad_by_total_norm_fp32, count_zeros_fp32
+from megatron.core.tensor_parallel.utils import split_tensor_along_last_dim, VocabUtility
+from megatron.core.tensor_parallel.layers import linear_with_grad_accumulation_and_async_allreduce, copy_tensor_model_parallel_attributes
+from megatron.core.tensor_parallel.random import initialize_rng_tracker, get_all_rng_states
+from megatron.core.fusions.fused_bias_dropout import get_bias_dropout_add
+from megatron.core.fusions.fused_bias_gelu import bias_gelu_impl
+from megatron.core.fusions.fused_bias_swiglu import bias_swiglu_impl
+from megatron.core.fusions.fused_softmax import FusedScaleMaskSoftmax
+from megatron.core.extensions.transformer_engine import TENorm, TEDotProductAttention, TELayerNormColumnParallelLinear, TEColumnParallelLinear
+from megatron.core.inference_params import InferenceParams
+from megatron.core.num_microbatches_calculator import reconfigure_num_microbatches_calculator, get_num_microbatches
+from megatron.core.pipeline_parallel.p2p_communication import send_forward_recv_forward, send_forward_backward_recv_forward_backward
+from megatron.core.transformer.moe.moe_utils import get_updated_expert_bias, sinkhorn
+from megatron.core.transformer.module import fp32_to_float16, float16_to_fp32
+from megatron.inference.text_generation.sampling import sample
+from megatron.inference.text_generation.tokenization import tokenize_prompts, detokenize_generations
+from megatron.inference.text_generation.communication import broadcast_int_list
+from megatron.training.utils import get_ltor_masks_and_position_ids, is_rank0, get_blend_and_blend_per_split
+from megatron.training.checkpointing import checkpoint_exists, find_checkpoint_rank_0, CheckpointType
+from megatron.training.arguments import add_megatron_arguments, moe_freq_type
+from megatron.training.training import print_datetime, update_train_iters
+from megatron.training.global_vars import get_one_logger, rebuild_tokenizer
+from megatron.legacy.model.utils import openai_gelu
+assert str(ModelType.encoder_and_decoder) == "encoder_and_decoder" and AttnMaskType.causal.value == 2 and divide(8, 4) == 2
+p = torch.nn.Parameter(torch.ones(4)); p.grad = torch.tensor([3.0, 0.0, 4.0, 0.0])
+assert abs(get_grad_norm_fp32([p.grad]) - 5.0) < 1e-6 and count_zeros_fp32([p]) == 2.0
+clip_grad_by_total_norm_fp32([p], 1.0, 5.0)
+assert torch.allclose(p.grad, torch.tensor([0.6, 0.0, 0.8, 0.0]), atol=1e-5)
+a = add_megatron_arguments(argparse.ArgumentParser(conflict_handler="resolve")).parse_args(["--num-layers", "3"])
+assert a.num_layers == 3 and moe_freq_type("([1]*2+[0])") == [1, 1, 0]
+assert sample(torch.tensor([[1.0, 3.0, 2.0]]), top_k=1).item() == 1
+x = torch.randn(4, 8)
+assert torch.allclose(float16_to_fp32(fp32_to_float16((x,), lambda t: t.bfloat16()))[0], x, atol=0.05)
+assert torch.equal(get_updated_expert_bias(torch.tensor([4.0, 1.0, 1.0]), torch.zeros(3), 0.5), torch.tensor([-0.5, 0.5, 0.5]))
+print("API-OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code, root], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert p.returncode == 0 and "API-OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+def test_compat_coverage_report():
+    """tools/compat_coverage.py against the reference tree (skipped when it is not mounted): most module paths resolve."""
+    import subprocess
+    import sys
+
+    import pytest
+
+    if not os.path.isdir("/root/reference/megatron"):
+        pytest.skip("reference tree not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "compat_coverage.py"), "/root/reference"], capture_output=True,
+                       text=True, timeout=600, cwd="/tmp")
+    assert p.returncode == 0, p.stderr[-2000:]
+    import json
+
+    summary = json.loads(p.stdout.splitlines()[0])
+    assert summary["modules_resolved"] >= 240 and summary["public_names_available"] >= 600, summary
