@@ -214,6 +214,71 @@ _ALIASES = {
     "megatron.training.wandb_utils": "megatronapp_b200.training.wandb_utils",
     "megatron.training.activations": "megatronapp_b200.transformer.mlp",
     "megatron.post_training.arguments": "megatronapp_b200.training.arguments",
+    "megatron.core.models.common.embeddings.rope_utils": "megatronapp_b200.models.common.embeddings",
+    "megatron.core.models.mamba.mamba_layer_specs": "megatronapp_b200.models.mamba.mamba_model",
+    "megatron.core.models.T5.t5_spec": "megatronapp_b200.models.T5.t5_model",
+    "megatron.core.models.gpt.moe_module_specs": "megatronapp_b200.models.gpt.gpt_layer_specs",
+    "megatron.core.models.retro.base_attention": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.retro.decoder_attention": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.retro.encoder_attention": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.models.retro.utils": "megatronapp_b200.models.retro.retro_model",
+    "megatron.core.transformer.heterogeneous.heterogeneous_config": "megatronapp_b200.models.gpt.heterogeneous.heterogeneous_layer_specs",
+    "megatron.core.transformer.moe.legacy_a2a_token_dispatcher": "megatronapp_b200.moe.token_dispatcher",
+    "megatron.core.transformer.moe.fused_a2a": "megatronapp_b200.moe.token_dispatcher",
+    "megatron.core.transformer.moe.grouped_gemm_util": "megatronapp_b200.ops.moe",
+    "megatron.core.distributed.custom_fsdp.param_and_grad_buffer": "megatronapp_b200.parallel.fsdp",
+    "megatron.core.ssm.mamba_config": "megatronapp_b200.config.transformer_config",
+    "megatron.core.ssm.mlp_layer": "megatronapp_b200.transformer.transformer_layer",
+    "megatron.core.dist_checkpointing.optimizer": "megatronapp_b200.optim.optimizer",
+    "megatron.core.dist_checkpointing.strategies.torch": "megatronapp_b200.ckpt.torch_dist",
+    "megatron.core.dist_checkpointing.strategies.fully_parallel": "megatronapp_b200.ckpt.torch_dist",
+    "megatron.core.dist_checkpointing.strategies.async_utils": "megatronapp_b200.training.async_utils",
+    "megatron.core.dist_checkpointing.strategies.filesystem_async": "megatronapp_b200.training.async_utils",
+    "megatron.core.dist_checkpointing.strategies.base": "megatronapp_b200.ckpt.serialization",
+    "megatron.core.dist_checkpointing.strategies.common": "megatronapp_b200.ckpt.serialization",
+    "megatron.core.dist_checkpointing.state_dict_utils": "megatronapp_b200.ckpt.serialization",
+    "megatron.core.datasets.megatron_dataset": "megatronapp_b200.data.gpt_dataset",
+    "megatron.core.datasets.utils": "megatronapp_b200.data.blended_builder",
+    "megatron.core.datasets.multimodal_dataset": "megatronapp_b200.legacy.data.multimodal_dataset",
+    "megatron.core.datasets.retro.utils": "megatronapp_b200.data.retro.config",
+    "megatron.core.datasets.retro.query.gpt_chunk_dataset": "megatronapp_b200.data.retro.query",
+    "megatron.core.datasets.retro.query.utils": "megatronapp_b200.data.retro.query",
+    "megatron.core.datasets.retro.db.dataset": "megatronapp_b200.data.retro.db",
+    "megatron.core.datasets.retro.db.utils": "megatronapp_b200.data.retro.db",
+    "megatron.core.datasets.retro.index.build": "megatronapp_b200.data.retro.index",
+    "megatron.core.datasets.retro.index.factory": "megatronapp_b200.data.retro.index",
+    "megatron.core.datasets.retro.index.utils": "megatronapp_b200.data.retro.index",
+    "megatron.core.export.trtllm.trt_model_config": "megatronapp_b200.export.trtllm",
+    "megatron.core.export.trtllm.trtllm_layers": "megatronapp_b200.export.trtllm",
+    "megatron.core.export.trtllm.model_to_trllm_mapping.default_conversion_dict": "megatronapp_b200.export.trtllm",
+    "megatron.core.inference.contexts.base_context": "megatronapp_b200.inference.core",
+    "megatron.core.inference.model_inference_wrappers.inference_wrapper_config": "megatronapp_b200.inference.core",
+    "megatron.core.inference.utils": "megatronapp_b200.inference.core",
+    "megatron.core.optimizer.cpu_offloading.hybrid_optimizer": "megatronapp_b200.optim.optimizer",
+    "megatron.core.post_training.modelopt.layers": "megatronapp_b200.post_training.quantization",
+    "megatron.core.post_training.modelopt.gpt.model_specs": "megatronapp_b200.models.gpt.gpt_layer_specs",
+    "megatron.core.post_training.modelopt.gpt.state_dict_hooks": "megatronapp_b200.post_training.quantization",
+    "megatron.core.post_training.modelopt.mamba.model_specs": "megatronapp_b200.models.mamba.mamba_model",
+    "megatron.core.inference.modelopt_support.gpt.model_specs": "megatronapp_b200.models.gpt.gpt_layer_specs",
+    "megatron.core.inference.modelopt_support.gpt.state_dict_hooks": "megatronapp_b200.post_training.quantization",
+    "megatron.core.inference.modelopt_support.mamba.model_specs": "megatronapp_b200.models.mamba.mamba_model",
+    "megatron.post_training.loss_func": "megatronapp_b200.post_training.distillation",
+    "megatron.post_training.model_provider": "megatronapp_b200.post_training.distillation",
+    "megatron.legacy.model.gpt_model": "megatronapp_b200.legacy.model",
+    "megatron.legacy.model.t5_model": "megatronapp_b200.legacy.model",
+    "megatron.legacy.model.language_model": "megatronapp_b200.legacy.model",
+    "megatron.legacy.model.transformer": "megatronapp_b200.legacy.model",
+    "megatron.legacy.model.realm_model": "megatronapp_b200.legacy.model.biencoder_model",
+    "megatron.legacy.model.fused_layer_norm": "megatronapp_b200.transformer.norms",
+    "megatron.legacy.model.rms_norm": "megatronapp_b200.transformer.norms",
+    "megatron.legacy.model.vision.vit_backbone": "megatronapp_b200.models.vision.vit_classification",
+    "megatron.legacy.data.dataset_utils": "megatronapp_b200.data.masked_dataset",
+    "megatron.legacy.data.biencoder_dataset_utils": "megatronapp_b200.data.ict_dataset",
+    "megatron.legacy.data.realm_dataset_utils": "megatronapp_b200.data.ict_dataset",
+    "megatron.training.tokenizer.gpt2_tokenization": "megatronapp_b200.data.tokenizer",
+    "megatron.training.tokenizer.bert_tokenization": "megatronapp_b200.data.tokenizer",
+    "megatron.inference.text_generation.forward_step": "megatronapp_b200.inference.core",
+    "megatron.inference.text_generation.mcore_engine_server": "megatronapp_b200.inference.server",
     # megatron.training & add-ons
     "megatron.training.arguments": "megatronapp_b200.training.arguments",
     "megatron.training.initialize": "megatronapp_b200.training.initialize",
@@ -355,7 +420,12 @@ class _Finder:
     @staticmethod
     def create_module(spec):
         if spec.name in _ALIASES:
-            return importlib.import_module(_ALIASES[spec.name])
+            mod = importlib.import_module(_ALIASES[spec.name])
+            if not hasattr(mod, "__path__") and any(k.startswith(spec.name + ".") for k in list(_ALIASES) + list(_UNIONS)):
+                # the reference has a package where this framework has one module (``...common.embeddings`` and its
+                # ``rotary_pos_embedding`` / ``language_model_embedding`` children): let the children be imported through it
+                mod.__path__ = []
+            return mod
         return _Lazy(spec.name)
 
     @staticmethod

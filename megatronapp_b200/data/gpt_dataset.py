@@ -257,3 +257,32 @@ def __getattr__(name):      # names the reference exposes from ``core/datasets/g
 
         return MockGPTDataset
     raise AttributeError(name)
+
+
+def parse_and_normalize_split(split: str) -> List[float]:
+    """``"949,50,1"`` -> normalised train / valid / test fractions (reference ``blended_megatron_dataset_config``)."""
+    return parse_split(split)
+
+
+def convert_split_vector_to_split_matrix(vector_a: List[float], vector_b: Optional[List[float]] = None):
+    """Per split the ``(begin, end)`` fraction of the document range it covers (``None`` for an empty split); with a second
+    vector, the overlap of the two bookings (used to carve e.g. a retrieval split out of the same corpus)."""
+    def matrix(v):
+        out, lo = [], 0.0
+        for f in v:
+            out.append((lo, lo + f) if f > 0 else None)
+            lo += f
+        return out
+
+    a = matrix(vector_a)
+    if vector_b is None:
+        return a
+    b = matrix(vector_b)
+    res = []
+    for x, y in zip(a, b):
+        if x is None or y is None:
+            res.append(None)
+            continue
+        lo, hi = max(x[0], y[0]), min(x[1], y[1])
+        res.append((lo, hi) if hi > lo else None)
+    return res

@@ -471,3 +471,64 @@ class StaticInferenceEngine:
             active = self.scheduler.active_request_pool
             self.controller.generate_all_output_tokens_static_batch(active)
             self.scheduler.update_requests_pools(active)
+
+
+# -- base-class and config names of the reference's ``core/inference`` tree ------------------------------------------------------
+AbstractModelInferenceWrapper = GPTInferenceWrapper          # the GPT wrapper is the base of the T5 / VLM ones here
+BaseInferenceContext = StaticInferenceContext
+
+
+class AbstractEngine:
+    """Interface of an inference engine: ``generate(prompts, sampling_params) -> List[InferenceRequest]``."""
+
+    def generate(self, prompts, sampling_params=None, **kw):
+        raise NotImplementedError
+
+
+@dataclass
+class InferenceWrapperConfig:
+    """Reference ``inference_wrapper_config.py``: the knobs a model inference wrapper is built from."""
+    hidden_size: int = 0
+    params_dtype: torch.dtype = torch.float32
+    inference_batch_times_seqlen_threshold: int = -1
+    padded_vocab_size: int = 0
+    inference_max_requests: int = 8
+    inference_max_seq_length: int = 2560
+    fp32_residual_connection: bool = False
+    nccl_all_reduce_for_prefill: bool = False
+
+    def add_attributes(self, attribute_value_pair: dict):
+        for k, v in attribute_value_pair.items():
+            setattr(self, k, v)
+
+
+class Counter:
+    """Monotonic request-id source (reference ``inference/utils.py``)."""
+
+    def __init__(self, start: int = 0) -> None:
+        self.counter = start
+
+    def __next__(self) -> int:
+        i = self.counter
+        self.counter += 1
+        return i
+
+    def reset(self) -> None:
+        self.counter = 0
+
+
+@dataclass
+class VLMInferenceRequest(InferenceRequest):
+    """An ``InferenceRequest`` that also carries the images of its prompt."""
+    num_img_embeddings_per_tile: int = 0
+    imgs: Optional[torch.Tensor] = None
+    num_tiles: Optional[torch.Tensor] = None
+    decoder_seq_length: int = 0
+
+
+class EncoderDecoderTextGenerationController(TextGenerationController):
+    """T5-style generation: the wrapper (``T5InferenceWrapper``) encodes once and decodes step by step."""
+
+
+class VLMTextGenerationController(TextGenerationController):
+    """LLaVA-style generation: the wrapper (``VLMInferenceWrapper``) splices the image embeddings in at prefill."""

@@ -469,3 +469,19 @@ class DynamicInferenceEngine:
                 if r.stream is not None:
                     r.stream.finish(r.req)
         return finished
+
+
+class ContextOverflowError(Exception):
+    """The dynamic context cannot take a request now (reference ``contexts/dynamic_context.py``)."""
+
+
+class RequestOverflowError(ContextOverflowError):
+    """More concurrent requests than ``max_requests``."""
+
+
+class TokenOverflowError(ContextOverflowError):
+    """More tokens in one step than ``max_tokens_per_step``."""
+
+
+class ChunkOverflowError(ContextOverflowError):
+    """No free KV block (the engine pauses or evicts a request instead of raising)."""

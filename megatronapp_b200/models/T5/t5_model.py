@@ -170,3 +170,33 @@ class T5Model(LanguageModule):
         if lm_labels is None:
             return logits.transpose(0, 1).contiguous()
         return self.compute_language_model_loss(lm_labels, logits)
+
+
+# -- spec / helper names of the reference's ``T5/t5_spec.py`` and ``t5_model.py`` ----------------------------------------------------
+def encoder_model_with_local_spec() -> ModuleSpec:
+    return encoder_layer_spec()
+
+
+def decoder_model_with_local_spec() -> ModuleSpec:
+    return decoder_layer_spec()
+
+
+encoder_model_with_transformer_engine_default_spec = encoder_model_with_local_spec     # one (native) implementation of the layers
+decoder_model_with_transformer_engine_default_spec = decoder_model_with_local_spec
+
+
+def get_t5_encoder_with_local_block_spec(num_layers: int):
+    return get_t5_encoder_block_spec(num_layers)
+
+
+def get_t5_decoder_with_local_block_spec(num_layers: int):
+    return get_t5_decoder_block_spec(num_layers)
+
+
+get_t5_encoder_with_transformer_engine_block_spec = get_t5_encoder_with_local_block_spec
+get_t5_decoder_with_transformer_engine_block_spec = get_t5_decoder_with_local_block_spec
+
+
+def t5_position_ids(token_ids: torch.Tensor) -> torch.Tensor:
+    """``[b, s]`` position ids ``0 .. s-1`` for every row."""
+    return torch.arange(token_ids.size(1), dtype=torch.long, device=token_ids.device).unsqueeze(0).expand_as(token_ids)

@@ -241,3 +241,57 @@ class RelativePositionEmbedding(torch.nn.Module):
         t = getattr(transformer, "input_tensor", None)
         s = (t if t is not None else transformer_input).size(0)
         return s * transformer_config.tensor_model_parallel_size if transformer_config.sequence_parallel else s
+
+
+# -- function forms of the reference's ``rope_utils.py`` ---------------------------------------------------------------------------
+def _rotate_half(x: torch.Tensor, rotary_interleaved: bool) -> torch.Tensor:
+    if not rotary_interleaved:
+        x1, x2 = torch.chunk(x, 2, dim=-1)
+        return torch.cat((-x2, x1), dim=-1)
+    x1, x2 = x[..., ::2], x[..., 1::2]
+    return torch.stack((-x2, x1), dim=-1).flatten(-2)
+
+
+def apply_rotary_pos_emb_with_cos_sin(t: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, rotary_interleaved: bool = False):
+    """``t [..., d]`` rotated by per-position ``cos`` / ``sin [..., rot]`` (``rot <= d``; the remaining channels pass through)."""
+    rot = cos.shape[-1]
+    tr, tp = t[..., :rot], t[..., rot:]
+    out = tr.float() * cos.float() + _rotate_half(tr.float(), rotary_interleaved) * sin.float()
+    return torch.cat((out.to(t.dtype), tp), dim=-1)
+
+
+def apply_rotary_pos_emb(t: torch.Tensor, freqs: torch.Tensor, config=None, cu_seqlens=None, mscale: float = 1.0, cp_group=None):
+    """``t [s, b, h, d]`` with either Megatron's ``freqs [s, 1, 1, rot]`` (the angles, each twice) or this framework's
+    ``[s, rot]`` cos | sin table (what ``RotaryEmbedding.forward`` returns here).  On a GPU the RoPE kernel is used; packed
+    sequences (``cu_seqlens``) apply each sequence's own positions."""
+    interleaved = bool(getattr(config, "rotary_interleaved", False))
+    if cu_seqlens is not None:                      # THD: t [t, h, d]; positions restart at every sequence boundary
+        bounds = [int(x) for x in (cu_seqlens.tolist() if torch.is_tensor(cu_seqlens) else cu_seqlens)]
+        parts = [apply_rotary_pos_emb(t[a:b].unsqueeze(1), freqs[: b - a], config, None, mscale).squeeze(1)
+                 for a, b in zip(bounds[:-1], bounds[1:])]
+        return torch.cat(parts, dim=0)
+    if freqs.dim() == 2:
+        # this framework's own table (``RotaryEmbedding.forward``): ``[s, rot]`` holding cos | sin of the rot / 2 angles
+        from ... import ops
+
+        out = ops.rope(t, freqs, interleaved) if t.dim() == 4 else ops.rope(t.unsqueeze(1), freqs, interleaved).squeeze(1)
+        return out if mscale == 1.0 else out * mscale
+    if t.is_cuda and mscale == 1.0 and t.dim() == 4:
+        from ...core_api.te import fused_apply_rotary_pos_emb
+
+        return fused_apply_rotary_pos_emb(t, freqs, interleaved=interleaved)
+    f = freqs.float()
+    return apply_rotary_pos_emb_with_cos_sin(t, (f.cos() * mscale).to(t.dtype), (f.sin() * mscale).to(t.dtype), interleaved)
+
+
+def get_pos_emb_on_this_cp_rank(pos_emb: torch.Tensor, seq_dim: int, cp_group=None) -> torch.Tensor:
+    """This context-parallel rank's two zig-zag chunks (``rank`` and ``2 cp - rank - 1``) of a position-embedding table."""
+    from ...parallel import state as ps
+
+    cp, rank = ps.get_context_parallel_world_size(), ps.get_context_parallel_rank()
+    if cp == 1:
+        return pos_emb
+    idx = torch.tensor([rank, 2 * cp - rank - 1], device=pos_emb.device)
+    shape = pos_emb.shape
+    x = pos_emb.view(*shape[:seq_dim], 2 * cp, -1, *shape[seq_dim + 1:]).index_select(seq_dim, idx)
+    return x.view(*shape[:seq_dim], -1, *shape[seq_dim + 1:])

@@ -83,3 +83,18 @@ def get_gpt_decoder_block_spec(config, use_transformer_engine: bool = False) -> 
     off = get_transformer_layer_offset(config)
     n = get_num_layers_to_build(config)
     return TransformerBlockSubmodules(layer_specs=specs[off:off + n], layer_norm=FusedLayerNorm)
+
+
+def get_moe_module_spec(use_te: bool = True, num_experts: Optional[int] = None, moe_grouped_gemm: bool = False,
+                        moe_use_legacy_grouped_gemm: bool = False) -> ModuleSpec:
+    """``MoELayer`` spec with its experts (reference ``moe_module_specs.get_moe_module_spec``)."""
+    if num_experts is None:
+        raise ValueError("num_experts is required for an MoE module spec")
+    return get_mlp_module_spec(use_te=False, num_experts=num_experts, moe_grouped_gemm=moe_grouped_gemm)
+
+
+def get_gpt_mtp_block_spec(config, spec, use_transformer_engine: bool = False):
+    """Multi-token-prediction block spec: ``config.mtp_num_layers`` copies of the decoder layer spec (``None`` without MTP)."""
+    from ...transformer.multi_token_prediction import get_mtp_block_spec
+
+    return get_mtp_block_spec(config, spec)

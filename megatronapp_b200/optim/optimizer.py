@@ -609,3 +609,38 @@ def get_megatron_optimizer(config: OptimizerConfig, model_chunks, no_weight_deca
         if not isinstance(m, DistributedDataParallel):
             raise TypeError("get_megatron_optimizer expects DistributedDataParallel-wrapped chunks")
     return MegatronOptimizer(config, list(model_chunks), no_weight_decay_cond, scale_lr_cond, lr_mult)
+
+
+# -- class names of the reference's ``optimizer.py`` ----------------------------------------------------------------------------------
+MixedPrecisionOptimizer = MegatronOptimizer          # fp32 master weights + 16-bit model weights are the one optimizer here
+Float16OptimizerWithFloat16Params = MegatronOptimizer
+DistributedOptimizer = MegatronOptimizer             # ZeRO-1 sharding is a mode of it (``use_distributed_optimizer``)
+
+
+class ProxyDict:
+    """Write-through view on a dict living inside another object (``optimizer.state`` / ``param_groups`` of a chained
+    optimizer's members): item access is forwarded to ``getattr(inner, attr)``."""
+
+    def __init__(self, inner_dicts):
+        self._inner_dicts = inner_dicts
+
+    def __getitem__(self, key):
+        idx, k = key
+        return self._inner_dicts[idx][k]
+
+    def __setitem__(self, key, value):
+        idx, k = key
+        self._inner_dicts[idx][k] = value
+
+    def __len__(self):
+        return sum(len(d) for d in self._inner_dicts)
+
+    def __iter__(self):
+        for idx, d in enumerate(self._inner_dicts):
+            for k in d:
+                yield (idx, k)
+
+    def items(self):
+        for idx, d in enumerate(self._inner_dicts):
+            for k, v in d.items():
+                yield (idx, k), v

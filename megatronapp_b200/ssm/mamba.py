@@ -277,3 +277,28 @@ class MambaStack(MegatronModule):
         if self.final_norm is not None:
             hidden_states = self.final_norm(hidden_states)
         return hidden_states
+
+
+# -- spec dataclasses / names of the reference's ``ssm`` package ----------------------------------------------------------------------
+@dataclass
+class MambaLayerSubmodules:
+    norm: Union[ModuleSpec, type] = FusedLayerNorm
+    mixer: Union[ModuleSpec, type] = MambaMixer
+    mamba_bda: Union[ModuleSpec, type, None] = None
+
+
+@dataclass
+class MambaStackSubmodules:
+    mamba_layer: Union[ModuleSpec, type] = MambaLayer
+    attention_layer: Union[ModuleSpec, type, None] = None
+    mlp_layer: Union[ModuleSpec, type, None] = None
+
+
+class ExtendedRMSNorm(FusedLayerNorm):
+    """Gated-RMSNorm name of the reference's mixer; the grouped gated norm itself is inside ``MambaMixer.forward`` here."""
+
+    def __init__(self, config, hidden_size: int, eps: float = 1e-5, **kw):
+        import dataclasses as _dc
+
+        super().__init__(_dc.replace(config, normalization="RMSNorm") if config is not None else None, hidden_size, eps,
+                         normalization="RMSNorm")

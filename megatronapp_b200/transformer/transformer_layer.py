@@ -136,3 +136,19 @@ class TransformerLayer(MegatronModule):
 
     def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
         return super().sharded_state_dict(prefix, sharded_offsets, metadata)
+
+
+class BaseTransformerLayer:
+    """Marker base class (reference ``BaseTransformerLayer``): layers implementing the ``TransformerLayer`` call contract --
+    ``forward(hidden_states, attention_mask, context, context_mask, rotary_pos_emb, inference_context, packed_seq_params)``
+    returning ``(hidden_states, context)`` -- can be placed in a ``TransformerBlock`` spec."""
+
+
+class MLPLayer(TransformerLayer):
+    """A transformer layer reduced to its MLP half (pre-norm -> MLP -> residual): the ``-`` symbol of hybrid Mamba stacks
+    (reference ``ssm/mlp_layer.py``).  Built from a spec whose attention submodules are ``IdentityOp``."""
+
+    def forward(self, hidden_states, attention_mask=None, **kwargs):
+        residual = hidden_states
+        out, bias = self.mlp(self.pre_mlp_layernorm(hidden_states))
+        return self._bda(out, bias, residual), kwargs.get("context")

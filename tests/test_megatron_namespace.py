@@ -134,4 +134,4 @@ def test_compat_coverage_report():
     import json
 
     summary = json.loads(p.stdout.splitlines()[0])
-    assert summary["modules_resolved"] >= 240 and summary["public_names_available"] >= 600, summary
+    assert summary["modules_resolved"] >= 320 and summary["public_names_available"] >= 660, summary
