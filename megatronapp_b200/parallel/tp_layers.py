@@ -609,30 +609,6 @@ def copy_tensor_model_parallel_attributes(destination_tensor, source_tensor):
             setattr(destination_tensor, k, getattr(source_tensor, k))
 
 
-def linear_with_frozen_weight(input, weight, bias, gradient_accumulation_fusion, allreduce_dgrad, sequence_parallel,
-                              grad_output_buffer=None, wgrad_deferral_limit=None, async_grad_allreduce=None, tp_group=None):
-    """``Y = X W^T + b`` for a weight that does not train: only the data gradient is produced (all-reduced over the tensor-parallel
-    group when ``allreduce_dgrad``).  The sequence-parallel form gathers the input first."""
-    from .mappings import copy_to_tensor_model_parallel_region, gather_from_sequence_parallel_region
-
-    w = weight.detach()
-    if sequence_parallel:
-        x = gather_from_sequence_parallel_region(input, tensor_parallel_output_grad=True)
-    else:
-        x = copy_to_tensor_model_parallel_region(input) if allreduce_dgrad else input
-    return ops.linear(x, w, bias)
-
-
-def linear_with_grad_accumulation_and_async_allreduce(input, weight, bias, gradient_accumulation_fusion, allreduce_dgrad,
-                                                      sequence_parallel, grad_output_buffer=None, wgrad_deferral_limit=0,
-                                                      async_grad_allreduce=None, tp_group=None):
-    """Functional form of the column-parallel linear (reference ``LinearWithGradAccumulationAndAsyncCommunication.apply``): the
-    forward all-gather (sequence parallel), the dgrad all-reduce / reduce-scatter and the wgrad accumulation into ``main_grad`` are
-    what ``_ColumnParallelFn`` does."""
-    return _ColumnParallelFn.apply(input, weight, bias, bool(sequence_parallel), bool(gradient_accumulation_fusion),
-                                   bool(allreduce_dgrad and not sequence_parallel))
-
-
 LinearWithGradAccumulationAndAsyncCommunication = _ColumnParallelFn
 
 
@@ -641,4 +617,4 @@ class LinearWithFrozenWeight:
 
     @staticmethod
     def apply(input, weight, bias, allreduce_dgrad, tp_group=None):
-        return linear_with_frozen_weight(input, weight, bias, False, allreduce_dgrad, False)
+        return linear_with_frozen_weight(input, weight, bias, allreduce_dgrad=allreduce_dgrad)
