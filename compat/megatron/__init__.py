@@ -55,7 +55,6 @@ _ALIASES = {
     "megatron.core.dist_checkpointing.serialization": "megatronapp_b200.ckpt.serialization",
     "megatron.core.dist_checkpointing.validation": "megatronapp_b200.ckpt.serialization",
     "megatron.core.dist_checkpointing.core": "megatronapp_b200.ckpt.serialization",
-    "megatron.core.dist_checkpointing.mapping": "megatronapp_b200.ckpt",
     "megatron.core.models.gpt.gpt_model": "megatronapp_b200.models.gpt.gpt_model",
     "megatron.core.models.gpt.gpt_layer_specs": "megatronapp_b200.models.gpt.gpt_layer_specs",
     "megatron.core.models.bert.bert_model": "megatronapp_b200.models.bert.bert_model",
@@ -366,8 +365,11 @@ _UNIONS = {
     "megatron.core.transformer.utils": ("megatronapp_b200.core_api.transformer_utils", "megatronapp_b200.ckpt.sharded"),
     "megatron.legacy.model.utils": ("megatronapp_b200.core_api.transformer_utils", "megatronapp_b200.config.transformer_config",
                                     "megatronapp_b200.core_api.utils"),
-    "megatron.core.dist_checkpointing.utils": ("megatronapp_b200.ckpt.serialization", "megatronapp_b200.ckpt.sharded"),
-    "megatron.core.dist_checkpointing.dict_utils": ("megatronapp_b200.ckpt.serialization", "megatronapp_b200.ckpt.sharded"),
+    "megatron.core.dist_checkpointing.utils": ("megatronapp_b200.core_api.dist_ckpt_utils", "megatronapp_b200.ckpt.serialization",
+                                               "megatronapp_b200.ckpt.sharded"),
+    "megatron.core.dist_checkpointing.dict_utils": ("megatronapp_b200.core_api.dist_ckpt_utils",),
+    "megatron.core.dist_checkpointing.mapping": ("megatronapp_b200.core_api.dist_ckpt_utils", "megatronapp_b200.ckpt",
+                                                 "megatronapp_b200.ckpt.sharded", "megatronapp_b200.ckpt.serialization"),
 }
 
 

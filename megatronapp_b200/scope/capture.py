@@ -221,3 +221,51 @@ class TensorTracers:
                 red = torch.zeros(x.shape[0], 2)
             self.report_fn((i, FlagType.MLP2_Plot), [rec.shape[0], rec.shape[1]], red.flatten())
         self.mlp2_record = [None] * len(self.mlp2_record)
+
+
+# -- module-level accessors of the reference's ``core/tensor_tracer.py`` (state lives in ``scope.hooks``) -------------------------
+def _registry(create: bool = False):
+    from . import hooks
+
+    if hooks._CAPTURE is None and create:
+        try:
+            from ..training.global_vars import get_args
+
+            n = int(get_args().num_layers)
+        except Exception:  # noqa: BLE001  (library use)
+            n = 0
+        hooks.install(TensorTracers(n), hooks._DISTURB)
+    return hooks._CAPTURE
+
+
+def get_tensor_tracers() -> Optional["TensorTracers"]:
+    return _registry(create=True)
+
+
+def get_tt_flags() -> "TTFlags":
+    return _registry(create=True).flags
+
+
+def get_compressor() -> "DefaultCompressor":
+    return _registry(create=True).compressor
+
+
+def get_report():
+    reg = _registry()
+    return (reg.report_fn if reg is not None and reg.report_fn is not None else (lambda name, args, tensor: None))
+
+
+def set_report(func) -> None:
+    _registry(create=True).set_report(func)
+
+
+def unset_report() -> None:
+    reg = _registry()
+    if reg is not None:
+        reg.set_report(None)
+
+
+def set_filter() -> None:
+    """Reset the per-layer MLP2 records the result plot is filtered with."""
+    reg = _registry(create=True)
+    reg.mlp2_record = [None] * len(reg.mlp2_record)

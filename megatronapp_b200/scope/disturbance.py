@@ -42,3 +42,20 @@ class Disturbance:
             with torch.no_grad():
                 return _FNS[self.fn[kind]](x, self.coef[kind])
         return _FNS[self.fn[kind]](x, self.coef[kind])
+
+
+def get_disturbance() -> "Disturbance":
+    """The installed perturbation object (created on first use), reference ``tensor_disturbance.get_disturbance``."""
+    from . import hooks
+
+    if hooks._DISTURB is None:
+        hooks.install(hooks._CAPTURE, Disturbance())
+    return hooks._DISTURB
+
+
+def noise1_factory(coef: float):
+    return lambda x: noise1(x, coef)
+
+
+def noise2_factory(val: float):
+    return lambda x: noise2(x, val)

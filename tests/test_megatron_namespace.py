@@ -134,4 +134,34 @@ def test_compat_coverage_report():
     import json
 
     summary = json.loads(p.stdout.splitlines()[0])
-    assert summary["modules_resolved"] >= 320 and summary["public_names_available"] >= 660, summary
+    assert summary["modules_resolved"] >= 320 and summary["public_names_available"] >= 700, summary
+
+
+def test_dist_checkpointing_dict_helpers():
+    """core_api.dist_ckpt_utils (reference dict_utils / utils / mapping): extraction by type, prefix rewriting, factories."""
+    import torch
+
+    from megatronapp_b200.ckpt.sharded import ShardedTensor
+    from megatronapp_b200.core_api import dist_ckpt_utils as u
+
+    t = lambda k: ShardedTensor.from_rank_offsets(k, torch.zeros(2, 2))  # noqa: E731
+    sd = {"a": t("layer.w"), "b": {"c": t("layer.b"), "n": 3}, "l": [t("x.0"), 5]}
+    yes, no = u.extract_sharded_tensors(sd)
+    assert sorted(yes) == ["a", "b", "l"] and no == {"b": {"n": 3}, "l": [5]} and len(yes["l"]) == 1
+    u.add_prefix_for_sharding(sd, "model.")
+    u.apply_prefix_mapping(sd, {"model.layer.": "m.L."})
+    assert (sd["a"].key, sd["b"]["c"].key, sd["l"][0].key) == ("m.L.w", "m.L.b", "model.x.0")
+    assert u.diff({"a": 1, "b": [1, 2]}, {"a": 2, "c": 0, "b": [1, 3]})[1] == [("c",)]
+    assert u.merge({"a": {"x": 1}}, {"a": {"y": 2}}) == {"a": {"x": 1, "y": 2}}
+    f = u.ShardedTensorFactory("w", torch.arange(4.0), lambda k, d, r, fr: {"lo": t(k + ".lo"), "hi": t(k + ".hi")},
+                               lambda sub: torch.cat([sub["lo"], sub["hi"]]))
+    s2 = {"w": f}
+    u.apply_factories(s2)
+    assert sorted(s2["w"]) == ["hi", "lo"] and s2["w"]["lo"].key == "w.lo"
+    merged = u.apply_factory_merges({"w": {"lo": torch.zeros(1), "hi": torch.ones(1)}}, {"w": f})
+    assert merged["w"].tolist() == [0.0, 1.0]
+    assert u.is_main_replica((0, 0, 0)) and not u.is_main_replica((0, 1, 0))
+    import pytest
+
+    with pytest.raises(ValueError):
+        list(u.zip_strict([1], [1, 2]))
