@@ -406,3 +406,105 @@ def get_forward_backward_func():
             return forward_backward_pipelining_with_interleaving
         return forward_backward_pipelining_without_interleaving
     return forward_backward_no_pipelining
+
+
+# -- helper names of the reference's ``pipeline_parallel/schedules.py`` ---------------------------------------------------------------
+def get_pp_rank_microbatches(num_microbatches: int, num_model_chunks: int, microbatch_group_size_per_vp_stage: Optional[int],
+                             forward_only: bool = False):
+    """-> ``(total virtual microbatches, all in warm-up?, warm-up count, remaining count)`` for this pipeline rank."""
+    pp, rank = ps.get_pipeline_model_parallel_world_size(), ps.get_pipeline_model_parallel_rank()
+    total = num_microbatches * num_model_chunks
+    if forward_only:
+        warm = total
+    elif num_model_chunks > 1:
+        warm = interleaved_warmup(pp, rank, num_microbatches, num_model_chunks, microbatch_group_size_per_vp_stage or pp)
+    else:
+        warm = min(pp - rank - 1, total)
+    return total, warm >= total, warm, total - warm
+
+
+def convert_schedule_table_to_order(num_warmup_microbatches: int, num_model_chunks: int, schedule_table) -> List[int]:
+    """Execution order as signed chunk numbers: ``+(chunk + 1)`` = a forward of that chunk, ``-(chunk + 1)`` = a backward
+    (backwards visit the chunks in reverse: chunk ``C - 1 - c``); warm-up forwards, then 1F1B pairs, then the cool-down backwards."""
+    _, chunk_ids = zip(*schedule_table)
+    fwd = [c + 1 for c in chunk_ids]
+    bwd = [c - num_model_chunks for c in chunk_ids]           # -(C - c): chunk C-1-c, negated and 1-based
+    order = fwd[:num_warmup_microbatches]
+    for i in range(num_warmup_microbatches, len(fwd)):
+        order.append(fwd[i])
+        order.append(bwd[i - num_warmup_microbatches])
+    if num_warmup_microbatches > 0:
+        order.extend(bwd[-num_warmup_microbatches:])
+    return order
+
+
+def check_first_val_step(first_val_step: Optional[bool], forward_only: bool, cond: bool) -> bool:
+    """fp8 weight caching: recompute cached weights only on the first validation microbatch."""
+    if first_val_step is not None and forward_only:
+        return first_val_step and cond
+    return cond
+
+
+def set_current_microbatch(model, microbatch_id: int) -> None:
+    """Tell the layers which microbatch runs (CUDA-graph / fp8 weight-cache bookkeeping keyed by microbatch)."""
+    core = _unwrap_chunk(model)
+    decoder = getattr(core, "decoder", None)
+    for layer in getattr(decoder, "layers", []) or []:
+        layer.current_microbatch = microbatch_id
+
+
+def clear_embedding_activation_buffer(config, model):
+    """Drop the output layer's stashed activations of ``defer_embedding_wgrad_compute`` (last stage only)."""
+    if ps.is_pipeline_last_stage(ignore_virtual=True) and getattr(config, "defer_embedding_wgrad_compute", False):
+        m = _unwrap_chunk(model[-1] if isinstance(model, list) else model)
+        if getattr(m, "share_embeddings_and_output_weights", False) or hasattr(m, "output_layer"):
+            buf = getattr(m, "embedding_activation_buffer", None)
+            if buf is not None:
+                buf.clear()
+            return m
+    return None
+
+
+def finish_embedding_wgrad_compute(config, embedding_module):
+    """Run the deferred output-layer weight-gradient GEMMs (see ``core_api.utils.drain_embedding_wgrad_compute``)."""
+    if ps.is_pipeline_last_stage(ignore_virtual=True) and getattr(config, "defer_embedding_wgrad_compute", False) \
+            and embedding_module is not None:
+        from ..core_api.utils import drain_embedding_wgrad_compute
+
+        weight = embedding_module.shared_embedding_or_output_weight() \
+            if getattr(embedding_module, "share_embeddings_and_output_weights", False) else embedding_module.output_layer.weight
+        drain_embedding_wgrad_compute(config, getattr(embedding_module, "embedding_activation_buffer", []),
+                                      getattr(embedding_module, "grad_output_buffer", []), weight)
+
+
+def recv_forward(tensor_shapes, config):
+    shapes = tensor_shapes if isinstance(tensor_shapes, list) else [tensor_shapes]
+    return [None if s is None else p2p.recv_forward(s, config) for s in shapes]
+
+
+def recv_backward(tensor_shapes, config):
+    shapes = tensor_shapes if isinstance(tensor_shapes, list) else [tensor_shapes]
+    return [None if s is None else p2p.recv_backward(s, config) for s in shapes]
+
+
+def send_forward(output_tensors, tensor_shapes, config):
+    outs = output_tensors if isinstance(output_tensors, list) else [output_tensors]
+    for o in outs:
+        if o is not None:
+            p2p.send_forward(o, config)
+
+
+def send_backward(input_tensor_grads, tensor_shapes, config):
+    grads = input_tensor_grads if isinstance(input_tensor_grads, list) else [input_tensor_grads]
+    for g in grads:
+        if g is not None:
+            p2p.send_backward(g, config)
+
+
+def send_corresponding_forward(tensor, config=None):
+    """MegaFBD: a forward rank hands a stage input to its backward twin."""
+    return p2p.send_corresponding_forward(tensor, config)
+
+
+def recv_corresponding_forward(tensor_shape, dtype):
+    return p2p.recv_corresponding_forward(tensor_shape, dtype)

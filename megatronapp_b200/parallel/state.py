@@ -500,3 +500,59 @@ def init_distributed(backend: Optional[str] = None, timeout_minutes: int = 30) -
         kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
     dist.init_process_group(backend=backend, world_size=world, rank=rank,
                             timeout=datetime.timedelta(minutes=timeout_minutes), **kwargs)
+
+
+# -- group-construction helpers of the reference's ``parallel_state.py`` -----------------------------------------------------------
+def get_nccl_options(pg_name: str, nccl_comm_cfgs: dict):
+    """``ProcessGroupNCCL.Options`` for ``pg_name`` from a communicator config (``--nccl-communicator-config-path`` yaml:
+    ``{group: {cga_cluster_size, max_ctas, min_ctas, net_name}}``); ``None`` when the group has no entry."""
+    if not nccl_comm_cfgs or pg_name not in nccl_comm_cfgs:
+        return None
+    cfg = nccl_comm_cfgs[pg_name]
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.cga_cluster_size = cfg.get("cga_cluster_size", 4)
+    opts.config.max_ctas = cfg.get("max_ctas", 32)
+    opts.config.min_ctas = cfg.get("min_ctas", 1)
+    if "net_name" in cfg:
+        opts.config.net_name = cfg["net_name"]
+    return opts
+
+
+def create_group(ranks=None, timeout=None, backend=None, pg_options=None, use_local_synchronization: bool = False, group_desc=None):
+    """``torch.distributed.new_group`` with the keyword set the reference uses (a description where torch supports one)."""
+    kwargs = {"ranks": ranks, "timeout": timeout, "backend": backend, "pg_options": pg_options,
+              "use_local_synchronization": use_local_synchronization}
+    try:
+        return dist.new_group(**kwargs, group_desc=group_desc)
+    except TypeError:                      # older torch: no ``group_desc``
+        return dist.new_group(**kwargs)
+
+
+def generate_masked_orthogonal_rank_groups(world_size: int, parallel_size: List[int], mask: List[bool]) -> List[List[int]]:
+    """All rank groups that vary along the masked dimensions of a ``parallel_size`` grid (first dimension fastest) while the
+    unmasked coordinates stay fixed -- the rule ``RankGenerator`` derives every tensor / pipeline / data / context / expert
+    parallel group from (reference ``parallel_state.py``)."""
+    def prefix_product(a, init=1):
+        r = [init]
+        for v in a:
+            init = init * v
+            r.append(init)
+        return r
+
+    def decompose(index, shape):
+        stride = prefix_product(shape)
+        return [(index // d) % s for s, d in zip(shape, stride)]
+
+    masked_shape = [s for s, m in zip(parallel_size, mask) if m]
+    unmasked_shape = [s for s, m in zip(parallel_size, mask) if not m]
+    global_stride = prefix_product(parallel_size)
+    masked_stride = [d for d, m in zip(global_stride, mask) if m]
+    unmasked_stride = [d for d, m in zip(global_stride, mask) if not m]
+    group_size = prefix_product(masked_shape)[-1]
+    num_of_group = world_size // group_size
+    ranks = []
+    for group_index in range(num_of_group):
+        fixed = decompose(group_index, unmasked_shape)
+        base = sum(x * y for x, y in zip(fixed, unmasked_stride))
+        ranks.append([base + sum(x * y for x, y in zip(decompose(r, masked_shape), masked_stride)) for r in range(group_size)])
+    return ranks
