@@ -224,3 +224,95 @@ def fused_vocab_parallel_cross_entropy(vocab_parallel_logits, target, tp_group=N
     from ..parallel.cross_entropy import vocab_parallel_cross_entropy
 
     return vocab_parallel_cross_entropy(vocab_parallel_logits, target)
+
+
+# -- remaining function names of fused_bias_geglu / fused_bias_swiglu / fused_cross_entropy ---------------------------------------------
+def geglu_back(g, y):
+    def dgelu(a):
+        t = torch.tanh(0.79788456 * a * (1 + 0.044715 * a * a))
+        return 0.5 * a * ((1 - t * t) * (0.79788456 + 0.1070322243 * a * a)) + 0.5 * (1 + t)
+
+    return _glu_back(g, y, lambda a: F.gelu(a, approximate="tanh"), dgelu).to(y.dtype)
+
+
+def bias_geglu_back(g, y, bias):
+    return geglu_back(g, y + bias)
+
+
+class GeGLUFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input):
+        ctx.save_for_backward(input)
+        return geglu(input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (input,) = ctx.saved_tensors
+        return geglu_back(grad_output, input)
+
+
+class BiasGeGLUFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, bias):
+        ctx.save_for_backward(input, bias)
+        return bias_geglu(bias, input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, bias = ctx.saved_tensors
+        tmp = bias_geglu_back(grad_output, input, bias)
+        return tmp, tmp.reshape(-1, tmp.shape[-1]).sum(0)
+
+
+def weighted_swiglu(y, weights):
+    return (ops.swiglu(y, None).float() * weights.float()).to(y.dtype)
+
+
+def weighted_swiglu_back(g, y, weights):
+    """-> (d input, d weights) of ``weighted_swiglu``."""
+    out = ops.swiglu(y.detach(), None).float()
+    gin = swiglu_back(g.float() * weights.float(), y)
+    return gin, (out * g.float()).sum(dim=-1, keepdim=True).to(weights.dtype)
+
+
+class WeightedSwiGLUFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, weights, fp8_input_store=False):
+        ctx.save_for_backward(input, weights)
+        return weighted_swiglu(input, weights)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weights = ctx.saved_tensors
+        gin, gw = weighted_swiglu_back(grad_output, input, weights)
+        return gin, gw, None
+
+
+def calculate_logits_max(vocab_parallel_logits):
+    """fp32 logits and their row maximum over this vocabulary shard (to be MAX-all-reduced)."""
+    logits = vocab_parallel_logits.float()
+    return logits, torch.max(logits, dim=-1)[0]
+
+
+def calculate_predicted_logits(vocab_parallel_logits, target, logits_max, vocab_start_index: int, vocab_end_index: int):
+    """Shifted logits, this shard's contribution to the target logit and to the soft-max normaliser (both to be SUM-all-reduced)."""
+    logits = vocab_parallel_logits - logits_max.unsqueeze(dim=-1)
+    target_mask = (target < vocab_start_index) | (target >= vocab_end_index)
+    masked_target = (target - vocab_start_index).masked_fill(target_mask, 0)
+    flat = logits.reshape(-1, logits.shape[-1])
+    picked = flat[torch.arange(flat.shape[0], device=flat.device), masked_target.reshape(-1)].view_as(target)
+    predicted = picked.masked_fill(target_mask, 0.0)
+    exp_logits = torch.exp(logits)
+    return target_mask, masked_target.reshape(-1), predicted, exp_logits.sum(dim=-1), exp_logits
+
+
+def calculate_cross_entropy_loss(exp_logits, predicted_logits, sum_exp_logits):
+    """-> (softmax probabilities of this shard, per-token loss) from the reduced sums."""
+    return exp_logits / sum_exp_logits.unsqueeze(dim=-1), torch.log(sum_exp_logits) - predicted_logits
+
+
+def calculate_gradients(softmax, grad_output, target_mask, masked_target_1d):
+    grad = softmax.clone().reshape(-1, softmax.shape[-1])
+    rows = torch.arange(grad.shape[0], device=grad.device)
+    grad[rows, masked_target_1d] -= 1.0 - target_mask.reshape(-1).float()
+    return grad.view_as(softmax) * grad_output.unsqueeze(dim=-1)

@@ -147,3 +147,33 @@ class BlendedMegatronDatasetBuilder:
                 frac = c.split_matrix[i]
                 out.append(None if frac is None or (n is not None and n <= 0) else self._mix(c.blend, i, n, frac))
         return out
+
+
+# -- names of the reference's ``datasets/utils.py`` and ``blended_megatron_dataset_config.py`` ------------------------------------------
+from enum import Enum as _Enum  # noqa: E402
+
+from .gpt_dataset import convert_split_vector_to_split_matrix, parse_and_normalize_split  # noqa: E402,F401
+
+
+class Split(_Enum):
+    train = 0
+    valid = 1
+    test = 2
+
+
+def normalize(weights):
+    """Weights scaled to sum to one."""
+    total = float(sum(weights))
+    return [w / total for w in weights]
+
+
+def compile_helpers():
+    """Build the C++ index helpers (sample / shuffle / blending index construction).  They are compiled ahead of time by
+    ``megatronapp_b200/build.py`` (``data/_helpers.so``); this (re)builds them when the shared object is missing."""
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    if not os.path.exists(os.path.join(here, "_helpers.so")):
+        from ..build import build_all
+
+        build_all()

@@ -400,3 +400,23 @@ def fp8_linear(x, weight, bias=None, recipe: Optional[Fp8Recipe] = None, cache: 
             return MxFp8LinearNativeFn.apply(x, weight, bias, recipe, cache, fuse_wgrad)
         return MxFp8LinearFn.apply(x, weight, bias, recipe, cache, fuse_wgrad)
     return Fp8LinearFn.apply(x, weight, bias, recipe or Fp8Recipe(), cache or _WeightCache(), fuse_wgrad)
+
+
+# -- names of the reference's ``core/fp8_utils.py`` (Transformer-Engine Float8Tensor parameters do not exist here) ----------------
+def is_float8tensor(tensor) -> bool:
+    """Parameters are never stored as fp8 tensors: weights are quantised per step into a cache (``_WeightCache``)."""
+    return False
+
+
+def modify_underlying_storage(tensor, new_raw_data):
+    tensor.data = new_raw_data
+
+
+def quantize_param_shard(model_params, main_params, start_offsets, data_parallel_group, fsdp_shard_model_params=None):
+    """fp8 parameter shards (``--fp8-param-gather``) are not used: the bf16 parameters are updated by the optimizer directly."""
+    return None
+
+
+def correct_amax_history_if_needed(model):
+    """Delayed-scaling amax histories live in ``Fp8Meta`` objects next to each linear and need no fix-up after a load."""
+    return None

@@ -238,3 +238,18 @@ class _RouterTopK(torch.autograd.Function):
 def router_topk(logits: torch.Tensor, k: int, pre_softmax: bool = False, scaling: Optional[float] = None):
     """Fused softmax + top-k -> (dense probs [n, E], routing map [n, E] bool, tokens_per_expert [E] int32)."""
     return _RouterTopK.apply(logits, k, pre_softmax, float(scaling) if scaling else 1.0)
+
+
+def grouped_gemm_is_available() -> bool:
+    """The grouped GEMM is part of the framework's own extension (no external ``grouped_gemm`` package)."""
+    from . import have_ext
+
+    return have_ext()
+
+
+def assert_grouped_gemm_is_available() -> None:
+    if not grouped_gemm_is_available():
+        raise AssertionError("the grouped tcgen05 GEMM needs the compiled extension (python -c 'import __graft_entry__ as g; g.build()')")
+
+
+ops = None          # reference ``grouped_gemm_util.ops`` handle: the entry points are ``grouped_gemm`` / ``grouped_wgrad`` above

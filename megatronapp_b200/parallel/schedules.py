@@ -508,3 +508,21 @@ def send_corresponding_forward(tensor, config=None):
 
 def recv_corresponding_forward(tensor_shape, dtype):
     return p2p.recv_corresponding_forward(tensor_shape, dtype)
+
+
+def send_forward_recv_backward(output_tensors, tensor_shapes, config):
+    outs = output_tensors if isinstance(output_tensors, list) else [output_tensors]
+    shapes = tensor_shapes if isinstance(tensor_shapes, list) else [tensor_shapes]
+    return [None if s is None else p2p.send_forward_recv_backward(o, s, config) for o, s in zip(outs, shapes)]
+
+
+def send_backward_recv_forward(input_tensor_grads, tensor_shapes, config):
+    grads = input_tensor_grads if isinstance(input_tensor_grads, list) else [input_tensor_grads]
+    shapes = tensor_shapes if isinstance(tensor_shapes, list) else [tensor_shapes]
+    return [None if s is None else p2p.send_backward_recv_forward(g, s, config) for g, s in zip(grads, shapes)]
+
+
+def forward_step_no_grad(*args, **kwargs):
+    """``forward_step`` under ``torch.no_grad`` (MegaFBD forward ranks, evaluation)."""
+    with torch.no_grad():
+        return forward_step(*args, **kwargs)

@@ -154,3 +154,14 @@ def capture_block_upfront(block: nn.Module, hidden_states: torch.Tensor, *extra:
             saved = m.calls
             m(*(torch.zeros_like(a).requires_grad_(a.requires_grad) for a in args))   # triggers the capture
             m.calls, m.replays = saved, max(0, m.replays - 1)
+
+
+def is_graph_capturing() -> bool:
+    """True while a CUDA graph is being captured on the current stream."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def create_cudagraphs() -> None:
+    """The reference records graph-able calls first and captures them all here.  ``CudaGraphManager`` captures a layer the first
+    time it is called after its warm-up steps (or up front through ``capture_block_upfront``), so nothing is pending."""
+    return None

@@ -119,3 +119,12 @@ class MLP(MegatronModule):
             out, out_bias = self.linear_fc2(inter)
             scope_hooks.tik_tensor(5, self.layer_number, out)
         return out, out_bias
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def fast_gelu(x):
+    """tanh approximation written out (reference ``training/activations.py``)."""
+    return 0.5 * x * (1.0 + torch.tanh(x * 0.7978845608 * (1.0 + 0.044715 * x * x)))

@@ -176,3 +176,36 @@ def get_mtp_block_spec(config, transformer_layer_spec: ModuleSpec) -> Optional[M
     ls = get_mtp_layer_spec(transformer_layer_spec)
     return ModuleSpec(module=MultiTokenPredictionBlock,
                       submodules=MultiTokenPredictionBlockSubmodules(layer_specs=[ls] * n))
+
+
+def get_mtp_num_layers_to_build(config) -> int:
+    """MTP layers live on the last pipeline stage only."""
+    from ..parallel import state as ps
+
+    return int(config.mtp_num_layers or 0) if ps.is_pipeline_last_stage(ignore_virtual=True) else 0
+
+
+def get_mtp_layer_offset(config) -> int:
+    """All MTP layers are on one stage: their local index is their global index."""
+    return 0
+
+
+def tie_word_embeddings_state_dict(sharded_state_dict: dict, word_emb_weight, word_emb_weight_key: str) -> None:
+    """The MTP block's embedding is the model's: store it under the model's key (replica of the first stage's copy)."""
+    from ..ckpt.sharded import make_tp_sharded_tensor_for_checkpoint
+    from ..parallel import state as ps
+
+    mtp_key = f"{word_emb_weight_key.rsplit('embedding.', 1)[0]}mtp_word_emb.weight"
+    sharded_state_dict.pop(mtp_key, None)
+    rid = (1, 0, ps.get_data_parallel_rank(with_context_parallel=True))      # not the main replica: stage 0 writes the tensor
+    sharded_state_dict[mtp_key] = make_tp_sharded_tensor_for_checkpoint(word_emb_weight, word_emb_weight_key, 0, replica_id=rid)
+
+
+def tie_output_layer_state_dict(sharded_state_dict: dict, output_layer_weight, output_layer_weight_key: str) -> None:
+    from ..ckpt.sharded import make_tp_sharded_tensor_for_checkpoint
+    from ..parallel import state as ps
+
+    mtp_key = f"{output_layer_weight_key.rsplit('output_layer.', 1)[0]}mtp_output_layer.weight"
+    sharded_state_dict.pop(mtp_key, None)
+    rid = (1, 0, ps.get_data_parallel_rank(with_context_parallel=True))
+    sharded_state_dict[mtp_key] = make_tp_sharded_tensor_for_checkpoint(output_layer_weight, output_layer_weight_key, 0, replica_id=rid)
