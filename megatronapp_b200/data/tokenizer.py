@@ -354,3 +354,127 @@ def build_tokenizer(args):
     if getattr(args, "padded_vocab_size", None) is None:
         args.padded_vocab_size = _vocab_size_with_padding(tok.vocab_size, args)
     return tok
+
+
+# -- class / function names of the reference's ``tokenizer/gpt2_tokenization.py`` and ``bert_tokenization.py`` ------------------------
+def get_pairs(word):
+    """Adjacent symbol pairs of a word (tuple of symbols)."""
+    return {(word[i], word[i + 1]) for i in range(len(word) - 1)}
+
+
+class GPT2Tokenizer(GPT2BPETokenizer):
+    """``GPT2Tokenizer(vocab_file, merges_file)`` with the reference's method names."""
+
+    def __init__(self, vocab_file, merges_file, errors="replace", special_tokens=None, max_len=None):
+        super().__init__(vocab_file, merges_file)
+        self.max_len = max_len if max_len is not None else int(1e12)
+
+    def encode(self, text):
+        return self.tokenize(text)
+
+    def decode(self, tokens):
+        return self.detokenize(tokens)
+
+    def convert_tokens_to_ids(self, tokens):
+        return [self.encoder.get(t, 0) for t in ([tokens] if isinstance(tokens, str) else tokens)]
+
+    def convert_ids_to_tokens(self, ids, skip_special_tokens=False):
+        return [self.decoder[i] for i in ids]
+
+    def __len__(self):
+        return len(self.encoder)
+
+
+def load_vocab(vocab_file):
+    """Ordered ``token -> id`` of a WordPiece vocabulary file."""
+    vocab = {}
+    with open(vocab_file, encoding="utf-8") as f:
+        for i, line in enumerate(f):
+            vocab[line.rstrip("\n")] = i
+    return vocab
+
+
+def convert_to_unicode(text):
+    return text.decode("utf-8", "ignore") if isinstance(text, bytes) else str(text)
+
+
+def printable_text(text):
+    return convert_to_unicode(text)
+
+
+def whitespace_tokenize(text):
+    return text.strip().split()
+
+
+def convert_by_vocab(vocab, items):
+    return [vocab[i] for i in items]
+
+
+def convert_tokens_to_ids(vocab, tokens):
+    return convert_by_vocab(vocab, tokens)
+
+
+def convert_ids_to_tokens(inv_vocab, ids):
+    return convert_by_vocab(inv_vocab, ids)
+
+
+class FullTokenizer:
+    """Basic (punctuation / lower-casing) + WordPiece tokenisation to *tokens* (strings), as the reference's BERT tokenizer."""
+
+    def __init__(self, vocab_file, do_lower_case=True):
+        self._impl = BertWordPieceTokenizer(vocab_file, lower_case=do_lower_case)
+        self.vocab, self.inv_vocab = self._impl.vocab_, self._impl.inv
+
+    def tokenize(self, text):
+        return [self.inv_vocab[i] for i in self._impl.tokenize(text)]
+
+    def convert_tokens_to_ids(self, tokens):
+        return convert_by_vocab(self.vocab, tokens)
+
+    def convert_ids_to_tokens(self, ids):
+        return convert_by_vocab(self.inv_vocab, ids)
+
+    @staticmethod
+    def convert_tokens_to_string(tokens, clean_up_tokenization_spaces=True):
+        return " ".join(tokens).replace(" ##", "").strip()
+
+    def vocab_size(self):
+        return len(self.vocab)
+
+
+class BasicTokenizer:
+    def __init__(self, do_lower_case=True):
+        self.do_lower_case = do_lower_case
+
+    def tokenize(self, text):
+        if self.do_lower_case:
+            text = "".join(c for c in unicodedata.normalize("NFD", text.lower()) if unicodedata.category(c) != "Mn")
+        return re.findall(r"\w+|[^\w\s]", text)
+
+
+class WordpieceTokenizer:
+    def __init__(self, vocab, unk_token="[UNK]", max_input_chars_per_word=200):
+        self.vocab, self.unk_token, self.max_input_chars_per_word = vocab, unk_token, max_input_chars_per_word
+
+    def tokenize(self, text):
+        out = []
+        for w in whitespace_tokenize(text):
+            if len(w) > self.max_input_chars_per_word:
+                out.append(self.unk_token)
+                continue
+            start, sub, bad = 0, [], False
+            while start < len(w):
+                end, cur = len(w), None
+                while start < end:
+                    piece = w[start:end] if start == 0 else "##" + w[start:end]
+                    if piece in self.vocab:
+                        cur = piece
+                        break
+                    end -= 1
+                if cur is None:
+                    bad = True
+                    break
+                sub.append(cur)
+                start = end
+            out.extend([self.unk_token] if bad else sub)
+        return out
