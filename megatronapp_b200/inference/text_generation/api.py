@@ -125,3 +125,75 @@ def beam_search_and_post_process(model, forward_step=None, prompts=None, tokens_
     texts = [tok.detokenize([t for t in r if t != tok.eod]) for r in rows]
     segments = [[tok.detokenize([t]) for t in r] for r in rows] if detokenize_segments else None
     return texts, segments, [float(s) for s in scores]
+
+
+# -- token-level entry points of the reference's ``generation.py`` --------------------------------------------------------------------
+def _rows(tokens: torch.Tensor, lengths: torch.Tensor) -> List[List[int]]:
+    return [tokens[i, : int(lengths[i])].tolist() for i in range(tokens.shape[0])]
+
+
+def generate_tokens_probs_and_return_on_first_stage(model, forward_step=None, tokens=None, lengths=None, return_output_log_probs=False,
+                                                    top_k=0, top_p=0.0, top_p_decay=0.0, top_p_bound=0.0, temperature=1.0,
+                                                    use_eod_token_for_early_termination=True, stop_on_double_eol=False,
+                                                    stop_on_eol=False, prevent_newline_after_colon=True, tokenizer=None,
+                                                    max_sequence_length=None, inference_context=None):
+    """Generation from already tokenised, right-padded prompts (``tokens [b, max_prompt + tokens_to_generate]``, ``lengths [b]`` =
+    prompt lengths): the continuation is written into ``tokens`` in place.  Returns ``(tokens, generated sequence lengths,
+    output_log_probs [b, max_len - 1] | None, None)`` like the reference."""
+    tok = _tokenizer(tokenizer)
+    b, total = tokens.shape
+    n_new = total - int(lengths.min())
+    eng = _engine(model, tok, b, max_sequence_length or total)
+    sp = SamplingParams(temperature=temperature, top_k=top_k, top_p=top_p, return_log_probs=return_output_log_probs,
+                        num_tokens_to_generate=n_new, top_p_decay=top_p_decay, top_p_bound=top_p_bound, stop_on_eol=stop_on_eol,
+                        stop_on_double_eol=stop_on_double_eol, prevent_newline_after_colon=prevent_newline_after_colon,
+                        use_eod_token_for_early_termination=use_eod_token_for_early_termination)
+    ids = [eng.scheduler.add_request(tok.detokenize(r), r, sp) for r in _rows(tokens, lengths)]
+    eng.run_engine()
+    res = [eng.scheduler.completed_request_pool[i] for i in ids]
+    out_lengths = lengths.clone()
+    logp = torch.zeros(b, total - 1, dtype=torch.float32, device=tokens.device) if return_output_log_probs else None
+    for i, r in enumerate(res):
+        n0 = int(lengths[i])
+        gen = [int(t) for t in r.generated_tokens][: total - n0]
+        tokens[i, n0:n0 + len(gen)] = torch.tensor(gen, dtype=tokens.dtype, device=tokens.device)
+        out_lengths[i] = n0 + len(gen)
+        if logp is not None and r.generated_log_probs:
+            lp = list(r.generated_log_probs)[: len(gen)]
+            logp[i, n0 - 1:n0 - 1 + len(lp)] = torch.tensor(lp, device=tokens.device)
+    return tokens, out_lengths, logp, None
+
+
+@torch.no_grad()
+def score_and_return_on_first_stage(model, tokens: torch.Tensor, lengths: torch.Tensor, **_):
+    """Log-probability of every token given its prefix under the model: ``(tokens, lengths, log_probs [b, s - 1], None)``
+    (position ``j`` scores ``tokens[:, j + 1]``).  One full forward pass; vocabulary-parallel logits are gathered."""
+    from ..core import gather_full_vocab
+
+    inner = model
+    while hasattr(inner, "module"):
+        inner = inner.module
+    was_training = inner.training
+    inner.eval()
+    try:
+        pos = torch.arange(tokens.shape[1], device=tokens.device).unsqueeze(0).expand_as(tokens)
+        logits = model(tokens, pos, None)                                   # [b, s, V / tp]
+        logits = gather_full_vocab(logits, getattr(inner, "vocab_size", None))
+        lp = torch.log_softmax(logits.float(), dim=-1)
+        out = torch.gather(lp[:, :-1], 2, tokens[:, 1:].unsqueeze(2)).squeeze(2)
+    finally:
+        inner.train(was_training)
+    return tokens, lengths, out, None
+
+
+def beam_search_and_return_on_first_stage(model, forward_step=None, tokens=None, lengths=None, beam_size: int = 1, stop_token=None,
+                                          num_return_gen: int = 1, length_penalty: float = 1.0, prevent_newline_after_colon: bool = True,
+                                          tokenizer=None, max_sequence_length=None, inference_context=None):
+    """Beam search from one tokenised prompt: ``(tokens [num_return_gen, len], scores [num_return_gen])``."""
+    if tokens.shape[0] != 1:
+        raise ValueError("beam search takes exactly one prompt")
+    tok = _tokenizer(tokenizer)
+    n0 = int(lengths[0])
+    eng = _engine(model, tok, max(beam_size, 1), max_sequence_length or tokens.shape[1])
+    return _beam_search(eng.controller.inference_wrapped_model, tokens[0, :n0].tolist(), beam_size, tokens.shape[1] - n0,
+                        tok.eod if stop_token is None else stop_token, length_penalty, num_return_gen)

@@ -507,3 +507,26 @@ def test_inference_performance_tool(mode):
     line = json.loads([x for x in p.stdout.splitlines() if x.startswith("{")][-1])
     assert line["batch"] == 3 and line["generated_tokens"] == 18 and line["tokens_per_s"] > 0
     assert line["engine"] == ("dynamic" if mode else "static") and (("time_to_first_token_s" in line) == bool(mode))
+
+
+def test_token_level_generation_and_scoring(engine):
+    """generate_tokens_probs_and_return_on_first_stage / score_and_return_on_first_stage (reference generation.py): continuation
+    written in place into padded token rows; teacher-forced log-probabilities equal the generation log-probabilities."""
+    from megatronapp_b200.inference.text_generation.api import (generate_tokens_probs_and_return_on_first_stage,
+                                                                 score_and_return_on_first_stage)
+
+    eng, model = engine
+    tok = NullTokenizer(127)
+    ref = eng.generate(["5 9 23 7", "11 3"], SamplingParams(top_k=1, num_tokens_to_generate=4, return_log_probs=True))
+    tokens = torch.full((2, 8), tok.eod, dtype=torch.long)
+    tokens[0, :4] = torch.tensor([5, 9, 23, 7])
+    tokens[1, :2] = torch.tensor([11, 3])
+    lengths = torch.tensor([4, 2])
+    out, out_len, logp, _ = generate_tokens_probs_and_return_on_first_stage(model, tokens=tokens, lengths=lengths, top_k=1,
+                                                                             return_output_log_probs=True, tokenizer=tok,
+                                                                             prevent_newline_after_colon=False)
+    assert out is tokens and out[0, 4:8].tolist() == ref[0].generated_tokens.tolist()[:4]
+    assert out[1, 2:6].tolist() == ref[1].generated_tokens.tolist()[:4] and out_len.tolist() == [8, 8]      # rows are filled
+    _, _, score, _ = score_and_return_on_first_stage(model, out[:1], torch.tensor([8]))
+    assert score.shape == (1, 7) and torch.allclose(score[0, 3:7], logp[0, 3:7], atol=1e-4)
+    assert torch.allclose(logp[0, 3:7], torch.tensor(ref[0].generated_log_probs[:4]), atol=1e-5)
