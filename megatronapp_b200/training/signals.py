@@ -43,3 +43,36 @@ class DistributedSignalHandler:
         signal.signal(self.sig, self.original)
         self.released = True
         return True
+
+
+# -- helper names of the reference's ``dist_signal_handler.py`` --------------------------------------------------------------------------
+def get_world_size() -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def get_device(local_rank=None):
+    """Device the signal flags are gathered on: the rank's GPU under NCCL, the CPU under gloo."""
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend() if dist.is_available() and dist.is_initialized() else "gloo"
+    if backend == "nccl":
+        return torch.device("cuda", torch.cuda.current_device() if local_rank is None else local_rank)
+    return torch.device("cpu")
+
+
+def all_gather_item(item, dtype, group=None, async_op: bool = False, local_rank=None):
+    """Every rank's scalar ``item`` as a python list (one entry per rank of ``group``)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [item]
+    dev = get_device(local_rank)
+    group = group if group is not None else dist.group.WORLD
+    t = torch.tensor([item], device=dev, dtype=dtype)
+    outs = [torch.zeros(1, dtype=t.dtype, device=dev) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(outs, t, group, async_op)
+    return [o.item() for o in outs]

@@ -963,3 +963,49 @@ def get_start_time_from_progress_log():
     if start_time is None:
         raise RuntimeError(f"no job start found in {path}")
     return start_time, start_flops
+
+
+def get_train_valid_test_num_samples():
+    """Samples the train / validation / test datasets must provide for this run (reference ``training.py``)."""
+    args = get_args()
+    train_samples = args.train_samples if args.train_samples else args.train_iters * args.global_batch_size
+    eval_iters = (args.train_iters // args.eval_interval + 1) * args.eval_iters if args.eval_interval else args.eval_iters
+    return train_samples, eval_iters * args.global_batch_size, args.eval_iters * args.global_batch_size
+
+
+def enable_forward_pre_hook(model_chunks):
+    """Turn the overlapped parameter all-gather back on (after evaluation / checkpointing ran with it off)."""
+    for m in model_chunks:
+        if hasattr(m, "enable_forward_pre_hook"):
+            m.enable_forward_pre_hook()
+
+
+def disable_forward_pre_hook(model_chunks, param_sync: bool = True):
+    """Turn the overlapped parameter all-gather off; with ``param_sync`` the parameters are synchronised once first."""
+    for m in model_chunks:
+        if hasattr(m, "disable_forward_pre_hook"):
+            m.disable_forward_pre_hook(param_sync=param_sync)
+        elif param_sync and hasattr(m, "start_param_sync"):
+            m.start_param_sync(force_sync=True)
+
+
+def dummy_train_step(data_iterator):
+    """Consume one global batch without computing anything (``--iterations-to-skip``)."""
+    from ..utils.microbatches import get_num_microbatches as _n
+
+    for _ in range(_n()):
+        next(data_iterator) if not isinstance(data_iterator, list) else [next(it) for it in data_iterator]
+
+
+def preprocess_common_state_dict(common_state_dict):
+    """What ranks must agree on in the common part of a distributed checkpoint: drop the per-rank entries of ``args``."""
+    import copy
+
+    sd = copy.deepcopy(common_state_dict)
+    a = sd.get("args")
+    if a is not None:
+        d = vars(a) if not isinstance(a, dict) else a
+        for k in ("rank", "local_rank"):
+            d.pop(k, None)
+        sd["args"] = d
+    return sd

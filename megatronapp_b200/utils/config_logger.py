@@ -47,3 +47,27 @@ def log_config_to_disk(config, dict_data, prefix: str = "", rank_str: str = ""):
     with open(fn, "w") as f:
         json.dump(_jsonable(dict_data), f, indent=1)
     return fn
+
+
+# -- helper names of the reference's ``core/config_logger.py`` --------------------------------------------------------------------------
+def get_config_logger_path(config):
+    return getattr(config, "config_logger_dir", "")
+
+
+def get_path_count(path: str) -> int:
+    """How many times ``path`` has been handed out so far (the counter that numbers repeated dumps of one module)."""
+    n = _COUNT.get(path, 0)
+    _COUNT[path] = n + 1
+    return n
+
+
+def get_path_with_count(path: str) -> str:
+    """``<path>.iter<n>`` with ``n`` counting the calls for this path."""
+    return f"{path}.iter{get_path_count(path)}"
+
+
+class JSONEncoderWithMcoreTypes(json.JSONEncoder):
+    """``json.dumps(..., cls=JSONEncoderWithMcoreTypes)``: dtypes, dataclasses, modules, callables and enums become strings / dicts."""
+
+    def default(self, o):
+        return _jsonable(o)
