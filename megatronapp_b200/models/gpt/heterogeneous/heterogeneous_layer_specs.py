@@ -117,3 +117,67 @@ def get_gpt_heterogeneous_layer_spec(config, blocks: List[BlockConfig]) -> Trans
     specs = [ModuleSpec(module=HeterogeneousLayer, params={"block": blocks[i]}, submodules=base.submodules)
              for i in range(off, off + n)]
     return TransformerBlockSubmodules(layer_specs=specs, layer_norm=FusedLayerNorm)
+
+
+# -- configuration classes of the reference's ``transformer/heterogeneous/heterogeneous_config.py`` ------------------------------------
+@dataclass
+class AttentionConfig:
+    """One block's attention: absent (``no_op``), replaced by a linear map, or grouped-query attention with its own group count."""
+    no_op: bool = False
+    replace_with_linear: bool = False
+    num_query_groups: Optional[int] = None
+
+    @classmethod
+    def build_config_from_dict(cls, d: dict, num_attention_heads: int) -> "AttentionConfig":
+        ng = d.get("num_query_groups")
+        if ng is None and d.get("n_heads_in_group"):
+            ng = num_attention_heads // int(d["n_heads_in_group"])
+        return cls(bool(d.get("no_op")), bool(d.get("replace_with_linear")), ng)
+
+
+@dataclass
+class MLPConfig:
+    no_op: bool = False
+    replace_with_linear: bool = False
+    ffn_hidden_size: Optional[int] = None
+
+    @classmethod
+    def build_config_from_dict(cls, d: dict, hidden_size: int) -> "MLPConfig":
+        ffn = d.get("intermediate_size") or d.get("ffn_hidden_size")
+        if ffn is None and d.get("ffn_mult") is not None:
+            ffn = _ffn_mult_to_size(float(d["ffn_mult"]), hidden_size)
+        return cls(bool(d.get("no_op")), bool(d.get("replace_with_linear")), ffn)
+
+
+@dataclass
+class TransformerBlockConfig:
+    attention: AttentionConfig
+    mlp: MLPConfig
+
+    @classmethod
+    def build_from_dict(cls, block: dict, num_attention_heads: int, hidden_size: int) -> "TransformerBlockConfig":
+        return cls(AttentionConfig.build_config_from_dict(block.get("attention", {}) or {}, num_attention_heads),
+                   MLPConfig.build_config_from_dict(block.get("ffn", block.get("mlp", {})) or {}, hidden_size))
+
+    def to_block_config(self) -> BlockConfig:
+        a, m = self.attention, self.mlp
+        return BlockConfig(a.no_op, a.replace_with_linear, a.num_query_groups, m.no_op, m.replace_with_linear, m.ffn_hidden_size)
+
+
+def HeterogeneousTransformerConfig(heterogeneous_layers_config_path=None, heterogeneous_layers_config_encoded_json=None, **kwargs):
+    """A ``TransformerConfig`` with the per-block description attached: ``per_block_parameters`` (list of
+    ``TransformerBlockConfig``) parsed from the JSON file / string, plus the two source attributes the reference's class has."""
+    from ....config.transformer_config import TransformerConfig
+
+    cfg = TransformerConfig(**kwargs)
+    cfg.heterogeneous_layers_config_path = heterogeneous_layers_config_path
+    cfg.heterogeneous_layers_config_encoded_json = heterogeneous_layers_config_encoded_json
+    data = None
+    if heterogeneous_layers_config_encoded_json:
+        data = json.loads(heterogeneous_layers_config_encoded_json)
+    elif heterogeneous_layers_config_path:
+        with open(heterogeneous_layers_config_path) as f:
+            data = json.load(f)
+    cfg.per_block_parameters = [] if data is None else [
+        TransformerBlockConfig.build_from_dict(b, cfg.num_attention_heads, cfg.hidden_size) for b in data["block_configs"]]
+    return cfg

@@ -241,3 +241,72 @@ def get_rerun_state_machine() -> RerunStateMachine:
 def destroy_rerun_state_machine():
     global _RSM
     _RSM = None
+
+
+# -- bookkeeping types of the reference's ``rerun_state_machine.py`` ----------------------------------------------------------------------
+from collections import namedtuple as _namedtuple  # noqa: E402
+from enum import Enum as _Enum  # noqa: E402
+
+Caller = _namedtuple("Caller", ["filename", "lineno", "rank"])       # where a validate_result call sits
+Call = _namedtuple("Call", ["caller", "sequence"])                   # ... and which call of that site within the step
+
+
+class RerunValidationStatus(str, _Enum):
+    """Outcome recorded for a rejected result."""
+    RERUN_DISABLED = "rerun_disabled"
+    INITIAL_RUN = "initial_run"
+    FIRST_RERUN_NOT_REPRODUCIBLE = "first_rerun_not_reproducible"
+    FIRST_RERUN_REPRODUCIBLE = "first_rerun_reproducible"
+    SECOND_RERUN_NOT_REPRODUCIBLE = "second_rerun_not_reproducible"
+    SECOND_RERUN_REPRODUCIBLE = "second_rerun_reproducible"
+
+
+class QuickStats:
+    """Distribution of a statistic (relative differences between an execution and its re-execution in ``report_stats`` mode):
+    up to ``max_size`` non-zero samples (a ring once full), the count of exact zeros, the maximum; ``print_stats`` -> one line."""
+
+    def __init__(self, max_size: int = 100000) -> None:
+        self.samples: List[float] = []
+        self.pos = 0
+        self.zero_cnt = 0
+        self.max = 0.0
+        self.max_size = max_size
+
+    def record(self, data: float) -> None:
+        if data == 0.0:
+            self.zero_cnt += 1
+            return
+        if self.pos < self.max_size:
+            self.samples.append(data)
+        else:
+            self.samples[self.pos % self.max_size] = data
+        self.pos += 1
+        self.max = max(self.max, data)
+
+    def combine(self, others: List["QuickStats"]) -> None:
+        if not others:
+            return
+        n = len(self.samples) + sum(len(o.samples) for o in others)
+        if n <= self.max_size:
+            for o in others:
+                self.samples.extend(o.samples)
+            self.pos = n
+        self.zero_cnt += sum(o.zero_cnt for o in others)
+        self.max = max(self.max, max(o.max for o in others))
+
+    def reset(self) -> None:
+        self.samples, self.pos, self.zero_cnt, self.max = [], 0, 0, 0.0
+
+    def print_stats(self) -> str:
+        z, n = self.zero_cnt, len(self.samples)
+        if n == 0:
+            return f"{z:,} samples, all identical"
+        xs = sorted(self.samples)
+        t = z + n
+
+        def pct(p):
+            i = int(t * p) - z
+            return f"{xs[min(i, n - 1)]:.3E}" if i >= 0 else "0.0"
+
+        return (f"{t:,}/{z:,} total/identical samples, rel. variability: avg= {sum(xs) / t:.3E}, p50= {pct(0.5)}, p90= {pct(0.9)}, "
+                f"p99= {pct(0.99)}, p99.9= {pct(0.999)}, max: {self.max:.3E}")
