@@ -251,5 +251,3 @@ def assert_grouped_gemm_is_available() -> None:
     if not grouped_gemm_is_available():
         raise AssertionError("the grouped tcgen05 GEMM needs the compiled extension (python -c 'import __graft_entry__ as g; g.build()')")
 
-
-ops = None          # reference ``grouped_gemm_util.ops`` handle: the entry points are ``grouped_gemm`` / ``grouped_wgrad`` above
